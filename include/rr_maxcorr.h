@@ -1,0 +1,141 @@
+/* rr_maxcorr.h -- C ABI of the B200-native MaxCorrelation scan.
+ *
+ * Drop-in boundary for the hot path of /root/reference/MaxCorrelation.c.  The reference
+ * has no FFI of its own: the path sits behind (1) the process boundary
+ *     ./MaxCorrelation <MSA> [-c cov] [-p n]  ->  MaxCorrsOf_<MSA>      (main, 916-1026)
+ * which bin/MaxCorrelation (csrc/rr_cli.c) reproduces on top of this header, and (2) the
+ * function boundary inside the program, which the entry points below replace one to one:
+ *
+ *   reference (MaxCorrelation.c)                      this ABI
+ *   ------------------------------------------------  ------------------------------------
+ *   Einlesen(path, von, bis)            270-335       rr_msa_read / rr_msa_from_text
+ *     (fgets rows, keep rule, char codes)
+ *   Einlesen, packing part              339-385       rr_pack            (device side)
+ *     (Groups, LocalCoverage, Groupsizearray, Coverage)
+ *   Parallel_AllMaxCorrsRechner(NTHREADS, 0,          rr_maxcorr_run     (all GPUs, merged)
+ *     siglength, mincov, signumber, cutoff) 839-908   rr_scan            (one GPU, one part)
+ *     -> HilfsMaxCorrsRechner           745-837
+ *     -> PositiveSignificance           421-434       fused epilogue, csrc/rr_score.h
+ *     -> Schnitt                        114-125       count kernels (bitset / tcgen05)
+ *   MaxCorrsRausschreiben(M, name)      516-532       rr_maxcorr_write
+ *
+ * Conventions: plain pointers and sizes only; every function returns RR_OK (0) or a
+ * negative RR_E_* code and never calls exit(); rr_last_error() gives a message for the
+ * calling thread.  Handles are not thread-safe; distinct handles may be used from
+ * distinct threads.  There is no CPU implementation of the scan behind this ABI: without
+ * a CUDA device rr_pack / rr_scan / rr_maxcorr_run fail with RR_E_NODEV.
+ */
+#ifndef RR_MAXCORR_H
+#define RR_MAXCORR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RR_OK 0
+#define RR_E_IO (-1)    /* cannot open/read/write a file ("MA is missing.", MaxCorrelation.c:284) */
+#define RR_E_NOMEM (-2) /* host or device allocation failed (Guarded_Malloc, 41-51) */
+#define RR_E_CUDA (-3)  /* a CUDA call or kernel failed */
+#define RR_E_ARG (-4)   /* invalid argument */
+#define RR_E_NODEV (-5) /* no usable CUDA device (there is no CPU fallback) */
+
+/* which count kernel computes the read-set intersections (Schnitt, 114-125) */
+enum {
+    RR_VARIANT_AUTO = 0,   /* the faster one for this shape */
+    RR_VARIANT_BITSET = 1, /* shared-memory staged u32 bitsets, AND + POPC */
+    RR_VARIANT_UMMA = 2    /* int8 0/1 operands, tcgen05.mma kind::i8, int32 accumulators in TMEM */
+};
+
+/* flags */
+#define RR_FLAG_NO_PRUNE 1u      /* evaluate the exact score of every pair test (no bound-based skipping) */
+#define RR_FLAG_HOST_FINALIZE 2u /* re-evaluate each group's winning pair with the host libm so that the
+                                    "%f" text is byte-identical to the reference's (device exp/log10
+                                    differ from glibc by <= 2 ulp) */
+#define RR_FLAG_GENERAL_BREAK 4u /* force the general first-break computation (MaxCorrelation.c:807-810)
+                                    even when every row is one contiguous span */
+
+typedef struct rr_msa rr_msa;       /* host: the kept rows of an MSA */
+typedef struct rr_packed rr_packed; /* device: one GPU's packed copy of an MSA */
+
+typedef struct rr_scan_opts {
+    int mincov;      /* the -c value (default 30, MaxCorrelation.c:925) */
+    int variant;     /* RR_VARIANT_* */
+    unsigned flags;  /* RR_FLAG_* */
+    int part_index;  /* this scan covers part part_index of part_count pair-balanced */
+    int part_count;  /*   contiguous ranges of row sites (1 -> the whole MSA) */
+} rr_scan_opts;
+
+typedef struct rr_scan_stats {
+    int64_t pair_tests;   /* PositiveSignificance calls the reference would make (820) */
+    int64_t exact_evals;  /* pairs whose exact score was evaluated */
+    int64_t bound_evals;  /* pairs that needed the pmf bound */
+    int64_t work_units;   /* tile pairs processed */
+    int64_t executed_ops; /* int8 MACs*2 (UMMA) or 32-bit AND+POPC word ops (bitset) executed */
+    int variant;          /* variant actually used */
+    int rows, cols;       /* R, N */
+    int row_sites;        /* sites with at least one admissible row group */
+    int general_break;    /* 1 if the general first-break path was used */
+    float h2d_ms, pack_ms, prepare_ms, kernel_ms, fetch_ms, finalize_ms;
+} rr_scan_stats;
+
+/* ---- host: reading the MSA (Einlesen, reading part) -------------------------------- */
+int rr_msa_read(const char *path, rr_msa **out);
+int rr_msa_from_text(const char *text, size_t nbytes, rr_msa **out);
+/* cells[rows][cols]; codes != 0: values 0..5 as in Signatures (304-329); else raw characters */
+int rr_msa_from_cells(const uint8_t *cells, int rows, int cols, int codes, rr_msa **out);
+/* allocate an uninitialised rows x cols cell matrix (page-locked when a device exists) to be
+ * filled in place through rr_msa_cells() */
+int rr_msa_alloc(int rows, int cols, int codes, rr_msa **out);
+int rr_msa_rows(const rr_msa *msa);
+int rr_msa_cols(const rr_msa *msa);
+uint8_t *rr_msa_cells(rr_msa *msa);
+void rr_msa_free(rr_msa *msa);
+
+/* ---- device ------------------------------------------------------------------------ */
+int rr_device_count(void);
+/* copy the cells to `device` and pack them there (bitsets, int8 operands, group sizes,
+ * coverage, read spans) */
+int rr_pack(const rr_msa *msa, int device, rr_packed **out);
+void rr_packed_free(rr_packed *pk);
+/* run the scan on the packed MSA; results stay on the device */
+int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *stats);
+/* copy the last scan's result to the host: maxcorr[5*cols] (line g of MaxCorrsOf_*,
+ * g = 5*site + {A,C,G,T,gap}); argmax[5*cols] = partner group id or -1 (may be NULL) */
+int rr_scan_fetch(rr_packed *pk, double *maxcorr, int32_t *argmax);
+/* the four intersection counts {schnitt, gr1, gr2, cov} (423-426) of n group pairs, from the
+ * device bitsets: out[4*n] */
+int rr_pair_counts(rr_packed *pk, int64_t n, const int32_t *gi, const int32_t *gj, int32_t *out);
+/* Groupsizearray (385) and Coverage (364-383) as computed on the device */
+int rr_packed_sizes(rr_packed *pk, int32_t *gsize /*[5*cols]*/, int32_t *coverage /*[cols]*/);
+
+/* ---- the whole path ------------------------------------------------------------------ */
+/* Parallel_AllMaxCorrsRechner replacement: pack on n_gpus devices, scan one part per GPU,
+ * merge by element-wise max (882-891).  maxcorr_out[5*cols], argmax_out[5*cols] or NULL. */
+int rr_maxcorr_run(const rr_msa *msa, int mincov, int n_gpus, int variant, unsigned flags,
+                   double *maxcorr_out, int32_t *argmax_out, rr_scan_stats *stats);
+/* MaxCorrsRausschreiben: count lines "%f\n" */
+int rr_maxcorr_write(const char *path, const double *maxcorr, int64_t count);
+int rr_argmax_write(const char *path, const int32_t *argmax, int64_t count);
+
+/* ---- host-side pieces exposed for tests and for RR_FLAG_HOST_FINALIZE ------------------ */
+double rr_lnfact(unsigned int n); /* gsl_sf_lnfact */
+void rr_lnfact_table(double *out, size_t count);
+/* PositiveSignificance (421-434) on counts, host libm */
+double rr_score_host(uint32_t schnitt, uint32_t gr1, uint32_t gr2, uint32_t cov, int32_t sizei, int32_t sizej);
+/* the pruning bounds of csrc/rr_score.h, host build */
+double rr_score_bound_host(uint32_t schnitt, uint32_t gr1, uint32_t gr2, uint32_t cov);
+int rr_below_median_host(uint32_t schnitt, uint32_t gr1, uint32_t gr2, uint32_t cov);
+/* first-break columns (807-810) for rows that are single spans: start[r], end[r] inclusive */
+int rr_breakcols_from_spans(const int32_t *start, const int32_t *end, int rows, int cols, int mincov,
+                            int32_t *breakcol /*[cols]*/);
+
+const char *rr_last_error(void);
+const char *rr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RR_MAXCORR_H */

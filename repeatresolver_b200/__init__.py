@@ -1,0 +1,17 @@
+"""repeatresolver_b200 -- B200-native MaxCorrelation scan (drop-in for
+PhilippBongartz/RepeatResolver's MaxCorrelation.c hot path).
+
+The package is a thin host-side mirror of the reference interface over the C ABI in
+include/rr_maxcorr.h (librr_maxcorr.so: hand-written sm_100a CUDA).  Importing it loads
+the shared library and fails if it has not been built.
+"""
+from .maxcorr import (MSA, Packed, RRError, Einlesen, Parallel_AllMaxCorrsRechner, MaxCorrsRausschreiben,
+                      MaxCorrelation, device_count, lnfact_table, score_host, score_bound_host,
+                      below_median_host, breakcols_from_spans, VARIANTS, VARIANT_NAMES,
+                      FLAG_NO_PRUNE, FLAG_HOST_FINALIZE, FLAG_GENERAL_BREAK)
+from .msagen import MsaGen
+
+__all__ = ["MSA", "Packed", "RRError", "Einlesen", "Parallel_AllMaxCorrsRechner", "MaxCorrsRausschreiben",
+           "MaxCorrelation", "device_count", "lnfact_table", "score_host", "score_bound_host",
+           "below_median_host", "breakcols_from_spans", "MsaGen", "VARIANTS", "VARIANT_NAMES",
+           "FLAG_NO_PRUNE", "FLAG_HOST_FINALIZE", "FLAG_GENERAL_BREAK"]

@@ -1,0 +1,101 @@
+"""ctypes loader for the in-tree shared libraries.
+
+librr_maxcorr.so is the C ABI declared in include/rr_maxcorr.h (CUDA, sm_100a).  It is
+loaded eagerly and loading fails loudly: there is no Python or CPU implementation of the
+scan behind this package.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class ScanOpts(C.Structure):
+    _fields_ = [("mincov", C.c_int), ("variant", C.c_int), ("flags", C.c_uint),
+                ("part_index", C.c_int), ("part_count", C.c_int)]
+
+
+class ScanStats(C.Structure):
+    _fields_ = [("pair_tests", C.c_int64), ("exact_evals", C.c_int64), ("bound_evals", C.c_int64),
+                ("work_units", C.c_int64), ("executed_ops", C.c_int64), ("variant", C.c_int),
+                ("rows", C.c_int), ("cols", C.c_int), ("row_sites", C.c_int), ("general_break", C.c_int),
+                ("h2d_ms", C.c_float), ("pack_ms", C.c_float), ("prepare_ms", C.c_float),
+                ("kernel_ms", C.c_float), ("fetch_ms", C.c_float), ("finalize_ms", C.c_float)]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+class MsagenParams(C.Structure):
+    _fields_ = [("type", C.c_int), ("copies", C.c_int), ("coverage", C.c_int), ("repeat_len", C.c_int),
+                ("diff", C.c_double), ("seed", C.c_uint64), ("flank", C.c_int), ("min_overlap", C.c_int),
+                ("max_reads", C.c_int), ("threads", C.c_int)]
+
+
+def _load(name):
+    path = os.path.join(_HERE, name)
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"or `make -C repeatresolver_b200/csrc` (nvcc, sm_100a). There is no fallback path.")
+    return C.CDLL(path, mode=C.RTLD_GLOBAL)
+
+
+lib = _load("librr_maxcorr.so")
+gen = _load("librr_msagen.so")
+
+_vp, _i, _i64, _u32, _d = C.c_void_p, C.c_int, C.c_int64, C.c_uint32, C.c_double
+_P = C.POINTER
+
+
+def _sig(fn, res, args):
+    fn.restype = res
+    fn.argtypes = args
+
+
+# every symbol include/rr_maxcorr.h declares
+ABI_SYMBOLS = [
+    "rr_msa_read", "rr_msa_from_text", "rr_msa_from_cells", "rr_msa_alloc", "rr_msa_rows", "rr_msa_cols",
+    "rr_msa_cells", "rr_msa_free", "rr_device_count", "rr_pack", "rr_packed_free", "rr_scan", "rr_scan_fetch",
+    "rr_pair_counts", "rr_packed_sizes", "rr_maxcorr_run", "rr_maxcorr_write", "rr_argmax_write", "rr_lnfact",
+    "rr_lnfact_table", "rr_score_host", "rr_score_bound_host", "rr_below_median_host", "rr_breakcols_from_spans",
+    "rr_last_error", "rr_version",
+]
+MSAGEN_SYMBOLS = ["rr_msagen_create", "rr_msagen_free", "rr_msagen_rows", "rr_msagen_cols", "rr_msagen_read_copy",
+                  "rr_msagen_fill_codes", "rr_msagen_fill_text", "rr_msagen_write"]
+
+_sig(lib.rr_msa_read, _i, [C.c_char_p, _P(_vp)])
+_sig(lib.rr_msa_from_text, _i, [C.c_char_p, C.c_size_t, _P(_vp)])
+_sig(lib.rr_msa_from_cells, _i, [_vp, _i, _i, _i, _P(_vp)])
+_sig(lib.rr_msa_alloc, _i, [_i, _i, _i, _P(_vp)])
+_sig(lib.rr_msa_rows, _i, [_vp])
+_sig(lib.rr_msa_cols, _i, [_vp])
+_sig(lib.rr_msa_cells, _vp, [_vp])
+_sig(lib.rr_msa_free, None, [_vp])
+_sig(lib.rr_device_count, _i, [])
+_sig(lib.rr_pack, _i, [_vp, _i, _P(_vp)])
+_sig(lib.rr_packed_free, None, [_vp])
+_sig(lib.rr_scan, _i, [_vp, _P(ScanOpts), _P(ScanStats)])
+_sig(lib.rr_scan_fetch, _i, [_vp, _vp, _vp])
+_sig(lib.rr_pair_counts, _i, [_vp, _i64, _vp, _vp, _vp])
+_sig(lib.rr_packed_sizes, _i, [_vp, _vp, _vp])
+_sig(lib.rr_maxcorr_run, _i, [_vp, _i, _i, _i, C.c_uint, _vp, _vp, _P(ScanStats)])
+_sig(lib.rr_maxcorr_write, _i, [C.c_char_p, _vp, _i64])
+_sig(lib.rr_argmax_write, _i, [C.c_char_p, _vp, _i64])
+_sig(lib.rr_lnfact, _d, [C.c_uint])
+_sig(lib.rr_lnfact_table, None, [_vp, C.c_size_t])
+_sig(lib.rr_score_host, _d, [_u32, _u32, _u32, _u32, C.c_int32, C.c_int32])
+_sig(lib.rr_score_bound_host, _d, [_u32, _u32, _u32, _u32])
+_sig(lib.rr_below_median_host, _i, [_u32, _u32, _u32, _u32])
+_sig(lib.rr_breakcols_from_spans, _i, [_vp, _vp, _i, _i, _i, _vp])
+_sig(lib.rr_last_error, C.c_char_p, [])
+_sig(lib.rr_version, C.c_char_p, [])
+
+_sig(gen.rr_msagen_create, _vp, [_P(MsagenParams)])
+_sig(gen.rr_msagen_free, None, [_vp])
+_sig(gen.rr_msagen_rows, _i, [_vp])
+_sig(gen.rr_msagen_cols, _i, [_vp])
+_sig(gen.rr_msagen_read_copy, _P(C.c_int), [_vp])
+_sig(gen.rr_msagen_fill_codes, None, [_vp, _vp])
+_sig(gen.rr_msagen_fill_text, None, [_vp, _vp])
+_sig(gen.rr_msagen_write, _i, [_vp, C.c_char_p])

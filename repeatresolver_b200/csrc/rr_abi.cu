@@ -1,0 +1,498 @@
+// rr_abi.cu -- the C ABI of include/rr_maxcorr.h: device packing, scan orchestration,
+// multi-GPU partition and merge.  Host logic here is O(R log R + N); everything per pair
+// runs in the CUDA kernels.  There is no CPU implementation of the scan in this library.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "rr_kernels.h"
+#include "rr_device.cuh"
+#include "rr_plan.h"
+
+#define RR_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            rr_set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e__), __FILE__, __LINE__, #call); \
+            return RR_E_CUDA;                                                                      \
+        }                                                                                          \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// host buffers
+// ---------------------------------------------------------------------------------------
+extern "C" int rr_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" void *rr_host_alloc(size_t bytes, int *pinned)
+{
+    void *p = nullptr;
+    *pinned = 0;
+    if (rr_device_count() > 0 && cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess) {
+        *pinned = 1;
+        return p;
+    }
+    cudaGetLastError();
+    return malloc(bytes);
+}
+
+extern "C" void rr_host_free(void *p, int pinned)
+{
+    if (!p) return;
+    if (pinned) cudaFreeHost(p);
+    else free(p);
+}
+
+// ---------------------------------------------------------------------------------------
+// host builds of the score functions (tests, RR_FLAG_HOST_FINALIZE)
+// ---------------------------------------------------------------------------------------
+static std::vector<double> &host_lnfact(size_t need)
+{
+    static thread_local std::vector<double> tab;
+    if (tab.size() < need) {
+        size_t old = tab.size();
+        tab.resize(std::max(need, old * 2 + 1024));
+        for (size_t n = old; n < tab.size(); n++) tab[n] = rr_lnfact((unsigned)n);
+    }
+    return tab;
+}
+
+extern "C" double rr_score_host(uint32_t s, uint32_t gr1, uint32_t gr2, uint32_t cov, int32_t sizei, int32_t sizej)
+{
+    std::vector<double> &t = host_lnfact((size_t)cov + 2);
+    return rr_positive_significance(t.data(), s, gr1, gr2, cov, sizei, sizej);
+}
+
+extern "C" double rr_score_bound_host(uint32_t s, uint32_t gr1, uint32_t gr2, uint32_t cov)
+{
+    std::vector<double> &t = host_lnfact((size_t)cov + 2);
+    return rr_score_upper_bound(t.data(), s, gr1, gr2, cov);
+}
+
+extern "C" int rr_below_median_host(uint32_t s, uint32_t gr1, uint32_t gr2, uint32_t cov)
+{
+    return rr_below_median(s, gr1, gr2, cov);
+}
+
+// ---------------------------------------------------------------------------------------
+// packed MSA
+// ---------------------------------------------------------------------------------------
+struct rr_packed {
+    int device = 0, n_sm = 148;
+    int R = 0, N = 0, W32 = 0, codes = 0;
+    cudaStream_t st = nullptr;
+    uint8_t *d_cells = nullptr;
+    int32_t *d_perm = nullptr;
+    uint32_t *d_bits = nullptr, *d_covbits = nullptr;
+    int32_t *d_gsize = nullptr, *d_coverage = nullptr;
+    double *d_lnfact = nullptr;
+    rr_best_t *d_best = nullptr;
+    unsigned long long *d_counters = nullptr;
+    std::vector<int32_t> h_start, h_end;  // spans in rank (span-start) order
+    std::vector<int32_t> h_gsize, h_coverage;
+    bool contiguous = true;
+    float h2d_ms = 0.f, pack_ms = 0.f;
+    bool have_result = false;
+    rr_umma_state *umma = nullptr;  // int8 operands + tensor maps, built on first use
+};
+
+template <typename T>
+static int dev_alloc(T **p, size_t count)
+{
+    *p = nullptr;
+    if (cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T)) != cudaSuccess) {
+        cudaGetLastError();
+        rr_set_error("out of device memory (%zu bytes)", count * sizeof(T));
+        return RR_E_NOMEM;
+    }
+    return RR_OK;
+}
+
+extern "C" void rr_packed_free(rr_packed *pk)
+{
+    if (!pk) return;
+    cudaSetDevice(pk->device);
+    rr_umma_free(pk->umma);
+    cudaFree(pk->d_cells); cudaFree(pk->d_perm); cudaFree(pk->d_bits); cudaFree(pk->d_covbits);
+    cudaFree(pk->d_gsize); cudaFree(pk->d_coverage); cudaFree(pk->d_lnfact); cudaFree(pk->d_best);
+    cudaFree(pk->d_counters);
+    if (pk->st) cudaStreamDestroy(pk->st);
+    delete pk;
+}
+
+static int pack_impl(const uint8_t *cells, int R, int N, int codes, int device, rr_packed *pk)
+{
+    int ndev = rr_device_count();
+    if (ndev <= 0) { rr_set_error("no CUDA device: the scan has no CPU fallback"); return RR_E_NODEV; }
+    if (device < 0 || device >= ndev) { rr_set_error("device %d out of range (%d devices)", device, ndev); return RR_E_ARG; }
+    RR_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RR_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { rr_set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return RR_E_NODEV; }
+    pk->device = device; pk->n_sm = prop.multiProcessorCount;
+    pk->R = R; pk->N = N; pk->codes = codes;
+    pk->W32 = ((R + 127) / 128) * 4;
+    if (pk->W32 == 0) pk->W32 = 4;
+    RR_CUDA(cudaStreamCreateWithFlags(&pk->st, cudaStreamNonBlocking));
+    cudaEvent_t e0, e1, e2;
+    RR_CUDA(cudaEventCreate(&e0)); RR_CUDA(cudaEventCreate(&e1)); RR_CUDA(cudaEventCreate(&e2));
+
+    const size_t ncell = (size_t)R * N;
+    int rc;
+    if ((rc = dev_alloc(&pk->d_cells, ncell))) return rc;
+    RR_CUDA(cudaEventRecord(e0, pk->st));
+    if (ncell) RR_CUDA(cudaMemcpyAsync(pk->d_cells, cells, ncell, cudaMemcpyHostToDevice, pk->st));
+    RR_CUDA(cudaEventRecord(e1, pk->st));
+
+    // spans -> row order (by span start, then end; uncovered rows last)
+    int32_t *d_span = nullptr;
+    if ((rc = dev_alloc(&d_span, (size_t)3 * std::max(R, 1)))) return rc;
+    RR_CUDA(rr_launch_row_spans(pk->d_cells, R, N, codes, d_span, d_span + R, d_span + 2 * (size_t)R, pk->st));
+    std::vector<int32_t> span((size_t)3 * std::max(R, 1));
+    RR_CUDA(cudaMemcpyAsync(span.data(), d_span, sizeof(int32_t) * 3 * (size_t)R, cudaMemcpyDeviceToHost, pk->st));
+    RR_CUDA(cudaStreamSynchronize(pk->st));
+    cudaFree(d_span);
+    std::vector<int32_t> perm(R);
+    std::iota(perm.begin(), perm.end(), 0);
+    const int32_t *sst = span.data(), *sen = span.data() + R, *scn = span.data() + 2 * (size_t)R;
+    std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) {
+        if (sst[a] != sst[b]) return sst[a] < sst[b];
+        return sen[a] < sen[b];
+    });
+    pk->h_start.resize(R); pk->h_end.resize(R);
+    pk->contiguous = true;
+    for (int k = 0; k < R; k++) {
+        const int r = perm[k];
+        pk->h_start[k] = sst[r]; pk->h_end[k] = sen[r];
+        if (scn[r] > 0 && scn[r] != sen[r] - sst[r] + 1) pk->contiguous = false;
+    }
+    if ((rc = dev_alloc(&pk->d_perm, (size_t)R))) return rc;
+    if (R) RR_CUDA(cudaMemcpyAsync(pk->d_perm, perm.data(), sizeof(int32_t) * R, cudaMemcpyHostToDevice, pk->st));
+
+    // bitsets, sizes
+    const size_t G = (size_t)5 * N;
+    if ((rc = dev_alloc(&pk->d_bits, G * pk->W32))) return rc;
+    if ((rc = dev_alloc(&pk->d_covbits, (size_t)N * pk->W32))) return rc;
+    if ((rc = dev_alloc(&pk->d_gsize, G))) return rc;
+    if ((rc = dev_alloc(&pk->d_coverage, (size_t)N))) return rc;
+    RR_CUDA(rr_launch_pack_bits(pk->d_cells, pk->d_perm, R, N, codes, pk->d_bits, pk->d_covbits, pk->W32, pk->st));
+    RR_CUDA(rr_launch_bitset_sizes(pk->d_bits, (int64_t)G, pk->W32, pk->d_gsize, pk->st));
+    RR_CUDA(rr_launch_bitset_sizes(pk->d_covbits, (int64_t)N, pk->W32, pk->d_coverage, pk->st));
+    pk->h_gsize.resize(G); pk->h_coverage.resize(N);
+    if (G) RR_CUDA(cudaMemcpyAsync(pk->h_gsize.data(), pk->d_gsize, sizeof(int32_t) * G, cudaMemcpyDeviceToHost, pk->st));
+    if (N) RR_CUDA(cudaMemcpyAsync(pk->h_coverage.data(), pk->d_coverage, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, pk->st));
+
+    // ln(n!) table, n = 0..R+1
+    std::vector<double> lnf((size_t)R + 2);
+    rr_lnfact_table(lnf.data(), lnf.size());
+    if ((rc = dev_alloc(&pk->d_lnfact, lnf.size()))) return rc;
+    RR_CUDA(cudaMemcpyAsync(pk->d_lnfact, lnf.data(), sizeof(double) * lnf.size(), cudaMemcpyHostToDevice, pk->st));
+
+    if ((rc = dev_alloc(&pk->d_best, G))) return rc;
+    if ((rc = dev_alloc(&pk->d_counters, (size_t)8))) return rc;
+    RR_CUDA(cudaEventRecord(e2, pk->st));
+    RR_CUDA(cudaStreamSynchronize(pk->st));
+    RR_CUDA(cudaEventElapsedTime(&pk->h2d_ms, e0, e1));
+    RR_CUDA(cudaEventElapsedTime(&pk->pack_ms, e1, e2));
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    return RR_OK;
+}
+
+extern "C" int rr_pack(const rr_msa *msa, int device, rr_packed **out)
+{
+    if (!msa || !out) { rr_set_error("rr_pack: bad arguments"); return RR_E_ARG; }
+    rr_packed *pk = new rr_packed();
+    int rc = pack_impl(msa->cells, msa->rows, msa->cols, msa->codes, device, pk);
+    if (rc) { rr_packed_free(pk); *out = nullptr; return rc; }
+    *out = pk;
+    return RR_OK;
+}
+
+extern "C" int rr_packed_sizes(rr_packed *pk, int32_t *gsize, int32_t *coverage)
+{
+    if (!pk) return RR_E_ARG;
+    if (gsize) memcpy(gsize, pk->h_gsize.data(), sizeof(int32_t) * pk->h_gsize.size());
+    if (coverage) memcpy(coverage, pk->h_coverage.data(), sizeof(int32_t) * pk->h_coverage.size());
+    return RR_OK;
+}
+
+extern "C" int rr_pair_counts(rr_packed *pk, int64_t n, const int32_t *gi, const int32_t *gj, int32_t *out)
+{
+    if (!pk || n < 0 || (n && (!gi || !gj || !out))) return RR_E_ARG;
+    if (n == 0) return RR_OK;
+    RR_CUDA(cudaSetDevice(pk->device));
+    int32_t *d_i = nullptr, *d_j = nullptr, *d_o = nullptr;
+    int rc;
+    if ((rc = dev_alloc(&d_i, (size_t)n)) || (rc = dev_alloc(&d_j, (size_t)n)) || (rc = dev_alloc(&d_o, (size_t)4 * n))) {
+        cudaFree(d_i); cudaFree(d_j); cudaFree(d_o);
+        return rc;
+    }
+    RR_CUDA(cudaMemcpyAsync(d_i, gi, sizeof(int32_t) * n, cudaMemcpyHostToDevice, pk->st));
+    RR_CUDA(cudaMemcpyAsync(d_j, gj, sizeof(int32_t) * n, cudaMemcpyHostToDevice, pk->st));
+    RR_CUDA(rr_launch_pair_counts(pk->d_bits, pk->d_covbits, pk->W32, n, d_i, d_j, d_o, pk->st));
+    RR_CUDA(cudaMemcpyAsync(out, d_o, sizeof(int32_t) * 4 * n, cudaMemcpyDeviceToHost, pk->st));
+    RR_CUDA(cudaStreamSynchronize(pk->st));
+    cudaFree(d_i); cudaFree(d_j); cudaFree(d_o);
+    return RR_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// scan
+// ---------------------------------------------------------------------------------------
+template <typename T>
+static int upload(T **d, const std::vector<T> &h, cudaStream_t st)
+{
+    int rc = dev_alloc(d, h.size());
+    if (rc) return rc;
+    if (!h.empty()) RR_CUDA(cudaMemcpyAsync(*d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, st));
+    return RR_OK;
+}
+
+struct scan_buffers {
+    uint8_t *rowok = nullptr, *colok = nullptr;
+    int32_t *breakcol = nullptr, *rowsites = nullptr, *unit_cb0 = nullptr, *word_hi = nullptr, *word_lo = nullptr;
+    int64_t *unit_prefix = nullptr;
+    ~scan_buffers()
+    {
+        cudaFree(rowok); cudaFree(colok); cudaFree(breakcol); cudaFree(rowsites); cudaFree(unit_cb0);
+        cudaFree(word_hi); cudaFree(word_lo); cudaFree(unit_prefix);
+    }
+};
+
+extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *stats)
+{
+    if (!pk || !opts) { rr_set_error("rr_scan: bad arguments"); return RR_E_ARG; }
+    if (opts->part_count < 1 || opts->part_index < 0 || opts->part_index >= opts->part_count) {
+        rr_set_error("rr_scan: part %d of %d", opts->part_index, opts->part_count);
+        return RR_E_ARG;
+    }
+    RR_CUDA(cudaSetDevice(pk->device));
+    const int R = pk->R, N = pk->N, mincov = opts->mincov;
+    cudaEvent_t e0, e1, e2;
+    RR_CUDA(cudaEventCreate(&e0)); RR_CUDA(cudaEventCreate(&e1)); RR_CUDA(cudaEventCreate(&e2));
+    RR_CUDA(cudaEventRecord(e0, pk->st));
+
+    int variant = opts->variant;
+    if (variant == RR_VARIANT_AUTO) variant = rr_umma_available() ? RR_VARIANT_UMMA : RR_VARIANT_BITSET;
+    if (variant != RR_VARIANT_BITSET && variant != RR_VARIANT_UMMA) { rr_set_error("unknown variant %d", variant); return RR_E_ARG; }
+
+    // ---- host plan: filters, first-break columns, tiles, partition (O(N)) ------------------
+    rr_plan plan;
+    std::vector<int32_t> breakcol(N);
+    const bool general = !pk->contiguous || (opts->flags & RR_FLAG_GENERAL_BREAK);
+    scan_buffers sb;
+    int rc;
+    if (general) {
+        if ((rc = dev_alloc(&sb.breakcol, (size_t)N))) return rc;
+        RR_CUDA(rr_launch_general_break(pk->d_covbits, pk->W32, N, mincov, sb.breakcol, pk->st));
+        if (N) RR_CUDA(cudaMemcpyAsync(breakcol.data(), sb.breakcol, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, pk->st));
+        RR_CUDA(cudaStreamSynchronize(pk->st));
+    } else {
+        rc = rr_breakcols_from_spans(pk->h_start.data(), pk->h_end.data(), R, N, mincov, breakcol.data());
+        if (rc) return rc;
+    }
+    const int ti = variant == RR_VARIANT_BITSET ? rr_bitset_ti() : rr_umma_row_sites();
+    const int tj = variant == RR_VARIANT_BITSET ? rr_bitset_tj() : rr_umma_col_sites();
+    rr_plan_build(plan, R, N, mincov, pk->h_gsize.data(), pk->h_coverage.data(), breakcol.data(),
+                  pk->contiguous && !general ? pk->h_start.data() : nullptr,
+                  pk->contiguous && !general ? pk->h_end.data() : nullptr, ti, tj, variant == RR_VARIANT_BITSET ? 32 : rr_umma_kblock(),
+                  opts->part_index, opts->part_count);
+
+    if ((rc = upload(&sb.rowok, plan.rowok, pk->st))) return rc;
+    if ((rc = upload(&sb.colok, plan.colok, pk->st))) return rc;
+    if (!general && (rc = upload(&sb.breakcol, breakcol, pk->st))) return rc;
+    if ((rc = upload(&sb.rowsites, plan.rowsites, pk->st))) return rc;
+    if ((rc = upload(&sb.unit_prefix, plan.unit_prefix, pk->st))) return rc;
+    if ((rc = upload(&sb.unit_cb0, plan.unit_cb0, pk->st))) return rc;
+    if ((rc = upload(&sb.word_hi, plan.k_hi, pk->st))) return rc;
+    if ((rc = upload(&sb.word_lo, plan.k_lo, pk->st))) return rc;
+
+    // running maxima: 0.0 / no partner
+    {
+        std::vector<rr_best_t> init((size_t)5 * N);
+        for (auto &b : init) { b.z = 0ull; b.p = ~0ull; }
+        if (!init.empty()) RR_CUDA(cudaMemcpyAsync(pk->d_best, init.data(), sizeof(rr_best_t) * init.size(), cudaMemcpyHostToDevice, pk->st));
+        RR_CUDA(cudaMemsetAsync(pk->d_counters, 0, sizeof(unsigned long long) * 8, pk->st));
+        RR_CUDA(cudaStreamSynchronize(pk->st));  // init[] goes out of scope
+    }
+
+    rr_scan_params P;
+    memset(&P, 0, sizeof P);
+    P.R = R; P.N = N; P.W32 = pk->W32; P.mincov = mincov; P.flags = opts->flags;
+    P.bits = pk->d_bits; P.gsize = pk->d_gsize; P.rowok = sb.rowok; P.colok = sb.colok;
+    P.breakcol = sb.breakcol; P.rowsites = sb.rowsites; P.n_rowsites = plan.n_rowsites;
+    P.lnfact = pk->d_lnfact; P.best = pk->d_best; P.counters = pk->d_counters;
+    P.unit_prefix = sb.unit_prefix; P.unit_cb0 = sb.unit_cb0; P.n_rowblocks = plan.n_rowblocks;
+    P.rb_lo = plan.rb_lo; P.rb_hi = plan.rb_hi; P.word_hi = sb.word_hi; P.word_lo = sb.word_lo;
+
+    RR_CUDA(cudaEventRecord(e1, pk->st));
+    int64_t executed = 0;
+    if (plan.rb_hi > plan.rb_lo && plan.unit_prefix[plan.rb_hi] > plan.unit_prefix[plan.rb_lo]) {
+        if (variant == RR_VARIANT_BITSET) {
+            RR_CUDA(rr_launch_scan_bitset(P, pk->n_sm, pk->st));
+        } else {
+            rc = rr_umma_scan(pk->umma, P, plan, pk->d_cells, pk->d_perm, pk->codes, pk->n_sm, pk->st);
+            if (rc) return rc;
+        }
+    }
+    RR_CUDA(cudaEventRecord(e2, pk->st));
+    unsigned long long counters[8];
+    RR_CUDA(cudaMemcpyAsync(counters, pk->d_counters, sizeof counters, cudaMemcpyDeviceToHost, pk->st));
+    RR_CUDA(cudaStreamSynchronize(pk->st));
+    RR_CUDA(cudaGetLastError());
+    pk->have_result = true;
+    executed = plan.executed_ops;
+
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->pair_tests = (int64_t)counters[0];
+        stats->exact_evals = (int64_t)counters[1];
+        stats->bound_evals = (int64_t)counters[2];
+        stats->work_units = (int64_t)counters[3];
+        stats->executed_ops = executed;
+        stats->variant = variant;
+        stats->rows = R; stats->cols = N; stats->row_sites = plan.n_rowsites;
+        stats->general_break = general ? 1 : 0;
+        stats->h2d_ms = pk->h2d_ms; stats->pack_ms = pk->pack_ms;
+        cudaEventElapsedTime(&stats->prepare_ms, e0, e1);
+        cudaEventElapsedTime(&stats->kernel_ms, e1, e2);
+    }
+    if ((int64_t)counters[0] != plan.part_pairs) {
+        rr_set_error("pair-test count mismatch: device %llu, host plan %lld", counters[0], (long long)plan.part_pairs);
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+        return RR_E_CUDA;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    return RR_OK;
+}
+
+extern "C" int rr_scan_fetch(rr_packed *pk, double *maxcorr, int32_t *argmax)
+{
+    if (!pk || !maxcorr) return RR_E_ARG;
+    if (!pk->have_result) { rr_set_error("rr_scan_fetch before rr_scan"); return RR_E_ARG; }
+    RR_CUDA(cudaSetDevice(pk->device));
+    const size_t G = (size_t)5 * pk->N;
+    std::vector<rr_best_t> best(G);
+    if (G) RR_CUDA(cudaMemcpyAsync(best.data(), pk->d_best, sizeof(rr_best_t) * G, cudaMemcpyDeviceToHost, pk->st));
+    RR_CUDA(cudaStreamSynchronize(pk->st));
+    for (size_t g = 0; g < G; g++) {
+        double z;
+        memcpy(&z, &best[g].z, sizeof z);
+        maxcorr[g] = z;
+        if (argmax) argmax[g] = best[g].p == ~0ull ? -1 : (int32_t)best[g].p;
+    }
+    return RR_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// the whole path: pack on n GPUs, scan one part each, merge (882-891)
+// ---------------------------------------------------------------------------------------
+extern "C" int rr_maxcorr_run(const rr_msa *msa, int mincov, int n_gpus, int variant, unsigned flags,
+                              double *maxcorr_out, int32_t *argmax_out, rr_scan_stats *stats)
+{
+    if (!msa || !maxcorr_out || n_gpus < 1) { rr_set_error("rr_maxcorr_run: bad arguments"); return RR_E_ARG; }
+    const int ndev = rr_device_count();
+    if (ndev <= 0) { rr_set_error("no CUDA device: the scan has no CPU fallback"); return RR_E_NODEV; }
+    if (n_gpus > ndev) { rr_set_error("%d GPUs requested, %d present", n_gpus, ndev); return RR_E_ARG; }
+    const size_t G = (size_t)5 * msa->cols;
+    std::vector<std::vector<double>> M(n_gpus, std::vector<double>(G));
+    std::vector<std::vector<int32_t>> A(n_gpus, std::vector<int32_t>(G));
+    std::vector<rr_scan_stats> S(n_gpus);
+    std::vector<int> RC(n_gpus, RR_OK);
+    std::vector<std::string> ERR(n_gpus);
+    std::vector<rr_packed *> PK(n_gpus, nullptr);
+
+    auto worker = [&](int d) {
+        rr_scan_opts o;
+        o.mincov = mincov; o.variant = variant; o.flags = flags; o.part_index = d; o.part_count = n_gpus;
+        int rc = rr_pack(msa, d, &PK[d]);
+        if (!rc) rc = rr_scan(PK[d], &o, &S[d]);
+        if (!rc) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            cudaEventRecord(a, PK[d]->st);
+            rc = rr_scan_fetch(PK[d], M[d].data(), A[d].data());
+            cudaEventRecord(b, PK[d]->st);
+            cudaEventSynchronize(b);
+            cudaEventElapsedTime(&S[d].fetch_ms, a, b);
+            cudaEventDestroy(a); cudaEventDestroy(b);
+        }
+        RC[d] = rc;
+        if (rc) ERR[d] = rr_last_error();
+    };
+    if (n_gpus == 1) worker(0);
+    else {
+        std::vector<std::thread> th;
+        for (int d = 0; d < n_gpus; d++) th.emplace_back(worker, d);
+        for (auto &t : th) t.join();
+    }
+    int rc = RR_OK;
+    for (int d = 0; d < n_gpus; d++)
+        if (RC[d]) { rc = RC[d]; rr_set_error("GPU %d: %s", d, ERR[d].c_str()); break; }
+
+    if (!rc) {
+        for (size_t g = 0; g < G; g++) {
+            double z = M[0][g];
+            int32_t p = A[0][g];
+            for (int d = 1; d < n_gpus; d++) {
+                if (M[d][g] > z) { z = M[d][g]; p = A[d][g]; }
+                else if (M[d][g] == z && z > 0.0 && A[d][g] >= 0 && (p < 0 || A[d][g] < p)) p = A[d][g];
+            }
+            maxcorr_out[g] = z;
+            if (argmax_out) argmax_out[g] = p;
+            A[0][g] = p;
+        }
+        if (stats) {
+            *stats = S[0];
+            for (int d = 1; d < n_gpus; d++) {
+                stats->pair_tests += S[d].pair_tests; stats->exact_evals += S[d].exact_evals;
+                stats->bound_evals += S[d].bound_evals; stats->work_units += S[d].work_units;
+                stats->executed_ops += S[d].executed_ops;
+                stats->kernel_ms = std::max(stats->kernel_ms, S[d].kernel_ms);
+                stats->h2d_ms = std::max(stats->h2d_ms, S[d].h2d_ms);
+                stats->pack_ms = std::max(stats->pack_ms, S[d].pack_ms);
+                stats->prepare_ms = std::max(stats->prepare_ms, S[d].prepare_ms);
+                stats->fetch_ms = std::max(stats->fetch_ms, S[d].fetch_ms);
+            }
+        }
+        if (flags & RR_FLAG_HOST_FINALIZE) {
+            // the winners' counts come from the device bitsets; only exp/log10 of the 5N winning
+            // pairs are redone with the host libm
+            std::vector<int32_t> gi, gj;
+            std::vector<size_t> idx;
+            for (size_t g = 0; g < G; g++)
+                if (A[0][g] >= 0) {
+                    const int32_t a = (int32_t)g, b = A[0][g];
+                    gi.push_back(std::min(a, b)); gj.push_back(std::max(a, b)); idx.push_back(g);
+                }
+            std::vector<int32_t> cnt(4 * gi.size());
+            cudaEvent_t a, b;
+            cudaSetDevice(PK[0]->device);
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            cudaEventRecord(a, PK[0]->st);
+            rc = rr_pair_counts(PK[0], (int64_t)gi.size(), gi.data(), gj.data(), cnt.data());
+            if (!rc) {
+                const std::vector<int32_t> &gs = PK[0]->h_gsize;
+                for (size_t k = 0; k < idx.size(); k++)
+                    maxcorr_out[idx[k]] = rr_score_host((uint32_t)cnt[4 * k], (uint32_t)cnt[4 * k + 1], (uint32_t)cnt[4 * k + 2],
+                                                        (uint32_t)cnt[4 * k + 3], gs[gi[k]], gs[gj[k]]);
+            }
+            cudaEventRecord(b, PK[0]->st);
+            cudaEventSynchronize(b);
+            if (stats) cudaEventElapsedTime(&stats->finalize_ms, a, b);
+            cudaEventDestroy(a); cudaEventDestroy(b);
+        }
+    }
+    for (int d = 0; d < n_gpus; d++) rr_packed_free(PK[d]);
+    return rc;
+}

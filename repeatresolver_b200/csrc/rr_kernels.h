@@ -1,0 +1,24 @@
+// rr_kernels.h -- launchers of the CUDA kernels (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "rr_host.h"
+
+struct rr_scan_params;
+struct rr_umma_plan;
+
+cudaError_t rr_launch_row_spans(const uint8_t *cells, int R, int N, int codes, int32_t *start, int32_t *end,
+                                int32_t *ncov, cudaStream_t st);
+cudaError_t rr_launch_pack_bits(const uint8_t *cells, const int32_t *perm, int R, int N, int codes, uint32_t *bits,
+                                uint32_t *covbits, int W32, cudaStream_t st);
+cudaError_t rr_launch_bitset_sizes(const uint32_t *sets, int64_t nsets, int W32, int32_t *sizes, cudaStream_t st);
+cudaError_t rr_launch_pair_counts(const uint32_t *bits, const uint32_t *covbits, int W32, int64_t n,
+                                  const int32_t *gi, const int32_t *gj, int32_t *out, cudaStream_t st);
+cudaError_t rr_launch_general_break(const uint32_t *covbits, int W32, int N, int mincov, int32_t *breakcol,
+                                    cudaStream_t st);
+cudaError_t rr_launch_pack_int8(const uint8_t *cells, const int32_t *perm, int R, int N, int codes, int8_t *xb,
+                                int64_t Kp, cudaStream_t st);
+
+cudaError_t rr_launch_scan_bitset(const rr_scan_params &P, int n_sm, cudaStream_t st);
+int rr_bitset_ti(void);
+int rr_bitset_tj(void);

@@ -1,0 +1,41 @@
+// rr_plan.h -- host-side scan plan (internal): admissibility flags, row-site compaction,
+// tile ranges, exact contraction ranges and the pair-balanced multi-GPU partition.
+// All of it is O(N + R) integer work derived from the filters of
+// /root/reference/MaxCorrelation.c:796-817.
+#pragma once
+#include <stdint.h>
+#include <vector>
+#include "rr_host.h"
+
+struct rr_plan {
+    std::vector<uint8_t> rowok, colok;  // [5N]  (802) / (817)
+    std::vector<int32_t> rowsites;      // sites with >= 1 admissible row group, ascending, padded with -1
+    int n_rowsites = 0, n_rowblocks = 0, n_colblocks = 0;
+    std::vector<int64_t> unit_prefix;   // [n_rowblocks+1] prefix sum of column blocks per row block
+    std::vector<int32_t> unit_cb0;      // [n_rowblocks] first column block
+    std::vector<int32_t> k_hi;          // [n_rowblocks] exclusive upper bound of contributing k-units
+    std::vector<int32_t> k_lo;          // [n_colblocks] inclusive lower bound
+    std::vector<int64_t> rb_pairs;      // [n_rowblocks] pair tests per row block
+    int rb_lo = 0, rb_hi = 0;           // this part's row blocks
+    int64_t total_pairs = 0, part_pairs = 0;
+    int64_t part_kunits = 0;            // sum over this part's units of contributing k-units
+    int64_t executed_ops = 0;           // filled by the variant
+};
+
+// ti / tj: row / column sites per tile; kunit: rows (reads) per contraction unit
+// (32 = one u32 word for the bitset kernel, the K block for the tcgen05 kernel).
+// start/end: spans in rank order, or NULL when rows are not single spans (no skipping).
+void rr_plan_build(rr_plan &plan, int R, int N, int mincov, const int32_t *gsize, const int32_t *coverage,
+                   const int32_t *breakcol, const int32_t *start, const int32_t *end, int ti, int tj, int kunit,
+                   int part_index, int part_count);
+
+// ---- tcgen05 variant hooks (rr_scan_umma.cu) ---------------------------------------------
+struct rr_umma_state;
+struct rr_scan_params;
+int rr_umma_available(void);
+int rr_umma_row_sites(void);
+int rr_umma_col_sites(void);
+int rr_umma_kblock(void);
+void rr_umma_free(rr_umma_state *s);
+int rr_umma_scan(rr_umma_state *&s, rr_scan_params &P, rr_plan &plan, const uint8_t *d_cells, const int32_t *d_perm,
+                 int codes, int n_sm, cudaStream_t st);

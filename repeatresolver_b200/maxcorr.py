@@ -1,0 +1,206 @@
+"""Host-side mirror of the reference's MaxCorrelation interface, on top of the C ABI.
+
+Names follow /root/reference/MaxCorrelation.c: reading an MSA is `Einlesen` (270-393), the
+scan is `Parallel_AllMaxCorrsRechner` (839-908), writing is `MaxCorrsRausschreiben`
+(516-532), and `MaxCorrelation(path, c, p)` is the program's `main` (916-1026).  Every call
+goes through librr_maxcorr.so; nothing here computes.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import ScanOpts, ScanStats, lib
+
+VARIANTS = {"auto": 0, "bitset": 1, "umma": 2}
+VARIANT_NAMES = {v: k for k, v in VARIANTS.items()}
+FLAG_NO_PRUNE = 1
+FLAG_HOST_FINALIZE = 2
+FLAG_GENERAL_BREAK = 4
+
+
+class RRError(RuntimeError):
+    def __init__(self, code, where):
+        self.code = code
+        super().__init__(f"{where} failed with {code}: {lib.rr_last_error().decode(errors='replace')}")
+
+
+def _check(rc, where):
+    if rc != 0:
+        raise RRError(rc, where)
+
+
+def device_count():
+    return lib.rr_device_count()
+
+
+class MSA:
+    """The kept rows of an MSA (the reading half of Einlesen)."""
+
+    def __init__(self, handle):
+        self._h = C.c_void_p(handle)
+
+    @classmethod
+    def read(cls, path):
+        h = C.c_void_p()
+        _check(lib.rr_msa_read(os.fsencode(path), C.byref(h)), "rr_msa_read")
+        return cls(h.value)
+
+    @classmethod
+    def from_text(cls, text):
+        if isinstance(text, str):
+            text = text.encode("latin1")
+        h = C.c_void_p()
+        _check(lib.rr_msa_from_text(text, len(text), C.byref(h)), "rr_msa_from_text")
+        return cls(h.value)
+
+    @classmethod
+    def from_cells(cls, cells, codes=True):
+        cells = np.ascontiguousarray(cells, dtype=np.uint8)
+        assert cells.ndim == 2
+        h = C.c_void_p()
+        _check(lib.rr_msa_from_cells(cells.ctypes.data, cells.shape[0], cells.shape[1], int(codes), C.byref(h)),
+               "rr_msa_from_cells")
+        return cls(h.value)
+
+    @classmethod
+    def alloc(cls, rows, cols, codes=True):
+        h = C.c_void_p()
+        _check(lib.rr_msa_alloc(rows, cols, int(codes), C.byref(h)), "rr_msa_alloc")
+        return cls(h.value)
+
+    @property
+    def rows(self):
+        return lib.rr_msa_rows(self._h)
+
+    @property
+    def cols(self):
+        return lib.rr_msa_cols(self._h)
+
+    def cells(self):
+        """numpy view of the [rows][cols] cell matrix (host memory owned by the handle)."""
+        n = self.rows * self.cols
+        if n == 0:
+            return np.zeros((self.rows, self.cols), dtype=np.uint8)
+        buf = (C.c_uint8 * n).from_address(lib.rr_msa_cells(self._h))
+        return np.frombuffer(buf, dtype=np.uint8).reshape(self.rows, self.cols)
+
+    def close(self):
+        if self._h:
+            lib.rr_msa_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Packed:
+    """One GPU's packed copy of an MSA (the packing half of Einlesen, on the device)."""
+
+    def __init__(self, msa, device=0):
+        h = C.c_void_p()
+        _check(lib.rr_pack(msa._h, device, C.byref(h)), "rr_pack")
+        self._h = h
+        self.rows, self.cols = msa.rows, msa.cols
+
+    def scan(self, mincov=30, variant="auto", flags=0, part_index=0, part_count=1):
+        opts = ScanOpts(mincov, VARIANTS[variant] if isinstance(variant, str) else variant, flags, part_index, part_count)
+        st = ScanStats()
+        _check(lib.rr_scan(self._h, C.byref(opts), C.byref(st)), "rr_scan")
+        return st.as_dict()
+
+    def fetch(self):
+        G = 5 * self.cols
+        M = np.zeros(G, dtype=np.float64)
+        A = np.zeros(G, dtype=np.int32)
+        _check(lib.rr_scan_fetch(self._h, M.ctypes.data, A.ctypes.data), "rr_scan_fetch")
+        return M, A
+
+    def pair_counts(self, gi, gj):
+        gi = np.ascontiguousarray(gi, dtype=np.int32)
+        gj = np.ascontiguousarray(gj, dtype=np.int32)
+        out = np.zeros((len(gi), 4), dtype=np.int32)
+        _check(lib.rr_pair_counts(self._h, len(gi), gi.ctypes.data, gj.ctypes.data, out.ctypes.data), "rr_pair_counts")
+        return out
+
+    def sizes(self):
+        gs = np.zeros(5 * self.cols, dtype=np.int32)
+        cv = np.zeros(self.cols, dtype=np.int32)
+        _check(lib.rr_packed_sizes(self._h, gs.ctypes.data, cv.ctypes.data), "rr_packed_sizes")
+        return gs, cv
+
+    def close(self):
+        if self._h:
+            lib.rr_packed_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def Einlesen(path):
+    """MaxCorrelation.c:270-335."""
+    return MSA.read(path)
+
+
+def Parallel_AllMaxCorrsRechner(msa, mincov=30, n_gpus=1, variant="auto", flags=FLAG_HOST_FINALIZE):
+    """MaxCorrelation.c:839-908 on n_gpus B200s.  Returns (MaxCorrs[5N], argmax[5N], stats)."""
+    G = 5 * msa.cols
+    M = np.zeros(G, dtype=np.float64)
+    A = np.zeros(G, dtype=np.int32)
+    st = ScanStats()
+    _check(lib.rr_maxcorr_run(msa._h, mincov, n_gpus, VARIANTS[variant] if isinstance(variant, str) else variant,
+                              flags, M.ctypes.data, A.ctypes.data, C.byref(st)), "rr_maxcorr_run")
+    return M, A, st.as_dict()
+
+
+def MaxCorrsRausschreiben(MaxCorrs, outputfile):
+    """MaxCorrelation.c:516-532."""
+    M = np.ascontiguousarray(MaxCorrs, dtype=np.float64)
+    _check(lib.rr_maxcorr_write(os.fsencode(outputfile), M.ctypes.data, len(M)), "rr_maxcorr_write")
+
+
+def MaxCorrelation(msa_path, c=30, p=1, variant="auto", flags=FLAG_HOST_FINALIZE, outdir=None):
+    """The program: read <msa_path>, scan on p GPUs with coverage floor c, write
+    MaxCorrsOf_<msa_path> (MaxCorrelation.c:991-993, 1014).  Returns (path written, stats)."""
+    msa = Einlesen(msa_path)
+    M, A, st = Parallel_AllMaxCorrsRechner(msa, c, max(1, p), variant, flags)
+    name = "MaxCorrsOf_" + os.path.basename(msa_path) if outdir is not None else "MaxCorrsOf_" + msa_path
+    out = os.path.join(outdir, name) if outdir is not None else name
+    MaxCorrsRausschreiben(M, out)
+    msa.close()
+    return out, st
+
+
+def lnfact_table(n):
+    t = np.zeros(n, dtype=np.float64)
+    lib.rr_lnfact_table(t.ctypes.data, n)
+    return t
+
+
+def score_host(s, gr1, gr2, cov, sizei, sizej):
+    return lib.rr_score_host(s, gr1, gr2, cov, sizei, sizej)
+
+
+def score_bound_host(s, gr1, gr2, cov):
+    return lib.rr_score_bound_host(s, gr1, gr2, cov)
+
+
+def below_median_host(s, gr1, gr2, cov):
+    return bool(lib.rr_below_median_host(s, gr1, gr2, cov))
+
+
+def breakcols_from_spans(start, end, cols, mincov):
+    start = np.ascontiguousarray(start, dtype=np.int32)
+    end = np.ascontiguousarray(end, dtype=np.int32)
+    out = np.zeros(cols, dtype=np.int32)
+    _check(lib.rr_breakcols_from_spans(start.ctypes.data, end.ctypes.data, len(start), cols, mincov, out.ctypes.data),
+           "rr_breakcols_from_spans")
+    return out

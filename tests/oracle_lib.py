@@ -1,0 +1,116 @@
+"""ctypes binding of oracle/liboracle.so -- the CPU restatement used as the checker.
+Test infrastructure: imported only from tests/, __graft_entry__.smoke() and bench.py."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(ROOT, "oracle", "liboracle.so")
+        if not os.path.exists(path):
+            import subprocess
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"])
+        L = C.CDLL(path)
+        L.rr_oracle_load.restype = C.c_void_p
+        L.rr_oracle_load.argtypes = [C.c_char_p]
+        L.rr_oracle_from_codes.restype = C.c_void_p
+        L.rr_oracle_from_codes.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.rr_oracle_free.argtypes = [C.c_void_p]
+        L.rr_oracle_R.argtypes = [C.c_void_p]
+        L.rr_oracle_N.argtypes = [C.c_void_p]
+        L.rr_oracle_gsize.restype = C.POINTER(C.c_int)
+        L.rr_oracle_gsize.argtypes = [C.c_void_p]
+        L.rr_oracle_coverage.restype = C.POINTER(C.c_int)
+        L.rr_oracle_coverage.argtypes = [C.c_void_p]
+        L.rr_oracle_counts.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.rr_oracle_score.restype = C.c_double
+        L.rr_oracle_score.argtypes = [C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_int]
+        L.rr_oracle_scan.restype = C.c_int64
+        L.rr_oracle_scan.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.rr_oracle_write.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
+        L.rr_oracle_lnfact.restype = C.c_double
+        L.rr_oracle_lnfact.argtypes = [C.c_uint]
+        L.gsl_cdf_hypergeometric_Q.restype = C.c_double
+        L.gsl_cdf_hypergeometric_Q.argtypes = [C.c_uint] * 4
+        _lib = L
+    return _lib
+
+
+class Oracle:
+    def __init__(self, handle):
+        if not handle:
+            raise OSError("MA is missing.")
+        self._h = C.c_void_p(handle)
+        self.R = lib().rr_oracle_R(self._h)
+        self.N = lib().rr_oracle_N(self._h)
+
+    @classmethod
+    def load(cls, path):
+        return cls(lib().rr_oracle_load(os.fsencode(path)))
+
+    @classmethod
+    def from_text(cls, text, tmp_path):
+        p = os.path.join(str(tmp_path), "oracle_in.msa")
+        with open(p, "wb") as f:
+            f.write(text)
+        return cls.load(p)
+
+    @classmethod
+    def from_codes(cls, codes):
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        return cls(lib().rr_oracle_from_codes(codes.ctypes.data, codes.shape[0], codes.shape[1]))
+
+    def gsize(self):
+        return np.ctypeslib.as_array(lib().rr_oracle_gsize(self._h), shape=(5 * self.N,)).copy()
+
+    def coverage(self):
+        return np.ctypeslib.as_array(lib().rr_oracle_coverage(self._h), shape=(self.N,)).copy()
+
+    def counts(self, i, j):
+        out = (C.c_int * 4)()
+        lib().rr_oracle_counts(self._h, int(i), int(j), out)
+        return list(out)
+
+    def scan(self, mincov=30, modulus=None, res_lo=0, res_hi=None, threads=8):
+        """full scan when modulus is None (threads pthreads), else rows ii % modulus in [res_lo,res_hi)"""
+        if modulus is None:
+            modulus, res_lo, res_hi = threads, 0, threads
+        G = 5 * self.N
+        M = np.zeros(G + 1, dtype=np.float64)
+        A = np.zeros(G + 1, dtype=np.int32)
+        P = lib().rr_oracle_scan(self._h, mincov, modulus, res_lo, res_hi, M.ctypes.data, A.ctypes.data)
+        return M[:G], A[:G], int(P)
+
+    def close(self):
+        if self._h:
+            lib().rr_oracle_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def score(s, gr1, gr2, cov, sizei=0, sizej=0):
+    return lib().rr_oracle_score(s, gr1, gr2, cov, sizei, sizej)
+
+
+def hyper_Q(k, n1, n2, t):
+    return lib().gsl_cdf_hypergeometric_Q(k, n1, n2, t)
+
+
+def lnfact(n):
+    return lib().rr_oracle_lnfact(n)
+
+
+def fmt_lines(M):
+    """the reference's "%f\\n" text (MaxCorrsRausschreiben, 527-530)"""
+    return "".join("%f\n" % v for v in M).encode()

@@ -1,0 +1,191 @@
+"""CPU-only tests of the product's host side: the C ABI loads and exports every declared
+symbol, the parser keeps the reference's row rules, ln(n!) / score / bounds (host build of
+csrc/rr_score.h) agree with the oracle, first-break sweep, CLI argument handling.  No scan
+is run here: without a GPU the ABI must refuse (there is no CPU path)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import repeatresolver_b200 as rr
+from repeatresolver_b200 import _lib
+from conftest import GOLDEN_CASES, ROOT, golden_msa
+import oracle_lib as O
+
+
+def test_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "rr_maxcorr.h")).read()
+    declared = set(re.findall(r"\b(rr_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"rr_last_error"} - set(_lib.ABI_SYMBOLS)
+    assert declared == set(_lib.ABI_SYMBOLS), declared ^ set(_lib.ABI_SYMBOLS)
+    for s in _lib.ABI_SYMBOLS:
+        assert hasattr(_lib.lib, s), s
+    hdr = open(os.path.join(ROOT, "include", "rr_msagen.h")).read()
+    declared = set(re.findall(r"\b(rr_msagen_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.MSAGEN_SYMBOLS)
+    for s in _lib.MSAGEN_SYMBOLS:
+        assert hasattr(_lib.gen, s), s
+    assert b"sm_100a" in _lib.lib.rr_version()
+
+
+def test_no_cpu_fallback_without_device():
+    if rr.device_count() > 0:
+        pytest.skip("a GPU is present")
+    m = rr.MSA.from_text(b"ACGT\nACGT\n")
+    with pytest.raises(rr.RRError) as e:
+        rr.Packed(m)
+    assert e.value.code == -5
+    with pytest.raises(rr.RRError) as e:
+        rr.Parallel_AllMaxCorrsRechner(m, 30, 1)
+    assert e.value.code == -5
+
+
+@pytest.mark.parametrize("name", sorted({n for n, _ in GOLDEN_CASES}))
+def test_parser_row_rules_match_oracle(name, tmp_path):
+    text = golden_msa(name)
+    m = rr.MSA.from_text(text)
+    o = O.Oracle.from_text(text, tmp_path)
+    assert (m.rows, m.cols) == (o.R, o.N)
+    p = tmp_path / "f.msa"
+    p.write_bytes(text)
+    m2 = rr.MSA.read(str(p))
+    assert (m2.cells() == m.cells()).all()
+
+
+def test_parser_edge_cases(tmp_path):
+    # first line fixes the width; other widths are skipped; last line without '\n' is dropped
+    m = rr.MSA.from_text(b"ACGT\nAC\nACGTA\nA-GT\n\nTTTT")
+    assert (m.rows, m.cols) == (2, 4)
+    assert bytes(m.cells()[1]) == b"A-GT"
+    # ... unless it is one longer, in which case its last character is cut (strlen-1 rule)
+    m = rr.MSA.from_text(b"ACGT\nTTTTX")
+    assert (m.rows, m.cols) == (2, 4) and bytes(m.cells()[1]) == b"TTTT"
+    # a NUL ends the line (strlen semantics)
+    m = rr.MSA.from_text(b"ACGT\nAC\x00T\nGGGG\n")
+    assert m.rows == 2
+    # single line without newline: width is strlen-1
+    m = rr.MSA.from_text(b"ACGTA")
+    assert (m.rows, m.cols) == (1, 4)
+    # empty input
+    m = rr.MSA.from_text(b"")
+    assert (m.rows, m.cols) == (0, 0)
+    with pytest.raises(rr.RRError) as e:
+        rr.MSA.read(str(tmp_path / "does_not_exist"))
+    assert e.value.code == -1 and "MA is missing." in str(e.value)
+
+
+def test_lnfact_table_bitwise_equal_to_oracle():
+    t = rr.lnfact_table(20000)
+    for n in list(range(0, 400)) + [1000, 4096, 13700, 19999]:
+        assert t[n] == O.lnfact(n), n
+
+
+def test_score_host_bitwise_equal_to_oracle():
+    rng = np.random.default_rng(3)
+    n = 0
+    while n < 3000:
+        cov = int(rng.integers(2, 5000))
+        gr1 = int(rng.integers(1, cov + 1))
+        gr2 = int(rng.integers(1, cov + 1))
+        lo, hi = max(0, gr1 + gr2 - cov), min(gr1, gr2)
+        s = int(rng.integers(lo, hi + 1))
+        si, sj = gr1 + int(rng.integers(0, 50)), gr2 + int(rng.integers(0, 50))
+        a, b = rr.score_host(s, gr1, gr2, cov, si, sj), O.score(s, gr1, gr2, cov, si, sj)
+        assert a == b or (a != a and b != b), (s, gr1, gr2, cov, a, b)
+        n += 1
+    # saturated branch and the s = minimum-of-support corner (lower tail with pdf == 0)
+    assert rr.score_host(300, 300, 320, 640, 300, 320) == O.score(300, 300, 320, 640, 300, 320) > 98
+    assert rr.score_host(900, 2000, 1800, 13700, 2000, 1800) == 98.0 + 1800.0 / 3800.0
+    assert rr.score_host(5, 10, 15, 20, 10, 15) == O.score(5, 10, 15, 20, 10, 15)
+
+
+def test_pruning_bounds_are_upper_bounds():
+    """the two bounds of rr_score.h never fall below the exact score (before caps)"""
+    rng = np.random.default_rng(4)
+    checked = med = 0
+    for _ in range(20000):
+        cov = int(rng.integers(2, 3000))
+        gr1 = int(rng.integers(1, cov + 1))
+        gr2 = int(rng.integers(1, cov + 1))
+        lo, hi = max(1, gr1 + gr2 - cov), min(gr1, gr2)
+        if lo > hi:
+            continue
+        mean = gr1 * gr2 / cov
+        s = int(np.clip(int(mean + rng.normal() * 3 * max(1.0, mean ** 0.5)), lo, hi))
+        z = O.score(s, gr1, gr2, cov, 10 ** 6, 10 ** 6)
+        if z >= 98:
+            continue
+        u = rr.score_bound_host(s, gr1, gr2, cov)
+        assert u >= z, (s, gr1, gr2, cov, z, u)
+        checked += 1
+        if rr.below_median_host(s, gr1, gr2, cov):
+            assert z <= 0.30103001, (s, gr1, gr2, cov, z)
+            med += 1
+    assert checked > 5000 and med > 500
+
+
+def test_median_bound_exhaustive_small_populations():
+    for cov in range(2, 41):
+        for gr1 in range(1, cov + 1):
+            for gr2 in range(1, cov + 1):
+                for s in range(max(1, gr1 + gr2 - cov), min(gr1, gr2) + 1):
+                    z = O.score(s, gr1, gr2, cov, 10 ** 6, 10 ** 6)
+                    if rr.below_median_host(s, gr1, gr2, cov):
+                        assert z <= 0.30103001
+                    assert rr.score_bound_host(s, gr1, gr2, cov) >= z
+
+
+def _brute_breakcols(start, end, cols, mincov):
+    out = np.zeros(cols, dtype=np.int32)
+    for ii in range(cols):
+        jj = ii + 20
+        while jj < cols:
+            cov = int(((start <= ii) & (end >= jj) & (end >= ii)).sum())
+            if cov < mincov:
+                break
+            jj += 1
+        out[ii] = max(jj, ii + 20)
+    return out
+
+
+@pytest.mark.parametrize("mincov", [0, 1, 3, 8])
+def test_breakcols_from_spans(mincov):
+    rng = np.random.default_rng(9 + mincov)
+    cols, rows = 150, 40
+    start = rng.integers(0, cols, rows).astype(np.int32)
+    end = np.minimum(cols - 1, start + rng.integers(0, 120, rows)).astype(np.int32)
+    start[5], end[5] = 2 ** 31 - 1, -1  # an uncovered row
+    got = rr.breakcols_from_spans(start, end, cols, mincov)
+    want = _brute_breakcols(start, end, cols, mincov)
+    assert (np.minimum(got, np.maximum(cols, np.arange(cols) + 20)) == np.minimum(want, np.maximum(cols, np.arange(cols) + 20))).all()
+
+
+def test_cli_without_gpu_reports_and_fails(tmp_path):
+    exe = os.path.join(ROOT, "repeatresolver_b200", "bin", "MaxCorrelation")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "Usage: ./MaxCorrelation MSApath <options>" in r.stdout
+    r = subprocess.run([exe, "nope"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1 and "MA is missing." in r.stdout
+    if rr.device_count() == 0:
+        (tmp_path / "M").write_bytes(golden_msa("kat_appendix_g"))
+        r = subprocess.run([exe, "M", "-c", "30"], capture_output=True, text=True, cwd=tmp_path)
+        assert r.returncode == 1 and "no CUDA device" in r.stderr
+        assert not (tmp_path / "MaxCorrsOf_M").exists()
+
+
+def test_msagen_deterministic_and_shaped():
+    a = rr.MsaGen(copies=3, coverage=10, repeat_len=400, seed=5, flank=200, min_overlap=50, threads=1)
+    b = rr.MsaGen(copies=3, coverage=10, repeat_len=400, seed=5, flank=200, min_overlap=50, threads=7)
+    assert (a.rows, a.cols) == (b.rows, b.cols) and (a.codes() == b.codes()).all()
+    codes = a.codes()
+    assert codes.max() <= 5 and a.cols >= 400
+    # every row is one contiguous span, with no leading / trailing gap
+    for r in range(a.rows):
+        cov = np.nonzero(codes[r] < 5)[0]
+        assert len(cov) and cov[-1] - cov[0] + 1 == len(cov)
+        assert codes[r, cov[0]] != 4 and codes[r, cov[-1]] != 4
+    t = a.text().split(b"\n")
+    assert len(t) == a.rows + 1 and set(b"".join(t)) <= set(b"ACGT- ")
