@@ -378,7 +378,7 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
 
 extern "C" int rr_scan_fetch(rr_packed *pk, double *maxcorr, int32_t *argmax)
 {
-    if (!pk || !maxcorr) return RR_E_ARG;
+    if (!pk || (!maxcorr && pk->N > 0)) { rr_set_error("rr_scan_fetch: bad arguments"); return RR_E_ARG; }
     if (!pk->have_result) { rr_set_error("rr_scan_fetch before rr_scan"); return RR_E_ARG; }
     RR_CUDA(cudaSetDevice(pk->device));
     const size_t G = (size_t)5 * pk->N;
@@ -400,7 +400,7 @@ extern "C" int rr_scan_fetch(rr_packed *pk, double *maxcorr, int32_t *argmax)
 extern "C" int rr_maxcorr_run(const rr_msa *msa, int mincov, int n_gpus, int variant, unsigned flags,
                               double *maxcorr_out, int32_t *argmax_out, rr_scan_stats *stats)
 {
-    if (!msa || !maxcorr_out || n_gpus < 1) { rr_set_error("rr_maxcorr_run: bad arguments"); return RR_E_ARG; }
+    if (!msa || (!maxcorr_out && msa->cols > 0) || n_gpus < 1) { rr_set_error("rr_maxcorr_run: bad arguments"); return RR_E_ARG; }
     const int ndev = rr_device_count();
     if (ndev <= 0) { rr_set_error("no CUDA device: the scan has no CPU fallback"); return RR_E_NODEV; }
     if (n_gpus > ndev) { rr_set_error("%d GPUs requested, %d present", n_gpus, ndev); return RR_E_ARG; }

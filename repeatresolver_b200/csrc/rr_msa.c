@@ -190,7 +190,9 @@ int rr_breakcols_from_spans(const int32_t *start, const int32_t *end, int rows, 
 {
     int32_t *sp, *heap;
     int r, ii, next = 0, hn = 0, nsp = 0;
-    if (!breakcol || rows < 0 || cols < 0) return RR_E_ARG;
+    if (rows < 0 || cols < 0) { rr_set_error("rr_breakcols_from_spans: bad arguments"); return RR_E_ARG; }
+    if (cols == 0) return RR_OK;
+    if (!breakcol || (rows && (!start || !end))) { rr_set_error("rr_breakcols_from_spans: null pointer"); return RR_E_ARG; }
     if (mincov <= 0) { /* shared coverage < mincov never holds */
         for (ii = 0; ii < cols; ii++) breakcol[ii] = cols > ii + 20 ? cols : ii + 20;
         return RR_OK;
