@@ -96,6 +96,8 @@ void rr_msa_free(rr_msa *msa);
 
 /* ---- device ------------------------------------------------------------------------ */
 int rr_device_count(void);
+/* 1 if the count-kernel variant is compiled into this library */
+int rr_variant_available(int variant);
 /* copy the cells to `device` and pack them there (bitsets, int8 operands, group sizes,
  * coverage, read spans) */
 int rr_pack(const rr_msa *msa, int device, rr_packed **out);
@@ -131,6 +133,13 @@ int rr_below_median_host(uint32_t schnitt, uint32_t gr1, uint32_t gr2, uint32_t 
 /* first-break columns (807-810) for rows that are single spans: start[r], end[r] inclusive */
 int rr_breakcols_from_spans(const int32_t *start, const int32_t *end, int rows, int cols, int mincov,
                             int32_t *breakcol /*[cols]*/);
+
+/* ---- measurement helpers ------------------------------------------------------------------ */
+/* CUDA events on the stream every kernel of this handle is launched on */
+int rr_timer_start(rr_packed *pk);
+int rr_timer_stop(rr_packed *pk, float *elapsed_ms);
+/* number of kernels this library has launched in this process so far */
+int64_t rr_launch_count(void);
 
 const char *rr_last_error(void);
 const char *rr_version(void);

@@ -56,10 +56,10 @@ def _sig(fn, res, args):
 # every symbol include/rr_maxcorr.h declares
 ABI_SYMBOLS = [
     "rr_msa_read", "rr_msa_from_text", "rr_msa_from_cells", "rr_msa_alloc", "rr_msa_rows", "rr_msa_cols",
-    "rr_msa_cells", "rr_msa_free", "rr_device_count", "rr_pack", "rr_packed_free", "rr_scan", "rr_scan_fetch",
+    "rr_msa_cells", "rr_msa_free", "rr_device_count", "rr_variant_available", "rr_pack", "rr_packed_free", "rr_scan", "rr_scan_fetch",
     "rr_pair_counts", "rr_packed_sizes", "rr_maxcorr_run", "rr_maxcorr_write", "rr_argmax_write", "rr_lnfact",
     "rr_lnfact_table", "rr_score_host", "rr_score_bound_host", "rr_below_median_host", "rr_breakcols_from_spans",
-    "rr_last_error", "rr_version",
+    "rr_timer_start", "rr_timer_stop", "rr_launch_count", "rr_last_error", "rr_version",
 ]
 MSAGEN_SYMBOLS = ["rr_msagen_create", "rr_msagen_free", "rr_msagen_rows", "rr_msagen_cols", "rr_msagen_read_copy",
                   "rr_msagen_fill_codes", "rr_msagen_fill_text", "rr_msagen_write"]
@@ -73,6 +73,7 @@ _sig(lib.rr_msa_cols, _i, [_vp])
 _sig(lib.rr_msa_cells, _vp, [_vp])
 _sig(lib.rr_msa_free, None, [_vp])
 _sig(lib.rr_device_count, _i, [])
+_sig(lib.rr_variant_available, _i, [_i])
 _sig(lib.rr_pack, _i, [_vp, _i, _P(_vp)])
 _sig(lib.rr_packed_free, None, [_vp])
 _sig(lib.rr_scan, _i, [_vp, _P(ScanOpts), _P(ScanStats)])
@@ -88,6 +89,9 @@ _sig(lib.rr_score_host, _d, [_u32, _u32, _u32, _u32, C.c_int32, C.c_int32])
 _sig(lib.rr_score_bound_host, _d, [_u32, _u32, _u32, _u32])
 _sig(lib.rr_below_median_host, _i, [_u32, _u32, _u32, _u32])
 _sig(lib.rr_breakcols_from_spans, _i, [_vp, _vp, _i, _i, _i, _vp])
+_sig(lib.rr_timer_start, _i, [_vp])
+_sig(lib.rr_timer_stop, _i, [_vp, _P(C.c_float)])
+_sig(lib.rr_launch_count, _i64, [])
 _sig(lib.rr_last_error, C.c_char_p, [])
 _sig(lib.rr_version, C.c_char_p, [])
 

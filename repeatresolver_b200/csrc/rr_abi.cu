@@ -2,6 +2,7 @@
 // multi-GPU partition and merge.  Host logic here is O(R log R + N); everything per pair
 // runs in the CUDA kernels.  There is no CPU implementation of the scan in this library.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -34,6 +35,13 @@ extern "C" int rr_device_count(void)
     return n;
 }
 
+extern "C" int rr_variant_available(int variant)
+{
+    if (variant == RR_VARIANT_BITSET || variant == RR_VARIANT_AUTO) return 1;
+    if (variant == RR_VARIANT_UMMA) return rr_umma_available();
+    return 0;
+}
+
 extern "C" void *rr_host_alloc(size_t bytes, int *pinned)
 {
     void *p = nullptr;
@@ -52,6 +60,13 @@ extern "C" void rr_host_free(void *p, int pinned)
     if (pinned) cudaFreeHost(p);
     else free(p);
 }
+
+// ---------------------------------------------------------------------------------------
+// measurement helpers
+// ---------------------------------------------------------------------------------------
+static std::atomic<long long> g_launches{0};
+extern "C" void rr_count_launch(int n) { g_launches += n; }
+extern "C" int64_t rr_launch_count(void) { return (int64_t)g_launches.load(); }
 
 // ---------------------------------------------------------------------------------------
 // host builds of the score functions (tests, RR_FLAG_HOST_FINALIZE)
@@ -104,6 +119,7 @@ struct rr_packed {
     float h2d_ms = 0.f, pack_ms = 0.f;
     bool have_result = false;
     rr_umma_state *umma = nullptr;  // int8 operands + tensor maps, built on first use
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
 };
 
 template <typename T>
@@ -126,6 +142,7 @@ extern "C" void rr_packed_free(rr_packed *pk)
     cudaFree(pk->d_cells); cudaFree(pk->d_perm); cudaFree(pk->d_bits); cudaFree(pk->d_covbits);
     cudaFree(pk->d_gsize); cudaFree(pk->d_coverage); cudaFree(pk->d_lnfact); cudaFree(pk->d_best);
     cudaFree(pk->d_counters);
+    if (pk->t0) { cudaEventDestroy(pk->t0); cudaEventDestroy(pk->t1); }
     if (pk->st) cudaStreamDestroy(pk->st);
     delete pk;
 }
@@ -215,6 +232,25 @@ extern "C" int rr_pack(const rr_msa *msa, int device, rr_packed **out)
     int rc = pack_impl(msa->cells, msa->rows, msa->cols, msa->codes, device, pk);
     if (rc) { rr_packed_free(pk); *out = nullptr; return rc; }
     *out = pk;
+    return RR_OK;
+}
+
+extern "C" int rr_timer_start(rr_packed *pk)
+{
+    if (!pk) return RR_E_ARG;
+    RR_CUDA(cudaSetDevice(pk->device));
+    if (!pk->t0) { RR_CUDA(cudaEventCreate(&pk->t0)); RR_CUDA(cudaEventCreate(&pk->t1)); }
+    RR_CUDA(cudaEventRecord(pk->t0, pk->st));
+    return RR_OK;
+}
+
+extern "C" int rr_timer_stop(rr_packed *pk, float *elapsed_ms)
+{
+    if (!pk || !pk->t0 || !elapsed_ms) return RR_E_ARG;
+    RR_CUDA(cudaSetDevice(pk->device));
+    RR_CUDA(cudaEventRecord(pk->t1, pk->st));
+    RR_CUDA(cudaEventSynchronize(pk->t1));
+    RR_CUDA(cudaEventElapsedTime(elapsed_ms, pk->t0, pk->t1));
     return RR_OK;
 }
 

@@ -5,6 +5,7 @@
 #include "rr_host.h"
 
 struct rr_scan_params;
+extern "C" void rr_count_launch(int n);
 struct rr_umma_plan;
 
 cudaError_t rr_launch_row_spans(const uint8_t *cells, int R, int N, int codes, int32_t *start, int32_t *end,

@@ -217,6 +217,7 @@ cudaError_t rr_launch_row_spans(const uint8_t *cells, int R, int N, int codes, i
                                 int32_t *ncov, cudaStream_t st)
 {
     if (R > 0) rr_k_row_spans<<<R, 256, 0, st>>>(cells, R, N, codes, start, end, ncov);
+    rr_count_launch(1);
     return cudaGetLastError();
 }
 
@@ -226,6 +227,7 @@ cudaError_t rr_launch_pack_bits(const uint8_t *cells, const int32_t *perm, int R
     if (N <= 0 || W32 <= 0) return cudaSuccess;
     dim3 grid((N + PK_COLS - 1) / PK_COLS, W32 / 4);
     rr_k_pack_bits<<<grid, PK_COLS, 0, st>>>(cells, perm, R, N, codes, bits, covbits, W32);
+    rr_count_launch(1);
     return cudaGetLastError();
 }
 
@@ -233,6 +235,7 @@ cudaError_t rr_launch_bitset_sizes(const uint32_t *sets, int64_t nsets, int W32,
 {
     if (nsets <= 0) return cudaSuccess;
     rr_k_bitset_sizes<<<(unsigned)((nsets + 7) / 8), 256, 0, st>>>(sets, nsets, W32, sizes);
+    rr_count_launch(1);
     return cudaGetLastError();
 }
 
@@ -241,6 +244,7 @@ cudaError_t rr_launch_pair_counts(const uint32_t *bits, const uint32_t *covbits,
 {
     if (n <= 0) return cudaSuccess;
     rr_k_pair_counts<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(bits, covbits, W32, n, gi, gj, out);
+    rr_count_launch(1);
     return cudaGetLastError();
 }
 
@@ -249,6 +253,7 @@ cudaError_t rr_launch_general_break(const uint32_t *covbits, int W32, int N, int
 {
     if (N <= 0) return cudaSuccess;
     rr_k_general_break<<<(N + 7) / 8, 256, 0, st>>>(covbits, W32, N, mincov, breakcol);
+    rr_count_launch(1);
     return cudaGetLastError();
 }
 
@@ -258,5 +263,6 @@ cudaError_t rr_launch_pack_int8(const uint8_t *cells, const int32_t *perm, int R
     if (N <= 0 || Kp <= 0) return cudaSuccess;
     dim3 grid((N + PX_COLS - 1) / PX_COLS, (unsigned)(Kp / PX_ROWS));
     rr_k_pack_int8<<<grid, 256, 0, st>>>(cells, perm, R, N, codes, xb, Kp);
+    rr_count_launch(1);
     return cudaGetLastError();
 }

@@ -146,6 +146,7 @@ cudaError_t rr_launch_scan_bitset(const rr_scan_params &P, int n_sm, cudaStream_
     (void)units;
     int grid = n_sm * 2 * 4;  // persistent: 2 resident CTAs per SM, 4 rounds of slack for balance
     rr_k_scan_bitset<<<grid, BS_TI * 32, 0, st>>>(P);
+    rr_count_launch(1);
     return cudaGetLastError();
 }
 

@@ -31,6 +31,10 @@ def _check(rc, where):
         raise RRError(rc, where)
 
 
+def variant_available(variant):
+    return bool(lib.rr_variant_available(VARIANTS[variant] if isinstance(variant, str) else variant))
+
+
 def device_count():
     return lib.rr_device_count()
 
@@ -127,6 +131,14 @@ class Packed:
         _check(lib.rr_pair_counts(self._h, len(gi), gi.ctypes.data, gj.ctypes.data, out.ctypes.data), "rr_pair_counts")
         return out
 
+    def timer_start(self):
+        _check(lib.rr_timer_start(self._h), "rr_timer_start")
+
+    def timer_stop(self):
+        ms = C.c_float()
+        _check(lib.rr_timer_stop(self._h, C.byref(ms)), "rr_timer_stop")
+        return ms.value
+
     def sizes(self):
         gs = np.zeros(5 * self.cols, dtype=np.int32)
         cv = np.zeros(self.cols, dtype=np.int32)
@@ -177,6 +189,10 @@ def MaxCorrelation(msa_path, c=30, p=1, variant="auto", flags=FLAG_HOST_FINALIZE
     MaxCorrsRausschreiben(M, out)
     msa.close()
     return out, st
+
+
+def launch_count():
+    return int(lib.rr_launch_count())
 
 
 def lnfact_table(n):

@@ -18,16 +18,7 @@ REL_TOL = 1e-9  # BASELINE.json: "significance values match within a relative 1e
 
 
 def variants():
-    import ctypes as C
-    v = ["bitset"]
-    try:
-        fn = rr._lib.lib.rr_umma_available
-        fn.restype = C.c_int
-        if fn():
-            v.append("umma")
-    except AttributeError:
-        pass
-    return v
+    return ["bitset"] + (["umma"] if rr.variant_available("umma") else [])
 
 
 VARIANTS = variants()
