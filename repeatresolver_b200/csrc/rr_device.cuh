@@ -109,3 +109,149 @@ __device__ __forceinline__ double rr_pair_score(const rr_scan_params &P, unsigne
     n_exact++;
     return rr_positive_significance(P.lnfact, s, gr1, gr2, cov, sizei, sizej);
 }
+
+// ---- tiered pruning with deferred, compacted evaluation -------------------------------------------
+// Per pair test, in order of cost:
+//   tier 0  trivial zero (MaxCorrelation.c:428-430)                          a few integer ops
+//   tier 1  median bound, then single-term pmf bound (rr_score.h)           6-9 table look-ups
+//   tier 2  windowed partial-sum bound in FP32 against FRESH maxima          ~100 FP32 ops
+//   tier 3  the exact score (exp + hypergeometric series + log10)            10^3..10^4 FP64 ops
+// Tiers 2 and 3 are needed by a few percent / per mille of the pairs.  Evaluating them in place
+// would serialise the warp behind single lanes, so survivors are pushed into per-warp shared
+// memory queues and evaluated 32 at a time, one candidate per lane.
+struct __align__(8) rr_cand {
+    uint32_t s, gr1, gr2, cov;   // the four counts of PositiveSignificance (423-426)
+    int32_t gi, gj;              // row group, column group
+};
+constexpr int RR_QUEUE_CAP = 64;
+
+// ln(n!) look-up: the first n_smem entries live in shared memory, the rest in HBM/L2
+struct rr_lnf_table {
+    const double *smem;
+    int n_smem;
+    const double *gmem;
+};
+__device__ __forceinline__ double rr_lnf(const rr_lnf_table &T, unsigned n)
+{
+    return n < (unsigned)T.n_smem ? T.smem[n] : __ldg(T.gmem + n);
+}
+// ln C(n, m) for bounds only (association order irrelevant; ln 0! = 0 makes m = 0 / m = n come out as 0)
+__device__ __forceinline__ double rr_lnchoose_t(const rr_lnf_table &T, unsigned n, unsigned m)
+{
+    return rr_lnf(T, n) - rr_lnf(T, m) - rr_lnf(T, n - m);
+}
+
+// tier 0 + 1.  lnc3 = lnchoose(cov, gr1), shared by the five column groups of a site.
+__device__ __forceinline__ bool rr_tier1(const rr_scan_params &P, const rr_lnf_table &T, unsigned s, unsigned gr1,
+                                         unsigned gr2, unsigned cov, double thr, double lnc3, unsigned &n_bound)
+{
+    if (gr1 == 0 || gr2 == 0 || s < 1) return false;
+    if (P.flags & RR_FLAG_NO_PRUNE) return true;
+    if (thr > RR_BOUND_MEDIAN && rr_below_median(s, gr1, gr2, cov)) return false;
+    if (P.flags & 0x200u) return false;  // timing experiment: nothing survives tier 1
+    if (!(thr > 0.0)) return true;
+    n_bound++;
+    const unsigned hi = gr1 < gr2 ? gr1 : gr2;
+    unsigned x = (unsigned)(__fdividef((float)gr1 * (float)gr2, (float)cov)) + 1u;
+    if (x < s) x = s;
+    if (x > hi) x = hi;
+    if (x + cov < gr1 + gr2) x = gr1 + gr2 - cov;
+    const double lp = rr_lnchoose_t(T, gr2, x) + rr_lnchoose_t(T, cov - gr2, gr1 - x) - lnc3;
+    return !(-RR_LOG10E * lp + 1e-6 < thr);
+}
+
+// tier 2: P[X >= s] >= sum_{x = x0}^{x0+m} pmf(x) for any x0 >= s; the window starts next to the mean
+// (or at s above it) and the term ratios are accumulated in FP32, every factor rounded down.
+__device__ __forceinline__ bool rr_tier2(const rr_lnf_table &T, unsigned s, unsigned gr1, unsigned gr2, unsigned cov,
+                                         double thr)
+{
+    if (!(thr > 0.0)) return true;
+    const unsigned hi = gr1 < gr2 ? gr1 : gr2;
+    const unsigned lo = gr1 + gr2 > cov ? gr1 + gr2 - cov : 0u;
+    int xm = (int)__fdividef((float)gr1 * (float)gr2, (float)cov) - 3;
+    unsigned x0 = xm > (int)s ? (unsigned)xm : s;
+    if (x0 > hi) x0 = hi;
+    if (x0 < lo) x0 = lo;
+    const double lp = rr_lnchoose_t(T, gr2, x0) + rr_lnchoose_t(T, cov - gr2, gr1 - x0) - rr_lnchoose_t(T, cov, gr1);
+    float S = 1.0f, term = 1.0f;
+    unsigned x = x0;
+#pragma unroll 1
+    for (int m = 0; m < 24 && x < hi; m++, x++) {
+        const float num = (float)(gr2 - x) * (float)(gr1 - x);
+        const float den = (float)(x + 1u) * (float)((cov + x + 1u) - gr1 - gr2);
+        term *= __fdividef(num, den) * 0.99999f;
+        S += term;
+        if (term < 1e-3f * S) break;
+    }
+    const double U2 = -RR_LOG10E * lp - (double)(__log2f(S) * 0.30103f * 0.99999f) + 2e-5;
+    return !(U2 < thr);
+}
+
+__device__ __forceinline__ void rr_queue_push(rr_cand *q, int &count, bool need, const rr_cand &c, int lane)
+{
+    const unsigned mask = __ballot_sync(0xffffffffu, need);
+    if (mask == 0u) return;
+    if (need) q[count + __popc(mask & ((1u << lane) - 1u))] = c;
+    count += __popc(mask);
+}
+
+// tier 3 on queued candidates, 32 per round (all of them when flush is set); both groups' maxima
+// are folded in with the 128-bit CAS
+static __device__ __noinline__ void rr_drain_exact(const rr_scan_params &P, rr_cand *q, int &count, int lane,
+                                                   unsigned &n_exact, bool flush)
+{
+    while (count >= 32 || (flush && count > 0)) {
+        __syncwarp();
+        const int take = count < 32 ? count : 32;
+        if (lane < take) {
+            const rr_cand c = q[count - take + lane];
+            n_exact++;
+            if (!(P.flags & 0x100u)) {  // 0x100: timing experiment, skip the evaluation
+                int iters = 0;
+                const double Z = rr_positive_significance(P.lnfact, c.s, c.gr1, c.gr2, c.cov, __ldg(P.gsize + c.gi),
+                                                          __ldg(P.gsize + c.gj), (P.flags & 0x800u) ? &iters : nullptr);
+                if (P.flags & 0x800u) {  // 0x800: statistics on the series lengths
+                    atomicAdd(P.counters + 5, (unsigned long long)(iters < 0 ? -iters : iters));
+                    if (iters < 0) atomicAdd(P.counters + 6, 1ull);
+                    int mx = iters < 0 ? -iters : iters;
+                    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(__activemask(), mx, o));
+                    if (lane == 0) atomicAdd(P.counters + 7, (unsigned long long)mx);
+                }
+                if (Z > 0.0) {
+                    if (Z >= rr_best_value(P.best + c.gi)) rr_best_update(P.best, c.gi, Z, c.gj);
+                    if (Z >= rr_best_value(P.best + c.gj)) rr_best_update(P.best, c.gj, Z, c.gi);
+                }
+            }
+        }
+        count -= take;
+        __syncwarp();
+    }
+}
+
+// tier 2 on queued tier-1 survivors; what survives moves on to the exact queue
+static __device__ __noinline__ void rr_drain_tier2(const rr_scan_params &P, const rr_lnf_table &T, rr_cand *q1, int &c1,
+                                                   rr_cand *q2, int &c2, int lane, unsigned &n_tier2, unsigned &n_exact,
+                                                   bool flush)
+{
+    while (c1 >= 32 || (flush && c1 > 0)) {
+        __syncwarp();
+        const int take = c1 < 32 ? c1 : 32;
+        bool need = false;
+        rr_cand c;
+        c.s = c.gr1 = c.gr2 = c.cov = 0u; c.gi = c.gj = 0;
+        if (lane < take) {
+            c = q1[c1 - take + lane];
+            n_tier2++;
+            need = true;
+            if (!(P.flags & RR_FLAG_NO_PRUNE)) {
+                const double thr = fmin(rr_best_value(P.best + c.gi), rr_best_value(P.best + c.gj));
+                need = rr_tier2(T, c.s, c.gr1, c.gr2, c.cov, thr);
+            }
+        }
+        c1 -= take;
+        __syncwarp();
+        rr_queue_push(q2, c2, need, c, lane);
+        if (c2 >= 32) rr_drain_exact(P, q2, c2, lane, n_exact, false);
+    }
+    if (flush) rr_drain_exact(P, q2, c2, lane, n_exact, true);
+}

@@ -14,10 +14,12 @@ void rr_plan_build(rr_plan &plan, int R, int N, int mincov, const int32_t *gsize
     std::vector<int32_t> colok_prefix((size_t)N + 1, 0);
     plan.rowsites.clear();
     std::vector<int32_t> nrow;
+    plan.max_cov = 0;
     for (int ii = 0; ii < N; ii++) {
         const int32_t *gs = gsize + (size_t)5 * ii;
         const int baseno = gs[0] + gs[1] + gs[2] + gs[3];            // 798
         const bool basey = baseno > coverage[ii] / 2;                // 802
+        plan.max_cov = std::max(plan.max_cov, (int)coverage[ii]);
         int nr = 0, nc = 0;
         for (int k = 0; k < 5; k++) {
             const bool sz = gs[k] > q && gs[k] < R;                  // 802 / 817 (maxgroup = signumber, 1008)

@@ -13,14 +13,15 @@
 //   K          reads in span-start order; only the 128-read blocks [k_lo(col tile), k_hi(row tile))
 //              can hold a read covering both tiles, the rest is skipped exactly.
 //
-// Warp roles (one persistent CTA per SM, 320 threads):
+// Warp roles (one persistent CTA per SM, 512 threads):
 //   warp 0      TMA producer (one elected lane): A and B boxes of a K block -> smem stage
 //   warp 1      TMEM allocator + MMA issuer (one elected lane): 4 x tcgen05.mma (K=32) per stage,
 //               tcgen05.commit frees the stage / publishes the accumulator
-//   warps 2-9   epilogue: tcgen05.ld the 128 x 240 int32 tile (two warps per 32-lane quarter, each
-//               taking alternate 40-column chunks), 5x5 block sums (in-thread row sums, 5-lane
-//               shuffle column sums), filters, pruning bounds, exact FP64 score, row max in
-//               registers, column max through a 128-bit CAS.
+//   warps 2-3   idle (keep the epilogue warps aligned to the TMEM lane quarters)
+//   warps 4-15  epilogue, three warps per 32-lane TMEM quarter, each taking every third column site:
+//               tcgen05.ld of the site's 5 counts, 5x5 block sums (in-thread row sum, 5-lane shuffle
+//               column sums), filters, tiered pruning bounds; survivors are queued per warp and
+//               evaluated 32 at a time (exact FP64 score), maxima folded in with a 128-bit CAS.
 // Two accumulators (2 x 256 TMEM columns) double-buffer MMA against the epilogue.
 #include <cuda.h>
 #include <vector>
@@ -36,30 +37,35 @@ constexpr int UM_M = 128;                        // rows per A tile (4 slabs x 3
 constexpr int UM_COL_SITES = 48;                 // column sites per tile
 constexpr int UM_N = UM_COL_SITES * 5;           // 240 columns per B tile
 constexpr int UM_KB = 128;                       // reads per K block (= 128 B swizzle span)
-constexpr int UM_STAGES = 4;
+constexpr int UM_STAGES = 3;
 constexpr int UM_A_BYTES = UM_M * UM_KB;         // 16384
 constexpr int UM_B_BYTES = UM_N * UM_KB;         // 30720
 constexpr int UM_STAGE_BYTES = UM_A_BYTES + UM_B_BYTES;  // 47104 = 46 * 1024
-constexpr int UM_EPI_WARPS = 8;
-constexpr int UM_THREADS = (2 + UM_EPI_WARPS) * 32;
-constexpr int UM_CHUNK_SITES = 8;                // column sites per epilogue chunk
-constexpr int UM_CHUNK_COLS = UM_CHUNK_SITES * 5;  // 40 TMEM columns = x32 + x8
-constexpr int UM_CHUNKS = UM_COL_SITES / UM_CHUNK_SITES;  // 6
+constexpr int UM_FIRST_EPI_WARP = 4;
+constexpr int UM_EPI_WARPS = 12;
+constexpr int UM_THREADS = (UM_FIRST_EPI_WARP + UM_EPI_WARPS) * 32;  // 512
+constexpr int UM_SUB = UM_EPI_WARPS / 4;         // epilogue warps per TMEM lane quarter
+constexpr int UM_WSITES = UM_COL_SITES / UM_SUB; // column sites per warp and tile (16)
 constexpr int UM_TMEM_COLS = 512;
 constexpr int UM_ACC_STRIDE = 256;               // TMEM columns between the two accumulators
 
-struct um_meta {                                  // per accumulator buffer, column-side metadata
-    double mj[UM_N];                              // running maxima of the tile's column groups
-    int szj[UM_N];                                // Groupsizearray, or -1 when not admissible (817)
+struct um_wmeta {                                 // per epilogue warp: metadata of its column groups in the tile
+    double mj[UM_WSITES * 5];                     // running maxima
+    int szj[UM_WSITES * 5];                       // Groupsizearray, or -1 when not admissible (817)
 };
 
 struct um_smem_tail {
-    um_meta meta[2];
+    um_wmeta meta[UM_EPI_WARPS];
+    rr_cand q1[UM_EPI_WARPS][RR_QUEUE_CAP];       // tier-1 survivors, one queue per epilogue warp
+    rr_cand q2[UM_EPI_WARPS][RR_QUEUE_CAP];       // tier-2 survivors (exact evaluation pending)
     unsigned long long full[UM_STAGES], empty[UM_STAGES], tfull[2], tempty[2];
     uint32_t tmem_base;
 };
 
-constexpr size_t UM_SMEM_BYTES = 1024 + (size_t)UM_STAGES * UM_STAGE_BYTES + sizeof(um_smem_tail);
+constexpr size_t UM_TAIL_OFF = (size_t)UM_STAGES * UM_STAGE_BYTES;
+constexpr size_t UM_LNF_OFF = (UM_TAIL_OFF + sizeof(um_smem_tail) + 15) & ~(size_t)15;
+constexpr size_t UM_SMEM_MAX = 227 * 1024;
+constexpr int UM_LNF_MAX = (int)((UM_SMEM_MAX - UM_LNF_OFF) / sizeof(double));  // ln(n!) entries that fit
 
 struct um_unit { int32_t rt, ct0, ct1; };         // row tile, column tiles [ct0, ct1)
 
@@ -69,6 +75,7 @@ struct um_params {
     int n_units;
     const int32_t *k_hi;      // [row tiles]   exclusive K-block bound
     const int32_t *k_lo;      // [column tiles] inclusive K-block bound
+    int lnf_smem;             // ln(n!) entries staged in shared memory
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -144,42 +151,33 @@ __device__ __forceinline__ uint32_t make_idesc()
            ((uint32_t)(UM_M >> 4) << 24);
 }
 
-#define TMEM_LD_32(v, addr)                                                                                     \
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                     \
-                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                       \
-                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"       \
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), \
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),        \
-                   "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),      \
-                   "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),      \
-                   "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                         \
-                 : "r"(addr))
-#define TMEM_LD_8(v, addr)                                                                                      \
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"               \
-                 : "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]),      \
-                   "=r"(v[39])                                                                                   \
+#define TMEM_LD_8(v, addr)                                                                          \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"   \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) \
                  : "r"(addr))
 
 // sum of x over the 5 lanes of a site (lanes 5t..5t+4), returned in every lane of the site
-__device__ __forceinline__ int site_sum5(int x, int lane, int base_lane)
+__device__ __forceinline__ int site_sum5(int x, int base_lane)
 {
     int s1 = x + __shfl_down_sync(0xffffffffu, x, 1);
     int s2 = s1 + __shfl_down_sync(0xffffffffu, s1, 2);
     int s = s2 + __shfl_down_sync(0xffffffffu, x, 4);
-    (void)lane;
     return __shfl_sync(0xffffffffu, s, base_lane);
 }
 
+// ALL_SMEM: every ln(n!) argument (<= largest column coverage) is inside the shared-memory table
+template <bool ALL_SMEM>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const um_params U)
 {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    um_smem_tail *T = reinterpret_cast<um_smem_tail *>(smem + (size_t)UM_STAGES * UM_STAGE_BYTES);
+    extern __shared__ __align__(1024) uint8_t smem[];
+    um_smem_tail *T = reinterpret_cast<um_smem_tail *>(smem + UM_TAIL_OFF);
+    double *lnf_s = reinterpret_cast<double *>(smem + UM_LNF_OFF);
     const rr_scan_params &P = U.P;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
+        if (smem_u32(smem) & 1023u) __trap();  // the swizzled operand tiles need a 1024-byte aligned base
         for (int s = 0; s < UM_STAGES; s++) { mbar_init(&T->full[s], 1); mbar_init(&T->empty[s], 1); }
         for (int a = 0; a < 2; a++) { mbar_init(&T->tfull[a], 1); mbar_init(&T->tempty[a], UM_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -188,6 +186,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&T->tmem_base)), "n"(UM_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    for (int n = threadIdx.x; n < U.lnf_smem; n += UM_THREADS) lnf_s[n] = U.P.lnfact[n];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -252,50 +251,51 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
             }
         }
-    } else {
+    } else if (warp >= UM_FIRST_EPI_WARP) {
         // ================= epilogue =================
-        const int ew = warp - 2;                 // 0..7
+        const int ew = warp - UM_FIRST_EPI_WARP;  // 0..UM_EPI_WARPS-1
         const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-        const int half = ew >> 2;                // which of the two warps of the quarter
-        const int et = threadIdx.x - 64;         // 0..255
+        const int sub = ew >> 2;                 // which of the UM_SUB warps of the quarter
         const int site_l = lane / 5;             // 0..5 (6 for the two pad lanes)
         const int a = lane - site_l * 5;         // group within the site
         const int base_lane = site_l * 5;
         const bool lane_row = lane < 30;
-        unsigned n_pairs = 0, n_exact = 0, n_bound = 0, n_units = 0;
-        uint32_t tile = 0, mtile = 0;
+        unsigned n_pairs = 0, n_exact = 0, n_bound = 0, n_units = 0, n_tier2 = 0;
+        uint32_t tile = 0;
+        rr_cand *q1 = T->q1[ew], *q2 = T->q2[ew];
+        um_wmeta &M = T->meta[ew];
+        int c1n = 0, c2n = 0;
+        rr_lnf_table LT;
+        LT.smem = lnf_s; LT.n_smem = ALL_SMEM ? 0x7fffffff : U.lnf_smem; LT.gmem = P.lnfact;
 
         for (int u = blockIdx.x; u < U.n_units; u += gridDim.x) {
             const um_unit un = U.units[u];
             const int khi = U.k_hi[un.rt];
-            n_units += (et == 0);
+            n_units += (ew == 0 && lane == 0);
             // ---- row-side state of this thread (one output row = one group of one row site) ----
             const int ii = lane_row ? P.rowsites[un.rt * UM_ROW_SITES + quarter * 6 + site_l] : -1;
             const int gi = ii >= 0 ? 5 * ii + a : -1;
             const bool row_ok = gi >= 0 && P.rowok[gi] != 0;
-            const int szi = row_ok ? P.gsize[gi] : 0;
             const int brk = ii >= 0 ? min(P.breakcol[ii], P.N) : 0;
-            // zi0: the group's maximum stored so far (other units / other warps); (lz, lp): the best
-            // pair this thread has seen in this unit.  Pruning threshold = max(zi0, lz).
-            const double zi0 = row_ok ? rr_best_value(P.best + gi) : 0.0;
-            double lz = 0.0;
-            int lp = 0x7fffffff;
+            double thr_i = 0.0;                    // running max of row group i (refreshed from HBM)
 
-            for (int ct = un.ct0; ct < un.ct1; ct++, mtile++) {
+            for (int ct = un.ct0; ct < un.ct1; ct++) {
                 const int klo = U.k_lo[ct];
                 const bool has_counts = klo < khi;
-                const int mb = mtile & 1;
-                // column-side metadata of this tile (all 256 epilogue threads)
-                um_meta &M = T->meta[mb];
-                if (et < UM_N) {
-                    const int j = ct * UM_N + et;
+                const int jsite0 = ct * UM_COL_SITES;
+                // ---- this warp's column groups: sites sub, sub+UM_SUB, ... (slot w <-> site sub + w*UM_SUB)
+                __syncwarp();
+                for (int e = lane; e < UM_WSITES * 5; e += 32) {
+                    const int w = e / 5, b = e - w * 5;
+                    const int j = 5 * (jsite0 + sub + w * UM_SUB) + b;
                     int sz = -1;
                     double m = 0.0;
                     if (j < 5 * P.N && P.colok[j]) { sz = P.gsize[j]; m = rr_best_value(P.best + j); }
-                    M.szj[et] = sz;
-                    M.mj[et] = m;
+                    M.szj[e] = sz;
+                    M.mj[e] = m;
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(UM_EPI_WARPS * 32) : "memory");
+                if (row_ok) thr_i = rr_best_value(P.best + gi);
+                __syncwarp();
 
                 int acc = 0;
                 if (has_counts) {
@@ -304,60 +304,54 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     mbar_wait(&T->tfull[acc], aph);
                     tc_fence_after();
                 }
-                const int jsite0 = ct * UM_COL_SITES;
-                for (int ch = half; ch < UM_CHUNKS; ch += 2) {
-                    const int cs0 = jsite0 + ch * UM_CHUNK_SITES;  // first column site of the chunk
-                    if (cs0 >= P.N) break;
-                    uint32_t v[UM_CHUNK_COLS];
+                const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * UM_ACC_STRIDE);
+                // 8 TMEM columns are fetched per site (5 used); the load of the next site is in flight
+                // while the current one is processed
+                uint32_t v[8];
+                const int t_end = (P.flags & 0x400u) ? 0 : min(UM_COL_SITES, P.N - jsite0);  // 0x400: MMA only
+                if (has_counts && sub < t_end) TMEM_LD_8(v, taddr0 + 5 * sub);
+#pragma unroll 1
+                for (int w = 0, t = sub; t < t_end; w++, t += UM_SUB) {
+                    int c[5];
                     if (has_counts) {
-                        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
-                                               (uint32_t)(acc * UM_ACC_STRIDE + ch * UM_CHUNK_COLS);
-                        TMEM_LD_32(v, taddr);
-                        TMEM_LD_8(v, taddr + 32);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int b = 0; b < 5; b++) c[b] = (int)v[b];
+                        if (t + UM_SUB < t_end) TMEM_LD_8(v, taddr0 + 5 * (t + UM_SUB));
                     } else {
 #pragma unroll
-                        for (int q = 0; q < UM_CHUNK_COLS; q++) v[q] = 0u;
+                        for (int b = 0; b < 5; b++) c[b] = 0;
                     }
-                    // warp-uniform skip: no lane of this warp pairs with this chunk
-                    {
-                        const bool any_lane = row_ok && cs0 + UM_CHUNK_SITES - 1 >= ii + 20 && cs0 < brk;
-                        if (!__any_sync(0xffffffffu, any_lane)) continue;
-                    }
+                    const int jj = jsite0 + t;
+                    const bool pair_site = row_ok && jj >= ii + 20 && jj < brk;
+                    if (!__any_sync(0xffffffffu, pair_site)) continue;
+                    const int rowsum = c[0] + c[1] + c[2] + c[3] + c[4];  // gr1 = |Gi & Cjj|
+                    int colsum[5];                                          // gr2 = |Gj & Cii| per column group
 #pragma unroll
-                    for (int t = 0; t < UM_CHUNK_SITES; t++) {
-                        const int jj = cs0 + t;
-                        if (jj >= P.N) break;  // warp-uniform
-                        const int c0 = (int)v[5 * t], c1 = (int)v[5 * t + 1], c2 = (int)v[5 * t + 2],
-                                  c3 = (int)v[5 * t + 3], c4 = (int)v[5 * t + 4];
-                        const int rowsum = c0 + c1 + c2 + c3 + c4;  // gr1 = |Gi & Cjj|
-                        int colsum[5];                                // gr2 = |Gj & Cii| per column group
-                        colsum[0] = site_sum5(c0, lane, base_lane);
-                        colsum[1] = site_sum5(c1, lane, base_lane);
-                        colsum[2] = site_sum5(c2, lane, base_lane);
-                        colsum[3] = site_sum5(c3, lane, base_lane);
-                        colsum[4] = site_sum5(c4, lane, base_lane);
-                        const int cov = colsum[0] + colsum[1] + colsum[2] + colsum[3] + colsum[4];
-                        const bool pair_site = row_ok && jj >= ii + 20 && jj < brk;
-                        if (!pair_site) continue;
-                        const int cc[5] = {c0, c1, c2, c3, c4};
+                    for (int b = 0; b < 5; b++) colsum[b] = site_sum5(c[b], base_lane);
+                    const int cov = colsum[0] + colsum[1] + colsum[2] + colsum[3] + colsum[4];
+                    const double lnc3 = rr_lnchoose_t(LT, (unsigned)cov, (unsigned)rowsum);
+                    // tier 0/1 for the five column groups (independent -> ILP), then the queue pushes
+                    bool need[5];
 #pragma unroll
-                        for (int b = 0; b < 5; b++) {
-                            const int col = (ch * UM_CHUNK_SITES + t) * 5 + b;
-                            const int szj = M.szj[col];
-                            if (szj < 0) continue;  // warp-uniform (817)
+                    for (int b = 0; b < 5; b++) {
+                        const int szj = M.szj[w * 5 + b];
+                        need[b] = false;
+                        if (pair_site && szj >= 0) {
                             n_pairs++;
-                            const double mj = M.mj[col];
-                            const double Z = rr_pair_score(P, (unsigned)cc[b], (unsigned)rowsum, (unsigned)colsum[b],
-                                                           (unsigned)cov, szi, szj, fmax(zi0, lz), mj, n_exact, n_bound);
-                            if (Z > 0.0) {
-                                const int gj = 5 * jj + b;
-                                if (Z > lz || (Z == lz && gj < lp)) { lz = Z; lp = gj; }
-                                if (Z >= mj) {
-                                    rr_best_update(P.best, gj, Z, gi);
-                                    if (Z > mj) M.mj[col] = Z;
-                                }
-                            }
+                            need[b] = rr_tier1(P, LT, (unsigned)c[b], (unsigned)rowsum, (unsigned)colsum[b], (unsigned)cov,
+                                               fmin(thr_i, M.mj[w * 5 + b]), lnc3, n_bound);
+                        }
+                    }
+#pragma unroll
+                    for (int b = 0; b < 5; b++) {
+                        rr_cand cand;
+                        cand.s = (uint32_t)c[b]; cand.gr1 = (uint32_t)rowsum; cand.gr2 = (uint32_t)colsum[b];
+                        cand.cov = (uint32_t)cov; cand.gi = gi; cand.gj = 5 * jj + b;
+                        rr_queue_push(q1, c1n, need[b], cand, lane);
+                        if (c1n >= 32) {
+                            rr_drain_tier2(P, LT, q1, c1n, q2, c2n, lane, n_tier2, n_exact, false);
+                            if (row_ok) thr_i = rr_best_value(P.best + gi);
                         }
                     }
                 }
@@ -368,21 +362,23 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     tile++;
                 }
             }
-            if (lz > 0.0 && lz >= zi0) rr_best_update(P.best, gi, lz, lp);
+            rr_drain_tier2(P, LT, q1, c1n, q2, c2n, lane, n_tier2, n_exact, true);
         }
 
-        unsigned long long v0 = n_pairs, v1 = n_exact, v2 = n_bound, v3 = n_units;
+        unsigned long long v0 = n_pairs, v1 = n_exact, v2 = n_bound, v3 = n_units, v4 = n_tier2;
         for (int o = 16; o > 0; o >>= 1) {
             v0 += __shfl_xor_sync(0xffffffffu, v0, o);
             v1 += __shfl_xor_sync(0xffffffffu, v1, o);
             v2 += __shfl_xor_sync(0xffffffffu, v2, o);
             v3 += __shfl_xor_sync(0xffffffffu, v3, o);
+            v4 += __shfl_xor_sync(0xffffffffu, v4, o);
         }
         if (lane == 0) {
             if (v0) atomicAdd(P.counters + 0, v0);
             if (v1) atomicAdd(P.counters + 1, v1);
             if (v2) atomicAdd(P.counters + 2, v2);
             if (v3) atomicAdd(P.counters + 3, v3);
+            if (v4) atomicAdd(P.counters + 4, v4);
         }
     }
 
@@ -517,16 +513,27 @@ int rr_umma_scan(rr_umma_state *&S, rr_scan_params &P, rr_plan &plan, const uint
     rr_count_launch(1);
     UM_CUDA(cudaGetLastError());
 
-    // work units: (row tile, up to UNIT_CT consecutive column tiles), this part's row tiles only
-    constexpr int UNIT_CT = 16;
-    std::vector<um_unit> units;
+    // work units: (row tile, aligned chunk of UNIT_CT column tiles), this part's row tiles only, ordered in
+    // 2-D blocks of GR row tiles x GC chunks so that the ~148 units in flight at any time share a working set
+    // (GR A row-tiles + GC*UNIT_CT B column-tiles, a few tens of MB) that stays resident in the 126 MB L2.
+    constexpr int UNIT_CT = 4, GR = 24, GC = 6;
+    struct keyed { int64_t key; um_unit u; };
+    std::vector<keyed> ku;
     int64_t kblocks = 0;
     for (int rb = plan.rb_lo; rb < plan.rb_hi; rb++) {
         const int cb0 = plan.unit_cb0[rb];
         const int ncb = (int)(plan.unit_prefix[rb + 1] - plan.unit_prefix[rb]);
-        for (int c = 0; c < ncb; c += UNIT_CT) units.push_back({rb, cb0 + c, cb0 + std::min(ncb, c + UNIT_CT)});
+        if (ncb <= 0) continue;
+        for (int cc = cb0 / UNIT_CT; cc <= (cb0 + ncb - 1) / UNIT_CT; cc++) {
+            um_unit un = {rb, std::max(cb0, cc * UNIT_CT), std::min(cb0 + ncb, (cc + 1) * UNIT_CT)};
+            const int64_t key = ((((int64_t)((rb - plan.rb_lo) / GR) << 20) + (cc / GC)) << 32) + ((int64_t)rb << 12) + (cc % (GC * 64));
+            ku.push_back({key, un});
+        }
         for (int c = 0; c < ncb; c++) kblocks += std::max(0, plan.k_hi[rb] - plan.k_lo[cb0 + c]);
     }
+    std::sort(ku.begin(), ku.end(), [](const keyed &x, const keyed &y) { return x.key < y.key; });
+    std::vector<um_unit> units(ku.size());
+    for (size_t q = 0; q < ku.size(); q++) units[q] = ku[q].u;
     plan.executed_ops = kblocks * (int64_t)(2LL * UM_M * UM_N * UM_KB);
     if (units.empty()) return RR_OK;
     if ((rc = grow(&S->d_units, &S->units_cap, units.size()))) return rc;
@@ -542,7 +549,8 @@ int rr_umma_scan(rr_umma_state *&S, rr_scan_params &P, rr_plan &plan, const uint
     if ((rc = make_map(&map_b, S->xb, (uint64_t)5 * P.N, (uint64_t)S->Kp, UM_N))) return rc;
 
     if (!S->attr_set) {
-        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_BYTES));
+        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
+        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
         S->attr_set = true;
     }
     um_params U;
@@ -552,7 +560,12 @@ int rr_umma_scan(rr_umma_state *&S, rr_scan_params &P, rr_plan &plan, const uint
     U.k_hi = S->d_khi;
     U.k_lo = S->d_klo;
     const int grid = std::min<int>(n_sm, (int)units.size());
-    rr_k_scan_umma<<<grid, UM_THREADS, UM_SMEM_BYTES, st>>>(map_a, map_b, U);
+    U.lnf_smem = std::min(std::min(plan.max_cov + 2, P.R + 2), UM_LNF_MAX);
+    const size_t smem_bytes = UM_LNF_OFF + (size_t)U.lnf_smem * sizeof(double);
+    if (U.lnf_smem >= plan.max_cov + 1)
+        rr_k_scan_umma<true><<<grid, UM_THREADS, smem_bytes, st>>>(map_a, map_b, U);
+    else
+        rr_k_scan_umma<false><<<grid, UM_THREADS, smem_bytes, st>>>(map_a, map_b, U);
     rr_count_launch(1);
     UM_CUDA(cudaGetLastError());
     return RR_OK;
