@@ -351,7 +351,11 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         rr_queue_push(q1, c1n, need[b], cand, lane);
                         if (c1n >= 32) {
                             rr_drain_tier2(P, LT, q1, c1n, q2, c2n, lane, n_tier2, n_exact, false);
+                            // pick up what this and the other warps / CTAs have found meanwhile
                             if (row_ok) thr_i = rr_best_value(P.best + gi);
+                            for (int e = lane; e < UM_WSITES * 5; e += 32)
+                                if (M.szj[e] >= 0) M.mj[e] = rr_best_value(P.best + 5 * (jsite0 + sub + (e / 5) * UM_SUB) + (e % 5));
+                            __syncwarp();
                         }
                     }
                 }
@@ -534,12 +538,23 @@ int rr_umma_scan(rr_umma_state *&S, rr_scan_params &P, rr_plan &plan, const uint
     std::sort(ku.begin(), ku.end(), [](const keyed &x, const keyed &y) { return x.key < y.key; });
     std::vector<um_unit> units(ku.size());
     for (size_t q = 0; q < ku.size(); q++) units[q] = ku[q].u;
+    // Seeding pass: the same kernel over every SEED-th row tile first.  It leaves true (lower-bound) maxima in
+    // best[] for all column groups, so the full pass starts with thresholds close to the final ones instead
+    // of 0 and the bounds prune from the first pair on.  Its pair statistics are discarded.
+    constexpr int SEED = 16;
+    std::vector<um_unit> seed_units;
+    if (plan.rb_hi - plan.rb_lo >= 2 * SEED && !(P.flags & (RR_FLAG_NO_PRUNE | 0x1000u)))
+        for (const um_unit &un : units)
+            if ((un.rt - plan.rb_lo) % SEED == SEED / 2) seed_units.push_back(un);
     plan.executed_ops = kblocks * (int64_t)(2LL * UM_M * UM_N * UM_KB);
     if (units.empty()) return RR_OK;
-    if ((rc = grow(&S->d_units, &S->units_cap, units.size()))) return rc;
+    if ((rc = grow(&S->d_units, &S->units_cap, units.size() + seed_units.size()))) return rc;
     if ((rc = grow(&S->d_khi, &S->khi_cap, plan.k_hi.size()))) return rc;
     if ((rc = grow(&S->d_klo, &S->klo_cap, plan.k_lo.size()))) return rc;
     UM_CUDA(cudaMemcpyAsync(S->d_units, units.data(), sizeof(um_unit) * units.size(), cudaMemcpyHostToDevice, st));
+    if (!seed_units.empty())
+        UM_CUDA(cudaMemcpyAsync(S->d_units + units.size(), seed_units.data(), sizeof(um_unit) * seed_units.size(),
+                                cudaMemcpyHostToDevice, st));
     UM_CUDA(cudaMemcpyAsync(S->d_khi, plan.k_hi.data(), sizeof(int32_t) * plan.k_hi.size(), cudaMemcpyHostToDevice, st));
     UM_CUDA(cudaMemcpyAsync(S->d_klo, plan.k_lo.data(), sizeof(int32_t) * plan.k_lo.size(), cudaMemcpyHostToDevice, st));
     UM_CUDA(cudaStreamSynchronize(st));  // units[] is a local
@@ -562,10 +577,20 @@ int rr_umma_scan(rr_umma_state *&S, rr_scan_params &P, rr_plan &plan, const uint
     const int grid = std::min<int>(n_sm, (int)units.size());
     U.lnf_smem = std::min(std::min(plan.max_cov + 2, P.R + 2), UM_LNF_MAX);
     const size_t smem_bytes = UM_LNF_OFF + (size_t)U.lnf_smem * sizeof(double);
-    if (U.lnf_smem >= plan.max_cov + 1)
-        rr_k_scan_umma<true><<<grid, UM_THREADS, smem_bytes, st>>>(map_a, map_b, U);
-    else
-        rr_k_scan_umma<false><<<grid, UM_THREADS, smem_bytes, st>>>(map_a, map_b, U);
+    const bool all_smem = U.lnf_smem >= plan.max_cov + 1;
+    if (!seed_units.empty()) {
+        um_params V = U;
+        V.units = S->d_units + units.size();
+        V.n_units = (int)seed_units.size();
+        const int sgrid = std::min<int>(n_sm, V.n_units);
+        if (all_smem) rr_k_scan_umma<true><<<sgrid, UM_THREADS, smem_bytes, st>>>(map_a, map_b, V);
+        else rr_k_scan_umma<false><<<sgrid, UM_THREADS, smem_bytes, st>>>(map_a, map_b, V);
+        rr_count_launch(1);
+        UM_CUDA(cudaGetLastError());
+        UM_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(unsigned long long) * 8, st));
+    }
+    if (all_smem) rr_k_scan_umma<true><<<grid, UM_THREADS, smem_bytes, st>>>(map_a, map_b, U);
+    else rr_k_scan_umma<false><<<grid, UM_THREADS, smem_bytes, st>>>(map_a, map_b, U);
     rr_count_launch(1);
     UM_CUDA(cudaGetLastError());
     return RR_OK;
