@@ -162,7 +162,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="Tree_1perc_30000", choices=sorted(WORKLOADS))
-    ap.add_argument("--variant", default="auto", choices=["auto", "bitset", "umma"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "bitset", "umma", "umma_f4"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -46,7 +46,10 @@ extern "C" {
 enum {
     RR_VARIANT_AUTO = 0,   /* the faster one for this shape */
     RR_VARIANT_BITSET = 1, /* shared-memory staged u32 bitsets, AND + POPC */
-    RR_VARIANT_UMMA = 2    /* int8 0/1 operands, tcgen05.mma kind::i8, int32 accumulators in TMEM */
+    RR_VARIANT_UMMA = 2,   /* int8 0/1 operands, tcgen05.mma kind::i8, int32 accumulators in TMEM */
+    RR_VARIANT_UMMA_F4 = 3 /* the same GEMM with the 0/1 operands stored as packed 4-bit e2m1 (half the HBM/L2
+                              bytes; TMA unpacks them into shared memory), tcgen05.mma kind::f8f6f4 at the 8-bit
+                              rate, fp32 accumulators in TMEM (exact: counts < 2^24) */
 };
 
 /* flags */
@@ -73,7 +76,7 @@ typedef struct rr_scan_stats {
     int64_t exact_evals;  /* pairs whose exact score was evaluated */
     int64_t bound_evals;  /* pairs that needed the pmf bound */
     int64_t work_units;   /* tile pairs processed */
-    int64_t executed_ops; /* int8 MACs*2 (UMMA) or 32-bit AND+POPC word ops (bitset) executed */
+    int64_t executed_ops; /* tensor-core MACs*2 (UMMA variants) or 32-bit AND+POPC word ops (bitset) executed */
     int variant;          /* variant actually used */
     int rows, cols;       /* R, N */
     int row_sites;        /* sites with at least one admissible row group */

@@ -38,7 +38,7 @@ extern "C" int rr_device_count(void)
 extern "C" int rr_variant_available(int variant)
 {
     if (variant == RR_VARIANT_BITSET || variant == RR_VARIANT_AUTO) return 1;
-    if (variant == RR_VARIANT_UMMA) return rr_umma_available();
+    if (variant == RR_VARIANT_UMMA || variant == RR_VARIANT_UMMA_F4) return rr_umma_available();
     return 0;
 }
 
@@ -319,8 +319,8 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
     RR_CUDA(cudaEventRecord(e0, pk->st));
 
     int variant = opts->variant;
-    if (variant == RR_VARIANT_AUTO) variant = rr_umma_available() ? RR_VARIANT_UMMA : RR_VARIANT_BITSET;
-    if (variant != RR_VARIANT_BITSET && variant != RR_VARIANT_UMMA) { rr_set_error("unknown variant %d", variant); return RR_E_ARG; }
+    if (variant == RR_VARIANT_AUTO) variant = rr_umma_available() ? RR_VARIANT_UMMA_F4 : RR_VARIANT_BITSET;
+    if (variant != RR_VARIANT_BITSET && variant != RR_VARIANT_UMMA && variant != RR_VARIANT_UMMA_F4) { rr_set_error("unknown variant %d", variant); return RR_E_ARG; }
 
     // ---- host plan: filters, first-break columns, tiles, partition (O(N)) ------------------
     rr_plan plan;
@@ -377,7 +377,7 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
         if (variant == RR_VARIANT_BITSET) {
             RR_CUDA(rr_launch_scan_bitset(P, pk->n_sm, pk->st));
         } else {
-            rc = rr_umma_scan(pk->umma, P, plan, pk->d_cells, pk->d_perm, pk->codes, pk->n_sm, pk->st);
+            rc = rr_umma_scan(pk->umma, variant == RR_VARIANT_UMMA_F4, P, plan, pk->d_cells, pk->d_perm, pk->codes, pk->n_sm, pk->st);
             if (rc) return rc;
         }
     }

@@ -125,24 +125,22 @@ struct __align__(8) rr_cand {
 };
 constexpr int RR_QUEUE_CAP = 64;
 
-// ln(n!) look-up: the first n_smem entries live in shared memory, the rest in HBM/L2
-struct rr_lnf_table {
-    const double *smem;
-    int n_smem;
+// ln(n!) look-up for the bounds: LT is a callable `double operator()(unsigned n)` supplied by the kernel
+// (shared-memory table, HBM table, or both).
+struct rr_lnf_global {
     const double *gmem;
+    __device__ __forceinline__ double operator()(unsigned n) const { return __ldg(gmem + n); }
 };
-__device__ __forceinline__ double rr_lnf(const rr_lnf_table &T, unsigned n)
-{
-    return n < (unsigned)T.n_smem ? T.smem[n] : __ldg(T.gmem + n);
-}
 // ln C(n, m) for bounds only (association order irrelevant; ln 0! = 0 makes m = 0 / m = n come out as 0)
-__device__ __forceinline__ double rr_lnchoose_t(const rr_lnf_table &T, unsigned n, unsigned m)
+template <class LT>
+__device__ __forceinline__ double rr_lnchoose_t(const LT &T, unsigned n, unsigned m)
 {
-    return rr_lnf(T, n) - rr_lnf(T, m) - rr_lnf(T, n - m);
+    return T(n) - T(m) - T(n - m);
 }
 
 // tier 0 + 1.  lnc3 = lnchoose(cov, gr1), shared by the five column groups of a site.
-__device__ __forceinline__ bool rr_tier1(const rr_scan_params &P, const rr_lnf_table &T, unsigned s, unsigned gr1,
+template <class LT>
+__device__ __forceinline__ bool rr_tier1(const rr_scan_params &P, const LT &T, unsigned s, unsigned gr1,
                                          unsigned gr2, unsigned cov, double thr, double lnc3, unsigned &n_bound)
 {
     if (gr1 == 0 || gr2 == 0 || s < 1) return false;
@@ -162,7 +160,8 @@ __device__ __forceinline__ bool rr_tier1(const rr_scan_params &P, const rr_lnf_t
 
 // tier 2: P[X >= s] >= sum_{x = x0}^{x0+m} pmf(x) for any x0 >= s; the window starts next to the mean
 // (or at s above it) and the term ratios are accumulated in FP32, every factor rounded down.
-__device__ __forceinline__ bool rr_tier2(const rr_lnf_table &T, unsigned s, unsigned gr1, unsigned gr2, unsigned cov,
+template <class LT>
+__device__ __forceinline__ bool rr_tier2(const LT &T, unsigned s, unsigned gr1, unsigned gr2, unsigned cov,
                                          double thr)
 {
     if (!(thr > 0.0)) return true;
@@ -229,7 +228,8 @@ static __device__ __noinline__ void rr_drain_exact(const rr_scan_params &P, rr_c
 }
 
 // tier 2 on queued tier-1 survivors; what survives moves on to the exact queue
-static __device__ __noinline__ void rr_drain_tier2(const rr_scan_params &P, const rr_lnf_table &T, rr_cand *q1, int &c1,
+template <class LT>
+static __device__ __noinline__ void rr_drain_tier2(const rr_scan_params &P, const LT &T, rr_cand *q1, int &c1,
                                                    rr_cand *q2, int &c2, int lane, unsigned &n_tier2, unsigned &n_exact,
                                                    bool flush)
 {

@@ -18,7 +18,7 @@ cudaError_t rr_launch_pair_counts(const uint32_t *bits, const uint32_t *covbits,
 cudaError_t rr_launch_general_break(const uint32_t *covbits, int W32, int N, int mincov, int32_t *breakcol,
                                     cudaStream_t st);
 cudaError_t rr_launch_pack_int8(const uint8_t *cells, const int32_t *perm, int R, int N, int codes, int8_t *xb,
-                                int64_t Kp, cudaStream_t st);
+                                int64_t Kp, int fp4, cudaStream_t st);
 
 cudaError_t rr_launch_scan_bitset(const rr_scan_params &P, int n_sm, cudaStream_t st);
 int rr_bitset_ti(void);

@@ -181,7 +181,7 @@ constexpr int PX_ROWS = 128;
 constexpr int PX_COLS = 64;
 __global__ void __launch_bounds__(256) rr_k_pack_int8(const uint8_t *__restrict__ cells,
                                                        const int32_t *__restrict__ perm, int R, int N, int codes,
-                                                       int8_t *__restrict__ xb, int64_t Kp)
+                                                       int8_t *__restrict__ xb, int64_t Kp, int fp4)
 {
     __shared__ uint8_t tile[PX_ROWS][PX_COLS + 4];
     const int c0 = blockIdx.x * PX_COLS;
@@ -205,10 +205,18 @@ __global__ void __launch_bounds__(256) rr_k_pack_int8(const uint8_t *__restrict_
         const int cl = o / 5, k = o - cl * 5;
         const int col = c0 + cl;
         if (col >= N) continue;
-        uint32_t v = 0;
+        if (!fp4) {
+            uint32_t v = 0;
 #pragma unroll
-        for (int b = 0; b < 4; b++) v |= (tile[lane * 4 + b][cl] == k ? 1u : 0u) << (8 * b);
-        *reinterpret_cast<uint32_t *>(xb + ((size_t)5 * col + k) * Kp + r0 + lane * 4) = v;
+            for (int b = 0; b < 4; b++) v |= (tile[lane * 4 + b][cl] == k ? 1u : 0u) << (8 * b);
+            *reinterpret_cast<uint32_t *>(xb + ((size_t)5 * col + k) * Kp + r0 + lane * 4) = v;
+        } else {
+            // packed e2m1: 1.0 = 0b0010, two reads per byte, row stride Kp/2 bytes
+            uint32_t v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) v |= (tile[lane * 4 + b][cl] == k ? 2u : 0u) << (4 * b);
+            *reinterpret_cast<uint16_t *>(xb + ((size_t)5 * col + k) * (Kp / 2) + r0 / 2 + lane * 2) = (uint16_t)v;
+        }
     }
 }
 
@@ -258,11 +266,11 @@ cudaError_t rr_launch_general_break(const uint32_t *covbits, int W32, int N, int
 }
 
 cudaError_t rr_launch_pack_int8(const uint8_t *cells, const int32_t *perm, int R, int N, int codes, int8_t *xb,
-                                int64_t Kp, cudaStream_t st)
+                                int64_t Kp, int fp4, cudaStream_t st)
 {
     if (N <= 0 || Kp <= 0) return cudaSuccess;
     dim3 grid((N + PX_COLS - 1) / PX_COLS, (unsigned)(Kp / PX_ROWS));
-    rr_k_pack_int8<<<grid, 256, 0, st>>>(cells, perm, R, N, codes, xb, Kp);
+    rr_k_pack_int8<<<grid, 256, 0, st>>>(cells, perm, R, N, codes, xb, Kp, fp4);
     rr_count_launch(1);
     return cudaGetLastError();
 }

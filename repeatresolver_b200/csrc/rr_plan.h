@@ -38,5 +38,5 @@ int rr_umma_row_sites(void);
 int rr_umma_col_sites(void);
 int rr_umma_kblock(void);
 void rr_umma_free(rr_umma_state *s);
-int rr_umma_scan(rr_umma_state *&s, rr_scan_params &P, rr_plan &plan, const uint8_t *d_cells, const int32_t *d_perm,
-                 int codes, int n_sm, cudaStream_t st);
+int rr_umma_scan(rr_umma_state *&s, int fp4, rr_scan_params &P, rr_plan &plan, const uint8_t *d_cells,
+                 const int32_t *d_perm, int codes, int n_sm, cudaStream_t st);

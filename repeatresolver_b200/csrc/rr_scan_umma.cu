@@ -109,6 +109,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 {
     while (!mbar_try_wait(bar, parity)) {}
 }
+// for the single-lane producer / MMA warps: back off so the spin does not steal issue slots from the epilogue
+__device__ __forceinline__ void mbar_wait_sleep(unsigned long long *bar, uint32_t parity, unsigned ns)
+{
+    while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1)
 {
     asm volatile(
@@ -122,15 +127,24 @@ __device__ __forceinline__ void tc_commit(unsigned long long *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], int8 x int8 -> int32
-__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+// D[tmem] (+)= A[smem] * B[smem]; F4 = false: int8 x int8 -> int32, true: e2m1 x e2m1 -> fp32
+template <bool F4>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+    if constexpr (F4)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
 }
 // K-major operand tile in the canonical SWIZZLE_128B layout: rows of 128 B, 8-row atoms of
 // 1024 B (SBO), LBO unused (1), descriptor version 1 (Blackwell), layout type 2.
@@ -144,10 +158,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr)
     d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
     return d;
 }
-// kind::i8 instruction descriptor: D = S32, A = B = unsigned 8 bit, both K-major, M = 128, N = 240
+// instruction descriptor, both operands K-major, M = 128, N = 240:
+//   kind::i8      D = S32 (2), A = B = unsigned 8 bit (0)
+//   kind::f8f6f4  D = F32 (1), A = B = E2M1 (5)
+template <bool F4>
 __device__ __forceinline__ uint32_t make_idesc()
 {
-    return (2u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(UM_N >> 3) << 17) |
+    const uint32_t cfmt = F4 ? 1u : 2u, abfmt = F4 ? 5u : 0u;
+    return (cfmt << 4) | (abfmt << 7) | (abfmt << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(UM_N >> 3) << 17) |
            ((uint32_t)(UM_M >> 4) << 24);
 }
 
@@ -165,12 +183,33 @@ __device__ __forceinline__ int site_sum5(int x, int base_lane)
     return __shfl_sync(0xffffffffu, s, base_lane);
 }
 
-// ALL_SMEM: every ln(n!) argument (<= largest column coverage) is inside the shared-memory table
+extern __shared__ __align__(1024) uint8_t um_smem[];
+
+// ln(n!) for the bounds.  ALL_SMEM: every argument (<= largest column coverage) is inside the table staged in
+// shared memory; otherwise the tail of the table is read from HBM/L2.
 template <bool ALL_SMEM>
+struct um_lnf {
+    uint32_t base;   // shared-window address of the table (computed once; keeps every look-up at IMAD + LDS)
+    int n_smem;
+    const double *gmem;
+    __device__ __forceinline__ double lds(unsigned n) const
+    {
+        double v;
+        asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + 8u * n));
+        return v;
+    }
+    __device__ __forceinline__ double operator()(unsigned n) const
+    {
+        if constexpr (ALL_SMEM) return lds(n);
+        else return n < (unsigned)n_smem ? lds(n) : __ldg(gmem + n);
+    }
+};
+
+template <bool ALL_SMEM, bool F4>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const um_params U)
 {
-    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *smem = um_smem;
     um_smem_tail *T = reinterpret_cast<um_smem_tail *>(smem + UM_TAIL_OFF);
     double *lnf_s = reinterpret_cast<double *>(smem + UM_LNF_OFF);
     const rr_scan_params &P = U.P;
@@ -205,8 +244,9 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (int kb = U.k_lo[ct]; kb < khi; kb++, it++) {
                         const int s = it % UM_STAGES;
                         const uint32_t ph = (it / UM_STAGES) & 1;
-                        mbar_wait(&T->empty[s], ph ^ 1);
-                        mbar_expect_tx(&T->full[s], UM_STAGE_BYTES);
+                        mbar_wait_sleep(&T->empty[s], ph ^ 1, 64);
+                        // the transaction count is in HBM-side bytes: packed e2m1 delivers half the smem footprint
+                        mbar_expect_tx(&T->full[s], F4 ? UM_STAGE_BYTES / 2 : UM_STAGE_BYTES);
                         uint8_t *sa = smem + (size_t)s * UM_STAGE_BYTES;
                         tma_load_2d(sa, &map_a, &T->full[s], kb * UM_KB, un.rt * UM_M);
                         tma_load_2d(sa + UM_A_BYTES, &map_b, &T->full[s], kb * UM_KB, ct * UM_N);
@@ -217,7 +257,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc();
+            const uint32_t idesc = make_idesc<F4>();
             uint32_t it = 0, tile = 0;
             for (int u = blockIdx.x; u < U.n_units; u += gridDim.x) {
                 const um_unit un = U.units[u];
@@ -227,13 +267,13 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (klo >= khi) continue;  // no read covers both tiles: the epilogue uses zeros
                     const int acc = tile & 1;
                     const uint32_t aph = (tile >> 1) & 1;
-                    mbar_wait(&T->tempty[acc], aph ^ 1);
+                    mbar_wait_sleep(&T->tempty[acc], aph ^ 1, 128);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(acc * UM_ACC_STRIDE);
                     for (int kb = klo; kb < khi; kb++, it++) {
                         const int s = it % UM_STAGES;
                         const uint32_t ph = (it / UM_STAGES) & 1;
-                        mbar_wait(&T->full[s], ph);
+                        mbar_wait_sleep(&T->full[s], ph, 32);
                         tc_fence_after();
                         const uint32_t sa = smem_u32(smem + (size_t)s * UM_STAGE_BYTES);
                         const uint64_t adesc = make_smem_desc(sa);
@@ -241,7 +281,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                         for (int k = 0; k < UM_KB / 32; k++) {
                             // advance 32 bytes (one K=32 slice) inside the 128 B swizzle span: +2 in 16 B units
-                            tc_mma_i8(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                            tc_mma<F4>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
                                       (kb > klo || k > 0) ? 1u : 0u);
                         }
                         tc_commit(&T->empty[s]);  // frees the smem stage when these MMAs retire
@@ -265,8 +305,8 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         rr_cand *q1 = T->q1[ew], *q2 = T->q2[ew];
         um_wmeta &M = T->meta[ew];
         int c1n = 0, c2n = 0;
-        rr_lnf_table LT;
-        LT.smem = lnf_s; LT.n_smem = ALL_SMEM ? 0x7fffffff : U.lnf_smem; LT.gmem = P.lnfact;
+        um_lnf<ALL_SMEM> LT;
+        LT.base = smem_u32(lnf_s); LT.n_smem = U.lnf_smem; LT.gmem = P.lnfact;
 
         for (int u = blockIdx.x; u < U.n_units; u += gridDim.x) {
             const um_unit un = U.units[u];
@@ -316,7 +356,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (has_counts) {
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                        for (int b = 0; b < 5; b++) c[b] = (int)v[b];
+                        for (int b = 0; b < 5; b++) c[b] = F4 ? (int)__uint_as_float(v[b]) : (int)v[b];
                         if (t + UM_SUB < t_end) TMEM_LD_8(v, taddr0 + 5 * (t + UM_SUB));
                     } else {
 #pragma unroll
@@ -396,7 +436,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
 // ---- A operand: gather the row sites' groups from xb into 32-row slabs -----------------------
 __global__ void __launch_bounds__(256) rr_k_build_xa(const int8_t *__restrict__ xb, const int32_t *__restrict__ rowsites,
-                                                      int64_t n_rows, int64_t Kp, int8_t *__restrict__ xa)
+                                                      int64_t n_rows, int64_t Kp /* bytes per row */, int8_t *__restrict__ xa)
 {
     const int64_t row = blockIdx.x;
     if (row >= n_rows) return;
@@ -413,7 +453,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t Kp, uint32_t box_rows)
+static int make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t Kp, uint32_t box_rows, bool fp4)
 {
     static PFN_encodeTiled encode = nullptr;
     if (!encode) {
@@ -426,10 +466,12 @@ static int make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t Kp, ui
         encode = (PFN_encodeTiled)fn;
     }
     cuuint64_t dims[2] = {Kp, rows};
-    cuuint64_t strides[1] = {Kp};
+    cuuint64_t strides[1] = {fp4 ? Kp / 2 : Kp};
     cuuint32_t box[2] = {(cuuint32_t)UM_KB, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    // fp4: packed 4-bit elements in HBM, expanded by the TMA unit to 16 elements per 16-byte chunk (8 data + 8
+    // pad bytes) in shared memory - the layout kind::f8f6f4 reads; the box is still 128 bytes wide there
+    CUresult r = encode(map, fp4 ? CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { rr_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return RR_E_CUDA; }
     return RR_OK;
@@ -438,9 +480,9 @@ static int make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t Kp, ui
 }  // namespace
 
 struct rr_umma_state {
-    int8_t *xb = nullptr;
-    int8_t *xa = nullptr;
-    size_t xa_rows_cap = 0;
+    int8_t *xb[2] = {nullptr, nullptr};   // [0] int8, [1] packed e2m1
+    int8_t *xa[2] = {nullptr, nullptr};
+    size_t xa_rows_cap[2] = {0, 0};
     int64_t Kp = 0;
     um_unit *d_units = nullptr;
     size_t units_cap = 0;
@@ -457,7 +499,8 @@ int rr_umma_kblock(void) { return UM_KB; }
 void rr_umma_free(rr_umma_state *s)
 {
     if (!s) return;
-    cudaFree(s->xb); cudaFree(s->xa); cudaFree(s->d_units); cudaFree(s->d_khi); cudaFree(s->d_klo);
+    for (int m = 0; m < 2; m++) { cudaFree(s->xb[m]); cudaFree(s->xa[m]); }
+    cudaFree(s->d_units); cudaFree(s->d_khi); cudaFree(s->d_klo);
     delete s;
 }
 
@@ -485,35 +528,39 @@ static int grow(T **p, size_t *cap, size_t need)
     return RR_OK;
 }
 
-int rr_umma_scan(rr_umma_state *&S, rr_scan_params &P, rr_plan &plan, const uint8_t *d_cells, const int32_t *d_perm,
-                 int codes, int n_sm, cudaStream_t st)
+int rr_umma_scan(rr_umma_state *&S, int fp4, rr_scan_params &P, rr_plan &plan, const uint8_t *d_cells,
+                 const int32_t *d_perm, int codes, int n_sm, cudaStream_t st)
 {
     int rc;
+    const int md = fp4 ? 1 : 0;
     if (!S) {
         S = new rr_umma_state();
         S->Kp = ((int64_t)P.R + UM_KB - 1) / UM_KB * UM_KB;
         if (S->Kp == 0) S->Kp = UM_KB;
+    }
+    const int64_t row_bytes = fp4 ? S->Kp / 2 : S->Kp;
+    if (!S->xb[md]) {
         const size_t rows = (size_t)5 * P.N;
-        if (cudaMalloc((void **)&S->xb, std::max<size_t>(rows * S->Kp, 16)) != cudaSuccess) {
+        if (cudaMalloc((void **)&S->xb[md], std::max<size_t>(rows * row_bytes, 32)) != cudaSuccess) {
             cudaGetLastError();
-            rr_set_error("out of device memory for the int8 operand (%zu bytes)", rows * (size_t)S->Kp);
+            rr_set_error("out of device memory for the B operand (%zu bytes)", rows * (size_t)row_bytes);
             return RR_E_NOMEM;
         }
-        UM_CUDA(rr_launch_pack_int8(d_cells, d_perm, P.R, P.N, codes, S->xb, S->Kp, st));
+        UM_CUDA(rr_launch_pack_int8(d_cells, d_perm, P.R, P.N, codes, S->xb[md], S->Kp, fp4, st));
     }
     // A operand for this plan's row sites
     const size_t xa_rows = (size_t)std::max(plan.n_rowblocks, 1) * UM_M;
-    if (xa_rows > S->xa_rows_cap) {
-        cudaFree(S->xa);
-        S->xa = nullptr;
-        if (cudaMalloc((void **)&S->xa, xa_rows * S->Kp) != cudaSuccess) {
+    if (xa_rows > S->xa_rows_cap[md]) {
+        cudaFree(S->xa[md]);
+        S->xa[md] = nullptr;
+        if (cudaMalloc((void **)&S->xa[md], xa_rows * row_bytes) != cudaSuccess) {
             cudaGetLastError();
-            rr_set_error("out of device memory for the A operand (%zu bytes)", xa_rows * (size_t)S->Kp);
+            rr_set_error("out of device memory for the A operand (%zu bytes)", xa_rows * (size_t)row_bytes);
             return RR_E_NOMEM;
         }
-        S->xa_rows_cap = xa_rows;
+        S->xa_rows_cap[md] = xa_rows;
     }
-    rr_k_build_xa<<<(unsigned)xa_rows, 256, 0, st>>>(S->xb, P.rowsites, (int64_t)xa_rows, S->Kp, S->xa);
+    rr_k_build_xa<<<(unsigned)xa_rows, 256, 0, st>>>(S->xb[md], P.rowsites, (int64_t)xa_rows, row_bytes, S->xa[md]);
     rr_count_launch(1);
     UM_CUDA(cudaGetLastError());
 
@@ -560,12 +607,14 @@ int rr_umma_scan(rr_umma_state *&S, rr_scan_params &P, rr_plan &plan, const uint
     UM_CUDA(cudaStreamSynchronize(st));  // units[] is a local
 
     CUtensorMap map_a, map_b;
-    if ((rc = make_map(&map_a, S->xa, xa_rows, (uint64_t)S->Kp, UM_M))) return rc;
-    if ((rc = make_map(&map_b, S->xb, (uint64_t)5 * P.N, (uint64_t)S->Kp, UM_N))) return rc;
+    if ((rc = make_map(&map_a, S->xa[md], xa_rows, (uint64_t)S->Kp, UM_M, fp4 != 0))) return rc;
+    if ((rc = make_map(&map_b, S->xb[md], (uint64_t)5 * P.N, (uint64_t)S->Kp, UM_N, fp4 != 0))) return rc;
 
     if (!S->attr_set) {
-        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
-        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
+        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
+        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
+        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
+        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
         S->attr_set = true;
     }
     um_params U;
@@ -578,19 +627,26 @@ int rr_umma_scan(rr_umma_state *&S, rr_scan_params &P, rr_plan &plan, const uint
     U.lnf_smem = std::min(std::min(plan.max_cov + 2, P.R + 2), UM_LNF_MAX);
     const size_t smem_bytes = UM_LNF_OFF + (size_t)U.lnf_smem * sizeof(double);
     const bool all_smem = U.lnf_smem >= plan.max_cov + 1;
+    auto launch = [&](int g, const um_params &prm) {
+        if (fp4) {
+            if (all_smem) rr_k_scan_umma<true, true><<<g, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
+            else rr_k_scan_umma<false, true><<<g, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
+        } else {
+            if (all_smem) rr_k_scan_umma<true, false><<<g, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
+            else rr_k_scan_umma<false, false><<<g, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
+        }
+    };
     if (!seed_units.empty()) {
         um_params V = U;
         V.units = S->d_units + units.size();
         V.n_units = (int)seed_units.size();
         const int sgrid = std::min<int>(n_sm, V.n_units);
-        if (all_smem) rr_k_scan_umma<true><<<sgrid, UM_THREADS, smem_bytes, st>>>(map_a, map_b, V);
-        else rr_k_scan_umma<false><<<sgrid, UM_THREADS, smem_bytes, st>>>(map_a, map_b, V);
+        launch(sgrid, V);
         rr_count_launch(1);
         UM_CUDA(cudaGetLastError());
         UM_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(unsigned long long) * 8, st));
     }
-    if (all_smem) rr_k_scan_umma<true><<<grid, UM_THREADS, smem_bytes, st>>>(map_a, map_b, U);
-    else rr_k_scan_umma<false><<<grid, UM_THREADS, smem_bytes, st>>>(map_a, map_b, U);
+    launch(grid, U);
     rr_count_launch(1);
     UM_CUDA(cudaGetLastError());
     return RR_OK;
