@@ -158,6 +158,30 @@ __device__ __forceinline__ bool rr_tier1(const rr_scan_params &P, const LT &T, u
     return !(-RR_LOG10E * lp + 1e-6 < thr);
 }
 
+// tier 0 + 1 without branches (the epilogue evaluates it for every admissible column of a site; straight-line
+// code lets the five columns' look-ups overlap).  meanfac = gr1 / cov (approximate, one per site);
+// returns (need, counted-as-bound-evaluation).
+template <class LT>
+__device__ __forceinline__ bool rr_tier1_flat(const LT &T, unsigned s, unsigned gr1, unsigned gr2, unsigned cov,
+                                              double thr, double lnc3, float meanfac, bool no_prune, bool dbg_skip,
+                                              bool &bound_used)
+{
+    const bool nz = (s >= 1u) & (gr1 != 0u) & (gr2 != 0u);                    // 428-430
+    const bool med = (thr > RR_BOUND_MEDIAN) &
+                     ((unsigned long long)(s + 2u) * cov <= (unsigned long long)gr1 * gr2);
+    const unsigned hi = gr1 < gr2 ? gr1 : gr2;
+    const unsigned sum = gr1 + gr2;
+    const unsigned lo = sum - (sum < cov ? sum : cov);                        // max(0, gr1 + gr2 - cov)
+    unsigned x = (unsigned)(meanfac * (float)gr2) + 1u;
+    x = x > s ? x : s;
+    x = x < hi ? x : hi;
+    x = x > lo ? x : lo;
+    const double lp = ((T(gr2) - T(x)) - T(gr2 - x)) + ((T(cov - gr2) - T(gr1 - x)) - T((cov + x) - sum)) - lnc3;
+    const bool pr = (thr > 0.0) & (-RR_LOG10E * lp + 1e-6 < thr);
+    bound_used = nz & !med;
+    return nz & (no_prune | !(med | pr | dbg_skip));
+}
+
 // tier 2: P[X >= s] >= sum_{x = x0}^{x0+m} pmf(x) for any x0 >= s; the window starts next to the mean
 // (or at s above it) and the term ratios are accumulated in FP32, every factor rounded down.
 template <class LT>

@@ -305,6 +305,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         rr_cand *q1 = T->q1[ew], *q2 = T->q2[ew];
         um_wmeta &M = T->meta[ew];
         int c1n = 0, c2n = 0;
+        const bool no_prune = (P.flags & RR_FLAG_NO_PRUNE) != 0, dbg_skip = (P.flags & 0x200u) != 0;
         um_lnf<ALL_SMEM> LT;
         LT.base = smem_u32(lnf_s); LT.n_smem = U.lnf_smem; LT.gmem = P.lnfact;
 
@@ -371,16 +372,21 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (int b = 0; b < 5; b++) colsum[b] = site_sum5(c[b], base_lane);
                     const int cov = colsum[0] + colsum[1] + colsum[2] + colsum[3] + colsum[4];
                     const double lnc3 = rr_lnchoose_t(LT, (unsigned)cov, (unsigned)rowsum);
-                    // tier 0/1 for the five column groups (independent -> ILP), then the queue pushes
+                    const float meanfac = __fdividef((float)rowsum, (float)max(cov, 1));
+                    // tier 0/1 for the admissible column groups of the site (warp-uniform skip of the others),
+                    // then the queue pushes
                     bool need[5];
 #pragma unroll
                     for (int b = 0; b < 5; b++) {
-                        const int szj = M.szj[w * 5 + b];
                         need[b] = false;
-                        if (pair_site && szj >= 0) {
-                            n_pairs++;
-                            need[b] = rr_tier1(P, LT, (unsigned)c[b], (unsigned)rowsum, (unsigned)colsum[b], (unsigned)cov,
-                                               fmin(thr_i, M.mj[w * 5 + b]), lnc3, n_bound);
+                        if (M.szj[w * 5 + b] >= 0) {  // warp-uniform (817)
+                            bool used;
+                            const bool nd = rr_tier1_flat(LT, (unsigned)c[b], (unsigned)rowsum, (unsigned)colsum[b],
+                                                          (unsigned)cov, fmin(thr_i, M.mj[w * 5 + b]), lnc3, meanfac,
+                                                          no_prune, dbg_skip, used);
+                            need[b] = nd & pair_site;
+                            n_pairs += pair_site;
+                            n_bound += used & pair_site;
                         }
                     }
 #pragma unroll
