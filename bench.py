@@ -36,6 +36,9 @@ WORKLOADS = {
     "Tree_1perc_10000_25": dict(type="Tree", copies=25, coverage=40, repeat_len=10000, diff=0.01, seed=1004),
 }
 MINCOV = 30
+# dram__bytes_read.sum + dram__bytes_write.sum of the scan kernel, per launch, from the committed ncu capture
+# (profiles/); None until measured for that workload
+TRAFFIC = {}
 
 
 def load_peaks():
@@ -47,42 +50,44 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region"""
+    """SM clock and throttle reasons during the timed region, sampled in-process through NVML every
+    100 ms (an `nvidia-smi -lms` child process was measured to delay CUDA API calls of the timed loop)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.sm = []
+        self.sm_max = None
+        self.reasons = set()
         self.stop_flag = threading.Event()
-        self.proc = None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                if self.stop_flag.is_set():
-                    break
-                self.rows.append([x.strip() for x in line.split(",")])
-        except Exception:
-            pass
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                     "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            while not self.stop_flag.is_set():
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for nm, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                self.stop_flag.wait(0.1)
+        except Exception as e:  # NVML missing: report that no sample was taken
+            self.error = repr(e)
 
     def finish(self):
         self.stop_flag.set()
-        if self.proc:
-            self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        reasons = []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for k, nm in enumerate(names):
-            if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows):
-                reasons.append(nm)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        self.join(timeout=2)
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 def make_msa(rr, workload):
@@ -292,16 +297,21 @@ def main():
 
     # ---- roofline of the dominant kernel -------------------------------------------------------
     peaks, peak_src = load_peaks()
-    if variant_used == "umma":
-        # algorithmic work: 2*R int8 ops per pair test; peak: dense INT8 = 2 x the
-        # measured bf16 cuBLAS burst (MEASURED_PEAKS.json has no int8 figure)
+    if variant_used in ("umma", "umma_f4"):
+        # algorithmic work: 2*R 8-bit-rate tensor ops per pair test (the reference touches all
+        # R/64+1 words per intersection); peak: dense INT8/FP8-rate = 2 x the measured bf16 cuBLAS burst
+        # (MEASURED_PEAKS.json has no 8-bit figure; the datasheet ratio is exactly 2)
         algo = 2.0 * R * P_total
         achieved = algo / (k_ms * 1e-3) / 1e12
         peak = 2.0 * peaks["bf16_tflops"] * world
+        ops = ("int8 mul+add (tcgen05 kind::i8), 2*R per pair test" if variant_used == "umma" else
+               "0/1 as e2m1 mul+add at the 8-bit rate (tcgen05 kind::f8f6f4, fp32 accumulate), 2*R per pair test")
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "ops": "int8 mul+add, 2*R per pair test",
+                "traffic": TRAFFIC.get(args.workload), "ops": ops,
                 "peak_source": f"2 x {peak_src} bf16 burst ({peaks['bf16_tflops']} TF/s) per GPU",
-                "executed_frac_of_algorithmic": st["executed_ops"] * world / algo if algo else None}
+                "executed_ops_per_step": st["executed_ops"] * world,
+                "executed_frac_of_algorithmic": st["executed_ops"] * world / algo if algo else None,
+                "executed_tflops": st["executed_ops"] * world / (k_ms * 1e-3) / 1e12}
     else:
         # AND+POPC variant: issue-bound on the POPC pipe (16 lanes/clk/SM); reported against that peak
         words = P_total * ((R + 31) // 32)
@@ -320,7 +330,8 @@ def main():
     line = {"metric": "site-group pair tests/sec (MaxCorrelation)", "value": value, "unit": "pair tests/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "int8->int32 counts, f64 score" if variant_used == "umma" else "u32 bitset counts, f64 score",
+            "dtype": {"umma": "int8->int32 counts, f64 score", "umma_f4": "e2m1(0/1)->f32 counts, f64 score"}.get(
+                variant_used, "u32 bitset counts, f64 score"),
             "data": "synthetic",
             "config": {"workload": args.workload, "rows": R, "cols": N, "mincov": MINCOV, "variant": variant_used,
                        "pair_tests": P_total, "l2": "inputs larger than L2 (packed operands >> 126 MB)",
