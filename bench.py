@@ -84,7 +84,8 @@ class ClockSampler(threading.Thread):
 
     def finish(self):
         self.stop_flag.set()
-        self.join(timeout=2)
+        if self.is_alive():
+            self.join(timeout=2)
         sm = sorted(self.sm)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max,
                 "reasons": sorted(self.reasons), "samples": len(sm)}
@@ -178,6 +179,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     import repeatresolver_b200 as rr
+    from repeatresolver_b200.dist import merge_over_ranks
 
     if args.impl == "reference":
         if rank != 0:
@@ -246,7 +248,8 @@ def main():
         st = pk.scan(mincov=MINCOV, variant=variant, part_index=rank, part_count=world)
     barrier()
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if not os.environ.get("BENCH_NO_SAMPLER"):
+        sampler.start()
     launches0 = rr.launch_count()
     kernel_ms = []
     pk.timer_start()
@@ -275,14 +278,7 @@ def main():
         pk2 = rr.Packed(msa, local_rank)                      # H2D (pinned) + device pack
         pk2.scan(mincov=MINCOV, variant=variant, part_index=rank, part_count=world)
         M, A = pk2.fetch()                                    # D2H of the per-group result
-        if world > 1:                                         # element-wise max over ranks (882-891)
-            Mt = torch.from_numpy(M).cuda()
-            dist.all_reduce(Mt, op=dist.ReduceOp.MAX)
-            At = torch.where(torch.from_numpy(M).cuda() == Mt, torch.from_numpy(A).cuda(),
-                             torch.full((G,), 2 ** 31 - 1, dtype=torch.int32, device="cuda"))
-            At = torch.where(At < 0, torch.full_like(At, 2 ** 31 - 1), At)
-            dist.all_reduce(At, op=dist.ReduceOp.MIN)
-            M = Mt.cpu().numpy()
+        M, A = merge_over_ranks(M, A)                         # element-wise max over ranks (882-891)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         pk2.close()

@@ -16,6 +16,22 @@
 #include "rr_device.cuh"
 #include "rr_plan.h"
 
+#include <chrono>
+static double rr_now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+#define RR_TRACE(tag)                                                                   \
+    do {                                                                                \
+        if (rr_trace_on()) fprintf(stderr, "[rr trace] %-22s %9.3f ms\n", tag, rr_now_ms() - trace_t0); \
+    } while (0)
+static bool rr_trace_on()
+{
+    static int on = -1;
+    if (on < 0) on = getenv("RR_TRACE") ? 1 : 0;
+    return on == 1;
+}
+
 #define RR_CUDA(call)                                                                              \
     do {                                                                                           \
         cudaError_t e__ = (call);                                                                  \
@@ -312,6 +328,7 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
         rr_set_error("rr_scan: part %d of %d", opts->part_index, opts->part_count);
         return RR_E_ARG;
     }
+    const double trace_t0 = rr_now_ms();
     RR_CUDA(cudaSetDevice(pk->device));
     const int R = pk->R, N = pk->N, mincov = opts->mincov;
     cudaEvent_t e0, e1, e2;
@@ -337,6 +354,7 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
         rc = rr_breakcols_from_spans(pk->h_start.data(), pk->h_end.data(), R, N, mincov, breakcol.data());
         if (rc) return rc;
     }
+    RR_TRACE("breakcols");
     const int ti = variant == RR_VARIANT_BITSET ? rr_bitset_ti() : rr_umma_row_sites();
     const int tj = variant == RR_VARIANT_BITSET ? rr_bitset_tj() : rr_umma_col_sites();
     rr_plan_build(plan, R, N, mincov, pk->h_gsize.data(), pk->h_coverage.data(), breakcol.data(),
@@ -344,6 +362,7 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
                   pk->contiguous && !general ? pk->h_end.data() : nullptr, ti, tj, variant == RR_VARIANT_BITSET ? 32 : rr_umma_kblock(),
                   opts->part_index, opts->part_count);
 
+    RR_TRACE("plan");
     if ((rc = upload(&sb.rowok, plan.rowok, pk->st))) return rc;
     if ((rc = upload(&sb.colok, plan.colok, pk->st))) return rc;
     if (!general && (rc = upload(&sb.breakcol, breakcol, pk->st))) return rc;
@@ -362,6 +381,7 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
         RR_CUDA(cudaStreamSynchronize(pk->st));  // init[] goes out of scope
     }
 
+    RR_TRACE("uploads+init");
     rr_scan_params P;
     memset(&P, 0, sizeof P);
     P.R = R; P.N = N; P.W32 = pk->W32; P.mincov = mincov; P.flags = opts->flags;
@@ -381,11 +401,13 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
             if (rc) return rc;
         }
     }
+    RR_TRACE("launched");
     RR_CUDA(cudaEventRecord(e2, pk->st));
     unsigned long long counters[8];
     RR_CUDA(cudaMemcpyAsync(counters, pk->d_counters, sizeof counters, cudaMemcpyDeviceToHost, pk->st));
     RR_CUDA(cudaStreamSynchronize(pk->st));
     RR_CUDA(cudaGetLastError());
+    RR_TRACE("kernels done");
     pk->have_result = true;
     executed = plan.executed_ops;
 

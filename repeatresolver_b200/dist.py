@@ -1,0 +1,36 @@
+"""Multi-process plumbing for the scan: one process per GPU (torch.distributed, NCCL on GPUs,
+gloo on CPU for tests).  The hot path has no collective: every rank holds the whole packed MSA
+and scans its own pair-balanced range of row sites (rr_scan part_index/part_count); the only
+exchange is the final element-wise max of the per-group results, the multi-process form of the
+reference's thread merge (MaxCorrelation.c:882-891).
+"""
+import numpy as np
+
+INT_MAX = 2 ** 31 - 1
+
+
+def merge_over_ranks(M, A, device=None):
+    """Element-wise max of the per-rank maxima M[5N] (float64); among ranks attaining the max the
+    smallest partner id wins (A[5N] int32, -1 = none).  Works on any initialised process group;
+    returns numpy arrays.  With no process group (single process) it returns its inputs."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return M, A
+    dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
+    Mt = torch.from_numpy(np.ascontiguousarray(M)).to(dev)
+    At = torch.from_numpy(np.ascontiguousarray(A)).to(dev)
+    Mg = Mt.clone()
+    dist.all_reduce(Mg, op=dist.ReduceOp.MAX)
+    cand = torch.where((Mt == Mg) & (At >= 0) & (Mg > 0), At, torch.full_like(At, INT_MAX))
+    dist.all_reduce(cand, op=dist.ReduceOp.MIN)
+    cand = torch.where(cand == INT_MAX, torch.full_like(cand, -1), cand)
+    return Mg.cpu().numpy(), cand.cpu().numpy()
+
+
+def rank_part():
+    """(part_index, part_count) of this process"""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
