@@ -182,6 +182,31 @@ __device__ __forceinline__ bool rr_tier1_flat(const LT &T, unsigned s, unsigned 
     return nz & (no_prune | !(med | pr | dbg_skip));
 }
 
+// The same test in FP32 on a float copy of the ln n! table (half the shared-memory bytes, no FP64 issue slots).
+// Every rounding is covered by `margin` (log10 units): 7 table entries rounded to float plus 6 float additions
+// of values <= ln(maxcov!) give an absolute error below 8 * 2^-23 * ln(maxcov!) in ln units.  thr is the
+// threshold rounded DOWN to float; meanfac = gr1 / cov (approximate).  LTF: callable float(unsigned n).
+template <class LTF>
+__device__ __forceinline__ bool rr_tier1_f32(const LTF &T, unsigned s, unsigned gr1, unsigned gr2, unsigned cov,
+                                             float thr, float lnc3, float meanfac, float margin, bool no_prune,
+                                             bool dbg_skip)
+{
+    const bool nz = (s >= 1u) & (gr1 != 0u) & (gr2 != 0u);                    // 428-430
+    const float m = meanfac * (float)gr2;                                    // ~ mean of the hypergeometric
+    // s + 2 <= mean  =>  score <= log10 2 (median bound); the 0.9999 covers the approximate division
+    const bool med = (thr > (float)RR_BOUND_MEDIAN + 1e-6f) & ((float)(s + 2u) <= m * 0.9999f);
+    const unsigned hi = gr1 < gr2 ? gr1 : gr2;
+    const unsigned sum = gr1 + gr2;
+    const unsigned lo = sum - (sum < cov ? sum : cov);                        // max(0, gr1 + gr2 - cov)
+    unsigned x = (unsigned)m + 1u;
+    x = x > s ? x : s;
+    x = x < hi ? x : hi;
+    x = x > lo ? x : lo;
+    const float lp = ((T(gr2) - T(x)) - T(gr2 - x)) + ((T(cov - gr2) - T(gr1 - x)) - T((cov + x) - sum)) - lnc3;
+    const bool pr = (thr > 0.0f) & (-(float)RR_LOG10E * lp + margin < thr);
+    return nz & (no_prune | !(med | pr | dbg_skip));
+}
+
 // tier 2: P[X >= s] >= sum_{x = x0}^{x0+m} pmf(x) for any x0 >= s; the window starts next to the mean
 // (or at s above it) and the term ratios are accumulated in FP32, every factor rounded down.
 template <class LT>

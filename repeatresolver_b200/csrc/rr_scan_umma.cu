@@ -50,7 +50,7 @@ constexpr int UM_TMEM_COLS = 512;
 constexpr int UM_ACC_STRIDE = 256;               // TMEM columns between the two accumulators
 
 struct um_wmeta {                                 // per epilogue warp: metadata of its column groups in the tile
-    double mj[UM_WSITES * 5];                     // running maxima
+    float mj[UM_WSITES * 5];                      // running maxima, rounded down to float (thresholds only)
     int szj[UM_WSITES * 5];                       // Groupsizearray, or -1 when not admissible (817)
 };
 
@@ -65,7 +65,7 @@ struct um_smem_tail {
 constexpr size_t UM_TAIL_OFF = (size_t)UM_STAGES * UM_STAGE_BYTES;
 constexpr size_t UM_LNF_OFF = (UM_TAIL_OFF + sizeof(um_smem_tail) + 15) & ~(size_t)15;
 constexpr size_t UM_SMEM_MAX = 227 * 1024;
-constexpr int UM_LNF_MAX = (int)((UM_SMEM_MAX - UM_LNF_OFF) / sizeof(double));  // ln(n!) entries that fit
+constexpr int UM_LNF_MAX = (int)((UM_SMEM_MAX - UM_LNF_OFF) / sizeof(float));  // ln(n!) float entries that fit
 
 struct um_unit { int32_t rt, ct0, ct1; };         // row tile, column tiles [ct0, ct1)
 
@@ -75,7 +75,8 @@ struct um_params {
     int n_units;
     const int32_t *k_hi;      // [row tiles]   exclusive K-block bound
     const int32_t *k_lo;      // [column tiles] inclusive K-block bound
-    int lnf_smem;             // ln(n!) entries staged in shared memory
+    int lnf_smem;             // ln(n!) entries (as float) staged in shared memory
+    float t1_margin;          // FP32 tier-1 rounding margin, log10 units (see rr_tier1_f32)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -189,19 +190,19 @@ extern __shared__ __align__(1024) uint8_t um_smem[];
 // shared memory; otherwise the tail of the table is read from HBM/L2.
 template <bool ALL_SMEM>
 struct um_lnf {
-    uint32_t base;   // shared-window address of the table (computed once; keeps every look-up at IMAD + LDS)
+    uint32_t base;   // shared-window address of the float table (computed once: every look-up is LEA + LDS)
     int n_smem;
     const double *gmem;
-    __device__ __forceinline__ double lds(unsigned n) const
+    __device__ __forceinline__ float lds(unsigned n) const
     {
-        double v;
-        asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + 8u * n));
+        float v;
+        asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + 4u * n));
         return v;
     }
-    __device__ __forceinline__ double operator()(unsigned n) const
+    __device__ __forceinline__ float operator()(unsigned n) const
     {
         if constexpr (ALL_SMEM) return lds(n);
-        else return n < (unsigned)n_smem ? lds(n) : __ldg(gmem + n);
+        else return n < (unsigned)n_smem ? lds(n) : (float)__ldg(gmem + n);
     }
 };
 
@@ -211,7 +212,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 {
     uint8_t *smem = um_smem;
     um_smem_tail *T = reinterpret_cast<um_smem_tail *>(smem + UM_TAIL_OFF);
-    double *lnf_s = reinterpret_cast<double *>(smem + UM_LNF_OFF);
+    float *lnf_s = reinterpret_cast<float *>(smem + UM_LNF_OFF);
     const rr_scan_params &P = U.P;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -225,7 +226,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&T->tmem_base)), "n"(UM_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int n = threadIdx.x; n < U.lnf_smem; n += UM_THREADS) lnf_s[n] = U.P.lnfact[n];
+    for (int n = threadIdx.x; n < U.lnf_smem; n += UM_THREADS) lnf_s[n] = (float)U.P.lnfact[n];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -306,8 +307,11 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         um_wmeta &M = T->meta[ew];
         int c1n = 0, c2n = 0;
         const bool no_prune = (P.flags & RR_FLAG_NO_PRUNE) != 0, dbg_skip = (P.flags & 0x200u) != 0;
-        um_lnf<ALL_SMEM> LT;
+        um_lnf<ALL_SMEM> LT;     // float table, tier 1
         LT.base = smem_u32(lnf_s); LT.n_smem = U.lnf_smem; LT.gmem = P.lnfact;
+        rr_lnf_global LG;        // double table in HBM/L2, tier 2 (rare, evaluated 32 at a time)
+        LG.gmem = P.lnfact;
+        const float margin = U.t1_margin;
 
         for (int u = blockIdx.x; u < U.n_units; u += gridDim.x) {
             const um_unit un = U.units[u];
@@ -318,7 +322,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int gi = ii >= 0 ? 5 * ii + a : -1;
             const bool row_ok = gi >= 0 && P.rowok[gi] != 0;
             const int brk = ii >= 0 ? min(P.breakcol[ii], P.N) : 0;
-            double thr_i = 0.0;                    // running max of row group i (refreshed from HBM)
+            float thr_i = 0.0f;                    // running max of row group i, rounded down (refreshed from HBM)
 
             for (int ct = un.ct0; ct < un.ct1; ct++) {
                 const int klo = U.k_lo[ct];
@@ -330,12 +334,12 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const int w = e / 5, b = e - w * 5;
                     const int j = 5 * (jsite0 + sub + w * UM_SUB) + b;
                     int sz = -1;
-                    double m = 0.0;
-                    if (j < 5 * P.N && P.colok[j]) { sz = P.gsize[j]; m = rr_best_value(P.best + j); }
+                    float m = 0.0f;
+                    if (j < 5 * P.N && P.colok[j]) { sz = P.gsize[j]; m = __double2float_rd(rr_best_value(P.best + j)); }
                     M.szj[e] = sz;
                     M.mj[e] = m;
                 }
-                if (row_ok) thr_i = rr_best_value(P.best + gi);
+                if (row_ok) thr_i = __double2float_rd(rr_best_value(P.best + gi));
                 __syncwarp();
 
                 int acc = 0;
@@ -371,7 +375,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                     for (int b = 0; b < 5; b++) colsum[b] = site_sum5(c[b], base_lane);
                     const int cov = colsum[0] + colsum[1] + colsum[2] + colsum[3] + colsum[4];
-                    const double lnc3 = rr_lnchoose_t(LT, (unsigned)cov, (unsigned)rowsum);
+                    const float lnc3 = (LT((unsigned)cov) - LT((unsigned)rowsum)) - LT((unsigned)(cov - rowsum));
                     const float meanfac = __fdividef((float)rowsum, (float)max(cov, 1));
                     // tier 0/1 for the admissible column groups of the site (warp-uniform skip of the others),
                     // then the queue pushes
@@ -380,13 +384,11 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (int b = 0; b < 5; b++) {
                         need[b] = false;
                         if (M.szj[w * 5 + b] >= 0) {  // warp-uniform (817)
-                            bool used;
-                            const bool nd = rr_tier1_flat(LT, (unsigned)c[b], (unsigned)rowsum, (unsigned)colsum[b],
-                                                          (unsigned)cov, fmin(thr_i, M.mj[w * 5 + b]), lnc3, meanfac,
-                                                          no_prune, dbg_skip, used);
+                            const bool nd = rr_tier1_f32(LT, (unsigned)c[b], (unsigned)rowsum, (unsigned)colsum[b],
+                                                         (unsigned)cov, fminf(thr_i, M.mj[w * 5 + b]), lnc3, meanfac,
+                                                         margin, no_prune, dbg_skip);
                             need[b] = nd & pair_site;
                             n_pairs += pair_site;
-                            n_bound += used & pair_site;
                         }
                     }
 #pragma unroll
@@ -396,11 +398,12 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         cand.cov = (uint32_t)cov; cand.gi = gi; cand.gj = 5 * jj + b;
                         rr_queue_push(q1, c1n, need[b], cand, lane);
                         if (c1n >= 32) {
-                            rr_drain_tier2(P, LT, q1, c1n, q2, c2n, lane, n_tier2, n_exact, false);
+                            rr_drain_tier2(P, LG, q1, c1n, q2, c2n, lane, n_tier2, n_exact, false);
                             // pick up what this and the other warps / CTAs have found meanwhile
-                            if (row_ok) thr_i = rr_best_value(P.best + gi);
+                            if (row_ok) thr_i = __double2float_rd(rr_best_value(P.best + gi));
                             for (int e = lane; e < UM_WSITES * 5; e += 32)
-                                if (M.szj[e] >= 0) M.mj[e] = rr_best_value(P.best + 5 * (jsite0 + sub + (e / 5) * UM_SUB) + (e % 5));
+                                if (M.szj[e] >= 0)
+                                    M.mj[e] = __double2float_rd(rr_best_value(P.best + 5 * (jsite0 + sub + (e / 5) * UM_SUB) + (e % 5)));
                             __syncwarp();
                         }
                     }
@@ -412,7 +415,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     tile++;
                 }
             }
-            rr_drain_tier2(P, LT, q1, c1n, q2, c2n, lane, n_tier2, n_exact, true);
+            rr_drain_tier2(P, LG, q1, c1n, q2, c2n, lane, n_tier2, n_exact, true);
         }
 
         unsigned long long v0 = n_pairs, v1 = n_exact, v2 = n_bound, v3 = n_units, v4 = n_tier2;
@@ -631,7 +634,10 @@ int rr_umma_scan(rr_umma_state *&S, int fp4, rr_scan_params &P, rr_plan &plan, c
     U.k_lo = S->d_klo;
     const int grid = std::min<int>(n_sm, (int)units.size());
     U.lnf_smem = std::min(std::min(plan.max_cov + 2, P.R + 2), UM_LNF_MAX);
-    const size_t smem_bytes = UM_LNF_OFF + (size_t)U.lnf_smem * sizeof(double);
+    const size_t smem_bytes = UM_LNF_OFF + (size_t)U.lnf_smem * sizeof(float);
+    // FP32 tier-1 margin: 8 roundings of magnitude <= 2^-24 * ln(maxcov!) each (7 table entries, 6 additions,
+    // generously doubled), in log10 units, plus the 1e-6 of the double-precision version
+    U.t1_margin = (float)(16.0 * 5.9604645e-8 * rr_lnfact((unsigned)std::max(plan.max_cov, 1)) * 0.4342944819 + 2e-6);
     const bool all_smem = U.lnf_smem >= plan.max_cov + 1;
     auto launch = [&](int g, const um_params &prm) {
         if (fp4) {
