@@ -118,6 +118,29 @@ extern "C" int rr_below_median_host(uint32_t s, uint32_t gr1, uint32_t gr2, uint
 // ---------------------------------------------------------------------------------------
 // packed MSA
 // ---------------------------------------------------------------------------------------
+struct scan_buffers {
+    uint8_t *rowok = nullptr, *colok = nullptr;
+    int32_t *breakcol = nullptr, *rowsites = nullptr, *unit_cb0 = nullptr, *word_hi = nullptr, *word_lo = nullptr;
+    int64_t *unit_prefix = nullptr;
+    void release()
+    {
+        cudaFree(rowok); cudaFree(colok); cudaFree(breakcol); cudaFree(rowsites); cudaFree(unit_cb0);
+        cudaFree(word_hi); cudaFree(word_lo); cudaFree(unit_prefix);
+        rowok = colok = nullptr; breakcol = rowsites = unit_cb0 = word_hi = word_lo = nullptr; unit_prefix = nullptr;
+    }
+    ~scan_buffers() { release(); }
+};
+
+// the host plan and its device copies are kept between scans of the same (mincov, variant, part, break mode)
+struct scan_cache {
+    bool valid = false;
+    int mincov = 0, variant = 0, part_index = 0, part_count = 0;
+    bool general = false;
+    uint64_t plan_id = 0;
+    rr_plan plan;
+    scan_buffers sb;
+};
+
 struct rr_packed {
     int device = 0, n_sm = 148;
     int R = 0, N = 0, W32 = 0, codes = 0;
@@ -136,6 +159,8 @@ struct rr_packed {
     bool have_result = false;
     rr_umma_state *umma = nullptr;  // int8 operands + tensor maps, built on first use
     cudaEvent_t t0 = nullptr, t1 = nullptr;
+    scan_cache cache;
+    uint64_t next_plan_id = 1;
 };
 
 template <typename T>
@@ -310,16 +335,6 @@ static int upload(T **d, const std::vector<T> &h, cudaStream_t st)
     return RR_OK;
 }
 
-struct scan_buffers {
-    uint8_t *rowok = nullptr, *colok = nullptr;
-    int32_t *breakcol = nullptr, *rowsites = nullptr, *unit_cb0 = nullptr, *word_hi = nullptr, *word_lo = nullptr;
-    int64_t *unit_prefix = nullptr;
-    ~scan_buffers()
-    {
-        cudaFree(rowok); cudaFree(colok); cudaFree(breakcol); cudaFree(rowsites); cudaFree(unit_cb0);
-        cudaFree(word_hi); cudaFree(word_lo); cudaFree(unit_prefix);
-    }
-};
 
 extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *stats)
 {
@@ -339,49 +354,54 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
     if (variant == RR_VARIANT_AUTO) variant = rr_umma_available() ? RR_VARIANT_UMMA_F4 : RR_VARIANT_BITSET;
     if (variant != RR_VARIANT_BITSET && variant != RR_VARIANT_UMMA && variant != RR_VARIANT_UMMA_F4) { rr_set_error("unknown variant %d", variant); return RR_E_ARG; }
 
-    // ---- host plan: filters, first-break columns, tiles, partition (O(N)) ------------------
-    rr_plan plan;
-    std::vector<int32_t> breakcol(N);
+    // ---- host plan: filters, first-break columns, tiles, partition (O(N)); cached between scans ----
     const bool general = !pk->contiguous || (opts->flags & RR_FLAG_GENERAL_BREAK);
-    scan_buffers sb;
+    scan_cache &C = pk->cache;
     int rc;
-    if (general) {
-        if ((rc = dev_alloc(&sb.breakcol, (size_t)N))) return rc;
-        RR_CUDA(rr_launch_general_break(pk->d_covbits, pk->W32, N, mincov, sb.breakcol, pk->st));
-        if (N) RR_CUDA(cudaMemcpyAsync(breakcol.data(), sb.breakcol, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, pk->st));
-        RR_CUDA(cudaStreamSynchronize(pk->st));
-    } else {
-        rc = rr_breakcols_from_spans(pk->h_start.data(), pk->h_end.data(), R, N, mincov, breakcol.data());
-        if (rc) return rc;
+    if (!(C.valid && C.mincov == mincov && C.variant == variant && C.part_index == opts->part_index &&
+          C.part_count == opts->part_count && C.general == general)) {
+        C.valid = false;
+        C.sb.release();
+        C.plan = rr_plan();
+        std::vector<int32_t> breakcol(N);
+        if (general) {
+            if ((rc = dev_alloc(&C.sb.breakcol, (size_t)N))) return rc;
+            RR_CUDA(rr_launch_general_break(pk->d_covbits, pk->W32, N, mincov, C.sb.breakcol, pk->st));
+            if (N) RR_CUDA(cudaMemcpyAsync(breakcol.data(), C.sb.breakcol, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, pk->st));
+            RR_CUDA(cudaStreamSynchronize(pk->st));
+        } else {
+            rc = rr_breakcols_from_spans(pk->h_start.data(), pk->h_end.data(), R, N, mincov, breakcol.data());
+            if (rc) return rc;
+        }
+        RR_TRACE("breakcols");
+        const int ti = variant == RR_VARIANT_BITSET ? rr_bitset_ti() : rr_umma_row_sites();
+        const int tj = variant == RR_VARIANT_BITSET ? rr_bitset_tj() : rr_umma_col_sites();
+        rr_plan_build(C.plan, R, N, mincov, pk->h_gsize.data(), pk->h_coverage.data(), breakcol.data(),
+                      pk->contiguous && !general ? pk->h_start.data() : nullptr,
+                      pk->contiguous && !general ? pk->h_end.data() : nullptr, ti, tj, variant == RR_VARIANT_BITSET ? 32 : rr_umma_kblock(),
+                      variant == RR_VARIANT_BITSET ? 8 : 300, opts->part_index, opts->part_count);
+        RR_TRACE("plan");
+        if ((rc = upload(&C.sb.rowok, C.plan.rowok, pk->st))) return rc;
+        if ((rc = upload(&C.sb.colok, C.plan.colok, pk->st))) return rc;
+        if (!general && (rc = upload(&C.sb.breakcol, breakcol, pk->st))) return rc;
+        if ((rc = upload(&C.sb.rowsites, C.plan.rowsites, pk->st))) return rc;
+        if ((rc = upload(&C.sb.unit_prefix, C.plan.unit_prefix, pk->st))) return rc;
+        if ((rc = upload(&C.sb.unit_cb0, C.plan.unit_cb0, pk->st))) return rc;
+        if ((rc = upload(&C.sb.word_hi, C.plan.k_hi, pk->st))) return rc;
+        if ((rc = upload(&C.sb.word_lo, C.plan.k_lo, pk->st))) return rc;
+        RR_CUDA(cudaStreamSynchronize(pk->st));  // the host vectors above are locals
+        C.mincov = mincov; C.variant = variant; C.part_index = opts->part_index; C.part_count = opts->part_count;
+        C.general = general; C.plan_id = pk->next_plan_id++;
+        C.valid = true;
     }
-    RR_TRACE("breakcols");
-    const int ti = variant == RR_VARIANT_BITSET ? rr_bitset_ti() : rr_umma_row_sites();
-    const int tj = variant == RR_VARIANT_BITSET ? rr_bitset_tj() : rr_umma_col_sites();
-    rr_plan_build(plan, R, N, mincov, pk->h_gsize.data(), pk->h_coverage.data(), breakcol.data(),
-                  pk->contiguous && !general ? pk->h_start.data() : nullptr,
-                  pk->contiguous && !general ? pk->h_end.data() : nullptr, ti, tj, variant == RR_VARIANT_BITSET ? 32 : rr_umma_kblock(),
-                  opts->part_index, opts->part_count);
-
-    RR_TRACE("plan");
-    if ((rc = upload(&sb.rowok, plan.rowok, pk->st))) return rc;
-    if ((rc = upload(&sb.colok, plan.colok, pk->st))) return rc;
-    if (!general && (rc = upload(&sb.breakcol, breakcol, pk->st))) return rc;
-    if ((rc = upload(&sb.rowsites, plan.rowsites, pk->st))) return rc;
-    if ((rc = upload(&sb.unit_prefix, plan.unit_prefix, pk->st))) return rc;
-    if ((rc = upload(&sb.unit_cb0, plan.unit_cb0, pk->st))) return rc;
-    if ((rc = upload(&sb.word_hi, plan.k_hi, pk->st))) return rc;
-    if ((rc = upload(&sb.word_lo, plan.k_lo, pk->st))) return rc;
+    rr_plan &plan = C.plan;
+    scan_buffers &sb = C.sb;
 
     // running maxima: 0.0 / no partner
-    {
-        std::vector<rr_best_t> init((size_t)5 * N);
-        for (auto &b : init) { b.z = 0ull; b.p = ~0ull; }
-        if (!init.empty()) RR_CUDA(cudaMemcpyAsync(pk->d_best, init.data(), sizeof(rr_best_t) * init.size(), cudaMemcpyHostToDevice, pk->st));
-        RR_CUDA(cudaMemsetAsync(pk->d_counters, 0, sizeof(unsigned long long) * 8, pk->st));
-        RR_CUDA(cudaStreamSynchronize(pk->st));  // init[] goes out of scope
-    }
-
+    RR_CUDA(rr_launch_init_best(pk->d_best, (int64_t)5 * N, pk->st));
+    RR_CUDA(cudaMemsetAsync(pk->d_counters, 0, sizeof(unsigned long long) * 8, pk->st));
     RR_TRACE("uploads+init");
+
     rr_scan_params P;
     memset(&P, 0, sizeof P);
     P.R = R; P.N = N; P.W32 = pk->W32; P.mincov = mincov; P.flags = opts->flags;
@@ -397,7 +417,7 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
         if (variant == RR_VARIANT_BITSET) {
             RR_CUDA(rr_launch_scan_bitset(P, pk->n_sm, pk->st));
         } else {
-            rc = rr_umma_scan(pk->umma, variant == RR_VARIANT_UMMA_F4, P, plan, pk->d_cells, pk->d_perm, pk->codes, pk->n_sm, pk->st);
+            rc = rr_umma_scan(pk->umma, variant == RR_VARIANT_UMMA_F4, C.plan_id, P, plan, pk->d_cells, pk->d_perm, pk->codes, pk->n_sm, pk->st);
             if (rc) return rc;
         }
     }

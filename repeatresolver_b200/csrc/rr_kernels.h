@@ -20,6 +20,8 @@ cudaError_t rr_launch_general_break(const uint32_t *covbits, int W32, int N, int
 cudaError_t rr_launch_pack_int8(const uint8_t *cells, const int32_t *perm, int R, int N, int codes, int8_t *xb,
                                 int64_t Kp, int fp4, cudaStream_t st);
 
+struct rr_best_t;
+cudaError_t rr_launch_init_best(rr_best_t *best, int64_t n, cudaStream_t st);
 cudaError_t rr_launch_scan_bitset(const rr_scan_params &P, int n_sm, cudaStream_t st);
 int rr_bitset_ti(void);
 int rr_bitset_tj(void);

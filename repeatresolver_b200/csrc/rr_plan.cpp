@@ -5,7 +5,7 @@
 
 void rr_plan_build(rr_plan &plan, int R, int N, int mincov, const int32_t *gsize, const int32_t *coverage,
                    const int32_t *breakcol, const int32_t *start, const int32_t *end, int ti, int tj, int kunit,
-                   int part_index, int part_count)
+                   int tile_cost, int part_index, int part_count)
 {
     const int q = mincov / 4;  // integer division, MaxCorrelation.c:802/817
     const size_t G = (size_t)5 * N;
@@ -84,15 +84,25 @@ void rr_plan_build(rr_plan &plan, int R, int N, int mincov, const int32_t *gsize
         }
     }
 
-    // pair-balanced contiguous partition of the row blocks
+    // cost-balanced contiguous partition of the row blocks: a tile costs tile_cost (the epilogue walks the whole
+    // tile) plus one per contributing k-unit (the contraction); measured on B200
+    std::vector<int64_t> rb_cost(std::max(plan.n_rowblocks, 1), 0);
+    int64_t total_cost = 0;
+    for (int rb = 0; rb < plan.n_rowblocks; rb++) {
+        const int ncb = (int)(plan.unit_prefix[rb + 1] - plan.unit_prefix[rb]);
+        int64_t c = 0;
+        for (int k = 0; k < ncb; k++) c += tile_cost + std::max(0, plan.k_hi[rb] - plan.k_lo[plan.unit_cb0[rb] + k]);
+        rb_cost[rb] = c;
+        total_cost += c;
+    }
     std::vector<int> cut((size_t)part_count + 1, plan.n_rowblocks);
     cut[0] = 0;
     {
         int64_t acc = 0;
         int p = 1;
         for (int rb = 0; rb < plan.n_rowblocks && p < part_count; rb++) {
-            acc += plan.rb_pairs[rb];
-            while (p < part_count && acc * part_count >= plan.total_pairs * (int64_t)p) cut[p++] = rb + 1;
+            acc += rb_cost[rb];
+            while (p < part_count && acc * part_count >= total_cost * (int64_t)p) cut[p++] = rb + 1;
         }
     }
     plan.rb_lo = cut[part_index];

@@ -24,11 +24,12 @@ struct rr_plan {
 };
 
 // ti / tj: row / column sites per tile; kunit: rows (reads) per contraction unit
-// (32 = one u32 word for the bitset kernel, the K block for the tcgen05 kernel).
+// (32 = one u32 word for the bitset kernel, the K block for the tcgen05 kernel); tile_cost: cost of a tile's
+// epilogue in k-unit equivalents (multi-GPU balance).
 // start/end: spans in rank order, or NULL when rows are not single spans (no skipping).
 void rr_plan_build(rr_plan &plan, int R, int N, int mincov, const int32_t *gsize, const int32_t *coverage,
                    const int32_t *breakcol, const int32_t *start, const int32_t *end, int ti, int tj, int kunit,
-                   int part_index, int part_count);
+                   int tile_cost, int part_index, int part_count);
 
 // ---- tcgen05 variant hooks (rr_scan_umma.cu) ---------------------------------------------
 struct rr_umma_state;
@@ -38,5 +39,5 @@ int rr_umma_row_sites(void);
 int rr_umma_col_sites(void);
 int rr_umma_kblock(void);
 void rr_umma_free(rr_umma_state *s);
-int rr_umma_scan(rr_umma_state *&s, int fp4, rr_scan_params &P, rr_plan &plan, const uint8_t *d_cells,
+int rr_umma_scan(rr_umma_state *&s, int fp4, uint64_t plan_id, rr_scan_params &P, rr_plan &plan, const uint8_t *d_cells,
                  const int32_t *d_perm, int codes, int n_sm, cudaStream_t st);

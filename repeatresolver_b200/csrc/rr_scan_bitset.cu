@@ -140,6 +140,20 @@ __global__ void __launch_bounds__(BS_TI * 32, 2) rr_k_scan_bitset(const rr_scan_
     }
 }
 
+__global__ void rr_k_init_best(rr_best_t *best, int64_t n)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n) { best[g].z = 0ull; best[g].p = ~0ull; }
+}
+
+cudaError_t rr_launch_init_best(rr_best_t *best, int64_t n, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    rr_k_init_best<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(best, n);
+    rr_count_launch(1);
+    return cudaGetLastError();
+}
+
 cudaError_t rr_launch_scan_bitset(const rr_scan_params &P, int n_sm, cudaStream_t st)
 {
     const int64_t units = 0;  // computed by the kernel from the prefix array

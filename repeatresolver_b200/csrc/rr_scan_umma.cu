@@ -498,6 +498,12 @@ struct rr_umma_state {
     int32_t *d_khi = nullptr, *d_klo = nullptr;
     size_t khi_cap = 0, klo_cap = 0;
     bool attr_set = false;
+    // what was built for the plan last seen (reused while plan_id and operand coding stay the same)
+    uint64_t built_plan_id = 0;
+    int built_md = -1;
+    int n_units = 0, n_seed = 0;
+    int64_t executed_ops = 0;
+    CUtensorMap map_a, map_b;
 };
 
 int rr_umma_available(void) { return 1; }
@@ -537,7 +543,7 @@ static int grow(T **p, size_t *cap, size_t need)
     return RR_OK;
 }
 
-int rr_umma_scan(rr_umma_state *&S, int fp4, rr_scan_params &P, rr_plan &plan, const uint8_t *d_cells,
+int rr_umma_scan(rr_umma_state *&S, int fp4, uint64_t plan_id, rr_scan_params &P, rr_plan &plan, const uint8_t *d_cells,
                  const int32_t *d_perm, int codes, int n_sm, cudaStream_t st)
 {
     int rc;
@@ -557,67 +563,75 @@ int rr_umma_scan(rr_umma_state *&S, int fp4, rr_scan_params &P, rr_plan &plan, c
         }
         UM_CUDA(rr_launch_pack_int8(d_cells, d_perm, P.R, P.N, codes, S->xb[md], S->Kp, fp4, st));
     }
-    // A operand for this plan's row sites
-    const size_t xa_rows = (size_t)std::max(plan.n_rowblocks, 1) * UM_M;
-    if (xa_rows > S->xa_rows_cap[md]) {
-        cudaFree(S->xa[md]);
-        S->xa[md] = nullptr;
-        if (cudaMalloc((void **)&S->xa[md], xa_rows * row_bytes) != cudaSuccess) {
-            cudaGetLastError();
-            rr_set_error("out of device memory for the A operand (%zu bytes)", xa_rows * (size_t)row_bytes);
-            return RR_E_NOMEM;
+    const bool seeding = !(P.flags & (RR_FLAG_NO_PRUNE | 0x1000u));
+    if (S->built_plan_id != plan_id || S->built_md != md) {
+        // A operand for this plan's row sites
+        const size_t xa_rows = (size_t)std::max(plan.n_rowblocks, 1) * UM_M;
+        if (xa_rows > S->xa_rows_cap[md]) {
+            cudaFree(S->xa[md]);
+            S->xa[md] = nullptr;
+            if (cudaMalloc((void **)&S->xa[md], xa_rows * row_bytes) != cudaSuccess) {
+                cudaGetLastError();
+                rr_set_error("out of device memory for the A operand (%zu bytes)", xa_rows * (size_t)row_bytes);
+                return RR_E_NOMEM;
+            }
+            S->xa_rows_cap[md] = xa_rows;
         }
-        S->xa_rows_cap[md] = xa_rows;
-    }
-    rr_k_build_xa<<<(unsigned)xa_rows, 256, 0, st>>>(S->xb[md], P.rowsites, (int64_t)xa_rows, row_bytes, S->xa[md]);
-    rr_count_launch(1);
-    UM_CUDA(cudaGetLastError());
+        rr_k_build_xa<<<(unsigned)xa_rows, 256, 0, st>>>(S->xb[md], P.rowsites, (int64_t)xa_rows, row_bytes, S->xa[md]);
+        rr_count_launch(1);
+        UM_CUDA(cudaGetLastError());
 
-    // work units: (row tile, aligned chunk of UNIT_CT column tiles), this part's row tiles only, ordered in
-    // 2-D blocks of GR row tiles x GC chunks so that the ~148 units in flight at any time share a working set
-    // (GR A row-tiles + GC*UNIT_CT B column-tiles, a few tens of MB) that stays resident in the 126 MB L2.
-    constexpr int UNIT_CT = 4, GR = 24, GC = 6;
-    struct keyed { int64_t key; um_unit u; };
-    std::vector<keyed> ku;
-    int64_t kblocks = 0;
-    for (int rb = plan.rb_lo; rb < plan.rb_hi; rb++) {
-        const int cb0 = plan.unit_cb0[rb];
-        const int ncb = (int)(plan.unit_prefix[rb + 1] - plan.unit_prefix[rb]);
-        if (ncb <= 0) continue;
-        for (int cc = cb0 / UNIT_CT; cc <= (cb0 + ncb - 1) / UNIT_CT; cc++) {
-            um_unit un = {rb, std::max(cb0, cc * UNIT_CT), std::min(cb0 + ncb, (cc + 1) * UNIT_CT)};
-            const int64_t key = ((((int64_t)((rb - plan.rb_lo) / GR) << 20) + (cc / GC)) << 32) + ((int64_t)rb << 12) + (cc % (GC * 64));
-            ku.push_back({key, un});
+        // work units: (row tile, aligned chunk of UNIT_CT column tiles), this part's row tiles only, ordered in
+        // 2-D blocks of GR row tiles x GC chunks so that the ~148 units in flight at any time share a working set
+        // (GR A row-tiles + GC*UNIT_CT B column-tiles, a few tens of MB) that stays resident in the 126 MB L2.
+        constexpr int UNIT_CT = 4, GR = 24, GC = 6;
+        struct keyed { int64_t key; um_unit u; };
+        std::vector<keyed> ku;
+        int64_t kblocks = 0;
+        for (int rb = plan.rb_lo; rb < plan.rb_hi; rb++) {
+            const int cb0 = plan.unit_cb0[rb];
+            const int ncb = (int)(plan.unit_prefix[rb + 1] - plan.unit_prefix[rb]);
+            if (ncb <= 0) continue;
+            for (int cc = cb0 / UNIT_CT; cc <= (cb0 + ncb - 1) / UNIT_CT; cc++) {
+                um_unit un = {rb, std::max(cb0, cc * UNIT_CT), std::min(cb0 + ncb, (cc + 1) * UNIT_CT)};
+                const int64_t key = ((((int64_t)((rb - plan.rb_lo) / GR) << 20) + (cc / GC)) << 32) + ((int64_t)rb << 12) + (cc % (GC * 64));
+                ku.push_back({key, un});
+            }
+            for (int c = 0; c < ncb; c++) kblocks += std::max(0, plan.k_hi[rb] - plan.k_lo[cb0 + c]);
         }
-        for (int c = 0; c < ncb; c++) kblocks += std::max(0, plan.k_hi[rb] - plan.k_lo[cb0 + c]);
+        std::sort(ku.begin(), ku.end(), [](const keyed &x, const keyed &y) { return x.key < y.key; });
+        std::vector<um_unit> units(ku.size());
+        for (size_t q = 0; q < ku.size(); q++) units[q] = ku[q].u;
+        // Seeding pass: the same kernel over every SEED-th row tile first.  It leaves true (lower-bound) maxima
+        // in best[] for all column groups, so the full pass starts with thresholds close to the final ones
+        // instead of 0 and the bounds prune from the first pair on.  Its pair statistics are discarded.
+        constexpr int SEED = 16;
+        std::vector<um_unit> seed_units;
+        if (plan.rb_hi - plan.rb_lo >= 2 * SEED)
+            for (const um_unit &un : units)
+                if ((un.rt - plan.rb_lo) % SEED == SEED / 2) seed_units.push_back(un);
+        S->executed_ops = kblocks * (int64_t)(2LL * UM_M * UM_N * UM_KB);
+        S->n_units = (int)units.size();
+        S->n_seed = (int)seed_units.size();
+        if (!units.empty()) {
+            if ((rc = grow(&S->d_units, &S->units_cap, units.size() + seed_units.size()))) return rc;
+            if ((rc = grow(&S->d_khi, &S->khi_cap, plan.k_hi.size()))) return rc;
+            if ((rc = grow(&S->d_klo, &S->klo_cap, plan.k_lo.size()))) return rc;
+            UM_CUDA(cudaMemcpyAsync(S->d_units, units.data(), sizeof(um_unit) * units.size(), cudaMemcpyHostToDevice, st));
+            if (!seed_units.empty())
+                UM_CUDA(cudaMemcpyAsync(S->d_units + units.size(), seed_units.data(), sizeof(um_unit) * seed_units.size(),
+                                        cudaMemcpyHostToDevice, st));
+            UM_CUDA(cudaMemcpyAsync(S->d_khi, plan.k_hi.data(), sizeof(int32_t) * plan.k_hi.size(), cudaMemcpyHostToDevice, st));
+            UM_CUDA(cudaMemcpyAsync(S->d_klo, plan.k_lo.data(), sizeof(int32_t) * plan.k_lo.size(), cudaMemcpyHostToDevice, st));
+            UM_CUDA(cudaStreamSynchronize(st));  // units[] is a local
+            if ((rc = make_map(&S->map_a, S->xa[md], xa_rows, (uint64_t)S->Kp, UM_M, fp4 != 0))) return rc;
+            if ((rc = make_map(&S->map_b, S->xb[md], (uint64_t)5 * P.N, (uint64_t)S->Kp, UM_N, fp4 != 0))) return rc;
+        }
+        S->built_plan_id = plan_id;
+        S->built_md = md;
     }
-    std::sort(ku.begin(), ku.end(), [](const keyed &x, const keyed &y) { return x.key < y.key; });
-    std::vector<um_unit> units(ku.size());
-    for (size_t q = 0; q < ku.size(); q++) units[q] = ku[q].u;
-    // Seeding pass: the same kernel over every SEED-th row tile first.  It leaves true (lower-bound) maxima in
-    // best[] for all column groups, so the full pass starts with thresholds close to the final ones instead
-    // of 0 and the bounds prune from the first pair on.  Its pair statistics are discarded.
-    constexpr int SEED = 16;
-    std::vector<um_unit> seed_units;
-    if (plan.rb_hi - plan.rb_lo >= 2 * SEED && !(P.flags & (RR_FLAG_NO_PRUNE | 0x1000u)))
-        for (const um_unit &un : units)
-            if ((un.rt - plan.rb_lo) % SEED == SEED / 2) seed_units.push_back(un);
-    plan.executed_ops = kblocks * (int64_t)(2LL * UM_M * UM_N * UM_KB);
-    if (units.empty()) return RR_OK;
-    if ((rc = grow(&S->d_units, &S->units_cap, units.size() + seed_units.size()))) return rc;
-    if ((rc = grow(&S->d_khi, &S->khi_cap, plan.k_hi.size()))) return rc;
-    if ((rc = grow(&S->d_klo, &S->klo_cap, plan.k_lo.size()))) return rc;
-    UM_CUDA(cudaMemcpyAsync(S->d_units, units.data(), sizeof(um_unit) * units.size(), cudaMemcpyHostToDevice, st));
-    if (!seed_units.empty())
-        UM_CUDA(cudaMemcpyAsync(S->d_units + units.size(), seed_units.data(), sizeof(um_unit) * seed_units.size(),
-                                cudaMemcpyHostToDevice, st));
-    UM_CUDA(cudaMemcpyAsync(S->d_khi, plan.k_hi.data(), sizeof(int32_t) * plan.k_hi.size(), cudaMemcpyHostToDevice, st));
-    UM_CUDA(cudaMemcpyAsync(S->d_klo, plan.k_lo.data(), sizeof(int32_t) * plan.k_lo.size(), cudaMemcpyHostToDevice, st));
-    UM_CUDA(cudaStreamSynchronize(st));  // units[] is a local
-
-    CUtensorMap map_a, map_b;
-    if ((rc = make_map(&map_a, S->xa[md], xa_rows, (uint64_t)S->Kp, UM_M, fp4 != 0))) return rc;
-    if ((rc = make_map(&map_b, S->xb[md], (uint64_t)5 * P.N, (uint64_t)S->Kp, UM_N, fp4 != 0))) return rc;
+    plan.executed_ops = S->executed_ops;
+    if (S->n_units == 0) return RR_OK;
 
     if (!S->attr_set) {
         UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
@@ -629,16 +643,17 @@ int rr_umma_scan(rr_umma_state *&S, int fp4, rr_scan_params &P, rr_plan &plan, c
     um_params U;
     U.P = P;
     U.units = S->d_units;
-    U.n_units = (int)units.size();
+    U.n_units = S->n_units;
     U.k_hi = S->d_khi;
     U.k_lo = S->d_klo;
-    const int grid = std::min<int>(n_sm, (int)units.size());
+    const int grid = std::min<int>(n_sm, S->n_units);
     U.lnf_smem = std::min(std::min(plan.max_cov + 2, P.R + 2), UM_LNF_MAX);
     const size_t smem_bytes = UM_LNF_OFF + (size_t)U.lnf_smem * sizeof(float);
     // FP32 tier-1 margin: 8 roundings of magnitude <= 2^-24 * ln(maxcov!) each (7 table entries, 6 additions,
     // generously doubled), in log10 units, plus the 1e-6 of the double-precision version
     U.t1_margin = (float)(16.0 * 5.9604645e-8 * rr_lnfact((unsigned)std::max(plan.max_cov, 1)) * 0.4342944819 + 2e-6);
     const bool all_smem = U.lnf_smem >= plan.max_cov + 1;
+    const CUtensorMap &map_a = S->map_a, &map_b = S->map_b;
     auto launch = [&](int g, const um_params &prm) {
         if (fp4) {
             if (all_smem) rr_k_scan_umma<true, true><<<g, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
@@ -648,10 +663,10 @@ int rr_umma_scan(rr_umma_state *&S, int fp4, rr_scan_params &P, rr_plan &plan, c
             else rr_k_scan_umma<false, false><<<g, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
         }
     };
-    if (!seed_units.empty()) {
+    if (seeding && S->n_seed > 0) {
         um_params V = U;
-        V.units = S->d_units + units.size();
-        V.n_units = (int)seed_units.size();
+        V.units = S->d_units + S->n_units;
+        V.n_units = S->n_seed;
         const int sgrid = std::min<int>(n_sm, V.n_units);
         launch(sgrid, V);
         rr_count_launch(1);
