@@ -331,7 +331,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": args.workload, "rows": R, "cols": N, "mincov": MINCOV, "variant": variant_used,
                        "pair_tests": P_total, "l2": "inputs larger than L2 (packed operands >> 126 MB)",
-                       "partition": f"{world} pair-balanced row ranges"},
+                       "partition": f"{world} cost-balanced contiguous row ranges"},
             "kernel_ms": k_ms, "exact_evals": st["exact_evals"], "bound_evals": st["bound_evals"],
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "pair tests/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -78,6 +78,33 @@ extern "C" void rr_host_free(void *p, int pinned)
 }
 
 // ---------------------------------------------------------------------------------------
+// device memory: stream-ordered pool
+// ---------------------------------------------------------------------------------------
+static thread_local cudaStream_t g_alloc_stream = nullptr;
+void rr_alloc_stream(cudaStream_t st) { g_alloc_stream = st; }
+
+cudaError_t rr_dev_malloc(void **p, size_t bytes)
+{
+    static std::atomic<unsigned> configured{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(configured.load() & (1u << dev))) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        configured |= (1u << dev);
+    }
+    return cudaMallocAsync(p, bytes, g_alloc_stream);
+}
+
+void rr_dev_free(void *p)
+{
+    if (p) cudaFreeAsync(p, g_alloc_stream);
+}
+
+// ---------------------------------------------------------------------------------------
 // measurement helpers
 // ---------------------------------------------------------------------------------------
 static std::atomic<long long> g_launches{0};
@@ -124,8 +151,8 @@ struct scan_buffers {
     int64_t *unit_prefix = nullptr;
     void release()
     {
-        cudaFree(rowok); cudaFree(colok); cudaFree(breakcol); cudaFree(rowsites); cudaFree(unit_cb0);
-        cudaFree(word_hi); cudaFree(word_lo); cudaFree(unit_prefix);
+        rr_dev_free(rowok); rr_dev_free(colok); rr_dev_free(breakcol); rr_dev_free(rowsites); rr_dev_free(unit_cb0);
+        rr_dev_free(word_hi); rr_dev_free(word_lo); rr_dev_free(unit_prefix);
         rowok = colok = nullptr; breakcol = rowsites = unit_cb0 = word_hi = word_lo = nullptr; unit_prefix = nullptr;
     }
     ~scan_buffers() { release(); }
@@ -167,7 +194,7 @@ template <typename T>
 static int dev_alloc(T **p, size_t count)
 {
     *p = nullptr;
-    if (cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T)) != cudaSuccess) {
+    if (rr_dev_malloc((void **)p, std::max<size_t>(count, 1) * sizeof(T)) != cudaSuccess) {
         cudaGetLastError();
         rr_set_error("out of device memory (%zu bytes)", count * sizeof(T));
         return RR_E_NOMEM;
@@ -178,18 +205,24 @@ static int dev_alloc(T **p, size_t count)
 extern "C" void rr_packed_free(rr_packed *pk)
 {
     if (!pk) return;
+    const double trace_t0 = rr_now_ms();
     cudaSetDevice(pk->device);
+    rr_alloc_stream(pk->st);
     rr_umma_free(pk->umma);
-    cudaFree(pk->d_cells); cudaFree(pk->d_perm); cudaFree(pk->d_bits); cudaFree(pk->d_covbits);
-    cudaFree(pk->d_gsize); cudaFree(pk->d_coverage); cudaFree(pk->d_lnfact); cudaFree(pk->d_best);
-    cudaFree(pk->d_counters);
+    rr_dev_free(pk->d_cells); rr_dev_free(pk->d_perm); rr_dev_free(pk->d_bits); rr_dev_free(pk->d_covbits);
+    rr_dev_free(pk->d_gsize); rr_dev_free(pk->d_coverage); rr_dev_free(pk->d_lnfact); rr_dev_free(pk->d_best);
+    rr_dev_free(pk->d_counters);
+    pk->cache.sb.release();  // while the stream still exists
     if (pk->t0) { cudaEventDestroy(pk->t0); cudaEventDestroy(pk->t1); }
-    if (pk->st) cudaStreamDestroy(pk->st);
+    if (pk->st) { cudaStreamSynchronize(pk->st); cudaStreamDestroy(pk->st); }
+    rr_alloc_stream(nullptr);
     delete pk;
+    RR_TRACE("free: done");
 }
 
 static int pack_impl(const uint8_t *cells, int R, int N, int codes, int device, rr_packed *pk)
 {
+    const double trace_t0 = rr_now_ms();
     int ndev = rr_device_count();
     if (ndev <= 0) { rr_set_error("no CUDA device: the scan has no CPU fallback"); return RR_E_NODEV; }
     if (device < 0 || device >= ndev) { rr_set_error("device %d out of range (%d devices)", device, ndev); return RR_E_ARG; }
@@ -202,6 +235,7 @@ static int pack_impl(const uint8_t *cells, int R, int N, int codes, int device, 
     pk->W32 = ((R + 127) / 128) * 4;
     if (pk->W32 == 0) pk->W32 = 4;
     RR_CUDA(cudaStreamCreateWithFlags(&pk->st, cudaStreamNonBlocking));
+    rr_alloc_stream(pk->st);
     cudaEvent_t e0, e1, e2;
     RR_CUDA(cudaEventCreate(&e0)); RR_CUDA(cudaEventCreate(&e1)); RR_CUDA(cudaEventCreate(&e2));
 
@@ -212,6 +246,7 @@ static int pack_impl(const uint8_t *cells, int R, int N, int codes, int device, 
     if (ncell) RR_CUDA(cudaMemcpyAsync(pk->d_cells, cells, ncell, cudaMemcpyHostToDevice, pk->st));
     RR_CUDA(cudaEventRecord(e1, pk->st));
 
+    RR_TRACE("pack: h2d issued");
     // spans -> row order (by span start, then end; uncovered rows last)
     int32_t *d_span = nullptr;
     if ((rc = dev_alloc(&d_span, (size_t)3 * std::max(R, 1)))) return rc;
@@ -219,7 +254,8 @@ static int pack_impl(const uint8_t *cells, int R, int N, int codes, int device, 
     std::vector<int32_t> span((size_t)3 * std::max(R, 1));
     RR_CUDA(cudaMemcpyAsync(span.data(), d_span, sizeof(int32_t) * 3 * (size_t)R, cudaMemcpyDeviceToHost, pk->st));
     RR_CUDA(cudaStreamSynchronize(pk->st));
-    cudaFree(d_span);
+    rr_dev_free(d_span);
+    RR_TRACE("pack: spans back");
     std::vector<int32_t> perm(R);
     std::iota(perm.begin(), perm.end(), 0);
     const int32_t *sst = span.data(), *sen = span.data() + R, *scn = span.data() + 2 * (size_t)R;
@@ -260,8 +296,10 @@ static int pack_impl(const uint8_t *cells, int R, int N, int codes, int device, 
     if ((rc = dev_alloc(&pk->d_counters, (size_t)8))) return rc;
     RR_CUDA(cudaEventRecord(e2, pk->st));
     RR_CUDA(cudaStreamSynchronize(pk->st));
+    RR_TRACE("pack: done");
     RR_CUDA(cudaEventElapsedTime(&pk->h2d_ms, e0, e1));
     RR_CUDA(cudaEventElapsedTime(&pk->pack_ms, e1, e2));
+    if (rr_trace_on()) fprintf(stderr, "[rr trace] h2d %.3f ms (%.1f GB/s), pack %.3f ms\n", pk->h2d_ms, ncell / (pk->h2d_ms * 1e6), pk->pack_ms);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     return RR_OK;
 }
@@ -308,10 +346,11 @@ extern "C" int rr_pair_counts(rr_packed *pk, int64_t n, const int32_t *gi, const
     if (!pk || n < 0 || (n && (!gi || !gj || !out))) return RR_E_ARG;
     if (n == 0) return RR_OK;
     RR_CUDA(cudaSetDevice(pk->device));
+    rr_alloc_stream(pk->st);
     int32_t *d_i = nullptr, *d_j = nullptr, *d_o = nullptr;
     int rc;
     if ((rc = dev_alloc(&d_i, (size_t)n)) || (rc = dev_alloc(&d_j, (size_t)n)) || (rc = dev_alloc(&d_o, (size_t)4 * n))) {
-        cudaFree(d_i); cudaFree(d_j); cudaFree(d_o);
+        rr_dev_free(d_i); rr_dev_free(d_j); rr_dev_free(d_o);
         return rc;
     }
     RR_CUDA(cudaMemcpyAsync(d_i, gi, sizeof(int32_t) * n, cudaMemcpyHostToDevice, pk->st));
@@ -319,7 +358,7 @@ extern "C" int rr_pair_counts(rr_packed *pk, int64_t n, const int32_t *gi, const
     RR_CUDA(rr_launch_pair_counts(pk->d_bits, pk->d_covbits, pk->W32, n, d_i, d_j, d_o, pk->st));
     RR_CUDA(cudaMemcpyAsync(out, d_o, sizeof(int32_t) * 4 * n, cudaMemcpyDeviceToHost, pk->st));
     RR_CUDA(cudaStreamSynchronize(pk->st));
-    cudaFree(d_i); cudaFree(d_j); cudaFree(d_o);
+    rr_dev_free(d_i); rr_dev_free(d_j); rr_dev_free(d_o);
     return RR_OK;
 }
 
@@ -345,6 +384,7 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
     }
     const double trace_t0 = rr_now_ms();
     RR_CUDA(cudaSetDevice(pk->device));
+    rr_alloc_stream(pk->st);
     const int R = pk->R, N = pk->N, mincov = opts->mincov;
     cudaEvent_t e0, e1, e2;
     RR_CUDA(cudaEventCreate(&e0)); RR_CUDA(cudaEventCreate(&e1)); RR_CUDA(cudaEventCreate(&e2));

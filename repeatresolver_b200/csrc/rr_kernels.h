@@ -6,6 +6,14 @@
 
 struct rr_scan_params;
 extern "C" void rr_count_launch(int n);
+
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync) with an unlimited release
+// threshold: packing the next MSA reuses the previous one's blocks instead of paying cudaMalloc/cudaFree of
+// multi-GB buffers (measured: 40-160 ms per pack/free cycle at config 2).  All work of a handle is on one
+// stream; the ABI entry points select it with rr_alloc_stream() before allocating or freeing.
+void rr_alloc_stream(cudaStream_t st);
+cudaError_t rr_dev_malloc(void **p, size_t bytes);
+void rr_dev_free(void *p);
 struct rr_umma_plan;
 
 cudaError_t rr_launch_row_spans(const uint8_t *cells, int R, int N, int codes, int32_t *start, int32_t *end,

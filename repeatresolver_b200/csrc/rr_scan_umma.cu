@@ -514,8 +514,8 @@ int rr_umma_kblock(void) { return UM_KB; }
 void rr_umma_free(rr_umma_state *s)
 {
     if (!s) return;
-    for (int m = 0; m < 2; m++) { cudaFree(s->xb[m]); cudaFree(s->xa[m]); }
-    cudaFree(s->d_units); cudaFree(s->d_khi); cudaFree(s->d_klo);
+    for (int m = 0; m < 2; m++) { rr_dev_free(s->xb[m]); rr_dev_free(s->xa[m]); }
+    rr_dev_free(s->d_units); rr_dev_free(s->d_khi); rr_dev_free(s->d_klo);
     delete s;
 }
 
@@ -532,9 +532,9 @@ template <typename T>
 static int grow(T **p, size_t *cap, size_t need)
 {
     if (need <= *cap && *p) return RR_OK;
-    cudaFree(*p);
+    rr_dev_free(*p);
     *p = nullptr;
-    if (cudaMalloc((void **)p, std::max<size_t>(need, 1) * sizeof(T)) != cudaSuccess) {
+    if (rr_dev_malloc((void **)p, std::max<size_t>(need, 1) * sizeof(T)) != cudaSuccess) {
         cudaGetLastError();
         rr_set_error("out of device memory (%zu bytes)", need * sizeof(T));
         return RR_E_NOMEM;
@@ -556,7 +556,7 @@ int rr_umma_scan(rr_umma_state *&S, int fp4, uint64_t plan_id, rr_scan_params &P
     const int64_t row_bytes = fp4 ? S->Kp / 2 : S->Kp;
     if (!S->xb[md]) {
         const size_t rows = (size_t)5 * P.N;
-        if (cudaMalloc((void **)&S->xb[md], std::max<size_t>(rows * row_bytes, 32)) != cudaSuccess) {
+        if (rr_dev_malloc((void **)&S->xb[md], std::max<size_t>(rows * row_bytes, 32)) != cudaSuccess) {
             cudaGetLastError();
             rr_set_error("out of device memory for the B operand (%zu bytes)", rows * (size_t)row_bytes);
             return RR_E_NOMEM;
@@ -568,9 +568,9 @@ int rr_umma_scan(rr_umma_state *&S, int fp4, uint64_t plan_id, rr_scan_params &P
         // A operand for this plan's row sites
         const size_t xa_rows = (size_t)std::max(plan.n_rowblocks, 1) * UM_M;
         if (xa_rows > S->xa_rows_cap[md]) {
-            cudaFree(S->xa[md]);
+            rr_dev_free(S->xa[md]);
             S->xa[md] = nullptr;
-            if (cudaMalloc((void **)&S->xa[md], xa_rows * row_bytes) != cudaSuccess) {
+            if (rr_dev_malloc((void **)&S->xa[md], xa_rows * row_bytes) != cudaSuccess) {
                 cudaGetLastError();
                 rr_set_error("out of device memory for the A operand (%zu bytes)", xa_rows * (size_t)row_bytes);
                 return RR_E_NOMEM;
