@@ -179,7 +179,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     import repeatresolver_b200 as rr
-    from repeatresolver_b200.dist import merge_over_ranks
+    from repeatresolver_b200.dist import merge_over_ranks, scan_part
 
     if args.impl == "reference":
         if rank != 0:
@@ -245,7 +245,7 @@ def main():
     # ---- value: inputs resident in HBM ------------------------------------------------------
     st = None
     for _ in range(args.warmup):
-        st = pk.scan(mincov=MINCOV, variant=variant, part_index=rank, part_count=world)
+        st = scan_part(pk, MINCOV, variant)
     barrier()
     sampler = ClockSampler(local_rank)
     if not os.environ.get("BENCH_NO_SAMPLER"):
@@ -254,7 +254,7 @@ def main():
     kernel_ms = []
     pk.timer_start()
     for _ in range(args.steps):
-        st = pk.scan(mincov=MINCOV, variant=variant, part_index=rank, part_count=world)
+        st = scan_part(pk, MINCOV, variant)   # N > 1: seeding pass, all-reduce MAX of thresholds, full pass
         kernel_ms.append(st["kernel_ms"])
     loop_ms = pk.timer_stop()
     launches = rr.launch_count() - launches0
@@ -276,7 +276,7 @@ def main():
         barrier()
         t0 = time.perf_counter()
         pk2 = rr.Packed(msa, local_rank)                      # H2D (pinned) + device pack
-        pk2.scan(mincov=MINCOV, variant=variant, part_index=rank, part_count=world)
+        scan_part(pk2, MINCOV, variant)
         M, A = pk2.fetch()                                    # D2H of the per-group result
         M, A = merge_over_ranks(M, A)                         # element-wise max over ranks (882-891)
         torch.cuda.synchronize()

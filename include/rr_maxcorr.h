@@ -60,6 +60,11 @@ enum {
 #define RR_FLAG_GENERAL_BREAK 4u /* force the general first-break computation (MaxCorrelation.c:807-810)
                                     even when every row is one contiguous span */
 
+#define RR_FLAG_SEED_ONLY 8u     /* run only the seeding pass (every 16th row tile of this part): multi-GPU runs
+                                    exchange the resulting maxima as thresholds before the full pass */
+#define RR_FLAG_SKIP_SEED 16u    /* keep the running maxima already on the device (previous RR_FLAG_SEED_ONLY
+                                    scan and/or rr_scan_set_thresholds) and go straight to the full pass */
+
 typedef struct rr_msa rr_msa;       /* host: the kept rows of an MSA */
 typedef struct rr_packed rr_packed; /* device: one GPU's packed copy of an MSA */
 
@@ -110,6 +115,9 @@ int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *stats);
 /* copy the last scan's result to the host: maxcorr[5*cols] (line g of MaxCorrsOf_*,
  * g = 5*site + {A,C,G,T,gap}); argmax[5*cols] = partner group id or -1 (may be NULL) */
 int rr_scan_fetch(rr_packed *pk, double *maxcorr, int32_t *argmax);
+/* raise the running maxima on the device to at least thr[5*cols] (e.g. the max over all GPUs' seeding passes);
+ * a value taken from thr carries no partner: it only prunes, and loses every tie against a real pair */
+int rr_scan_set_thresholds(rr_packed *pk, const double *thr);
 /* the four intersection counts {schnitt, gr1, gr2, cov} (423-426) of n group pairs, from the
  * device bitsets: out[4*n] */
 int rr_pair_counts(rr_packed *pk, int64_t n, const int32_t *gi, const int32_t *gj, int32_t *out);

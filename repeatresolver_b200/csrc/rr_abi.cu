@@ -6,7 +6,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -438,7 +440,7 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
     scan_buffers &sb = C.sb;
 
     // running maxima: 0.0 / no partner
-    RR_CUDA(rr_launch_init_best(pk->d_best, (int64_t)5 * N, pk->st));
+    if (!(opts->flags & RR_FLAG_SKIP_SEED)) RR_CUDA(rr_launch_init_best(pk->d_best, (int64_t)5 * N, pk->st));
     RR_CUDA(cudaMemsetAsync(pk->d_counters, 0, sizeof(unsigned long long) * 8, pk->st));
     RR_TRACE("uploads+init");
 
@@ -455,7 +457,7 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
     int64_t executed = 0;
     if (plan.rb_hi > plan.rb_lo && plan.unit_prefix[plan.rb_hi] > plan.unit_prefix[plan.rb_lo]) {
         if (variant == RR_VARIANT_BITSET) {
-            RR_CUDA(rr_launch_scan_bitset(P, pk->n_sm, pk->st));
+            if (!(opts->flags & RR_FLAG_SEED_ONLY)) RR_CUDA(rr_launch_scan_bitset(P, pk->n_sm, pk->st));  // no seeding pass in this variant
         } else {
             rc = rr_umma_scan(pk->umma, variant == RR_VARIANT_UMMA_F4, C.plan_id, P, plan, pk->d_cells, pk->d_perm, pk->codes, pk->n_sm, pk->st);
             if (rc) return rc;
@@ -488,12 +490,30 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
         cudaEventElapsedTime(&stats->prepare_ms, e0, e1);
         cudaEventElapsedTime(&stats->kernel_ms, e1, e2);
     }
-    if ((int64_t)counters[0] != plan.part_pairs && !(opts->flags & 0x700u)) {
+    if ((int64_t)counters[0] != plan.part_pairs && !(opts->flags & (0x700u | RR_FLAG_SEED_ONLY))) {
         rr_set_error("pair-test count mismatch: device %llu, host plan %lld", counters[0], (long long)plan.part_pairs);
         cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
         return RR_E_CUDA;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    return RR_OK;
+}
+
+extern "C" int rr_scan_set_thresholds(rr_packed *pk, const double *thr)
+{
+    if (!pk || (!thr && pk->N > 0)) { rr_set_error("rr_scan_set_thresholds: bad arguments"); return RR_E_ARG; }
+    if (!pk->have_result) { rr_set_error("rr_scan_set_thresholds before a seeding scan"); return RR_E_ARG; }
+    RR_CUDA(cudaSetDevice(pk->device));
+    rr_alloc_stream(pk->st);
+    const size_t G = (size_t)5 * pk->N;
+    if (G == 0) return RR_OK;
+    double *d_thr = nullptr;
+    int rc = dev_alloc(&d_thr, G);
+    if (rc) return rc;
+    RR_CUDA(cudaMemcpyAsync(d_thr, thr, sizeof(double) * G, cudaMemcpyHostToDevice, pk->st));
+    RR_CUDA(rr_launch_raise_best(pk->d_best, d_thr, (int64_t)G, pk->st));
+    RR_CUDA(cudaStreamSynchronize(pk->st));
+    rr_dev_free(d_thr);
     return RR_OK;
 }
 
@@ -533,10 +553,41 @@ extern "C" int rr_maxcorr_run(const rr_msa *msa, int mincov, int n_gpus, int var
     std::vector<std::string> ERR(n_gpus);
     std::vector<rr_packed *> PK(n_gpus, nullptr);
 
+    // phase barrier for the per-GPU host threads
+    std::mutex mu;
+    std::condition_variable cv;
+    int arrived = 0, generation = 0;
+    auto barrier = [&]() {
+        std::unique_lock<std::mutex> lk(mu);
+        const int gen = generation;
+        if (++arrived == n_gpus) { arrived = 0; generation++; cv.notify_all(); }
+        else cv.wait(lk, [&] { return generation != gen; });
+    };
+    std::vector<double> thr(G, 0.0);
+
     auto worker = [&](int d) {
         rr_scan_opts o;
         o.mincov = mincov; o.variant = variant; o.flags = flags; o.part_index = d; o.part_count = n_gpus;
         int rc = rr_pack(msa, d, &PK[d]);
+        if (n_gpus > 1) {
+            // seeding pass on every GPU, max over GPUs as common thresholds, then the full pass
+            if (!rc) { o.flags = flags | RR_FLAG_SEED_ONLY; rc = rr_scan(PK[d], &o, &S[d]); }
+            if (!rc) rc = rr_scan_fetch(PK[d], M[d].data(), nullptr);
+            RC[d] = rc;
+            barrier();
+            bool all_ok = true;
+            for (int e = 0; e < n_gpus; e++) all_ok = all_ok && RC[e] == RR_OK;
+            if (d == 0 && all_ok)
+                for (size_t g = 0; g < G; g++) {
+                    double z = M[0][g];
+                    for (int e = 1; e < n_gpus; e++) z = std::max(z, M[e][g]);
+                    thr[g] = z;
+                }
+            barrier();
+            if (!all_ok) { if (rc) ERR[d] = rr_last_error(); return; }
+            rc = rr_scan_set_thresholds(PK[d], thr.data());
+            o.flags = flags | RR_FLAG_SKIP_SEED;
+        }
         if (!rc) rc = rr_scan(PK[d], &o, &S[d]);
         if (!rc) {
             cudaEvent_t a, b;

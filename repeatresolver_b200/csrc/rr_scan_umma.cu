@@ -563,7 +563,7 @@ int rr_umma_scan(rr_umma_state *&S, int fp4, uint64_t plan_id, rr_scan_params &P
         }
         UM_CUDA(rr_launch_pack_int8(d_cells, d_perm, P.R, P.N, codes, S->xb[md], S->Kp, fp4, st));
     }
-    const bool seeding = !(P.flags & (RR_FLAG_NO_PRUNE | 0x1000u));
+    const bool seeding = !(P.flags & (RR_FLAG_NO_PRUNE | RR_FLAG_SKIP_SEED | 0x1000u));
     if (S->built_plan_id != plan_id || S->built_md != md) {
         // A operand for this plan's row sites
         const size_t xa_rows = (size_t)std::max(plan.n_rowblocks, 1) * UM_M;
@@ -673,6 +673,7 @@ int rr_umma_scan(rr_umma_state *&S, int fp4, uint64_t plan_id, rr_scan_params &P
         UM_CUDA(cudaGetLastError());
         UM_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(unsigned long long) * 8, st));
     }
+    if (P.flags & RR_FLAG_SEED_ONLY) return RR_OK;
     launch(grid, U);
     rr_count_launch(1);
     UM_CUDA(cudaGetLastError());

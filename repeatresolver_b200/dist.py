@@ -34,3 +34,26 @@ def rank_part():
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1
+
+
+def scan_part(pk, mincov=30, variant="auto", flags=0):
+    """This rank's part of the scan (pk: repeatresolver_b200.Packed of the whole MSA on this rank's GPU).
+    With more than one rank: seeding pass on every rank, all-reduce MAX of the seeded maxima as common
+    pruning thresholds (values only, 5N doubles), then the full pass.  Returns the stats of the full pass;
+    results stay on the device (pk.fetch(), then merge_over_ranks)."""
+    import torch
+    import torch.distributed as dist
+    from .maxcorr import FLAG_SEED_ONLY, FLAG_SKIP_SEED
+    rank, world = rank_part()
+    if world == 1:
+        return pk.scan(mincov=mincov, variant=variant, flags=flags)
+    st0 = pk.scan(mincov=mincov, variant=variant, flags=flags | FLAG_SEED_ONLY, part_index=rank, part_count=world)
+    M, _ = pk.fetch()
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    Mt = torch.from_numpy(M).to(dev)
+    dist.all_reduce(Mt, op=dist.ReduceOp.MAX)
+    pk.set_thresholds(Mt.cpu().numpy())
+    st = pk.scan(mincov=mincov, variant=variant, flags=flags | FLAG_SKIP_SEED, part_index=rank, part_count=world)
+    st["kernel_ms"] += st0["kernel_ms"]  # both passes
+    st["prepare_ms"] += st0["prepare_ms"]
+    return st

@@ -18,6 +18,8 @@ VARIANT_NAMES = {v: k for k, v in VARIANTS.items()}
 FLAG_NO_PRUNE = 1
 FLAG_HOST_FINALIZE = 2
 FLAG_GENERAL_BREAK = 4
+FLAG_SEED_ONLY = 8
+FLAG_SKIP_SEED = 16
 
 
 class RRError(RuntimeError):
@@ -123,6 +125,11 @@ class Packed:
         A = np.zeros(G, dtype=np.int32)
         _check(lib.rr_scan_fetch(self._h, M.ctypes.data, A.ctypes.data), "rr_scan_fetch")
         return M, A
+
+    def set_thresholds(self, thr):
+        thr = np.ascontiguousarray(thr, dtype=np.float64)
+        assert len(thr) == 5 * self.cols
+        _check(lib.rr_scan_set_thresholds(self._h, thr.ctypes.data), "rr_scan_set_thresholds")
 
     def pair_counts(self, gi, gj):
         gi = np.ascontiguousarray(gi, dtype=np.int32)

@@ -113,6 +113,27 @@ def test_generated_msa_full_parity(kind, seed, variant):
         Mm = np.where(better, Mp, Mm)
         Am = np.where(better, Ap, Am)
     assert Pm == P0 and (Mm == M).all() and (Am == A).all()
+    # the same with the multi-GPU threshold exchange: seeding pass per part, max over parts injected as
+    # partner-less thresholds, full pass per part; the merged result must not change
+    seeds = []
+    for p in range(parts):
+        pk.scan(mincov=30, variant=variant, flags=rr.FLAG_SEED_ONLY, part_index=p, part_count=parts)
+        seeds.append(pk.fetch()[0])
+    thr = np.maximum.reduce(seeds)
+    assert (thr <= M).all()
+    Mm = np.zeros_like(M)
+    Am = np.full_like(A, -1)
+    Pm = 0
+    for p in range(parts):
+        pk.scan(mincov=30, variant=variant, flags=rr.FLAG_SEED_ONLY, part_index=p, part_count=parts)
+        pk.set_thresholds(thr)
+        s = pk.scan(mincov=30, variant=variant, flags=rr.FLAG_SKIP_SEED, part_index=p, part_count=parts)
+        Mp, Ap = pk.fetch()
+        Pm += s["pair_tests"]
+        better = (Mp > Mm) | ((Mp == Mm) & (Mp > 0) & (Ap >= 0) & ((Am < 0) | (Ap < Am)))
+        Mm = np.where(better, Mp, Mm)
+        Am = np.where(better, Ap, Am)
+    assert Pm == P0 and (Mm == M).all() and (Am == A).all()
     pk.close()
 
 
