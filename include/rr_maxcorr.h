@@ -79,7 +79,7 @@ typedef struct rr_scan_opts {
 typedef struct rr_scan_stats {
     int64_t pair_tests;   /* PositiveSignificance calls the reference would make (820) */
     int64_t exact_evals;  /* pairs whose exact score was evaluated */
-    int64_t bound_evals;  /* pairs that needed the pmf bound */
+    int64_t bound_evals;  /* pairs that went through the queued bound tier (tcgen05 variants: tier 2) */
     int64_t work_units;   /* tile pairs processed */
     int64_t executed_ops; /* tensor-core MACs*2 (UMMA variants) or 32-bit AND+POPC word ops (bitset) executed */
     int variant;          /* variant actually used */
@@ -118,6 +118,10 @@ int rr_scan_fetch(rr_packed *pk, double *maxcorr, int32_t *argmax);
 /* raise the running maxima on the device to at least thr[5*cols] (e.g. the max over all GPUs' seeding passes);
  * a value taken from thr carries no partner: it only prunes, and loses every tie against a real pair */
 int rr_scan_set_thresholds(rr_packed *pk, const double *thr);
+/* the same exchange without the host: d_values / d_thr are DEVICE pointers (same device and process as the
+ * handle, e.g. a torch tensor's data_ptr) to 5*cols doubles; both calls return after their work has completed */
+int rr_scan_values_device(rr_packed *pk, double *d_values);
+int rr_scan_set_thresholds_device(rr_packed *pk, const double *d_thr);
 /* the four intersection counts {schnitt, gr1, gr2, cov} (423-426) of n group pairs, from the
  * device bitsets: out[4*n] */
 int rr_pair_counts(rr_packed *pk, int64_t n, const int32_t *gi, const int32_t *gj, int32_t *out);

@@ -56,7 +56,7 @@ def _sig(fn, res, args):
 # every symbol include/rr_maxcorr.h declares
 ABI_SYMBOLS = [
     "rr_msa_read", "rr_msa_from_text", "rr_msa_from_cells", "rr_msa_alloc", "rr_msa_rows", "rr_msa_cols",
-    "rr_msa_cells", "rr_msa_free", "rr_device_count", "rr_variant_available", "rr_pack", "rr_packed_free", "rr_scan", "rr_scan_fetch", "rr_scan_set_thresholds",
+    "rr_msa_cells", "rr_msa_free", "rr_device_count", "rr_variant_available", "rr_pack", "rr_packed_free", "rr_scan", "rr_scan_fetch", "rr_scan_set_thresholds", "rr_scan_values_device", "rr_scan_set_thresholds_device",
     "rr_pair_counts", "rr_packed_sizes", "rr_maxcorr_run", "rr_maxcorr_write", "rr_argmax_write", "rr_lnfact",
     "rr_lnfact_table", "rr_score_host", "rr_score_bound_host", "rr_below_median_host", "rr_breakcols_from_spans",
     "rr_timer_start", "rr_timer_stop", "rr_launch_count", "rr_last_error", "rr_version",
@@ -79,6 +79,8 @@ _sig(lib.rr_packed_free, None, [_vp])
 _sig(lib.rr_scan, _i, [_vp, _P(ScanOpts), _P(ScanStats)])
 _sig(lib.rr_scan_fetch, _i, [_vp, _vp, _vp])
 _sig(lib.rr_scan_set_thresholds, _i, [_vp, _vp])
+_sig(lib.rr_scan_values_device, _i, [_vp, _vp])
+_sig(lib.rr_scan_set_thresholds_device, _i, [_vp, _vp])
 _sig(lib.rr_pair_counts, _i, [_vp, _i64, _vp, _vp, _vp])
 _sig(lib.rr_packed_sizes, _i, [_vp, _vp, _vp])
 _sig(lib.rr_maxcorr_run, _i, [_vp, _i, _i, _i, C.c_uint, _vp, _vp, _P(ScanStats)])

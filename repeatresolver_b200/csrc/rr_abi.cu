@@ -421,7 +421,7 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
         rr_plan_build(C.plan, R, N, mincov, pk->h_gsize.data(), pk->h_coverage.data(), breakcol.data(),
                       pk->contiguous && !general ? pk->h_start.data() : nullptr,
                       pk->contiguous && !general ? pk->h_end.data() : nullptr, ti, tj, variant == RR_VARIANT_BITSET ? 32 : rr_umma_kblock(),
-                      variant == RR_VARIANT_BITSET ? 8 : 300, opts->part_index, opts->part_count);
+                      variant == RR_VARIANT_BITSET ? 8 : 75, opts->part_index, opts->part_count);
         RR_TRACE("plan");
         if ((rc = upload(&C.sb.rowok, C.plan.rowok, pk->st))) return rc;
         if ((rc = upload(&C.sb.colok, C.plan.colok, pk->st))) return rc;
@@ -480,7 +480,7 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
         memset(stats, 0, sizeof *stats);
         stats->pair_tests = (int64_t)counters[0];
         stats->exact_evals = (int64_t)counters[1];
-        stats->bound_evals = (int64_t)counters[2];
+        stats->bound_evals = (int64_t)(counters[2] + counters[4]);  // tier-1 table bounds (bitset kernel) + tier-2 evaluations (UMMA)
         stats->work_units = (int64_t)counters[3];
         stats->executed_ops = executed;
         stats->variant = variant;
@@ -514,6 +514,26 @@ extern "C" int rr_scan_set_thresholds(rr_packed *pk, const double *thr)
     RR_CUDA(rr_launch_raise_best(pk->d_best, d_thr, (int64_t)G, pk->st));
     RR_CUDA(cudaStreamSynchronize(pk->st));
     rr_dev_free(d_thr);
+    return RR_OK;
+}
+
+extern "C" int rr_scan_values_device(rr_packed *pk, double *d_values)
+{
+    if (!pk || (!d_values && pk->N > 0)) { rr_set_error("rr_scan_values_device: bad arguments"); return RR_E_ARG; }
+    if (!pk->have_result) { rr_set_error("rr_scan_values_device before rr_scan"); return RR_E_ARG; }
+    RR_CUDA(cudaSetDevice(pk->device));
+    RR_CUDA(rr_launch_best_values(pk->d_best, d_values, (int64_t)5 * pk->N, pk->st));
+    RR_CUDA(cudaStreamSynchronize(pk->st));
+    return RR_OK;
+}
+
+extern "C" int rr_scan_set_thresholds_device(rr_packed *pk, const double *d_thr)
+{
+    if (!pk || (!d_thr && pk->N > 0)) { rr_set_error("rr_scan_set_thresholds_device: bad arguments"); return RR_E_ARG; }
+    if (!pk->have_result) { rr_set_error("rr_scan_set_thresholds_device before a seeding scan"); return RR_E_ARG; }
+    RR_CUDA(cudaSetDevice(pk->device));
+    RR_CUDA(rr_launch_raise_best(pk->d_best, d_thr, (int64_t)5 * pk->N, pk->st));
+    RR_CUDA(cudaStreamSynchronize(pk->st));
     return RR_OK;
 }
 

@@ -31,6 +31,7 @@ cudaError_t rr_launch_pack_int8(const uint8_t *cells, const int32_t *perm, int R
 struct rr_best_t;
 cudaError_t rr_launch_init_best(rr_best_t *best, int64_t n, cudaStream_t st);
 cudaError_t rr_launch_raise_best(rr_best_t *best, const double *thr, int64_t n, cudaStream_t st);
+cudaError_t rr_launch_best_values(const rr_best_t *best, double *values, int64_t n, cudaStream_t st);
 cudaError_t rr_launch_scan_bitset(const rr_scan_params &P, int n_sm, cudaStream_t st);
 int rr_bitset_ti(void);
 int rr_bitset_tj(void);

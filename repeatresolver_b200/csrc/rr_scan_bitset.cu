@@ -170,6 +170,20 @@ cudaError_t rr_launch_raise_best(rr_best_t *best, const double *thr, int64_t n, 
     return cudaGetLastError();
 }
 
+__global__ void rr_k_best_values(const rr_best_t *best, double *values, int64_t n)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n) values[g] = __longlong_as_double((long long)best[g].z);
+}
+
+cudaError_t rr_launch_best_values(const rr_best_t *best, double *values, int64_t n, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    rr_k_best_values<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(best, values, n);
+    rr_count_launch(1);
+    return cudaGetLastError();
+}
+
 cudaError_t rr_launch_scan_bitset(const rr_scan_params &P, int n_sm, cudaStream_t st)
 {
     const int64_t units = 0;  // computed by the kernel from the prefix array

@@ -501,7 +501,7 @@ struct rr_umma_state {
     // what was built for the plan last seen (reused while plan_id and operand coding stay the same)
     uint64_t built_plan_id = 0;
     int built_md = -1;
-    int n_units = 0, n_seed = 0;
+    int n_units = 0, n_seed = 0, n_preseed = 0;
     int64_t executed_ops = 0;
     CUtensorMap map_a, map_b;
 };
@@ -605,14 +605,23 @@ int rr_umma_scan(rr_umma_state *&S, int fp4, uint64_t plan_id, rr_scan_params &P
         // Seeding pass: the same kernel over every SEED-th row tile first.  It leaves true (lower-bound) maxima
         // in best[] for all column groups, so the full pass starts with thresholds close to the final ones
         // instead of 0 and the bounds prune from the first pair on.  Its pair statistics are discarded.
-        constexpr int SEED = 16;
-        std::vector<um_unit> seed_units;
+        // The seeding pass itself starts from zero thresholds, where every pair is a candidate; a pre-seed over
+        // every PRESEED-th seed row tile takes that warm-up on ~1/128 of the row tiles instead of 1/16.
+        constexpr int SEED = 16, PRESEED = 8;
+        std::vector<um_unit> seed_units, preseed_units;
         if (plan.rb_hi - plan.rb_lo >= 2 * SEED)
-            for (const um_unit &un : units)
-                if ((un.rt - plan.rb_lo) % SEED == SEED / 2) seed_units.push_back(un);
+            for (const um_unit &un : units) {
+                const int d = un.rt - plan.rb_lo;
+                if (d % SEED == SEED / 2) {
+                    seed_units.push_back(un);
+                    if ((d / SEED) % PRESEED == 0) preseed_units.push_back(un);
+                }
+            }
+        seed_units.insert(seed_units.end(), preseed_units.begin(), preseed_units.end());  // stored behind the seed list
         S->executed_ops = kblocks * (int64_t)(2LL * UM_M * UM_N * UM_KB);
         S->n_units = (int)units.size();
-        S->n_seed = (int)seed_units.size();
+        S->n_preseed = (int)preseed_units.size();
+        S->n_seed = (int)seed_units.size() - S->n_preseed;
         if (!units.empty()) {
             if ((rc = grow(&S->d_units, &S->units_cap, units.size() + seed_units.size()))) return rc;
             if ((rc = grow(&S->d_khi, &S->khi_cap, plan.k_hi.size()))) return rc;
@@ -665,10 +674,16 @@ int rr_umma_scan(rr_umma_state *&S, int fp4, uint64_t plan_id, rr_scan_params &P
     };
     if (seeding && S->n_seed > 0) {
         um_params V = U;
+        if (S->n_preseed > 0) {
+            V.units = S->d_units + S->n_units + S->n_seed;
+            V.n_units = S->n_preseed;
+            launch(std::min<int>(n_sm, V.n_units), V);
+            rr_count_launch(1);
+            UM_CUDA(cudaGetLastError());
+        }
         V.units = S->d_units + S->n_units;
         V.n_units = S->n_seed;
-        const int sgrid = std::min<int>(n_sm, V.n_units);
-        launch(sgrid, V);
+        launch(std::min<int>(n_sm, V.n_units), V);
         rr_count_launch(1);
         UM_CUDA(cudaGetLastError());
         UM_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(unsigned long long) * 8, st));

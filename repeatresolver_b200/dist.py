@@ -48,11 +48,19 @@ def scan_part(pk, mincov=30, variant="auto", flags=0):
     if world == 1:
         return pk.scan(mincov=mincov, variant=variant, flags=flags)
     st0 = pk.scan(mincov=mincov, variant=variant, flags=flags | FLAG_SEED_ONLY, part_index=rank, part_count=world)
-    M, _ = pk.fetch()
-    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
-    Mt = torch.from_numpy(M).to(dev)
-    dist.all_reduce(Mt, op=dist.ReduceOp.MAX)
-    pk.set_thresholds(Mt.cpu().numpy())
+    if dist.get_backend() == "nccl":
+        # device to device: the library writes the maxima into a torch tensor, NCCL reduces it over NVLink,
+        # the library reads it back as thresholds; nothing crosses PCIe
+        Mt = torch.empty(5 * pk.cols, dtype=torch.float64, device=torch.device("cuda", torch.cuda.current_device()))
+        pk.values_to_device(Mt.data_ptr())
+        dist.all_reduce(Mt, op=dist.ReduceOp.MAX)
+        torch.cuda.current_stream().synchronize()
+        pk.set_thresholds_device(Mt.data_ptr())
+    else:
+        M, _ = pk.fetch()
+        Mt = torch.from_numpy(M)
+        dist.all_reduce(Mt, op=dist.ReduceOp.MAX)
+        pk.set_thresholds(Mt.numpy())
     st = pk.scan(mincov=mincov, variant=variant, flags=flags | FLAG_SKIP_SEED, part_index=rank, part_count=world)
     st["kernel_ms"] += st0["kernel_ms"]  # both passes
     st["prepare_ms"] += st0["prepare_ms"]

@@ -131,6 +131,13 @@ class Packed:
         assert len(thr) == 5 * self.cols
         _check(lib.rr_scan_set_thresholds(self._h, thr.ctypes.data), "rr_scan_set_thresholds")
 
+    def values_to_device(self, device_ptr):
+        """write the 5N running maxima to a device buffer (e.g. torch_tensor.data_ptr())"""
+        _check(lib.rr_scan_values_device(self._h, C.c_void_p(device_ptr)), "rr_scan_values_device")
+
+    def set_thresholds_device(self, device_ptr):
+        _check(lib.rr_scan_set_thresholds_device(self._h, C.c_void_p(device_ptr)), "rr_scan_set_thresholds_device")
+
     def pair_counts(self, gi, gj):
         gi = np.ascontiguousarray(gi, dtype=np.int32)
         gj = np.ascontiguousarray(gj, dtype=np.int32)

@@ -210,3 +210,30 @@ def test_cli_drop_in(tmp_path):
     assert "There are" in r.stdout and "Siglength is" in r.stdout and "Runtime:" in r.stdout
     arg = (tmp_path / "MaxCorrsArgOf_MSAreal").read_text().split()
     assert len(arg) == len(golden_maxcorrs("tree_small", 10).split())
+
+
+def test_threshold_exchange_device_pointers():
+    """the device-to-device form of the multi-GPU threshold exchange (torch tensor <-> library)"""
+    import torch
+    g = rr.MsaGen(type="Tree", copies=6, coverage=30, repeat_len=1500, diff=0.02, seed=61, flank=1500, min_overlap=100)
+    codes = g.codes()
+    pk = rr.Packed(rr.MSA.from_cells(codes), 0)
+    pk.scan(mincov=30)
+    M, A = pk.fetch()
+    pk.scan(mincov=30, flags=rr.FLAG_SEED_ONLY)
+    Ms, _ = pk.fetch()
+    t = torch.empty(5 * g.cols, dtype=torch.float64, device="cuda:0")
+    pk.values_to_device(t.data_ptr())
+    assert (t.cpu().numpy() == Ms).all()
+    t2 = torch.from_numpy(np.maximum(Ms, 0.5 * M)).to("cuda:0")  # thresholds below the true maxima
+    pk.set_thresholds_device(t2.data_ptr())
+    st = pk.scan(mincov=30, flags=rr.FLAG_SKIP_SEED)
+    M2, A2 = pk.fetch()
+    assert (M2 == M).all() and (A2 == A).all()
+    # thresholds equal to the true maxima: values stay, ties are still resolved to the real partner
+    pk.scan(mincov=30, flags=rr.FLAG_SEED_ONLY)
+    pk.set_thresholds(M)
+    pk.scan(mincov=30, flags=rr.FLAG_SKIP_SEED)
+    M3, A3 = pk.fetch()
+    assert (M3 == M).all() and (A3 == A).all()
+    pk.close()
