@@ -105,6 +105,8 @@ void rr_plan_build(rr_plan &plan, int R, int N, int mincov, const int32_t *gsize
             while (p < part_count && acc * part_count >= total_cost * (int64_t)p) cut[p++] = rb + 1;
         }
     }
+    plan.part_index = part_index;
+    plan.part_count = part_count;
     plan.rb_lo = cut[part_index];
     plan.rb_hi = cut[part_index + 1];
     plan.part_pairs = 0;

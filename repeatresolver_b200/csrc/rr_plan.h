@@ -17,6 +17,7 @@ struct rr_plan {
     std::vector<int32_t> k_lo;          // [n_colblocks] inclusive lower bound
     std::vector<int64_t> rb_pairs;      // [n_rowblocks] pair tests per row block
     int rb_lo = 0, rb_hi = 0;           // this part's row blocks
+    int part_index = 0, part_count = 1;
     int max_cov = 0;                    // largest column coverage (bounds every ln(n!) argument)
     int64_t total_pairs = 0, part_pairs = 0;
     int64_t part_kunits = 0;            // sum over this part's units of contributing k-units

@@ -26,6 +26,7 @@
 #include <cuda.h>
 #include <vector>
 #include <algorithm>
+#include <cstdlib>
 #include "rr_kernels.h"
 #include "rr_device.cuh"
 #include "rr_plan.h"
@@ -307,6 +308,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         um_wmeta &M = T->meta[ew];
         int c1n = 0, c2n = 0;
         const bool no_prune = (P.flags & RR_FLAG_NO_PRUNE) != 0, dbg_skip = (P.flags & 0x200u) != 0;
+        const bool subsample = (P.flags & 0x2000u) != 0;  // set by the host for the pre-seed launch only
         um_lnf<ALL_SMEM> LT;     // float table, tier 1
         LT.base = smem_u32(lnf_s); LT.n_smem = U.lnf_smem; LT.gmem = P.lnfact;
         rr_lnf_global LG;        // double table in HBM/L2, tier 2 (rare, evaluated 32 at a time)
@@ -387,7 +389,10 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             const bool nd = rr_tier1_f32(LT, (unsigned)c[b], (unsigned)rowsum, (unsigned)colsum[b],
                                                          (unsigned)cov, fminf(thr_i, M.mj[w * 5 + b]), lnc3, meanfac,
                                                          margin, no_prune, dbg_skip);
-                            need[b] = nd & pair_site;
+                            // pre-seed pass only: a column seen for the first time (no maximum yet) would make
+                            // every row of the tile a candidate at once; one row in eight is enough to seed it
+                            const bool sampled = !subsample || M.mj[w * 5 + b] > 0.0f || ((lane + t) & 7) == 0;
+                            need[b] = nd & pair_site & sampled;
                             n_pairs += pair_site;
                         }
                     }
@@ -602,21 +607,35 @@ int rr_umma_scan(rr_umma_state *&S, int fp4, uint64_t plan_id, rr_scan_params &P
         std::sort(ku.begin(), ku.end(), [](const keyed &x, const keyed &y) { return x.key < y.key; });
         std::vector<um_unit> units(ku.size());
         for (size_t q = 0; q < ku.size(); q++) units[q] = ku[q].u;
-        // Seeding pass: the same kernel over every SEED-th row tile first.  It leaves true (lower-bound) maxima
-        // in best[] for all column groups, so the full pass starts with thresholds close to the final ones
-        // instead of 0 and the bounds prune from the first pair on.  Its pair statistics are discarded.
-        // The seeding pass itself starts from zero thresholds, where every pair is a candidate; a pre-seed over
-        // every PRESEED-th seed row tile takes that warm-up on ~1/128 of the row tiles instead of 1/16.
-        constexpr int SEED = 16, PRESEED = 8;
+        // Seeding pass: the same kernel over every SEED-th row tile of the WHOLE MSA first.  It leaves true
+        // (lower-bound) maxima in best[] for all column groups, so the full pass starts with thresholds close
+        // to the final ones instead of 0 and the bounds prune from the first pair on.  Its pair statistics are
+        // discarded.  With several parts (GPUs) the seed tiles are split by COLUMN chunk (chunk % parts == part):
+        // a column's first visit, where every pair is a candidate, then happens on one GPU only, and the GPUs
+        // exchange the seeded maxima (all-reduce MAX) before their full passes.
+        // The seeding pass itself starts from zero thresholds; a pre-seed over every PRESEED-th seed row tile
+        // takes that warm-up on ~1/128 of the row tiles instead of 1/16.
+        static const int SEED = getenv("RR_SEED") ? atoi(getenv("RR_SEED")) : 16;        // tuning knobs (debug)
+        static const int PRESEED = getenv("RR_PRESEED") ? atoi(getenv("RR_PRESEED")) : 8;
         std::vector<um_unit> seed_units, preseed_units;
-        if (plan.rb_hi - plan.rb_lo >= 2 * SEED)
-            for (const um_unit &un : units) {
-                const int d = un.rt - plan.rb_lo;
-                if (d % SEED == SEED / 2) {
-                    seed_units.push_back(un);
-                    if ((d / SEED) % PRESEED == 0) preseed_units.push_back(un);
+        if (plan.n_rowblocks >= 2 * SEED) {
+            std::vector<keyed> ks;
+            for (int rb = SEED / 2; rb < plan.n_rowblocks; rb += SEED) {
+                const int cb0 = plan.unit_cb0[rb];
+                const int ncb = (int)(plan.unit_prefix[rb + 1] - plan.unit_prefix[rb]);
+                if (ncb <= 0) continue;
+                for (int cc = cb0 / UNIT_CT; cc <= (cb0 + ncb - 1) / UNIT_CT; cc++) {
+                    if (cc % plan.part_count != plan.part_index) continue;
+                    um_unit un = {rb, std::max(cb0, cc * UNIT_CT), std::min(cb0 + ncb, (cc + 1) * UNIT_CT)};
+                    ks.push_back({((int64_t)(cc / GC) << 32) + ((int64_t)rb << 12) + (cc % (GC * 64)), un});
                 }
             }
+            std::sort(ks.begin(), ks.end(), [](const keyed &x, const keyed &y) { return x.key < y.key; });
+            for (const keyed &k : ks) {
+                seed_units.push_back(k.u);
+                if ((k.u.rt / SEED) % PRESEED == 0) preseed_units.push_back(k.u);
+            }
+        }
         seed_units.insert(seed_units.end(), preseed_units.begin(), preseed_units.end());  // stored behind the seed list
         S->executed_ops = kblocks * (int64_t)(2LL * UM_M * UM_N * UM_KB);
         S->n_units = (int)units.size();
@@ -677,7 +696,9 @@ int rr_umma_scan(rr_umma_state *&S, int fp4, uint64_t plan_id, rr_scan_params &P
         if (S->n_preseed > 0) {
             V.units = S->d_units + S->n_units + S->n_seed;
             V.n_units = S->n_preseed;
+            V.P.flags |= 0x2000u;  // subsample first-visit columns
             launch(std::min<int>(n_sm, V.n_units), V);
+            V.P.flags &= ~0x2000u;
             rr_count_launch(1);
             UM_CUDA(cudaGetLastError());
         }

@@ -20,7 +20,8 @@ for p in range(parts):
                     pk.scan(mincov=30, variant="auto", part_index=q, part_count=parts, flags=rr.FLAG_SEED_ONLY)
                     seeds.append(pk.fetch()[0])
                 thr = np.maximum.reduce(seeds)
-                pk.scan(mincov=30, variant="auto", part_index=p, part_count=parts, flags=rr.FLAG_SEED_ONLY)
+                st0 = pk.scan(mincov=30, variant="auto", part_index=p, part_count=parts, flags=rr.FLAG_SEED_ONLY)
+                print("   seed pass ms", round(st0["kernel_ms"], 2), end="")
                 pk.set_thresholds(thr)
                 st = pk.scan(mincov=30, variant="auto", part_index=p, part_count=parts, flags=rr.FLAG_SKIP_SEED)
                 dt = 0.0
