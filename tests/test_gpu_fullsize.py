@@ -1,0 +1,80 @@
+"""BASELINE.json configs[1] at full size (Tree_1perc_30000: ~13.6k rows x ~133k columns, 3.5e10 pair tests)
+on the GPU, checked through size-independent properties - a full oracle scan would take ~24 core-hours:
+  (a) the two independent count kernels (tcgen05 e2m1 GEMM, bitset AND+POPC) agree bit for bit on all
+      5N maxima and arg-max partners, and on the pair-test count (which must also equal the host plan);
+  (b) an exact 1/k cyclic row sample of the oracle (the reference's own `ii % NTHREADS == thread` split,
+      MaxCorrelation.c:796) is a lower bound everywhere and is attained on the sampled rows whose best
+      partner lies to their right;
+  (c) every reported maximum is reproduced from its reported partner by the oracle's counts and score;
+  (d) idempotence: a second scan of the same packed MSA returns the same bits;
+  (e) the 8-way partition merges to the same result."""
+import numpy as np
+import pytest
+
+import repeatresolver_b200 as rr
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def config2():
+    g = rr.MsaGen(type="Tree", copies=100, coverage=40, repeat_len=30000, diff=0.01, seed=1002, threads=16)
+    msa = rr.MSA.alloc(g.rows, g.cols, codes=True)
+    g.codes(out=msa.cells())
+    pk = rr.Packed(msa, 0)
+    yield g, msa, pk
+    pk.close()
+
+
+def test_config2_properties(config2):
+    g, msa, pk = config2
+    assert g.rows > 13000 and g.cols > 120000
+    st = pk.scan(mincov=30, variant="auto")
+    M, A = pk.fetch()
+    assert st["pair_tests"] > 3e10 and rr.VARIANT_NAMES[st["variant"]] == "umma_f4"
+    # (d)
+    st2 = pk.scan(mincov=30, variant="auto")
+    M2, A2 = pk.fetch()
+    assert (M2 == M).all() and (A2 == A).all() and st2["pair_tests"] == st["pair_tests"]
+    # (a)
+    stb = pk.scan(mincov=30, variant="bitset")
+    Mb, Ab = pk.fetch()
+    assert stb["pair_tests"] == st["pair_tests"]
+    assert (Mb == M).all() and (Ab == A).all()
+    # (e)
+    parts = 8
+    Mm = np.zeros_like(M); Am = np.full_like(A, -1); Pm = 0
+    for p in range(parts):
+        s = pk.scan(mincov=30, variant="auto", part_index=p, part_count=parts)
+        Mp, Ap = pk.fetch()
+        Pm += s["pair_tests"]
+        better = (Mp > Mm) | ((Mp == Mm) & (Mp > 0) & (Ap >= 0) & ((Am < 0) | (Ap < Am)))
+        Mm = np.where(better, Mp, Mm); Am = np.where(better, Ap, Am)
+    assert Pm == st["pair_tests"] and (Mm == M).all() and (Am == A).all()
+    # (b), (c): oracle on the same code matrix
+    oracle = O.Oracle.from_codes(msa.cells())
+    gs, cv = pk.sizes()
+    assert (gs == oracle.gsize()).all() and (cv == oracle.coverage()).all()
+    k = 9973
+    Ms, As, Ps = oracle.scan(30, modulus=k, res_lo=0, res_hi=1)
+    assert Ps > 1e6
+    assert (M >= Ms * (1 - REL_TOL)).all()
+    rows = np.nonzero((Ms > 0) & ((np.arange(len(Ms)) // 5) % k == 0))[0]
+    right = rows[(As[rows] > rows) & (A[rows] > rows)]
+    assert len(right) >= 5
+    assert (np.abs(M[right] - Ms[right]) <= REL_TOL * Ms[right]).all()
+    rng = np.random.default_rng(7)
+    for gidx in rng.choice(np.nonzero(M > 0)[0], 400, replace=False):
+        i, j = min(gidx, A[gidx]), max(gidx, A[gidx])
+        c = oracle.counts(i, j)
+        z = O.score(c[0], c[1], c[2], c[3], gs[i], gs[j])
+        assert abs(z - M[gidx]) <= REL_TOL * z
+    # saturated scores exist at this depth and follow 98 + 2s/(|Gi|+|Gj|)
+    sat = np.nonzero(M > 98)[0]
+    assert len(sat) > 100
+    for gidx in sat[:50]:
+        i, j = min(gidx, A[gidx]), max(gidx, A[gidx])
+        c = oracle.counts(i, j)
+        assert M[gidx] == 98.0 + 2.0 * c[0] / (gs[i] + gs[j])

@@ -237,3 +237,27 @@ def test_threshold_exchange_device_pointers():
     M3, A3 = pk.fetch()
     assert (M3 == M).all() and (A3 == A).all()
     pk.close()
+
+
+@pytest.mark.parametrize("n_gpus", [2, 4, 8])
+def test_whole_path_on_several_gpus(n_gpus, tmp_path):
+    """rr_maxcorr_run with one host thread per GPU: pack everywhere, seeding pass, threshold exchange, full
+    pass per part, max-merge; byte-identical text with host finalisation.  Also the CLI with -p."""
+    if rr.device_count() < n_gpus:
+        pytest.skip(f"needs {n_gpus} GPUs")
+    g = rr.MsaGen(type="Tree", copies=10, coverage=30, repeat_len=2500, diff=0.02, seed=71, flank=2500, min_overlap=200)
+    codes = g.codes()
+    oracle = O.Oracle.from_codes(codes)
+    M0, A0, P0 = oracle.scan(30)
+    msa = rr.MSA.from_cells(codes)
+    for variant in VARIANTS:
+        M, A, st = rr.Parallel_AllMaxCorrsRechner(msa, 30, n_gpus, variant, rr.FLAG_HOST_FINALIZE)
+        assert st["pair_tests"] == P0
+        assert (M == M0).all() and (A == A0).all()
+        M1, A1, st1 = rr.Parallel_AllMaxCorrsRechner(msa, 30, n_gpus, variant, 0)
+        check_against_oracle(M1, A1, st1["pair_tests"], oracle, 30, M0, A0, P0)
+    (tmp_path / "MSAreal").write_bytes(g.text())
+    exe = os.path.join(ROOT, "repeatresolver_b200", "bin", "MaxCorrelation")
+    r = subprocess.run([exe, "MSAreal", "-c", "30", "-p", str(n_gpus)], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "MaxCorrsOf_MSAreal").read_bytes() == O.fmt_lines(M0)
