@@ -136,7 +136,7 @@ extern "C" double rr_score_host(uint32_t s, uint32_t gr1, uint32_t gr2, uint32_t
 extern "C" double rr_score_bound_host(uint32_t s, uint32_t gr1, uint32_t gr2, uint32_t cov)
 {
     std::vector<double> &t = host_lnfact((size_t)cov + 2);
-    return rr_score_upper_bound(t.data(), s, gr1, gr2, cov);
+    return rr_bound_effective(rr_score_upper_bound(t.data(), s, gr1, gr2, cov));
 }
 
 extern "C" int rr_below_median_host(uint32_t s, uint32_t gr1, uint32_t gr2, uint32_t cov)

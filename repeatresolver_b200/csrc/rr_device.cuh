@@ -103,7 +103,7 @@ __device__ __forceinline__ double rr_pair_score(const rr_scan_params &P, unsigne
         if (m > RR_BOUND_MEDIAN && rr_below_median(s, gr1, gr2, cov)) return -1.0;
         if (m > 0.0) {
             n_bound++;
-            if (rr_score_upper_bound(P.lnfact, s, gr1, gr2, cov) < m) return -1.0;
+            if (rr_bound_effective(rr_score_upper_bound(P.lnfact, s, gr1, gr2, cov)) < m) return -1.0;
         }
     }
     n_exact++;
@@ -155,7 +155,7 @@ __device__ __forceinline__ bool rr_tier1(const rr_scan_params &P, const LT &T, u
     if (x > hi) x = hi;
     if (x + cov < gr1 + gr2) x = gr1 + gr2 - cov;
     const double lp = rr_lnchoose_t(T, gr2, x) + rr_lnchoose_t(T, cov - gr2, gr1 - x) - lnc3;
-    return !(-RR_LOG10E * lp + 1e-6 < thr);
+    return !(rr_bound_effective(-RR_LOG10E * lp + 1e-6) < thr);
 }
 
 // tier 0 + 1 without branches (the epilogue evaluates it for every admissible column of a site; straight-line
@@ -177,7 +177,7 @@ __device__ __forceinline__ bool rr_tier1_flat(const LT &T, unsigned s, unsigned 
     x = x < hi ? x : hi;
     x = x > lo ? x : lo;
     const double lp = ((T(gr2) - T(x)) - T(gr2 - x)) + ((T(cov - gr2) - T(gr1 - x)) - T((cov + x) - sum)) - lnc3;
-    const bool pr = (thr > 0.0) & (-RR_LOG10E * lp + 1e-6 < thr);
+    const bool pr = (thr > 0.0) & (rr_bound_effective(-RR_LOG10E * lp + 1e-6) < thr);
     bound_used = nz & !med;
     return nz & (no_prune | !(med | pr | dbg_skip));
 }
@@ -203,7 +203,9 @@ __device__ __forceinline__ bool rr_tier1_f32(const LTF &T, unsigned s, unsigned 
     x = x < hi ? x : hi;
     x = x > lo ? x : lo;
     const float lp = ((T(gr2) - T(x)) - T(gr2 - x)) + ((T(cov - gr2) - T(gr1 - x)) - T((cov + x) - sum)) - lnc3;
-    const bool pr = (thr > 0.0f) & (-(float)RR_LOG10E * lp + margin < thr);
+    const float U = -(float)RR_LOG10E * lp + margin;
+    // a raw score above 98 saturates to 98 + F, which may exceed it: no pruning there (rr_bound_effective)
+    const bool pr = (thr > 0.0f) & (U < thr) & (U <= (float)RR_SATURATION_START);
     return nz & (no_prune | !(med | pr | dbg_skip));
 }
 
@@ -232,7 +234,7 @@ __device__ __forceinline__ bool rr_tier2(const LT &T, unsigned s, unsigned gr1, 
         if (term < 1e-3f * S) break;
     }
     const double U2 = -RR_LOG10E * lp - (double)(__log2f(S) * 0.30103f * 0.99999f) + 2e-5;
-    return !(U2 < thr);
+    return !(rr_bound_effective(U2) < thr);
 }
 
 __device__ __forceinline__ void rr_queue_push(rr_cand *q, int &count, bool need, const rr_cand &c, int lane)

@@ -162,9 +162,13 @@ RR_HD double rr_positive_significance(const double *lnf, unsigned int s, unsigne
  *  (2) P[X >= s] >= pmf(x) for every x >= s inside the support, so the score is
  *      <= -log10 pmf(x); x = s when s is above the mean, else a point next to the mean
  *      (any admissible x is valid, so the mean may be computed approximately).
- * The caps only lower the score (min with 99, then 98+F <= 99), and bound (2) is
- * compared with a 1e-6 margin, far above the 2.5e-11 noise of the lnfact differences.
+ * Bound (2) is compared with a 1e-6 margin, far above the 2.5e-11 noise of the lnfact
+ * differences.  Saturation: a raw score above 98 is REPLACED by 98 + F in (98, 99], which can
+ * exceed the raw score (raw 98.4 -> e.g. 98.95), so a bound above 98 proves nothing below 99:
+ * rr_bound_effective() maps it to 99 and such pairs are never pruned.
  */
+#define RR_SATURATION_START 98.0
+#define RR_SCORE_MAX 99.0
 #define RR_BOUND_MEDIAN 0.30103001
 
 RR_HD int rr_below_median(unsigned int s, unsigned int gr1, unsigned int gr2, unsigned int cov)
@@ -184,6 +188,12 @@ RR_HD double rr_score_upper_bound(const double *lnf, unsigned int s, unsigned in
     if (x + cov < gr1 + gr2) x = gr1 + gr2 - cov;
     lp = rr_hyper_lnpdf_unchecked(lnf, x, gr2, cov - gr2, gr1);
     return -RR_LOG10E * lp + 1e-6;
+}
+
+/* what a bound on the raw score says about the final score */
+RR_HD double rr_bound_effective(double raw_bound)
+{
+    return raw_bound > RR_SATURATION_START ? RR_SCORE_MAX + 1.0 : raw_bound;
 }
 
 #endif /* RR_SCORE_H */

@@ -261,3 +261,23 @@ def test_whole_path_on_several_gpus(n_gpus, tmp_path):
     r = subprocess.run([exe, "MSAreal", "-c", "30", "-p", str(n_gpus)], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert (tmp_path / "MaxCorrsOf_MSAreal").read_bytes() == O.fmt_lines(M0)
+
+
+def test_pruning_is_sound_at_depth_with_saturation():
+    """R ~ 1.8k rows, 1.2e9 pair tests, thousands of saturated (> 98) maxima: the pruned scans of all variants
+    must be bitwise equal to the scan that evaluates every pair exactly (RR_FLAG_NO_PRUNE).  Regression test
+    for the saturation window: a raw score in (98, 99) is replaced by 98 + F, which may exceed it."""
+    g = rr.MsaGen(type="Tree", copies=25, coverage=40, repeat_len=10000, diff=0.01, seed=1004)
+    msa = rr.MSA.alloc(g.rows, g.cols, codes=True)
+    g.codes(out=msa.cells())
+    pk = rr.Packed(msa, 0)
+    st = pk.scan(mincov=30, variant="umma_f4", flags=rr.FLAG_NO_PRUNE)
+    M0, A0 = pk.fetch()
+    assert st["exact_evals"] > 0.5 * st["pair_tests"] and (M0 > 98).sum() > 1000
+    for variant in VARIANTS:
+        for _ in range(2):
+            s = pk.scan(mincov=30, variant=variant)
+            M, A = pk.fetch()
+            assert s["pair_tests"] == st["pair_tests"] and s["exact_evals"] < 0.1 * s["pair_tests"]
+            assert (M == M0).all() and (A == A0).all(), variant
+    pk.close()

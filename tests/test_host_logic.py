@@ -115,9 +115,8 @@ def test_pruning_bounds_are_upper_bounds():
             continue
         mean = gr1 * gr2 / cov
         s = int(np.clip(int(mean + rng.normal() * 3 * max(1.0, mean ** 0.5)), lo, hi))
-        z = O.score(s, gr1, gr2, cov, 10 ** 6, 10 ** 6)
-        if z >= 98:
-            continue
+        # sizes chosen so that the saturated branch returns its largest possible value, 98 + 2s/(2s) = 99
+        z = O.score(s, gr1, gr2, cov, s, s)
         u = rr.score_bound_host(s, gr1, gr2, cov)
         assert u >= z, (s, gr1, gr2, cov, z, u)
         checked += 1
@@ -127,12 +126,27 @@ def test_pruning_bounds_are_upper_bounds():
     assert checked > 5000 and med > 500
 
 
+def test_bound_covers_the_saturation_window():
+    """raw scores in (98, 99) are replaced by 98 + F, which may be LARGER than the raw score: the effective
+    bound must not drop below 99 there"""
+    import math
+    hits = 0
+    for cov, gr1, gr2 in [(640, 300, 320), (700, 330, 340), (800, 380, 390), (1000, 470, 480), (900, 400, 450)]:
+        for s in range(max(1, gr1 + gr2 - cov), min(gr1, gr2) + 1):
+            raw = -math.log10(max(O.hyper_Q(s - 1, gr2, cov - gr2, gr1), 1e-300))
+            if 97.5 < raw < 99.5:
+                z = O.score(s, gr1, gr2, cov, s, s)       # F = 1 -> 99 when saturated
+                assert rr.score_bound_host(s, gr1, gr2, cov) >= z
+                hits += 98 < raw < 99
+    assert hits >= 3
+
+
 def test_median_bound_exhaustive_small_populations():
     for cov in range(2, 41):
         for gr1 in range(1, cov + 1):
             for gr2 in range(1, cov + 1):
                 for s in range(max(1, gr1 + gr2 - cov), min(gr1, gr2) + 1):
-                    z = O.score(s, gr1, gr2, cov, 10 ** 6, 10 ** 6)
+                    z = O.score(s, gr1, gr2, cov, s, s)
                     if rr.below_median_host(s, gr1, gr2, cov):
                         assert z <= 0.30103001
                     assert rr.score_bound_host(s, gr1, gr2, cov) >= z
