@@ -60,7 +60,7 @@ enum {
 #define RR_FLAG_GENERAL_BREAK 4u /* force the general first-break computation (MaxCorrelation.c:807-810)
                                     even when every row is one contiguous span */
 
-#define RR_FLAG_SEED_ONLY 8u     /* run only the seeding pass (every 16th row tile of this part): multi-GPU runs
+#define RR_FLAG_SEED_ONLY 8u     /* run only the seeding pass (every 32nd row tile): multi-GPU runs
                                     exchange the resulting maxima as thresholds before the full pass */
 #define RR_FLAG_SKIP_SEED 16u    /* keep the running maxima already on the device (previous RR_FLAG_SEED_ONLY
                                     scan and/or rr_scan_set_thresholds) and go straight to the full pass */

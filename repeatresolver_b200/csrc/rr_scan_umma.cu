@@ -114,7 +114,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 // for the single-lane producer / MMA warps: back off so the spin does not steal issue slots from the epilogue
 __device__ __forceinline__ void mbar_wait_sleep(unsigned long long *bar, uint32_t parity, unsigned ns)
 {
+#ifdef RR_NO_SLEEP
+    (void)ns;
+    while (!mbar_try_wait(bar, parity)) {}
+#else
     while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+#endif
 }
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1)
 {
@@ -614,8 +619,8 @@ int rr_umma_scan(rr_umma_state *&S, int fp4, uint64_t plan_id, rr_scan_params &P
         // a column's first visit, where every pair is a candidate, then happens on one GPU only, and the GPUs
         // exchange the seeded maxima (all-reduce MAX) before their full passes.
         // The seeding pass itself starts from zero thresholds; a pre-seed over every PRESEED-th seed row tile
-        // takes that warm-up on ~1/128 of the row tiles instead of 1/16.
-        static const int SEED = getenv("RR_SEED") ? atoi(getenv("RR_SEED")) : 16;        // tuning knobs (debug)
+        // takes that warm-up on ~1/256 of the row tiles instead of 1/32.
+        static const int SEED = getenv("RR_SEED") ? atoi(getenv("RR_SEED")) : 32;        // tuning knobs (debug)
         static const int PRESEED = getenv("RR_PRESEED") ? atoi(getenv("RR_PRESEED")) : 8;
         std::vector<um_unit> seed_units, preseed_units;
         if (plan.n_rowblocks >= 2 * SEED) {
