@@ -168,7 +168,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="Tree_1perc_30000", choices=sorted(WORKLOADS))
-    ap.add_argument("--variant", default="auto", choices=["auto", "bitset", "umma", "umma_f4"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "bitset", "umma", "umma_f4", "umma_mxf4"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -293,21 +293,26 @@ def main():
 
     # ---- roofline of the dominant kernel -------------------------------------------------------
     peaks, peak_src = load_peaks()
-    if variant_used in ("umma", "umma_f4"):
+    if variant_used in ("umma", "umma_f4", "umma_mxf4"):
         # algorithmic work: 2*R 8-bit-rate tensor ops per pair test (the reference touches all
         # R/64+1 words per intersection); peak: dense INT8/FP8-rate = 2 x the measured bf16 cuBLAS burst
         # (MEASURED_PEAKS.json has no 8-bit figure; the datasheet ratio is exactly 2)
         algo = 2.0 * R * P_total
         achieved = algo / (k_ms * 1e-3) / 1e12
         peak = 2.0 * peaks["bf16_tflops"] * world
-        ops = ("int8 mul+add (tcgen05 kind::i8), 2*R per pair test" if variant_used == "umma" else
-               "0/1 as e2m1 mul+add at the 8-bit rate (tcgen05 kind::f8f6f4, fp32 accumulate), 2*R per pair test")
+        ops = {"umma": "int8 mul+add (tcgen05 kind::i8), 2*R per pair test",
+               "umma_f4": "0/1 as e2m1 mul+add at the 8-bit rate (tcgen05 kind::f8f6f4, fp32 accumulate), 2*R per pair test",
+               "umma_mxf4": "0/1 as packed e2m1 with unit block scales (tcgen05 kind::mxf4.block_scale, fp32 accumulate; "
+                            "this kind runs at twice the 8-bit rate), 2*R per pair test; peak kept at the 8-bit (INT8) rate "
+                            "the north star names"}[variant_used]
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": TRAFFIC.get(args.workload), "ops": ops,
                 "peak_source": f"2 x {peak_src} bf16 burst ({peaks['bf16_tflops']} TF/s) per GPU",
                 "executed_ops_per_step": st["executed_ops"] * world,
                 "executed_frac_of_algorithmic": st["executed_ops"] * world / algo if algo else None,
                 "executed_tflops": st["executed_ops"] * world / (k_ms * 1e-3) / 1e12}
+        if variant_used == "umma_mxf4":
+            roof["frac_of_fp4_rate"] = achieved / (2.0 * peak)
     else:
         # AND+POPC variant: issue-bound on the POPC pipe (16 lanes/clk/SM); reported against that peak
         words = P_total * ((R + 31) // 32)
@@ -326,7 +331,8 @@ def main():
     line = {"metric": "site-group pair tests/sec (MaxCorrelation)", "value": value, "unit": "pair tests/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": {"umma": "int8->int32 counts, f64 score", "umma_f4": "e2m1(0/1)->f32 counts, f64 score"}.get(
+            "dtype": {"umma": "int8->int32 counts, f64 score", "umma_f4": "e2m1(0/1)->f32 counts, f64 score",
+                      "umma_mxf4": "e2m1(0/1) x unit block scale ->f32 counts, f64 score"}.get(
                 variant_used, "u32 bitset counts, f64 score"),
             "data": "synthetic",
             "config": {"workload": args.workload, "rows": R, "cols": N, "mincov": MINCOV, "variant": variant_used,

@@ -44,12 +44,14 @@ extern "C" {
 
 /* which count kernel computes the read-set intersections (Schnitt, 114-125) */
 enum {
-    RR_VARIANT_AUTO = 0,   /* the faster one for this shape */
+    RR_VARIANT_AUTO = 0,   /* the fastest one by measurement: RR_VARIANT_UMMA_MXF4 */
     RR_VARIANT_BITSET = 1, /* shared-memory staged u32 bitsets, AND + POPC */
     RR_VARIANT_UMMA = 2,   /* int8 0/1 operands, tcgen05.mma kind::i8, int32 accumulators in TMEM */
-    RR_VARIANT_UMMA_F4 = 3 /* the same GEMM with the 0/1 operands stored as packed 4-bit e2m1 (half the HBM/L2
+    RR_VARIANT_UMMA_F4 = 3,/* the same GEMM with the 0/1 operands stored as packed 4-bit e2m1 (half the HBM/L2
                               bytes; TMA unpacks them into shared memory), tcgen05.mma kind::f8f6f4 at the 8-bit
                               rate, fp32 accumulators in TMEM (exact: counts < 2^24) */
+    RR_VARIANT_UMMA_MXF4 = 4 /* the packed e2m1 operands fed to tcgen05.mma kind::mxf4.block_scale with unit (2^0)
+                              block scales: 4-bit operands stay packed in shared memory, twice the 8-bit MMA rate */
 };
 
 /* flags */

@@ -56,7 +56,7 @@ extern "C" int rr_device_count(void)
 extern "C" int rr_variant_available(int variant)
 {
     if (variant == RR_VARIANT_BITSET || variant == RR_VARIANT_AUTO) return 1;
-    if (variant == RR_VARIANT_UMMA || variant == RR_VARIANT_UMMA_F4) return rr_umma_available();
+    if (variant == RR_VARIANT_UMMA || variant == RR_VARIANT_UMMA_F4 || variant == RR_VARIANT_UMMA_MXF4) return rr_umma_available();
     return 0;
 }
 
@@ -393,9 +393,10 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
     RR_CUDA(cudaEventRecord(e0, pk->st));
 
     int variant = opts->variant;
-    if (variant == RR_VARIANT_AUTO) variant = rr_umma_available() ? RR_VARIANT_UMMA_F4 : RR_VARIANT_BITSET;
-    if (variant != RR_VARIANT_BITSET && variant != RR_VARIANT_UMMA && variant != RR_VARIANT_UMMA_F4) { rr_set_error("unknown variant %d", variant); return RR_E_ARG; }
+    if (variant == RR_VARIANT_AUTO) variant = rr_umma_available() ? RR_VARIANT_UMMA_MXF4 : RR_VARIANT_BITSET;
+    if (variant != RR_VARIANT_BITSET && variant != RR_VARIANT_UMMA && variant != RR_VARIANT_UMMA_F4 && variant != RR_VARIANT_UMMA_MXF4) { rr_set_error("unknown variant %d", variant); return RR_E_ARG; }
 
+    const int umma_mode = variant == RR_VARIANT_UMMA_MXF4 ? 2 : variant == RR_VARIANT_UMMA_F4 ? 1 : 0;
     // ---- host plan: filters, first-break columns, tiles, partition (O(N)); cached between scans ----
     const bool general = !pk->contiguous || (opts->flags & RR_FLAG_GENERAL_BREAK);
     scan_cache &C = pk->cache;
@@ -420,7 +421,7 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
         const int tj = variant == RR_VARIANT_BITSET ? rr_bitset_tj() : rr_umma_col_sites();
         rr_plan_build(C.plan, R, N, mincov, pk->h_gsize.data(), pk->h_coverage.data(), breakcol.data(),
                       pk->contiguous && !general ? pk->h_start.data() : nullptr,
-                      pk->contiguous && !general ? pk->h_end.data() : nullptr, ti, tj, variant == RR_VARIANT_BITSET ? 32 : rr_umma_kblock(),
+                      pk->contiguous && !general ? pk->h_end.data() : nullptr, ti, tj, variant == RR_VARIANT_BITSET ? 32 : rr_umma_kblock(umma_mode),
                       variant == RR_VARIANT_BITSET ? 8 : 75, opts->part_index, opts->part_count);
         RR_TRACE("plan");
         if ((rc = upload(&C.sb.rowok, C.plan.rowok, pk->st))) return rc;
@@ -459,7 +460,7 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
         if (variant == RR_VARIANT_BITSET) {
             if (!(opts->flags & RR_FLAG_SEED_ONLY)) RR_CUDA(rr_launch_scan_bitset(P, pk->n_sm, pk->st));  // no seeding pass in this variant
         } else {
-            rc = rr_umma_scan(pk->umma, variant == RR_VARIANT_UMMA_F4, C.plan_id, P, plan, pk->d_cells, pk->d_perm, pk->codes, pk->n_sm, pk->st);
+            rc = rr_umma_scan(pk->umma, umma_mode, C.plan_id, P, plan, pk->d_cells, pk->d_perm, pk->codes, pk->n_sm, pk->st);
             if (rc) return rc;
         }
     }

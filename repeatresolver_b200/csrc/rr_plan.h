@@ -38,7 +38,7 @@ struct rr_scan_params;
 int rr_umma_available(void);
 int rr_umma_row_sites(void);
 int rr_umma_col_sites(void);
-int rr_umma_kblock(void);
+int rr_umma_kblock(int mode);
 void rr_umma_free(rr_umma_state *s);
-int rr_umma_scan(rr_umma_state *&s, int fp4, uint64_t plan_id, rr_scan_params &P, rr_plan &plan, const uint8_t *d_cells,
+int rr_umma_scan(rr_umma_state *&s, int mode /* 0 int8, 1 e2m1 f8f6f4, 2 e2m1 mxf4 */, uint64_t plan_id, rr_scan_params &P, rr_plan &plan, const uint8_t *d_cells,
                  const int32_t *d_perm, int codes, int n_sm, cudaStream_t st);

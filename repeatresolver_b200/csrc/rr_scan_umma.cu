@@ -49,6 +49,7 @@ constexpr int UM_SUB = UM_EPI_WARPS / 4;         // epilogue warps per TMEM lane
 constexpr int UM_WSITES = UM_COL_SITES / UM_SUB; // column sites per warp and tile (16)
 constexpr int UM_TMEM_COLS = 512;
 constexpr int UM_ACC_STRIDE = 256;               // TMEM columns between the two accumulators
+constexpr int UM_SF_COL = 240;                   // 16 spare TMEM columns behind accumulator 0: unit block scales (mxf4)
 
 struct um_wmeta {                                 // per epilogue warp: metadata of its column groups in the tile
     float mj[UM_WSITES * 5];                      // running maxima, rounded down to float (thresholds only)
@@ -134,11 +135,21 @@ __device__ __forceinline__ void tc_commit(unsigned long long *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]; F4 = false: int8 x int8 -> int32, true: e2m1 x e2m1 -> fp32
-template <bool F4>
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+// D[tmem] (+)= A[smem] * B[smem].  MODE 0: int8 x int8 -> int32 (kind::i8); 1: e2m1 x e2m1 -> fp32 at the 8-bit
+// rate (kind::f8f6f4, operands unpacked to one element per byte in smem); 2: packed e2m1 with unit block scales
+// (kind::mxf4.block_scale, UE8M0 scale 2^0 per 32 elements, K = 64 per instruction, twice the 8-bit rate)
+template <int MODE>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                       uint32_t tsfa, uint32_t tsfb)
 {
-    if constexpr (F4)
+    if constexpr (MODE == 2)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tsfa), "r"(tsfb)
+            : "memory");
+    else if constexpr (MODE == 1)
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "setp.ne.b32 p, %4, 0;\n\t"
@@ -168,10 +179,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr)
 // instruction descriptor, both operands K-major, M = 128, N = 240:
 //   kind::i8      D = S32 (2), A = B = unsigned 8 bit (0)
 //   kind::f8f6f4  D = F32 (1), A = B = E2M1 (5)
-template <bool F4>
+//   kind::mxf4    block-scaled descriptor: A = B = E2M1 (1), scale format UE8M0 (bit 23), scale ids 0, K = 64
+template <int MODE>
 __device__ __forceinline__ uint32_t make_idesc()
 {
-    const uint32_t cfmt = F4 ? 1u : 2u, abfmt = F4 ? 5u : 0u;
+    if constexpr (MODE == 2)
+        return (1u << 7) | (1u << 10) | ((uint32_t)(UM_N >> 3) << 17) | (1u << 23) | ((uint32_t)(UM_M >> 4) << 24);
+    const uint32_t cfmt = MODE == 1 ? 1u : 2u, abfmt = MODE == 1 ? 5u : 0u;
     return (cfmt << 4) | (abfmt << 7) | (abfmt << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(UM_N >> 3) << 17) |
            ((uint32_t)(UM_M >> 4) << 24);
 }
@@ -212,7 +226,7 @@ struct um_lnf {
     }
 };
 
-template <bool ALL_SMEM, bool F4>
+template <bool ALL_SMEM, int MODE>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const um_params U)
 {
@@ -237,6 +251,21 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = T->tmem_base;
+    if constexpr (MODE == 2) {
+        // unit block scales: every byte of TMEM columns 240..255 = 0x7F (UE8M0 2^0), in all 128 lanes, so that the
+        // MMA reads 1.0 wherever its scale-factor layout points inside that window
+        if (warp >= UM_FIRST_EPI_WARP && warp < UM_FIRST_EPI_WARP + 4) {
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)UM_SF_COL;
+            const uint32_t one = 0x7F7F7F7Fu;
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+                ::"r"(taddr), "r"(one) : "memory");
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -253,10 +282,11 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const uint32_t ph = (it / UM_STAGES) & 1;
                         mbar_wait_sleep(&T->empty[s], ph ^ 1, 64);
                         // the transaction count is in HBM-side bytes: packed e2m1 delivers half the smem footprint
-                        mbar_expect_tx(&T->full[s], F4 ? UM_STAGE_BYTES / 2 : UM_STAGE_BYTES);
+                        mbar_expect_tx(&T->full[s], MODE == 1 ? UM_STAGE_BYTES / 2 : UM_STAGE_BYTES);
                         uint8_t *sa = smem + (size_t)s * UM_STAGE_BYTES;
-                        tma_load_2d(sa, &map_a, &T->full[s], kb * UM_KB, un.rt * UM_M);
-                        tma_load_2d(sa + UM_A_BYTES, &map_b, &T->full[s], kb * UM_KB, ct * UM_N);
+                        constexpr int KREADS = MODE == 2 ? 2 * UM_KB : UM_KB;  // reads per 128-byte smem row
+                        tma_load_2d(sa, &map_a, &T->full[s], kb * KREADS, un.rt * UM_M);
+                        tma_load_2d(sa + UM_A_BYTES, &map_b, &T->full[s], kb * KREADS, ct * UM_N);
                     }
                 }
             }
@@ -264,7 +294,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc<F4>();
+            const uint32_t idesc = make_idesc<MODE>();
             uint32_t it = 0, tile = 0;
             for (int u = blockIdx.x; u < U.n_units; u += gridDim.x) {
                 const um_unit un = U.units[u];
@@ -288,8 +318,8 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                         for (int k = 0; k < UM_KB / 32; k++) {
                             // advance 32 bytes (one K=32 slice) inside the 128 B swizzle span: +2 in 16 B units
-                            tc_mma<F4>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                      (kb > klo || k > 0) ? 1u : 0u);
+                            tc_mma<MODE>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                         (kb > klo || k > 0) ? 1u : 0u, tmem_base + UM_SF_COL, tmem_base + UM_SF_COL + 8);
                         }
                         tc_commit(&T->empty[s]);  // frees the smem stage when these MMAs retire
                     }
@@ -368,7 +398,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (has_counts) {
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                        for (int b = 0; b < 5; b++) c[b] = F4 ? (int)__uint_as_float(v[b]) : (int)v[b];
+                        for (int b = 0; b < 5; b++) c[b] = MODE != 0 ? (int)__uint_as_float(v[b]) : (int)v[b];
                         if (t + UM_SUB < t_end) TMEM_LD_8(v, taddr0 + 5 * (t + UM_SUB));
                     } else {
 #pragma unroll
@@ -472,7 +502,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t Kp, uint32_t box_rows, bool fp4)
+static int make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t Kp, uint32_t box_rows, int mode)
 {
     static PFN_encodeTiled encode = nullptr;
     if (!encode) {
@@ -485,12 +515,14 @@ static int make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t Kp, ui
         encode = (PFN_encodeTiled)fn;
     }
     cuuint64_t dims[2] = {Kp, rows};
+    const bool fp4 = mode != 0;
     cuuint64_t strides[1] = {fp4 ? Kp / 2 : Kp};
-    cuuint32_t box[2] = {(cuuint32_t)UM_KB, box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)(mode == 2 ? 2 * UM_KB : UM_KB), box_rows};  // 128 bytes of smem per row
     cuuint32_t estr[2] = {1, 1};
     // fp4: packed 4-bit elements in HBM, expanded by the TMA unit to 16 elements per 16-byte chunk (8 data + 8
     // pad bytes) in shared memory - the layout kind::f8f6f4 reads; the box is still 128 bytes wide there
-    CUresult r = encode(map, fp4 ? CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    // mxf4: the packed nibbles go to shared memory as they are (16U4_ALIGN8B), 256 reads per 128-byte row
+    CUresult r = encode(map, mode == 2 ? CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN8B : mode == 1 ? CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { rr_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return RR_E_CUDA; }
     return RR_OK;
@@ -519,7 +551,7 @@ struct rr_umma_state {
 int rr_umma_available(void) { return 1; }
 int rr_umma_row_sites(void) { return UM_ROW_SITES; }
 int rr_umma_col_sites(void) { return UM_COL_SITES; }
-int rr_umma_kblock(void) { return UM_KB; }
+int rr_umma_kblock(int mode) { return mode == 2 ? 2 * UM_KB : UM_KB; }
 
 void rr_umma_free(rr_umma_state *s)
 {
@@ -553,15 +585,16 @@ static int grow(T **p, size_t *cap, size_t need)
     return RR_OK;
 }
 
-int rr_umma_scan(rr_umma_state *&S, int fp4, uint64_t plan_id, rr_scan_params &P, rr_plan &plan, const uint8_t *d_cells,
+int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &P, rr_plan &plan, const uint8_t *d_cells,
                  const int32_t *d_perm, int codes, int n_sm, cudaStream_t st)
 {
     int rc;
+    const int fp4 = mode != 0;            // modes 1 and 2 share the packed e2m1 operands
     const int md = fp4 ? 1 : 0;
     if (!S) {
         S = new rr_umma_state();
-        S->Kp = ((int64_t)P.R + UM_KB - 1) / UM_KB * UM_KB;
-        if (S->Kp == 0) S->Kp = UM_KB;
+        S->Kp = ((int64_t)P.R + 2 * UM_KB - 1) / (2 * UM_KB) * (2 * UM_KB);  // whole mxf4 K blocks (256 reads)
+        if (S->Kp == 0) S->Kp = 2 * UM_KB;
     }
     const int64_t row_bytes = fp4 ? S->Kp / 2 : S->Kp;
     if (!S->xb[md]) {
@@ -574,7 +607,7 @@ int rr_umma_scan(rr_umma_state *&S, int fp4, uint64_t plan_id, rr_scan_params &P
         UM_CUDA(rr_launch_pack_int8(d_cells, d_perm, P.R, P.N, codes, S->xb[md], S->Kp, fp4, st));
     }
     const bool seeding = !(P.flags & (RR_FLAG_NO_PRUNE | RR_FLAG_SKIP_SEED | 0x1000u));
-    if (S->built_plan_id != plan_id || S->built_md != md) {
+    if (S->built_plan_id != plan_id || S->built_md != mode) {
         // A operand for this plan's row sites
         const size_t xa_rows = (size_t)std::max(plan.n_rowblocks, 1) * UM_M;
         if (xa_rows > S->xa_rows_cap[md]) {
@@ -642,7 +675,7 @@ int rr_umma_scan(rr_umma_state *&S, int fp4, uint64_t plan_id, rr_scan_params &P
             }
         }
         seed_units.insert(seed_units.end(), preseed_units.begin(), preseed_units.end());  // stored behind the seed list
-        S->executed_ops = kblocks * (int64_t)(2LL * UM_M * UM_N * UM_KB);
+        S->executed_ops = kblocks * (int64_t)(2LL * UM_M * UM_N * UM_KB) * (mode == 2 ? 2 : 1);
         S->n_units = (int)units.size();
         S->n_preseed = (int)preseed_units.size();
         S->n_seed = (int)seed_units.size() - S->n_preseed;
@@ -657,20 +690,22 @@ int rr_umma_scan(rr_umma_state *&S, int fp4, uint64_t plan_id, rr_scan_params &P
             UM_CUDA(cudaMemcpyAsync(S->d_khi, plan.k_hi.data(), sizeof(int32_t) * plan.k_hi.size(), cudaMemcpyHostToDevice, st));
             UM_CUDA(cudaMemcpyAsync(S->d_klo, plan.k_lo.data(), sizeof(int32_t) * plan.k_lo.size(), cudaMemcpyHostToDevice, st));
             UM_CUDA(cudaStreamSynchronize(st));  // units[] is a local
-            if ((rc = make_map(&S->map_a, S->xa[md], xa_rows, (uint64_t)S->Kp, UM_M, fp4 != 0))) return rc;
-            if ((rc = make_map(&S->map_b, S->xb[md], (uint64_t)5 * P.N, (uint64_t)S->Kp, UM_N, fp4 != 0))) return rc;
+            if ((rc = make_map(&S->map_a, S->xa[md], xa_rows, (uint64_t)S->Kp, UM_M, mode))) return rc;
+            if ((rc = make_map(&S->map_b, S->xb[md], (uint64_t)5 * P.N, (uint64_t)S->Kp, UM_N, mode))) return rc;
         }
         S->built_plan_id = plan_id;
-        S->built_md = md;
+        S->built_md = mode;
     }
     plan.executed_ops = S->executed_ops;
     if (S->n_units == 0) return RR_OK;
 
     if (!S->attr_set) {
-        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
-        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
-        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
-        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
+        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
+        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
+        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
+        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
+        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
+        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
         S->attr_set = true;
     }
     um_params U;
@@ -688,12 +723,15 @@ int rr_umma_scan(rr_umma_state *&S, int fp4, uint64_t plan_id, rr_scan_params &P
     const bool all_smem = U.lnf_smem >= plan.max_cov + 1;
     const CUtensorMap &map_a = S->map_a, &map_b = S->map_b;
     auto launch = [&](int g, const um_params &prm) {
-        if (fp4) {
-            if (all_smem) rr_k_scan_umma<true, true><<<g, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
-            else rr_k_scan_umma<false, true><<<g, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
+        if (mode == 2) {
+            if (all_smem) rr_k_scan_umma<true, 2><<<g, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
+            else rr_k_scan_umma<false, 2><<<g, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
+        } else if (mode == 1) {
+            if (all_smem) rr_k_scan_umma<true, 1><<<g, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
+            else rr_k_scan_umma<false, 1><<<g, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
         } else {
-            if (all_smem) rr_k_scan_umma<true, false><<<g, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
-            else rr_k_scan_umma<false, false><<<g, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
+            if (all_smem) rr_k_scan_umma<true, 0><<<g, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
+            else rr_k_scan_umma<false, 0><<<g, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
         }
     };
     if (seeding && S->n_seed > 0) {

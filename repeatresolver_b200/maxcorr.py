@@ -13,7 +13,7 @@ import numpy as np
 from . import _lib
 from ._lib import ScanOpts, ScanStats, lib
 
-VARIANTS = {"auto": 0, "bitset": 1, "umma": 2, "umma_f4": 3}
+VARIANTS = {"auto": 0, "bitset": 1, "umma": 2, "umma_f4": 3, "umma_mxf4": 4}
 VARIANT_NAMES = {v: k for k, v in VARIANTS.items()}
 FLAG_NO_PRUNE = 1
 FLAG_HOST_FINALIZE = 2

@@ -1,6 +1,6 @@
 """BASELINE.json configs[1] at full size (Tree_1perc_30000: ~13.6k rows x ~133k columns, 3.5e10 pair tests)
 on the GPU, checked through size-independent properties - a full oracle scan would take ~24 core-hours:
-  (a) the two independent count kernels (tcgen05 e2m1 GEMM, bitset AND+POPC) agree bit for bit on all
+  (a) the independent count kernels (tcgen05 mxf4 / f8f6f4 / int8 GEMMs, bitset AND+POPC) agree bit for bit on all
       5N maxima and arg-max partners, and on the pair-test count (which must also equal the host plan);
   (b) an exact 1/k cyclic row sample of the oracle (the reference's own `ii % NTHREADS == thread` split,
       MaxCorrelation.c:796) is a lower bound everywhere and is attained on the sampled rows whose best
@@ -33,16 +33,17 @@ def test_config2_properties(config2):
     assert g.rows > 13000 and g.cols > 120000
     st = pk.scan(mincov=30, variant="auto")
     M, A = pk.fetch()
-    assert st["pair_tests"] > 3e10 and rr.VARIANT_NAMES[st["variant"]] == "umma_f4"
+    assert st["pair_tests"] > 3e10 and rr.VARIANT_NAMES[st["variant"]] == "umma_mxf4"
     # (d)
     st2 = pk.scan(mincov=30, variant="auto")
     M2, A2 = pk.fetch()
     assert (M2 == M).all() and (A2 == A).all() and st2["pair_tests"] == st["pair_tests"]
     # (a)
-    stb = pk.scan(mincov=30, variant="bitset")
-    Mb, Ab = pk.fetch()
-    assert stb["pair_tests"] == st["pair_tests"]
-    assert (Mb == M).all() and (Ab == A).all()
+    for other in ("bitset", "umma", "umma_f4"):
+        stb = pk.scan(mincov=30, variant=other)
+        Mb, Ab = pk.fetch()
+        assert stb["pair_tests"] == st["pair_tests"]
+        assert (Mb == M).all() and (Ab == A).all(), other
     # (e)
     parts = 8
     Mm = np.zeros_like(M); Am = np.full_like(A, -1); Pm = 0

@@ -18,7 +18,7 @@ REL_TOL = 1e-9  # BASELINE.json: "significance values match within a relative 1e
 
 
 def variants():
-    return ["bitset"] + [v for v in ("umma", "umma_f4") if rr.variant_available(v)]
+    return ["bitset"] + [v for v in ("umma", "umma_f4", "umma_mxf4") if rr.variant_available(v)]
 
 
 VARIANTS = variants()
