@@ -422,7 +422,7 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
         rr_plan_build(C.plan, R, N, mincov, pk->h_gsize.data(), pk->h_coverage.data(), breakcol.data(),
                       pk->contiguous && !general ? pk->h_start.data() : nullptr,
                       pk->contiguous && !general ? pk->h_end.data() : nullptr, ti, tj, variant == RR_VARIANT_BITSET ? 32 : rr_umma_kblock(umma_mode),
-                      variant == RR_VARIANT_BITSET ? 8 : 75, opts->part_index, opts->part_count);
+                      variant == RR_VARIANT_BITSET ? 8 : umma_mode == 2 ? 136 : 75, opts->part_index, opts->part_count);
         RR_TRACE("plan");
         if ((rc = upload(&C.sb.rowok, C.plan.rowok, pk->st))) return rc;
         if ((rc = upload(&C.sb.colok, C.plan.colok, pk->st))) return rc;
