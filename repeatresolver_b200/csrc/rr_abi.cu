@@ -229,10 +229,13 @@ static int pack_impl(const uint8_t *cells, int R, int N, int codes, int device, 
     if (ndev <= 0) { rr_set_error("no CUDA device: the scan has no CPU fallback"); return RR_E_NODEV; }
     if (device < 0 || device >= ndev) { rr_set_error("device %d out of range (%d devices)", device, ndev); return RR_E_ARG; }
     RR_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    RR_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) { rr_set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return RR_E_NODEV; }
-    pk->device = device; pk->n_sm = prop.multiProcessorCount;
+    // cudaGetDeviceProperties costs ~130 ms per call on this driver; two attributes are all that is needed
+    int cc_major = 0, cc_minor = 0, n_sm = 0;
+    RR_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+    RR_CUDA(cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, device));
+    RR_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    if (cc_major < 10) { rr_set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, cc_major, cc_minor); return RR_E_NODEV; }
+    pk->device = device; pk->n_sm = n_sm;
     pk->R = R; pk->N = N; pk->codes = codes;
     pk->W32 = ((R + 127) / 128) * 4;
     if (pk->W32 == 0) pk->W32 = 4;

@@ -629,22 +629,30 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
         // (GR A row-tiles + GC*UNIT_CT B column-tiles, a few tens of MB) that stays resident in the 126 MB L2.
         constexpr int UNIT_CT = 4, GR = 24, GC = 6;
         struct keyed { int64_t key; um_unit u; };
-        std::vector<keyed> ku;
+        // generated directly in block order (row group, chunk group, row tile, chunk): no sort needed
+        std::vector<um_unit> units;
         int64_t kblocks = 0;
-        for (int rb = plan.rb_lo; rb < plan.rb_hi; rb++) {
-            const int cb0 = plan.unit_cb0[rb];
-            const int ncb = (int)(plan.unit_prefix[rb + 1] - plan.unit_prefix[rb]);
-            if (ncb <= 0) continue;
-            for (int cc = cb0 / UNIT_CT; cc <= (cb0 + ncb - 1) / UNIT_CT; cc++) {
-                um_unit un = {rb, std::max(cb0, cc * UNIT_CT), std::min(cb0 + ncb, (cc + 1) * UNIT_CT)};
-                const int64_t key = ((((int64_t)((rb - plan.rb_lo) / GR) << 20) + (cc / GC)) << 32) + ((int64_t)rb << 12) + (cc % (GC * 64));
-                ku.push_back({key, un});
+        {
+            int cc_min = 0x7fffffff, cc_max = -1;
+            for (int rb = plan.rb_lo; rb < plan.rb_hi; rb++) {
+                const int cb0 = plan.unit_cb0[rb];
+                const int ncb = (int)(plan.unit_prefix[rb + 1] - plan.unit_prefix[rb]);
+                if (ncb <= 0) continue;
+                cc_min = std::min(cc_min, cb0 / UNIT_CT);
+                cc_max = std::max(cc_max, (cb0 + ncb - 1) / UNIT_CT);
+                for (int c = 0; c < ncb; c++) kblocks += std::max(0, plan.k_hi[rb] - plan.k_lo[cb0 + c]);
             }
-            for (int c = 0; c < ncb; c++) kblocks += std::max(0, plan.k_hi[rb] - plan.k_lo[cb0 + c]);
+            for (int rg = plan.rb_lo; rg < plan.rb_hi; rg += GR)
+                for (int cg = cc_max < 0 ? 1 : cc_min / GC; cc_max >= 0 && cg <= cc_max / GC; cg++)
+                    for (int rb = rg; rb < std::min(rg + GR, plan.rb_hi); rb++) {
+                        const int cb0 = plan.unit_cb0[rb];
+                        const int ncb = (int)(plan.unit_prefix[rb + 1] - plan.unit_prefix[rb]);
+                        if (ncb <= 0) continue;
+                        const int c_lo = std::max(cg * GC, cb0 / UNIT_CT), c_hi = std::min(cg * GC + GC - 1, (cb0 + ncb - 1) / UNIT_CT);
+                        for (int cc = c_lo; cc <= c_hi; cc++)
+                            units.push_back({rb, std::max(cb0, cc * UNIT_CT), std::min(cb0 + ncb, (cc + 1) * UNIT_CT)});
+                    }
         }
-        std::sort(ku.begin(), ku.end(), [](const keyed &x, const keyed &y) { return x.key < y.key; });
-        std::vector<um_unit> units(ku.size());
-        for (size_t q = 0; q < ku.size(); q++) units[q] = ku[q].u;
         // Seeding pass: the same kernel over every SEED-th row tile of the WHOLE MSA first.  It leaves true
         // (lower-bound) maxima in best[] for all column groups, so the full pass starts with thresholds close
         // to the final ones instead of 0 and the bounds prune from the first pair on.  Its pair statistics are
