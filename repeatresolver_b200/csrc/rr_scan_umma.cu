@@ -625,9 +625,11 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
         UM_CUDA(cudaGetLastError());
 
         // work units: (row tile, aligned chunk of UNIT_CT column tiles), this part's row tiles only, ordered in
-        // 2-D blocks of GR row tiles x GC chunks so that the ~148 units in flight at any time share a working set
+        // 2-D blocks of GR (48) row tiles x GC (3) chunks so that the ~148 units in flight at any time share a working set
         // (GR A row-tiles + GC*UNIT_CT B column-tiles, a few tens of MB) that stays resident in the 126 MB L2.
-        constexpr int UNIT_CT = 4, GR = 24, GC = 6;
+        constexpr int UNIT_CT = 4;
+        static const int GR = getenv("RR_GR") ? atoi(getenv("RR_GR")) : 48;   // tuning knobs (debug)
+        static const int GC = getenv("RR_GC") ? atoi(getenv("RR_GC")) : 3;
         struct keyed { int64_t key; um_unit u; };
         // generated directly in block order (row group, chunk group, row tile, chunk): no sort needed
         std::vector<um_unit> units;
