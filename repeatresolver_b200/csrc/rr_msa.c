@@ -20,6 +20,7 @@
 #include <unistd.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <pthread.h>
 #include "rr_host.h"
 
 static __thread char rr_errbuf[512];
@@ -75,35 +76,65 @@ static inline size_t line_strlen(const char *p, size_t raw)
     return z ? (size_t)(z - p) : raw;
 }
 
+/* copy the kept rows into the cell matrix with a few threads (the copy of a 1-2 GB MSA is memory-bound and
+ * dominates the host side once the scan itself takes a fraction of a second) */
+typedef struct { const char **rowp; uint8_t *cells; size_t cols; int r0, r1; } copy_job;
+static void *copy_rows_thread(void *x)
+{
+    copy_job *j = (copy_job *)x;
+    int r;
+    for (r = j->r0; r < j->r1; r++) memcpy(j->cells + (size_t)r * j->cols, j->rowp[r], j->cols);
+    return NULL;
+}
+
 int rr_msa_from_text(const char *text, size_t nbytes, rr_msa **out)
 {
-    size_t pos;
+    size_t pos = 0;
     long cols = -1;
-    int rows = 0, pass, rc;
+    int rows = 0, cap = 0, rc, t, nt;
+    const char **rowp = NULL;
     rr_msa *m = NULL;
+    pthread_t th[16];
+    copy_job jobs[16];
     if (!out || (!text && nbytes)) { rr_set_error("rr_msa_from_text: bad arguments"); return RR_E_ARG; }
-    for (pass = 0; pass < 2; pass++) {
-        int r = 0;
-        pos = 0;
-        while (pos < nbytes) {
-            const char *p = text + pos;
-            const char *nl = (const char *)memchr(p, '\n', nbytes - pos);
-            size_t raw = nl ? (size_t)(nl - p) + 1 : nbytes - pos;
-            size_t sl = line_strlen(p, raw);
-            pos += raw;
-            if (cols < 0) cols = (long)sl - 1;                 /* 291 */
-            if ((long)sl - 1 != cols) continue;                /* 299 */
-            if (pass == 1 && cols > 0) memcpy(m->cells + (size_t)r * cols, p, (size_t)cols);
-            r++;
+    /* pass 1 (sequential, memchr-bound): line boundaries and the keep rule */
+    while (pos < nbytes) {
+        const char *p = text + pos;
+        const char *nl = (const char *)memchr(p, '\n', nbytes - pos);
+        size_t raw = nl ? (size_t)(nl - p) + 1 : nbytes - pos;
+        size_t sl;
+        pos += raw;
+        /* strlen semantics need the NUL scan only when the line length could match */
+        if (cols >= 0 && (long)raw - 1 < cols) continue;
+        sl = line_strlen(p, raw);
+        if (cols < 0) cols = (long)sl - 1;                 /* 291 */
+        if ((long)sl - 1 != cols) continue;                /* 299 */
+        if (rows == cap) {
+            const char **np;
+            cap = cap ? cap * 2 : 1024;
+            np = (const char **)realloc((void *)rowp, sizeof(char *) * (size_t)cap);
+            if (!np) { free((void *)rowp); rr_set_error("out of host memory"); return RR_E_NOMEM; }
+            rowp = np;
         }
-        if (pass == 0) {
-            rows = r;
-            if (cols < 0) cols = 0;
-            if (cols > 0x7fffffffL / 8) { rr_set_error("MSA too wide (%ld columns)", cols); return RR_E_ARG; }
-            rc = rr_msa_alloc(rows, (int)cols, 0, &m);
-            if (rc) return rc;
-        }
+        rowp[rows++] = p;
     }
+    if (cols < 0) cols = 0;
+    if (cols > 0x7fffffffL / 8) { free((void *)rowp); rr_set_error("MSA too wide (%ld columns)", cols); return RR_E_ARG; }
+    rc = rr_msa_alloc(rows, (int)cols, 0, &m);
+    if (rc) { free((void *)rowp); return rc; }
+    /* pass 2: parallel copy */
+    nt = (size_t)rows * (size_t)cols > (1u << 24) ? 8 : 1;
+    if (cols > 0)
+        for (t = 0; t < nt; t++) {
+            jobs[t].rowp = rowp; jobs[t].cells = m->cells; jobs[t].cols = (size_t)cols;
+            jobs[t].r0 = (int)((long long)rows * t / nt); jobs[t].r1 = (int)((long long)rows * (t + 1) / nt);
+            if (nt == 1) copy_rows_thread(&jobs[t]);
+            else if (pthread_create(&th[t], NULL, copy_rows_thread, &jobs[t]) != 0) { copy_rows_thread(&jobs[t]); th[t] = 0; }
+        }
+    if (cols > 0 && nt > 1)
+        for (t = 0; t < nt; t++)
+            if (th[t]) pthread_join(th[t], NULL);
+    free((void *)rowp);
     *out = m;
     return RR_OK;
 }
