@@ -399,6 +399,8 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
     if (variant == RR_VARIANT_AUTO) variant = rr_umma_available() ? RR_VARIANT_UMMA_MXF4 : RR_VARIANT_BITSET;
     if (variant != RR_VARIANT_BITSET && variant != RR_VARIANT_UMMA && variant != RR_VARIANT_UMMA_F4 && variant != RR_VARIANT_UMMA_MXF4) { rr_set_error("unknown variant %d", variant); return RR_E_ARG; }
 
+    // fp32 accumulation of 0/1 products is exact only below 2^24 reads: deeper MSAs use the int8/int32 coding
+    if ((variant == RR_VARIANT_UMMA_MXF4 || variant == RR_VARIANT_UMMA_F4) && R >= (1 << 24)) variant = RR_VARIANT_UMMA;
     const int umma_mode = variant == RR_VARIANT_UMMA_MXF4 ? 2 : variant == RR_VARIANT_UMMA_F4 ? 1 : 0;
     // ---- host plan: filters, first-break columns, tiles, partition (O(N)); cached between scans ----
     const bool general = !pk->contiguous || (opts->flags & RR_FLAG_GENERAL_BREAK);

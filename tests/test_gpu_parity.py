@@ -281,3 +281,38 @@ def test_pruning_is_sound_at_depth_with_saturation():
             assert s["pair_tests"] == st["pair_tests"] and s["exact_evals"] < 0.1 * s["pair_tests"]
             assert (M == M0).all() and (A == A0).all(), variant
     pk.close()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_deep_msa_uses_the_non_resident_lnfact_path(variant):
+    """coverage depth above the shared-memory table capacity (~9.4k entries): the tail of ln n! is read from
+    HBM (kernel template ALL_SMEM = false)"""
+    rng = np.random.default_rng(81)
+    R, N = 12000, 150
+    codes = np.zeros((R, N), np.uint8)
+    truth = rng.integers(0, 3, R)                      # three read classes
+    for c in range(N):
+        base = rng.integers(0, 4, 3)
+        col = base[truth] if c % 7 == 0 else np.full(R, base[0])
+        noise = rng.random(R) < 0.03
+        codes[:, c] = np.where(noise, rng.integers(0, 5, R), col)
+    oracle = O.Oracle.from_codes(codes)
+    pk = rr.Packed(rr.MSA.from_cells(codes), 0)
+    st = pk.scan(mincov=30, variant=variant)
+    M, A = pk.fetch()
+    check_against_oracle(M, A, st["pair_tests"], oracle, 30)
+    assert (M > 98).any()
+    pk.close()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("mincov", [0, 1, 3, 200])
+def test_unusual_coverage_floors(mincov, variant, tmp_path):
+    text = golden_msa("tree_small")
+    oracle = O.Oracle.from_text(text, tmp_path)
+    pk = rr.Packed(rr.MSA.from_text(text), 0)
+    st = pk.scan(mincov=mincov, variant=variant)
+    M, A = pk.fetch()
+    M0, A0, P0 = check_against_oracle(M, A, st["pair_tests"], oracle, mincov)
+    assert (A == A0).all()
+    pk.close()
