@@ -316,3 +316,24 @@ def test_unusual_coverage_floors(mincov, variant, tmp_path):
     M0, A0, P0 = check_against_oracle(M, A, st["pair_tests"], oracle, mincov)
     assert (A == A0).all()
     pk.close()
+
+
+def test_config1_shape_full_oracle_scan():
+    """BASELINE.json configs[0] shape from the generator (Tree, 10 copies, 40x, 5 kbp: ~670 rows x ~17.6k columns,
+    ~5e8 pair tests): the largest case with a FULL oracle scan (all host threads); every variant, values within
+    1e-9, arg-max identical, byte-identical text after host finalisation."""
+    g = rr.MsaGen(type="Tree", copies=10, coverage=40, repeat_len=5000, diff=0.01, seed=1001)
+    codes = g.codes()
+    oracle = O.Oracle.from_codes(codes)
+    M0, A0, P0 = oracle.scan(30, threads=min(32, os.cpu_count() or 8))
+    assert P0 > 1e8
+    msa = rr.MSA.from_cells(codes)
+    pk = rr.Packed(msa, 0)
+    for variant in VARIANTS:
+        st = pk.scan(mincov=30, variant=variant)
+        M, A = pk.fetch()
+        check_against_oracle(M, A, st["pair_tests"], oracle, 30, M0, A0, P0)
+        assert (A == A0).all()
+    pk.close()
+    Mf, Af, _ = rr.Parallel_AllMaxCorrsRechner(msa, 30, 1, "auto", rr.FLAG_HOST_FINALIZE)
+    assert O.fmt_lines(Mf) == O.fmt_lines(M0) and (Mf == M0).all()
