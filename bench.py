@@ -34,6 +34,8 @@ WORKLOADS = {
     "EquiDistant_1perc_30000": dict(type="EquiDistant", copies=100, coverage=40, repeat_len=30000, diff=0.01, seed=1003),
     "Tree_1perc_5000": dict(type="Tree", copies=10, coverage=40, repeat_len=5000, diff=0.01, seed=1001),
     "Tree_1perc_10000_25": dict(type="Tree", copies=25, coverage=40, repeat_len=10000, diff=0.01, seed=1004),
+    # BASELINE.json configs[4] shape (~40k reads, 100 kbp repeat): 37 120 rows x 440 004 columns, 1.66e11 pair tests
+    "Tree_1perc_100000_92": dict(type="Tree", copies=92, coverage=40, repeat_len=100000, diff=0.01, seed=1005),
 }
 MINCOV = 30
 # dram__bytes_read.sum + dram__bytes_write.sum of the scan kernel, per launch, from the committed ncu capture
