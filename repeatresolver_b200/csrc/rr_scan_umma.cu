@@ -277,6 +277,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const um_unit un = U.units[u];
                 const int khi = U.k_hi[un.rt];
                 for (int ct = un.ct0; ct < un.ct1; ct++) {
+                    if (U.P.flags & 0x8000u) continue;  // timing experiment: epilogue only
                     for (int kb = U.k_lo[ct]; kb < khi; kb++, it++) {
                         const int s = it % UM_STAGES;
                         const uint32_t ph = (it / UM_STAGES) & 1;
@@ -301,7 +302,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int khi = U.k_hi[un.rt];
                 for (int ct = un.ct0; ct < un.ct1; ct++) {
                     const int klo = U.k_lo[ct];
-                    if (klo >= khi) continue;  // no read covers both tiles: the epilogue uses zeros
+                    if (klo >= khi || (U.P.flags & 0x8000u)) continue;  // no read covers both tiles: the epilogue uses zeros
                     const int acc = tile & 1;
                     const uint32_t aph = (tile >> 1) & 1;
                     mbar_wait_sleep(&T->tempty[acc], aph ^ 1, 128);
@@ -363,7 +364,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
             for (int ct = un.ct0; ct < un.ct1; ct++) {
                 const int klo = U.k_lo[ct];
-                const bool has_counts = klo < khi;
+                const bool has_counts = klo < khi && !(P.flags & 0x8000u);
                 const int jsite0 = ct * UM_COL_SITES;
                 // ---- this warp's column groups: sites sub, sub+UM_SUB, ... (slot w <-> site sub + w*UM_SUB)
                 __syncwarp();
