@@ -138,53 +138,12 @@ __device__ __forceinline__ double rr_lnchoose_t(const LT &T, unsigned n, unsigne
     return T(n) - T(m) - T(n - m);
 }
 
-// tier 0 + 1.  lnc3 = lnchoose(cov, gr1), shared by the five column groups of a site.
-template <class LT>
-__device__ __forceinline__ bool rr_tier1(const rr_scan_params &P, const LT &T, unsigned s, unsigned gr1,
-                                         unsigned gr2, unsigned cov, double thr, double lnc3, unsigned &n_bound)
-{
-    if (gr1 == 0 || gr2 == 0 || s < 1) return false;
-    if (P.flags & RR_FLAG_NO_PRUNE) return true;
-    if (thr > RR_BOUND_MEDIAN && rr_below_median(s, gr1, gr2, cov)) return false;
-    if (P.flags & 0x200u) return false;  // timing experiment: nothing survives tier 1
-    if (!(thr > 0.0)) return true;
-    n_bound++;
-    const unsigned hi = gr1 < gr2 ? gr1 : gr2;
-    unsigned x = (unsigned)(__fdividef((float)gr1 * (float)gr2, (float)cov)) + 1u;
-    if (x < s) x = s;
-    if (x > hi) x = hi;
-    if (x + cov < gr1 + gr2) x = gr1 + gr2 - cov;
-    const double lp = rr_lnchoose_t(T, gr2, x) + rr_lnchoose_t(T, cov - gr2, gr1 - x) - lnc3;
-    return !(rr_bound_effective(-RR_LOG10E * lp + 1e-6) < thr);
-}
-
-// tier 0 + 1 without branches (the epilogue evaluates it for every admissible column of a site; straight-line
-// code lets the five columns' look-ups overlap).  meanfac = gr1 / cov (approximate, one per site);
-// returns (need, counted-as-bound-evaluation).
-template <class LT>
-__device__ __forceinline__ bool rr_tier1_flat(const LT &T, unsigned s, unsigned gr1, unsigned gr2, unsigned cov,
-                                              double thr, double lnc3, float meanfac, bool no_prune, bool dbg_skip,
-                                              bool &bound_used)
-{
-    const bool nz = (s >= 1u) & (gr1 != 0u) & (gr2 != 0u);                    // 428-430
-    const bool med = (thr > RR_BOUND_MEDIAN) &
-                     ((unsigned long long)(s + 2u) * cov <= (unsigned long long)gr1 * gr2);
-    const unsigned hi = gr1 < gr2 ? gr1 : gr2;
-    const unsigned sum = gr1 + gr2;
-    const unsigned lo = sum - (sum < cov ? sum : cov);                        // max(0, gr1 + gr2 - cov)
-    unsigned x = (unsigned)(meanfac * (float)gr2) + 1u;
-    x = x > s ? x : s;
-    x = x < hi ? x : hi;
-    x = x > lo ? x : lo;
-    const double lp = ((T(gr2) - T(x)) - T(gr2 - x)) + ((T(cov - gr2) - T(gr1 - x)) - T((cov + x) - sum)) - lnc3;
-    const bool pr = (thr > 0.0) & (rr_bound_effective(-RR_LOG10E * lp + 1e-6) < thr);
-    bound_used = nz & !med;
-    return nz & (no_prune | !(med | pr | dbg_skip));
-}
-
-// The same test in FP32 on a float copy of the ln n! table (half the shared-memory bytes, no FP64 issue slots).
-// Every rounding is covered by `margin` (log10 units): 7 table entries rounded to float plus 6 float additions
-// of values <= ln(maxcov!) give an absolute error below 8 * 2^-23 * ln(maxcov!) in ln units.  thr is the
+// tier 0 + 1, evaluated in FP32 on a float copy of the ln n! table: lnc3 = lnchoose(cov, gr1) is shared by the five
+// column groups of a site; straight-line code (no branches) so the look-ups of a site overlap.
+// (half the shared-memory bytes of a double table, no FP64 issue slots)
+// Every rounding is covered by `margin` (log10 units): 9 table entries rounded to float plus 8 float additions
+// of values <= ln(maxcov!) err by at most 17 * 2^-25 * ln(maxcov!) in ln units; the host passes
+// 16 * 2^-24 * ln(maxcov!) * log10(e) (+2e-6), almost twice that.  thr is the
 // threshold rounded DOWN to float; meanfac = gr1 / cov (approximate).  LTF: callable float(unsigned n).
 template <class LTF>
 __device__ __forceinline__ bool rr_tier1_f32(const LTF &T, unsigned s, unsigned gr1, unsigned gr2, unsigned cov,

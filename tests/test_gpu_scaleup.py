@@ -1,0 +1,42 @@
+"""BASELINE.json configs[4] shape (~40k reads on a 100 kbp repeat: 37 120 rows x 440 004 columns, 16 GB of cells,
+1.66e11 pair tests).  Opt-in (RR_RUN_SCALEUP=1): needs ~40 GB of host memory and ~1 minute.  The reference's
+static limits (30 000 rows, 150 000 columns) exclude this shape, so the check is the oracle's score on the
+device's counts for a sample of winners plus the bitset-count cross-check of rr_pair_counts."""
+import os
+
+import numpy as np
+import pytest
+
+import repeatresolver_b200 as rr
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.skipif(os.environ.get("RR_RUN_SCALEUP") != "1", reason="opt-in: RR_RUN_SCALEUP=1")
+def test_scaleup_shape():
+    g = rr.MsaGen(type="Tree", copies=92, coverage=40, repeat_len=100000, diff=0.01, seed=1005, threads=16)
+    assert g.rows > 30000 and g.cols > 400000
+    msa = rr.MSA.alloc(g.rows, g.cols, codes=True)
+    g.codes(out=msa.cells())
+    pk = rr.Packed(msa, 0)
+    st = pk.scan(mincov=30)
+    M, A = pk.fetch()
+    assert st["pair_tests"] > 1e11
+    gs, cv = pk.sizes()
+    idx = np.random.default_rng(1).choice(np.nonzero(M > 0)[0], 300, replace=False)
+    gi = np.minimum(idx, A[idx]).astype(np.int32)
+    gj = np.maximum(idx, A[idx]).astype(np.int32)
+    cnt = pk.pair_counts(gi, gj)
+    for k in range(len(idx)):
+        z = O.score(int(cnt[k, 0]), int(cnt[k, 1]), int(cnt[k, 2]), int(cnt[k, 3]), int(gs[gi[k]]), int(gs[gj[k]]))
+        assert abs(z - M[idx[k]]) <= 1e-9 * z
+    # 8-way partition merges to the same result
+    Mm = np.zeros_like(M); Am = np.full_like(A, -1)
+    for p in range(8):
+        pk.scan(mincov=30, part_index=p, part_count=8)
+        Mp, Ap = pk.fetch()
+        better = (Mp > Mm) | ((Mp == Mm) & (Mp > 0) & (Ap >= 0) & ((Am < 0) | (Ap < Am)))
+        Mm = np.where(better, Mp, Mm); Am = np.where(better, Ap, Am)
+    assert (Mm == M).all() and (Am == A).all()
+    pk.close()

@@ -25,15 +25,4 @@ for rep in range(2):
 M, A = pk.fetch()
 print("pair tests/s %.3e" % (st["pair_tests"] / (st["kernel_ms"] * 1e-3)), "algorithmic int8-rate TOP/s %.0f" % (2.0 * g.rows * st["pair_tests"] / (st["kernel_ms"] * 1e-3) / 1e12))
 print("M>0", int((M > 0).sum()), "of", len(M), "saturated", int((M > 98).sum()))
-# spot check against the oracle: counts + score of 200 reported winners
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
-import oracle_lib as O
-gs, cv = pk.sizes()
-idx = np.random.default_rng(1).choice(np.nonzero(M > 0)[0], 200, replace=False)
-gi = np.minimum(idx, A[idx]).astype(np.int32); gj = np.maximum(idx, A[idx]).astype(np.int32)
-cnt = pk.pair_counts(gi, gj)
-bad = 0
-for k in range(len(idx)):
-    z = O.score(int(cnt[k, 0]), int(cnt[k, 1]), int(cnt[k, 2]), int(cnt[k, 3]), int(gs[gi[k]]), int(gs[gj[k]]))
-    bad += abs(z - M[idx[k]]) > 1e-9 * z
-print("winner re-evaluation mismatches (oracle score on device counts):", bad)
+# the oracle spot check of this shape lives in tests/test_gpu_scaleup.py (opt-in: RR_RUN_SCALEUP=1)
