@@ -113,7 +113,7 @@ __device__ __forceinline__ double rr_pair_score(const rr_scan_params &P, unsigne
 // ---- tiered pruning with deferred, compacted evaluation -------------------------------------------
 // Per pair test, in order of cost:
 //   tier 0  trivial zero (MaxCorrelation.c:428-430)                          a few integer ops
-//   tier 1  median bound, then single-term pmf bound (rr_score.h)           6-9 table look-ups
+//   tier 1  single-term pmf bound at max(s, ~mean+1) (rr_score.h), FP32       6 table look-ups
 //   tier 2  windowed partial-sum bound in FP32 against FRESH maxima          ~100 FP32 ops
 //   tier 3  the exact score (exp + hypergeometric series + log10)            10^3..10^4 FP64 ops
 // Tiers 2 and 3 are needed by a few percent / per mille of the pairs.  Evaluating them in place
@@ -150,22 +150,18 @@ __device__ __forceinline__ bool rr_tier1_f32(const LTF &T, unsigned s, unsigned 
                                              float thr, float lnc3, float meanfac, float margin, bool no_prune,
                                              bool dbg_skip)
 {
-    const bool nz = (s >= 1u) & (gr1 != 0u) & (gr2 != 0u);                    // 428-430
-    const float m = meanfac * (float)gr2;                                    // ~ mean of the hypergeometric
-    // s + 2 <= mean  =>  score <= log10 2 (median bound); the 0.9999 covers the approximate division
-    const bool med = (thr > (float)RR_BOUND_MEDIAN + 1e-6f) & ((float)(s + 2u) <= m * 0.9999f);
+    // s >= 1 implies gr1 >= 1 and gr2 >= 1 (s <= gr1, gr2): the three tests of 428-430 collapse to one
+    const bool nz = s >= 1u;
     const unsigned hi = gr1 < gr2 ? gr1 : gr2;
-    const unsigned sum = gr1 + gr2;
-    const unsigned lo = sum - (sum < cov ? sum : cov);                        // max(0, gr1 + gr2 - cov)
-    unsigned x = (unsigned)m + 1u;
+    // pmf is evaluated at x = max(s, ~mean + 1) clamped to the support; x >= s >= max(0, gr1 + gr2 - cov) already
+    unsigned x = (unsigned)(meanfac * (float)gr2) + 1u;
     x = x > s ? x : s;
     x = x < hi ? x : hi;
-    x = x > lo ? x : lo;
-    const float lp = ((T(gr2) - T(x)) - T(gr2 - x)) + ((T(cov - gr2) - T(gr1 - x)) - T((cov + x) - sum)) - lnc3;
+    const float lp = ((T(gr2) - T(x)) - T(gr2 - x)) + ((T(cov - gr2) - T(gr1 - x)) - T((cov + x) - (gr1 + gr2))) - lnc3;
     const float U = -(float)RR_LOG10E * lp + margin;
     // a raw score above 98 saturates to 98 + F, which may exceed it: no pruning there (rr_bound_effective)
     const bool pr = (thr > 0.0f) & (U < thr) & (U <= (float)RR_SATURATION_START);
-    return nz & (no_prune | !(med | pr | dbg_skip));
+    return nz & (no_prune | !(pr | dbg_skip));
 }
 
 // tier 2: P[X >= s] >= sum_{x = x0}^{x0+m} pmf(x) for any x0 >= s; the window starts next to the mean

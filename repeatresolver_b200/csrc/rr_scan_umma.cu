@@ -54,6 +54,7 @@ constexpr int UM_SF_COL = 240;                   // 16 spare TMEM columns behind
 struct um_wmeta {                                 // per epilogue warp: metadata of its column groups in the tile
     float mj[UM_WSITES * 5];                      // running maxima, rounded down to float (thresholds only)
     int szj[UM_WSITES * 5];                       // Groupsizearray, or -1 when not admissible (817)
+    int vmask[UM_WSITES];                         // bit b set: group b of the site is admissible
 };
 
 struct um_smem_tail {
@@ -379,6 +380,13 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
                 if (row_ok) thr_i = __double2float_rd(rr_best_value(P.best + gi));
                 __syncwarp();
+                if (lane < UM_WSITES) {
+                    int vm = 0;
+#pragma unroll
+                    for (int b = 0; b < 5; b++) vm |= (M.szj[lane * 5 + b] >= 0) ? (1 << b) : 0;
+                    M.vmask[lane] = vm;
+                }
+                __syncwarp();
 
                 int acc = 0;
                 if (has_counts) {
@@ -415,23 +423,42 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const int cov = colsum[0] + colsum[1] + colsum[2] + colsum[3] + colsum[4];
                     const float lnc3 = (LT((unsigned)cov) - LT((unsigned)rowsum)) - LT((unsigned)(cov - rowsum));
                     const float meanfac = __fdividef((float)rowsum, (float)max(cov, 1));
-                    // tier 0/1 for the admissible column groups of the site (warp-uniform skip of the others),
-                    // then the queue pushes
+                    // tier 0/1 for the admissible column groups of the site, then the queue pushes.  Sites whose
+                    // five groups are all admissible (template columns, first insertion columns: ~2/3 of the pair
+                    // tests) take a straight-line path so that the 30 table look-ups of the site overlap; the
+                    // others skip their inadmissible groups with warp-uniform branches (817).
                     bool need[5];
+                    const int vmask = M.vmask[w];
+                    if (vmask == 31) {
 #pragma unroll
-                    for (int b = 0; b < 5; b++) {
-                        need[b] = false;
-                        if (M.szj[w * 5 + b] >= 0) {  // warp-uniform (817)
+                        for (int b = 0; b < 5; b++) {
+                            const float mjb = M.mj[w * 5 + b];
                             const bool nd = rr_tier1_f32(LT, (unsigned)c[b], (unsigned)rowsum, (unsigned)colsum[b],
-                                                         (unsigned)cov, fminf(thr_i, M.mj[w * 5 + b]), lnc3, meanfac,
-                                                         margin, no_prune, dbg_skip);
+                                                         (unsigned)cov, fminf(thr_i, mjb), lnc3, meanfac, margin,
+                                                         no_prune, dbg_skip);
                             // pre-seed pass only: a column seen for the first time (no maximum yet) would make
                             // every row of the tile a candidate at once; one row in eight is enough to seed it
-                            const bool sampled = !subsample || M.mj[w * 5 + b] > 0.0f || ((lane + t) & 7) == 0;
+                            const bool sampled = !subsample || mjb > 0.0f || ((lane + t) & 7) == 0;
                             need[b] = nd & pair_site & sampled;
-                            n_pairs += pair_site;
+                        }
+                        n_pairs += pair_site ? 5 : 0;
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < 5; b++) {
+                            need[b] = false;
+                            if (vmask & (1 << b)) {  // warp-uniform
+                                const float mjb = M.mj[w * 5 + b];
+                                const bool nd = rr_tier1_f32(LT, (unsigned)c[b], (unsigned)rowsum, (unsigned)colsum[b],
+                                                             (unsigned)cov, fminf(thr_i, mjb), lnc3, meanfac, margin,
+                                                             no_prune, dbg_skip);
+                                const bool sampled = !subsample || mjb > 0.0f || ((lane + t) & 7) == 0;
+                                need[b] = nd & pair_site & sampled;
+                                n_pairs += pair_site;
+                            }
                         }
                     }
+                    // most sites yield no candidate at all: one vote instead of five
+                    if (!__any_sync(0xffffffffu, need[0] | need[1] | need[2] | need[3] | need[4])) continue;
 #pragma unroll
                     for (int b = 0; b < 5; b++) {
                         rr_cand cand;
