@@ -144,11 +144,18 @@ __device__ __forceinline__ double rr_lnchoose_t(const LT &T, unsigned n, unsigne
 // Every rounding is covered by `margin` (log10 units): 9 table entries rounded to float plus 8 float additions
 // of values <= ln(maxcov!) err by at most 17 * 2^-25 * ln(maxcov!) in ln units; the host passes
 // 16 * 2^-24 * ln(maxcov!) * log10(e) (+2e-6), almost twice that.  thr is the
-// threshold rounded DOWN to float; meanfac = gr1 / cov (approximate).  LTF: callable float(unsigned n).
+// threshold rounded DOWN to float and clamped by rr_thr_f32 (0 = "no maximum yet / never prune");
+// meanfac = gr1 / cov (approximate).  LTF: callable float(unsigned n).
+__device__ __forceinline__ float rr_thr_f32(double best, bool no_prune)
+{
+    // a raw score above 98 saturates to 98 + F, which may exceed it (rr_bound_effective): a bound only prunes when it
+    // is below min(threshold, 98), so the clamp is folded into the threshold once per refresh
+    return no_prune ? 0.0f : fminf(__double2float_rd(best), (float)RR_SATURATION_START);
+}
+
 template <class LTF>
 __device__ __forceinline__ bool rr_tier1_f32(const LTF &T, unsigned s, unsigned gr1, unsigned gr2, unsigned cov,
-                                             float thr, float lnc3, float meanfac, float margin, bool no_prune,
-                                             bool dbg_skip)
+                                             float thr, float lnc3, float meanfac, float margin)
 {
     // s >= 1 implies gr1 >= 1 and gr2 >= 1 (s <= gr1, gr2): the three tests of 428-430 collapse to one
     const bool nz = s >= 1u;
@@ -158,10 +165,9 @@ __device__ __forceinline__ bool rr_tier1_f32(const LTF &T, unsigned s, unsigned 
     x = x > s ? x : s;
     x = x < hi ? x : hi;
     const float lp = ((T(gr2) - T(x)) - T(gr2 - x)) + ((T(cov - gr2) - T(gr1 - x)) - T((cov + x) - (gr1 + gr2))) - lnc3;
+    // U >= 0 (lp <= 0 up to the rounding the margin covers), so thr == 0 never prunes
     const float U = -(float)RR_LOG10E * lp + margin;
-    // a raw score above 98 saturates to 98 + F, which may exceed it: no pruning there (rr_bound_effective)
-    const bool pr = (thr > 0.0f) & (U < thr) & (U <= (float)RR_SATURATION_START);
-    return nz & (no_prune | !(pr | dbg_skip));
+    return nz & !(U < thr);
 }
 
 // tier 2: P[X >= s] >= sum_{x = x0}^{x0+m} pmf(x) for any x0 >= s; the window starts next to the mean

@@ -374,11 +374,11 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const int j = 5 * (jsite0 + sub + w * UM_SUB) + b;
                     int sz = -1;
                     float m = 0.0f;
-                    if (j < 5 * P.N && P.colok[j]) { sz = P.gsize[j]; m = __double2float_rd(rr_best_value(P.best + j)); }
+                    if (j < 5 * P.N && P.colok[j]) { sz = P.gsize[j]; m = rr_thr_f32(rr_best_value(P.best + j), no_prune); }
                     M.szj[e] = sz;
                     M.mj[e] = m;
                 }
-                if (row_ok) thr_i = __double2float_rd(rr_best_value(P.best + gi));
+                if (row_ok) thr_i = rr_thr_f32(rr_best_value(P.best + gi), no_prune);
                 __syncwarp();
                 if (lane < UM_WSITES) {
                     int vm = 0;
@@ -431,36 +431,30 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const int vmask = M.vmask[w];
                     if (vmask == 31) {
 #pragma unroll
-                        for (int b = 0; b < 5; b++) {
-                            const float mjb = M.mj[w * 5 + b];
-                            const bool nd = rr_tier1_f32(LT, (unsigned)c[b], (unsigned)rowsum, (unsigned)colsum[b],
-                                                         (unsigned)cov, fminf(thr_i, mjb), lnc3, meanfac, margin,
-                                                         no_prune, dbg_skip);
-                            // pre-seed pass only: a column seen for the first time (no maximum yet) would make
-                            // every row of the tile a candidate at once; one row in eight is enough to seed it
-                            const bool sampled = !subsample || mjb > 0.0f || ((lane + t) & 7) == 0;
-                            need[b] = nd & pair_site & sampled;
-                        }
+                        for (int b = 0; b < 5; b++)
+                            need[b] = pair_site & rr_tier1_f32(LT, (unsigned)c[b], (unsigned)rowsum, (unsigned)colsum[b],
+                                                               (unsigned)cov, fminf(thr_i, M.mj[w * 5 + b]), lnc3,
+                                                               meanfac, margin);
                         n_pairs += pair_site ? 5 : 0;
                     } else {
 #pragma unroll
                         for (int b = 0; b < 5; b++) {
                             need[b] = false;
                             if (vmask & (1 << b)) {  // warp-uniform
-                                const float mjb = M.mj[w * 5 + b];
-                                const bool nd = rr_tier1_f32(LT, (unsigned)c[b], (unsigned)rowsum, (unsigned)colsum[b],
-                                                             (unsigned)cov, fminf(thr_i, mjb), lnc3, meanfac, margin,
-                                                             no_prune, dbg_skip);
-                                const bool sampled = !subsample || mjb > 0.0f || ((lane + t) & 7) == 0;
-                                need[b] = nd & pair_site & sampled;
+                                need[b] = pair_site & rr_tier1_f32(LT, (unsigned)c[b], (unsigned)rowsum,
+                                                                   (unsigned)colsum[b], (unsigned)cov,
+                                                                   fminf(thr_i, M.mj[w * 5 + b]), lnc3, meanfac, margin);
                                 n_pairs += pair_site;
                             }
                         }
                     }
-                    // most sites yield no candidate at all: one vote instead of five
-                    if (!__any_sync(0xffffffffu, need[0] | need[1] | need[2] | need[3] | need[4])) continue;
+                    // most sites yield no candidate at all: one vote instead of five.  0x200 (debug): tier 1 prunes all
+                    if (dbg_skip || !__any_sync(0xffffffffu, need[0] | need[1] | need[2] | need[3] | need[4])) continue;
 #pragma unroll
                     for (int b = 0; b < 5; b++) {
+                        // pre-seed pass only: a column seen for the first time (no maximum yet) would make every row
+                        // of the tile a candidate at once; one row in eight is enough to seed it
+                        if (subsample) need[b] &= M.mj[w * 5 + b] > 0.0f || ((lane + t) & 7) == 0;
                         rr_cand cand;
                         cand.s = (uint32_t)c[b]; cand.gr1 = (uint32_t)rowsum; cand.gr2 = (uint32_t)colsum[b];
                         cand.cov = (uint32_t)cov; cand.gi = gi; cand.gj = 5 * jj + b;
@@ -468,10 +462,10 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         if (c1n >= 32) {
                             rr_drain_tier2(P, LG, q1, c1n, q2, c2n, lane, n_tier2, n_exact, false);
                             // pick up what this and the other warps / CTAs have found meanwhile
-                            if (row_ok) thr_i = __double2float_rd(rr_best_value(P.best + gi));
+                            if (row_ok) thr_i = rr_thr_f32(rr_best_value(P.best + gi), no_prune);
                             for (int e = lane; e < UM_WSITES * 5; e += 32)
                                 if (M.szj[e] >= 0)
-                                    M.mj[e] = __double2float_rd(rr_best_value(P.best + 5 * (jsite0 + sub + (e / 5) * UM_SUB) + (e % 5)));
+                                    M.mj[e] = rr_thr_f32(rr_best_value(P.best + 5 * (jsite0 + sub + (e / 5) * UM_SUB) + (e % 5)), no_prune);
                             __syncwarp();
                         }
                     }
