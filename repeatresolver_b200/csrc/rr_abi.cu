@@ -23,16 +23,8 @@ static double rr_now_ms()
 {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
-#define RR_TRACE(tag)                                                                   \
-    do {                                                                                \
-        if (rr_trace_on()) fprintf(stderr, "[rr trace] %-22s %9.3f ms\n", tag, rr_now_ms() - trace_t0); \
-    } while (0)
-static bool rr_trace_on()
-{
-    static int on = -1;
-    if (on < 0) on = getenv("RR_TRACE") ? 1 : 0;
-    return on == 1;
-}
+#define RR_TRACE(tag) rr_trace_mark(tag)
+static bool rr_trace_on() { return getenv("RR_TRACE") != nullptr; }
 
 #define RR_CUDA(call)                                                                              \
     do {                                                                                           \
@@ -77,6 +69,30 @@ extern "C" void rr_host_free(void *p, int pinned)
     if (!p) return;
     if (pinned) cudaFreeHost(p);
     else free(p);
+}
+
+// first CUDA call of a process = context creation (a few hundred ms): rr_msa_read starts it on a background thread
+// while the text is being indexed
+static std::mutex g_warm_mu;
+static std::thread g_warm_thread;
+extern "C" void rr_cuda_warmup_end(void)
+{
+    std::lock_guard<std::mutex> lk(g_warm_mu);
+    if (g_warm_thread.joinable()) g_warm_thread.join();
+}
+extern "C" void rr_cuda_warmup_begin(void)
+{
+    static bool once = false;
+    std::lock_guard<std::mutex> lk(g_warm_mu);
+    if (once) return;
+    once = true;
+    g_warm_thread = std::thread([] {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return; }
+        if (cudaSetDevice(0) == cudaSuccess) cudaFree(nullptr);
+        cudaGetLastError();
+    });
+    atexit(rr_cuda_warmup_end);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -207,7 +223,6 @@ static int dev_alloc(T **p, size_t count)
 extern "C" void rr_packed_free(rr_packed *pk)
 {
     if (!pk) return;
-    const double trace_t0 = rr_now_ms();
     cudaSetDevice(pk->device);
     rr_alloc_stream(pk->st);
     rr_umma_free(pk->umma);
@@ -222,9 +237,84 @@ extern "C" void rr_packed_free(rr_packed *pk)
     RR_TRACE("free: done");
 }
 
-static int pack_impl(const uint8_t *cells, int R, int N, int codes, int device, rr_packed *pk)
+extern "C" void rr_msa_gather_rows(const rr_msa *m, int r0, int r1, uint8_t *dst, int threads);
+
+// Rows of a text-backed or pageable host MSA -> d_cells through a small page-locked ring: a few host threads gather
+// whole rows into ring slots (this is the only host copy the rows ever see) while earlier slots are in flight on the
+// copy engine.  Page-locking the whole 1-2 GB matrix instead costs ~1 s per GB.
+static int staged_upload(const rr_msa *msa, uint8_t *d_cells, int device, cudaStream_t st)
 {
-    const double trace_t0 = rr_now_ms();
+    const int R = msa->rows;
+    const size_t N = (size_t)msa->cols;
+    constexpr int NSLOT = 6, NTHREAD = 6;
+    constexpr size_t SLOT_BYTES = (size_t)8 << 20;
+    const int rows_per_slot = (int)std::max<size_t>(1, SLOT_BYTES / N);
+    const size_t slot_bytes = (size_t)rows_per_slot * N;
+    const int n_chunks = (R + rows_per_slot - 1) / rows_per_slot;
+    uint8_t *ring = nullptr;
+    RR_CUDA(cudaHostAlloc((void **)&ring, slot_bytes * NSLOT, cudaHostAllocDefault));
+    cudaStream_t cst;
+    cudaEvent_t ev[NSLOT];
+    cudaError_t err0 = cudaStreamCreateWithFlags(&cst, cudaStreamNonBlocking);
+    for (int k = 0; k < NSLOT; k++) if (err0 == cudaSuccess) err0 = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+    if (err0 != cudaSuccess) { cudaFreeHost(ring); rr_set_error("CUDA error %s (staged upload set-up)", cudaGetErrorString(err0)); return RR_E_CUDA; }
+    std::mutex mu;
+    std::condition_variable cv;
+    int recorded[NSLOT] = {0};          // how many uses of the slot have had their copy issued + event recorded
+    std::atomic<int> next{0};
+    std::atomic<int> failed{0};
+    auto work = [&]() {
+        cudaSetDevice(device);
+        for (;;) {
+            const int c = next.fetch_add(1);
+            if (c >= n_chunks || failed.load()) return;
+            const int slot = c % NSLOT, use = c / NSLOT;
+            {   // the previous use of this slot must have been issued, then completed
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return recorded[slot] == use || failed.load(); });
+            }
+            if (failed.load()) return;
+            if (use > 0 && cudaEventSynchronize(ev[slot]) != cudaSuccess) { failed = 1; cv.notify_all(); return; }
+            const int r0 = c * rows_per_slot, r1 = std::min(R, r0 + rows_per_slot);
+            uint8_t *buf = ring + (size_t)slot * slot_bytes;
+            rr_msa_gather_rows(msa, r0, r1, buf, 1);
+            cudaError_t e = cudaMemcpyAsync(d_cells + (size_t)r0 * N, buf, (size_t)(r1 - r0) * N, cudaMemcpyHostToDevice, cst);
+            {
+                std::lock_guard<std::mutex> lk(mu);   // record under the lock: events of one stream stay in issue order
+                if (e == cudaSuccess) e = cudaEventRecord(ev[slot], cst);
+                if (e != cudaSuccess) failed = 1;
+                recorded[slot] = use + 1;
+            }
+            cv.notify_all();
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < std::min(NTHREAD, n_chunks); t++) th.emplace_back(work);
+        work();
+        for (auto &t : th) t.join();
+    }
+    cudaError_t e = failed.load() ? cudaErrorUnknown : cudaSuccess;
+    cudaEvent_t done;
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
+    if (e == cudaSuccess) {
+        e = cudaEventRecord(done, cst);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, done, 0);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cst);   // the ring is freed below
+        cudaEventDestroy(done);
+    }
+    for (int k = 0; k < NSLOT; k++) cudaEventDestroy(ev[k]);
+    cudaStreamDestroy(cst);
+    cudaFreeHost(ring);
+    if (e != cudaSuccess) { cudaGetLastError(); rr_set_error("CUDA error during the staged upload of the MSA (%s)", cudaGetErrorString(e)); return RR_E_CUDA; }
+    return RR_OK;
+}
+
+static int pack_impl(const rr_msa *msa, int device, rr_packed *pk)
+{
+    const uint8_t *cells = msa->cells;
+    const int R = msa->rows, N = msa->cols, codes = msa->codes;
+    rr_cuda_warmup_end();
     int ndev = rr_device_count();
     if (ndev <= 0) { rr_set_error("no CUDA device: the scan has no CPU fallback"); return RR_E_NODEV; }
     if (device < 0 || device >= ndev) { rr_set_error("device %d out of range (%d devices)", device, ndev); return RR_E_ARG; }
@@ -248,7 +338,10 @@ static int pack_impl(const uint8_t *cells, int R, int N, int codes, int device, 
     int rc;
     if ((rc = dev_alloc(&pk->d_cells, ncell))) return rc;
     RR_CUDA(cudaEventRecord(e0, pk->st));
-    if (ncell) RR_CUDA(cudaMemcpyAsync(pk->d_cells, cells, ncell, cudaMemcpyHostToDevice, pk->st));
+    if (ncell) {
+        if (cells && msa->pinned) RR_CUDA(cudaMemcpyAsync(pk->d_cells, cells, ncell, cudaMemcpyHostToDevice, pk->st));
+        else if ((rc = staged_upload(msa, pk->d_cells, device, pk->st))) return rc;
+    }
     RR_CUDA(cudaEventRecord(e1, pk->st));
 
     RR_TRACE("pack: h2d issued");
@@ -313,7 +406,7 @@ extern "C" int rr_pack(const rr_msa *msa, int device, rr_packed **out)
 {
     if (!msa || !out) { rr_set_error("rr_pack: bad arguments"); return RR_E_ARG; }
     rr_packed *pk = new rr_packed();
-    int rc = pack_impl(msa->cells, msa->rows, msa->cols, msa->codes, device, pk);
+    int rc = pack_impl(msa, device, pk);
     if (rc) { rr_packed_free(pk); *out = nullptr; return rc; }
     *out = pk;
     return RR_OK;
@@ -387,7 +480,6 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
         rr_set_error("rr_scan: part %d of %d", opts->part_index, opts->part_count);
         return RR_E_ARG;
     }
-    const double trace_t0 = rr_now_ms();
     RR_CUDA(cudaSetDevice(pk->device));
     rr_alloc_stream(pk->st);
     const int R = pk->R, N = pk->N, mincov = opts->mincov;
@@ -568,7 +660,9 @@ extern "C" int rr_maxcorr_run(const rr_msa *msa, int mincov, int n_gpus, int var
                               double *maxcorr_out, int32_t *argmax_out, rr_scan_stats *stats)
 {
     if (!msa || (!maxcorr_out && msa->cols > 0) || n_gpus < 1) { rr_set_error("rr_maxcorr_run: bad arguments"); return RR_E_ARG; }
+    RR_TRACE("run: start");
     const int ndev = rr_device_count();
+    RR_TRACE("run: device count");
     if (ndev <= 0) { rr_set_error("no CUDA device: the scan has no CPU fallback"); return RR_E_NODEV; }
     if (n_gpus > ndev) { rr_set_error("%d GPUs requested, %d present", n_gpus, ndev); return RR_E_ARG; }
     const size_t G = (size_t)5 * msa->cols;
@@ -634,6 +728,7 @@ extern "C" int rr_maxcorr_run(const rr_msa *msa, int mincov, int n_gpus, int var
         for (int d = 0; d < n_gpus; d++) th.emplace_back(worker, d);
         for (auto &t : th) t.join();
     }
+    RR_TRACE("run: scans fetched");
     int rc = RR_OK;
     for (int d = 0; d < n_gpus; d++)
         if (RC[d]) { rc = RC[d]; rr_set_error("GPU %d: %s", d, ERR[d].c_str()); break; }
@@ -663,6 +758,7 @@ extern "C" int rr_maxcorr_run(const rr_msa *msa, int mincov, int n_gpus, int var
                 stats->fetch_ms = std::max(stats->fetch_ms, S[d].fetch_ms);
             }
         }
+        RR_TRACE("run: merged");
         if (flags & RR_FLAG_HOST_FINALIZE) {
             // the winners' counts come from the device bitsets; only exp/log10 of the 5N winning
             // pairs are redone with the host libm
@@ -691,6 +787,8 @@ extern "C" int rr_maxcorr_run(const rr_msa *msa, int mincov, int n_gpus, int var
             cudaEventDestroy(a); cudaEventDestroy(b);
         }
     }
+    RR_TRACE("run: finalized");
     for (int d = 0; d < n_gpus; d++) rr_packed_free(PK[d]);
+    RR_TRACE("run: freed");
     return rc;
 }

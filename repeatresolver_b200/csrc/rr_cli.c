@@ -18,6 +18,8 @@
 #include <time.h>
 #include "../../include/rr_maxcorr.h"
 
+void rr_trace_mark(const char *tag); /* librr_maxcorr.so internal: RR_TRACE=1 prints host phase times */
+
 int main(int argc, char *argv[])
 {
     const char *path;
@@ -53,7 +55,9 @@ int main(int argc, char *argv[])
         if (!strcmp(argv[i], "--no-finalize")) flags &= ~RR_FLAG_HOST_FINALIZE;
         if (!strcmp(argv[i], "--no-prune")) flags |= RR_FLAG_NO_PRUNE;
     }
+    rr_trace_mark("cli: start");
     rc = rr_msa_read(path, &msa);
+    rr_trace_mark("cli: MSA read");
     if (rc == RR_E_IO) { printf("MA is missing.\n"); exit(1); }
     if (rc) { fprintf(stderr, "\nError in MaxCorrelation\n   %s\n", rr_last_error()); exit(1); }
     printf("There are %d sequences.\n", rr_msa_rows(msa));
@@ -70,13 +74,15 @@ int main(int argc, char *argv[])
     if (rc) { fprintf(stderr, "\nError in MaxCorrelation\n   %s\n", rr_last_error()); exit(1); }
     snprintf(name, sizeof name, "MaxCorrsOf_%s", path);
     printf("%s\n", name);
+    rr_trace_mark("cli: scan done");
     rc = rr_maxcorr_write(name, M, G);
     if (rc) { printf("DateiVerbratei!\n"); exit(1); }
     snprintf(name, sizeof name, "MaxCorrsArgOf_%s", path);
     rr_argmax_write(name, A, G);
+    rr_trace_mark("cli: files written");
     printf("pair tests %lld, exact evaluations %lld, kernel %.3f ms (%s), pack %.3f ms, h2d %.3f ms\n",
            (long long)st.pair_tests, (long long)st.exact_evals, st.kernel_ms,
-           st.variant == RR_VARIANT_UMMA ? "tcgen05 int8" : "bitset", st.pack_ms, st.h2d_ms);
+           st.variant == RR_VARIANT_UMMA ? "tcgen05 int8" : st.variant == RR_VARIANT_UMMA_F4 ? "tcgen05 e2m1" : st.variant == RR_VARIANT_UMMA_MXF4 ? "tcgen05 mxf4" : "bitset", st.pack_ms, st.h2d_ms);
     printf("Runtime: %lu sec.\n", (unsigned long)(time(NULL) - t0));
     rr_msa_free(msa);
     free(M); free(A);

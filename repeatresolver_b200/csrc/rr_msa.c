@@ -21,6 +21,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <pthread.h>
+#include <time.h>
 #include "rr_host.h"
 
 static __thread char rr_errbuf[512];
@@ -31,6 +32,20 @@ void rr_set_error(const char *fmt, ...)
     va_start(ap, fmt);
     vsnprintf(rr_errbuf, sizeof rr_errbuf, fmt, ap);
     va_end(ap);
+}
+void rr_trace_mark(const char *tag)
+{
+    static int on = -1;
+    static double t0 = 0.0, last = 0.0;
+    struct timespec ts;
+    double now;
+    if (on < 0) on = getenv("RR_TRACE") ? 1 : 0;
+    if (!on) return;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    if (t0 == 0.0) t0 = last = now;
+    fprintf(stderr, "[rr trace] %-28s +%9.3f ms  (t = %9.3f ms)\n", tag, now - last, now - t0);
+    last = now;
 }
 const char *rr_last_error(void) { return rr_errbuf; }
 const char *rr_version(void) { return "repeatresolver_b200 0.1 (sm_100a)"; }
@@ -52,13 +67,59 @@ int rr_msa_alloc(int rows, int cols, int codes, rr_msa **out)
 void rr_msa_free(rr_msa *m)
 {
     if (!m) return;
-    rr_host_free(m->cells, m->pinned);
+    if (m->cells) rr_host_free(m->cells, m->pinned);
+    if (m->map) munmap((void *)m->map, m->map_len);
+    free(m->rowoff);
     free(m);
 }
 
 int rr_msa_rows(const rr_msa *m) { return m ? m->rows : 0; }
 int rr_msa_cols(const rr_msa *m) { return m ? m->cols : 0; }
-uint8_t *rr_msa_cells(rr_msa *m) { return m ? m->cells : NULL; }
+
+/* copy rows [r0, r1) into a [.][cols] matrix with a few threads (memory-bound) */
+typedef struct { const rr_msa *m; uint8_t *dst; int r0, r1; } copy_job;
+static void *copy_rows_thread(void *x)
+{
+    copy_job *j = (copy_job *)x;
+    int r;
+    for (r = j->r0; r < j->r1; r++) memcpy(j->dst + (size_t)(r - j->r0) * j->m->cols, rr_msa_row(j->m, r), (size_t)j->m->cols);
+    return NULL;
+}
+void rr_msa_gather_rows(const rr_msa *m, int r0, int r1, uint8_t *dst, int threads)
+{
+    pthread_t th[16];
+    copy_job jobs[16];
+    int t, nt = threads;
+    if (r1 <= r0 || m->cols <= 0) return;
+    if (nt > 16) nt = 16;
+    if ((size_t)(r1 - r0) * (size_t)m->cols < (1u << 22) || nt < 1) nt = 1;
+    for (t = 0; t < nt; t++) {
+        jobs[t].m = m;
+        jobs[t].r0 = r0 + (int)((long long)(r1 - r0) * t / nt);
+        jobs[t].r1 = r0 + (int)((long long)(r1 - r0) * (t + 1) / nt);
+        jobs[t].dst = dst + (size_t)(jobs[t].r0 - r0) * m->cols;
+        th[t] = 0;
+        if (nt == 1 || pthread_create(&th[t], NULL, copy_rows_thread, &jobs[t]) != 0) { copy_rows_thread(&jobs[t]); th[t] = 0; }
+    }
+    for (t = 0; t < nt; t++)
+        if (th[t]) pthread_join(th[t], NULL);
+}
+
+uint8_t *rr_msa_cells(rr_msa *m)
+{
+    if (!m) return NULL;
+    if (!m->cells && m->map) { /* text-backed: materialise once (pageable memory: rr_pack stages it through its ring) */
+        size_t bytes = (size_t)m->rows * (size_t)m->cols;
+        uint8_t *c = (uint8_t *)malloc(bytes ? bytes : 1);
+        if (!c) { rr_set_error("out of host memory (%zu bytes)", bytes); return NULL; }
+        rr_msa_gather_rows(m, 0, m->rows, c, 8);
+        m->cells = c; m->pinned = 0;
+        munmap((void *)m->map, m->map_len);
+        m->map = NULL; m->map_len = 0;
+        free(m->rowoff); m->rowoff = NULL;
+    }
+    return m->cells;
+}
 
 int rr_msa_from_cells(const uint8_t *cells, int rows, int cols, int codes, rr_msa **out)
 {
@@ -76,75 +137,124 @@ static inline size_t line_strlen(const char *p, size_t raw)
     return z ? (size_t)(z - p) : raw;
 }
 
-/* copy the kept rows into the cell matrix with a few threads (the copy of a 1-2 GB MSA is memory-bound and
- * dominates the host side once the scan itself takes a fraction of a second) */
-typedef struct { const char **rowp; uint8_t *cells; size_t cols; int r0, r1; } copy_job;
-static void *copy_rows_thread(void *x)
+/* Line index of a text MSA with the reference's row rules (291, 299): the first line fixes cols = strlen - 1, every
+ * line of that length is a row.  Two parallel passes over byte ranges / line ranges (a 1-2 GB MSA is memchr-bound):
+ * newline positions, then the keep test (the NUL scan of strlen semantics only where the raw length could match). */
+typedef struct {
+    const char *text; size_t lo, hi;      /* pass 1: byte range */
+    int64_t *starts; size_t n, cap; int oom;
+    const int64_t *line; size_t l0, l1, nbytes; long cols; uint8_t *keep;  /* pass 2: line range */
+} scan_job;
+static void *scan_newlines_thread(void *x)
 {
-    copy_job *j = (copy_job *)x;
-    int r;
-    for (r = j->r0; r < j->r1; r++) memcpy(j->cells + (size_t)r * j->cols, j->rowp[r], j->cols);
+    scan_job *j = (scan_job *)x;
+    size_t pos = j->lo;
+    while (pos < j->hi) {
+        const char *nl = (const char *)memchr(j->text + pos, '\n', j->hi - pos);
+        if (!nl) break;
+        pos = (size_t)(nl - j->text) + 1;
+        if (j->n == j->cap) {
+            size_t nc = j->cap ? j->cap * 2 : 4096;
+            int64_t *np = (int64_t *)realloc(j->starts, nc * sizeof(int64_t));
+            if (!np) { j->oom = 1; return NULL; }
+            j->starts = np; j->cap = nc;
+        }
+        j->starts[j->n++] = (int64_t)pos;  /* a line starts after every '\n' */
+    }
     return NULL;
 }
+static void *scan_keep_thread(void *x)
+{
+    scan_job *j = (scan_job *)x;
+    size_t l;
+    for (l = j->l0; l < j->l1; l++) {
+        size_t raw = (size_t)(j->line[l + 1] - j->line[l]);
+        j->keep[l] = (long)raw - 1 >= j->cols && (long)line_strlen(j->text + j->line[l], raw) - 1 == j->cols;
+    }
+    return NULL;
+}
+static int index_lines(const char *text, size_t nbytes, int *rows_out, long *cols_out, int64_t **rowoff_out)
+{
+    enum { MAXT = 16 };
+    pthread_t th[MAXT];
+    scan_job jobs[MAXT];
+    int t, nt = nbytes > (1u << 24) ? 8 : 1, rows = 0;
+    size_t nlines = 1, l, k;
+    int64_t *line, *rowoff;
+    uint8_t *keep;
+    long cols;
+    memset(jobs, 0, sizeof jobs);
+    for (t = 0; t < nt; t++) {
+        jobs[t].text = text; jobs[t].lo = nbytes / nt * t; jobs[t].hi = t == nt - 1 ? nbytes : nbytes / nt * (t + 1);
+        th[t] = 0;
+        if (nt == 1 || pthread_create(&th[t], NULL, scan_newlines_thread, &jobs[t]) != 0) { scan_newlines_thread(&jobs[t]); th[t] = 0; }
+    }
+    for (t = 0; t < nt; t++) {
+        if (th[t]) pthread_join(th[t], NULL);
+        nlines += jobs[t].n;
+    }
+    line = (int64_t *)malloc(sizeof(int64_t) * (nlines + 1));
+    for (t = 0, k = 1; t < nt; t++) {
+        if (line && !jobs[t].oom) { memcpy(line + k, jobs[t].starts, sizeof(int64_t) * jobs[t].n); k += jobs[t].n; }
+        else if (line) { free(line); line = NULL; }
+        free(jobs[t].starts);
+    }
+    if (!line) { rr_set_error("out of host memory"); return RR_E_NOMEM; }
+    line[0] = 0;
+    if ((size_t)line[nlines - 1] == nbytes) nlines--;  /* the text ends with '\n': no line after it */
+    line[nlines] = (int64_t)nbytes;
+    cols = nlines ? (long)line_strlen(text, (size_t)(line[1] - line[0])) - 1 : -1;   /* 291 */
+    keep = (uint8_t *)malloc(nlines ? nlines : 1);
+    if (!keep) { free(line); rr_set_error("out of host memory"); return RR_E_NOMEM; }
+    for (t = 0; t < nt; t++) {
+        jobs[t].line = line; jobs[t].l0 = nlines * t / nt; jobs[t].l1 = nlines * (t + 1) / nt;
+        jobs[t].cols = cols; jobs[t].keep = keep; jobs[t].nbytes = nbytes;
+        th[t] = 0;
+        if (nt == 1 || pthread_create(&th[t], NULL, scan_keep_thread, &jobs[t]) != 0) { scan_keep_thread(&jobs[t]); th[t] = 0; }
+    }
+    for (t = 0; t < nt; t++)
+        if (th[t]) pthread_join(th[t], NULL);
+    for (l = 0; l < nlines; l++) rows += keep[l];
+    rowoff = (int64_t *)malloc(sizeof(int64_t) * (size_t)(rows ? rows : 1));
+    if (!rowoff) { free(line); free(keep); rr_set_error("out of host memory"); return RR_E_NOMEM; }
+    for (l = 0, k = 0; l < nlines; l++)
+        if (keep[l]) rowoff[k++] = line[l];                /* 299 */
+    free(line); free(keep);
+    *rows_out = rows; *cols_out = cols < 0 ? 0 : cols; *rowoff_out = rowoff;
+    return RR_OK;
+}
 
+/* text in caller-owned memory: the rows are copied out (the text may go away) */
 int rr_msa_from_text(const char *text, size_t nbytes, rr_msa **out)
 {
-    size_t pos = 0;
-    long cols = -1;
-    int rows = 0, cap = 0, rc, t, nt;
-    const char **rowp = NULL;
-    rr_msa *m = NULL;
-    pthread_t th[16];
-    copy_job jobs[16];
+    long cols = 0;
+    int rows = 0, rc;
+    int64_t *rowoff = NULL;
+    rr_msa *m = NULL, view;
     if (!out || (!text && nbytes)) { rr_set_error("rr_msa_from_text: bad arguments"); return RR_E_ARG; }
-    /* pass 1 (sequential, memchr-bound): line boundaries and the keep rule */
-    while (pos < nbytes) {
-        const char *p = text + pos;
-        const char *nl = (const char *)memchr(p, '\n', nbytes - pos);
-        size_t raw = nl ? (size_t)(nl - p) + 1 : nbytes - pos;
-        size_t sl;
-        pos += raw;
-        /* strlen semantics need the NUL scan only when the line length could match */
-        if (cols >= 0 && (long)raw - 1 < cols) continue;
-        sl = line_strlen(p, raw);
-        if (cols < 0) cols = (long)sl - 1;                 /* 291 */
-        if ((long)sl - 1 != cols) continue;                /* 299 */
-        if (rows == cap) {
-            const char **np;
-            cap = cap ? cap * 2 : 1024;
-            np = (const char **)realloc((void *)rowp, sizeof(char *) * (size_t)cap);
-            if (!np) { free((void *)rowp); rr_set_error("out of host memory"); return RR_E_NOMEM; }
-            rowp = np;
-        }
-        rowp[rows++] = p;
-    }
-    if (cols < 0) cols = 0;
-    if (cols > 0x7fffffffL / 8) { free((void *)rowp); rr_set_error("MSA too wide (%ld columns)", cols); return RR_E_ARG; }
+    if ((rc = index_lines(text, nbytes, &rows, &cols, &rowoff))) return rc;
+    if (cols > 0x7fffffffL / 8) { free(rowoff); rr_set_error("MSA too wide (%ld columns)", cols); return RR_E_ARG; }
     rc = rr_msa_alloc(rows, (int)cols, 0, &m);
-    if (rc) { free((void *)rowp); return rc; }
-    /* pass 2: parallel copy */
-    nt = (size_t)rows * (size_t)cols > (1u << 24) ? 8 : 1;
-    if (cols > 0)
-        for (t = 0; t < nt; t++) {
-            jobs[t].rowp = rowp; jobs[t].cells = m->cells; jobs[t].cols = (size_t)cols;
-            jobs[t].r0 = (int)((long long)rows * t / nt); jobs[t].r1 = (int)((long long)rows * (t + 1) / nt);
-            if (nt == 1) copy_rows_thread(&jobs[t]);
-            else if (pthread_create(&th[t], NULL, copy_rows_thread, &jobs[t]) != 0) { copy_rows_thread(&jobs[t]); th[t] = 0; }
-        }
-    if (cols > 0 && nt > 1)
-        for (t = 0; t < nt; t++)
-            if (th[t]) pthread_join(th[t], NULL);
-    free((void *)rowp);
+    if (rc) { free(rowoff); return rc; }
+    memset(&view, 0, sizeof view);
+    view.rows = rows; view.cols = (int)cols; view.map = text; view.rowoff = rowoff;
+    rr_msa_gather_rows(&view, 0, rows, m->cells, 8);
+    free(rowoff);
     *out = m;
     return RR_OK;
 }
 
+/* Einlesen's file handling (270-335): the file stays mapped, the rows are indexed, nothing is copied */
 int rr_msa_read(const char *path, rr_msa **out)
 {
-    int fd, rc;
+    int fd, rc, rows = 0;
+    long cols = 0;
     struct stat st;
     void *map;
+    int64_t *rowoff = NULL;
+    rr_msa *m;
     if (!path || !out) { rr_set_error("rr_msa_read: bad arguments"); return RR_E_ARG; }
+    rr_trace_mark("read: start");
     fd = open(path, O_RDONLY);
     if (fd < 0) { rr_set_error("MA is missing. (%s: %s)", path, strerror(errno)); return RR_E_IO; }
     if (fstat(fd, &st) != 0) { close(fd); rr_set_error("fstat %s: %s", path, strerror(errno)); return RR_E_IO; }
@@ -152,10 +262,19 @@ int rr_msa_read(const char *path, rr_msa **out)
     map = mmap(NULL, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
     close(fd);
     if (map == MAP_FAILED) { rr_set_error("mmap %s: %s", path, strerror(errno)); return RR_E_IO; }
-    madvise(map, (size_t)st.st_size, MADV_SEQUENTIAL);
-    rc = rr_msa_from_text((const char *)map, (size_t)st.st_size, out);
-    munmap(map, (size_t)st.st_size);
-    return rc;
+    if ((size_t)st.st_size > (1u << 26)) rr_cuda_warmup_begin();  /* the context comes up while the text is indexed */
+    rc = index_lines((const char *)map, (size_t)st.st_size, &rows, &cols, &rowoff);
+    rr_trace_mark("read: lines indexed");
+    if (!rc && cols > 0x7fffffffL / 8) { rc = RR_E_ARG; rr_set_error("MSA too wide (%ld columns)", cols); }
+    m = rc ? NULL : (rr_msa *)calloc(1, sizeof(*m));
+    if (!m) {
+        if (!rc) { rc = RR_E_NOMEM; rr_set_error("out of host memory"); }
+        free(rowoff); munmap(map, (size_t)st.st_size);
+        return rc;
+    }
+    m->rows = rows; m->cols = (int)cols; m->map = (const char *)map; m->map_len = (size_t)st.st_size; m->rowoff = rowoff;
+    *out = m;
+    return RR_OK;
 }
 
 /* MaxCorrsRausschreiben (516-532): one "%f\n" per group */

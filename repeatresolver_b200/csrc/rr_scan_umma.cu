@@ -642,6 +642,7 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
             }
             S->xa_rows_cap[md] = xa_rows;
         }
+        rr_trace_mark("umma: operands allocated");
         rr_k_build_xa<<<(unsigned)xa_rows, 256, 0, st>>>(S->xb[md], P.rowsites, (int64_t)xa_rows, row_bytes, S->xa[md]);
         rr_count_launch(1);
         UM_CUDA(cudaGetLastError());
@@ -721,10 +722,13 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
                                         cudaMemcpyHostToDevice, st));
             UM_CUDA(cudaMemcpyAsync(S->d_khi, plan.k_hi.data(), sizeof(int32_t) * plan.k_hi.size(), cudaMemcpyHostToDevice, st));
             UM_CUDA(cudaMemcpyAsync(S->d_klo, plan.k_lo.data(), sizeof(int32_t) * plan.k_lo.size(), cudaMemcpyHostToDevice, st));
+            rr_trace_mark("umma: units built");
             UM_CUDA(cudaStreamSynchronize(st));  // units[] is a local
+            rr_trace_mark("umma: uploads synced");
             if ((rc = make_map(&S->map_a, S->xa[md], xa_rows, (uint64_t)S->Kp, UM_M, mode))) return rc;
             if ((rc = make_map(&S->map_b, S->xb[md], (uint64_t)5 * P.N, (uint64_t)S->Kp, UM_N, mode))) return rc;
         }
+        rr_trace_mark("umma: tensor maps");
         S->built_plan_id = plan_id;
         S->built_md = mode;
     }
@@ -739,6 +743,7 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
         UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
         UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
         S->attr_set = true;
+        rr_trace_mark("umma: func attributes");
     }
     um_params U;
     U.P = P;

@@ -212,6 +212,30 @@ def test_cli_drop_in(tmp_path):
     assert len(arg) == len(golden_maxcorrs("tree_small", 10).split())
 
 
+def test_file_backed_msa_streams_through_the_upload_ring(tmp_path):
+    """rr_msa_read keeps the file mapped; rr_pack gathers its rows through the page-locked ring (several chunks, the
+    ring wraps around) - the packed result must equal the one from page-locked cells, ragged lines skipped"""
+    g = rr.MsaGen(type="Tree", copies=12, coverage=40, repeat_len=24000, diff=0.01, seed=77, flank=2000)
+    text = bytearray(g.text())
+    assert len(text) > 7 * (8 << 20)  # more chunks than ring slots
+    width = g.cols + 1
+    extra = b"ACGT-\n"               # a short line in the middle: skipped by the row rule (299)
+    cut = (g.rows // 2) * width
+    text = bytes(text[:cut]) + extra + bytes(text[cut:])
+    p = tmp_path / "MSAreal"
+    p.write_bytes(text)
+    m_file, m_mem = rr.MSA.read(str(p)), rr.MSA.from_text(text)
+    assert (m_file.rows, m_file.cols) == (m_mem.rows, m_mem.cols) == (g.rows, g.cols)
+    pk_file, pk_mem = rr.Packed(m_file, 0), rr.Packed(m_mem, 0)
+    for a, b in zip(pk_file.sizes(), pk_mem.sizes()):
+        assert (a == b).all()
+    st_f, st_m = pk_file.scan(mincov=30), pk_mem.scan(mincov=30)
+    assert st_f["pair_tests"] == st_m["pair_tests"] > 0
+    (Mf, Af), (Mm, Am) = pk_file.fetch(), pk_mem.fetch()
+    assert (Mf == Mm).all() and (Af == Am).all()
+    assert (m_file.cells() == m_mem.cells()).all()  # materialised on demand afterwards
+
+
 def test_threshold_exchange_device_pointers():
     """the device-to-device form of the multi-GPU threshold exchange (torch tensor <-> library)"""
     import torch

@@ -77,6 +77,53 @@ def test_parser_edge_cases(tmp_path):
     assert e.value.code == -1 and "MA is missing." in str(e.value)
 
 
+def _kept_rows(data: bytes):
+    """the row rules of Einlesen (291, 299) restated on bytes: lines split at \n, strlen semantics at NUL"""
+    lines = data.split(b"\n")
+    lines = [l + b"\n" for l in lines[:-1]] + ([lines[-1]] if lines[-1] else [])
+    if not lines:
+        return 0, []
+    sl = lambda l: len(l.split(b"\0")[0]) if b"\0" in l else len(l)
+    cols = sl(lines[0]) - 1
+    return max(cols, 0), [l[:cols] for l in lines if sl(l) - 1 == cols]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_parser_parallel_index_matches_restated_rules(seed, tmp_path):
+    """> 16 MB of text takes the multi-threaded line index; the file-backed MSA (no host copy until cells() is asked
+    for) and the in-memory parse must keep exactly the rows the reference would"""
+    rng = np.random.default_rng(seed)
+    cols = 3000 + seed
+    out = []
+    for r in range(6500):
+        k = rng.integers(0, 40)
+        line = bytes(rng.choice(np.frombuffer(b"ACGT- ", dtype=np.uint8), cols).tobytes())
+        if k == 0:
+            line = line[: cols - 1 - int(rng.integers(0, 5))]                # too short
+        elif k == 1:
+            line = line + b"A" * int(rng.integers(1, 9))                      # too long
+        elif k == 2:
+            line = line[:100] + b"\0" + line[101:]                            # strlen stops early: dropped
+        elif k == 3:
+            line = line + b"\0garbage"                                       # strlen == cols (the newline comes after the NUL): dropped
+        elif k == 4:
+            line = b""
+        out.append(line + b"\n")
+    data = b"".join(out)
+    if seed == 2:
+        data = data[:-1]                                                     # no trailing newline on the last line
+    assert len(data) > (1 << 24)
+    cols_want, rows_want = _kept_rows(data)
+    p = tmp_path / "MSAreal"
+    p.write_bytes(data)
+    for m in (rr.MSA.read(str(p)), rr.MSA.from_text(data)):
+        assert m.cols == cols_want and m.rows == len(rows_want)
+        c = m.cells()
+        assert c.shape == (len(rows_want), cols_want)
+        assert c.tobytes() == b"".join(rows_want)
+        m.close()
+
+
 def test_lnfact_table_bitwise_equal_to_oracle():
     t = rr.lnfact_table(20000)
     for n in list(range(0, 400)) + [1000, 4096, 13700, 19999]:
