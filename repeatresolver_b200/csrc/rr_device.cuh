@@ -99,6 +99,8 @@ __device__ __forceinline__ double rr_pair_score(const rr_scan_params &P, unsigne
 {
     if (gr1 == 0 || gr2 == 0 || s < 1) return 0.0;  // MaxCorrelation.c:428-430
     if (!(P.flags & RR_FLAG_NO_PRUNE)) {
+        // s at the lower end of the support: P[X >= s] = 1, and GSL returns exactly 1 (score 0): nothing to record
+        if (s + cov == gr1 + gr2) return -1.0;
         double m = fmin(mi, mj);
         if (m > RR_BOUND_MEDIAN && rr_below_median(s, gr1, gr2, cov)) return -1.0;
         if (m > 0.0) {

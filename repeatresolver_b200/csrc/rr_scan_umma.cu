@@ -199,6 +199,9 @@ __device__ __forceinline__ uint32_t make_idesc()
 // sum of x over the 5 lanes of a site (lanes 5t..5t+4), returned in every lane of the site
 __device__ __forceinline__ int site_sum5(int x, int base_lane)
 {
+#if defined(RR_EXP) && (RR_EXP & 2)   // timing experiment only (wrong results): no shuffles
+    return x * 5 + base_lane;
+#endif
     int s1 = x + __shfl_down_sync(0xffffffffu, x, 1);
     int s2 = s1 + __shfl_down_sync(0xffffffffu, s1, 2);
     int s = s2 + __shfl_down_sync(0xffffffffu, x, 4);
@@ -216,6 +219,12 @@ struct um_lnf {
     const double *gmem;
     __device__ __forceinline__ float lds(unsigned n) const
     {
+#if defined(RR_EXP) && (RR_EXP & 1)   // timing experiment only (wrong results): no table look-ups
+        return __uint_as_float(base + 4u * n);
+#endif
+#if defined(RR_EXP) && (RR_EXP & 2)
+        n &= 511u;
+#endif
         float v;
         asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + 4u * n));
         return v;
@@ -455,6 +464,12 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         // pre-seed pass only: a column seen for the first time (no maximum yet) would make every row
                         // of the tile a candidate at once; one row in eight is enough to seed it
                         if (subsample) need[b] &= M.mj[w * 5 + b] > 0.0f || ((lane + t) & 7) == 0;
+                        // s at the lower end of the support (s = gr1 + gr2 - cov >= 1): P[X >= s] = 1 and GSL returns
+                        // exactly that (its lower-tail sum starts from pdf(s-1) = 0), so the score is 0 and the pair can
+                        // change nothing.  Without this test such pairs are candidates for every group whose maximum is
+                        // still 0 or tiny - the gap groups of insertion columns, 60 % of the columns of config 2 and
+                        // 88 % of its exact evaluations.  (Kept under RR_FLAG_NO_PRUNE: the exhaustive scan.)
+                        need[b] &= no_prune || c[b] + cov != rowsum + colsum[b];
                         rr_cand cand;
                         cand.s = (uint32_t)c[b]; cand.gr1 = (uint32_t)rowsum; cand.gr2 = (uint32_t)colsum[b];
                         cand.cov = (uint32_t)cov; cand.gi = gi; cand.gj = 5 * jj + b;

@@ -173,6 +173,26 @@ def test_pruning_bounds_are_upper_bounds():
     assert checked > 5000 and med > 500
 
 
+def test_score_at_the_lower_end_of_the_support_is_exactly_zero():
+    """the kernels drop pairs with s = gr1 + gr2 - cov >= 1 without evaluating them: P[X >= s] = 1 there, and the GSL
+    chain returns exactly 1 (the lower-tail sum starts from pdf(s - 1) = 0), i.e. a score of (minus) zero that can
+    never replace a maximum - checked on the oracle's shim and on the library's host build of the score"""
+    rng = np.random.default_rng(11)
+    n = 0
+    for _ in range(4000):
+        cov = int(rng.integers(1, 6000))
+        gr1 = int(rng.integers(1, cov + 1))
+        gr2 = int(rng.integers(max(1, cov - gr1 + 1), cov + 1))   # gr1 + gr2 > cov
+        s = gr1 + gr2 - cov
+        assert 1 <= s <= min(gr1, gr2)
+        for z in (O.score(s, gr1, gr2, cov, gr1 + 3, gr2 + 5), rr.score_host(s, gr1, gr2, cov, gr1 + 3, gr2 + 5)):
+            assert z == 0.0, (s, gr1, gr2, cov, z)
+        n += 1
+    for cov, gr1 in ((2493, 7), (1961, 1688), (70, 1)):            # gr2 = cov: pairs seen at config 2
+        assert O.score(gr1, gr1, cov, cov, 10, 4000) == 0.0 == rr.score_host(gr1, gr1, cov, cov, 10, 4000)
+    assert n == 4000
+
+
 def test_bound_covers_the_saturation_window():
     """raw scores in (98, 99) are replaced by 98 + F, which may be LARGER than the raw score: the effective
     bound must not drop below 99 there"""
