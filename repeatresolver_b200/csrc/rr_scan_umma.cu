@@ -43,7 +43,7 @@ constexpr int UM_A_BYTES = UM_M * UM_KB;         // 16384
 constexpr int UM_B_BYTES = UM_N * UM_KB;         // 30720
 constexpr int UM_STAGE_BYTES = UM_A_BYTES + UM_B_BYTES;  // 47104 = 46 * 1024
 constexpr int UM_FIRST_EPI_WARP = 4;
-constexpr int UM_EPI_WARPS = 12;
+constexpr int UM_EPI_WARPS = 16;
 constexpr int UM_THREADS = (UM_FIRST_EPI_WARP + UM_EPI_WARPS) * 32;  // 512
 constexpr int UM_SUB = UM_EPI_WARPS / 4;         // epilogue warps per TMEM lane quarter
 constexpr int UM_WSITES = UM_COL_SITES / UM_SUB; // column sites per warp and tile (16)
@@ -277,6 +277,9 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tc_fence_after();
     }
 
+    // register reallocation: the control warpgroup (warps 0-3) gives registers to the 16 epilogue warps
+    if (warp < UM_FIRST_EPI_WARP) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
@@ -339,7 +342,9 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
             }
         }
-    } else if (warp >= UM_FIRST_EPI_WARP) {
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
         // ================= epilogue =================
         const int ew = warp - UM_FIRST_EPI_WARP;  // 0..UM_EPI_WARPS-1
         const int quarter = warp & 3;            // TMEM lane quarter this warp may access
