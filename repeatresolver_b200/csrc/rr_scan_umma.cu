@@ -51,10 +51,13 @@ constexpr int UM_TMEM_COLS = 512;
 constexpr int UM_ACC_STRIDE = 256;               // TMEM columns between the two accumulators
 constexpr int UM_SF_COL = 240;                   // 16 spare TMEM columns behind accumulator 0: unit block scales (mxf4)
 
-struct um_wmeta {                                 // per epilogue warp: metadata of its column groups in the tile
-    float mj[UM_WSITES * 5];                      // running maxima, rounded down to float (thresholds only)
-    int szj[UM_WSITES * 5];                       // Groupsizearray, or -1 when not admissible (817)
-    int vmask[UM_WSITES];                         // bit b set: group b of the site is admissible
+struct __align__(16) um_wsite {                   // one column site: read by the whole warp as two 16-byte broadcasts
+    float mj[5];                                  // running maxima, rounded down to float (thresholds only)
+    int vmask;                                    // bit b set: group b of the site is admissible (817)
+    int pad[2];
+};
+struct um_wmeta {                                 // per epilogue warp: metadata of its column sites in the tile
+    um_wsite site[UM_WSITES];
 };
 
 struct um_smem_tail {
@@ -386,19 +389,17 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int e = lane; e < UM_WSITES * 5; e += 32) {
                     const int w = e / 5, b = e - w * 5;
                     const int j = 5 * (jsite0 + sub + w * UM_SUB) + b;
-                    int sz = -1;
-                    float m = 0.0f;
-                    if (j < 5 * P.N && P.colok[j]) { sz = P.gsize[j]; m = rr_thr_f32(rr_best_value(P.best + j), no_prune); }
-                    M.szj[e] = sz;
-                    M.mj[e] = m;
+                    float m = -1.0f;   // -1: not admissible (817)
+                    if (j < 5 * P.N && P.colok[j]) m = rr_thr_f32(rr_best_value(P.best + j), no_prune);
+                    M.site[w].mj[b] = m;
                 }
                 if (row_ok) thr_i = rr_thr_f32(rr_best_value(P.best + gi), no_prune);
                 __syncwarp();
                 if (lane < UM_WSITES) {
                     int vm = 0;
 #pragma unroll
-                    for (int b = 0; b < 5; b++) vm |= (M.szj[lane * 5 + b] >= 0) ? (1 << b) : 0;
-                    M.vmask[lane] = vm;
+                    for (int b = 0; b < 5; b++) vm |= (M.site[lane].mj[b] >= 0.0f) ? (1 << b) : 0;
+                    M.site[lane].vmask = vm;
                 }
                 __syncwarp();
 
@@ -442,12 +443,19 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     // tests) take a straight-line path so that the 30 table look-ups of the site overlap; the
                     // others skip their inadmissible groups with warp-uniform branches (817).
                     bool need[5];
-                    const int vmask = M.vmask[w];
+                    float mjw[5];
+                    int vmask;
+                    {
+                        const float4 m0 = *reinterpret_cast<const float4 *>(&M.site[w].mj[0]);
+                        const float4 m1 = *reinterpret_cast<const float4 *>(&M.site[w].mj[4]);
+                        mjw[0] = m0.x; mjw[1] = m0.y; mjw[2] = m0.z; mjw[3] = m0.w; mjw[4] = m1.x;
+                        vmask = __float_as_int(m1.y);
+                    }
                     if (vmask == 31) {
 #pragma unroll
                         for (int b = 0; b < 5; b++)
                             need[b] = pair_site & rr_tier1_f32(LT, (unsigned)c[b], (unsigned)rowsum, (unsigned)colsum[b],
-                                                               (unsigned)cov, fminf(thr_i, M.mj[w * 5 + b]), lnc3,
+                                                               (unsigned)cov, fminf(thr_i, mjw[b]), lnc3,
                                                                meanfac, margin);
                         n_pairs += pair_site ? 5 : 0;
                     } else {
@@ -457,7 +465,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             if (vmask & (1 << b)) {  // warp-uniform
                                 need[b] = pair_site & rr_tier1_f32(LT, (unsigned)c[b], (unsigned)rowsum,
                                                                    (unsigned)colsum[b], (unsigned)cov,
-                                                                   fminf(thr_i, M.mj[w * 5 + b]), lnc3, meanfac, margin);
+                                                                   fminf(thr_i, mjw[b]), lnc3, meanfac, margin);
                                 n_pairs += pair_site;
                             }
                         }
@@ -468,7 +476,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (int b = 0; b < 5; b++) {
                         // pre-seed pass only: a column seen for the first time (no maximum yet) would make every row
                         // of the tile a candidate at once; one row in eight is enough to seed it
-                        if (subsample) need[b] &= M.mj[w * 5 + b] > 0.0f || ((lane + t) & 7) == 0;
+                        if (subsample) need[b] &= mjw[b] > 0.0f || ((lane + t) & 7) == 0;
                         // s at the lower end of the support (s = gr1 + gr2 - cov >= 1): P[X >= s] = 1 and GSL returns
                         // exactly that (its lower-tail sum starts from pdf(s-1) = 0), so the score is 0 and the pair can
                         // change nothing.  Without this test such pairs are candidates for every group whose maximum is
@@ -484,8 +492,8 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             // pick up what this and the other warps / CTAs have found meanwhile
                             if (row_ok) thr_i = rr_thr_f32(rr_best_value(P.best + gi), no_prune);
                             for (int e = lane; e < UM_WSITES * 5; e += 32)
-                                if (M.szj[e] >= 0)
-                                    M.mj[e] = rr_thr_f32(rr_best_value(P.best + 5 * (jsite0 + sub + (e / 5) * UM_SUB) + (e % 5)), no_prune);
+                                if (M.site[e / 5].mj[e % 5] >= 0.0f)
+                                    M.site[e / 5].mj[e % 5] = rr_thr_f32(rr_best_value(P.best + 5 * (jsite0 + sub + (e / 5) * UM_SUB) + (e % 5)), no_prune);
                             __syncwarp();
                         }
                     }
