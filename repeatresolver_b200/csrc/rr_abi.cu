@@ -588,11 +588,13 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
         cudaEventElapsedTime(&stats->prepare_ms, e0, e1);
         cudaEventElapsedTime(&stats->kernel_ms, e1, e2);
     }
+#ifndef RR_EXP   // (timing-experiment builds change the counts on purpose)
     if ((int64_t)counters[0] != plan.part_pairs && !(opts->flags & (0x700u | RR_FLAG_SEED_ONLY))) {
         rr_set_error("pair-test count mismatch: device %llu, host plan %lld", counters[0], (long long)plan.part_pairs);
         cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
         return RR_E_CUDA;
     }
+#endif
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     return RR_OK;
 }

@@ -211,6 +211,14 @@ __device__ __forceinline__ int site_sum5(int x, int base_lane)
     return __shfl_sync(0xffffffffu, s, base_lane);
 }
 
+// the same for two counts at once, packed 16 + 16 bits (every sum is <= the shared coverage <= R < 65536)
+__device__ __forceinline__ void site_sum5_x2(int x0, int x1, int base_lane, int &s0, int &s1)
+{
+    const int s = site_sum5(x0 | (x1 << 16), base_lane);
+    s0 = s & 0xffff;
+    s1 = (int)((unsigned)s >> 16);
+}
+
 extern __shared__ __align__(1024) uint8_t um_smem[];
 
 // ln(n!) for the bounds.  ALL_SMEM: every argument (<= largest column coverage) is inside the table staged in
@@ -247,7 +255,9 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     um_smem_tail *T = reinterpret_cast<um_smem_tail *>(smem + UM_TAIL_OFF);
     float *lnf_s = reinterpret_cast<float *>(smem + UM_LNF_OFF);
     const rr_scan_params &P = U.P;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the warp index through a shuffle: the compiler then keeps it (and what derives from it) in uniform registers
+    // instead of re-reading SR_TID inside the epilogue loop
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();  // the swizzled operand tiles need a 1024-byte aligned base
@@ -361,10 +371,11 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         rr_cand *q1 = T->q1[ew], *q2 = T->q2[ew];
         um_wmeta &M = T->meta[ew];
         int c1n = 0, c2n = 0;
-        const bool no_prune = (P.flags & RR_FLAG_NO_PRUNE) != 0, dbg_skip = (P.flags & 0x200u) != 0;
+        const bool no_prune = (P.flags & RR_FLAG_NO_PRUNE) != 0;
+        const bool pack16 = P.R < 65536;
         const bool subsample = (P.flags & 0x2000u) != 0;  // set by the host for the pre-seed launch only
         um_lnf<ALL_SMEM> LT;     // float table, tier 1
-        LT.base = smem_u32(lnf_s); LT.n_smem = U.lnf_smem; LT.gmem = P.lnfact;
+        LT.base = (uint32_t)__shfl_sync(0xffffffffu, (int)smem_u32(lnf_s), 0); LT.n_smem = U.lnf_smem; LT.gmem = P.lnfact;
         rr_lnf_global LG;        // double table in HBM/L2, tier 2 (rare, evaluated 32 at a time)
         LG.gmem = P.lnfact;
         const float margin = U.t1_margin;
@@ -385,15 +396,24 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const bool has_counts = klo < khi && !(P.flags & 0x8000u);
                 const int jsite0 = ct * UM_COL_SITES;
                 // ---- this warp's column groups: sites sub, sub+UM_SUB, ... (slot w <-> site sub + w*UM_SUB)
+                // all loads of the tile's thresholds are issued back to back (the maximum is read whether or not the
+                // group is admissible) so that one L2 round trip covers them
                 __syncwarp();
-                for (int e = lane; e < UM_WSITES * 5; e += 32) {
-                    const int w = e / 5, b = e - w * 5;
-                    const int j = 5 * (jsite0 + sub + w * UM_SUB) + b;
-                    float m = -1.0f;   // -1: not admissible (817)
-                    if (j < 5 * P.N && P.colok[j]) m = rr_thr_f32(rr_best_value(P.best + j), no_prune);
-                    M.site[w].mj[b] = m;
+                {
+                    static_assert(UM_WSITES * 5 <= 64, "two metadata entries per lane");
+                    const int w0 = lane / 5, b0 = lane - w0 * 5;
+                    const int e1 = lane + 32, w1 = e1 / 5, b1 = e1 - w1 * 5;
+                    const bool has1 = e1 < UM_WSITES * 5;
+                    const int j0 = 5 * (jsite0 + sub + w0 * UM_SUB) + b0, j1 = 5 * (jsite0 + sub + w1 * UM_SUB) + b1;
+                    const bool in0 = j0 < 5 * P.N, in1 = has1 && j1 < 5 * P.N;
+                    const double z0 = in0 ? rr_best_value(P.best + j0) : 0.0;
+                    const double z1 = in1 ? rr_best_value(P.best + j1) : 0.0;
+                    const double zi = row_ok ? rr_best_value(P.best + gi) : 0.0;
+                    const bool ok0 = in0 && P.colok[j0] != 0, ok1 = in1 && P.colok[j1] != 0;
+                    M.site[w0].mj[b0] = ok0 ? rr_thr_f32(z0, no_prune) : -1.0f;   // -1: not admissible (817)
+                    if (has1) M.site[w1].mj[b1] = ok1 ? rr_thr_f32(z1, no_prune) : -1.0f;
+                    if (row_ok) thr_i = rr_thr_f32(zi, no_prune);
                 }
-                if (row_ok) thr_i = rr_thr_f32(rr_best_value(P.best + gi), no_prune);
                 __syncwarp();
                 if (lane < UM_WSITES) {
                     int vm = 0;
@@ -428,16 +448,37 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                         for (int b = 0; b < 5; b++) c[b] = 0;
                     }
+#if defined(RR_EXP) && (RR_EXP & 16)  // timing experiment: the site costs pure ALU time (no TMEM data use, no shared memory)
+                    {
+                        float z = __int_as_float(0x3f800000 + lane + t);
+#pragma unroll 1
+                        for (int q = 0; q < 250; q++) z = fmaf(z, 1.0000001f, 1e-9f);
+                        if (z == 0.123f) n_pairs++;
+                        n_pairs += (row_ok && jsite0 + t >= ii + 20 && jsite0 + t < brk) ? 5 : 0;
+                        continue;
+                    }
+#endif
+#if defined(RR_EXP) && (RR_EXP & 8)   // timing experiment: half of the epilogue work
+                    if (w & 1) continue;
+#endif
                     const int jj = jsite0 + t;
                     const bool pair_site = row_ok && jj >= ii + 20 && jj < brk;
                     if (!__any_sync(0xffffffffu, pair_site)) continue;
                     const int rowsum = c[0] + c[1] + c[2] + c[3] + c[4];  // gr1 = |Gi & Cjj|
                     int colsum[5];                                          // gr2 = |Gj & Cii| per column group
+                    if (pack16) {   // R < 65536 (warp-uniform): three shuffle rounds instead of five
+                        site_sum5_x2(c[0], c[1], base_lane, colsum[0], colsum[1]);
+                        site_sum5_x2(c[2], c[3], base_lane, colsum[2], colsum[3]);
+                        colsum[4] = site_sum5(c[4], base_lane);
+                    } else {
 #pragma unroll
-                    for (int b = 0; b < 5; b++) colsum[b] = site_sum5(c[b], base_lane);
+                        for (int b = 0; b < 5; b++) colsum[b] = site_sum5(c[b], base_lane);
+                    }
                     const int cov = colsum[0] + colsum[1] + colsum[2] + colsum[3] + colsum[4];
                     const float lnc3 = (LT((unsigned)cov) - LT((unsigned)rowsum)) - LT((unsigned)(cov - rowsum));
-                    const float meanfac = __fdividef((float)rowsum, (float)max(cov, 1));
+                    float meanfac;   // ~ gr1 / cov (only steers where the pmf bound is evaluated; cov = 0 has no pair test)
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(meanfac) : "f"((float)max(cov, 1)));
+                    meanfac *= (float)rowsum;
                     // tier 0/1 for the admissible column groups of the site, then the queue pushes.  Sites whose
                     // five groups are all admissible (template columns, first insertion columns: ~2/3 of the pair
                     // tests) take a straight-line path so that the 30 table look-ups of the site overlap; the
@@ -470,8 +511,8 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             }
                         }
                     }
-                    // most sites yield no candidate at all: one vote instead of five.  0x200 (debug): tier 1 prunes all
-                    if (dbg_skip || !__any_sync(0xffffffffu, need[0] | need[1] | need[2] | need[3] | need[4])) continue;
+                    // most sites yield no candidate at all: one vote instead of five
+                    if (!__any_sync(0xffffffffu, need[0] | need[1] | need[2] | need[3] | need[4])) continue;
 #pragma unroll
                     for (int b = 0; b < 5; b++) {
                         // pre-seed pass only: a column seen for the first time (no maximum yet) would make every row
