@@ -448,16 +448,6 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                         for (int b = 0; b < 5; b++) c[b] = 0;
                     }
-#if defined(RR_EXP) && (RR_EXP & 16)  // timing experiment: the site costs pure ALU time (no TMEM data use, no shared memory)
-                    {
-                        float z = __int_as_float(0x3f800000 + lane + t);
-#pragma unroll 1
-                        for (int q = 0; q < 250; q++) z = fmaf(z, 1.0000001f, 1e-9f);
-                        if (z == 0.123f) n_pairs++;
-                        n_pairs += (row_ok && jsite0 + t >= ii + 20 && jsite0 + t < brk) ? 5 : 0;
-                        continue;
-                    }
-#endif
 #if defined(RR_EXP) && (RR_EXP & 8)   // timing experiment: half of the epilogue work
                     if (w & 1) continue;
 #endif
