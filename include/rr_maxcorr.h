@@ -92,6 +92,10 @@ typedef struct rr_scan_stats {
 } rr_scan_stats;
 
 /* ---- host: reading the MSA (Einlesen, reading part) -------------------------------- */
+/* rr_msa_read applies the row rules of 291/299 to the file and keeps it memory-mapped: nothing is copied on the
+ * host, rr_pack gathers the kept rows straight into its upload ring.  The file must stay unchanged until
+ * rr_msa_free (or the first rr_msa_cells call, which materialises the matrix and drops the mapping).
+ * rr_msa_from_text does the same for text in caller-owned memory and copies the kept rows out. */
 int rr_msa_read(const char *path, rr_msa **out);
 int rr_msa_from_text(const char *text, size_t nbytes, rr_msa **out);
 /* cells[rows][cols]; codes != 0: values 0..5 as in Signatures (304-329); else raw characters */
@@ -101,6 +105,7 @@ int rr_msa_from_cells(const uint8_t *cells, int rows, int cols, int codes, rr_ms
 int rr_msa_alloc(int rows, int cols, int codes, rr_msa **out);
 int rr_msa_rows(const rr_msa *msa);
 int rr_msa_cols(const rr_msa *msa);
+/* [rows][cols] cell matrix owned by the handle (NULL on allocation failure, see rr_last_error) */
 uint8_t *rr_msa_cells(rr_msa *msa);
 void rr_msa_free(rr_msa *msa);
 

@@ -1,7 +1,8 @@
-// rr_scan_umma.cu -- count-kernel variant A: the read-set intersections as a 0/1 int8 GEMM on
-// the 5th-generation tensor cores (tcgen05.mma kind::i8, int32 accumulators in TMEM), operands
-// staged by TMA into a 128B-swizzled shared-memory ring, with the significance epilogue fused
-// behind the accumulator so that the count matrix never reaches HBM.
+// rr_scan_umma.cu -- count-kernel variant A: the read-set intersections as a 0/1 GEMM on the 5th-generation tensor
+// cores (tcgen05.mma; operands as int8 with int32 accumulators, or as packed 4-bit e2m1 with fp32 accumulators, the
+// latter also block-scaled kind::mxf4 at twice the rate), accumulators in TMEM, operands staged by TMA into a
+// 128B-swizzled shared-memory ring, with the significance epilogue fused behind the accumulator so that the count
+// matrix never reaches HBM.
 //
 // Replaces the pair loop of HilfsMaxCorrsRechner (/root/reference/MaxCorrelation.c:796-830):
 // counts = X^T X restricted to the band jj in [ii+20, break(ii)), X in {0,1}^(reads x groups).
@@ -10,15 +11,16 @@
 //              32-row slab (5 groups each + 2 zero rows) so that a site never straddles a warp
 //              of the epilogue; 24 sites per 128-row tile.
 //   B operand  xb[5N][Kp]             every group, 48 sites = 240 columns per tile.
-//   K          reads in span-start order; only the 128-read blocks [k_lo(col tile), k_hi(row tile))
-//              can hold a read covering both tiles, the rest is skipped exactly.
+//   K          reads in span-start order; only the K blocks [k_lo(col tile), k_hi(row tile)) (128 reads, 256 for
+//              mxf4) can hold a read covering both tiles, the rest is skipped exactly.
 //
-// Warp roles (one persistent CTA per SM, 512 threads):
+// Warp roles (one persistent CTA per SM, 640 threads):
 //   warp 0      TMA producer (one elected lane): A and B boxes of a K block -> smem stage
-//   warp 1      TMEM allocator + MMA issuer (one elected lane): 4 x tcgen05.mma (K=32) per stage,
+//   warp 1      TMEM allocator + MMA issuer (one elected lane): 4 x tcgen05.mma per stage,
 //               tcgen05.commit frees the stage / publishes the accumulator
-//   warps 2-3   idle (keep the epilogue warps aligned to the TMEM lane quarters)
-//   warps 4-15  epilogue, three warps per 32-lane TMEM quarter, each taking every third column site:
+//   warps 2-3   idle (keep the epilogue warps aligned to the TMEM lane quarters); warps 0-3 give their registers
+//               to the epilogue (setmaxnreg 32 / 112)
+//   warps 4-19  epilogue, four warps per 32-lane TMEM quarter, each taking every fourth column site:
 //               tcgen05.ld of the site's 5 counts, 5x5 block sums (in-thread row sum, 5-lane shuffle
 //               column sums), filters, tiered pruning bounds; survivors are queued per warp and
 //               evaluated 32 at a time (exact FP64 score), maxima folded in with a 128-bit CAS.
