@@ -253,6 +253,7 @@ static int staged_upload(const rr_msa *msa, uint8_t *d_cells, int device, cudaSt
     const int n_chunks = (R + rows_per_slot - 1) / rows_per_slot;
     uint8_t *ring = nullptr;
     RR_CUDA(cudaHostAlloc((void **)&ring, slot_bytes * NSLOT, cudaHostAllocDefault));
+    RR_TRACE("pack: ring page-locked");
     cudaStream_t cst;
     cudaEvent_t ev[NSLOT];
     cudaError_t err0 = cudaStreamCreateWithFlags(&cst, cudaStreamNonBlocking);
@@ -315,6 +316,7 @@ static int pack_impl(const rr_msa *msa, int device, rr_packed *pk)
     const uint8_t *cells = msa->cells;
     const int R = msa->rows, N = msa->cols, codes = msa->codes;
     rr_cuda_warmup_end();
+    RR_TRACE("pack: context ready");
     int ndev = rr_device_count();
     if (ndev <= 0) { rr_set_error("no CUDA device: the scan has no CPU fallback"); return RR_E_NODEV; }
     if (device < 0 || device >= ndev) { rr_set_error("device %d out of range (%d devices)", device, ndev); return RR_E_ARG; }
@@ -337,6 +339,7 @@ static int pack_impl(const rr_msa *msa, int device, rr_packed *pk)
     const size_t ncell = (size_t)R * N;
     int rc;
     if ((rc = dev_alloc(&pk->d_cells, ncell))) return rc;
+    RR_TRACE("pack: cells allocated");
     RR_CUDA(cudaEventRecord(e0, pk->st));
     if (ncell) {
         if (cells && msa->pinned) RR_CUDA(cudaMemcpyAsync(pk->d_cells, cells, ncell, cudaMemcpyHostToDevice, pk->st));
