@@ -5,7 +5,7 @@
 
 void rr_plan_build(rr_plan &plan, int R, int N, int mincov, const int32_t *gsize, const int32_t *coverage,
                    const int32_t *breakcol, const int32_t *start, const int32_t *end, int ti, int tj, int kunit,
-                   int tile_cost, int part_index, int part_count)
+                   int tile_cost, int overlap_pct, int part_index, int part_count)
 {
     const int q = mincov / 4;  // integer division, MaxCorrelation.c:802/817
     const size_t G = (size_t)5 * N;
@@ -85,13 +85,18 @@ void rr_plan_build(rr_plan &plan, int R, int N, int mincov, const int32_t *gsize
     }
 
     // cost-balanced contiguous partition of the row blocks: a tile costs tile_cost (the epilogue walks the whole
-    // tile) plus one per contributing k-unit (the contraction); measured on B200
+    // tile) and one per contributing k-unit (the contraction).  The bitset kernel does one after the other; in the
+    // tcgen05 kernel the MMA pipeline runs beside the epilogue, so a tile costs the larger of the two plus the part
+    // of the smaller one that does not hide (fitted on B200 part by part).
     std::vector<int64_t> rb_cost(std::max(plan.n_rowblocks, 1), 0);
     int64_t total_cost = 0;
     for (int rb = 0; rb < plan.n_rowblocks; rb++) {
         const int ncb = (int)(plan.unit_prefix[rb + 1] - plan.unit_prefix[rb]);
         int64_t c = 0;
-        for (int k = 0; k < ncb; k++) c += tile_cost + std::max(0, plan.k_hi[rb] - plan.k_lo[plan.unit_cb0[rb] + k]);
+        for (int k = 0; k < ncb; k++) {
+            const int kb = std::max(0, plan.k_hi[rb] - plan.k_lo[plan.unit_cb0[rb] + k]);
+            c += 100 * (int64_t)std::max(tile_cost, kb) + (int64_t)(100 - overlap_pct) * std::min(tile_cost, kb);
+        }
         rb_cost[rb] = c;
         total_cost += c;
     }

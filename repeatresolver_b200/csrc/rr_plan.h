@@ -26,11 +26,12 @@ struct rr_plan {
 
 // ti / tj: row / column sites per tile; kunit: rows (reads) per contraction unit
 // (32 = one u32 word for the bitset kernel, the K block for the tcgen05 kernel); tile_cost: cost of a tile's
-// epilogue in k-unit equivalents (multi-GPU balance).
+// epilogue in k-unit equivalents, overlap_pct: how much of the smaller of (epilogue, contraction) hides behind the
+// larger one, 0 = none (multi-GPU balance).
 // start/end: spans in rank order, or NULL when rows are not single spans (no skipping).
 void rr_plan_build(rr_plan &plan, int R, int N, int mincov, const int32_t *gsize, const int32_t *coverage,
                    const int32_t *breakcol, const int32_t *start, const int32_t *end, int ti, int tj, int kunit,
-                   int tile_cost, int part_index, int part_count);
+                   int tile_cost, int overlap_pct, int part_index, int part_count);
 
 // ---- tcgen05 variant hooks (rr_scan_umma.cu) ---------------------------------------------
 struct rr_umma_state;
