@@ -4,6 +4,7 @@
 // /root/reference/MaxCorrelation.c:796-817.
 #pragma once
 #include <stdint.h>
+#include <algorithm>
 #include <vector>
 #include "rr_host.h"
 
@@ -13,8 +14,16 @@ struct rr_plan {
     int n_rowsites = 0, n_rowblocks = 0, n_colblocks = 0;
     std::vector<int64_t> unit_prefix;   // [n_rowblocks+1] prefix sum of column blocks per row block
     std::vector<int32_t> unit_cb0;      // [n_rowblocks] first column block
-    std::vector<int32_t> k_hi;          // [n_rowblocks] exclusive upper bound of contributing k-units
-    std::vector<int32_t> k_lo;          // [n_colblocks] inclusive lower bound
+    // contraction ranges, one per LENGTH CLASS of rows (c = 0: ranks [0, class_split), c = 1: the rest; each class
+    // sorted by span start): the k-units of class c that can contribute to (row block rb, column block cb) are
+    // [k_lo[c * n_colblocks + cb], k_hi[c * n_rowblocks + rb]) - empty when lo >= hi
+    std::vector<int32_t> k_hi;          // [2][n_rowblocks] exclusive upper bound of contributing k-units
+    std::vector<int32_t> k_lo;          // [2][n_colblocks] inclusive lower bound
+    int kunits(int rb, int cb) const
+    {
+        const int a = k_hi[rb] - k_lo[cb], b = k_hi[(size_t)std::max(n_rowblocks, 1) + rb] - k_lo[(size_t)std::max(n_colblocks, 1) + cb];
+        return (a > 0 ? a : 0) + (b > 0 ? b : 0);
+    }
     std::vector<int64_t> rb_pairs;      // [n_rowblocks] pair tests per row block
     int rb_lo = 0, rb_hi = 0;           // this part's row blocks
     int part_index = 0, part_count = 1;
@@ -28,9 +37,10 @@ struct rr_plan {
 // (32 = one u32 word for the bitset kernel, the K block for the tcgen05 kernel); tile_cost: cost of a tile's
 // epilogue in k-unit equivalents, overlap_pct: how much of the smaller of (epilogue, contraction) hides behind the
 // larger one, 0 = none (multi-GPU balance).
-// start/end: spans in rank order, or NULL when rows are not single spans (no skipping).
+// start/end: spans in rank order, or NULL when rows are not single spans (no skipping); class_split: ranks
+// [0, class_split) are the short rows, the rest the long ones, each class sorted by span start (a multiple of 256).
 void rr_plan_build(rr_plan &plan, int R, int N, int mincov, const int32_t *gsize, const int32_t *coverage,
-                   const int32_t *breakcol, const int32_t *start, const int32_t *end, int ti, int tj, int kunit,
+                   const int32_t *breakcol, const int32_t *start, const int32_t *end, int class_split, int ti, int tj, int kunit,
                    int tile_cost, int overlap_pct, int part_index, int part_count);
 
 // ---- tcgen05 variant hooks (rr_scan_umma.cu) ---------------------------------------------

@@ -81,8 +81,9 @@ struct um_params {
     rr_scan_params P;
     const um_unit *units;
     int n_units;
-    const int32_t *k_hi;      // [row tiles]   exclusive K-block bound
-    const int32_t *k_lo;      // [column tiles] inclusive K-block bound
+    const int32_t *k_hi;      // [2][n_rt] exclusive K-block bound per length class of rows (rr_plan.h) and row tile
+    const int32_t *k_lo;      // [2][n_ct] inclusive K-block bound per class and column tile
+    int n_rt, n_ct;
     int lnf_smem;             // ln(n!) entries (as float) staged in shared memory
     float t1_margin;          // FP32 tier-1 rounding margin, log10 units (see rr_tier1_f32)
 };
@@ -303,10 +304,11 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint32_t it = 0;
             for (int u = blockIdx.x; u < U.n_units; u += gridDim.x) {
                 const um_unit un = U.units[u];
-                const int khi = U.k_hi[un.rt];
+                const int khi[2] = {U.k_hi[un.rt], U.k_hi[U.n_rt + un.rt]};
                 for (int ct = un.ct0; ct < un.ct1; ct++) {
                     if (U.P.flags & 0x8000u) continue;  // timing experiment: epilogue only
-                    for (int kb = U.k_lo[ct]; kb < khi; kb++, it++) {
+                    for (int seg = 0; seg < 2; seg++)
+                    for (int kb = U.k_lo[seg * U.n_ct + ct]; kb < khi[seg]; kb++, it++) {
                         const int s = it % UM_STAGES;
                         const uint32_t ph = (it / UM_STAGES) & 1;
                         mbar_wait_sleep(&T->empty[s], ph ^ 1, 64);
@@ -327,16 +329,19 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint32_t it = 0, tile = 0;
             for (int u = blockIdx.x; u < U.n_units; u += gridDim.x) {
                 const um_unit un = U.units[u];
-                const int khi = U.k_hi[un.rt];
+                const int khi[2] = {U.k_hi[un.rt], U.k_hi[U.n_rt + un.rt]};
                 for (int ct = un.ct0; ct < un.ct1; ct++) {
-                    const int klo = U.k_lo[ct];
-                    if (klo >= khi || (U.P.flags & 0x8000u)) continue;  // no read covers both tiles: the epilogue uses zeros
+                    const int klo[2] = {U.k_lo[ct], U.k_lo[U.n_ct + ct]};
+                    // no read covers both tiles: the epilogue uses zeros
+                    if ((klo[0] >= khi[0] && klo[1] >= khi[1]) || (U.P.flags & 0x8000u)) continue;
                     const int acc = tile & 1;
                     const uint32_t aph = (tile >> 1) & 1;
                     mbar_wait_sleep(&T->tempty[acc], aph ^ 1, 128);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(acc * UM_ACC_STRIDE);
-                    for (int kb = klo; kb < khi; kb++, it++) {
+                    uint32_t accumulate = 0;   // the first MMA of a tile overwrites the accumulator
+                    for (int seg = 0; seg < 2; seg++)
+                    for (int kb = klo[seg]; kb < khi[seg]; kb++, it++) {
                         const int s = it % UM_STAGES;
                         const uint32_t ph = (it / UM_STAGES) & 1;
                         mbar_wait_sleep(&T->full[s], ph, 32);
@@ -347,8 +352,9 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                         for (int k = 0; k < UM_KB / 32; k++) {
                             // advance 32 bytes (one K=32 slice) inside the 128 B swizzle span: +2 in 16 B units
-                            tc_mma<MODE>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                         (kb > klo || k > 0) ? 1u : 0u, tmem_base + UM_SF_COL, tmem_base + UM_SF_COL + 8);
+                            tc_mma<MODE>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate,
+                                         tmem_base + UM_SF_COL, tmem_base + UM_SF_COL + 8);
+                            accumulate = 1u;
                         }
                         tc_commit(&T->empty[s]);  // frees the smem stage when these MMAs retire
                     }
@@ -384,7 +390,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
         for (int u = blockIdx.x; u < U.n_units; u += gridDim.x) {
             const um_unit un = U.units[u];
-            const int khi = U.k_hi[un.rt];
+            const int khi0 = U.k_hi[un.rt], khi1 = U.k_hi[U.n_rt + un.rt];
             n_units += (ew == 0 && lane == 0);
             // ---- row-side state of this thread (one output row = one group of one row site) ----
             const int ii = lane_row ? P.rowsites[un.rt * UM_ROW_SITES + quarter * 6 + site_l] : -1;
@@ -394,8 +400,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             float thr_i = 0.0f;                    // running max of row group i, rounded down (refreshed from HBM)
 
             for (int ct = un.ct0; ct < un.ct1; ct++) {
-                const int klo = U.k_lo[ct];
-                const bool has_counts = klo < khi && !(P.flags & 0x8000u);
+                const bool has_counts = (U.k_lo[ct] < khi0 || U.k_lo[U.n_ct + ct] < khi1) && !(P.flags & 0x8000u);
                 const int jsite0 = ct * UM_COL_SITES;
                 // ---- this warp's column groups: sites sub, sub+UM_SUB, ... (slot w <-> site sub + w*UM_SUB)
                 // all loads of the tile's thresholds are issued back to back (the maximum is read whether or not the
@@ -726,7 +731,7 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
                 if (ncb <= 0) continue;
                 cc_min = std::min(cc_min, cb0 / UNIT_CT);
                 cc_max = std::max(cc_max, (cb0 + ncb - 1) / UNIT_CT);
-                for (int c = 0; c < ncb; c++) kblocks += std::max(0, plan.k_hi[rb] - plan.k_lo[cb0 + c]);
+                for (int c = 0; c < ncb; c++) kblocks += plan.kunits(rb, cb0 + c);
             }
             for (int rg = plan.rb_lo; rg < plan.rb_hi; rg += GR)
                 for (int cg = cc_max < 0 ? 1 : cc_min / GC; cc_max >= 0 && cg <= cc_max / GC; cg++)
@@ -812,6 +817,8 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
     U.n_units = S->n_units;
     U.k_hi = S->d_khi;
     U.k_lo = S->d_klo;
+    U.n_rt = std::max(plan.n_rowblocks, 1);
+    U.n_ct = std::max(plan.n_colblocks, 1);
     const int grid = std::min<int>(n_sm, S->n_units);
     U.lnf_smem = std::min(std::min(plan.max_cov + 2, P.R + 2), UM_LNF_MAX);
     const size_t smem_bytes = UM_LNF_OFF + (size_t)U.lnf_smem * sizeof(float);
