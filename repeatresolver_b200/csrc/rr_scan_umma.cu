@@ -751,8 +751,8 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
         // a column's first visit, where every pair is a candidate, then happens on one GPU only, and the GPUs
         // exchange the seeded maxima (all-reduce MAX) before their full passes.
         // The seeding pass itself starts from zero thresholds; a pre-seed over every PRESEED-th seed row tile
-        // takes that warm-up on ~1/256 of the row tiles instead of 1/32.
-        static const int SEED = getenv("RR_SEED") ? atoi(getenv("RR_SEED")) : 32;        // tuning knobs (debug)
+        // takes that warm-up on ~1/512 of the row tiles instead of 1/64.
+        static const int SEED = getenv("RR_SEED") ? atoi(getenv("RR_SEED")) : 64;        // tuning knobs (debug)
         static const int PRESEED = getenv("RR_PRESEED") ? atoi(getenv("RR_PRESEED")) : 8;
         std::vector<um_unit> seed_units, preseed_units;
         if (plan.n_rowblocks >= 2 * SEED) {
