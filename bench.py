@@ -40,7 +40,7 @@ WORKLOADS = {
 MINCOV = 30
 # dram__bytes_read.sum + dram__bytes_write.sum of the scan kernel, per launch, from the committed ncu capture
 # (profiles/); None until measured for that workload
-TRAFFIC = {"Tree_1perc_30000": 5.08e11}  # profiles/r1_ncu_full_summary_e.csv: dram read 506.2 GB + write 2.1 GB, full pass, mxf4 operands
+TRAFFIC = {"Tree_1perc_30000": 1.092e11}  # profiles/r1_scan_metrics_config2_final.csv (ID 2 = full pass): dram read 107.9 GB + write 1.3 GB, mxf4 operands
 
 
 def load_peaks():
