@@ -156,6 +156,15 @@ int rr_below_median_host(uint32_t schnitt, uint32_t gr1, uint32_t gr2, uint32_t 
 int rr_breakcols_from_spans(const int32_t *start, const int32_t *end, int rows, int cols, int mincov,
                             int32_t *breakcol /*[cols]*/);
 
+/* the exact contraction ranges of the scan plan (csrc/rr_plan.h), for tests: rows in rank order with spans
+ * start[r]..end[r] (inclusive), ranks [0, class_split) and [class_split, rows) each sorted by start; every site is
+ * taken as a row site, ti / tj sites per row / column block, kunit rows per contraction unit.  A row of class c can
+ * only contribute to (row block rb, column block cb) if its rank lies in
+ * [k_lo[c * n_colblocks + cb] * kunit, k_hi[c * n_rowblocks + rb] * kunit).  k_lo: [2 * ceil(cols / tj)],
+ * k_hi: [2 * n_rowblocks] with n_rowblocks = ceil(max(cols - 20, 0) / ti) returned through *n_rowblocks. */
+int rr_contraction_ranges(const int32_t *start, const int32_t *end, int rows, int cols, int class_split, int ti, int tj,
+                          int kunit, int32_t *k_lo, int32_t *k_hi, int *n_rowblocks);
+
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* CUDA events on the stream every kernel of this handle is launched on */
 int rr_timer_start(rr_packed *pk);

@@ -122,6 +122,37 @@ void rr_dev_free(void *p)
     if (p) cudaFreeAsync(p, g_alloc_stream);
 }
 
+extern "C" int rr_contraction_ranges(const int32_t *start, const int32_t *end, int rows, int cols, int class_split,
+                                     int ti, int tj, int kunit, int32_t *k_lo, int32_t *k_hi, int *n_rowblocks)
+{
+    if (rows < 0 || cols < 0 || ti < 1 || tj < 1 || kunit < 1 || !k_lo || !k_hi || !n_rowblocks || (rows && (!start || !end))) {
+        rr_set_error("rr_contraction_ranges: bad arguments");
+        return RR_E_ARG;
+    }
+    const int ncb = std::max((cols + tj - 1) / tj, 1);
+    if (rows < 4) {   // too few rows for an admissible group (size < R): no row site, nothing contributes
+        std::fill(k_lo, k_lo + 2 * ncb, 0);
+        k_hi[0] = k_hi[1] = 0;
+        *n_rowblocks = 0;
+        return RR_OK;
+    }
+    // every group admissible as a row and as a column group, no first-break: all sites with a partner are row sites
+    const int mincov = 4;
+    std::vector<int32_t> gsize((size_t)5 * cols), coverage(cols, 20), breakcol(cols, cols);
+    for (size_t g = 0; g < gsize.size(); g++) gsize[g] = (g % 5 < 4) ? 3 : 2;   // mincov/4 < size < rows; 4 x 3 bases > 20 / 2
+    rr_plan plan;
+    rr_plan_build(plan, rows, cols, mincov, gsize.data(), coverage.data(), breakcol.data(), start, end,
+                  class_split, ti, tj, kunit, 1, 0, 0, 1);
+    if ((int)plan.k_lo.size() != 2 * std::max(plan.n_colblocks, 1) || (int)plan.k_hi.size() != 2 * std::max(plan.n_rowblocks, 1)) {
+        rr_set_error("rr_contraction_ranges: unexpected plan shape");
+        return RR_E_ARG;
+    }
+    std::copy(plan.k_lo.begin(), plan.k_lo.end(), k_lo);
+    std::copy(plan.k_hi.begin(), plan.k_hi.end(), k_hi);
+    *n_rowblocks = plan.n_rowblocks;
+    return RR_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // measurement helpers
 // ---------------------------------------------------------------------------------------

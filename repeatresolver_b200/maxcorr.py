@@ -227,6 +227,21 @@ def below_median_host(s, gr1, gr2, cov):
     return bool(lib.rr_below_median_host(s, gr1, gr2, cov))
 
 
+def contraction_ranges(start, end, cols, class_split, ti, tj, kunit):
+    """k_lo [2][ceil(cols/tj)], k_hi [2][n_rowblocks] of the scan plan for rows given in rank order (test hook)"""
+    start = np.ascontiguousarray(start, dtype=np.int32)
+    end = np.ascontiguousarray(end, dtype=np.int32)
+    ncb = max((cols + tj - 1) // tj, 1)
+    nrb_max = max((max(cols - 20, 0) + ti - 1) // ti, 1)
+    k_lo = np.zeros(2 * ncb, dtype=np.int32)
+    k_hi = np.zeros(2 * nrb_max, dtype=np.int32)
+    nrb = C.c_int(0)
+    _check(lib.rr_contraction_ranges(start.ctypes.data, end.ctypes.data, len(start), cols, class_split, ti, tj, kunit,
+                                     k_lo.ctypes.data, k_hi.ctypes.data, C.byref(nrb)), "rr_contraction_ranges")
+    n = max(nrb.value, 1)
+    return k_lo.reshape(2, ncb), k_hi[:2 * n].reshape(2, n), nrb.value
+
+
 def breakcols_from_spans(start, end, cols, mincov):
     start = np.ascontiguousarray(start, dtype=np.int32)
     end = np.ascontiguousarray(end, dtype=np.int32)

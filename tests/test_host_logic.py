@@ -244,6 +244,43 @@ def test_breakcols_from_spans(mincov):
     assert (np.minimum(got, np.maximum(cols, np.arange(cols) + 20)) == np.minimum(want, np.maximum(cols, np.arange(cols) + 20))).all()
 
 
+@pytest.mark.parametrize("seed,kunit,ti,tj", [(1, 256, 24, 48), (2, 128, 24, 48), (3, 32, 8, 32), (4, 256, 24, 48)])
+def test_contraction_ranges_cover_every_contributing_row(seed, kunit, ti, tj):
+    """K-range skipping is exact only if every row that covers a site of the row block AND a site of the column block
+    lies inside the two rank ranges the plan keeps (one per length class of rows) - checked exhaustively on random
+    spans with a few MSA-spanning rows, rows are ordered as rr_pack orders them"""
+    rng = np.random.default_rng(seed)
+    R, N = (1500, 2600) if seed != 4 else (700, 1900)   # seed 4: below 1024 rows -> a single class
+    ln = np.minimum(N, (rng.gamma(2.0, 300.0, R) + 30).astype(np.int64))
+    ln[rng.integers(0, R, 12)] = N                                        # rows spanning everything
+    st = (rng.random(R) * (N - ln + 1)).astype(np.int64)
+    en = st + ln - 1
+    split = (R * 3 // 4 // 256 * 256) if R >= 1024 else 0                  # rr_pack's rule
+    by_len = np.lexsort((st, en - st))
+    cls = np.ones(R, dtype=np.int64)
+    cls[by_len[:split]] = 0
+    order = np.lexsort((en, st, cls))
+    st, en, cls = st[order], en[order], cls[order]
+    assert (cls[:split] == 0).all() and (cls[split:] == 1).all()
+    k_lo, k_hi, nrb = rr.contraction_ranges(st, en, N, split, ti, tj, kunit)
+    assert nrb == (N - 20 + ti - 1) // ti
+    rank = np.arange(R)
+    checked = 0
+    for rb in range(0, nrb, 7):
+        s_lo, s_hi = rb * ti, min(rb * ti + ti - 1, N - 21)
+        for cb in range((s_lo + 20) // tj, k_lo.shape[1], 5):
+            c_lo = cb * tj
+            contributes = (st <= s_hi) & (en >= max(c_lo, s_lo))         # covers some site of both blocks
+            for c in (0, 1):
+                r = rank[contributes & (cls == c)]
+                if len(r):
+                    assert k_lo[c, cb] * kunit <= r.min() and r.max() < k_hi[c, rb] * kunit, (rb, cb, c)
+                    checked += 1
+            # and the ranges stay inside their class
+            assert k_hi[0, rb] * kunit <= max(split, 0) + kunit - 1 and k_lo[1, cb] * kunit >= split - (split % kunit)
+    assert checked > 40
+
+
 def test_cli_without_gpu_reports_and_fails(tmp_path):
     exe = os.path.join(ROOT, "repeatresolver_b200", "bin", "MaxCorrelation")
     r = subprocess.run([exe], capture_output=True, text=True)
