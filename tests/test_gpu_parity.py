@@ -342,6 +342,62 @@ def test_unusual_coverage_floors(mincov, variant, tmp_path):
     pk.close()
 
 
+def transposon_shaped_codes():
+    """BASELINE.json configs[3]: one section of ~7 kbp (25k columns with the insertion columns), ~2.8k reads most of
+    which span most of the section, MIXED coverage: 70 % of the reads are cut back to a random 25-100 % of their span
+    (still one span per row), so the depth varies more than twofold along the section"""
+    g = rr.MsaGen(type="Distributed", copies=60, coverage=40, repeat_len=6000, diff=0.01, seed=1004, flank=600, threads=8)
+    cells = g.codes()
+    rng = np.random.default_rng(1004)
+    cov = cells < 5
+    start = cov.argmax(1)
+    end = cells.shape[1] - 1 - cov[:, ::-1].argmax(1)
+    for r in np.nonzero(rng.random(g.rows) < 0.7)[0]:
+        ln = end[r] - start[r] + 1
+        keep = int(ln * rng.uniform(0.25, 1.0))
+        s0 = start[r] + int(rng.integers(0, ln - keep + 1))
+        cells[r, : s0] = 5
+        cells[r, s0 + keep:] = 5
+    return cells
+
+
+def test_config3_transposon_shape_mixed_coverage():
+    cells = transposon_shaped_codes()
+    R, N = cells.shape
+    depth = (cells < 5).sum(0)
+    assert R > 2500 and N > 20000 and depth.max() > 2 * depth.min() and depth.max() > 1500
+    msa = rr.MSA.from_cells(cells, codes=True)
+    pk = rr.Packed(msa, 0)
+    oracle = O.Oracle.from_codes(cells)
+    gs, cv = pk.sizes()
+    assert (gs == oracle.gsize()).all() and (cv == oracle.coverage()).all()
+    st = pk.scan(mincov=30, variant="auto")
+    M, A = pk.fetch()
+    assert st["pair_tests"] > 2e8
+    for other in VARIANTS:   # the independent count kernels agree bit for bit
+        s2 = pk.scan(mincov=30, variant=other)
+        M2, A2 = pk.fetch()
+        assert s2["pair_tests"] == st["pair_tests"] and (M2 == M).all() and (A2 == A).all(), other
+    # an exact 1/k cyclic row sample of the oracle: a lower bound everywhere, attained where the best partner of a
+    # sampled row lies to its right
+    k = 499
+    Ms, As, Ps = oracle.scan(30, modulus=k, res_lo=0, res_hi=1)
+    assert Ps > 2e5
+    assert (M >= Ms * (1 - REL_TOL)).all()
+    rows = np.nonzero((Ms > 0) & ((np.arange(len(Ms)) // 5) % k == 0))[0]
+    right = rows[(As[rows] > rows) & (A[rows] > rows)]
+    assert len(right) >= 5
+    assert (np.abs(M[right] - Ms[right]) <= REL_TOL * Ms[right]).all()
+    # every reported maximum is reproduced from its reported partner by the oracle's counts and score
+    rng = np.random.default_rng(3)
+    for gidx in rng.choice(np.nonzero(M > 0)[0], 300, replace=False):
+        i, j = min(gidx, A[gidx]), max(gidx, A[gidx])
+        c = oracle.counts(i, j)
+        z = O.score(c[0], c[1], c[2], c[3], gs[i], gs[j])
+        assert abs(z - M[gidx]) <= REL_TOL * z
+    pk.close()
+
+
 def test_config1_shape_full_oracle_scan():
     """BASELINE.json configs[0] shape from the generator (Tree, 10 copies, 40x, 5 kbp: ~670 rows x ~17.6k columns,
     ~5e8 pair tests): the largest case with a FULL oracle scan (all host threads); every variant, values within
