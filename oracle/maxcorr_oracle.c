@@ -250,6 +250,80 @@ int64_t rr_oracle_scan(const rr_oracle *o, int mincov, int modulus, int res_lo, 
     return pairs;
 }
 
+/* ---- the clique of one query group, /root/reference/RepeatResolver.c ----------
+ * Restated for the round that builds the GPU path of Group_Refinement; validated against the unmodified
+ * RepeatResolver.c behind oracle/ref_cliquer_driver.c (tests/test_oracle_cliquer.py). */
+
+/* Group_PositiveSignificance, RepeatResolver.c:472-488, on already-computed counts: like PositiveSignificance but
+ * without the schnitt < 1 brake (the caller only asks for schnitt > mincov/4) and saturating at 97.90 + F1. */
+double rr_oracle_group_score(unsigned int schnitt, unsigned int gr1, unsigned int gr2, unsigned int cov, int sizei,
+                             int sizej)
+{
+    double Z;
+    if (gr1 == 0 || gr2 == 0) return 0.0;                                /* 482 */
+    Z = gsl_cdf_hypergeometric_Q(schnitt - 1, gr2, cov - gr2, gr1);      /* 451 */
+    Z = -1.0 * log10(Z);                                                 /* 452 */
+    if (isinf(Z) || Z > 99) Z = 99.0;                                    /* 453 */
+    if (isinf(Z) || Z > 98.0) {                                          /* 486: 97.90 + F_beta(G1, G2, 1.0), 432-447 */
+        double s = (double)schnitt, F = (1.0 + 1.0) * s;
+        if (F < 0.0001) F = 0.0;
+        else F /= ((1 + 1.0 * 1.0) * s + (1.0 * 1.0 * (double)(sizei - (int)schnitt)) + (double)(sizej - (int)schnitt));
+        Z = 97.90 + F;
+    }
+    return Z;
+}
+
+/* TheBestUpdater, RepeatResolver.c:1156-1176: insertion into the descending list, behind equal values; slot 0 (the
+ * query group itself) is never displaced */
+static void rr_best_updater(int32_t *clique, double *best, int maxclique, int i, double Z)
+{
+    int ii, j;
+    if (best[maxclique - 1] >= Z) return;                                /* 1158 */
+    ii = maxclique - 1;
+    while (best[ii] < Z && ii > 0) ii--;                                 /* 1162-1165 */
+    ii++;
+    for (j = maxclique - 1; j > ii; j--) { best[j] = best[j - 1]; clique[j] = clique[j - 1]; }
+    best[ii] = Z;
+    clique[ii] = i;
+}
+
+/* Cliquer, RepeatResolver.c:1179-1240: the up to maxclique-1 groups of columns [anfang, ende) that correlate best
+ * with group a (score > greedy, intersection > mincov/4), best first.  clique: [maxclique+1], clique[0] = a, unused
+ * slots and clique[maxclique] = -1; best: [maxclique] scores, best[0] = 100 (1229).  Returns the number of members
+ * including a.  The reference leaves the unused slots of its malloc'ed array uninitialised until its trimming loop
+ * (1231-1232) overwrites them with -1; this restatement starts from -1 and does not step below slot 1 there. */
+int rr_oracle_cliquer(const rr_oracle *o, int anfang, int ende, int mincov, int maxclique, double greedy, int a,
+                      int32_t *clique, double *best)
+{
+    const int sc = o->sc;
+    const uint64_t *ga = o->groups + (size_t)a * sc, *ca = o->cover + (size_t)(a / 5) * sc;
+    int ii, k, j, n;
+    for (j = 0; j <= maxclique; j++) clique[j] = -1;
+    for (j = 0; j < maxclique; j++) best[j] = 0.0;                       /* 1198 */
+    clique[0] = a;                                                       /* 1197 */
+    if (ende > o->N) ende = o->N;
+    for (ii = anfang < 0 ? 0 : anfang; ii < ende; ii++)                  /* 1205 */
+        for (k = 0; k < 5; k++) {
+            const int i = ii * 5 + k;
+            const uint64_t *gi = o->groups + (size_t)i * sc, *ci = o->cover + (size_t)ii * sc;
+            int schnitt;
+            if (i == a) continue;                                        /* 1210 */
+            schnitt = rr_isect(gi, ga, sc);                              /* 1213 */
+            if (schnitt > mincov / 4) {                                  /* 1215 */
+                const double Z = rr_oracle_group_score((unsigned)schnitt, (unsigned)rr_isect(gi, ca, sc),
+                                                       (unsigned)rr_isect(ga, ci, sc), (unsigned)rr_isect(ci, ca, sc),
+                                                       o->gsize[i], o->gsize[a]);   /* 1217, argument order of 472 */
+                if (Z > greedy) rr_best_updater(clique, best, maxclique, i, Z);       /* 1218-1220 */
+            }
+        }
+    best[0] = 100.0;                                                     /* 1229 */
+    clique[maxclique] = -1;                                              /* 1230 */
+    j = maxclique - 1;
+    while (j >= 1 && (best[j] < greedy || clique[j] == clique[j - 1])) { clique[j] = -1; j--; }   /* 1231-1232 */
+    for (n = 0; n < maxclique && clique[n] >= 0; n++) {}
+    return n;
+}
+
 /* MaxCorrelation.c:516-532 (MaxCorrsRausschreiben) */
 int rr_oracle_write(const char *path, const double *M, int G)
 {

@@ -34,6 +34,10 @@ def lib():
         L.rr_oracle_scan.restype = C.c_int64
         L.rr_oracle_scan.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.rr_oracle_write.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
+        L.rr_oracle_group_score.restype = C.c_double
+        L.rr_oracle_group_score.argtypes = [C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_int]
+        L.rr_oracle_cliquer.restype = C.c_int
+        L.rr_oracle_cliquer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         L.rr_oracle_lnfact.restype = C.c_double
         L.rr_oracle_lnfact.argtypes = [C.c_uint]
         L.gsl_cdf_hypergeometric_Q.restype = C.c_double
@@ -87,6 +91,14 @@ class Oracle:
         P = lib().rr_oracle_scan(self._h, mincov, modulus, res_lo, res_hi, M.ctypes.data, A.ctypes.data)
         return M[:G], A[:G], int(P)
 
+    def cliquer(self, a, mincov=30, maxclique=30, greedy=3.0, anfang=0, ende=None):
+        """RepeatResolver.c:1179-1240 for query group a: (members incl. a, scores with best[0] = 100)"""
+        clique = np.full(maxclique + 1, -1, dtype=np.int32)
+        best = np.zeros(maxclique, dtype=np.float64)
+        n = lib().rr_oracle_cliquer(self._h, anfang, self.N if ende is None else ende, mincov, maxclique, greedy, int(a),
+                                    clique.ctypes.data, best.ctypes.data)
+        return clique[:n].copy(), best[:n].copy()
+
     def close(self):
         if self._h:
             lib().rr_oracle_free(self._h)
@@ -101,6 +113,10 @@ class Oracle:
 
 def score(s, gr1, gr2, cov, sizei=0, sizej=0):
     return lib().rr_oracle_score(s, gr1, gr2, cov, sizei, sizej)
+
+
+def group_score(s, gr1, gr2, cov, sizei=0, sizej=0):
+    return lib().rr_oracle_group_score(s, gr1, gr2, cov, sizei, sizej)
 
 
 def hyper_Q(k, n1, n2, t):

@@ -1,0 +1,108 @@
+"""SURVEY.md section 8f row 2 ("next"): the oracle for Group_Refinement's inner step, Cliquer
+(/root/reference/RepeatResolver.c:1179-1240), pinned before a GPU path for it exists.
+  * the C restatement (oracle/maxcorr_oracle.c: rr_oracle_cliquer, rr_oracle_group_score) against the committed
+    output of the UNMODIFIED RepeatResolver.c (tests/golden/cliquer.json, made by oracle/gen_golden_cliquer.py);
+  * against the reference binary itself on a fresh input, where oracle/_ref/ref_cliquer_driver exists;
+  * the score variant's relation to MaxCorrelation's (472-488 vs 421-434)."""
+import gzip
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from conftest import GOLD, ROOT, golden_msa
+
+DRV = os.path.join(ROOT, "oracle", "_ref", "ref_cliquer_driver")
+CODES = np.full(256, 5, dtype=np.uint8)
+for _ch, _k in ((b"aA", 0), (b"cC", 1), (b"gG", 2), (b"tT", 3), (b"-_", 4)):
+    for _c in _ch:
+        CODES[_c] = _k
+
+
+def window_codes(text, von, bis):
+    """RepeatResolver.c's reader (293-429): rows with a symbol at both ends of the window, its columns only"""
+    lines = text.split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()
+    rows = [l for l in lines if l[von:von + 1] != b" " and l[bis:bis + 1] != b" "]
+    return np.stack([CODES[np.frombuffer(l[von:bis + 1], dtype=np.uint8)] for l in rows])
+
+
+def cliquer_cases():
+    with open(os.path.join(GOLD, "cliquer.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", sorted(cliquer_cases()))
+def test_cliquer_matches_the_unmodified_reference(name):
+    case = cliquer_cases()[name]
+    codes = window_codes(golden_msa(name), case["von"], case["bis"])
+    assert codes.shape == (case["rows"], case["cols"])
+    o = O.Oracle.from_codes(codes)
+    sizes = set()
+    for q, want in case["queries"].items():
+        members, best = o.cliquer(int(q), case["mincov"], case["maxclique"], case["greedy"])
+        assert members[0] == int(q) and best[0] == 100.0
+        assert list(members[1:]) == want["members"], q
+        assert [float(b).hex() for b in best[1:]] == want["scores"], q      # bit for bit
+        assert len(members) == want["n"] <= case["maxclique"]
+        assert (np.diff(best[1:]) <= 0).all() and (best[1:] > case["greedy"]).all()
+        sizes.add(len(members))
+    assert 1 in sizes and max(sizes) > 1                                      # empty and non-empty cliques both pinned
+    if name == "saturated":                                                   # 97.90 + F1 (486) is exercised
+        top = [float.fromhex(s) for w in case["queries"].values() for s in w["scores"]]
+        assert any(97.9 < z <= 98.9 for z in top)
+
+
+@pytest.mark.skipif(not os.path.exists(DRV), reason="oracle/_ref/ref_cliquer_driver not built (no reference sources here)")
+def test_cliquer_matches_the_reference_binary_on_fresh_input(tmp_path):
+    import repeatresolver_b200 as rr
+    g = rr.MsaGen(type="Tree", copies=8, coverage=40, repeat_len=1500, diff=0.01, seed=21, flank=300)
+    text = g.text()
+    p = tmp_path / "M"
+    p.write_bytes(text)
+    N = g.cols
+    von, bis = N // 4, 3 * N // 4
+    codes = window_codes(text, von, bis)
+    o = O.Oracle.from_codes(codes)
+    M, A, P = o.scan(30)
+    queries = [int(q) for q in np.argsort(-M, kind="stable")[:8]] + [7, 5 * (codes.shape[1] // 2) + 4]
+    out = subprocess.run([DRV, str(p), str(von), str(bis), "30", "30", "3.0"] + [str(q) for q in queries],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    lines = [l for l in out.stdout.splitlines() if l and l[0].isdigit()]
+    assert tuple(int(x) for x in lines[0].split()) == codes.shape
+    assert len(lines) == 1 + len(queries)
+    nonempty = 0
+    for l in lines[1:]:
+        f = l.split()
+        a, n = int(f[0]), int(f[1])
+        members, best = o.cliquer(a, 30, 30, 3.0)
+        assert len(members) == n
+        assert list(members[1:]) == [int(x.split(":")[0]) for x in f[2:]]
+        assert np.array_equal(best[1:], np.array([float(x.split(":")[1]) for x in f[2:]]))
+        nonempty += n > 1
+    assert nonempty >= 8
+
+
+def test_group_score_is_the_scan_score_below_saturation_and_97_90_plus_f1_above():
+    rng = np.random.default_rng(5)
+    for _ in range(2000):
+        cov = int(rng.integers(2, 3000))
+        gr1 = int(rng.integers(1, cov + 1))
+        gr2 = int(rng.integers(1, cov + 1))
+        s = int(rng.integers(max(1, gr1 + gr2 - cov), min(gr1, gr2) + 1)) if max(1, gr1 + gr2 - cov) <= min(gr1, gr2) else 0
+        if s < 1:
+            continue
+        zi, zj = gr1 + int(rng.integers(0, 50)), gr2 + int(rng.integers(0, 50))
+        a, b = O.score(s, gr1, gr2, cov, zi, zj), O.group_score(s, gr1, gr2, cov, zi, zj)
+        if a <= 98.0:
+            assert a == b                                                     # 472-488 == 421-434 below saturation
+        else:
+            assert b == 97.90 + (a - 98.0) or abs(b - (a - 0.1)) < 1e-12      # same F1, other offset (486 vs 432)
+    assert O.group_score(0, 0, 5, 10, 3, 5) == 0.0                            # 482
+    # deep saturation: F1 = 2s / (|Gi| + |Gj|)
+    assert O.group_score(400, 400, 400, 2000, 400, 400) == 97.90 + 1.0
