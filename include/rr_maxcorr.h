@@ -156,6 +156,22 @@ int rr_below_median_host(uint32_t schnitt, uint32_t gr1, uint32_t gr2, uint32_t 
 int rr_breakcols_from_spans(const int32_t *start, const int32_t *end, int rows, int cols, int mincov,
                             int32_t *breakcol /*[cols]*/);
 
+/* ---- next scope row: Cliquer, the inner step of Group_Refinement ----------------------
+ * RepeatResolver.c:1179-1240: the up to maxclique-1 groups of columns [anfang, ende) that correlate best with group
+ * `query_group` (Group_PositiveSignificance 472-488 > greedy, intersection > mincov/4), best first, ties in group
+ * order (TheBestUpdater 1156-1176).  members: [maxclique+1], members[0] = query_group, unused slots -1;
+ * scores: [maxclique], scores[0] = 100 (1229), unused slots 0; *n_members counts the query group itself.
+ * First version: the four intersection counts of every candidate come from the device bitsets (the reference's
+ * Schnitt calls, its dominant cost); the scores of the candidates are evaluated on the host, in threads. */
+int rr_cliquer(rr_packed *pk, int query_group, int anfang, int ende, int mincov, int maxclique, double greedy,
+               int32_t *members, double *scores, int *n_members);
+/* the host half of rr_cliquer on given counts (tests): groups[k] ascending candidate ids, counts[4k..4k+3] =
+ * {|Gk & Gq|, |Gk & Cq|, |Gq & Ck|, |Ck & Cq|}, sizes[k] = |Gk| */
+int rr_cliquer_from_counts(int query_group, int64_t n, const int32_t *groups, const int32_t *counts, const int32_t *sizes,
+                           int size_query, int mincov, int maxclique, double greedy, int32_t *members, double *scores,
+                           int *n_members);
+double rr_group_score_host(uint32_t schnitt, uint32_t gr1, uint32_t gr2, uint32_t cov, int32_t sizei, int32_t sizej);
+
 /* the exact contraction ranges of the scan plan (csrc/rr_plan.h), for tests: rows in rank order with spans
  * start[r]..end[r] (inclusive), ranks [0, class_split) and [class_split, rows) each sorted by start; every site is
  * taken as a row site, ti / tj sites per row / column block, kunit rows per contraction unit.  A row of class c can

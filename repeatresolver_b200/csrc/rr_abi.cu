@@ -511,6 +511,80 @@ extern "C" int rr_pair_counts(rr_packed *pk, int64_t n, const int32_t *gi, const
 }
 
 // ---------------------------------------------------------------------------------------
+// Cliquer (RepeatResolver.c:1179-1240), first version: device counts, host scores
+// ---------------------------------------------------------------------------------------
+extern "C" double rr_group_score_host(uint32_t s, uint32_t gr1, uint32_t gr2, uint32_t cov, int32_t sizei, int32_t sizej)
+{
+    std::vector<double> &t = host_lnfact((size_t)cov + 2);
+    return rr_group_significance(t.data(), s, gr1, gr2, cov, sizei, sizej);
+}
+
+extern "C" int rr_cliquer_from_counts(int query_group, int64_t n, const int32_t *groups, const int32_t *counts,
+                                      const int32_t *sizes, int size_query, int mincov, int maxclique, double greedy,
+                                      int32_t *members, double *scores, int *n_members)
+{
+    if (n < 0 || maxclique < 1 || !members || !scores || !n_members || (n && (!groups || !counts || !sizes))) {
+        rr_set_error("rr_cliquer_from_counts: bad arguments");
+        return RR_E_ARG;
+    }
+    for (int j = 0; j <= maxclique; j++) members[j] = -1;
+    for (int j = 0; j < maxclique; j++) scores[j] = 0.0;
+    members[0] = query_group;                                            // 1197
+    scores[0] = 100.0;                                                   // 1229
+    // scores of the candidates with an intersection above mincov/4 (1215), a few host threads
+    std::vector<double> Z((size_t)n, 0.0);
+    int32_t max_cov = 0;
+    for (int64_t k = 0; k < n; k++) max_cov = std::max(max_cov, counts[4 * k + 3]);
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)16, (int64_t)std::thread::hardware_concurrency(), n / 4096 + 1}));
+    auto work = [&](int t) {
+        host_lnfact((size_t)max_cov + 2);   // per-thread table, grown once
+        for (int64_t k = n * t / nt; k < n * (t + 1) / nt; k++) {
+            const int32_t *c = counts + 4 * k;
+            if (groups[k] == query_group || c[0] <= mincov / 4) continue;     // 1210, 1215
+            Z[k] = rr_group_score_host((uint32_t)c[0], (uint32_t)c[1], (uint32_t)c[2], (uint32_t)c[3], sizes[k], size_query);
+        }
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) th.emplace_back(work, t);
+        for (auto &t : th) t.join();
+    }
+    // TheBestUpdater (1156-1176) keeps the maxclique-1 largest scores above greedy, equal scores in candidate order:
+    // a stable sort by descending score
+    std::vector<int64_t> cand;
+    for (int64_t k = 0; k < n; k++)
+        if (Z[k] > greedy) cand.push_back(k);                            // 1218
+    std::stable_sort(cand.begin(), cand.end(), [&](int64_t a, int64_t b) { return Z[a] > Z[b]; });
+    int m = 1;
+    for (size_t r = 0; r < cand.size() && m < maxclique; r++, m++) {
+        members[m] = groups[cand[r]];
+        scores[m] = Z[cand[r]];
+    }
+    *n_members = m;
+    return RR_OK;
+}
+
+extern "C" int rr_cliquer(rr_packed *pk, int query_group, int anfang, int ende, int mincov, int maxclique, double greedy,
+                          int32_t *members, double *scores, int *n_members)
+{
+    if (!pk || maxclique < 1 || !members || !scores || !n_members) { rr_set_error("rr_cliquer: bad arguments"); return RR_E_ARG; }
+    if (query_group < 0 || query_group >= 5 * pk->N) { rr_set_error("rr_cliquer: group %d out of range", query_group); return RR_E_ARG; }
+    anfang = std::max(anfang, 0);
+    ende = std::min(ende, pk->N);
+    const int64_t n = ende > anfang ? (int64_t)5 * (ende - anfang) : 0;
+    std::vector<int32_t> gi((size_t)n), gj((size_t)n, query_group), cnt((size_t)4 * n), sz((size_t)n);
+    for (int64_t k = 0; k < n; k++) {
+        gi[k] = (int32_t)(5 * (int64_t)anfang + k);                      // Group1 = the candidate, Group2 = the query (1217)
+        sz[k] = pk->h_gsize[gi[k]];
+    }
+    int rc = rr_pair_counts(pk, n, gi.data(), gj.data(), cnt.data());
+    if (rc) return rc;
+    return rr_cliquer_from_counts(query_group, n, gi.data(), cnt.data(), sz.data(), pk->h_gsize[query_group], mincov, maxclique,
+                                  greedy, members, scores, n_members);
+}
+
+// ---------------------------------------------------------------------------------------
 // scan
 // ---------------------------------------------------------------------------------------
 template <typename T>

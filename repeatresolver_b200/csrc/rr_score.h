@@ -154,6 +154,24 @@ RR_HD double rr_positive_significance(const double *lnf, unsigned int s, unsigne
     return Z;
 }
 
+/* Group_PositiveSignificance (/root/reference/RepeatResolver.c:472-488) on counts: the same hypergeometric score,
+ * without the s < 1 brake (its caller Cliquer only asks for s > mincov/4, 1215) and saturating at 97.90 + F1 (486). */
+RR_HD double rr_group_significance(const double *lnf, unsigned int s, unsigned int gr1, unsigned int gr2,
+                                   unsigned int cov, int sizei, int sizej)
+{
+    double Q, Z;
+    if (gr1 == 0 || gr2 == 0) return 0.0;
+    Q = rr_hyper_Q(lnf, s - 1, gr2, cov - gr2, gr1, 0);
+    Z = RR_MUL(-1.0, log10(Q));
+    if (isinf(Z) || Z > 99) Z = 99.0;
+    if (isinf(Z) || Z > 98.0) {
+        const double sd = (double)s, F = RR_MUL(2.0, sd);
+        if (F < 0.0001) return RR_ADD(97.90, 0.0);
+        Z = RR_ADD(97.90, RR_DIV(F, RR_ADD(RR_ADD(RR_MUL(2.0, sd), (double)(sizei - (int)s)), (double)(sizej - (int)s))));
+    }
+    return Z;
+}
+
 /* ---- pruning bounds (no reference counterpart) -------------------------------------
  * With X ~ Hypergeom(pop = cov, successes = gr2, draws = gr1) the score before the caps
  * is -log10 P[X >= s].  Two rigorous upper bounds:

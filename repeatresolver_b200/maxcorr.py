@@ -138,6 +138,15 @@ class Packed:
     def set_thresholds_device(self, device_ptr):
         _check(lib.rr_scan_set_thresholds_device(self._h, C.c_void_p(device_ptr)), "rr_scan_set_thresholds_device")
 
+    def cliquer(self, query_group, mincov=30, maxclique=30, greedy=3.0, anfang=0, ende=None):
+        """Cliquer (RepeatResolver.c:1179-1240) for one query group: (members incl. the query, scores)"""
+        members = np.full(maxclique + 1, -1, dtype=np.int32)
+        scores = np.zeros(maxclique, dtype=np.float64)
+        n = C.c_int(0)
+        _check(lib.rr_cliquer(self._h, int(query_group), anfang, 2 ** 30 if ende is None else ende, mincov, maxclique, greedy,
+                              members.ctypes.data, scores.ctypes.data, C.byref(n)), "rr_cliquer")
+        return members[:n.value].copy(), scores[:n.value].copy()
+
     def pair_counts(self, gi, gj):
         gi = np.ascontiguousarray(gi, dtype=np.int32)
         gj = np.ascontiguousarray(gj, dtype=np.int32)
@@ -225,6 +234,26 @@ def score_bound_host(s, gr1, gr2, cov):
 
 def below_median_host(s, gr1, gr2, cov):
     return bool(lib.rr_below_median_host(s, gr1, gr2, cov))
+
+
+def group_score_host(s, gr1, gr2, cov, sizei, sizej):
+    """Group_PositiveSignificance (RepeatResolver.c:472-488) on counts, host libm"""
+    return lib.rr_group_score_host(s, gr1, gr2, cov, sizei, sizej)
+
+
+def cliquer_from_counts(query_group, groups, counts, sizes, size_query, mincov=30, maxclique=30, greedy=3.0):
+    """the host half of Cliquer on given counts (test hook): (members incl. the query, scores with scores[0] = 100)"""
+    groups = np.ascontiguousarray(groups, dtype=np.int32)
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    sizes = np.ascontiguousarray(sizes, dtype=np.int32)
+    assert counts.shape == (len(groups), 4) and sizes.shape == groups.shape
+    members = np.full(maxclique + 1, -1, dtype=np.int32)
+    scores = np.zeros(maxclique, dtype=np.float64)
+    n = C.c_int(0)
+    _check(lib.rr_cliquer_from_counts(int(query_group), len(groups), groups.ctypes.data, counts.ctypes.data, sizes.ctypes.data,
+                                      int(size_query), mincov, maxclique, greedy, members.ctypes.data, scores.ctypes.data,
+                                      C.byref(n)), "rr_cliquer_from_counts")
+    return members[:n.value].copy(), scores[:n.value].copy()
 
 
 def contraction_ranges(start, end, cols, class_split, ti, tj, kunit):

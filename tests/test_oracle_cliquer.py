@@ -106,3 +106,35 @@ def test_group_score_is_the_scan_score_below_saturation_and_97_90_plus_f1_above(
     assert O.group_score(0, 0, 5, 10, 3, 5) == 0.0                            # 482
     # deep saturation: F1 = 2s / (|Gi| + |Gj|)
     assert O.group_score(400, 400, 400, 2000, 400, 400) == 97.90 + 1.0
+
+
+# ---- the product's host half of Cliquer (rr_cliquer_from_counts) against the oracle, on the oracle's own counts ------
+@pytest.mark.parametrize("name", sorted(cliquer_cases()))
+def test_product_host_half_matches_the_oracle_on_given_counts(name):
+    import repeatresolver_b200 as rr
+    case = cliquer_cases()[name]
+    codes = window_codes(golden_msa(name), case["von"], case["bis"])
+    o = O.Oracle.from_codes(codes)
+    gs = o.gsize()
+    G = 5 * codes.shape[1]
+    groups = np.arange(G, dtype=np.int32)
+    for q, want in case["queries"].items():
+        q = int(q)
+        counts = np.array([o.counts(i, q) for i in range(G)], dtype=np.int32)
+        members, scores = rr.cliquer_from_counts(q, groups, counts, gs, gs[q], case["mincov"], case["maxclique"], case["greedy"])
+        assert list(members[1:]) == want["members"] and members[0] == q
+        assert [float(z).hex() for z in scores[1:]] == want["scores"] and scores[0] == 100.0
+
+
+def test_group_score_host_bitwise_equal_to_oracle():
+    import repeatresolver_b200 as rr
+    rng = np.random.default_rng(9)
+    for _ in range(3000):
+        cov = int(rng.integers(2, 4000))
+        gr1, gr2 = int(rng.integers(1, cov + 1)), int(rng.integers(1, cov + 1))
+        lo, hi = max(1, gr1 + gr2 - cov), min(gr1, gr2)
+        if lo > hi:
+            continue
+        s = int(rng.integers(lo, hi + 1))
+        zi, zj = gr1 + int(rng.integers(0, 40)), gr2 + int(rng.integers(0, 40))
+        assert rr.group_score_host(s, gr1, gr2, cov, zi, zj) == O.group_score(s, gr1, gr2, cov, zi, zj)
