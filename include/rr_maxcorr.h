@@ -157,20 +157,44 @@ int rr_breakcols_from_spans(const int32_t *start, const int32_t *end, int rows, 
                             int32_t *breakcol /*[cols]*/);
 
 /* ---- next scope row: Cliquer, the inner step of Group_Refinement ----------------------
- * RepeatResolver.c:1179-1240: the up to maxclique-1 groups of columns [anfang, ende) that correlate best with group
- * `query_group` (Group_PositiveSignificance 472-488 > greedy, intersection > mincov/4), best first, ties in group
- * order (TheBestUpdater 1156-1176).  members: [maxclique+1], members[0] = query_group, unused slots -1;
- * scores: [maxclique], scores[0] = 100 (1229), unused slots 0; *n_members counts the query group itself.
- * First version: the four intersection counts of every candidate come from the device bitsets (the reference's
- * Schnitt calls, its dominant cost); the scores of the candidates are evaluated on the host, in threads. */
+ * RepeatResolver.c:1179-1240: the up to maxclique-1 groups of columns [anfang, ende) that correlate best with a query
+ * group (Group_PositiveSignificance 472-488 > greedy, intersection > mincov/4), best first, ties in group order
+ * (TheBestUpdater 1156-1176).  Per query: members[maxclique+1], members[0] = the query group, unused slots -1 (the
+ * reference's -1 terminator, 1230); scores[maxclique], scores[0] = 100 (1229), unused slots 0; n_members counts the
+ * query group itself.  Scores are evaluated (finally) with the host libm on exact integer counts, so members and
+ * scores are bit-identical to the reference's.
+ *
+ * rr_cliquer_batch is the product path: all queries of a Group_Refinement pass (the groups with MaxCorrs > cutoff,
+ * 1647-1649) in one call; counts, filter, score bound and score run on the device (csrc/rr_cliquer.cu), the host
+ * re-evaluates and orders the few hits per query that decide its clique.  rr_cliquer is the plain single-query
+ * implementation (device counts of every candidate through rr_pair_counts, every score on the host) the tests hold
+ * it against.  Queries are independent: several GPUs take disjoint slices of the query list. */
+typedef struct rr_cliquer_stats {
+    int64_t pairs;        /* (query, candidate group) pairs tested = Schnitt calls of 1213 */
+    int64_t candidates;   /* pairs above mincov/4 whose score bound exceeds greedy */
+    int64_t hits;         /* candidates whose device score exceeds greedy */
+    int64_t host_evals;   /* scores re-evaluated with the host libm */
+    float kernel_ms;      /* CUDA-event time of the two kernels, summed over launches */
+    int launches;
+    int retries;          /* launches repeated with fewer queries because the candidate list overflowed */
+} rr_cliquer_stats;
+int rr_cliquer_batch(rr_packed *pk, int64_t n_queries, const int32_t *query_groups, int anfang, int ende, int mincov,
+                     int maxclique, double greedy, int32_t *members /*[n_queries][maxclique+1]*/,
+                     double *scores /*[n_queries][maxclique]*/, int32_t *n_members /*[n_queries]*/,
+                     rr_cliquer_stats *stats /* may be NULL */);
 int rr_cliquer(rr_packed *pk, int query_group, int anfang, int ende, int mincov, int maxclique, double greedy,
                int32_t *members, double *scores, int *n_members);
-/* the host half of rr_cliquer on given counts (tests): groups[k] ascending candidate ids, counts[4k..4k+3] =
+/* the host half on given counts (tests): groups[k] ascending candidate ids, counts[4k..4k+3] =
  * {|Gk & Gq|, |Gk & Cq|, |Gq & Ck|, |Ck & Cq|}, sizes[k] = |Gk| */
 int rr_cliquer_from_counts(int query_group, int64_t n, const int32_t *groups, const int32_t *counts, const int32_t *sizes,
                            int size_query, int mincov, int maxclique, double greedy, int32_t *members, double *scores,
                            int *n_members);
 double rr_group_score_host(uint32_t schnitt, uint32_t gr1, uint32_t gr2, uint32_t cov, int32_t sizei, int32_t sizej);
+/* the host half of rr_cliquer_batch on a given hit list (tests): hit_records[n_hits] of 32 bytes each,
+ * {int32 slot (index into query_groups), group, s, gr1, gr2, cov; double device score}, in any order; gsize[n_groups] */
+int rr_cliquer_from_hits(int64_t n_queries, const int32_t *query_groups, int64_t n_hits, const void *hit_records,
+                         const int32_t *gsize, int64_t n_groups, int mincov, int maxclique, double greedy,
+                         int32_t *members, double *scores, int32_t *n_members);
 
 /* the exact contraction ranges of the scan plan (csrc/rr_plan.h), for tests: rows in rank order with spans
  * start[r]..end[r] (inclusive), ranks [0, class_split) and [class_split, rows) each sorted by start; every site is

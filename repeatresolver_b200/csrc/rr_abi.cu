@@ -519,23 +519,20 @@ extern "C" double rr_group_score_host(uint32_t s, uint32_t gr1, uint32_t gr2, ui
     return rr_group_significance(t.data(), s, gr1, gr2, cov, sizei, sizej);
 }
 
-extern "C" int rr_cliquer_from_counts(int query_group, int64_t n, const int32_t *groups, const int32_t *counts,
-                                      const int32_t *sizes, int size_query, int mincov, int maxclique, double greedy,
-                                      int32_t *members, double *scores, int *n_members)
+// scores the candidates with the host libm and applies TheBestUpdater's order (1156-1176): the maxclique-1 largest
+// scores above greedy, equal scores in candidate order (candidates are given in ascending group order)
+static void clq_select(int query_group, int64_t n, const int32_t *groups, const int32_t *counts, const int32_t *sizes,
+                       int size_query, int mincov, int maxclique, double greedy, int threads, int32_t *members,
+                       double *scores, int *n_members)
 {
-    if (n < 0 || maxclique < 1 || !members || !scores || !n_members || (n && (!groups || !counts || !sizes))) {
-        rr_set_error("rr_cliquer_from_counts: bad arguments");
-        return RR_E_ARG;
-    }
     for (int j = 0; j <= maxclique; j++) members[j] = -1;
     for (int j = 0; j < maxclique; j++) scores[j] = 0.0;
     members[0] = query_group;                                            // 1197
     scores[0] = 100.0;                                                   // 1229
-    // scores of the candidates with an intersection above mincov/4 (1215), a few host threads
     std::vector<double> Z((size_t)n, 0.0);
     int32_t max_cov = 0;
     for (int64_t k = 0; k < n; k++) max_cov = std::max(max_cov, counts[4 * k + 3]);
-    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)16, (int64_t)std::thread::hardware_concurrency(), n / 4096 + 1}));
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)threads, (int64_t)std::thread::hardware_concurrency(), n / 4096 + 1}));
     auto work = [&](int t) {
         host_lnfact((size_t)max_cov + 2);   // per-thread table, grown once
         for (int64_t k = n * t / nt; k < n * (t + 1) / nt; k++) {
@@ -550,8 +547,6 @@ extern "C" int rr_cliquer_from_counts(int query_group, int64_t n, const int32_t 
         for (int t = 0; t < nt; t++) th.emplace_back(work, t);
         for (auto &t : th) t.join();
     }
-    // TheBestUpdater (1156-1176) keeps the maxclique-1 largest scores above greedy, equal scores in candidate order:
-    // a stable sort by descending score
     std::vector<int64_t> cand;
     for (int64_t k = 0; k < n; k++)
         if (Z[k] > greedy) cand.push_back(k);                            // 1218
@@ -562,13 +557,28 @@ extern "C" int rr_cliquer_from_counts(int query_group, int64_t n, const int32_t 
         scores[m] = Z[cand[r]];
     }
     *n_members = m;
+}
+
+extern "C" int rr_cliquer_from_counts(int query_group, int64_t n, const int32_t *groups, const int32_t *counts,
+                                      const int32_t *sizes, int size_query, int mincov, int maxclique, double greedy,
+                                      int32_t *members, double *scores, int *n_members)
+{
+    if (n < 0 || maxclique < 1 || mincov < 0 || !members || !scores || !n_members || (n && (!groups || !counts || !sizes))) {
+        rr_set_error("rr_cliquer_from_counts: bad arguments");
+        return RR_E_ARG;
+    }
+    for (int64_t k = 1; k < n; k++)
+        if (groups[k] <= groups[k - 1]) { rr_set_error("rr_cliquer_from_counts: candidate groups must be ascending"); return RR_E_ARG; }
+    clq_select(query_group, n, groups, counts, sizes, size_query, mincov, maxclique, greedy, 16, members, scores, n_members);
     return RR_OK;
 }
 
+// one query, every candidate's counts from rr_pair_counts, every score on the host: the plain second implementation
+// the tests hold rr_cliquer_batch against
 extern "C" int rr_cliquer(rr_packed *pk, int query_group, int anfang, int ende, int mincov, int maxclique, double greedy,
                           int32_t *members, double *scores, int *n_members)
 {
-    if (!pk || maxclique < 1 || !members || !scores || !n_members) { rr_set_error("rr_cliquer: bad arguments"); return RR_E_ARG; }
+    if (!pk || maxclique < 1 || mincov < 0 || !members || !scores || !n_members) { rr_set_error("rr_cliquer: bad arguments"); return RR_E_ARG; }
     if (query_group < 0 || query_group >= 5 * pk->N) { rr_set_error("rr_cliquer: group %d out of range", query_group); return RR_E_ARG; }
     anfang = std::max(anfang, 0);
     ende = std::min(ende, pk->N);
@@ -580,8 +590,219 @@ extern "C" int rr_cliquer(rr_packed *pk, int query_group, int anfang, int ende, 
     }
     int rc = rr_pair_counts(pk, n, gi.data(), gj.data(), cnt.data());
     if (rc) return rc;
-    return rr_cliquer_from_counts(query_group, n, gi.data(), cnt.data(), sz.data(), pk->h_gsize[query_group], mincov, maxclique,
-                                  greedy, members, scores, n_members);
+    clq_select(query_group, n, gi.data(), cnt.data(), sz.data(), pk->h_gsize[query_group], mincov, maxclique, greedy, 16,
+               members, scores, n_members);
+    return RR_OK;
+}
+
+// Cliquer for a batch of query groups (the calls of Group_Refinement, 1647-1649): counts, the 1215 filter, a rigorous
+// score bound and the exact score on the device (rr_cliquer.cu); the host keeps, per query, the hits that can decide
+// the top maxclique-1, re-evaluates them with its own libm and orders them like TheBestUpdater.  A device score
+// differs from the host's by a few ulp (exp, log10), so "can decide" = within 1e-9 relative of the weakest of the
+// top maxclique-1 device scores, or anywhere near the saturation switch at 98 (486), where a last-bit difference
+// selects the other formula.
+// The host half of rr_cliquer_batch for the n queries of one launch: `hits` holds, in no particular order, the listed
+// pairs with their counts and device scores; slot = index into queries.  Per query the hits that can decide the top
+// maxclique-1 are re-evaluated and ordered by clq_select.
+static void clq_finalize(const int32_t *queries, int n, std::vector<rr_clq_rec> &hits, const int32_t *gsize, int mincov,
+                         int maxclique, double greedy, int32_t *members, double *scores, int32_t *n_members, long long *evals_out)
+{
+    const int K = maxclique - 1;
+    std::sort(hits.begin(), hits.end(), [](const rr_clq_rec &a, const rr_clq_rec &b) {
+        return a.slot != b.slot ? a.slot < b.slot : a.group < b.group;
+    });
+    std::vector<int64_t> first((size_t)n + 1, 0);
+    for (const rr_clq_rec &h : hits) first[(size_t)h.slot + 1]++;
+    for (int i = 0; i < n; i++) first[(size_t)i + 1] += first[i];
+    std::atomic<int> next{0};
+    std::atomic<long long> evals{0};
+    auto work = [&]() {
+        std::vector<double> zs;
+        std::vector<int32_t> g, c, sz;
+        for (;;) {
+            const int i = next.fetch_add(1);
+            if (i >= n) return;
+            const rr_clq_rec *h = hits.data() + first[i];
+            const int64_t nh = first[(size_t)i + 1] - first[i];
+            if (nh == 0 || K < 1) continue;
+            double cut = -HUGE_VAL;
+            if (nh > K) {
+                zs.resize((size_t)nh);
+                for (int64_t k = 0; k < nh; k++) zs[k] = h[k].z;
+                std::nth_element(zs.begin(), zs.begin() + (K - 1), zs.end(), std::greater<double>());
+                cut = zs[K - 1] - 1e-9 * std::max(1.0, std::fabs(zs[K - 1]));
+            }
+            g.clear(); c.clear(); sz.clear();
+            for (int64_t k = 0; k < nh; k++) {
+                if (h[k].z < cut && h[k].z < 97.89) continue;
+                g.push_back(h[k].group);
+                c.push_back(h[k].s); c.push_back(h[k].gr1); c.push_back(h[k].gr2); c.push_back(h[k].cov);
+                sz.push_back(gsize[h[k].group]);
+            }
+            int m = 0;
+            clq_select(queries[i], (int64_t)g.size(), g.data(), c.data(), sz.data(), gsize[queries[i]], mincov, maxclique, greedy, 1,
+                       members + i * ((int64_t)maxclique + 1), scores + i * (int64_t)maxclique, &m);
+            n_members[i] = m;
+            evals += (long long)g.size();
+        }
+    };
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)16, (int64_t)std::thread::hardware_concurrency(), (int64_t)n / 8 + 1}));
+    if (nt == 1) work();
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) th.emplace_back(work);
+        for (auto &t : th) t.join();
+    }
+    if (evals_out) *evals_out = evals.load();
+}
+
+static void clq_init_outputs(int64_t nq, const int32_t *queries, int maxclique, int32_t *members, double *scores, int32_t *n_members)
+{
+    for (int64_t i = 0; i < nq; i++) {                                   // the clique of a query without partners
+        int32_t *m = members + i * ((int64_t)maxclique + 1);
+        double *z = scores + i * (int64_t)maxclique;
+        for (int j = 0; j <= maxclique; j++) m[j] = -1;
+        for (int j = 0; j < maxclique; j++) z[j] = 0.0;
+        m[0] = queries[i];
+        z[0] = 100.0;
+        n_members[i] = 1;
+    }
+}
+
+// test hook: clq_finalize on hits given by the caller (layout of rr_clq_rec: six int32 {slot, group, s, gr1, gr2, cov}
+// and the device score as a double)
+extern "C" int rr_cliquer_from_hits(int64_t nq, const int32_t *queries, int64_t n_hits, const void *hit_records,
+                                    const int32_t *gsize, int64_t n_groups, int mincov, int maxclique, double greedy,
+                                    int32_t *members, double *scores, int32_t *n_members)
+{
+    if (nq < 0 || nq > 0x7fffffff || n_hits < 0 || maxclique < 1 || mincov < 0 || !gsize || (n_hits && !hit_records) ||
+        (nq && (!queries || !members || !scores || !n_members))) {
+        rr_set_error("rr_cliquer_from_hits: bad arguments");
+        return RR_E_ARG;
+    }
+    const rr_clq_rec *h = static_cast<const rr_clq_rec *>(hit_records);
+    for (int64_t i = 0; i < nq; i++)
+        if (queries[i] < 0 || queries[i] >= n_groups) { rr_set_error("rr_cliquer_from_hits: query out of range"); return RR_E_ARG; }
+    for (int64_t k = 0; k < n_hits; k++)
+        if (h[k].slot < 0 || h[k].slot >= nq || h[k].group < 0 || h[k].group >= n_groups) {
+            rr_set_error("rr_cliquer_from_hits: hit %lld out of range", (long long)k);
+            return RR_E_ARG;
+        }
+    clq_init_outputs(nq, queries, maxclique, members, scores, n_members);
+    std::vector<rr_clq_rec> hits(h, h + n_hits);
+    clq_finalize(queries, (int)nq, hits, gsize, mincov, maxclique, greedy, members, scores, n_members, nullptr);
+    return RR_OK;
+}
+
+static void clq_release(int32_t *q, unsigned long long *c, rr_clq_rec *a, rr_clq_rec *b, cudaEvent_t e0, cudaEvent_t e1)
+{
+    rr_dev_free(q); rr_dev_free(c); rr_dev_free(a); rr_dev_free(b);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+}
+
+extern "C" int rr_cliquer_batch(rr_packed *pk, int64_t nq, const int32_t *queries, int anfang, int ende, int mincov,
+                                int maxclique, double greedy, int32_t *members, double *scores, int32_t *n_members,
+                                rr_cliquer_stats *stats)
+{
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (!pk || nq < 0 || nq > 0x7fffffff || maxclique < 1 || mincov < 0 || std::isnan(greedy) ||
+        (nq && (!queries || !members || !scores || !n_members))) {
+        rr_set_error("rr_cliquer_batch: bad arguments");
+        return RR_E_ARG;
+    }
+    for (int64_t i = 0; i < nq; i++)
+        if (queries[i] < 0 || queries[i] >= 5 * pk->N) { rr_set_error("rr_cliquer_batch: group %d out of range", queries[i]); return RR_E_ARG; }
+    clq_init_outputs(nq, queries, maxclique, members, scores, n_members);
+    anfang = std::max(anfang, 0);
+    ende = std::min(ende, pk->N);
+    if (nq == 0 || ende <= anfang || maxclique == 1) return RR_OK;
+    const unsigned long long n_cand_groups = 5ull * (unsigned long long)(ende - anfang);
+    if ((ende - anfang + RR_CLQ_SLAB - 1) / RR_CLQ_SLAB > 65535 || rr_cliquer_smem_bytes(pk->W32) > 227u * 1024u) {
+        rr_set_error("rr_cliquer_batch: MSA too large for the kernel's tiling (%d columns, %d rows)", ende - anfang, pk->R);
+        return RR_E_ARG;
+    }
+    RR_CUDA(cudaSetDevice(pk->device));
+    rr_alloc_stream(pk->st);
+
+    unsigned long long cap = 1ull << 24;                                 // entries of 32 bytes per list
+    if (const char *e = getenv("RR_CLIQUER_CAP")) cap = std::max(1ull, strtoull(e, nullptr, 10));   // tests: force the retry path
+    int64_t group_len = std::min<int64_t>(nq, 4096);
+    cap = std::min(cap, (unsigned long long)group_len * n_cand_groups);
+
+    int32_t *d_queries = nullptr;
+    unsigned long long *d_counters = nullptr;
+    rr_clq_rec *d_cand = nullptr, *d_hits = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int rc;
+    if ((rc = dev_alloc(&d_queries, (size_t)nq)) || (rc = dev_alloc(&d_counters, 2)) || (rc = dev_alloc(&d_cand, (size_t)cap)) ||
+        (rc = dev_alloc(&d_hits, (size_t)cap))) {
+        clq_release(d_queries, d_counters, d_cand, d_hits, ev0, ev1);
+        return rc;
+    }
+#define CLQ_CUDA(call)                                                                             \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            rr_set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e__), __FILE__, __LINE__, #call); \
+            clq_release(d_queries, d_counters, d_cand, d_hits, ev0, ev1);                          \
+            return RR_E_CUDA;                                                                      \
+        }                                                                                          \
+    } while (0)
+    CLQ_CUDA(cudaEventCreate(&ev0));
+    CLQ_CUDA(cudaEventCreate(&ev1));
+    CLQ_CUDA(cudaMemcpyAsync(d_queries, queries, sizeof(int32_t) * (size_t)nq, cudaMemcpyHostToDevice, pk->st));
+
+    double thr = greedy - 1e-9 * std::max(1.0, std::fabs(greedy));
+    thr = std::min(thr, 97.89);                                          // both sides of the switch at 98 reach the host
+    std::vector<rr_clq_rec> hits;
+    int64_t q0 = 0;
+    while (q0 < nq) {
+        const int n = (int)std::min<int64_t>(group_len, nq - q0);
+        unsigned long long cnt[2] = {0, 0};
+        float ms = 0.f;
+        CLQ_CUDA(cudaMemsetAsync(d_counters, 0, 2 * sizeof(unsigned long long), pk->st));
+        CLQ_CUDA(cudaEventRecord(ev0, pk->st));
+        CLQ_CUDA(rr_launch_cliquer(pk->d_bits, pk->d_covbits, pk->d_gsize, pk->d_lnfact, pk->W32, d_queries + q0, n, anfang, ende,
+                                   mincov / 4, greedy, thr, d_cand, d_hits, cap, d_counters, pk->n_sm, pk->st));
+        CLQ_CUDA(cudaEventRecord(ev1, pk->st));
+        CLQ_CUDA(cudaMemcpyAsync(cnt, d_counters, sizeof(cnt), cudaMemcpyDeviceToHost, pk->st));
+        CLQ_CUDA(cudaStreamSynchronize(pk->st));
+        CLQ_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        if (stats) { stats->kernel_ms += ms; stats->launches += 2; }
+        if (cnt[0] > cap) {                                              // candidate list overflowed: fewer queries per launch
+            if (stats) stats->retries++;
+            if (n > 1) { group_len = std::max(1, n / 2); continue; }
+            cap = n_cand_groups;                                         // one query lists at most every candidate group
+            rr_dev_free(d_cand); rr_dev_free(d_hits);
+            d_cand = d_hits = nullptr;
+            if ((rc = dev_alloc(&d_cand, (size_t)cap)) || (rc = dev_alloc(&d_hits, (size_t)cap))) {
+                clq_release(d_queries, d_counters, d_cand, d_hits, ev0, ev1);
+                return rc;
+            }
+            continue;
+        }
+        hits.resize((size_t)cnt[1]);
+        if (cnt[1]) {
+            CLQ_CUDA(cudaMemcpyAsync(hits.data(), d_hits, sizeof(rr_clq_rec) * (size_t)cnt[1], cudaMemcpyDeviceToHost, pk->st));
+            CLQ_CUDA(cudaStreamSynchronize(pk->st));
+        }
+        if (stats) {
+            stats->pairs += (int64_t)n * (int64_t)n_cand_groups;
+            for (int i = 0; i < n; i++)                                  // 1210: a query group is not its own candidate
+                if (queries[q0 + i] / 5 >= anfang && queries[q0 + i] / 5 < ende) stats->pairs--;
+            stats->candidates += (int64_t)cnt[0];
+            stats->hits += (int64_t)cnt[1];
+        }
+        long long evals = 0;
+        clq_finalize(queries + q0, n, hits, pk->h_gsize.data(), mincov, maxclique, greedy, members + q0 * ((int64_t)maxclique + 1),
+                     scores + q0 * (int64_t)maxclique, n_members + q0, &evals);
+        if (stats) stats->host_evals += evals;
+        q0 += n;
+    }
+#undef CLQ_CUDA
+    clq_release(d_queries, d_counters, d_cand, d_hits, ev0, ev1);
+    return RR_OK;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -1,0 +1,182 @@
+// rr_cliquer.cu -- Cliquer, the inner step of Group_Refinement (/root/reference/RepeatResolver.c:1179-1240), for a
+// batch of query groups on the device bitsets of the packed MSA.
+//
+// The reference calls Cliquer once for every group whose MaxCorrs value is above the cutoff (1647-1649, 1723-1725);
+// each call walks all 5 * (ende - anfang) candidate groups with one Schnitt (1213) and, where that intersection is
+// above mincov/4 (1215), three more plus the hypergeometric score (Group_PositiveSignificance 472-488).  Here:
+//
+//   rr_k_cliquer_counts   one block = (batch of CLQ_QB queries, slab of CLQ_SLAB candidate sites).  The queries'
+//                         group and coverage bitsets sit in shared memory; a warp takes one candidate site, streams
+//                         its six bitsets (5 groups + coverage) 32 words at a time and accumulates, per query, the
+//                         twelve AND+POPC counts of the site (5 x |Gk & Gq|, 5 x |Gk & Cq|, |Gq & Ck|, |Ck & Cq|).
+//                         Integer work on HBM-resident bitsets: blocks of one slab are adjacent in launch order
+//                         (blockIdx.x = batch), so a slab is read from HBM once and then served from L2 to every
+//                         batch; two exact skips cut the words touched: 32-word chunks in which no query of the
+//                         batch covers a read, and chunks in which the candidate site covers none (rows are in
+//                         span order, so both are long runs).  Pairs that pass 1215 and whose rigorous score bound
+//                         (rr_score.h) can exceed `greedy` are appended to a candidate list.
+//   rr_k_cliquer_score    one thread per listed candidate: the exact score in IEEE double, GSL's operation order
+//                         (rr_group_significance); candidates above greedy (less a 1e-9 margin) go to the hit list.
+//
+// The host (rr_cliquer_batch in rr_abi.cu) sorts the hits per query, re-evaluates the few that decide the top
+// maxclique-1 with the host libm (the same finalisation as the scan's RR_FLAG_HOST_FINALIZE) and applies
+// TheBestUpdater's order (1156-1176).
+#include "rr_kernels.h"
+#include "rr_score.h"
+
+constexpr int CLQ_QB = RR_CLQ_QB;       // queries per block
+constexpr int CLQ_SLAB = RR_CLQ_SLAB;   // candidate sites per block
+constexpr int CLQ_WARPS = 8;
+constexpr unsigned CLQ_FULL = 0xffffffffu;
+
+static_assert(CLQ_QB * 5 <= 32, "one lane per (query, group of the site) in the tail of the site loop");
+static_assert(sizeof(rr_clq_rec) == 32, "record layout is shared with the host");
+
+__device__ __forceinline__ void clq_append(rr_clq_rec *list, unsigned long long cap, unsigned long long *counter,
+                                           const rr_clq_rec &r)
+{
+    const unsigned long long idx = atomicAdd(counter, 1ull);   // keeps counting past cap: the host sees the overflow
+    if (idx < cap) list[idx] = r;
+}
+
+__global__ void __launch_bounds__(CLQ_WARPS * 32, 2)
+rr_k_cliquer_counts(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ covbits, int W32,
+                    const int32_t *__restrict__ queries, int nq, int anfang, int ende, int min_s, double greedy,
+                    const double *__restrict__ lnf, rr_clq_rec *__restrict__ cand, unsigned long long cap,
+                    unsigned long long *__restrict__ counter)
+{
+    extern __shared__ uint32_t clq_smem[];
+    const int nchunks = (W32 + 31) >> 5, W32p = nchunks << 5;
+    uint32_t *qg = clq_smem;                          // [CLQ_QB][W32p] query group bitsets, zero padded
+    uint32_t *qc = qg + (size_t)CLQ_QB * W32p;        // [CLQ_QB][W32p] coverage of the queries' sites
+    uint32_t *qmask = qc + (size_t)CLQ_QB * W32p;     // [nchunks] bit q: query q covers a read of this chunk
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot0 = blockIdx.x * CLQ_QB;
+
+    for (int idx = threadIdx.x; idx < CLQ_QB * W32p; idx += CLQ_WARPS * 32) {
+        const int q = idx / W32p, w = idx - q * W32p;
+        uint32_t y = 0u, cy = 0u;
+        if (slot0 + q < nq && w < W32) {
+            const int g = queries[slot0 + q];
+            y = bits[(size_t)g * W32 + w];
+            cy = covbits[(size_t)(g / 5) * W32 + w];
+        }
+        qg[idx] = y;
+        qc[idx] = cy;
+    }
+    __syncthreads();
+    for (int c = warp; c < nchunks; c += CLQ_WARPS) {
+        unsigned m = 0u;
+#pragma unroll
+        for (int q = 0; q < CLQ_QB; q++)
+            if (__ballot_sync(CLQ_FULL, qc[q * W32p + c * 32 + lane] != 0u)) m |= 1u << q;
+        if (lane == 0) qmask[c] = m;
+    }
+    __syncthreads();
+
+    // my (query, group of the candidate site) in the tail of the site loop
+    const int my_q = lane / 5, my_k = lane - my_q * 5;
+    const bool my_valid = lane < CLQ_QB * 5 && slot0 + my_q < nq;
+    const int my_query = my_valid ? queries[slot0 + my_q] : -1;
+
+    const int site_end = min(ende, anfang + ((int)blockIdx.y + 1) * CLQ_SLAB);
+    for (int ii = anfang + (int)blockIdx.y * CLQ_SLAB + warp; ii < site_end; ii += CLQ_WARPS) {
+        unsigned s[CLQ_QB][5], g1[CLQ_QB][5], g2[CLQ_QB], cv[CLQ_QB];
+#pragma unroll
+        for (int q = 0; q < CLQ_QB; q++) {
+            g2[q] = cv[q] = 0u;
+#pragma unroll
+            for (int k = 0; k < 5; k++) s[q][k] = g1[q][k] = 0u;
+        }
+        const uint32_t *cb = covbits + (size_t)ii * W32;
+        const uint32_t *gb = bits + (size_t)ii * 5 * W32;
+        for (int c = 0; c < nchunks; c++) {
+            const unsigned m = qmask[c];
+            if (m == 0u) continue;                                   // no query of the batch covers a read here
+            const int w = c * 32 + lane;
+            const uint32_t cx = w < W32 ? __ldg(cb + w) : 0u;
+            if (__ballot_sync(CLQ_FULL, cx != 0u) == 0u) continue;   // nor does the candidate site
+            uint32_t x[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) x[k] = w < W32 ? __ldg(gb + (size_t)k * W32 + w) : 0u;
+#pragma unroll
+            for (int q = 0; q < CLQ_QB; q++) {
+                if (!((m >> q) & 1u)) continue;                      // warp-uniform
+                const uint32_t y = qg[q * W32p + w], cy = qc[q * W32p + w];
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+                    s[q][k] += __popc(x[k] & y);
+                    g1[q][k] += __popc(x[k] & cy);
+                }
+                g2[q] += __popc(y & cx);
+                cv[q] += __popc(cx & cy);
+            }
+        }
+        // warp totals (redux.sync), only as far as they are needed: every group of the site lies inside its coverage,
+        // so |Gk & Gq| <= |Ck & Gq| and a site with |Ck & Gq| <= mincov/4 has no group that passes 1215
+        int ms = 0, mg1 = 0, mg2 = 0, mcv = 0;
+#pragma unroll
+        for (int q = 0; q < CLQ_QB; q++) {
+            const int t2 = (int)__reduce_add_sync(CLQ_FULL, g2[q]);
+            if (t2 <= min_s) continue;                               // warp-uniform
+            const int tc = (int)__reduce_add_sync(CLQ_FULL, cv[q]);
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const int ts = (int)__reduce_add_sync(CLQ_FULL, s[q][k]);
+                if (ts <= min_s) continue;                           // warp-uniform
+                const int t1 = (int)__reduce_add_sync(CLQ_FULL, g1[q][k]);
+                if (lane == q * 5 + k) { ms = ts; mg1 = t1; mg2 = t2; mcv = tc; }
+            }
+        }
+        const int group = ii * 5 + my_k;
+        if (my_valid && ms > min_s && group != my_query) {           // 1210, 1215
+            // Z <= bound; a bound above 98 proves nothing (the raw score is replaced by 97.90 + F1 there, 486)
+            const double bound = rr_bound_effective(rr_score_upper_bound(lnf, (unsigned)ms, (unsigned)mg1, (unsigned)mg2, (unsigned)mcv));
+            if (bound > greedy) {
+                rr_clq_rec r;
+                r.slot = slot0 + my_q; r.group = group; r.s = ms; r.gr1 = mg1; r.gr2 = mg2; r.cov = mcv; r.z = 0.0;
+                clq_append(cand, cap, counter, r);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+rr_k_cliquer_score(const rr_clq_rec *__restrict__ cand, unsigned long long cap, const unsigned long long *__restrict__ counter,
+                   const int32_t *__restrict__ queries, const int32_t *__restrict__ gsize, const double *__restrict__ lnf,
+                   double threshold, rr_clq_rec *__restrict__ hits, unsigned long long *__restrict__ hit_counter)
+{
+    const unsigned long long n = min(*counter, cap);
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n;
+         t += (unsigned long long)gridDim.x * blockDim.x) {
+        rr_clq_rec r = cand[t];
+        // Group1 = the candidate, Group2 = the query (1217): gr1 = |Gk & Cq|, gr2 = |Gq & Ck|
+        r.z = rr_group_significance(lnf, (unsigned)r.s, (unsigned)r.gr1, (unsigned)r.gr2, (unsigned)r.cov, gsize[r.group],
+                                    gsize[queries[r.slot]]);
+        if (r.z > threshold) clq_append(hits, cap, hit_counter, r);
+    }
+}
+
+size_t rr_cliquer_smem_bytes(int W32)
+{
+    const size_t nchunks = ((size_t)W32 + 31) / 32;
+    return (2 * (size_t)CLQ_QB * nchunks * 32 + nchunks) * sizeof(uint32_t);
+}
+
+cudaError_t rr_launch_cliquer(const uint32_t *bits, const uint32_t *covbits, const int32_t *gsize, const double *lnf,
+                              int W32, const int32_t *queries, int nq, int anfang, int ende, int min_s, double greedy,
+                              double threshold, rr_clq_rec *cand, rr_clq_rec *hits, unsigned long long cap,
+                              unsigned long long *counters /* [2]: candidates, hits */, int n_sm, cudaStream_t st)
+{
+    if (nq <= 0 || ende <= anfang) return cudaSuccess;
+    const size_t smem = rr_cliquer_smem_bytes(W32);
+    cudaError_t e = cudaFuncSetAttribute(rr_k_cliquer_counts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)((nq + CLQ_QB - 1) / CLQ_QB), (unsigned)((ende - anfang + CLQ_SLAB - 1) / CLQ_SLAB));
+    rr_k_cliquer_counts<<<grid, CLQ_WARPS * 32, smem, st>>>(bits, covbits, W32, queries, nq, anfang, ende, min_s, greedy, lnf,
+                                                            cand, cap, counters);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    rr_k_cliquer_score<<<n_sm * 8, 128, 0, st>>>(cand, cap, counters, queries, gsize, lnf, threshold, hits, counters + 1);
+    rr_count_launch(2);
+    return cudaGetLastError();
+}

@@ -28,6 +28,19 @@ cudaError_t rr_launch_general_break(const uint32_t *covbits, int W32, int N, int
 cudaError_t rr_launch_pack_int8(const uint8_t *cells, const int32_t *perm, int R, int N, int codes, int8_t *xb,
                                 int64_t Kp, int fp4, cudaStream_t st);
 
+// Cliquer (rr_cliquer.cu): one listed (query slot, candidate group) pair with its four counts and, once scored, Z
+#define RR_CLQ_QB 4      // queries per block of rr_k_cliquer_counts
+#define RR_CLQ_SLAB 256  // candidate sites per block
+struct rr_clq_rec {
+    int32_t slot, group, s, gr1, gr2, cov;
+    double z;
+};
+size_t rr_cliquer_smem_bytes(int W32);
+cudaError_t rr_launch_cliquer(const uint32_t *bits, const uint32_t *covbits, const int32_t *gsize, const double *lnf,
+                              int W32, const int32_t *queries, int nq, int anfang, int ende, int min_s, double greedy,
+                              double threshold, rr_clq_rec *cand, rr_clq_rec *hits, unsigned long long cap,
+                              unsigned long long *counters, int n_sm, cudaStream_t st);
+
 struct rr_best_t;
 cudaError_t rr_launch_init_best(rr_best_t *best, int64_t n, cudaStream_t st);
 cudaError_t rr_launch_raise_best(rr_best_t *best, const double *thr, int64_t n, cudaStream_t st);

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 from . import _lib
-from ._lib import ScanOpts, ScanStats, lib
+from ._lib import CliquerStats, ScanOpts, ScanStats, lib
 
 VARIANTS = {"auto": 0, "bitset": 1, "umma": 2, "umma_f4": 3, "umma_mxf4": 4}
 VARIANT_NAMES = {v: k for k, v in VARIANTS.items()}
@@ -139,13 +139,28 @@ class Packed:
         _check(lib.rr_scan_set_thresholds_device(self._h, C.c_void_p(device_ptr)), "rr_scan_set_thresholds_device")
 
     def cliquer(self, query_group, mincov=30, maxclique=30, greedy=3.0, anfang=0, ende=None):
-        """Cliquer (RepeatResolver.c:1179-1240) for one query group: (members incl. the query, scores)"""
+        """Cliquer (RepeatResolver.c:1179-1240) for one query group, plain path (rr_cliquer): (members incl. the
+        query, scores with scores[0] = 100)"""
         members = np.full(maxclique + 1, -1, dtype=np.int32)
         scores = np.zeros(maxclique, dtype=np.float64)
         n = C.c_int(0)
         _check(lib.rr_cliquer(self._h, int(query_group), anfang, 2 ** 30 if ende is None else ende, mincov, maxclique, greedy,
                               members.ctypes.data, scores.ctypes.data, C.byref(n)), "rr_cliquer")
         return members[:n.value].copy(), scores[:n.value].copy()
+
+    def cliquer_batch(self, query_groups, mincov=30, maxclique=30, greedy=3.0, anfang=0, ende=None):
+        """Cliquer for all query groups of a Group_Refinement pass (1647-1649) on the device (rr_cliquer_batch):
+        (members [nq][maxclique+1] in the reference's -1 terminated layout, scores [nq][maxclique], n_members [nq],
+        stats dict)"""
+        q = np.ascontiguousarray(query_groups, dtype=np.int32).ravel()
+        members = np.full((len(q), maxclique + 1), -1, dtype=np.int32)
+        scores = np.zeros((len(q), maxclique), dtype=np.float64)
+        n = np.zeros(len(q), dtype=np.int32)
+        st = CliquerStats()
+        _check(lib.rr_cliquer_batch(self._h, len(q), q.ctypes.data, anfang, 2 ** 30 if ende is None else ende, mincov, maxclique,
+                                    greedy, members.ctypes.data, scores.ctypes.data, n.ctypes.data, C.byref(st)),
+               "rr_cliquer_batch")
+        return members, scores, n, st.as_dict()
 
     def pair_counts(self, gi, gj):
         gi = np.ascontiguousarray(gi, dtype=np.int32)
@@ -214,6 +229,24 @@ def MaxCorrelation(msa_path, c=30, p=1, variant="auto", flags=FLAG_HOST_FINALIZE
     return out, st
 
 
+def Cliquer(packed, anfang, ende, mincov, maxclique, greedy, a):
+    """RepeatResolver.c:1179-1240 with the reference's argument order: the clique of group `a` among the groups of
+    columns [anfang, ende) as the reference's int[maxclique+1] (Clique[0] = a, best partner first, -1 after the last)."""
+    members, _, _, _ = packed.cliquer_batch([a], mincov, maxclique, greedy, anfang, ende)
+    return members[0]
+
+
+def Group_Refinement_Cliques(packed, MaxCorrs, cutoff, anfang, ende, mincov, maxclique, greedy):
+    """The Cliquer calls of Group_Refinement (RepeatResolver.c:1638-1650) in one device batch: for every group i with
+    MaxCorrs[i] > cutoff its clique and Sizes[i] (1650: members before the first entry <= 0).  Returns
+    (groups [nq], Cliques [nq][maxclique+1], Sizes [nq], scores [nq][maxclique], stats)."""
+    M = np.asarray(MaxCorrs, dtype=np.float64)
+    groups = np.flatnonzero(M > cutoff).astype(np.int32)
+    members, scores, _, st = packed.cliquer_batch(groups, mincov, maxclique, greedy, anfang, ende)
+    sizes = np.array([int(np.argmax(row <= 0)) for row in members], dtype=np.int32)     # while(Cliques[i][Sizes[i]]>0)
+    return groups, members, sizes, scores, st
+
+
 def launch_count():
     return int(lib.rr_launch_count())
 
@@ -254,6 +287,24 @@ def cliquer_from_counts(query_group, groups, counts, sizes, size_query, mincov=3
                                       int(size_query), mincov, maxclique, greedy, members.ctypes.data, scores.ctypes.data,
                                       C.byref(n)), "rr_cliquer_from_counts")
     return members[:n.value].copy(), scores[:n.value].copy()
+
+
+HIT_DTYPE = np.dtype([("slot", "<i4"), ("group", "<i4"), ("s", "<i4"), ("gr1", "<i4"), ("gr2", "<i4"), ("cov", "<i4"),
+                      ("z", "<f8")])
+
+
+def cliquer_from_hits(query_groups, hits, gsize, mincov=30, maxclique=30, greedy=3.0):
+    """the host half of rr_cliquer_batch on a given hit list (test hook; hits: array of HIT_DTYPE)"""
+    q = np.ascontiguousarray(query_groups, dtype=np.int32)
+    hits = np.ascontiguousarray(hits, dtype=HIT_DTYPE)
+    gsize = np.ascontiguousarray(gsize, dtype=np.int32)
+    members = np.full((len(q), maxclique + 1), -1, dtype=np.int32)
+    scores = np.zeros((len(q), maxclique), dtype=np.float64)
+    n = np.zeros(len(q), dtype=np.int32)
+    _check(lib.rr_cliquer_from_hits(len(q), q.ctypes.data, len(hits), hits.ctypes.data, gsize.ctypes.data, len(gsize), mincov,
+                                    maxclique, greedy, members.ctypes.data, scores.ctypes.data, n.ctypes.data),
+           "rr_cliquer_from_hits")
+    return members, scores, n
 
 
 def contraction_ranges(start, end, cols, class_split, ti, tj, kunit):

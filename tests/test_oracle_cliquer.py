@@ -138,3 +138,82 @@ def test_group_score_host_bitwise_equal_to_oracle():
         s = int(rng.integers(lo, hi + 1))
         zi, zj = gr1 + int(rng.integers(0, 40)), gr2 + int(rng.integers(0, 40))
         assert rr.group_score_host(s, gr1, gr2, cov, zi, zj) == O.group_score(s, gr1, gr2, cov, zi, zj)
+
+
+# ---- the host half of the device batch path (rr_cliquer_from_hits): the device stage is emulated with the oracle -----
+def emulated_hits(o, queries, mincov, greedy, rng, noise=2e-13):
+    """what rr_k_cliquer_counts + rr_k_cliquer_score leave behind: every pair above mincov/4 whose (device) score
+    exceeds greedy less a margin, in arbitrary order; the device score is the oracle's, off by a few ulp"""
+    import repeatresolver_b200 as rr
+    gs = o.gsize()
+    hits = []
+    thr = min(greedy - 1e-9 * max(1.0, abs(greedy)), 97.89)
+    for slot, q in enumerate(queries):
+        for i in range(len(gs)):
+            if i == q:
+                continue
+            c = o.counts(i, q)
+            if c[0] <= mincov // 4:
+                continue
+            z = O.group_score(c[0], c[1], c[2], c[3], gs[i], gs[q]) * (1.0 + noise * float(rng.uniform(-1, 1)))
+            if z > thr:
+                hits.append((slot, i, c[0], c[1], c[2], c[3], z))
+    hits = np.array(hits, dtype=rr.HIT_DTYPE)
+    rng.shuffle(hits)
+    return hits
+
+
+@pytest.mark.parametrize("name", sorted(cliquer_cases()))
+def test_batch_host_half_on_emulated_device_hits(name):
+    import repeatresolver_b200 as rr
+    case = cliquer_cases()[name]
+    codes = window_codes(golden_msa(name), case["von"], case["bis"])
+    o = O.Oracle.from_codes(codes)
+    queries = [int(q) for q in case["queries"]]
+    hits = emulated_hits(o, queries, case["mincov"], case["greedy"], np.random.default_rng(3))
+    members, scores, n = rr.cliquer_from_hits(queries, hits, o.gsize(), case["mincov"], case["maxclique"], case["greedy"])
+    for k, q in enumerate(queries):
+        want = case["queries"][str(q)]
+        assert n[k] == want["n"] and members[k, 0] == q and scores[k, 0] == 100.0
+        assert list(members[k, 1:n[k]]) == want["members"] and (members[k, n[k]:] == -1).all()
+        assert [float(z).hex() for z in scores[k, 1:n[k]]] == want["scores"] and (scores[k, n[k]:] == 0).all()
+    # a smaller clique than the number of hits: the cut at the weakest of the top maxclique-1 device scores
+    for maxclique in (2, 3, 5):
+        members, scores, n = rr.cliquer_from_hits(queries, hits, o.gsize(), case["mincov"], maxclique, case["greedy"])
+        for k, q in enumerate(queries):
+            m0, b0 = o.cliquer(q, case["mincov"], maxclique, case["greedy"])
+            assert list(members[k, :n[k]]) == list(m0) and np.array_equal(scores[k, :n[k]], b0)
+
+
+def test_batch_host_half_keeps_group_order_among_equal_scores():
+    """duplicated columns give exactly equal scores: TheBestUpdater keeps the earlier group (1156-1176), also where the
+    tie straddles the end of the clique and the device scores of the tied pairs differ in the last bits"""
+    import repeatresolver_b200 as rr
+    rng = np.random.default_rng(11)
+    R, base = 120, 12
+    cols = rng.integers(0, 2, size=(R, base)).astype(np.uint8)
+    cols[:, 1] = cols[:, 0]                       # strongly correlated sites ...
+    flip = rng.random(R) < 0.1
+    cols[flip, 1] ^= 1
+    codes = np.concatenate([cols, cols, cols[:, :4], cols], axis=1)      # ... several times over
+    o = O.Oracle.from_codes(codes)
+    G = 5 * codes.shape[1]
+    queries = [0, 1, 5, 5 * base + 1, G - 5]
+    hits = emulated_hits(o, queries, 8, 1.0, rng, noise=4e-13)
+    for maxclique in (2, 3, 4, 6, 30):
+        members, scores, n = rr.cliquer_from_hits(queries, hits, o.gsize(), 8, maxclique, 1.0)
+        ties = 0
+        for k, q in enumerate(queries):
+            m0, b0 = o.cliquer(q, 8, maxclique, 1.0)
+            assert list(members[k, :n[k]]) == list(m0) and np.array_equal(scores[k, :n[k]], b0), (maxclique, q)
+            ties += int((np.diff(b0[1:]) == 0).sum())
+        assert ties > 0 or maxclique == 2
+
+
+def test_batch_host_half_rejects_bad_hits():
+    import repeatresolver_b200 as rr
+    bad = np.array([(3, 1, 5, 5, 5, 9, 4.0)], dtype=rr.HIT_DTYPE)       # slot 3 of 1 query
+    with pytest.raises(rr.RRError):
+        rr.cliquer_from_hits([0], bad, np.full(10, 5, dtype=np.int32))
+    with pytest.raises(rr.RRError):
+        rr.cliquer_from_hits([10], bad[:0], np.full(10, 5, dtype=np.int32))

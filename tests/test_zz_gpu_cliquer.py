@@ -1,0 +1,127 @@
+"""GPU parity tests (-m gpu) for SURVEY.md section 8f row 2: Cliquer (/root/reference/RepeatResolver.c:1179-1240),
+called through the C ABI (rr_cliquer_batch = device path, rr_cliquer = plain path), against
+  * the committed output of the UNMODIFIED RepeatResolver.c (tests/golden/cliquer.json), bit for bit;
+  * the oracle's restatement on a flanked MSA deep enough for several 32-word chunks per bitset (the kernel's two
+    exact skips), with a query count that is not a multiple of the batch, sub-ranges [anfang, ende), small cliques,
+    and the list-overflow retry forced through RR_CLIQUER_CAP.
+Bar: members identical, scores identical as doubles (integer counts on the device, final scores with the host libm).
+The file sorts last on purpose: a first failure here must not hide the scan's parity tests under `-x`."""
+import os
+
+import numpy as np
+import pytest
+
+import repeatresolver_b200 as rr
+from conftest import golden_msa
+import oracle_lib as O
+from test_oracle_cliquer import cliquer_cases, window_codes
+
+pytestmark = pytest.mark.gpu
+
+
+def check(members, scores, n, k, oracle_members, oracle_scores):
+    assert n[k] == len(oracle_members), (k, n[k], len(oracle_members))
+    assert list(members[k, :n[k]]) == list(oracle_members), k
+    assert (members[k, n[k]:] == -1).all()
+    assert [float(z).hex() for z in scores[k, :n[k]]] == [float(z).hex() for z in oracle_scores], k
+    assert (scores[k, n[k]:] == 0).all()
+
+
+@pytest.mark.parametrize("name", sorted(cliquer_cases()))
+def test_cliquer_golden(name):
+    case = cliquer_cases()[name]
+    codes = window_codes(golden_msa(name), case["von"], case["bis"])
+    pk = rr.Packed(rr.MSA.from_cells(codes, codes=True), 0)
+    queries = [int(q) for q in case["queries"]]
+    members, scores, n, st = pk.cliquer_batch(queries, case["mincov"], case["maxclique"], case["greedy"])
+    assert st["launches"] >= 2 and st["retries"] == 0 and st["hits"] <= st["candidates"] <= st["pairs"]
+    for k, q in enumerate(queries):
+        want = case["queries"][str(q)]
+        check(members, scores, n, k, [q] + want["members"], [100.0] + [float.fromhex(s) for s in want["scores"]])
+        m1, z1 = pk.cliquer(q, case["mincov"], case["maxclique"], case["greedy"])      # the plain path
+        assert list(m1) == [q] + want["members"] and [float(z).hex() for z in z1[1:]] == want["scores"]
+        assert list(rr.Cliquer(pk, 0, codes.shape[1], case["mincov"], case["maxclique"], case["greedy"], q)[:n[k]]) == list(m1)
+    pk.close()
+
+
+@pytest.fixture(scope="module")
+def deep():
+    g = rr.MsaGen(type="Tree", copies=80, coverage=40, repeat_len=1500, diff=0.03, seed=5, flank=500, min_overlap=100)
+    codes = g.codes()
+    assert codes.shape[0] > 3072                                   # > 3 chunks of 32 words per bitset
+    o = O.Oracle.from_codes(codes)
+    gs = o.gsize()
+    cand = np.flatnonzero((gs > 30) & (gs < codes.shape[0] // 3))
+    queries = [int(q) for q in cand[::len(cand) // 61][:61]] + [0, 5 * codes.shape[1] - 1]      # 63 queries, 4 per block
+    pk = rr.Packed(rr.MSA.from_cells(codes, codes=True), 0)
+    yield codes, o, pk, queries
+    pk.close()
+
+
+def test_cliquer_batch_deep_msa_against_oracle(deep):
+    codes, o, pk, queries = deep
+    members, scores, n, st = pk.cliquer_batch(queries, 30, 30, 3.0)
+    sizes = set()
+    for k, q in enumerate(queries):
+        m0, z0 = o.cliquer(q, 30, 30, 3.0)
+        check(members, scores, n, k, m0, z0)
+        sizes.add(len(m0))
+    assert 1 in sizes and 30 in sizes and len(sizes) > 5
+    inside = len(queries)                                           # every query group is itself a candidate column
+    assert st["pairs"] == len(queries) * 5 * codes.shape[1] - inside
+    assert 0 < st["hits"] <= st["candidates"] < st["pairs"] and st["host_evals"] <= st["hits"]
+    print(f"cliquer_batch deep: R={codes.shape[0]} N={codes.shape[1]} queries={len(queries)} {st}")
+    # the plain path on a few of them
+    for q in queries[2:40:9]:
+        m0, z0 = o.cliquer(q, 30, 30, 3.0)
+        m1, z1 = pk.cliquer(q, 30, 30, 3.0)
+        assert list(m1) == list(m0) and np.array_equal(z1, z0)
+
+
+@pytest.mark.parametrize("anfang,ende,maxclique,greedy,mincov", [(1000, 4000, 6, 3.0, 30), (37, 38, 30, 0.5, 8),
+                                                                 (6000, 10 ** 6, 2, 10.0, 30), (300, 300, 5, 3.0, 30),
+                                                                 (0, 2500, 1, 3.0, 30)])
+def test_cliquer_batch_subranges_and_small_cliques(deep, anfang, ende, maxclique, greedy, mincov):
+    codes, o, pk, queries = deep
+    qs = queries[:21]
+    members, scores, n, st = pk.cliquer_batch(qs, mincov, maxclique, greedy, anfang, ende)
+    for k, q in enumerate(qs):
+        m0, z0 = o.cliquer(q, mincov, maxclique, greedy, anfang, min(ende, codes.shape[1]))
+        check(members, scores, n, k, m0, z0)
+
+
+def test_cliquer_batch_list_overflow_retries(deep):
+    codes, o, pk, queries = deep
+    want = pk.cliquer_batch(queries[:13], 30, 30, 3.0)
+    os.environ["RR_CLIQUER_CAP"] = "700"
+    try:
+        got = pk.cliquer_batch(queries[:13], 30, 30, 3.0)
+    finally:
+        del os.environ["RR_CLIQUER_CAP"]
+    assert got[3]["retries"] > 0 and want[3]["retries"] == 0
+    for a, b in zip(want[:3], got[:3]):
+        assert np.array_equal(a, b)
+
+
+def test_group_refinement_cliques_mirror(deep):
+    codes, o, pk, queries = deep
+    M = np.zeros(5 * codes.shape[1])
+    M[queries[:9]] = np.linspace(5, 50, 9)
+    groups, cliques, sizes, scores, st = rr.Group_Refinement_Cliques(pk, M, 10.0, 0, codes.shape[1], 30, 30, 3.0)
+    assert list(groups) == sorted(q for q in queries[:9] if M[q] > 10.0)
+    for k, q in enumerate(groups):
+        m0, z0 = o.cliquer(int(q), 30, 30, 3.0)
+        assert list(cliques[k, :len(m0)]) == list(m0) and cliques[k, len(m0)] == -1
+        assert sizes[k] == (len(m0) if q > 0 else 0)               # 1650 counts entries > 0 from Clique[0]
+
+
+def test_cliquer_argument_errors(deep):
+    codes, o, pk, queries = deep
+    with pytest.raises(rr.RRError):
+        pk.cliquer_batch([5 * codes.shape[1]], 30, 30, 3.0)
+    with pytest.raises(rr.RRError):
+        pk.cliquer_batch([0], -1, 30, 3.0)
+    with pytest.raises(rr.RRError):
+        pk.cliquer_batch([0], 30, 0, 3.0)
+    members, scores, n, st = pk.cliquer_batch([], 30, 30, 3.0)
+    assert members.shape == (0, 31) and st["launches"] == 0

@@ -1,0 +1,51 @@
+"""Timing probe for rr_cliquer_batch: a generated MSA, the queries a Group_Refinement pass
+would issue (minor groups of a plausible size), device time of the two kernels and wall time of the whole call.
+Usage: python tools/probe_cliquer.py [copies] [repeat_len] [n_queries] [out.json]
+The figures it prints: candidate pairs per second (one pair = one Schnitt of RepeatResolver.c:1213) and the bytes of
+bitsets one launch has to stream at least once (6 bitsets per candidate site), i.e. the HBM floor of the count kernel."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import repeatresolver_b200 as rr  # noqa: E402
+
+
+def main():
+    copies = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+    repeat_len = int(sys.argv[2]) if len(sys.argv) > 2 else 6000
+    nq = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
+    out = sys.argv[4] if len(sys.argv) > 4 else None
+    t = time.time()
+    g = rr.MsaGen(type="Tree", copies=copies, coverage=40, repeat_len=repeat_len, diff=0.01, seed=1002, flank=1000)
+    codes = g.codes()
+    t_gen = time.time() - t
+    pk = rr.Packed(rr.MSA.from_cells(codes, codes=True), 0)
+    gs, _ = pk.sizes()
+    cand = np.flatnonzero((gs > 30) & (gs < codes.shape[0] // 3))
+    queries = cand[::max(1, len(cand) // nq)][:nq].astype(np.int32)
+    res = {"rows": int(codes.shape[0]), "cols": int(codes.shape[1]), "queries": int(len(queries)), "gen_s": round(t_gen, 2)}
+    for rep in range(3):
+        t = time.time()
+        members, scores, n, st = pk.cliquer_batch(queries, 30, 30, 3.0)
+        wall = time.time() - t
+        res[f"run{rep}"] = dict(st, wall_ms=round(wall * 1e3, 2), mean_clique=float(n.mean()))
+    st = res["run2"]
+    w32 = 4 * ((codes.shape[0] + 127) // 128)
+    res["pairs_per_s_kernel"] = st["pairs"] / (st["kernel_ms"] * 1e-3)
+    res["pairs_per_s_call"] = st["pairs"] / (st["wall_ms"] * 1e-3)
+    res["bitset_bytes_one_pass"] = int(6 * codes.shape[1] * w32 * 4)
+    res["us_per_query_kernel"] = st["kernel_ms"] * 1e3 / len(queries)
+    line = json.dumps(res)
+    print(line)
+    if out:
+        with open(out, "w") as f:
+            f.write(line + "\n")
+    pk.close()
+
+
+if __name__ == "__main__":
+    main()
