@@ -163,8 +163,158 @@ def count_pairs_host(codes, mincov):
     return int((nrow * np.maximum(0, pref[np.maximum(brk, lo)] - pref[lo])).sum())
 
 
+def cliquer_queries(np, pk, R, nq):
+    """the queries a Group_Refinement pass issues are the groups with MaxCorrs > cutoff (RepeatResolver.c:1647): minor
+    groups of a plausible size; here every len/nq-th group with 30 < size < R/3"""
+    gs, _ = pk.sizes()
+    cand = np.flatnonzero((gs > 30) & (gs < R // 3))
+    return cand[::max(1, len(cand) // nq)][:nq].astype(np.int32)
+
+
+def cliquer_cpu_sample(np, codes, queries, seconds_target):
+    """The oracle's Cliquer (oracle/maxcorr_oracle.c, pinned against the unmodified RepeatResolver.c) on the box's host
+    cores, on a bounded sample of the same queries: one query per task, all cores."""
+    import oracle_lib as O
+    from concurrent.futures import ThreadPoolExecutor
+    cores = os.cpu_count() or 1
+    o = O.Oracle.from_codes(codes)
+    t0 = time.perf_counter()
+    o.cliquer(int(queries[0]), MINCOV, 30, 3.0)
+    one = max(time.perf_counter() - t0, 1e-4)
+    n = int(max(cores, min(len(queries), seconds_target * cores / one)))
+    sample = [int(q) for q in queries[np.linspace(0, len(queries) - 1, n).astype(np.int64)]]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        sizes = list(ex.map(lambda q: len(o.cliquer(q, MINCOV, 30, 3.0)[0]), sample))
+    dt = time.perf_counter() - t0
+    pairs = len(sample) * (5 * codes.shape[1] - 1)
+    return {"value": pairs / dt, "unit": "candidate pairs/s", "cores": cores, "kind": "port",
+            "sample": f"{len(sample)} of the {len(queries)} queries, all candidate groups, -c {MINCOV}, maxclique 30, greedy 3.0",
+            "seconds": dt, "mean_clique": sum(sizes) / len(sizes)}
+
+
+def bench_cliquer(args, rr):
+    """--path cliquer: the next row of the scope table.  A step = Cliquer (RepeatResolver.c:1179-1240)
+    for every query group of one Group_Refinement pass against all groups of the MSA.  Unit: candidate pairs/s, one
+    pair = one (query, candidate group) = one Schnitt of line 1213.  Queries are independent, so N GPUs take
+    disjoint slices of the same query list (strong scaling, no collective on the data path)."""
+    import numpy as np
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        g = rr.MsaGen(**WORKLOADS[args.workload], threads=min(32, os.cpu_count() or 8))
+        codes = g.codes()
+        gs = np.stack([(codes == k).sum(0) for k in range(5)], 1).reshape(-1)
+        cand = np.flatnonzero((gs > 30) & (gs < g.rows // 3))
+        queries = cand[::max(1, len(cand) // args.queries)][:args.queries].astype(np.int32)
+        vals = [cliquer_cpu_sample(np, codes, queries, args.cpu_seconds) for _ in range(args.warmup + args.steps)][args.warmup:]
+        v = sum(x["value"] for x in vals) / len(vals)
+        print(json.dumps({"impl": "reference", "metric": "Cliquer candidate pairs/sec (Group_Refinement)", "value": v,
+                          "unit": "candidate pairs/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
+                          "ms_per_step": 1e3 * sum(x["seconds"] for x in vals) / len(vals), "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                          "config": {"workload": args.workload, "path": "cliquer", "rows": g.rows, "cols": g.cols,
+                                     "queries": int(len(queries))},
+                          "cpu_baseline": {k: (v if k == "value" else vals[0][k]) for k in ("value", "unit", "cores", "kind", "sample")},
+                          "e2e": {"value": v, "unit": "candidate pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return 0
+    if rr.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU path")
+    if world > 1:                                    # torch only as the process-group plumbing of the N > 1 launch
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():                                   # rr_cliquer_batch returns with its stream drained
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    def allred(x, op):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op={"sum": dist.ReduceOp.SUM, "max": dist.ReduceOp.MAX}[op])
+        return float(t.item())
+
+    g, msa = make_msa(rr, args.workload)
+    R, N = g.rows, g.cols
+    pk = rr.Packed(msa, local_rank)
+    queries = cliquer_queries(np, pk, R, args.queries)
+    mine = queries[rank::world]                      # independent queries: a cyclic slice per GPU
+    if world > 1:                                    # + one all-gather of the cliques, so that every rank holds all of them
+        from repeatresolver_b200.dist import cliquer_over_ranks
+
+        def step():
+            return cliquer_over_ranks(pk.cliquer_batch, queries, maxclique=30, mincov=MINCOV, greedy=3.0)
+    else:
+        def step():
+            return pk.cliquer_batch(queries, MINCOV, 30, 3.0)
+    st = None
+    for _ in range(args.warmup):
+        st = step()[3]
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = rr.launch_count()
+    k_ms, t0 = [], time.perf_counter()
+    for _ in range(args.steps):
+        members, scores, n, st = step()              # host query list in, cliques out: the C-ABI call
+        k_ms.append(st["kernel_ms"])
+    call_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    launches = rr.launch_count() - launches0
+    barrier()
+    clocks = sampler.finish()
+    pairs = int(allred(st["pairs"], "sum"))
+    kernel_ms = allred(sum(k_ms) / len(k_ms), "max")
+    call_ms = allred(call_ms, "max")
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    peaks, peak_src = load_peaks()
+    words = (R + 31) // 32
+    achieved = pairs * words / (kernel_ms * 1e-3) / 1e12
+    peak = 148 * 16 * (clocks["sm_mhz"] or 1965) * 1e6 / 1e12 * world
+    w32 = 4 * ((R + 127) // 128)
+    roof = {"bound": "popc-issue", "achieved": achieved, "peak": peak, "unit": "Tpopc32/s", "frac": achieved / peak, "traffic": None,
+            "ops": "32-bit AND+POPC of the Schnitt at RepeatResolver.c:1213, ceil(R/32) per candidate pair (the reference touches "
+                   "every word); words outside the shared coverage of query and candidate site are skipped exactly, so the "
+                   "executed count is lower",
+            "peak_source": "148 SMs x 16 POPC lanes/clk x median SM clock under load",
+            "hbm_floor_bytes_per_step": 6 * N * w32 * 4,
+            "hbm_floor_ms": 6 * N * w32 * 4 / (peaks["hbm_gbs"] * 1e9) * 1e3}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cliquer_cpu_sample(np, g.codes(), queries, args.cpu_seconds)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps({"metric": "Cliquer candidate pairs/sec (Group_Refinement)", "value": pairs / (kernel_ms * 1e-3),
+                      "unit": "candidate pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                      "dtype": "u32 bitset counts, f64 score", "data": "synthetic",
+                      "config": {"workload": args.workload, "path": "cliquer", "rows": R, "cols": N, "queries": int(len(queries)),
+                                 "mincov": MINCOV, "maxclique": 30, "greedy": 3.0, "kernel": os.environ.get("RR_CLIQUER_KERNEL", "default"),
+                                 "l2": "candidate bitsets larger than L2 at config 2; smaller workloads are L2-resident"},
+                      "candidates": st["candidates"], "hits": st["hits"], "host_evals": st["host_evals"],
+                      "mean_clique": float(n.mean()) if len(n) else 0.0, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                      "e2e": {"value": pairs / (call_ms * 1e-3), "unit": "candidate pairs/s", "ms_per_step": call_ms,
+                              "h2d_bytes_per_step": int(4 * len(mine)), "d2h_bytes_per_step": int(32 * st["hits"] + 16)},
+                      "gpu_launches": launches}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--path", default="scan", choices=["scan", "cliquer"],
+                    help="scan = the north-star hot path (default); cliquer = the next scope row (SURVEY.md 8f, 2)")
+    ap.add_argument("--queries", type=int, default=1024, help="--path cliquer: query groups per step")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
@@ -181,6 +331,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     import repeatresolver_b200 as rr
+    if args.path == "cliquer":
+        return bench_cliquer(args, rr)
     from repeatresolver_b200.dist import merge_over_ranks, scan_part
 
     if args.impl == "reference":

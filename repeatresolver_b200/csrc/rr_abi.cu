@@ -694,6 +694,7 @@ extern "C" int rr_cliquer_from_hits(int64_t nq, const int32_t *queries, int64_t 
     return RR_OK;
 }
 
+#define RR_CLIQUER_KERNEL_DEFAULT 1
 static void clq_release(int32_t *q, unsigned long long *c, rr_clq_rec *a, rr_clq_rec *b, cudaEvent_t e0, cudaEvent_t e1)
 {
     rr_dev_free(q); rr_dev_free(c); rr_dev_free(a); rr_dev_free(b);
@@ -725,6 +726,8 @@ extern "C" int rr_cliquer_batch(rr_packed *pk, int64_t nq, const int32_t *querie
     RR_CUDA(cudaSetDevice(pk->device));
     rr_alloc_stream(pk->st);
 
+    int kernel = RR_CLIQUER_KERNEL_DEFAULT;
+    if (const char *e = getenv("RR_CLIQUER_KERNEL")) kernel = atoi(e) == 2 ? 2 : 1;   // tests / probes: both count kernels
     unsigned long long cap = 1ull << 24;                                 // entries of 32 bytes per list
     if (const char *e = getenv("RR_CLIQUER_CAP")) cap = std::max(1ull, strtoull(e, nullptr, 10));   // tests: force the retry path
     int64_t group_len = std::min<int64_t>(nq, 4096);
@@ -763,7 +766,7 @@ extern "C" int rr_cliquer_batch(rr_packed *pk, int64_t nq, const int32_t *querie
         float ms = 0.f;
         CLQ_CUDA(cudaMemsetAsync(d_counters, 0, 2 * sizeof(unsigned long long), pk->st));
         CLQ_CUDA(cudaEventRecord(ev0, pk->st));
-        CLQ_CUDA(rr_launch_cliquer(pk->d_bits, pk->d_covbits, pk->d_gsize, pk->d_lnfact, pk->W32, d_queries + q0, n, anfang, ende,
+        CLQ_CUDA(rr_launch_cliquer(kernel, pk->d_bits, pk->d_covbits, pk->d_gsize, pk->d_lnfact, pk->W32, d_queries + q0, n, anfang, ende,
                                    mincov / 4, greedy, thr, d_cand, d_hits, cap, d_counters, pk->n_sm, pk->st));
         CLQ_CUDA(cudaEventRecord(ev1, pk->st));
         CLQ_CUDA(cudaMemcpyAsync(cnt, d_counters, sizeof(cnt), cudaMemcpyDeviceToHost, pk->st));

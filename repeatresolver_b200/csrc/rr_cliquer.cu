@@ -15,6 +15,12 @@
 //                         batch covers a read, and chunks in which the candidate site covers none (rows are in
 //                         span order, so both are long runs).  Pairs that pass 1215 and whose rigorous score bound
 //                         (rr_score.h) can exceed `greedy` are appended to a candidate list.
+//   rr_k_cliquer_counts2  the same block shape with the counts split in two steps (RR_CLQ_QB2 queries per block): the
+//                         stream over the site computes only the five |Gk & Gq| (the groups of a site partition
+//                         its coverage, so their sum is |Gq & Ck|); the few (query, group) pairs above mincov/4
+//                         then get |Gk & Cq| and |Ck & Cq| from a second pass over the site's words, which are still
+//                         in L1.  5 instead of 12 POPC per word and query: the kernel is bound by the POPC pipe
+//                         (16 lanes/clk/SM), not by bytes.
 //   rr_k_cliquer_score    one thread per listed candidate: the exact score in IEEE double, GSL's operation order
 //                         (rr_group_significance); candidates above greedy (less a 1e-9 margin) go to the hit list.
 //
@@ -24,12 +30,13 @@
 #include "rr_kernels.h"
 #include "rr_score.h"
 
-constexpr int CLQ_QB = RR_CLQ_QB;       // queries per block
+constexpr int CLQ_QB = RR_CLQ_QB;       // queries per block, one-step kernel
+constexpr int CLQ_QB2 = RR_CLQ_QB2;     // queries per block, two-step kernel
 constexpr int CLQ_SLAB = RR_CLQ_SLAB;   // candidate sites per block
 constexpr int CLQ_WARPS = 8;
 constexpr unsigned CLQ_FULL = 0xffffffffu;
 
-static_assert(CLQ_QB * 5 <= 32, "one lane per (query, group of the site) in the tail of the site loop");
+static_assert(CLQ_QB * 5 <= 32 && CLQ_QB2 * 5 <= 32, "one lane per (query, group of the site) in the tail of the site loop");
 static_assert(sizeof(rr_clq_rec) == 32, "record layout is shared with the host");
 
 __device__ __forceinline__ void clq_append(rr_clq_rec *list, unsigned long long cap, unsigned long long *counter,
@@ -37,6 +44,37 @@ __device__ __forceinline__ void clq_append(rr_clq_rec *list, unsigned long long 
 {
     const unsigned long long idx = atomicAdd(counter, 1ull);   // keeps counting past cap: the host sees the overflow
     if (idx < cap) list[idx] = r;
+}
+
+// the block's queries into shared memory: group and coverage bitsets, zero padded to whole 32-word chunks, and per chunk
+// the set of queries that cover a read of it
+template <int QB>
+__device__ __forceinline__ void clq_stage_queries(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ covbits,
+                                                  int W32, const int32_t *__restrict__ queries, int nq, int slot0,
+                                                  uint32_t *qg, uint32_t *qc, uint32_t *qmask)
+{
+    const int nchunks = (W32 + 31) >> 5, W32p = nchunks << 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int idx = threadIdx.x; idx < QB * W32p; idx += CLQ_WARPS * 32) {
+        const int q = idx / W32p, w = idx - q * W32p;
+        uint32_t y = 0u, cy = 0u;
+        if (slot0 + q < nq && w < W32) {
+            const int g = queries[slot0 + q];
+            y = bits[(size_t)g * W32 + w];
+            cy = covbits[(size_t)(g / 5) * W32 + w];
+        }
+        qg[idx] = y;
+        qc[idx] = cy;
+    }
+    __syncthreads();
+    for (int c = warp; c < nchunks; c += CLQ_WARPS) {
+        unsigned m = 0u;
+#pragma unroll
+        for (int q = 0; q < QB; q++)
+            if (__ballot_sync(CLQ_FULL, qc[q * W32p + c * 32 + lane] != 0u)) m |= 1u << q;
+        if (lane == 0) qmask[c] = m;
+    }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(CLQ_WARPS * 32, 2)
@@ -52,27 +90,7 @@ rr_k_cliquer_counts(const uint32_t *__restrict__ bits, const uint32_t *__restric
     uint32_t *qmask = qc + (size_t)CLQ_QB * W32p;     // [nchunks] bit q: query q covers a read of this chunk
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot0 = blockIdx.x * CLQ_QB;
-
-    for (int idx = threadIdx.x; idx < CLQ_QB * W32p; idx += CLQ_WARPS * 32) {
-        const int q = idx / W32p, w = idx - q * W32p;
-        uint32_t y = 0u, cy = 0u;
-        if (slot0 + q < nq && w < W32) {
-            const int g = queries[slot0 + q];
-            y = bits[(size_t)g * W32 + w];
-            cy = covbits[(size_t)(g / 5) * W32 + w];
-        }
-        qg[idx] = y;
-        qc[idx] = cy;
-    }
-    __syncthreads();
-    for (int c = warp; c < nchunks; c += CLQ_WARPS) {
-        unsigned m = 0u;
-#pragma unroll
-        for (int q = 0; q < CLQ_QB; q++)
-            if (__ballot_sync(CLQ_FULL, qc[q * W32p + c * 32 + lane] != 0u)) m |= 1u << q;
-        if (lane == 0) qmask[c] = m;
-    }
-    __syncthreads();
+    clq_stage_queries<CLQ_QB>(bits, covbits, W32, queries, nq, slot0, qg, qc, qmask);
 
     // my (query, group of the candidate site) in the tail of the site loop
     const int my_q = lane / 5, my_k = lane - my_q * 5;
@@ -141,6 +159,100 @@ rr_k_cliquer_counts(const uint32_t *__restrict__ bits, const uint32_t *__restric
     }
 }
 
+// two-step counts: see the header comment
+__global__ void __launch_bounds__(CLQ_WARPS * 32, 2)
+rr_k_cliquer_counts2(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ covbits, int W32,
+                     const int32_t *__restrict__ queries, int nq, int anfang, int ende, int min_s, double greedy,
+                     const double *__restrict__ lnf, rr_clq_rec *__restrict__ cand, unsigned long long cap,
+                     unsigned long long *__restrict__ counter)
+{
+    extern __shared__ uint32_t clq_smem[];
+    const int nchunks = (W32 + 31) >> 5, W32p = nchunks << 5;
+    uint32_t *qg = clq_smem;
+    uint32_t *qc = qg + (size_t)CLQ_QB2 * W32p;
+    uint32_t *qmask = qc + (size_t)CLQ_QB2 * W32p;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot0 = blockIdx.x * CLQ_QB2;
+    clq_stage_queries<CLQ_QB2>(bits, covbits, W32, queries, nq, slot0, qg, qc, qmask);
+
+    const int my_q = lane / 5, my_k = lane - my_q * 5;
+    const bool my_valid = lane < CLQ_QB2 * 5 && slot0 + my_q < nq;
+    const int my_query = my_valid ? queries[slot0 + my_q] : -1;
+
+    const int site_end = min(ende, anfang + ((int)blockIdx.y + 1) * CLQ_SLAB);
+    for (int ii = anfang + (int)blockIdx.y * CLQ_SLAB + warp; ii < site_end; ii += CLQ_WARPS) {
+        unsigned s[CLQ_QB2][5];
+#pragma unroll
+        for (int q = 0; q < CLQ_QB2; q++)
+#pragma unroll
+            for (int k = 0; k < 5; k++) s[q][k] = 0u;
+        const uint32_t *cb = covbits + (size_t)ii * W32;
+        const uint32_t *gb = bits + (size_t)ii * 5 * W32;
+        // step 1: |Gk & Gq| for the five groups of the site and every query of the block
+        for (int c = 0; c < nchunks; c++) {
+            const unsigned m = qmask[c];
+            if (m == 0u) continue;
+            const int w = c * 32 + lane;
+            const uint32_t cx = w < W32 ? __ldg(cb + w) : 0u;
+            if (__ballot_sync(CLQ_FULL, cx != 0u) == 0u) continue;
+            uint32_t x[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) x[k] = w < W32 ? __ldg(gb + (size_t)k * W32 + w) : 0u;
+#pragma unroll
+            for (int q = 0; q < CLQ_QB2; q++) {
+                if (!((m >> q) & 1u)) continue;                      // warp-uniform
+                const uint32_t y = qg[q * W32p + w];
+#pragma unroll
+                for (int k = 0; k < 5; k++) s[q][k] += __popc(x[k] & y);
+            }
+        }
+        int ms = 0, mg1 = 0, mg2 = 0, mcv = 0;
+#pragma unroll
+        for (int q = 0; q < CLQ_QB2; q++) {
+            // the five groups of a site are disjoint and their union is its coverage (rr_k_pack_bits): |Gq & Ck| = sum
+            const int t2 = (int)__reduce_add_sync(CLQ_FULL, s[q][0] + s[q][1] + s[q][2] + s[q][3] + s[q][4]);
+            if (t2 <= min_s) continue;                               // warp-uniform: no group of the site passes 1215
+            int ts[5];
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                ts[k] = (int)__reduce_add_sync(CLQ_FULL, s[q][k]);
+                any = any || ts[k] > min_s;
+            }
+            if (!any) continue;                                      // warp-uniform
+            // step 2: |Ck & Cq| and, for the groups that passed, |Gk & Cq|; the site's words are still in L1
+            unsigned cacc = 0u, gacc[5] = {0u, 0u, 0u, 0u, 0u};
+            for (int c = 0; c < nchunks; c++) {
+                if (!((qmask[c] >> q) & 1u)) continue;
+                const int w = c * 32 + lane;
+                const uint32_t cx = w < W32 ? __ldg(cb + w) : 0u;
+                if (__ballot_sync(CLQ_FULL, cx != 0u) == 0u) continue;
+                const uint32_t cy = qc[q * W32p + w];
+                cacc += __popc(cx & cy);
+#pragma unroll
+                for (int k = 0; k < 5; k++)
+                    if (ts[k] > min_s) gacc[k] += __popc((w < W32 ? __ldg(gb + (size_t)k * W32 + w) : 0u) & cy);
+            }
+            const int tc = (int)__reduce_add_sync(CLQ_FULL, cacc);
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                if (ts[k] <= min_s) continue;                        // warp-uniform
+                const int t1 = (int)__reduce_add_sync(CLQ_FULL, gacc[k]);
+                if (lane == q * 5 + k) { ms = ts[k]; mg1 = t1; mg2 = t2; mcv = tc; }
+            }
+        }
+        const int group = ii * 5 + my_k;
+        if (my_valid && ms > min_s && group != my_query) {           // 1210, 1215
+            const double bound = rr_bound_effective(rr_score_upper_bound(lnf, (unsigned)ms, (unsigned)mg1, (unsigned)mg2, (unsigned)mcv));
+            if (bound > greedy) {
+                rr_clq_rec r;
+                r.slot = slot0 + my_q; r.group = group; r.s = ms; r.gr1 = mg1; r.gr2 = mg2; r.cov = mcv; r.z = 0.0;
+                clq_append(cand, cap, counter, r);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128)
 rr_k_cliquer_score(const rr_clq_rec *__restrict__ cand, unsigned long long cap, const unsigned long long *__restrict__ counter,
                    const int32_t *__restrict__ queries, const int32_t *__restrict__ gsize, const double *__restrict__ lnf,
@@ -157,24 +269,33 @@ rr_k_cliquer_score(const rr_clq_rec *__restrict__ cand, unsigned long long cap, 
     }
 }
 
-size_t rr_cliquer_smem_bytes(int W32)
+static size_t clq_smem_bytes(int W32, int qb)
 {
     const size_t nchunks = ((size_t)W32 + 31) / 32;
-    return (2 * (size_t)CLQ_QB * nchunks * 32 + nchunks) * sizeof(uint32_t);
+    return (2 * (size_t)qb * nchunks * 32 + nchunks) * sizeof(uint32_t);
 }
 
-cudaError_t rr_launch_cliquer(const uint32_t *bits, const uint32_t *covbits, const int32_t *gsize, const double *lnf,
+size_t rr_cliquer_smem_bytes(int W32) { return clq_smem_bytes(W32, CLQ_QB2 > CLQ_QB ? CLQ_QB2 : CLQ_QB); }
+
+cudaError_t rr_launch_cliquer(int kernel, const uint32_t *bits, const uint32_t *covbits, const int32_t *gsize, const double *lnf,
                               int W32, const int32_t *queries, int nq, int anfang, int ende, int min_s, double greedy,
                               double threshold, rr_clq_rec *cand, rr_clq_rec *hits, unsigned long long cap,
                               unsigned long long *counters /* [2]: candidates, hits */, int n_sm, cudaStream_t st)
 {
     if (nq <= 0 || ende <= anfang) return cudaSuccess;
-    const size_t smem = rr_cliquer_smem_bytes(W32);
-    cudaError_t e = cudaFuncSetAttribute(rr_k_cliquer_counts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int qb = kernel == 2 ? CLQ_QB2 : CLQ_QB;
+    const size_t smem = clq_smem_bytes(W32, qb);
+    cudaError_t e = kernel == 2 ? cudaFuncSetAttribute(rr_k_cliquer_counts2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                : cudaFuncSetAttribute(rr_k_cliquer_counts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    dim3 grid((unsigned)((nq + CLQ_QB - 1) / CLQ_QB), (unsigned)((ende - anfang + CLQ_SLAB - 1) / CLQ_SLAB));
-    rr_k_cliquer_counts<<<grid, CLQ_WARPS * 32, smem, st>>>(bits, covbits, W32, queries, nq, anfang, ende, min_s, greedy, lnf,
-                                                            cand, cap, counters);
+    // blockIdx.x = batch of queries, blockIdx.y = slab of candidate sites: the batches of one slab are adjacent in launch order
+    dim3 grid((unsigned)((nq + qb - 1) / qb), (unsigned)((ende - anfang + CLQ_SLAB - 1) / CLQ_SLAB));
+    if (kernel == 2)
+        rr_k_cliquer_counts2<<<grid, CLQ_WARPS * 32, smem, st>>>(bits, covbits, W32, queries, nq, anfang, ende, min_s, greedy, lnf,
+                                                                 cand, cap, counters);
+    else
+        rr_k_cliquer_counts<<<grid, CLQ_WARPS * 32, smem, st>>>(bits, covbits, W32, queries, nq, anfang, ende, min_s, greedy, lnf,
+                                                                cand, cap, counters);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     rr_k_cliquer_score<<<n_sm * 8, 128, 0, st>>>(cand, cap, counters, queries, gsize, lnf, threshold, hits, counters + 1);
     rr_count_launch(2);

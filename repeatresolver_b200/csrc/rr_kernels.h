@@ -30,13 +30,14 @@ cudaError_t rr_launch_pack_int8(const uint8_t *cells, const int32_t *perm, int R
 
 // Cliquer (rr_cliquer.cu): one listed (query slot, candidate group) pair with its four counts and, once scored, Z
 #define RR_CLQ_QB 4      // queries per block of rr_k_cliquer_counts
+#define RR_CLQ_QB2 6     // queries per block of rr_k_cliquer_counts2
 #define RR_CLQ_SLAB 256  // candidate sites per block
 struct rr_clq_rec {
     int32_t slot, group, s, gr1, gr2, cov;
     double z;
 };
 size_t rr_cliquer_smem_bytes(int W32);
-cudaError_t rr_launch_cliquer(const uint32_t *bits, const uint32_t *covbits, const int32_t *gsize, const double *lnf,
+cudaError_t rr_launch_cliquer(int kernel /* 1: one-step counts, 2: two-step */, const uint32_t *bits, const uint32_t *covbits, const int32_t *gsize, const double *lnf,
                               int W32, const int32_t *queries, int nq, int anfang, int ende, int min_s, double greedy,
                               double threshold, rr_clq_rec *cand, rr_clq_rec *hits, unsigned long long cap,
                               unsigned long long *counters, int n_sm, cudaStream_t st);

@@ -65,3 +65,34 @@ def scan_part(pk, mincov=30, variant="auto", flags=0):
     st["kernel_ms"] += st0["kernel_ms"]  # both passes
     st["prepare_ms"] += st0["prepare_ms"]
     return st
+
+
+def cliquer_over_ranks(cliquer_batch, query_groups, maxclique=30, **kw):
+    """Cliquer (RepeatResolver.c:1179-1240) for a query list shared by all ranks.  Queries are independent, so the path
+    shards without a data-path collective: rank r takes queries r, r + world, ... (cyclic, so that the significant
+    groups of one region of the MSA spread over the GPUs), runs `cliquer_batch` on them (Packed.cliquer_batch of the
+    rank's own packed copy of the MSA) and one all-gather returns every rank the full result in query order:
+    (members [nq][maxclique+1], scores [nq][maxclique], n_members [nq], this rank's stats)."""
+    import torch
+    import torch.distributed as dist
+    q = np.ascontiguousarray(query_groups, dtype=np.int32).ravel()
+    rank, world = rank_part()
+    members, scores, n, st = cliquer_batch(q[rank::world], maxclique=maxclique, **kw)
+    if world == 1:
+        return members, scores, n, st
+    per = (len(q) + world - 1) // world                     # slices differ by at most one query: pad to the longest
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+
+    def gather(a, fill):
+        pad = np.full((per,) + a.shape[1:], fill, dtype=a.dtype)
+        pad[:len(a)] = a
+        mine = torch.from_numpy(pad).to(dev)
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        out = np.full((len(q),) + a.shape[1:], fill, dtype=a.dtype)
+        for r in range(world):
+            k = len(q[r::world])
+            out[r::world] = parts[r][:k].cpu().numpy()
+        return out
+
+    return gather(members, -1), gather(scores, 0.0), gather(n, 0), st

@@ -57,3 +57,55 @@ def test_merge_single_process_is_identity():
     M = np.array([0.0, 1.5]); A = np.array([-1, 7], dtype=np.int32)
     M2, A2 = merge_over_ranks(M, A)
     assert M2 is M and A2 is A
+
+
+# ---- Cliquer over ranks: queries sliced cyclically, results all-gathered in query order --------------------------------
+def _cliquer_worker(rank, world, port, codes, queries, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle_lib as O
+    from repeatresolver_b200.dist import cliquer_over_ranks
+    o = O.Oracle.from_codes(codes)
+    seen = []
+
+    def batch(qs, mincov, maxclique, greedy):
+        """stands in for Packed.cliquer_batch on a machine without a GPU: same signature and result layout"""
+        seen.extend(int(q) for q in qs)
+        members = np.full((len(qs), maxclique + 1), -1, dtype=np.int32)
+        scores = np.zeros((len(qs), maxclique), dtype=np.float64)
+        n = np.zeros(len(qs), dtype=np.int32)
+        for k, q in enumerate(qs):
+            m, z = o.cliquer(int(q), mincov, maxclique, greedy)
+            members[k, :len(m)], scores[k, :len(z)], n[k] = m, z, len(m)
+        return members, scores, n, {"pairs": len(qs) * 5 * codes.shape[1]}
+
+    members, scores, n, st = cliquer_over_ranks(batch, queries, maxclique=8, mincov=12, greedy=2.0)
+    assert seen == [int(q) for q in queries[rank::world]]
+    np.savez(os.path.join(out_dir, f"clq{rank}.npz"), members=members, scores=scores, n=n)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nq", [(2, 7), (3, 10), (2, 1)])
+def test_cliquer_over_ranks_gloo(world, nq, tmp_path):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    import repeatresolver_b200 as rr
+    g = rr.MsaGen(type="Tree", copies=4, coverage=16, repeat_len=500, diff=0.03, seed=78, flank=300, min_overlap=50)
+    codes = g.codes()
+    o = O.Oracle.from_codes(codes)
+    M0, _, _ = o.scan(12)
+    queries = np.argsort(-M0, kind="stable")[:nq].astype(np.int32)
+    port = 29100 + (os.getpid() % 500) + 7 * world + nq
+    mp.spawn(_cliquer_worker, args=(world, port, codes, queries, str(tmp_path)), nprocs=world, join=True)
+    results = [np.load(tmp_path / f"clq{r}.npz") for r in range(world)]
+    for k, q in enumerate(queries):
+        m, z = o.cliquer(int(q), 12, 8, 2.0)
+        for res in results:                                   # every rank holds the full result, in query order
+            assert res["n"][k] == len(m)
+            assert list(res["members"][k, :len(m)]) == list(m) and (res["members"][k, len(m):] == -1).all()
+            assert np.array_equal(res["scores"][k, :len(z)], z)
+    assert max(int(r["n"].max()) for r in results) > 1

@@ -19,6 +19,18 @@ from test_oracle_cliquer import cliquer_cases, window_codes
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["1", "2"], ids=["one_step_counts", "two_step_counts"])
+def count_kernel(request):
+    """both count kernels of csrc/rr_cliquer.cu (RR_CLIQUER_KERNEL is read at every rr_cliquer_batch call)"""
+    old = os.environ.get("RR_CLIQUER_KERNEL")
+    os.environ["RR_CLIQUER_KERNEL"] = request.param
+    yield request.param
+    if old is None:
+        del os.environ["RR_CLIQUER_KERNEL"]
+    else:
+        os.environ["RR_CLIQUER_KERNEL"] = old
+
+
 def check(members, scores, n, k, oracle_members, oracle_scores):
     assert n[k] == len(oracle_members), (k, n[k], len(oracle_members))
     assert list(members[k, :n[k]]) == list(oracle_members), k
@@ -52,7 +64,7 @@ def deep():
     o = O.Oracle.from_codes(codes)
     gs = o.gsize()
     cand = np.flatnonzero((gs > 30) & (gs < codes.shape[0] // 3))
-    queries = [int(q) for q in cand[::len(cand) // 61][:61]] + [0, 5 * codes.shape[1] - 1]      # 63 queries, 4 per block
+    queries = [int(q) for q in cand[::len(cand) // 61][:61]] + [0, 5 * codes.shape[1] - 1]      # 63 queries: a partial last block with 4 and with 6 per block
     pk = rr.Packed(rr.MSA.from_cells(codes, codes=True), 0)
     yield codes, o, pk, queries
     pk.close()
