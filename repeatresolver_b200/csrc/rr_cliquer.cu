@@ -15,12 +15,15 @@
 //                         batch covers a read, and chunks in which the candidate site covers none (rows are in
 //                         span order, so both are long runs).  Pairs that pass 1215 and whose rigorous score bound
 //                         (rr_score.h) can exceed `greedy` are appended to a candidate list.
-//   rr_k_cliquer_counts2  the same block shape with the counts split in two steps (RR_CLQ_QB2 queries per block): the
-//                         stream over the site computes only the five |Gk & Gq| (the groups of a site partition
-//                         its coverage, so their sum is |Gq & Ck|); the few (query, group) pairs above mincov/4
-//                         then get |Gk & Cq| and |Ck & Cq| from a second pass over the site's words, which are still
-//                         in L1.  5 instead of 12 POPC per word and query: the kernel is bound by the POPC pipe
-//                         (16 lanes/clk/SM), not by bytes.
+//   rr_k_cliquer_counts2  experiment, selectable with RR_CLIQUER_KERNEL=2, same results: the counts split in two steps
+//                         (RR_CLQ_QB2 queries per block).  The stream over the site computes only the five |Gk & Gq|
+//                         (the groups of a site partition its coverage, so their sum is |Gq & Ck|); the (query, group)
+//                         pairs above mincov/4 then get |Gk & Cq| and |Ck & Cq| from a second pass over the site's
+//                         words.  5 instead of 12 POPC per word and query - but measured SLOWER on a B200 (27.6 against
+//                         18.5 ms for 1024 queries on a 4740 x 26594 MSA, profiles/r1_cliquer_ncu_summary.csv): the
+//                         second pass fires for most sites near the query (their major group shares its reads), the
+//                         kernel executes 1.48x the warp instructions and the POPC pipe drops from 62 % to 25 % busy.
+//                         The one-step kernel stays the default.
 //   rr_k_cliquer_score    one thread per listed candidate: the exact score in IEEE double, GSL's operation order
 //                         (rr_group_significance); candidates above greedy (less a 1e-9 margin) go to the hit list.
 //
