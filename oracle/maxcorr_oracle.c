@@ -324,6 +324,78 @@ int rr_oracle_cliquer(const rr_oracle *o, int anfang, int ende, int mincov, int 
     return n;
 }
 
+/* ---- Relative_Vars, /root/reference/RepeatResolver.c:2424-2493 ----------------
+ * Which groups vary inside one part of the current read partition: restated before any GPU path for it exists,
+ * validated against the unmodified RepeatResolver.c behind oracle/ref_relvars_driver.c (tests/test_oracle_relvars.py). */
+
+/* Triple_Schnitt, RepeatResolver.c:150-161 */
+static inline int rr_isect3(const uint64_t *a, const uint64_t *b, const uint64_t *c, int sc)
+{
+    int z, n = 0;
+    for (z = 0; z < sc; z++) n += __builtin_popcountll(a[z] & b[z] & c[z]);
+    return n;
+}
+
+/* Relative_Group_Significance (506-523) on counts, with CumHypGeo_Log (490-504): the two-sided test - the smaller of
+ * the lower tail P[X <= schnitt] and the upper tail P[X >= schnitt] of Hypergeom(pop = cov, successes = gr2, draws =
+ * gr1), as -log10, capped at 99.  schnitt = |G1 & G2 & U|, gr1 = |G1 & U|, gr2 = |G2 & U|, cov = |U|. */
+double rr_oracle_relative_score(unsigned int schnitt, unsigned int gr1, unsigned int gr2, unsigned int cov)
+{
+    double posP, posQ, Z;
+    if (gr1 == 0 || gr2 == 0) return 0.0;                                /* 517 */
+    posP = gsl_cdf_hypergeometric_P(schnitt, gr2, cov - gr2, gr1);       /* 492 */
+    posQ = gsl_cdf_hypergeometric_Q(schnitt - 1, gr2, cov - gr2, gr1);   /* 493: schnitt - 1 wraps for 0, Q = 0 then */
+    if (posP < posQ || schnitt == 0) {                                   /* 495 */
+        Z = -1.0 * log10(posP);
+        if (isinf(Z) || Z > 99) Z = 99.0;
+    } else {
+        Z = -1.0 * log10(posQ);                                          /* 501 */
+        if (isinf(Z) || Z > 99) Z = 99.0;
+    }
+    if (isinf(Z) || Z > 99.0) Z = 99.0;                                  /* 521 */
+    return Z;
+}
+
+/* Relative_Vars, 2424-2493.  unterteilung: [R] part number of every read; maxcorrs: [5N]; vars: [5N+1], receives the
+ * selected groups in ascending order followed by -1; returns their number.
+ *   selected = MaxCorrs > cutoff (2432) and |U & G| >= mingroup (2449)
+ *   kept     = has a partner j >= i + 100 or i >= j + 100 among the selected with score(Gj, Gi, U) > cutoff (2461-2475) */
+int rr_oracle_relative_vars(const rr_oracle *o, const int32_t *unterteilung, int u_no, const double *maxcorrs,
+                            double cutoff, int mingroup, int32_t *vars)
+{
+    const int sc = o->sc, G = 5 * o->N;
+    uint64_t *U = (uint64_t *)calloc((size_t)sc, sizeof(uint64_t));
+    int *sel = (int *)malloc(sizeof(int) * (size_t)(G > 0 ? G : 1));
+    int *gu = (int *)malloc(sizeof(int) * (size_t)(G > 0 ? G : 1));
+    int i, j, count = 0, cov = 0;
+    for (i = 0; i < G; i++) sel[i] = maxcorrs[i] > cutoff ? 1 : 0;                       /* 2430-2434 */
+    for (i = 0; i < o->R; i++)
+        if (unterteilung[i] == u_no) { U[i / 64] |= (uint64_t)1 << (i % 64); cov++; }    /* 2438 */
+    for (i = 0; i < G; i++) {
+        gu[i] = 0;
+        if (sel[i]) {
+            gu[i] = rr_isect(U, o->groups + (size_t)i * sc, sc);
+            if (gu[i] < mingroup) sel[i] = 0;                                           /* 2449 */
+        }
+    }
+    for (i = 0; i < G; i++) {
+        if (!sel[i]) continue;
+        for (j = i + 100; j < G; j++) {                                                 /* 2461 */
+            if (!sel[j]) continue;
+            {   /* Relative_Group_Significance(Groups[j], Groups[i], U_Group): Group1 = j, Group2 = i (2465) */
+                const int s = rr_isect3(o->groups + (size_t)j * sc, o->groups + (size_t)i * sc, U, sc);
+                const double Z = rr_oracle_relative_score((unsigned)s, (unsigned)gu[j], (unsigned)gu[i], (unsigned)cov);
+                if (Z > cutoff) { sel[i] = 2; sel[j] = 2; }                              /* 2467-2471 */
+            }
+        }
+    }
+    for (i = 0; i < G; i++)
+        if (sel[i] == 2) vars[count++] = i;                                             /* 2485 */
+    vars[count] = -1;                                                                   /* 2483 */
+    free(U); free(sel); free(gu);
+    return count;
+}
+
 /* MaxCorrelation.c:516-532 (MaxCorrsRausschreiben) */
 int rr_oracle_write(const char *path, const double *M, int G)
 {

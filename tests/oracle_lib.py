@@ -38,6 +38,12 @@ def lib():
         L.rr_oracle_group_score.argtypes = [C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_int]
         L.rr_oracle_cliquer.restype = C.c_int
         L.rr_oracle_cliquer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        L.rr_oracle_relative_score.restype = C.c_double
+        L.rr_oracle_relative_score.argtypes = [C.c_uint] * 4
+        L.rr_oracle_relative_vars.restype = C.c_int
+        L.rr_oracle_relative_vars.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_void_p]
+        L.gsl_cdf_hypergeometric_P.restype = C.c_double
+        L.gsl_cdf_hypergeometric_P.argtypes = [C.c_uint] * 4
         L.rr_oracle_lnfact.restype = C.c_double
         L.rr_oracle_lnfact.argtypes = [C.c_uint]
         L.gsl_cdf_hypergeometric_Q.restype = C.c_double
@@ -99,6 +105,17 @@ class Oracle:
                                     clique.ctypes.data, best.ctypes.data)
         return clique[:n].copy(), best[:n].copy()
 
+    def relative_vars(self, unterteilung, u_no, maxcorrs, cutoff, mingroup):
+        """RepeatResolver.c:2424-2493: the groups that vary inside part u_no of the read partition (ascending ids)"""
+        u = np.ascontiguousarray(unterteilung, dtype=np.int32)
+        m = np.ascontiguousarray(maxcorrs, dtype=np.float64)
+        assert len(u) == self.R and len(m) == 5 * self.N
+        out = np.zeros(5 * self.N + 1, dtype=np.int32)
+        n = lib().rr_oracle_relative_vars(self._h, u.ctypes.data, int(u_no), m.ctypes.data, float(cutoff), int(mingroup),
+                                          out.ctypes.data)
+        assert out[n] == -1
+        return out[:n].copy()
+
     def close(self):
         if self._h:
             lib().rr_oracle_free(self._h)
@@ -117,6 +134,15 @@ def score(s, gr1, gr2, cov, sizei=0, sizej=0):
 
 def group_score(s, gr1, gr2, cov, sizei=0, sizej=0):
     return lib().rr_oracle_group_score(s, gr1, gr2, cov, sizei, sizej)
+
+
+def relative_score(s, gr1, gr2, cov):
+    """Relative_Group_Significance on counts (RepeatResolver.c:506-523, 490-504)"""
+    return lib().rr_oracle_relative_score(s, gr1, gr2, cov)
+
+
+def hyper_P(k, n1, n2, t):
+    return lib().gsl_cdf_hypergeometric_P(k, n1, n2, t)
 
 
 def hyper_Q(k, n1, n2, t):
