@@ -196,6 +196,22 @@ int rr_cliquer_from_hits(int64_t n_queries, const int32_t *query_groups, int64_t
                          const int32_t *gsize, int64_t n_groups, int mincov, int maxclique, double greedy,
                          int32_t *members, double *scores, int32_t *n_members);
 
+/* ---- scope row 8f-3: Relative_Vars (RepeatResolver.c:2424-2493), first version ------------------------------------
+ * Which groups vary inside part u_no of a read partition: groups with MaxCorrs > cutoff that hold at least mingroup
+ * reads of the part and have a partner at least 100 group ids away whose two-sided hypergeometric score restricted
+ * to the part's reads (Relative_Group_Significance 506-523, CumHypGeo_Log 490-504) exceeds cutoff.
+ * unterteilung: [rows of msa] part number of every read; maxcorrs: [5 * cols]; vars: [5 * cols + 1], receives the
+ * ascending group ids followed by -1 (the reference's terminator, 2483).  mingroup >= 1 and cutoff >= 0 are required.
+ * This version packs the part's rows as an MSA of their own on `device` (rr_pack), takes the triple intersections
+ * from rr_pair_counts and scores on the host with the same libm as the reference (bit-identical). */
+int rr_relative_vars(const rr_msa *msa, int device, const int32_t *unterteilung, int u_no, const double *maxcorrs,
+                     double cutoff, int mingroup, int32_t *vars, int *n_vars, int64_t *pairs_tested /* may be NULL */);
+/* the host half on given counts (tests): gsize_u[g] = |G_g & U|, cov_u = |U|; with S == NULL only the selection
+ * (sel_out, n_sel) is returned, else S[n_sel][n_sel] holds |G_sel[a] & G_sel[b] & U| */
+int rr_relative_vars_from_counts(int64_t n_groups, const double *maxcorrs, const int32_t *gsize_u, int cov_u, double cutoff,
+                                 int mingroup, const int32_t *S, int32_t *sel_out, int *n_sel, int32_t *vars, int *n_vars);
+double rr_relative_score_host(uint32_t schnitt, uint32_t gr1, uint32_t gr2, uint32_t cov);
+
 /* the exact contraction ranges of the scan plan (csrc/rr_plan.h), for tests: rows in rank order with spans
  * start[r]..end[r] (inclusive), ranks [0, class_split) and [class_split, rows) each sorted by start; every site is
  * taken as a row site, ti / tj sites per row / column block, kunit rows per contraction unit.  A row of class c can

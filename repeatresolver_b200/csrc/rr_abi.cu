@@ -809,6 +809,151 @@ extern "C" int rr_cliquer_batch(rr_packed *pk, int64_t nq, const int32_t *querie
 }
 
 // ---------------------------------------------------------------------------------------
+// Relative_Vars (RepeatResolver.c:2424-2493), first version: the rows of the part are packed as an MSA of their own, so
+// that the triple intersections |Gi & Gj & U| are plain pair intersections of that MSA (rr_pair_counts) and |Gi & U|
+// its group sizes; selection, the two-sided score (rr_relative_significance) and the marks are host code.
+// ---------------------------------------------------------------------------------------
+extern "C" double rr_relative_score_host(uint32_t s, uint32_t gr1, uint32_t gr2, uint32_t cov)
+{
+    std::vector<double> &t = host_lnfact((size_t)cov + 2);
+    return rr_relative_significance(t.data(), s, gr1, gr2, cov);
+}
+
+// 2430-2452: groups with MaxCorrs > cutoff of which at least mingroup reads lie in the part
+static void relvars_select(int64_t n_groups, const double *maxcorrs, const int32_t *gsize_u, double cutoff, int mingroup,
+                           std::vector<int32_t> &sel)
+{
+    sel.clear();
+    for (int64_t g = 0; g < n_groups; g++)
+        if (maxcorrs[g] > cutoff && gsize_u[g] >= mingroup) sel.push_back((int32_t)g);
+}
+
+// first selected index whose group id is at least sel[a] + 100 (2461)
+static size_t relvars_first_partner(const std::vector<int32_t> &sel, size_t a)
+{
+    return (size_t)(std::lower_bound(sel.begin() + a, sel.end(), sel[a] + 100) - sel.begin());
+}
+
+// 2461-2475 for the listed pairs: pa/pb index into sel, S = |G_pa & G_pb & U|
+static void relvars_mark(const std::vector<int32_t> &sel, int64_t n, const int32_t *pa, const int32_t *pb, const int32_t *S,
+                         int64_t S_stride, const int32_t *gsize_u, int cov_u, double cutoff, std::vector<uint8_t> &mark)
+{
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)16, (int64_t)std::thread::hardware_concurrency(), n / 2048 + 1}));
+    std::vector<std::vector<uint8_t>> local(nt, std::vector<uint8_t>(nt > 1 ? sel.size() : 0, 0));
+    auto work = [&](int t) {
+        std::vector<uint8_t> &m = nt > 1 ? local[t] : mark;
+        host_lnfact((size_t)cov_u + 2);
+        for (int64_t k = n * t / nt; k < n * (t + 1) / nt; k++) {
+            const int a = pa[k], b = pb[k];
+            if (m[a] && m[b]) continue;
+            // Relative_Group_Significance(Groups[j], Groups[i], U_Group): Group1 = the later group (2465)
+            const double Z = rr_relative_score_host((uint32_t)S[k * S_stride], (uint32_t)gsize_u[sel[b]], (uint32_t)gsize_u[sel[a]],
+                                                    (uint32_t)cov_u);
+            if (Z > cutoff) m[a] = m[b] = 1;
+        }
+    };
+    if (nt == 1) { work(0); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back(work, t);
+    for (auto &t : th) t.join();
+    for (int t = 0; t < nt; t++)
+        for (size_t k = 0; k < sel.size(); k++) mark[k] |= local[t][k];
+}
+
+// test hook: the host half on given counts.  Call once with S = NULL for the selection (sel_out[n_sel], ascending group
+// ids), then with S[n_sel][n_sel] = |G_sel[a] & G_sel[b] & U| for the result.
+extern "C" int rr_relative_vars_from_counts(int64_t n_groups, const double *maxcorrs, const int32_t *gsize_u, int cov_u,
+                                            double cutoff, int mingroup, const int32_t *S, int32_t *sel_out, int *n_sel,
+                                            int32_t *vars, int *n_vars)
+{
+    if (n_groups < 0 || n_groups > 0x7fffffff || cov_u < 0 || mingroup < 1 || !(cutoff >= 0.0) || !n_sel ||
+        (n_groups && (!maxcorrs || !gsize_u))) {
+        rr_set_error("rr_relative_vars_from_counts: bad arguments");
+        return RR_E_ARG;
+    }
+    std::vector<int32_t> sel;
+    relvars_select(n_groups, maxcorrs, gsize_u, cutoff, mingroup, sel);
+    *n_sel = (int)sel.size();
+    if (sel_out) std::copy(sel.begin(), sel.end(), sel_out);
+    if (!S) return RR_OK;
+    if (!vars || !n_vars) { rr_set_error("rr_relative_vars_from_counts: bad arguments"); return RR_E_ARG; }
+    std::vector<int32_t> pa, pb, sv;
+    for (size_t a = 0; a < sel.size(); a++)
+        for (size_t b = relvars_first_partner(sel, a); b < sel.size(); b++) {
+            pa.push_back((int32_t)a); pb.push_back((int32_t)b); sv.push_back(S[a * sel.size() + b]);
+        }
+    std::vector<uint8_t> mark(sel.size(), 0);
+    relvars_mark(sel, (int64_t)pa.size(), pa.data(), pb.data(), sv.data(), 1, gsize_u, cov_u, cutoff, mark);
+    int n = 0;
+    for (size_t a = 0; a < sel.size(); a++)
+        if (mark[a]) vars[n++] = sel[a];
+    vars[n] = -1;                                                        // 2483
+    *n_vars = n;
+    return RR_OK;
+}
+
+extern "C" int rr_relative_vars(const rr_msa *msa, int device, const int32_t *unterteilung, int u_no, const double *maxcorrs,
+                                double cutoff, int mingroup, int32_t *vars, int *n_vars, int64_t *pairs_tested)
+{
+    if (pairs_tested) *pairs_tested = 0;
+    if (!msa || !unterteilung || !maxcorrs || !vars || !n_vars || mingroup < 1 || !(cutoff >= 0.0)) {
+        rr_set_error("rr_relative_vars: bad arguments");
+        return RR_E_ARG;
+    }
+    vars[0] = -1;
+    *n_vars = 0;
+    const int R = msa->rows, N = msa->cols;
+    std::vector<int> rows;
+    for (int r = 0; r < R; r++)
+        if (unterteilung[r] == u_no) rows.push_back(r);                  // 2438
+    const int cov_u = (int)rows.size();
+    if (cov_u < mingroup || N == 0) return RR_OK;                        // no group can hold mingroup reads of the part (2449)
+    // the part's rows as an MSA of their own
+    rr_msa *sub = nullptr;
+    int rc = rr_msa_alloc(cov_u, N, msa->codes, &sub);
+    if (rc) return rc;
+    for (int k = 0; k < cov_u; k++) memcpy(sub->cells + (size_t)k * N, rr_msa_row(msa, rows[k]), (size_t)N);
+    rr_packed *pk = nullptr;
+    rc = rr_pack(sub, device, &pk);
+    rr_msa_free(sub);
+    if (rc) return rc;
+    const int32_t *gsize_u = pk->h_gsize.data();                         // |G & U|
+    std::vector<int32_t> sel;
+    relvars_select((int64_t)5 * N, maxcorrs, gsize_u, cutoff, mingroup, sel);
+    std::vector<uint8_t> mark(sel.size(), 0);
+    constexpr int64_t CHUNK = (int64_t)4 << 20;                          // pairs per rr_pair_counts call
+    std::vector<int32_t> pa, pb, gi, gj, cnt;
+    int64_t tested = 0;
+    auto flush = [&]() -> int {
+        if (pa.empty()) return RR_OK;
+        cnt.resize(4 * pa.size());
+        int e = rr_pair_counts(pk, (int64_t)pa.size(), gi.data(), gj.data(), cnt.data());
+        if (e) return e;
+        relvars_mark(sel, (int64_t)pa.size(), pa.data(), pb.data(), cnt.data(), 4, gsize_u, cov_u, cutoff, mark);
+        tested += (int64_t)pa.size();
+        pa.clear(); pb.clear(); gi.clear(); gj.clear();
+        return RR_OK;
+    };
+    for (size_t a = 0; a < sel.size() && !rc; a++)
+        for (size_t b = relvars_first_partner(sel, a); b < sel.size() && !rc; b++) {
+            if (mark[a] && mark[b]) continue;                            // the pair could only set marks that are set
+            pa.push_back((int32_t)a); pb.push_back((int32_t)b);
+            gi.push_back(sel[b]); gj.push_back(sel[a]);                  // counts[0] = |G_b & G_a| within the part's rows
+            if ((int64_t)pa.size() >= CHUNK) rc = flush();
+        }
+    if (!rc) rc = flush();
+    rr_packed_free(pk);
+    if (rc) return rc;
+    int n = 0;
+    for (size_t a = 0; a < sel.size(); a++)
+        if (mark[a]) vars[n++] = sel[a];
+    vars[n] = -1;
+    *n_vars = n;
+    if (pairs_tested) *pairs_tested = tested;
+    return RR_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // scan
 // ---------------------------------------------------------------------------------------
 template <typename T>

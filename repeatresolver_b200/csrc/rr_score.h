@@ -172,6 +172,79 @@ RR_HD double rr_group_significance(const double *lnf, unsigned int s, unsigned i
     return Z;
 }
 
+/* ---- Relative_Group_Significance (/root/reference/RepeatResolver.c:506-523), the two-sided score of Relative_Vars ----
+ * CumHypGeo_Log (490-504) needs gsl_cdf_hypergeometric_P beside Q.  The two tail series are written out again here
+ * rather than shared with rr_hyper_Q above, so that the code the scan kernels compile is untouched. */
+RR_HD double rr_hyper_lower_tail(const double *lnf, unsigned int k, unsigned int n1, unsigned int n2, unsigned int t)
+{
+    int i = (int)k;
+    double s = rr_hyper_pdf(lnf, (unsigned int)i, n1, n2, t);
+    double P = s;
+    if (s == 0.0) return 0.0; /* every later term is 0*factor = 0 */
+    while (i > 0) {
+        double f1 = RR_DIV((double)i, RR_ADD((double)(n1 - (unsigned int)i), 1.0));
+        double f2 = RR_DIV((double)(n2 + (unsigned int)i - t), RR_ADD((double)(t - (unsigned int)i), 1.0));
+        double relerr;
+        s = RR_MUL(s, RR_MUL(f1, f2));
+        P = RR_ADD(P, s);
+        relerr = RR_DIV(s, P);
+        if (relerr < DBL_EPSILON) break;
+        i--;
+    }
+    return P;
+}
+
+RR_HD double rr_hyper_upper_tail(const double *lnf, unsigned int k, unsigned int n1, unsigned int n2, unsigned int t)
+{
+    unsigned int i = k + 1;
+    double s = rr_hyper_pdf(lnf, i, n1, n2, t);
+    double Q = s;
+    if (s == 0.0) return 0.0;
+    while (i < t) {
+        double f1 = RR_DIV((double)(n1 - i), RR_ADD((double)i, 1.0));
+        double f2 = RR_DIV((double)(t - i), RR_SUB(RR_ADD((double)(n2 + i), 1.0), (double)t));
+        double relerr;
+        s = RR_MUL(s, RR_MUL(f1, f2));
+        Q = RR_ADD(Q, s);
+        relerr = RR_DIV(s, Q);
+        if (relerr < DBL_EPSILON) break;
+        i++;
+    }
+    return Q;
+}
+
+/* gsl_cdf_hypergeometric_P(k, n1, n2, t) */
+RR_HD double rr_hyper_P(const double *lnf, unsigned int k, unsigned int n1, unsigned int n2, unsigned int t)
+{
+    double midpoint;
+    if (k >= n1 || k >= t) return 1.0;
+    midpoint = RR_DIV(RR_MUL((double)t, (double)n1), RR_ADD((double)n1, (double)n2));
+    if ((double)k >= midpoint) return RR_SUB(1.0, rr_hyper_upper_tail(lnf, k, n1, n2, t));
+    return rr_hyper_lower_tail(lnf, k, n1, n2, t);
+}
+
+/* the same Q as rr_hyper_Q, on the two series above (kept separate, see the note) */
+RR_HD double rr_hyper_Q2(const double *lnf, unsigned int k, unsigned int n1, unsigned int n2, unsigned int t)
+{
+    double midpoint;
+    if (k >= n1 || k >= t) return 0.0;
+    midpoint = RR_DIV(RR_MUL((double)t, (double)n1), RR_ADD((double)n1, (double)n2));
+    if ((double)k < midpoint) return RR_SUB(1.0, rr_hyper_lower_tail(lnf, k, n1, n2, t));
+    return rr_hyper_upper_tail(lnf, k, n1, n2, t);
+}
+
+/* Relative_Group_Significance on counts: schnitt = |G1 & G2 & U|, gr1 = |G1 & U|, gr2 = |G2 & U|, cov = |U| */
+RR_HD double rr_relative_significance(const double *lnf, unsigned int s, unsigned int gr1, unsigned int gr2, unsigned int cov)
+{
+    double P, Q, Z;
+    if (gr1 == 0 || gr2 == 0) return 0.0;                                /* 517 */
+    P = rr_hyper_P(lnf, s, gr2, cov - gr2, gr1);                         /* 492 */
+    Q = rr_hyper_Q2(lnf, s - 1u, gr2, cov - gr2, gr1);                   /* 493: s - 1 wraps for 0, Q = 0 then */
+    Z = RR_MUL(-1.0, log10((P < Q || s == 0) ? P : Q));                  /* 495-503 */
+    if (isinf(Z) || Z > 99) Z = 99.0;
+    return Z;
+}
+
 /* ---- pruning bounds (no reference counterpart) -------------------------------------
  * With X ~ Hypergeom(pop = cov, successes = gr2, draws = gr1) the score before the caps
  * is -log10 P[X >= s].  Two rigorous upper bounds:

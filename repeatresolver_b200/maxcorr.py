@@ -247,6 +247,47 @@ def Group_Refinement_Cliques(packed, MaxCorrs, cutoff, anfang, ende, mincov, max
     return groups, members, sizes, scores, st
 
 
+def Relative_Vars(msa, Unterteilung, u_no, MaxCorrs, cutoff, mingroup, device=0):
+    """RepeatResolver.c:2424-2493 with the reference's argument order (first version, rr_relative_vars): the groups that
+    vary inside part u_no of the read partition, ascending ids (the reference's array without its -1 terminator)."""
+    u = np.ascontiguousarray(Unterteilung, dtype=np.int32)
+    M = np.ascontiguousarray(MaxCorrs, dtype=np.float64)
+    assert len(u) == msa.rows and len(M) == 5 * msa.cols
+    out = np.zeros(5 * msa.cols + 1, dtype=np.int32)
+    n, pairs = C.c_int(0), C.c_int64(0)
+    _check(lib.rr_relative_vars(msa._h, device, u.ctypes.data, int(u_no), M.ctypes.data, float(cutoff), int(mingroup),
+                                out.ctypes.data, C.byref(n), C.byref(pairs)), "rr_relative_vars")
+    assert out[n.value] == -1
+    return out[:n.value].copy()
+
+
+def relative_score_host(s, gr1, gr2, cov):
+    """Relative_Group_Significance on counts (RepeatResolver.c:506-523), host libm"""
+    return lib.rr_relative_score_host(s, gr1, gr2, cov)
+
+
+def relative_vars_from_counts(maxcorrs, gsize_u, cov_u, cutoff, mingroup, triple_counts=None):
+    """the host half of rr_relative_vars (test hook).  triple_counts: callable(sel) -> [n_sel][n_sel] int32 of
+    |G_sel[a] & G_sel[b] & U|; without it only the selection is returned."""
+    M = np.ascontiguousarray(maxcorrs, dtype=np.float64)
+    gu = np.ascontiguousarray(gsize_u, dtype=np.int32)
+    sel = np.zeros(len(M), dtype=np.int32)
+    n_sel = C.c_int(0)
+    _check(lib.rr_relative_vars_from_counts(len(M), M.ctypes.data, gu.ctypes.data, int(cov_u), float(cutoff), int(mingroup), None,
+                                            sel.ctypes.data, C.byref(n_sel), None, None), "rr_relative_vars_from_counts")
+    sel = sel[:n_sel.value].copy()
+    if triple_counts is None:
+        return sel
+    S = np.ascontiguousarray(triple_counts(sel), dtype=np.int32)
+    assert S.shape == (len(sel), len(sel))
+    out = np.zeros(len(M) + 1, dtype=np.int32)
+    n = C.c_int(0)
+    _check(lib.rr_relative_vars_from_counts(len(M), M.ctypes.data, gu.ctypes.data, int(cov_u), float(cutoff), int(mingroup),
+                                            S.ctypes.data, None, C.byref(n_sel), out.ctypes.data, C.byref(n)),
+           "rr_relative_vars_from_counts")
+    return out[:n.value].copy()
+
+
 def launch_count():
     return int(lib.rr_launch_count())
 

@@ -103,7 +103,8 @@ def test_relative_score_is_the_smaller_tail():
         z = O.relative_score(s, gr1, gr2, cov)
         P = hypergeom.cdf(s, cov, gr2, gr1)           # P[X <= s]
         Q = hypergeom.sf(s - 1, cov, gr2, gr1)        # P[X >= s]
-        want = -np.log10(P if (P < Q or s == 0) else Q)
+        with np.errstate(divide="ignore"):
+            want = -np.log10(P if (P < Q or s == 0) else Q)
         want = 99.0 if (np.isinf(want) or want > 99) else want
         assert abs(z - want) <= 1e-7 * max(1.0, abs(want)) + 1e-9, (s, gr1, gr2, cov, z, want)
         lower += P < Q
@@ -115,3 +116,56 @@ def test_relative_score_is_the_smaller_tail():
     assert O.relative_score(40, 40, 40, 100) > 20.0
     # schnitt - 1 wraps for schnitt = 0 (493): the upper tail is then 0 and the lower tail is used
     assert O.hyper_Q(0xFFFFFFFF, 40, 60, 40) == 0.0
+
+
+# ---- the product's host half (rr_relative_vars_from_counts, rr_relative_score_host) against the oracle ------------------
+def test_relative_score_host_bitwise_equal_to_oracle():
+    import repeatresolver_b200 as rr
+    rng = np.random.default_rng(19)
+    for _ in range(4000):
+        cov = int(rng.integers(1, 4000))
+        gr1, gr2 = int(rng.integers(0, cov + 1)), int(rng.integers(0, cov + 1))
+        lo, hi = max(0, gr1 + gr2 - cov), min(gr1, gr2)
+        s = int(rng.integers(lo, hi + 1))
+        assert rr.relative_score_host(s, gr1, gr2, cov) == O.relative_score(s, gr1, gr2, cov), (s, gr1, gr2, cov)
+
+
+def group_matrix(codes):
+    """X[r][5*site+k] = read r has symbol k at the site"""
+    R, N = codes.shape
+    X = np.zeros((R, 5 * N), dtype=np.int32)
+    for k in range(5):
+        X[:, k::5] = codes == k
+    return X
+
+
+@pytest.mark.parametrize("name", sorted(relvars_cases()))
+def test_product_host_half_matches_the_reference_on_given_counts(name):
+    import repeatresolver_b200 as rr
+    case = relvars_cases()[name]
+    codes = window_codes(golden_msa(name), case["von"], case["bis"])
+    o = O.Oracle.from_codes(codes)
+    M, _, _ = o.scan(case["mincov"])
+    ut, _ = partition_by_site(codes, M)
+    X = group_matrix(codes)
+    for u_no, want in case["parts"].items():
+        XU = X[ut == int(u_no)]
+        gsize_u = XU.sum(0)
+        sel = rr.relative_vars_from_counts(M, gsize_u, len(XU), case["cutoff"], case["mingroup"])
+        assert (M[sel] > case["cutoff"]).all() and (gsize_u[sel] >= case["mingroup"]).all() and (np.diff(sel) > 0).all()
+        got = rr.relative_vars_from_counts(M, gsize_u, len(XU), case["cutoff"], case["mingroup"],
+                                           lambda s: XU[:, s].T @ XU[:, s])
+        assert list(got) == want["vars"], u_no
+
+
+def test_product_host_half_argument_errors_and_empty_part():
+    import repeatresolver_b200 as rr
+    M = np.full(20, 5.0)
+    gu = np.full(20, 3, dtype=np.int32)
+    with pytest.raises(rr.RRError):
+        rr.relative_vars_from_counts(M, gu, 10, 3.0, 0)                  # mingroup >= 1
+    with pytest.raises(rr.RRError):
+        rr.relative_vars_from_counts(M, gu, 10, -1.0, 2)                 # cutoff >= 0
+    assert len(rr.relative_vars_from_counts(M, gu, 10, 3.0, 4)) == 0     # no group holds mingroup reads of the part
+    assert len(rr.relative_vars_from_counts(M, gu, 10, 5.0, 2)) == 0     # MaxCorrs > cutoff is strict (2432)
+    assert list(rr.relative_vars_from_counts(M, gu, 10, 3.0, 2)) == list(range(20))
