@@ -396,6 +396,92 @@ int rr_oracle_relative_vars(const rr_oracle *o, const int32_t *unterteilung, int
     return count;
 }
 
+/* ---- Kmeans, /root/reference/RepeatResolver.c:2604-2821 ------------------------
+ * Splits part u_no of the read partition by the reads' signatures over the selected groups (the output of
+ * Relative_Vars).  Restated before any GPU path for it exists; validated against the unmodified RepeatResolver.c behind
+ * oracle/ref_kmeans_driver.c (tests/test_oracle_kmeans.py).  The dominant cost is the two read x read similarity
+ * sweeps (GrMatch 163-175: sc*64 minus the Hamming distance of two varzahl-bit signatures). */
+static inline int rr_match(const uint64_t *a, const uint64_t *b, int scv)
+{
+    int z, d = 0;
+    for (z = 0; z < scv; z++) d += __builtin_popcountll(a[z] ^ b[z]);
+    return scv * 64 - d;                                                 /* 174 */
+}
+
+/* unterteilung: [R] in/out; vars: varzahl selected group ids.  Returns the number of non-empty clusters (2790-2797);
+ * the reads of the part get the new part numbers cluster + max(unterteilung) + 1 (2815-2817). */
+int rr_oracle_kmeans(const rr_oracle *o, int32_t *unterteilung, int u_no, const int32_t *vars, int varzahl, int mingroup)
+{
+    const int scv = varzahl / 64 + 1;                                    /* 2626 */
+    int *I = (int *)malloc(sizeof(int) * (size_t)(o->R + 1));
+    int anzahl = 0, i, j, k, l, min, aufgeteilt = 0, max_u = 0;
+    uint64_t *sig, *cen;
+    int *cluster, *size;
+    for (i = 0; i < o->R; i++)
+        if (unterteilung[i] == u_no) I[anzahl++] = i;                    /* 2616-2623 */
+    sig = (uint64_t *)calloc((size_t)(anzahl > 0 ? anzahl : 1) * scv, sizeof(uint64_t));
+    cen = (uint64_t *)calloc((size_t)(anzahl > 0 ? anzahl : 1) * scv, sizeof(uint64_t));
+    cluster = (int *)calloc((size_t)anzahl + 1, sizeof(int));
+    size = (int *)calloc((size_t)anzahl + 1, sizeof(int));
+#define RR_HAS(g, r) ((o->groups[(size_t)(g) * o->sc + (r) / 64] >> ((r) % 64)) & 1u)
+    for (i = 0; i < anzahl; i++)                                         /* 2634-2642: signature of read I[i] */
+        for (j = 0; j < varzahl; j++)
+            if (RR_HAS(vars[j], I[i])) sig[(size_t)i * scv + j / 64] |= (uint64_t)1 << (j % 64);
+    /* 2659-2706: centroid of read i = majority vote (3 of 5) of the five reads kept by the replace-the-smallest
+     * rule below; the slots start as (score 0, read 0) and read i itself takes part */
+    for (i = 0; i < anzahl; i++) {
+        int bs[5] = {0, 0, 0, 0, 0}, bj[5] = {0, 0, 0, 0, 0};
+        for (j = 0; j < anzahl; j++) {
+            const int score = rr_match(sig + (size_t)j * scv, sig + (size_t)i * scv, scv);
+            for (k = 0; k < 5; k++)                                      /* 2670-2685: exchange sort, ascending */
+                for (l = k + 1; l < 5; l++)
+                    if (bs[l] < bs[k]) {
+                        int t = bs[l]; bs[l] = bs[k]; bs[k] = t;
+                        t = bj[l]; bj[l] = bj[k]; bj[k] = t;
+                    }
+            if (score > bs[0]) { bs[0] = score; bj[0] = j; }             /* 2686-2691 */
+        }
+        for (j = 0; j < varzahl; j++) {                                  /* 2697-2705 */
+            int votes = 0;
+            for (k = 0; k < 5; k++) votes += (int)RR_HAS(vars[j], I[bj[k]]);
+            if (votes > 2) cen[(size_t)i * scv + j / 64] |= (uint64_t)1 << (j % 64);
+        }
+    }
+    /* 2709-2725: every read joins the centroid (of another read) that matches it best; first best wins */
+    for (i = 0; i < anzahl; i++) {
+        int best = 0, best_j = 0;
+        for (j = 0; j < anzahl; j++) {
+            const int score = rr_match(cen + (size_t)j * scv, sig + (size_t)i * scv, scv);
+            if (score > best && i != j) { best = score; best_j = j; }
+        }
+        cluster[i] = best_j;
+        size[best_j]++;
+    }
+    /* 2728-2757: clusters of at most `min` reads are dissolved into clusters of at least `min`, in read order, with
+     * the sizes updated as it goes */
+    for (min = 2; min < mingroup; min++)
+        for (i = 0; i < anzahl; i++)
+            if (size[cluster[i]] <= min) {
+                int best = 0, best_j = 0;
+                for (j = 0; j < anzahl; j++)
+                    if (size[j] >= min && cluster[i] != j) {
+                        const int score = rr_match(cen + (size_t)j * scv, sig + (size_t)i * scv, scv);
+                        if (score > best && i != j) { best = score; best_j = j; }
+                    }
+                size[cluster[i]]--;
+                cluster[i] = best_j;
+                size[best_j]++;
+            }
+#undef RR_HAS
+    for (i = 0; i < anzahl; i++)
+        if (size[i] > 0) aufgeteilt++;                                   /* 2792-2794 */
+    for (i = 0; i < o->R; i++)
+        if (unterteilung[i] > max_u) max_u = unterteilung[i];            /* 2814 */
+    for (i = 0; i < anzahl; i++) unterteilung[I[i]] = cluster[i] + max_u + 1;   /* 2815 */
+    free(I); free(sig); free(cen); free(cluster); free(size);
+    return aufgeteilt;
+}
+
 /* MaxCorrelation.c:516-532 (MaxCorrsRausschreiben) */
 int rr_oracle_write(const char *path, const double *M, int G)
 {

@@ -489,24 +489,34 @@ extern "C" int rr_packed_sizes(rr_packed *pk, int32_t *gsize, int32_t *coverage)
     return RR_OK;
 }
 
+// device buffers of one call, returned to the pool on every exit path
+struct dev_scope {
+    std::vector<void *> ptrs;
+    template <typename T>
+    int alloc(T **p, size_t count)
+    {
+        int rc = dev_alloc(p, count);
+        if (!rc) ptrs.push_back(*p);
+        return rc;
+    }
+    ~dev_scope() { for (void *p : ptrs) rr_dev_free(p); }
+};
+
 extern "C" int rr_pair_counts(rr_packed *pk, int64_t n, const int32_t *gi, const int32_t *gj, int32_t *out)
 {
     if (!pk || n < 0 || (n && (!gi || !gj || !out))) return RR_E_ARG;
     if (n == 0) return RR_OK;
     RR_CUDA(cudaSetDevice(pk->device));
     rr_alloc_stream(pk->st);
+    dev_scope scope;
     int32_t *d_i = nullptr, *d_j = nullptr, *d_o = nullptr;
     int rc;
-    if ((rc = dev_alloc(&d_i, (size_t)n)) || (rc = dev_alloc(&d_j, (size_t)n)) || (rc = dev_alloc(&d_o, (size_t)4 * n))) {
-        rr_dev_free(d_i); rr_dev_free(d_j); rr_dev_free(d_o);
-        return rc;
-    }
+    if ((rc = scope.alloc(&d_i, (size_t)n)) || (rc = scope.alloc(&d_j, (size_t)n)) || (rc = scope.alloc(&d_o, (size_t)4 * n))) return rc;
     RR_CUDA(cudaMemcpyAsync(d_i, gi, sizeof(int32_t) * n, cudaMemcpyHostToDevice, pk->st));
     RR_CUDA(cudaMemcpyAsync(d_j, gj, sizeof(int32_t) * n, cudaMemcpyHostToDevice, pk->st));
     RR_CUDA(rr_launch_pair_counts(pk->d_bits, pk->d_covbits, pk->W32, n, d_i, d_j, d_o, pk->st));
     RR_CUDA(cudaMemcpyAsync(out, d_o, sizeof(int32_t) * 4 * n, cudaMemcpyDeviceToHost, pk->st));
     RR_CUDA(cudaStreamSynchronize(pk->st));
-    rr_dev_free(d_i); rr_dev_free(d_j); rr_dev_free(d_o);
     return RR_OK;
 }
 

@@ -42,6 +42,8 @@ def lib():
         L.rr_oracle_relative_score.argtypes = [C.c_uint] * 4
         L.rr_oracle_relative_vars.restype = C.c_int
         L.rr_oracle_relative_vars.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_void_p]
+        L.rr_oracle_kmeans.restype = C.c_int
+        L.rr_oracle_kmeans.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
         L.gsl_cdf_hypergeometric_P.restype = C.c_double
         L.gsl_cdf_hypergeometric_P.argtypes = [C.c_uint] * 4
         L.rr_oracle_lnfact.restype = C.c_double
@@ -115,6 +117,14 @@ class Oracle:
                                           out.ctypes.data)
         assert out[n] == -1
         return out[:n].copy()
+
+    def kmeans(self, unterteilung, u_no, vars_, mingroup):
+        """RepeatResolver.c:2604-2821: (number of non-empty clusters, the partition after the split)"""
+        u = np.array(unterteilung, dtype=np.int32)
+        v = np.ascontiguousarray(vars_, dtype=np.int32)
+        assert len(u) == self.R
+        n = lib().rr_oracle_kmeans(self._h, u.ctypes.data, int(u_no), v.ctypes.data, len(v), int(mingroup))
+        return n, u
 
     def close(self):
         if self._h:
