@@ -217,3 +217,25 @@ def test_batch_host_half_rejects_bad_hits():
         rr.cliquer_from_hits([0], bad, np.full(10, 5, dtype=np.int32))
     with pytest.raises(rr.RRError):
         rr.cliquer_from_hits([10], bad[:0], np.full(10, 5, dtype=np.int32))
+
+
+def test_batch_host_half_is_immune_to_the_saturation_switch_on_the_device():
+    """a device score next to 98 may come from the other formula than the host's (486: raw > 98 -> 97.90 + F1): every hit
+    at or above 97.89 is re-evaluated, so whatever the device reports for those must not change the result"""
+    import repeatresolver_b200 as rr
+    case = cliquer_cases()["saturated"]
+    codes = window_codes(golden_msa("saturated"), case["von"], case["bis"])
+    o = O.Oracle.from_codes(codes)
+    queries = [int(q) for q in case["queries"]]
+    rng = np.random.default_rng(8)
+    hits = emulated_hits(o, queries, case["mincov"], case["greedy"], rng)
+    high = hits["z"] >= 97.89
+    assert high.sum() >= 5
+    for maxclique in (3, case["maxclique"], 40):
+        want = [o.cliquer(q, case["mincov"], maxclique, case["greedy"]) for q in queries]
+        for _ in range(5):
+            h = hits.copy()
+            h["z"][high] = rng.uniform(97.89, 98.9, size=int(high.sum()))     # arbitrary order among the saturated ones
+            members, scores, n = rr.cliquer_from_hits(queries, h, o.gsize(), case["mincov"], maxclique, case["greedy"])
+            for k, (m0, z0) in enumerate(want):
+                assert list(members[k, :n[k]]) == list(m0) and np.array_equal(scores[k, :n[k]], z0), (maxclique, k)
