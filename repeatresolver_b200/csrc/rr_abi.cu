@@ -902,6 +902,51 @@ extern "C" int rr_relative_vars_from_counts(int64_t n_groups, const double *maxc
     return RR_OK;
 }
 
+static int relvars_device_pairs(rr_packed *pk, const std::vector<int32_t> &sel, int cov_u, double cutoff, std::vector<uint8_t> &mark,
+                                int64_t *pairs_tested)
+{
+    const int nsel = (int)sel.size();
+    std::vector<int32_t> first((size_t)nsel);
+    int64_t pairs = 0;
+    for (int a = 0; a < nsel; a++) {
+        first[a] = (int32_t)relvars_first_partner(sel, (size_t)a);
+        pairs += nsel - first[a];
+    }
+    RR_CUDA(cudaSetDevice(pk->device));
+    rr_alloc_stream(pk->st);
+    dev_scope scope;
+    constexpr unsigned UNSURE_CAP = 1u << 20;
+    int32_t *d_sel = nullptr, *d_first = nullptr;
+    unsigned char *d_mark = nullptr;
+    int4 *d_unsure = nullptr;
+    unsigned int *d_count = nullptr, count = 0;
+    int rc;
+    if ((rc = scope.alloc(&d_sel, (size_t)nsel)) || (rc = scope.alloc(&d_first, (size_t)nsel)) || (rc = scope.alloc(&d_mark, (size_t)nsel)) ||
+        (rc = scope.alloc(&d_unsure, (size_t)UNSURE_CAP)) || (rc = scope.alloc(&d_count, 1)))
+        return rc;
+    RR_CUDA(cudaMemcpyAsync(d_sel, sel.data(), sizeof(int32_t) * (size_t)nsel, cudaMemcpyHostToDevice, pk->st));
+    RR_CUDA(cudaMemcpyAsync(d_first, first.data(), sizeof(int32_t) * (size_t)nsel, cudaMemcpyHostToDevice, pk->st));
+    RR_CUDA(cudaMemsetAsync(d_mark, 0, (size_t)nsel, pk->st));
+    RR_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned int), pk->st));
+    RR_CUDA(rr_launch_relvars_pairs(pk->d_bits, pk->W32, d_sel, nsel, d_first, pk->d_gsize, cov_u, pk->d_lnfact, cutoff, d_mark, d_unsure,
+                                    UNSURE_CAP, d_count, pk->st));
+    RR_CUDA(cudaMemcpyAsync(mark.data(), d_mark, (size_t)nsel, cudaMemcpyDeviceToHost, pk->st));
+    RR_CUDA(cudaMemcpyAsync(&count, d_count, sizeof(count), cudaMemcpyDeviceToHost, pk->st));
+    RR_CUDA(cudaStreamSynchronize(pk->st));
+    if (count > UNSURE_CAP) { rr_set_error("rr_relative_vars: %u undecided pairs exceed the list", count); return RR_E_NOMEM; }
+    std::vector<int4> unsure(count);
+    if (count) {
+        RR_CUDA(cudaMemcpyAsync(unsure.data(), d_unsure, sizeof(int4) * count, cudaMemcpyDeviceToHost, pk->st));
+        RR_CUDA(cudaStreamSynchronize(pk->st));
+    }
+    for (const int4 &u : unsure) {
+        const double Z = rr_relative_score_host((uint32_t)u.z, (uint32_t)pk->h_gsize[sel[u.y]], (uint32_t)pk->h_gsize[sel[u.x]], (uint32_t)cov_u);
+        if (Z > cutoff) mark[u.x] = mark[u.y] = 1;
+    }
+    if (pairs_tested) *pairs_tested = pairs;
+    return RR_OK;
+}
+
 extern "C" int rr_relative_vars(const rr_msa *msa, int device, const int32_t *unterteilung, int u_no, const double *maxcorrs,
                                 double cutoff, int mingroup, int32_t *vars, int *n_vars, int64_t *pairs_tested)
 {
@@ -931,6 +976,19 @@ extern "C" int rr_relative_vars(const rr_msa *msa, int device, const int32_t *un
     std::vector<int32_t> sel;
     relvars_select((int64_t)5 * N, maxcorrs, gsize_u, cutoff, mingroup, sel);
     std::vector<uint8_t> mark(sel.size(), 0);
+    if (getenv("RR_RELVARS_KERNEL") && atoi(getenv("RR_RELVARS_KERNEL")) == 1 && !sel.empty()) {
+        // EXPERIMENTAL (rr_relvars.cu, not yet run on a GPU): the all-pairs step in one tiled kernel; pairs it cannot decide
+        // (score within 1e-9 of the cutoff) come back in a list and are scored here with the host libm
+        rc = relvars_device_pairs(pk, sel, cov_u, cutoff, mark, pairs_tested);
+        rr_packed_free(pk);
+        if (rc) return rc;
+        int n = 0;
+        for (size_t a = 0; a < sel.size(); a++)
+            if (mark[a]) vars[n++] = sel[a];
+        vars[n] = -1;
+        *n_vars = n;
+        return RR_OK;
+    }
     constexpr int64_t CHUNK = (int64_t)4 << 20;                          // pairs per rr_pair_counts call
     std::vector<int32_t> pa, pb, gi, gj, cnt;
     int64_t tested = 0;

@@ -42,6 +42,11 @@ cudaError_t rr_launch_cliquer(int kernel /* 1: one-step counts, 2: two-step */, 
                               double threshold, rr_clq_rec *cand, rr_clq_rec *hits, unsigned long long cap,
                               unsigned long long *counters, int n_sm, cudaStream_t st);
 
+// Relative_Vars (rr_relvars.cu, experimental): the all-pairs step on the packed rows of one part
+cudaError_t rr_launch_relvars_pairs(const uint32_t *bits, int W32, const int32_t *sel, int nsel, const int32_t *first_partner,
+                                    const int32_t *gsize_u, int cov_u, const double *lnf, double cutoff, unsigned char *mark,
+                                    int4 *unsure, unsigned int unsure_cap, unsigned int *unsure_count, cudaStream_t st);
+
 struct rr_best_t;
 cudaError_t rr_launch_init_best(rr_best_t *best, int64_t n, cudaStream_t st);
 cudaError_t rr_launch_raise_best(rr_best_t *best, const double *thr, int64_t n, cudaStream_t st);
