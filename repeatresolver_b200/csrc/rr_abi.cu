@@ -737,7 +737,7 @@ extern "C" int rr_cliquer_batch(rr_packed *pk, int64_t nq, const int32_t *querie
     rr_alloc_stream(pk->st);
 
     int kernel = RR_CLIQUER_KERNEL_DEFAULT;
-    if (const char *e = getenv("RR_CLIQUER_KERNEL")) kernel = atoi(e) == 2 ? 2 : 1;   // tests / probes: both count kernels
+    if (const char *e = getenv("RR_CLIQUER_KERNEL")) kernel = atoi(e) == 2 ? 2 : atoi(e) == 3 ? 3 : 1;   // tests / probes: both count kernels
     unsigned long long cap = 1ull << 24;                                 // entries of 32 bytes per list
     if (const char *e = getenv("RR_CLIQUER_CAP")) cap = std::max(1ull, strtoull(e, nullptr, 10));   // tests: force the retry path
     int64_t group_len = std::min<int64_t>(nq, 4096);

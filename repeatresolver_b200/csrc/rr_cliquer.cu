@@ -30,6 +30,7 @@
 // The host (rr_cliquer_batch in rr_abi.cu) sorts the hits per query, re-evaluates the few that decide the top
 // maxclique-1 with the host libm (the same finalisation as the scan's RR_FLAG_HOST_FINALIZE) and applies
 // TheBestUpdater's order (1156-1176).
+#include <algorithm>
 #include "rr_kernels.h"
 #include "rr_score.h"
 
@@ -256,6 +257,112 @@ rr_k_cliquer_counts2(const uint32_t *__restrict__ bits, const uint32_t *__restri
     }
 }
 
+// EXPERIMENTAL (RR_CLIQUER_KERNEL=3), written from the profile of the one-step kernel (POPC pipe 62 % busy at 16 resident
+// warps) when the round's GPU minutes were spent - never run on a GPU, opt-in test only.  Same structure, three changes:
+//   * the groups of a site partition its coverage (rr_k_pack_bits), so the fifth group's counts are differences:
+//     |G4 & Gq| = |Ck & Gq| - sum of the other four, |G4 & Cq| = |Ck & Cq| - sum of the other four: 10 POPC and five
+//     loads per word instead of 12 and six;
+//   * a chunk is skipped unless some read is covered by the candidate site AND by one of the block's queries (word-wise
+//     AND with the union of the queries' coverage, instead of the two chunk-level tests);
+//   * three blocks per SM (launch bound 85 registers) instead of two.
+__global__ void __launch_bounds__(CLQ_WARPS * 32, 3)
+rr_k_cliquer_counts3(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ covbits, int W32,
+                     const int32_t *__restrict__ queries, int nq, int anfang, int ende, int min_s, double greedy,
+                     const double *__restrict__ lnf, rr_clq_rec *__restrict__ cand, unsigned long long cap,
+                     unsigned long long *__restrict__ counter)
+{
+    extern __shared__ uint32_t clq_smem[];
+    const int nchunks = (W32 + 31) >> 5, W32p = nchunks << 5;
+    uint32_t *qg = clq_smem;
+    uint32_t *qc = qg + (size_t)CLQ_QB * W32p;
+    uint32_t *qmask = qc + (size_t)CLQ_QB * W32p;
+    uint32_t *qany = qmask + nchunks;                  // [W32p] union of the queries' coverage
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot0 = blockIdx.x * CLQ_QB;
+    clq_stage_queries<CLQ_QB>(bits, covbits, W32, queries, nq, slot0, qg, qc, qmask);
+    for (int w = threadIdx.x; w < W32p; w += CLQ_WARPS * 32) {
+        uint32_t u = 0u;
+#pragma unroll
+        for (int q = 0; q < CLQ_QB; q++) u |= qc[q * W32p + w];
+        qany[w] = u;
+    }
+    __syncthreads();
+
+    const int my_q = lane / 5, my_k = lane - my_q * 5;
+    const bool my_valid = lane < CLQ_QB * 5 && slot0 + my_q < nq;
+    const int my_query = my_valid ? queries[slot0 + my_q] : -1;
+
+    const int site_end = min(ende, anfang + ((int)blockIdx.y + 1) * CLQ_SLAB);
+    for (int ii = anfang + (int)blockIdx.y * CLQ_SLAB + warp; ii < site_end; ii += CLQ_WARPS) {
+        unsigned s[CLQ_QB][4], g1[CLQ_QB][4], g2[CLQ_QB], cv[CLQ_QB];
+#pragma unroll
+        for (int q = 0; q < CLQ_QB; q++) {
+            g2[q] = cv[q] = 0u;
+#pragma unroll
+            for (int k = 0; k < 4; k++) s[q][k] = g1[q][k] = 0u;
+        }
+        const uint32_t *cb = covbits + (size_t)ii * W32;
+        const uint32_t *gb = bits + (size_t)ii * 5 * W32;
+        for (int c = 0; c < nchunks; c++) {
+            const unsigned m = qmask[c];
+            if (m == 0u) continue;
+            const int w = c * 32 + lane;
+            const uint32_t cx = w < W32 ? __ldg(cb + w) : 0u;
+            if (__ballot_sync(CLQ_FULL, (cx & qany[w]) != 0u) == 0u) continue;   // no read covered on both sides
+            uint32_t x[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) x[k] = w < W32 ? __ldg(gb + (size_t)k * W32 + w) : 0u;
+#pragma unroll
+            for (int q = 0; q < CLQ_QB; q++) {
+                if (!((m >> q) & 1u)) continue;                      // warp-uniform
+                const uint32_t y = qg[q * W32p + w], cy = qc[q * W32p + w];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    s[q][k] += __popc(x[k] & y);
+                    g1[q][k] += __popc(x[k] & cy);
+                }
+                g2[q] += __popc(y & cx);
+                cv[q] += __popc(cx & cy);
+            }
+        }
+        int ms = 0, mg1 = 0, mg2 = 0, mcv = 0;
+#pragma unroll
+        for (int q = 0; q < CLQ_QB; q++) {
+            const int t2 = (int)__reduce_add_sync(CLQ_FULL, g2[q]);
+            if (t2 <= min_s) continue;                               // warp-uniform
+            const int tc = (int)__reduce_add_sync(CLQ_FULL, cv[q]);
+            int ts[5], t1[5];
+            ts[4] = t2;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                ts[k] = (int)__reduce_add_sync(CLQ_FULL, s[q][k]);
+                ts[4] -= ts[k];
+            }
+            const bool need5 = ts[4] > min_s;                        // the fifth |Gk & Cq| needs the other four
+            t1[4] = tc;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                t1[k] = 0;
+                if (ts[k] <= min_s && !need5) continue;              // warp-uniform
+                t1[k] = (int)__reduce_add_sync(CLQ_FULL, g1[q][k]);
+                t1[4] -= t1[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 5; k++)
+                if (ts[k] > min_s && lane == q * 5 + k) { ms = ts[k]; mg1 = t1[k]; mg2 = t2; mcv = tc; }
+        }
+        const int group = ii * 5 + my_k;
+        if (my_valid && ms > min_s && group != my_query) {           // 1210, 1215
+            const double bound = rr_bound_effective(rr_score_upper_bound(lnf, (unsigned)ms, (unsigned)mg1, (unsigned)mg2, (unsigned)mcv));
+            if (bound > greedy) {
+                rr_clq_rec r;
+                r.slot = slot0 + my_q; r.group = group; r.s = ms; r.gr1 = mg1; r.gr2 = mg2; r.cov = mcv; r.z = 0.0;
+                clq_append(cand, cap, counter, r);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128)
 rr_k_cliquer_score(const rr_clq_rec *__restrict__ cand, unsigned long long cap, const unsigned long long *__restrict__ counter,
                    const int32_t *__restrict__ queries, const int32_t *__restrict__ gsize, const double *__restrict__ lnf,
@@ -278,7 +385,9 @@ static size_t clq_smem_bytes(int W32, int qb)
     return (2 * (size_t)qb * nchunks * 32 + nchunks) * sizeof(uint32_t);
 }
 
-size_t rr_cliquer_smem_bytes(int W32) { return clq_smem_bytes(W32, CLQ_QB2 > CLQ_QB ? CLQ_QB2 : CLQ_QB); }
+static size_t clq_smem_bytes3(int W32) { return clq_smem_bytes(W32, CLQ_QB) + (((size_t)W32 + 31) / 32) * 32 * sizeof(uint32_t); }
+
+size_t rr_cliquer_smem_bytes(int W32) { return std::max(clq_smem_bytes(W32, CLQ_QB2 > CLQ_QB ? CLQ_QB2 : CLQ_QB), clq_smem_bytes3(W32)); }
 
 cudaError_t rr_launch_cliquer(int kernel, const uint32_t *bits, const uint32_t *covbits, const int32_t *gsize, const double *lnf,
                               int W32, const int32_t *queries, int nq, int anfang, int ende, int min_s, double greedy,
@@ -287,13 +396,17 @@ cudaError_t rr_launch_cliquer(int kernel, const uint32_t *bits, const uint32_t *
 {
     if (nq <= 0 || ende <= anfang) return cudaSuccess;
     const int qb = kernel == 2 ? CLQ_QB2 : CLQ_QB;
-    const size_t smem = clq_smem_bytes(W32, qb);
-    cudaError_t e = kernel == 2 ? cudaFuncSetAttribute(rr_k_cliquer_counts2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                : cudaFuncSetAttribute(rr_k_cliquer_counts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = kernel == 3 ? clq_smem_bytes3(W32) : clq_smem_bytes(W32, qb);
+    cudaError_t e = kernel == 2   ? cudaFuncSetAttribute(rr_k_cliquer_counts2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                    : kernel == 3 ? cudaFuncSetAttribute(rr_k_cliquer_counts3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                  : cudaFuncSetAttribute(rr_k_cliquer_counts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     // blockIdx.x = batch of queries, blockIdx.y = slab of candidate sites: the batches of one slab are adjacent in launch order
     dim3 grid((unsigned)((nq + qb - 1) / qb), (unsigned)((ende - anfang + CLQ_SLAB - 1) / CLQ_SLAB));
-    if (kernel == 2)
+    if (kernel == 3)
+        rr_k_cliquer_counts3<<<grid, CLQ_WARPS * 32, smem, st>>>(bits, covbits, W32, queries, nq, anfang, ende, min_s, greedy, lnf,
+                                                                 cand, cap, counters);
+    else if (kernel == 2)
         rr_k_cliquer_counts2<<<grid, CLQ_WARPS * 32, smem, st>>>(bits, covbits, W32, queries, nq, anfang, ende, min_s, greedy, lnf,
                                                                  cand, cap, counters);
     else

@@ -33,7 +33,7 @@ def main():
     res = {"rows": int(codes.shape[0]), "cols": int(codes.shape[1]), "queries": int(len(queries)), "gen_s": round(t_gen, 2)}
     w32 = 4 * ((codes.shape[0] + 127) // 128)
     res["bitset_bytes_one_pass"] = int(6 * codes.shape[1] * w32 * 4)
-    for kernel in ("1", "2"):
+    for kernel in ("1", "2") + (("3",) if os.environ.get("RR_TEST_UNVALIDATED") == "1" else ()):
         os.environ["RR_CLIQUER_KERNEL"] = kernel
         runs = []
         for rep in range(reps):
