@@ -143,6 +143,14 @@ int rr_maxcorr_run(const rr_msa *msa, int mincov, int n_gpus, int variant, unsig
 /* MaxCorrsRausschreiben: count lines "%f\n" */
 int rr_maxcorr_write(const char *path, const double *maxcorr, int64_t count);
 int rr_argmax_write(const char *path, const int32_t *argmax, int64_t count);
+/* Binary side format, "MaxCorrsBinOf_<MSA>": magic "RRMAXC01", int64 count, int64 flags (bit 0:
+ * partners stored), count doubles, count int32; little endian.  argmax may be NULL.  The text file remains the contract
+ * with the unmodified consumers (RepeatResolver.c:609-646, TransposonAssessment.py:51-58). */
+int rr_maxcorr_write_bin(const char *path, const double *maxcorr, const int32_t *argmax, int64_t count);
+/* The window MaxCorrsEinlesen(file, von, bis) keeps (RepeatResolver.c:631: columns von..bis inclusive), clipped to the
+ * file; outputs [5 * (bis - von + 1)] or NULL, *n_out = values delivered; as_text != 0 rounds the values as the "%f"
+ * text file would, so a consumer decides exactly as it would on MaxCorrsOf_*. */
+int rr_maxcorr_read_bin(const char *path, int von, int bis, int as_text, double *maxcorr_out, int32_t *argmax_out, int64_t *n_out);
 
 /* ---- host-side pieces exposed for tests and for RR_FLAG_HOST_FINALIZE ------------------ */
 double rr_lnfact(unsigned int n); /* gsl_sf_lnfact */

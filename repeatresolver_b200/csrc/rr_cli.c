@@ -10,7 +10,8 @@
  * cannot be opened (284).  Differences: -p is the number of B200s to use (the reference's
  * thread count has no meaning here; values above the device count are clamped, -p 0 means
  * 1); the arg-max partners go to a side file "MaxCorrsArgOf_" + argv[1] (never into
- * MaxCorrsOf_*); --variant bitset|umma and --no-finalize are extra switches.
+ * MaxCorrsOf_*); --variant bitset|umma, --no-finalize and --bin (also write the binary side
+ * file "MaxCorrsBinOf_" + argv[1]) are extra switches.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -23,7 +24,7 @@ void rr_trace_mark(const char *tag); /* librr_maxcorr.so internal: RR_TRACE=1 pr
 int main(int argc, char *argv[])
 {
     const char *path;
-    int cov = 30, parallel = 1, i, rc, variant = RR_VARIANT_AUTO, ndev;
+    int cov = 30, parallel = 1, i, rc, variant = RR_VARIANT_AUTO, ndev, write_bin = 0;
     unsigned flags = RR_FLAG_HOST_FINALIZE;
     rr_msa *msa = NULL;
     rr_scan_stats st;
@@ -52,6 +53,7 @@ int main(int argc, char *argv[])
             printf("Full coverage from column %ld until %ld.\n", strtol(argv[i + 1], NULL, 10), strtol(argv[i + 2], NULL, 10));
         if (!strcmp(argv[i], "--variant") && i + 1 < argc)
             variant = !strcmp(argv[i + 1], "bitset") ? RR_VARIANT_BITSET : !strcmp(argv[i + 1], "umma") ? RR_VARIANT_UMMA : RR_VARIANT_AUTO;
+        if (!strcmp(argv[i], "--bin")) write_bin = 1;
         if (!strcmp(argv[i], "--no-finalize")) flags &= ~RR_FLAG_HOST_FINALIZE;
         if (!strcmp(argv[i], "--no-prune")) flags |= RR_FLAG_NO_PRUNE;
     }
@@ -79,6 +81,10 @@ int main(int argc, char *argv[])
     if (rc) { printf("DateiVerbratei!\n"); exit(1); }
     snprintf(name, sizeof name, "MaxCorrsArgOf_%s", path);
     rr_argmax_write(name, A, G);
+    if (write_bin) {   /* full-precision values + partners for consumers that link the library (rr_maxcorr_read_bin) */
+        snprintf(name, sizeof name, "MaxCorrsBinOf_%s", path);
+        if (rr_maxcorr_write_bin(name, M, A, G)) { printf("DateiVerbratei!\n"); exit(1); }
+    }
     rr_trace_mark("cli: files written");
     printf("pair tests %lld, exact evaluations %lld, kernel %.3f ms (%s), pack %.3f ms, h2d %.3f ms\n",
            (long long)st.pair_tests, (long long)st.exact_evals, st.kernel_ms,

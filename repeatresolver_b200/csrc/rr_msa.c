@@ -302,6 +302,86 @@ int rr_argmax_write(const char *path, const int32_t *argmax, int64_t count)
     return RR_OK;
 }
 
+/* ---- binary side format of the result ("the MaxCorrsOf_* binary side-format to skip text") ----
+ * MaxCorrsBinOf_<MSA>, little endian:  8 bytes magic "RRMAXC01", int64 count (= 5 * siglength), int64 flags (bit 0: the
+ * arg-max partners follow), count doubles, then count int32.  The text file stays the contract with the unmodified
+ * downstream programs; this one spares a consumer that links the library the 5N sscanf calls of MaxCorrsEinlesen
+ * (RepeatResolver.c:609-646) and keeps the values at full precision. */
+static const char RR_BIN_MAGIC[8] = {'R', 'R', 'M', 'A', 'X', 'C', '0', '1'};
+
+int rr_maxcorr_write_bin(const char *path, const double *maxcorr, const int32_t *argmax, int64_t count)
+{
+    FILE *f;
+    int64_t head[2];
+    if (!path || count < 0 || (!maxcorr && count)) { rr_set_error("rr_maxcorr_write_bin: bad arguments"); return RR_E_ARG; }
+    f = fopen(path, "wb");
+    if (!f) { rr_set_error("cannot write %s: %s", path, strerror(errno)); return RR_E_IO; }
+    head[0] = count; head[1] = argmax ? 1 : 0;
+    if (fwrite(RR_BIN_MAGIC, 1, 8, f) != 8 || fwrite(head, sizeof(int64_t), 2, f) != 2 ||
+        (count && fwrite(maxcorr, sizeof(double), (size_t)count, f) != (size_t)count) ||
+        (count && argmax && fwrite(argmax, sizeof(int32_t), (size_t)count, f) != (size_t)count)) {
+        rr_set_error("write %s: %s", path, strerror(errno));
+        fclose(f);
+        return RR_E_IO;
+    }
+    if (fclose(f) != 0) { rr_set_error("write %s: %s", path, strerror(errno)); return RR_E_IO; }
+    return RR_OK;
+}
+
+/* what a "%f" line of MaxCorrsOf_* gives back to sscanf("%lf") (516-532 / 632) */
+static double rr_through_text(double v)
+{
+    char buf[400];
+    snprintf(buf, sizeof buf, "%f", v);
+    return strtod(buf, NULL);
+}
+
+/* The window MaxCorrsEinlesen(inputfile, von, bis) keeps: the groups of columns von..bis inclusive (631: i/5 >= von &&
+ * i/5 <= bis), clipped to the file.  maxcorr_out / argmax_out: [5 * (bis - von + 1)] or NULL; *n_out = values delivered.
+ * as_text != 0 rounds every value the way the text file would ("%f", six decimals), so that a consumer makes the very
+ * decisions it would make on MaxCorrsOf_*.  argmax_out without stored partners is filled with -1. */
+int rr_maxcorr_read_bin(const char *path, int von, int bis, int as_text, double *maxcorr_out, int32_t *argmax_out, int64_t *n_out)
+{
+    FILE *f;
+    char magic[8];
+    int64_t head[2], lo, hi, n, i;
+    if (!path || !n_out) { rr_set_error("rr_maxcorr_read_bin: bad arguments"); return RR_E_ARG; }
+    *n_out = 0;
+    f = fopen(path, "rb");
+    if (!f) { rr_set_error("cannot open %s: %s", path, strerror(errno)); return RR_E_IO; }
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, RR_BIN_MAGIC, 8) != 0 || fread(head, sizeof(int64_t), 2, f) != 2 || head[0] < 0) {
+        rr_set_error("%s is not a MaxCorrsBinOf_ file", path);
+        fclose(f);
+        return RR_E_IO;
+    }
+    lo = (int64_t)5 * (von < 0 ? 0 : von);
+    hi = bis < 0 ? 0 : (int64_t)5 * ((int64_t)bis + 1);
+    if (hi > head[0]) hi = head[0];
+    n = hi > lo ? hi - lo : 0;
+    if (n && maxcorr_out) {
+        if (fseek(f, (long)(24 + lo * (int64_t)sizeof(double)), SEEK_SET) != 0 || fread(maxcorr_out, sizeof(double), (size_t)n, f) != (size_t)n) {
+            rr_set_error("%s is truncated", path);
+            fclose(f);
+            return RR_E_IO;
+        }
+        if (as_text)
+            for (i = 0; i < n; i++) maxcorr_out[i] = rr_through_text(maxcorr_out[i]);
+    }
+    if (n && argmax_out) {
+        if (!(head[1] & 1)) {
+            for (i = 0; i < n; i++) argmax_out[i] = -1;
+        } else if (fseek(f, (long)(24 + head[0] * (int64_t)sizeof(double) + lo * (int64_t)sizeof(int32_t)), SEEK_SET) != 0 ||
+                   fread(argmax_out, sizeof(int32_t), (size_t)n, f) != (size_t)n) {
+            rr_set_error("%s is truncated", path);
+            fclose(f);
+            return RR_E_IO;
+        }
+    }
+    fclose(f);
+    *n_out = n;
+    return RR_OK;
+}
+
 /* First-break columns for rows that are single spans.  With contiguous spans the shared
  * coverage |C[ii] & C[jj]| = #{r : start_r <= ii, end_r >= jj} never increases with jj, so
  * the reference's "stop at the first jj with shared coverage < mincov" (807-810) is

@@ -217,6 +217,27 @@ def MaxCorrsRausschreiben(MaxCorrs, outputfile):
     _check(lib.rr_maxcorr_write(os.fsencode(outputfile), M.ctypes.data, len(M)), "rr_maxcorr_write")
 
 
+def MaxCorrsRausschreiben_bin(MaxCorrs, outputfile, argmax=None):
+    """the binary side format "MaxCorrsBinOf_<MSA>" (rr_maxcorr_write_bin): full-precision values, optional partners"""
+    M = np.ascontiguousarray(MaxCorrs, dtype=np.float64)
+    A = None if argmax is None else np.ascontiguousarray(argmax, dtype=np.int32)
+    assert A is None or len(A) == len(M)
+    _check(lib.rr_maxcorr_write_bin(os.fsencode(outputfile), M.ctypes.data, None if A is None else A.ctypes.data, len(M)),
+           "rr_maxcorr_write_bin")
+
+
+def MaxCorrsEinlesen_bin(inputfile, von, bis, as_text=False):
+    """MaxCorrsEinlesen (RepeatResolver.c:609-646) on the binary side format: the groups of columns von..bis inclusive,
+    (MaxCorrs, argmax); as_text rounds the values as the "%f" text file would"""
+    n = max(0, 5 * (bis - max(von, 0) + 1))
+    M = np.zeros(n, dtype=np.float64)
+    A = np.zeros(n, dtype=np.int32)
+    got = C.c_int64(0)
+    _check(lib.rr_maxcorr_read_bin(os.fsencode(inputfile), von, bis, int(as_text), M.ctypes.data, A.ctypes.data, C.byref(got)),
+           "rr_maxcorr_read_bin")
+    return M[:got.value].copy(), A[:got.value].copy()
+
+
 def MaxCorrelation(msa_path, c=30, p=1, variant="auto", flags=FLAG_HOST_FINALIZE, outdir=None):
     """The program: read <msa_path>, scan on p GPUs with coverage floor c, write
     MaxCorrsOf_<msa_path> (MaxCorrelation.c:991-993, 1014).  Returns (path written, stats)."""

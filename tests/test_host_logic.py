@@ -307,3 +307,62 @@ def test_msagen_deterministic_and_shaped():
         assert codes[r, cov[0]] != 4 and codes[r, cov[-1]] != 4
     t = a.text().split(b"\n")
     assert len(t) == a.rows + 1 and set(b"".join(t)) <= set(b"ACGT- ")
+
+
+# ---- binary side format of the result --------------------------------------------------------
+def reference_text_window(text_path, von, bis):
+    """MaxCorrsEinlesen (RepeatResolver.c:609-646) restated: line i is kept when von <= i/5 <= bis"""
+    out = []
+    with open(text_path) as f:
+        for i, line in enumerate(f):
+            if von <= i // 5 <= bis:
+                out.append(float(line))
+    return np.array(out)
+
+
+def test_binary_side_format_round_trip_and_window(tmp_path):
+    rng = np.random.default_rng(12)
+    N = 57
+    M = np.round(rng.uniform(0, 99, 5 * N), 9)
+    M[rng.random(5 * N) < 0.3] = 0.0
+    M[3] = 98.897959183673464                      # a saturated value with more than six decimals
+    A = rng.integers(-1, 5 * N, 5 * N).astype(np.int32)
+    tp, bp = str(tmp_path / "MaxCorrsOf_X"), str(tmp_path / "MaxCorrsBinOf_X")
+    rr.MaxCorrsRausschreiben(M, tp)
+    rr.MaxCorrsRausschreiben_bin(M, bp, A)
+    assert os.path.getsize(bp) == 24 + 5 * N * 12
+    for von, bis in ((0, N - 1), (0, 10 ** 6), (5, 9), (56, 56), (56, 70), (57, 80), (-3, 2), (9, 5)):
+        Mb, Ab = rr.MaxCorrsEinlesen_bin(bp, von, bis)
+        lo, hi = 5 * max(von, 0), min(5 * N, 5 * (bis + 1))
+        assert np.array_equal(Mb, M[lo:hi]) and np.array_equal(Ab, A[lo:hi]), (von, bis)       # full precision
+        Mt, _ = rr.MaxCorrsEinlesen_bin(bp, von, bis, as_text=True)
+        assert np.array_equal(Mt, reference_text_window(tp, von, bis)), (von, bis)               # what the text reader sees
+    assert rr.MaxCorrsEinlesen_bin(bp, 0, 0, as_text=True)[0][3] == 98.897959
+    # without partners
+    rr.MaxCorrsRausschreiben_bin(M, bp)
+    assert os.path.getsize(bp) == 24 + 5 * N * 8
+    Mb, Ab = rr.MaxCorrsEinlesen_bin(bp, 2, 3)
+    assert np.array_equal(Mb, M[10:20]) and (Ab == -1).all()
+    # empty result
+    rr.MaxCorrsRausschreiben_bin(np.zeros(0), bp)
+    assert len(rr.MaxCorrsEinlesen_bin(bp, 0, 5)[0]) == 0
+
+
+def test_binary_side_format_rejects_other_files(tmp_path):
+    p = tmp_path / "junk"
+    p.write_bytes(b"0.000000\n" * 10)
+    with pytest.raises(rr.RRError):
+        rr.MaxCorrsEinlesen_bin(str(p), 0, 1)
+    with pytest.raises(rr.RRError):
+        rr.MaxCorrsEinlesen_bin(str(tmp_path / "missing"), 0, 1)
+    good = tmp_path / "good"
+    rr.MaxCorrsRausschreiben_bin(np.arange(50, dtype=np.float64), str(good), np.arange(50, dtype=np.int32))
+    data = good.read_bytes()
+    (tmp_path / "short").write_bytes(data[:24 + 100])
+    with pytest.raises(rr.RRError):
+        rr.MaxCorrsEinlesen_bin(str(tmp_path / "short"), 0, 9)
+    (tmp_path / "noargs").write_bytes(data[:24 + 400 + 40])
+    M, _ = rr.MaxCorrsEinlesen_bin(str(tmp_path / "noargs"), 0, 1)      # values intact, partners of the window intact
+    assert list(M) == list(range(10))
+    with pytest.raises(rr.RRError):
+        rr.MaxCorrsEinlesen_bin(str(tmp_path / "noargs"), 5, 9)         # partners of that window are cut off
