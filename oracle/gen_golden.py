@@ -6,7 +6,8 @@ linked against oracle/gsl_shim.c) writes for them.  Run in the build container o
 /root/reference does not exist on the GPU box.
 
 The reference ships no fixtures of its own, so apart from the
-formula-defined case of SURVEY.md Appendix G these are generated ones.
+formula-defined case of SURVEY.md Appendix G and one MSA made by the reference's own pipeline
+(real_pipeline_msareal, see main()) these are generated ones.
 """
 import gzip
 import json
@@ -74,6 +75,20 @@ def main():
     lines.insert(12, "")
     ragged = "\n".join(lines)  # no trailing newline: the last row is dropped by the reference
     cases["ragged"] = (ragged.encode(), [20])
+
+    # The reference's OWN pipeline output (BASELINE.json configs[0]): DataSimulator.py -c 40 -n 10 -d 1 -l 5000 -t Tree ->
+    # ReadCutter -> InitialAligner -p 8 -> PW_ReAligner (a snapshot after its sixth realignment round), all built from the
+    # unmodified sources under /root/reference in a scratch directory (DataSimulator.py run under python3 through a
+    # scratch copy with print() calls).  DataSimulator.py takes no seed, so the MSA cannot be regenerated bit for bit:
+    # the file itself is the fixture (312 reads x 18 557 columns, 53 % blanks, 28 % gaps; 7.7e7 pair tests at -c 30).
+    real = os.environ.get("RR_REAL_MSAREAL", "/tmp/pipe/Tree_1perc_5000kb_MSAreal")
+    committed = os.path.join(GOLD, "real_pipeline_msareal.msa.gz")
+    if os.path.exists(committed):
+        with gzip.open(committed, "rb") as f:
+            cases["real_pipeline_msareal"] = (f.read(), [30])
+    elif os.path.exists(real):
+        with open(real, "rb") as f:
+            cases["real_pipeline_msareal"] = (f.read(), [30])
 
     index = {}
     for name, (text, covs) in cases.items():
