@@ -44,6 +44,9 @@ def check_against_oracle(M, A, P, oracle, mincov, M0=None, A0=None, P0=None):
     return M0, A0, P0
 
 
+_ORACLE_SCANS = {}
+
+
 @pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("name,cov", GOLDEN_CASES)
 def test_golden_cases(name, cov, variant, tmp_path):
@@ -55,7 +58,9 @@ def test_golden_cases(name, cov, variant, tmp_path):
     assert (gs == oracle.gsize()).all() and (cv == oracle.coverage()).all()
     st = pk.scan(mincov=cov, variant=variant)
     M, A = pk.fetch()
-    M0, A0, P0 = check_against_oracle(M, A, st["pair_tests"], oracle, cov)
+    if (name, cov) not in _ORACLE_SCANS:             # one oracle scan per case, shared by the variants
+        _ORACLE_SCANS[(name, cov)] = oracle.scan(cov, threads=os.cpu_count() or 8)
+    M0, A0, P0 = check_against_oracle(M, A, st["pair_tests"], oracle, cov, *_ORACLE_SCANS[(name, cov)])
     assert (A == A0).all()  # the CAS keeps the smallest partner among exact ties, like the oracle
     # without pruning the result is bitwise the same
     st2 = pk.scan(mincov=cov, variant=variant, flags=rr.FLAG_NO_PRUNE)
