@@ -220,6 +220,22 @@ int rr_relative_vars_from_counts(int64_t n_groups, const double *maxcorrs, const
                                  int mingroup, const int32_t *S, int32_t *sel_out, int *n_sel, int32_t *vars, int *n_vars);
 double rr_relative_score_host(uint32_t schnitt, uint32_t gr1, uint32_t gr2, uint32_t cov);
 
+/* ---- scope row 8f-4: Kmeans (RepeatResolver.c:2604-2821), EXPERIMENTAL (device part never run on a GPU yet) --------
+ * Splits part u_no of the read partition by the reads' signatures over the groups `vars` (the output of Relative_Vars):
+ * unterteilung[rows of msa] is updated in place exactly as the reference does (the part's reads get cluster + max + 1,
+ * 2814-2815), *n_clusters = the reference's return value (non-empty clusters).  All arithmetic is integer: bit-exact. */
+int rr_kmeans(const rr_msa *msa, int device, int32_t *unterteilung, int u_no, const int32_t *vars, int n_vars, int mingroup,
+              int *n_clusters);
+/* host pieces (tests): the part's reads and signatures ([anzahl][n_vars/64+1] 64-bit words; sig_out may be NULL to get the
+ * count), the dissolution of small clusters given the device's first assignment, and the two integer rules the kernels
+ * share with the host (csrc/rr_kmeans.h) */
+int rr_kmeans_signatures(const rr_msa *msa, const int32_t *unterteilung, int u_no, const int32_t *vars, int n_vars,
+                         int32_t *reads_out /*[rows]*/, int *anzahl_out, uint64_t *sig_out);
+int rr_kmeans_finish(int anzahl, int scv, const uint64_t *sig, const uint64_t *cen, const int32_t *cluster_in, int mingroup,
+                     int32_t *cluster_out, int *n_clusters);
+int rr_kmeans_top5_host(int anzahl, int scv, const uint64_t *sig, int i, int32_t *best_j /*[5]*/);
+uint64_t rr_kmeans_majority5_host(uint64_t a, uint64_t b, uint64_t c, uint64_t d, uint64_t e);
+
 /* the exact contraction ranges of the scan plan (csrc/rr_plan.h), for tests: rows in rank order with spans
  * start[r]..end[r] (inclusive), ranks [0, class_split) and [class_split, rows) each sorted by start; every site is
  * taken as a row site, ti / tj sites per row / column block, kunit rows per contraction unit.  A row of class c can

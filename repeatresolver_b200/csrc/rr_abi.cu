@@ -17,6 +17,7 @@
 #include "rr_kernels.h"
 #include "rr_device.cuh"
 #include "rr_plan.h"
+#include "rr_kmeans.h"
 
 #include <chrono>
 static double rr_now_ms()
@@ -1018,6 +1019,147 @@ extern "C" int rr_relative_vars(const rr_msa *msa, int device, const int32_t *un
     vars[n] = -1;
     *n_vars = n;
     if (pairs_tested) *pairs_tested = tested;
+    return RR_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Kmeans (RepeatResolver.c:2604-2821), EXPERIMENTAL: signatures and the dissolution of small clusters on the host, the
+// two read x read sweeps and the centroids on the device (rr_kmeans.cu, never run on a GPU yet).  The host pieces and the
+// integer rules shared with the kernels (rr_kmeans.h) are pinned against the unmodified reference on the CPU.
+// ---------------------------------------------------------------------------------------
+static inline int host_class(uint8_t c, int codes)                       // 304-329, as rr_classify in rr_pack.cu
+{
+    if (codes) return c < 5 ? (int)c : 5;
+    switch (c) {
+    case 'a': case 'A': return 0;
+    case 'c': case 'C': return 1;
+    case 'g': case 'G': return 2;
+    case 't': case 'T': return 3;
+    case '-': case '_': return 4;
+    default: return 5;
+    }
+}
+
+// 2616-2642: the reads of the part and their signatures over the selected groups
+extern "C" int rr_kmeans_signatures(const rr_msa *msa, const int32_t *unterteilung, int u_no, const int32_t *vars, int n_vars,
+                                    int32_t *reads_out, int *anzahl_out, uint64_t *sig_out)
+{
+    if (!msa || !unterteilung || n_vars < 0 || (n_vars && !vars) || !reads_out || !anzahl_out) {
+        rr_set_error("rr_kmeans_signatures: bad arguments");
+        return RR_E_ARG;
+    }
+    for (int j = 0; j < n_vars; j++)
+        if (vars[j] < 0 || vars[j] >= 5 * msa->cols) { rr_set_error("rr_kmeans_signatures: group %d out of range", vars[j]); return RR_E_ARG; }
+    const int scv = n_vars / 64 + 1;                                      // 2626
+    int anzahl = 0;
+    for (int r = 0; r < msa->rows; r++)
+        if (unterteilung[r] == u_no) reads_out[anzahl++] = r;
+    *anzahl_out = anzahl;
+    if (!sig_out) return RR_OK;
+    std::fill(sig_out, sig_out + (size_t)anzahl * scv, (uint64_t)0);
+    for (int i = 0; i < anzahl; i++) {
+        const uint8_t *row = rr_msa_row(msa, reads_out[i]);
+        uint64_t *sg = sig_out + (size_t)i * scv;
+        for (int j = 0; j < n_vars; j++)
+            if (host_class(row[vars[j] / 5], msa->codes) == vars[j] % 5) sg[j / 64] |= (uint64_t)1 << (j % 64);
+    }
+    return RR_OK;
+}
+
+// 2728-2757 and 2790-2797: clusters of at most `min` reads are dissolved into clusters of at least `min`, in read order,
+// sizes updated as it goes; returns the number of non-empty clusters
+extern "C" int rr_kmeans_finish(int anzahl, int scv, const uint64_t *sig, const uint64_t *cen, const int32_t *cluster_in, int mingroup,
+                                int32_t *cluster_out, int *n_clusters)
+{
+    if (anzahl < 0 || scv < 1 || !n_clusters || (anzahl && (!sig || !cen || !cluster_in || !cluster_out))) {
+        rr_set_error("rr_kmeans_finish: bad arguments");
+        return RR_E_ARG;
+    }
+    std::vector<int> size((size_t)anzahl + 1, 0);
+    for (int i = 0; i < anzahl; i++) {
+        if (cluster_in[i] < 0 || cluster_in[i] >= anzahl) { rr_set_error("rr_kmeans_finish: cluster %d out of range", cluster_in[i]); return RR_E_ARG; }
+        cluster_out[i] = cluster_in[i];
+        size[cluster_in[i]]++;
+    }
+    for (int min = 2; min < mingroup; min++)
+        for (int i = 0; i < anzahl; i++)
+            if (size[cluster_out[i]] <= min) {
+                int best = 0, best_j = 0;
+                for (int j = 0; j < anzahl; j++)
+                    if (size[j] >= min && cluster_out[i] != j) {
+                        const int score = rr_km_match(cen + (size_t)j * scv, sig + (size_t)i * scv, scv);
+                        if (score > best && i != j) { best = score; best_j = j; }
+                    }
+                size[cluster_out[i]]--;
+                cluster_out[i] = best_j;
+                size[best_j]++;
+            }
+    int n = 0;
+    for (int i = 0; i < anzahl; i++) n += size[i] > 0;
+    *n_clusters = n;
+    return RR_OK;
+}
+
+// function-level hooks on the rules the kernels share with the host (rr_kmeans.h)
+extern "C" int rr_kmeans_top5_host(int anzahl, int scv, const uint64_t *sig, int i, int32_t *best_j)
+{
+    if (anzahl < 1 || scv < 1 || !sig || i < 0 || i >= anzahl || !best_j) return RR_E_ARG;
+    int bs[5] = {0, 0, 0, 0, 0}, bj[5] = {0, 0, 0, 0, 0};
+    for (int j = 0; j < anzahl; j++) rr_km_top5_step(bs, bj, rr_km_match(sig + (size_t)j * scv, sig + (size_t)i * scv, scv), j);
+    for (int k = 0; k < 5; k++) best_j[k] = bj[k];
+    return RR_OK;
+}
+
+extern "C" uint64_t rr_kmeans_majority5_host(uint64_t a, uint64_t b, uint64_t c, uint64_t d, uint64_t e)
+{
+    return rr_km_majority5(a, b, c, d, e);
+}
+
+extern "C" int rr_kmeans(const rr_msa *msa, int device, int32_t *unterteilung, int u_no, const int32_t *vars, int n_vars,
+                         int mingroup, int *n_clusters)
+{
+    if (!msa || !unterteilung || !n_clusters || n_vars < 0 || (n_vars && !vars)) { rr_set_error("rr_kmeans: bad arguments"); return RR_E_ARG; }
+    *n_clusters = 0;
+    const int ndev = rr_device_count();
+    if (ndev <= 0) { rr_set_error("no CUDA device: Kmeans has no CPU fallback"); return RR_E_NODEV; }
+    if (device < 0 || device >= ndev) { rr_set_error("device %d out of range (%d devices)", device, ndev); return RR_E_ARG; }
+    const int scv = n_vars / 64 + 1;
+    std::vector<int32_t> reads((size_t)std::max(msa->rows, 1));
+    int anzahl = 0, rc;
+    if ((rc = rr_kmeans_signatures(msa, unterteilung, u_no, vars, n_vars, reads.data(), &anzahl, nullptr))) return rc;
+    if (anzahl == 0) return RR_OK;
+    std::vector<uint64_t> sig((size_t)anzahl * scv), cen((size_t)anzahl * scv);
+    if ((rc = rr_kmeans_signatures(msa, unterteilung, u_no, vars, n_vars, reads.data(), &anzahl, sig.data()))) return rc;
+    std::vector<int32_t> cluster((size_t)anzahl), final_cluster((size_t)anzahl);
+    RR_CUDA(cudaSetDevice(device));
+    cudaStream_t st = nullptr;
+    RR_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    rr_alloc_stream(st);
+    {
+        dev_scope scope;
+        uint64_t *d_sig = nullptr, *d_cen = nullptr;
+        int32_t *d_best = nullptr, *d_cluster = nullptr;
+        cudaError_t e = cudaSuccess;
+        if ((rc = scope.alloc(&d_sig, sig.size())) || (rc = scope.alloc(&d_cen, cen.size())) || (rc = scope.alloc(&d_best, (size_t)anzahl * 5)) ||
+            (rc = scope.alloc(&d_cluster, (size_t)anzahl))) {
+            // fall through to the clean-up below
+        } else if ((e = cudaMemcpyAsync(d_sig, sig.data(), sizeof(uint64_t) * sig.size(), cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+                   (e = rr_launch_kmeans_sweeps(d_sig, anzahl, scv, d_best, d_cen, d_cluster, st)) != cudaSuccess ||
+                   (e = cudaMemcpyAsync(cen.data(), d_cen, sizeof(uint64_t) * cen.size(), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+                   (e = cudaMemcpyAsync(cluster.data(), d_cluster, sizeof(int32_t) * (size_t)anzahl, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+                   (e = cudaStreamSynchronize(st)) != cudaSuccess) {
+            rr_set_error("CUDA error %s in rr_kmeans", cudaGetErrorString(e));
+            rc = RR_E_CUDA;
+        }
+    }   // device buffers go back to the pool while the stream still exists
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    rr_alloc_stream(nullptr);
+    if (rc) return rc;
+    if ((rc = rr_kmeans_finish(anzahl, scv, sig.data(), cen.data(), cluster.data(), mingroup, final_cluster.data(), n_clusters))) return rc;
+    int max_u = 0;                                                       // 2814-2815
+    for (int r = 0; r < msa->rows; r++) max_u = std::max(max_u, unterteilung[r]);
+    for (int i = 0; i < anzahl; i++) unterteilung[reads[i]] = final_cluster[i] + max_u + 1;
     return RR_OK;
 }
 

@@ -47,6 +47,10 @@ cudaError_t rr_launch_relvars_pairs(const uint32_t *bits, int W32, const int32_t
                                     const int32_t *gsize_u, int cov_u, const double *lnf, double cutoff, unsigned char *mark,
                                     int4 *unsure, unsigned int unsure_cap, unsigned int *unsure_count, cudaStream_t st);
 
+// Kmeans (rr_kmeans.cu, experimental): the two read x read sweeps and the centroids on the part's signatures
+cudaError_t rr_launch_kmeans_sweeps(const uint64_t *sig, int anzahl, int scv, int32_t *best_j, uint64_t *cen, int32_t *cluster,
+                                    cudaStream_t st);
+
 struct rr_best_t;
 cudaError_t rr_launch_init_best(rr_best_t *best, int64_t n, cudaStream_t st);
 cudaError_t rr_launch_raise_best(rr_best_t *best, const double *thr, int64_t n, cudaStream_t st);

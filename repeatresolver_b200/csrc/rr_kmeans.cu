@@ -1,0 +1,106 @@
+// rr_kmeans.cu -- the read x read sweeps of Kmeans (/root/reference/RepeatResolver.c:2604-2821) on the device
+// ("the transposed Gram problem").  EXPERIMENTAL: written when the round's GPU minutes
+// were spent, never run on a GPU; its test is opt-in (RR_TEST_UNVALIDATED=1).  The integer rules are shared with the
+// host through rr_kmeans.h and pinned there against the unmodified reference (tests/test_oracle_kmeans.py).
+//
+// sig[anzahl][scv]: the signatures of the part's reads over the selected groups (64-bit words, padding 0).
+//   rr_k_km_top5       one thread per read i, all reads j in order (tiles of signatures through shared memory, every
+//                      thread of the block reads the same word: a broadcast): GrMatch and the reference's five-slot rule
+//                      (2662-2692), which depends on the order of the reads and so stays sequential per read
+//   rr_k_km_centroids  one thread per (read, word): bitwise majority of the five kept reads' signatures (2697-2705)
+//   rr_k_km_assign     one thread per read i: the first best centroid of another read (2709-2725)
+// XOR+POPC work on a few KB of signatures per tile: POPC-issue bound, anzahl^2 * scv word operations per sweep.
+#include <algorithm>
+#include "rr_kernels.h"
+#include "rr_kmeans.h"
+
+constexpr int KM_THREADS = 128;
+
+// stage signatures [j0, j0 + nj) into shared memory, coalesced
+__device__ __forceinline__ void km_stage(uint64_t *tile, const uint64_t *__restrict__ src, int j0, int nj, int scv)
+{
+    for (int idx = threadIdx.x; idx < nj * scv; idx += KM_THREADS) tile[idx] = src[(size_t)j0 * scv + idx];
+}
+
+__global__ void __launch_bounds__(KM_THREADS)
+rr_k_km_top5(const uint64_t *__restrict__ sig, int anzahl, int scv, int tile_reads, int32_t *__restrict__ best_j /*[anzahl][5]*/)
+{
+    extern __shared__ uint64_t km_smem[];
+    uint64_t *tile = km_smem;                                   // [tile_reads][scv]
+    const int i = blockIdx.x * KM_THREADS + threadIdx.x;
+    const uint64_t *mine = sig + (size_t)min(i, anzahl - 1) * scv;   // idle threads still take part in the staging
+    int bs[5] = {0, 0, 0, 0, 0}, bj[5] = {0, 0, 0, 0, 0};
+    for (int j0 = 0; j0 < anzahl; j0 += tile_reads) {
+        const int nj = min(tile_reads, anzahl - j0);
+        __syncthreads();
+        km_stage(tile, sig, j0, nj, scv);
+        __syncthreads();
+        for (int j = 0; j < nj; j++) {
+            int d = 0;
+            for (int z = 0; z < scv; z++) d += __popcll(tile[j * scv + z] ^ __ldg(mine + z));
+            rr_km_top5_step(bs, bj, scv * 64 - d, j0 + j);
+        }
+    }
+    if (i < anzahl)
+        for (int k = 0; k < 5; k++) best_j[(size_t)i * 5 + k] = bj[k];
+}
+
+__global__ void __launch_bounds__(256)
+rr_k_km_centroids(const uint64_t *__restrict__ sig, const int32_t *__restrict__ best_j, int anzahl, int scv,
+                  uint64_t *__restrict__ cen)
+{
+    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= (int64_t)anzahl * scv) return;
+    const int i = (int)(t / scv), z = (int)(t - (int64_t)i * scv);
+    const int32_t *b = best_j + (size_t)i * 5;
+    cen[t] = rr_km_majority5(sig[(size_t)b[0] * scv + z], sig[(size_t)b[1] * scv + z], sig[(size_t)b[2] * scv + z],
+                             sig[(size_t)b[3] * scv + z], sig[(size_t)b[4] * scv + z]);
+}
+
+__global__ void __launch_bounds__(KM_THREADS)
+rr_k_km_assign(const uint64_t *__restrict__ sig, const uint64_t *__restrict__ cen, int anzahl, int scv, int tile_reads,
+               int32_t *__restrict__ cluster)
+{
+    extern __shared__ uint64_t km_smem[];
+    uint64_t *tile = km_smem;
+    const int i = blockIdx.x * KM_THREADS + threadIdx.x;
+    const uint64_t *mine = sig + (size_t)min(i, anzahl - 1) * scv;
+    int best = 0, best_j = 0;
+    for (int j0 = 0; j0 < anzahl; j0 += tile_reads) {
+        const int nj = min(tile_reads, anzahl - j0);
+        __syncthreads();
+        km_stage(tile, cen, j0, nj, scv);
+        __syncthreads();
+        for (int j = 0; j < nj; j++) {
+            int d = 0;
+            for (int z = 0; z < scv; z++) d += __popcll(tile[j * scv + z] ^ __ldg(mine + z));
+            const int score = scv * 64 - d;
+            if (score > best && i != j0 + j) { best = score; best_j = j0 + j; }     // 2717: first best, not itself
+        }
+    }
+    if (i < anzahl) cluster[i] = best_j;
+}
+
+cudaError_t rr_launch_kmeans_sweeps(const uint64_t *sig, int anzahl, int scv, int32_t *best_j, uint64_t *cen, int32_t *cluster,
+                                    cudaStream_t st)
+{
+    if (anzahl <= 0) return cudaSuccess;
+    // signatures per shared-memory tile: up to 32 KB
+    const int tile_reads = (int)std::max<size_t>(1, std::min<size_t>(256, ((size_t)32 << 10) / ((size_t)scv * sizeof(uint64_t))));
+    const size_t smem = (size_t)tile_reads * scv * sizeof(uint64_t);
+    if (smem > ((size_t)200 << 10)) return cudaErrorInvalidValue;   // more than 1.6 M selected groups: not this kernel
+    cudaError_t e;
+    if (smem > ((size_t)48 << 10)) {
+        if ((e = cudaFuncSetAttribute(rr_k_km_top5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(rr_k_km_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    }
+    const unsigned nb = (unsigned)((anzahl + KM_THREADS - 1) / KM_THREADS);
+    rr_k_km_top5<<<nb, KM_THREADS, smem, st>>>(sig, anzahl, scv, tile_reads, best_j);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    const int64_t nw = (int64_t)anzahl * scv;
+    rr_k_km_centroids<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(sig, best_j, anzahl, scv, cen);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    rr_k_km_assign<<<nb, KM_THREADS, smem, st>>>(sig, cen, anzahl, scv, tile_reads, cluster);
+    rr_count_launch(3);
+    return cudaGetLastError();
+}

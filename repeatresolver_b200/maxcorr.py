@@ -309,6 +309,54 @@ def relative_vars_from_counts(maxcorrs, gsize_u, cov_u, cutoff, mingroup, triple
     return out[:n.value].copy()
 
 
+def Kmeans(msa, Unterteilung, u_no, Vars, mingroup, device=0):
+    """RepeatResolver.c:2604-2821 with the reference's argument order (EXPERIMENTAL, rr_kmeans): splits part u_no of the
+    read partition; returns (number of non-empty clusters, the new partition) - the reference updates Unterteilung in place"""
+    u = np.array(Unterteilung, dtype=np.int32)
+    v = np.ascontiguousarray(Vars, dtype=np.int32)
+    assert len(u) == msa.rows
+    n = C.c_int(0)
+    _check(lib.rr_kmeans(msa._h, device, u.ctypes.data, int(u_no), v.ctypes.data, len(v), int(mingroup), C.byref(n)), "rr_kmeans")
+    return n.value, u
+
+
+def kmeans_signatures(msa, Unterteilung, u_no, Vars):
+    """host piece of rr_kmeans (test hook): (reads of the part, signatures [anzahl][n_vars/64+1] uint64)"""
+    u = np.ascontiguousarray(Unterteilung, dtype=np.int32)
+    v = np.ascontiguousarray(Vars, dtype=np.int32)
+    reads = np.zeros(max(msa.rows, 1), dtype=np.int32)
+    n = C.c_int(0)
+    _check(lib.rr_kmeans_signatures(msa._h, u.ctypes.data, int(u_no), v.ctypes.data, len(v), reads.ctypes.data, C.byref(n), None),
+           "rr_kmeans_signatures")
+    sig = np.zeros((n.value, len(v) // 64 + 1), dtype=np.uint64)
+    _check(lib.rr_kmeans_signatures(msa._h, u.ctypes.data, int(u_no), v.ctypes.data, len(v), reads.ctypes.data, C.byref(n),
+                                    sig.ctypes.data), "rr_kmeans_signatures")
+    return reads[:n.value].copy(), sig
+
+
+def kmeans_top5_host(sig, i):
+    sig = np.ascontiguousarray(sig, dtype=np.uint64)
+    out = np.zeros(5, dtype=np.int32)
+    _check(lib.rr_kmeans_top5_host(sig.shape[0], sig.shape[1], sig.ctypes.data, int(i), out.ctypes.data), "rr_kmeans_top5_host")
+    return out
+
+
+def kmeans_majority5_host(a, b, c, d, e):
+    return int(lib.rr_kmeans_majority5_host(int(a), int(b), int(c), int(d), int(e)))
+
+
+def kmeans_finish(sig, cen, cluster, mingroup):
+    """host piece of rr_kmeans (test hook): the dissolution of small clusters, (final clusters, number of non-empty ones)"""
+    sig = np.ascontiguousarray(sig, dtype=np.uint64)
+    cen = np.ascontiguousarray(cen, dtype=np.uint64)
+    cl = np.ascontiguousarray(cluster, dtype=np.int32)
+    out = np.zeros(len(cl), dtype=np.int32)
+    n = C.c_int(0)
+    _check(lib.rr_kmeans_finish(sig.shape[0], sig.shape[1], sig.ctypes.data, cen.ctypes.data, cl.ctypes.data, int(mingroup),
+                                out.ctypes.data, C.byref(n)), "rr_kmeans_finish")
+    return out, n.value
+
+
 def launch_count():
     return int(lib.rr_launch_count())
 

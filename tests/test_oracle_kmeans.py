@@ -126,3 +126,74 @@ def test_kmeans_first_assignment_against_numpy():
     fam = (np.arange(R) >= 20)[I]
     for c in set(cluster):
         assert len(set(fam[np.array(cluster) == c])) == 1
+
+
+# ---- the product's host pieces and the integer rules its kernels share with the host (csrc/rr_kmeans.h) ----------------
+def popcount64(a):
+    return np.unpackbits(a.view(np.uint8), axis=-1).sum(-1).astype(np.int64)
+
+
+def test_majority_of_five_is_exact_for_all_patterns():
+    import repeatresolver_b200 as rr
+    rng = np.random.default_rng(6)
+    for _ in range(300):
+        w = [int(x) for x in rng.integers(0, 2 ** 63, 5, dtype=np.uint64) * 2 + rng.integers(0, 2, 5, dtype=np.uint64)]
+        got = rr.kmeans_majority5_host(*w)
+        want = 0
+        for b in range(64):
+            if sum((x >> b) & 1 for x in w) > 2:
+                want |= 1 << b
+        assert got == want
+    assert rr.kmeans_majority5_host(2 ** 64 - 1, 2 ** 64 - 1, 2 ** 64 - 1, 0, 0) == 2 ** 64 - 1
+    assert rr.kmeans_majority5_host(2 ** 64 - 1, 2 ** 64 - 1, 0, 0, 0) == 0
+
+
+@pytest.mark.parametrize("name", sorted(kmeans_cases()))
+def test_product_pieces_chain_to_the_reference_result(name):
+    """signatures (host), five-slot rule and majority (shared with the kernels), first-best assignment (numpy here, a kernel
+    in the product), dissolution (host): chained, they must give the unmodified reference's partition"""
+    import repeatresolver_b200 as rr
+    rel = relvars_cases()[name]
+    codes = window_codes(golden_msa(name), rel["von"], rel["bis"])
+    o = O.Oracle.from_codes(codes)
+    M, _, _ = o.scan(rel["mincov"])
+    ut, _ = partition_by_site(codes, M)
+    msa = rr.MSA.from_cells(codes, codes=True)
+    for key, want in kmeans_cases()[name].items():
+        u_no, mingroup = (int(x) for x in key.split("/"))
+        vars_ = np.array(rel["parts"][str(u_no)]["vars"], dtype=np.int32)
+        reads, sig = rr.kmeans_signatures(msa, ut, u_no, vars_)
+        assert list(reads) == list(np.flatnonzero(ut == u_no))
+        bits = np.zeros((len(reads), sig.shape[1] * 64), dtype=np.uint8)
+        bits[:, :len(vars_)] = codes[reads][:, vars_ // 5] == vars_ % 5
+        assert np.array_equal(sig, np.packbits(bits, axis=1, bitorder="little").view(np.uint64))
+        n, scv = sig.shape
+        cen = np.zeros_like(sig)
+        for i in range(n):
+            bj = rr.kmeans_top5_host(sig, i)
+            for z in range(scv):
+                cen[i, z] = rr.kmeans_majority5_host(*(int(sig[j, z]) for j in bj))
+        cluster = np.zeros(n, dtype=np.int32)
+        for i in range(n):
+            score = scv * 64 - popcount64(cen ^ sig[i]).reshape(n, -1).sum(1)
+            score[i] = -1                                            # i != j (2717)
+            best = int(score.max())
+            cluster[i] = int(np.argmax(score)) if best > 0 else 0    # first best; nothing above 0 leaves slot 0
+        final, split = rr.kmeans_finish(sig, cen, cluster, mingroup)
+        after = ut.copy()
+        after[reads] = final + ut.max() + 1
+        assert split == want["split"] and list(after) == want["after"], key
+    msa.close()
+
+
+def test_kmeans_needs_a_device():
+    import repeatresolver_b200 as rr
+    if rr.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    codes = np.zeros((4, 6), dtype=np.uint8)
+    msa = rr.MSA.from_cells(codes, codes=True)
+    with pytest.raises(rr.RRError):
+        rr.Kmeans(msa, np.zeros(4, dtype=np.int32), 0, [0, 5], 3)
+    with pytest.raises(rr.RRError):
+        rr.Relative_Vars(msa, np.zeros(4, dtype=np.int32), 0, np.full(30, 9.0), 3.0, 2)
+    msa.close()
