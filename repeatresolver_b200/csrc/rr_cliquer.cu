@@ -87,7 +87,7 @@ rr_k_cliquer_counts(const uint32_t *__restrict__ bits, const uint32_t *__restric
                     const double *__restrict__ lnf, rr_clq_rec *__restrict__ cand, unsigned long long cap,
                     unsigned long long *__restrict__ counter)
 {
-    extern __shared__ uint32_t clq_smem[];
+    RR_DYN_SMEM(uint32_t, clq_smem);
     const int nchunks = (W32 + 31) >> 5, W32p = nchunks << 5;
     uint32_t *qg = clq_smem;                          // [CLQ_QB][W32p] query group bitsets, zero padded
     uint32_t *qc = qg + (size_t)CLQ_QB * W32p;        // [CLQ_QB][W32p] coverage of the queries' sites
@@ -170,7 +170,7 @@ rr_k_cliquer_counts2(const uint32_t *__restrict__ bits, const uint32_t *__restri
                      const double *__restrict__ lnf, rr_clq_rec *__restrict__ cand, unsigned long long cap,
                      unsigned long long *__restrict__ counter)
 {
-    extern __shared__ uint32_t clq_smem[];
+    RR_DYN_SMEM(uint32_t, clq_smem);
     const int nchunks = (W32 + 31) >> 5, W32p = nchunks << 5;
     uint32_t *qg = clq_smem;
     uint32_t *qc = qg + (size_t)CLQ_QB2 * W32p;
@@ -258,7 +258,7 @@ rr_k_cliquer_counts2(const uint32_t *__restrict__ bits, const uint32_t *__restri
 }
 
 // EXPERIMENTAL (RR_CLIQUER_KERNEL=3), written from the profile of the one-step kernel (POPC pipe 62 % busy at 16 resident
-// warps) when the round's GPU minutes were spent - never run on a GPU, opt-in test only.  Same structure, three changes:
+// warps) when the round's GPU minutes were spent - never run on a GPU (its logic passes under the CPU emulation of tests/emu), opt-in GPU test only.  Same structure, three changes:
 //   * the groups of a site partition its coverage (rr_k_pack_bits), so the fifth group's counts are differences:
 //     |G4 & Gq| = |Ck & Gq| - sum of the other four, |G4 & Cq| = |Ck & Cq| - sum of the other four: 10 POPC and five
 //     loads per word instead of 12 and six;
@@ -271,7 +271,7 @@ rr_k_cliquer_counts3(const uint32_t *__restrict__ bits, const uint32_t *__restri
                      const double *__restrict__ lnf, rr_clq_rec *__restrict__ cand, unsigned long long cap,
                      unsigned long long *__restrict__ counter)
 {
-    extern __shared__ uint32_t clq_smem[];
+    RR_DYN_SMEM(uint32_t, clq_smem);
     const int nchunks = (W32 + 31) >> 5, W32p = nchunks << 5;
     uint32_t *qg = clq_smem;
     uint32_t *qc = qg + (size_t)CLQ_QB * W32p;
@@ -389,6 +389,7 @@ static size_t clq_smem_bytes3(int W32) { return clq_smem_bytes(W32, CLQ_QB) + ((
 
 size_t rr_cliquer_smem_bytes(int W32) { return std::max(clq_smem_bytes(W32, CLQ_QB2 > CLQ_QB ? CLQ_QB2 : CLQ_QB), clq_smem_bytes3(W32)); }
 
+#ifndef RR_CPU_EMU   // tests/emu compiles the kernels above with a host compiler; the launch syntax below is nvcc only
 cudaError_t rr_launch_cliquer(int kernel, const uint32_t *bits, const uint32_t *covbits, const int32_t *gsize, const double *lnf,
                               int W32, const int32_t *queries, int nq, int anfang, int ende, int min_s, double greedy,
                               double threshold, rr_clq_rec *cand, rr_clq_rec *hits, unsigned long long cap,
@@ -417,3 +418,4 @@ cudaError_t rr_launch_cliquer(int kernel, const uint32_t *bits, const uint32_t *
     rr_count_launch(2);
     return cudaGetLastError();
 }
+#endif

@@ -7,6 +7,11 @@
 struct rr_scan_params;
 extern "C" void rr_count_launch(int n);
 
+// the dynamic shared memory of a kernel (tests/emu substitutes a host buffer when it compiles kernel bodies on the CPU)
+#ifndef RR_DYN_SMEM
+#define RR_DYN_SMEM(type, name) extern __shared__ type name[]
+#endif
+
 // Device memory comes from the device's stream-ordered pool (cudaMallocAsync) with an unlimited release
 // threshold: packing the next MSA reuses the previous one's blocks instead of paying cudaMalloc/cudaFree of
 // multi-GB buffers (measured: 40-160 ms per pack/free cycle at config 2).  All work of a handle is on one

@@ -1,6 +1,6 @@
 // rr_kmeans.cu -- the read x read sweeps of Kmeans (/root/reference/RepeatResolver.c:2604-2821) on the device
 // ("the transposed Gram problem").  EXPERIMENTAL: written when the round's GPU minutes
-// were spent, never run on a GPU; its test is opt-in (RR_TEST_UNVALIDATED=1).  The integer rules are shared with the
+// were spent, never run on a GPU (the logic passes under the CPU emulation of tests/emu); its test is opt-in (RR_TEST_UNVALIDATED=1).  The integer rules are shared with the
 // host through rr_kmeans.h and pinned there against the unmodified reference (tests/test_oracle_kmeans.py).
 //
 // sig[anzahl][scv]: the signatures of the part's reads over the selected groups (64-bit words, padding 0).
@@ -25,7 +25,7 @@ __device__ __forceinline__ void km_stage(uint64_t *tile, const uint64_t *__restr
 __global__ void __launch_bounds__(KM_THREADS)
 rr_k_km_top5(const uint64_t *__restrict__ sig, int anzahl, int scv, int tile_reads, int32_t *__restrict__ best_j /*[anzahl][5]*/)
 {
-    extern __shared__ uint64_t km_smem[];
+    RR_DYN_SMEM(uint64_t, km_smem);
     uint64_t *tile = km_smem;                                   // [tile_reads][scv]
     const int i = blockIdx.x * KM_THREADS + threadIdx.x;
     const uint64_t *mine = sig + (size_t)min(i, anzahl - 1) * scv;   // idle threads still take part in the staging
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(KM_THREADS)
 rr_k_km_assign(const uint64_t *__restrict__ sig, const uint64_t *__restrict__ cen, int anzahl, int scv, int tile_reads,
                int32_t *__restrict__ cluster)
 {
-    extern __shared__ uint64_t km_smem[];
+    RR_DYN_SMEM(uint64_t, km_smem);
     uint64_t *tile = km_smem;
     const int i = blockIdx.x * KM_THREADS + threadIdx.x;
     const uint64_t *mine = sig + (size_t)min(i, anzahl - 1) * scv;
@@ -81,6 +81,7 @@ rr_k_km_assign(const uint64_t *__restrict__ sig, const uint64_t *__restrict__ ce
     if (i < anzahl) cluster[i] = best_j;
 }
 
+#ifndef RR_CPU_EMU   // tests/emu compiles the kernels above with a host compiler; the launch syntax below is nvcc only
 cudaError_t rr_launch_kmeans_sweeps(const uint64_t *sig, int anzahl, int scv, int32_t *best_j, uint64_t *cen, int32_t *cluster,
                                     cudaStream_t st)
 {
@@ -104,3 +105,4 @@ cudaError_t rr_launch_kmeans_sweeps(const uint64_t *sig, int anzahl, int scv, in
     rr_count_launch(3);
     return cudaGetLastError();
 }
+#endif

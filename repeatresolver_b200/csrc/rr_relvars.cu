@@ -1,6 +1,6 @@
 // rr_relvars.cu -- the all-pairs step of Relative_Vars (/root/reference/RepeatResolver.c:2455-2476) on the device
 // (SURVEY.md section 8f, row 3).  EXPERIMENTAL: selected with RR_RELVARS_KERNEL=1, written when the round's GPU minutes
-// were spent and not yet run on a GPU; the default path of rr_relative_vars (rr_abi.cu) uses rr_pair_counts instead.
+// were spent and not yet run on a GPU (its logic passes under the CPU emulation of tests/emu); the default path of rr_relative_vars (rr_abi.cu) uses rr_pair_counts instead.
 //
 // Input is the packed copy of the part's rows (rr_pack of the reads with Unterteilung == u_no), so a group bitset is
 // already G & U, its size |G & U|, and |Gi & Gj & U| (Triple_Schnitt 150-161) a plain AND+POPC of two rows of `bits`.
@@ -77,6 +77,7 @@ rr_k_relvars_pairs(const uint32_t *__restrict__ bits, int W32, const int32_t *__
         }
 }
 
+#ifndef RR_CPU_EMU   // tests/emu compiles the kernels above with a host compiler; the launch syntax below is nvcc only
 cudaError_t rr_launch_relvars_pairs(const uint32_t *bits, int W32, const int32_t *sel, int nsel, const int32_t *first_partner,
                                     const int32_t *gsize_u, int cov_u, const double *lnf, double cutoff, unsigned char *mark,
                                     int4 *unsure, unsigned int unsure_cap, unsigned int *unsure_count, cudaStream_t st)
@@ -88,3 +89,4 @@ cudaError_t rr_launch_relvars_pairs(const uint32_t *bits, int W32, const int32_t
     rr_count_launch(1);
     return cudaGetLastError();
 }
+#endif

@@ -1,0 +1,110 @@
+/* TEST INFRASTRUCTURE ONLY.  Builds the kernel bodies of csrc/rr_cliquer.cu, rr_relvars.cu and rr_kmeans.cu with a host
+ * compiler (see cuda_runtime.h in this directory) and exposes one C entry point per kernel that runs a whole grid, block
+ * after block, every CUDA thread a pthread.  tests/test_kernel_emulation.py feeds them and compares with the oracle. */
+#define RR_CPU_EMU 1
+#include "cuda_runtime.h"
+#include <vector>
+
+thread_local uint3 threadIdx, blockIdx;
+thread_local dim3 blockDim, gridDim;
+thread_local emu_block *emu_blk;
+
+extern "C" void rr_count_launch(int) {}
+alignas(16) unsigned char emu_dynamic_smem[256 << 10];
+#define RR_DYN_SMEM(type, name) type *name = (type *)emu_dynamic_smem
+
+#include "../../repeatresolver_b200/csrc/rr_cliquer.cu"
+#include "../../repeatresolver_b200/csrc/rr_relvars.cu"
+#include "../../repeatresolver_b200/csrc/rr_kmeans.cu"
+
+template <typename F>
+struct emu_job { F *body; emu_block *blk; dim3 grid, block; unsigned bx, by, tx; };
+
+template <typename F>
+static void *emu_thread(void *x)
+{
+    emu_job<F> *j = (emu_job<F> *)x;
+    threadIdx.x = j->tx; threadIdx.y = threadIdx.z = 0;
+    blockIdx.x = j->bx; blockIdx.y = j->by; blockIdx.z = 0;
+    blockDim = j->block; gridDim = j->grid;
+    emu_blk = j->blk;
+    (*j->body)();
+    return nullptr;
+}
+
+/* Run body() once per CUDA thread.  A thread that leaves the kernel early must not be waited for at a later barrier:
+ * the kernels here only return early block-uniformly or after their last barrier. */
+template <typename F>
+static void emu_launch(dim3 grid, unsigned threads, F body)
+{
+    const unsigned nwarps = (threads + 31) / 32;
+    for (unsigned by = 0; by < grid.y; by++)
+        for (unsigned bx = 0; bx < grid.x; bx++) {
+            emu_block blk;
+            std::vector<emu_warp> warps(nwarps);
+            pthread_barrier_init(&blk.bar, nullptr, threads);
+            for (unsigned w = 0; w < nwarps; w++) pthread_barrier_init(&warps[w].bar, nullptr, std::min(32u, threads - 32 * w));
+            blk.warps = warps.data();
+            std::vector<pthread_t> th(threads);
+            std::vector<emu_job<F>> jobs(threads);
+            pthread_attr_t attr;
+            pthread_attr_init(&attr);
+            pthread_attr_setstacksize(&attr, 256 << 10);
+            for (unsigned t = 0; t < threads; t++) {
+                jobs[t] = emu_job<F>{&body, &blk, grid, dim3(threads), bx, by, t};
+                pthread_create(&th[t], &attr, emu_thread<F>, &jobs[t]);
+            }
+            for (unsigned t = 0; t < threads; t++) pthread_join(th[t], nullptr);
+            pthread_attr_destroy(&attr);
+            pthread_barrier_destroy(&blk.bar);
+            for (unsigned w = 0; w < nwarps; w++) pthread_barrier_destroy(&warps[w].bar);
+        }
+}
+
+extern "C" {
+
+int emu_clq_qb(int kernel) { return kernel == 2 ? CLQ_QB2 : CLQ_QB; }
+int emu_clq_slab(void) { return CLQ_SLAB; }
+
+/* rr_launch_cliquer's grid, one of the three count kernels, then the score kernel */
+int emu_cliquer(int kernel, const uint32_t *bits, const uint32_t *covbits, const int32_t *gsize, const double *lnf, int W32,
+                const int32_t *queries, int nq, int anfang, int ende, int min_s, double greedy, double threshold,
+                rr_clq_rec *cand, rr_clq_rec *hits, unsigned long long cap, unsigned long long *counters)
+{
+    const int qb = kernel == 2 ? CLQ_QB2 : CLQ_QB;
+    const size_t smem = kernel == 3 ? clq_smem_bytes3(W32) : clq_smem_bytes(W32, qb);
+    if (smem > sizeof(emu_dynamic_smem) || nq <= 0 || ende <= anfang) return 1;
+    dim3 grid((unsigned)((nq + qb - 1) / qb), (unsigned)((ende - anfang + CLQ_SLAB - 1) / CLQ_SLAB));
+    if (kernel == 3)
+        emu_launch(grid, CLQ_WARPS * 32, [&] { rr_k_cliquer_counts3(bits, covbits, W32, queries, nq, anfang, ende, min_s, greedy, lnf, cand, cap, counters); });
+    else if (kernel == 2)
+        emu_launch(grid, CLQ_WARPS * 32, [&] { rr_k_cliquer_counts2(bits, covbits, W32, queries, nq, anfang, ende, min_s, greedy, lnf, cand, cap, counters); });
+    else
+        emu_launch(grid, CLQ_WARPS * 32, [&] { rr_k_cliquer_counts(bits, covbits, W32, queries, nq, anfang, ende, min_s, greedy, lnf, cand, cap, counters); });
+    emu_launch(dim3(3), 128, [&] { rr_k_cliquer_score(cand, cap, counters, queries, gsize, lnf, threshold, hits, counters + 1); });
+    return 0;
+}
+
+int emu_relvars_pairs(const uint32_t *bits, int W32, const int32_t *sel, int nsel, const int32_t *first_partner, const int32_t *gsize_u,
+                      int cov_u, const double *lnf, double cutoff, unsigned char *mark, int4 *unsure, unsigned unsure_cap,
+                      unsigned *unsure_count)
+{
+    if (nsel <= 0) return 0;
+    const unsigned nt = (unsigned)((nsel + RV_TILE - 1) / RV_TILE);
+    emu_launch(dim3(nt, nt), 256, [&] { rr_k_relvars_pairs(bits, W32, sel, nsel, first_partner, gsize_u, cov_u, lnf, cutoff, mark, unsure, unsure_cap, unsure_count); });
+    return 0;
+}
+
+/* rr_launch_kmeans_sweeps with a caller-chosen tile size, so that several tiles per sweep are exercised on small inputs */
+int emu_kmeans_sweeps(const uint64_t *sig, int anzahl, int scv, int tile_reads, int32_t *best_j, uint64_t *cen, int32_t *cluster)
+{
+    if (anzahl <= 0 || (size_t)tile_reads * scv * 8 > sizeof(emu_dynamic_smem)) return 1;
+    const unsigned nb = (unsigned)((anzahl + KM_THREADS - 1) / KM_THREADS);
+    emu_launch(dim3(nb), KM_THREADS, [&] { rr_k_km_top5(sig, anzahl, scv, tile_reads, best_j); });
+    const int64_t nw = (int64_t)anzahl * scv;
+    emu_launch(dim3((unsigned)((nw + 255) / 256)), 256, [&] { rr_k_km_centroids(sig, best_j, anzahl, scv, cen); });
+    emu_launch(dim3(nb), KM_THREADS, [&] { rr_k_km_assign(sig, cen, anzahl, scv, tile_reads, cluster); });
+    return 0;
+}
+
+}

@@ -1,0 +1,217 @@
+"""The kernel bodies of csrc/rr_cliquer.cu, rr_relvars.cu and rr_kmeans.cu, compiled by the HOST compiler against the
+stand-in CUDA header of tests/emu (every CUDA thread a pthread, __syncthreads and the warp primitives as barriers) and run
+on small inputs against the oracle.  This checks the kernels' logic - indexing, staging, skips, reductions, tails - on the
+CPU, in the build container, every round; it is test infrastructure, says nothing about speed and does not replace the GPU
+tests.  The two Cliquer count kernels that ARE validated on a B200 (tests/test_zz_gpu_cliquer.py) run here too: they pin the
+emulation itself.  For count kernel 3, the tiled Relative_Vars kernel and the Kmeans sweeps - written after the round's last
+GPU call - this is the only execution so far."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import repeatresolver_b200 as rr
+from conftest import ROOT, golden_msa
+import oracle_lib as O
+from test_oracle_cliquer import cliquer_cases
+from test_oracle_kmeans import kmeans_cases
+from test_oracle_relvars import partition_by_site, relvars_cases, window_codes
+
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+CSRC = os.path.join(ROOT, "repeatresolver_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    out = os.path.join(EMU_DIR, "_build", "libemu.so")
+    srcs = [os.path.join(EMU_DIR, f) for f in ("emu_driver.cpp", "cuda_runtime.h")] + \
+           [os.path.join(CSRC, f) for f in ("rr_cliquer.cu", "rr_relvars.cu", "rr_kmeans.cu", "rr_score.h", "rr_kmeans.h", "rr_kernels.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        # -Bsymbolic: librr_maxcorr.so (loaded RTLD_GLOBAL by the package) exports nvcc's host stubs under the very names of
+        # the kernels; the emulation must call its own bodies, not those stubs
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wl,-Bsymbolic", "-I" + EMU_DIR,
+                               "-I" + CSRC, "-o", out, os.path.join(EMU_DIR, "emu_driver.cpp"), "-lpthread"])
+    lib = C.CDLL(out)
+    vp, i, d, u64, u32 = C.c_void_p, C.c_int, C.c_double, C.c_ulonglong, C.c_uint
+    lib.emu_cliquer.argtypes = [i, vp, vp, vp, vp, i, vp, i, i, i, i, d, d, vp, vp, u64, vp]
+    lib.emu_relvars_pairs.argtypes = [vp, i, vp, i, vp, vp, i, vp, d, vp, vp, u32, vp]
+    lib.emu_kmeans_sweeps.argtypes = [vp, i, i, i, vp, vp, vp]
+    return lib
+
+
+def pack_bits(codes):
+    """the layout rr_k_pack_bits writes: bits[5N][W32], covbits[N][W32], bit r%32 of word r/32 = read r (any row order
+    gives the same counts), W32 a multiple of 4"""
+    R, N = codes.shape
+    W32 = 4 * ((R + 127) // 128)
+    member = np.zeros((5 * N, W32 * 32), dtype=np.uint8)
+    for k in range(5):
+        member[k::5, :R] = (codes == k).T
+    cover = np.zeros((N, W32 * 32), dtype=np.uint8)
+    cover[:, :R] = (codes < 5).T
+    as_words = lambda m: np.ascontiguousarray(np.packbits(m, axis=1, bitorder="little").view(np.uint32))
+    return as_words(member), as_words(cover), W32
+
+
+def two_family_msa(R, N, seed, variant_every=3):
+    """reads with random spans over N sites, two families that differ at every variant_every-th site, 4 % noise"""
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 4, N)
+    alt = (base + 1 + rng.integers(0, 3, N)) % 4
+    fam = rng.random(R) < 0.35
+    codes = np.where(fam[:, None] & (np.arange(N) % variant_every == 0)[None, :], alt[None, :], base[None, :]).astype(np.uint8)
+    noise = rng.random((R, N)) < 0.04
+    codes[noise] = rng.integers(0, 5, int(noise.sum()))
+    start = rng.integers(0, N // 2, R)
+    end = np.minimum(N - 1, start + rng.integers(N // 3, N, R))
+    col = np.arange(N)[None, :]
+    codes[(col < start[:, None]) | (col > end[:, None])] = 5
+    return codes[np.argsort(start, kind="stable")]
+
+
+def run_cliquer(emu, kernel, codes, queries, mincov, maxclique, greedy, anfang=0, ende=None):
+    o = O.Oracle.from_codes(codes)
+    bits, cov, W32 = pack_bits(codes)
+    gs = o.gsize().astype(np.int32)
+    lnf = rr.lnfact_table(codes.shape[0] + 2)
+    q = np.ascontiguousarray(queries, dtype=np.int32)
+    ende = codes.shape[1] if ende is None else ende
+    cap = len(q) * 5 * codes.shape[1]
+    cand = np.zeros(cap, dtype=rr.HIT_DTYPE)
+    hits = np.zeros(cap, dtype=rr.HIT_DTYPE)
+    counters = np.zeros(2, dtype=np.uint64)
+    thr = min(greedy - 1e-9 * max(1.0, abs(greedy)), 97.89)
+    rc = emu.emu_cliquer(kernel, bits.ctypes.data, cov.ctypes.data, gs.ctypes.data, lnf.ctypes.data, W32, q.ctypes.data, len(q),
+                         anfang, ende, mincov // 4, greedy, thr, cand.ctypes.data, hits.ctypes.data,
+                         cap, counters.ctypes.data)
+    assert rc == 0 and counters[1] <= counters[0] <= cap
+    cand, hits = cand[:int(counters[0])], hits[:int(counters[1])]
+    # every listed pair carries the oracle's four counts (argument order of 1217: Group1 = the candidate)
+    for h in cand[:: max(1, len(cand) // 200)]:
+        assert [h["s"], h["gr1"], h["gr2"], h["cov"]] == o.counts(int(h["group"]), int(q[h["slot"]])), h
+    members, scores, n = rr.cliquer_from_hits(q, hits, gs, mincov, maxclique, greedy)
+    return o, members, scores, n, len(cand), len(hits)
+
+
+@pytest.mark.parametrize("kernel", [1, 2, 3])
+def test_cliquer_count_kernels_on_the_golden_cases(emu, kernel):
+    for name in ("tree_small", "saturated"):
+        case = cliquer_cases()[name]
+        codes = window_codes(golden_msa(name), case["von"], case["bis"])[:, :330]       # a slab and a partial one
+        queries = [int(x) for x in case["queries"] if int(x) < 5 * codes.shape[1]][:5]
+        o, members, scores, n, nc, nh = run_cliquer(emu, kernel, codes, queries, case["mincov"], case["maxclique"], case["greedy"])
+        assert nh > 0
+        for k, qq in enumerate(queries):
+            m0, z0 = o.cliquer(qq, case["mincov"], case["maxclique"], case["greedy"])
+            assert list(members[k, :n[k]]) == list(m0) and np.array_equal(scores[k, :n[k]], z0), (name, qq)
+
+
+@pytest.mark.parametrize("kernel", [1, 2, 3])
+def test_cliquer_count_kernels_with_several_chunks_and_ragged_coverage(emu, kernel):
+    """more than 1024 reads = two 32-word chunks per bitset; spans so that chunks are skipped on either side"""
+    codes = two_family_msa(1300, 70, seed=41)
+    o = O.Oracle.from_codes(codes)
+    gs = o.gsize()
+    cand = np.flatnonzero((gs > 40) & (gs < 600))
+    queries = [int(x) for x in cand[:: len(cand) // 9][:9]] + [0]                      # 10 queries: partial last block
+    o, members, scores, n, nc, nh = run_cliquer(emu, kernel, codes, queries, 30, 8, 3.0)
+    sizes = set()
+    for k, qq in enumerate(queries):
+        m0, z0 = o.cliquer(qq, 30, 8, 3.0)
+        assert list(members[k, :n[k]]) == list(m0) and np.array_equal(scores[k, :n[k]], z0), qq
+        sizes.add(len(m0))
+    assert max(sizes) == 8 and nh > 50
+    # a sub-range of candidate columns
+    o, members, scores, n, _, _ = run_cliquer(emu, kernel, codes, queries[:3], 30, 5, 2.0, anfang=11, ende=52)
+    for k, qq in enumerate(queries[:3]):
+        m0, z0 = o.cliquer(qq, 30, 5, 2.0, 11, 52)
+        assert list(members[k, :n[k]]) == list(m0) and np.array_equal(scores[k, :n[k]], z0), qq
+
+
+def run_relvars(emu, codes, ut, u_no, M, cutoff, mingroup):
+    sub = np.ascontiguousarray(codes[ut == u_no])
+    cov_u = len(sub)
+    if cov_u < mingroup:
+        return np.zeros(0, dtype=np.int32), 0
+    bits, _, W32 = pack_bits(sub)
+    gu = np.stack([(sub == k).sum(0) for k in range(5)], 1).reshape(-1).astype(np.int32)
+    sel = rr.relative_vars_from_counts(M, gu, cov_u, cutoff, mingroup)
+    if len(sel) == 0:
+        return sel, 0
+    first = np.searchsorted(sel, sel + 100, side="left").astype(np.int32)
+    lnf = rr.lnfact_table(cov_u + 2)
+    mark = np.zeros(len(sel), dtype=np.uint8)
+    unsure = np.zeros((4096, 4), dtype=np.int32)
+    count = np.zeros(1, dtype=np.uint32)
+    emu.emu_relvars_pairs(bits.ctypes.data, W32, sel.ctypes.data, len(sel), first.ctypes.data, gu.ctypes.data, cov_u, lnf.ctypes.data,
+                          cutoff, mark.ctypes.data, unsure.ctypes.data, 4096, count.ctypes.data)
+    assert count[0] <= 4096
+    for a, b, s, _ in unsure[:int(count[0])]:                           # what rr_abi.cu does with the undecided pairs
+        if rr.relative_score_host(int(s), int(gu[sel[b]]), int(gu[sel[a]]), cov_u) > cutoff:
+            mark[a] = mark[b] = 1
+    return sel[mark > 0], int(count[0])
+
+
+def test_relvars_pair_kernel_on_the_golden_cases(emu):
+    checked = 0
+    for name, case in sorted(relvars_cases().items()):
+        codes = window_codes(golden_msa(name), case["von"], case["bis"])
+        o = O.Oracle.from_codes(codes)
+        M, _, _ = o.scan(case["mincov"])
+        ut, _ = partition_by_site(codes, M)
+        for u_no, want in case["parts"].items():
+            got, _ = run_relvars(emu, codes, ut, int(u_no), M, case["cutoff"], case["mingroup"])
+            assert list(got) == want["vars"], (name, u_no)
+            checked += len(got) > 0
+    assert checked >= 4
+
+
+def test_relvars_pair_kernel_with_several_chunks_and_a_cutoff_hit_exactly(emu):
+    codes = two_family_msa(1200, 90, seed=43, variant_every=4)
+    o = O.Oracle.from_codes(codes)
+    rng = np.random.default_rng(2)
+    M = np.where(rng.random(5 * codes.shape[1]) < 0.8, 9.0, 0.0)
+    ut = (rng.random(codes.shape[0]) < 0.1).astype(np.int32)             # part 0 holds ~1080 reads: two chunks
+    for cutoff, mingroup in ((3.0, 8), (8.5, 30)):
+        got, _ = run_relvars(emu, codes, ut, 0, M, cutoff, mingroup)
+        want = o.relative_vars(ut, 0, M, cutoff, mingroup)
+        assert list(got) == list(want) and len(want) > 5, (cutoff, mingroup)
+    # a cutoff equal to a score that occurs: the pair is undecided on the device and settled by the host (Z > cutoff is strict)
+    sub = codes[ut == 0]
+    gu = np.stack([(sub == k).sum(0) for k in range(5)], 1).reshape(-1)
+    sel = rr.relative_vars_from_counts(M, gu, len(sub), 3.0, 8)
+    a, b = int(sel[0]), int(sel[np.searchsorted(sel, sel[0] + 100)])
+    ga, gb = sub[:, a // 5] == a % 5, sub[:, b // 5] == b % 5
+    z = O.relative_score(int((ga & gb).sum()), int(gb.sum()), int(ga.sum()), len(sub))
+    if z > 0.5:
+        got, undecided = run_relvars(emu, codes, ut, 0, M, z, 8)
+        assert list(got) == list(o.relative_vars(ut, 0, M, z, 8)) and undecided >= 1
+
+
+@pytest.mark.parametrize("tile_reads", [5, 64])
+def test_kmeans_sweeps_on_the_golden_cases(emu, tile_reads):
+    for name in sorted(kmeans_cases()):
+        rel = relvars_cases()[name]
+        codes = window_codes(golden_msa(name), rel["von"], rel["bis"])
+        o = O.Oracle.from_codes(codes)
+        M, _, _ = o.scan(rel["mincov"])
+        ut, _ = partition_by_site(codes, M)
+        msa = rr.MSA.from_cells(codes, codes=True)
+        for key, want in kmeans_cases()[name].items():
+            u_no, mingroup = (int(x) for x in key.split("/"))
+            reads, sig = rr.kmeans_signatures(msa, ut, u_no, rel["parts"][str(u_no)]["vars"])
+            n, scv = sig.shape
+            best_j = np.zeros((n, 5), dtype=np.int32)
+            cen = np.zeros_like(sig)
+            cluster = np.zeros(n, dtype=np.int32)
+            assert emu.emu_kmeans_sweeps(sig.ctypes.data, n, scv, tile_reads, best_j.ctypes.data, cen.ctypes.data, cluster.ctypes.data) == 0
+            for i in range(0, n, max(1, n // 10)):
+                assert list(best_j[i]) == list(rr.kmeans_top5_host(sig, i))
+            final, split = rr.kmeans_finish(sig, cen, cluster, mingroup)
+            after = ut.copy()
+            after[reads] = final + ut.max() + 1
+            assert split == want["split"] and list(after) == want["after"], (name, key)
+        msa.close()
