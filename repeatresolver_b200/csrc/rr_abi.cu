@@ -619,21 +619,25 @@ static void clq_finalize(const int32_t *queries, int n, std::vector<rr_clq_rec> 
                          int maxclique, double greedy, int32_t *members, double *scores, int32_t *n_members, long long *evals_out)
 {
     const int K = maxclique - 1;
-    std::sort(hits.begin(), hits.end(), [](const rr_clq_rec &a, const rr_clq_rec &b) {
-        return a.slot != b.slot ? a.slot < b.slot : a.group < b.group;
-    });
+    // bucket the hits by query slot (one linear pass; the device appends them in no particular order)
     std::vector<int64_t> first((size_t)n + 1, 0);
     for (const rr_clq_rec &h : hits) first[(size_t)h.slot + 1]++;
     for (int i = 0; i < n; i++) first[(size_t)i + 1] += first[i];
+    std::vector<rr_clq_rec> by_slot(hits.size());
+    {
+        std::vector<int64_t> fill(first.begin(), first.end() - 1);
+        for (const rr_clq_rec &h : hits) by_slot[(size_t)fill[h.slot]++] = h;
+    }
     std::atomic<int> next{0};
     std::atomic<long long> evals{0};
     auto work = [&]() {
         std::vector<double> zs;
+        std::vector<rr_clq_rec> keep;
         std::vector<int32_t> g, c, sz;
         for (;;) {
             const int i = next.fetch_add(1);
             if (i >= n) return;
-            const rr_clq_rec *h = hits.data() + first[i];
+            const rr_clq_rec *h = by_slot.data() + first[i];
             const int64_t nh = first[(size_t)i + 1] - first[i];
             if (nh == 0 || K < 1) continue;
             double cut = -HUGE_VAL;
@@ -643,12 +647,16 @@ static void clq_finalize(const int32_t *queries, int n, std::vector<rr_clq_rec> 
                 std::nth_element(zs.begin(), zs.begin() + (K - 1), zs.end(), std::greater<double>());
                 cut = zs[K - 1] - 1e-9 * std::max(1.0, std::fabs(zs[K - 1]));
             }
+            keep.clear();
+            for (int64_t k = 0; k < nh; k++)
+                if (!(h[k].z < cut && h[k].z < 97.89)) keep.push_back(h[k]);
+            // candidates in ascending group order: equal scores keep the earlier group (TheBestUpdater, 1156-1176)
+            std::sort(keep.begin(), keep.end(), [](const rr_clq_rec &a, const rr_clq_rec &b) { return a.group < b.group; });
             g.clear(); c.clear(); sz.clear();
-            for (int64_t k = 0; k < nh; k++) {
-                if (h[k].z < cut && h[k].z < 97.89) continue;
-                g.push_back(h[k].group);
-                c.push_back(h[k].s); c.push_back(h[k].gr1); c.push_back(h[k].gr2); c.push_back(h[k].cov);
-                sz.push_back(gsize[h[k].group]);
+            for (const rr_clq_rec &r : keep) {
+                g.push_back(r.group);
+                c.push_back(r.s); c.push_back(r.gr1); c.push_back(r.gr2); c.push_back(r.cov);
+                sz.push_back(gsize[r.group]);
             }
             int m = 0;
             clq_select(queries[i], (int64_t)g.size(), g.data(), c.data(), sz.data(), gsize[queries[i]], mincov, maxclique, greedy, 1,
