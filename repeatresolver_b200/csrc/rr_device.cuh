@@ -44,6 +44,7 @@ struct rr_scan_params {
     int n_colblocks;
 };
 
+#ifndef RR_CPU_EMU
 __device__ __forceinline__ rr_best_t rr_best_load(const rr_best_t *p)
 {
     rr_best_t v;
@@ -74,6 +75,14 @@ __device__ __forceinline__ bool rr_cas128(rr_best_t *addr, rr_best_t expected, r
     old->p = o1;
     return o0 == expected.z && o1 == expected.p;
 }
+
+#else
+// tests/emu compiles the kernel bodies with a host compiler: the three PTX helpers above as plain C++ behind one lock
+// (same semantics: 16-byte load, 8-byte load, 16-byte compare-and-swap returning the old value)
+rr_best_t rr_best_load(const rr_best_t *p);
+double rr_best_value(const rr_best_t *p);
+bool rr_cas128(rr_best_t *addr, rr_best_t expected, rr_best_t desired, rr_best_t *old);
+#endif
 
 // M[g] = max(M[g], Z) with strict > (MaxCorrelation.c:822-823); among equal values the
 // smallest partner id is kept.  Z must be > 0 (NaN and -0.0 never win).

@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(BS_TI * 32, 2) rr_k_scan_bitset(const rr_scan_
     }
 }
 
+#ifndef RR_CPU_EMU   // tests/emu compiles rr_k_scan_bitset above with a host compiler; the launch syntax below is nvcc only
 __global__ void rr_k_init_best(rr_best_t *best, int64_t n)
 {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -195,6 +196,8 @@ cudaError_t rr_launch_scan_bitset(const rr_scan_params &P, int n_sm, cudaStream_
     rr_count_launch(1);
     return cudaGetLastError();
 }
+
+#endif
 
 int rr_bitset_ti(void) { return BS_TI; }
 int rr_bitset_tj(void) { return BS_TJ; }

@@ -25,6 +25,8 @@ static inline int4 make_int4(int x, int y, int z, int w) { int4 v = {x, y, z, w}
 #define __forceinline__ inline
 #define __shared__ static            /* one block runs at a time */
 #define __launch_bounds__(...)
+#define __noinline__
+#define __align__(n) alignas(n)
 
 struct emu_warp { pthread_barrier_t bar; unsigned long long buf[32]; };
 struct emu_block { pthread_barrier_t bar; emu_warp *warps; };
@@ -56,6 +58,29 @@ static inline unsigned __reduce_add_sync(unsigned, unsigned v)
     pthread_barrier_wait(&w->bar);
     return s;
 }
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int lane_mask)
+{
+    static_assert(sizeof(T) <= 8, "one 64-bit slot per lane");
+    emu_warp *w = emu_my_warp();
+    unsigned long long raw = 0;
+    memcpy(&raw, &v, sizeof(T));
+    w->buf[threadIdx.x & 31] = raw;
+    pthread_barrier_wait(&w->bar);
+    raw = w->buf[(threadIdx.x & 31) ^ (unsigned)lane_mask];
+    pthread_barrier_wait(&w->bar);
+    T out;
+    memcpy(&out, &raw, sizeof(T));
+    return out;
+}
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
+static inline void __syncwarp() { pthread_barrier_wait(&emu_my_warp()->bar); }
+static inline unsigned __activemask() { return 0xffffffffu; }     /* only meaningful where the whole warp is active */
+static inline long long __double_as_longlong(double d) { long long x; memcpy(&x, &d, 8); return x; }
+static inline double __longlong_as_double(long long x) { double d; memcpy(&d, &x, 8); return d; }
+static inline float __fdividef(float a, float b) { return a / b; }
+static inline float emu_log2f(float x) { return log2f(x); }
+#define __log2f emu_log2f             /* glibc declares a __log2f of its own */
+static inline float __double2float_rd(double d) { float f = (float)d; return (double)f > d ? nextafterf(f, -INFINITY) : f; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }

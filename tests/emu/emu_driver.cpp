@@ -13,9 +13,25 @@ extern "C" void rr_count_launch(int) {}
 alignas(16) unsigned char emu_dynamic_smem[256 << 10];
 #define RR_DYN_SMEM(type, name) type *name = (type *)emu_dynamic_smem
 
+#include <mutex>
+#include "../../repeatresolver_b200/csrc/rr_plan.cpp"           /* the host plan, as rr_scan builds it */
+#include "../../repeatresolver_b200/csrc/rr_scan_bitset.cu"
 #include "../../repeatresolver_b200/csrc/rr_cliquer.cu"
 #include "../../repeatresolver_b200/csrc/rr_relvars.cu"
 #include "../../repeatresolver_b200/csrc/rr_kmeans.cu"
+
+/* the three PTX helpers of rr_device.cuh (16-byte load, 8-byte load, 16-byte compare-and-swap) behind one lock */
+static std::mutex emu_best_lock;
+rr_best_t rr_best_load(const rr_best_t *p) { std::lock_guard<std::mutex> g(emu_best_lock); return *p; }
+double rr_best_value(const rr_best_t *p) { std::lock_guard<std::mutex> g(emu_best_lock); return __longlong_as_double((long long)p->z); }
+bool rr_cas128(rr_best_t *addr, rr_best_t expected, rr_best_t desired, rr_best_t *old)
+{
+    std::lock_guard<std::mutex> g(emu_best_lock);
+    *old = *addr;
+    if (old->z != expected.z || old->p != expected.p) return false;
+    *addr = desired;
+    return true;
+}
 
 template <typename F>
 struct emu_job { F *body; emu_block *blk; dim3 grid, block; unsigned bx, by, tx; };
@@ -62,6 +78,31 @@ static void emu_launch(dim3 grid, unsigned threads, F body)
 }
 
 extern "C" {
+
+/* The AND+POPC variant of the scan, set up as rr_scan (rr_abi.cu) sets it up: plan from the spans in rank order, then
+ * rr_k_scan_bitset over `blocks` persistent blocks.  bits/gsize/coverage in rank order as rr_pack leaves them; best:
+ * [5N] {value bits, partner}; counters: [8]; returns the plan's pair count (what the device count must equal). */
+long long emu_scan_bitset(int R, int N, int W32, int mincov, unsigned flags, const uint32_t *bits, const int32_t *gsize,
+                          const int32_t *coverage, const int32_t *breakcol, const int32_t *start, const int32_t *end,
+                          int class_split, const double *lnfact, rr_best_t *best, unsigned long long *counters, int blocks,
+                          int part_index, int part_count)
+{
+    rr_plan plan;
+    rr_plan_build(plan, R, N, mincov, gsize, coverage, breakcol, start, end, class_split, rr_bitset_ti(), rr_bitset_tj(), 32, 8, 0,
+                  part_index, part_count);
+    rr_scan_params P;
+    memset(&P, 0, sizeof P);
+    P.R = R; P.N = N; P.W32 = W32; P.mincov = mincov; P.flags = flags;
+    P.bits = bits; P.gsize = gsize; P.rowok = plan.rowok.data(); P.colok = plan.colok.data();
+    P.breakcol = breakcol; P.rowsites = plan.rowsites.data(); P.n_rowsites = plan.n_rowsites;
+    P.lnfact = lnfact; P.best = best; P.counters = counters;
+    P.unit_prefix = plan.unit_prefix.data(); P.unit_cb0 = plan.unit_cb0.data(); P.n_rowblocks = plan.n_rowblocks;
+    P.rb_lo = plan.rb_lo; P.rb_hi = plan.rb_hi; P.word_hi = plan.k_hi.data(); P.word_lo = plan.k_lo.data();
+    P.n_colblocks = plan.n_colblocks;
+    if (plan.rb_hi > plan.rb_lo && plan.unit_prefix[plan.rb_hi] > plan.unit_prefix[plan.rb_lo])
+        emu_launch(dim3((unsigned)blocks), BS_TI * 32, [&] { rr_k_scan_bitset(P); });
+    return (long long)plan.part_pairs;
+}
 
 int emu_clq_qb(int kernel) { return kernel == 2 ? CLQ_QB2 : CLQ_QB; }
 int emu_clq_slab(void) { return CLQ_SLAB; }

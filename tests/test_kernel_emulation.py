@@ -1,4 +1,5 @@
-"""The kernel bodies of csrc/rr_cliquer.cu, rr_relvars.cu and rr_kmeans.cu, compiled by the HOST compiler against the
+"""The kernel bodies of csrc/rr_scan_bitset.cu (the AND+POPC variant of the hot path with the fused epilogue of
+rr_device.cuh), rr_cliquer.cu, rr_relvars.cu and rr_kmeans.cu, compiled by the HOST compiler against the
 stand-in CUDA header of tests/emu (every CUDA thread a pthread, __syncthreads and the warp primitives as barriers) and run
 on small inputs against the oracle.  This checks the kernels' logic - indexing, staging, skips, reductions, tails - on the
 CPU, in the build container, every round; it is test infrastructure, says nothing about speed and does not replace the GPU
@@ -215,3 +216,91 @@ def test_kmeans_sweeps_on_the_golden_cases(emu, tile_reads):
             after[reads] = final + ut.max() + 1
             assert split == want["split"] and list(after) == want["after"], (name, key)
         msa.close()
+
+
+# ---- the AND+POPC variant of the scan itself (rr_k_scan_bitset with the fused epilogue of rr_device.cuh) ---------------
+def ranked(codes):
+    """rows in the order rr_pack leaves them: (length class, span start, span end); returns codes, start, end, class_split"""
+    R, N = codes.shape
+    cov = codes < 5
+    start = cov.argmax(1).astype(np.int32)
+    end = (N - 1 - cov[:, ::-1].argmax(1)).astype(np.int32)
+    split = (R * 3 // 4 // 256 * 256) if R >= 1024 else 0
+    cls = np.ones(R, dtype=np.int64)
+    if split:
+        by_len = np.lexsort((np.arange(R), start, end - start))          # stable: (length, start, original order)
+        cls[by_len[:split]] = 0
+    perm = np.lexsort((np.arange(R), end, start, cls))
+    return np.ascontiguousarray(codes[perm]), start[perm].copy(), end[perm].copy(), split
+
+
+def run_scan_bitset(emu, codes, mincov, flags=0, blocks=3, part=(0, 1)):
+    rc, start, end, split = ranked(codes)
+    R, N = rc.shape
+    bits, _, W32 = pack_bits(rc)
+    gs = np.stack([(rc == k).sum(0) for k in range(5)], 1).reshape(-1).astype(np.int32)
+    coverage = (rc < 5).sum(0).astype(np.int32)
+    brk = np.ascontiguousarray(rr.breakcols_from_spans(start, end, N, mincov), dtype=np.int32)
+    lnf = rr.lnfact_table(R + 2)
+    best = np.zeros(5 * N, dtype=[("z", "<u8"), ("p", "<u8")])
+    best["p"] = np.uint64(2 ** 64 - 1)
+    counters = np.zeros(8, dtype=np.uint64)
+    pairs = emu.emu_scan_bitset(R, N, W32, mincov, flags, bits.ctypes.data, gs.ctypes.data, coverage.ctypes.data, brk.ctypes.data,
+                                start.ctypes.data, end.ctypes.data, split, lnf.ctypes.data, best.ctypes.data, counters.ctypes.data,
+                                blocks, part[0], part[1])
+    M = best["z"].view(np.float64).copy()
+    A = np.where(best["p"] == np.uint64(2 ** 64 - 1), -1, best["p"].astype(np.int64)).astype(np.int32)
+    return M, A, int(pairs), counters
+
+
+@pytest.fixture(scope="module")
+def emu_scan(emu):
+    vp, i, u32 = C.c_void_p, C.c_int, C.c_uint
+    emu.emu_scan_bitset.restype = C.c_longlong
+    emu.emu_scan_bitset.argtypes = [i, i, i, i, u32, vp, vp, vp, vp, vp, vp, i, vp, vp, vp, i, i, i]
+    return emu
+
+
+@pytest.mark.parametrize("name,cov", [("kat_appendix_g", 20), ("kat_appendix_g", 44), ("tree_small", 10), ("ragged", 20)])
+def test_bitset_scan_kernel_on_golden_cases(emu_scan, name, cov, tmp_path):
+    """the hot path's second implementation, kernel body and fused epilogue, on the CPU against the oracle: pair count,
+    maxima (same libm on both sides: equal as doubles), arg-max; with and without pruning"""
+    text = golden_msa(name)
+    o = O.Oracle.from_text(text, tmp_path)
+    msa = rr.MSA.from_text(text)
+    cells = msa.cells().copy()
+    table = np.full(256, 5, dtype=np.uint8)
+    for ch, k in ((b"aA", 0), (b"cC", 1), (b"gG", 2), (b"tT", 3), (b"-_", 4)):
+        for c in ch:
+            table[c] = k
+    codes = table[cells]
+    msa.close()
+    M0, A0, P0 = o.scan(cov)
+    for flags in (0, rr.FLAG_NO_PRUNE):
+        M, A, pairs, counters = run_scan_bitset(emu_scan, codes, cov, flags)
+        assert pairs == P0 and int(counters[0]) == P0
+        assert np.array_equal(M, M0), np.abs(M - M0).max()
+        assert np.array_equal(A, A0)
+        if flags:
+            assert int(counters[1]) >= int((M0 > 0).sum()) // 2            # exact evaluations happened
+
+
+def test_bitset_scan_kernel_two_length_classes_and_parts(emu_scan):
+    """1 300 reads: two length classes of rows (class split at 768), word ranges per class, and a two-way partition of the
+    row blocks whose element-wise max (ties to the smaller partner) is the full result"""
+    codes = two_family_msa(1300, 75, seed=47)
+    assert ranked(codes)[3] == 768
+    o = O.Oracle.from_codes(codes)
+    M0, A0, P0 = o.scan(30)
+    assert (M0 > 0).sum() > 50
+    M, A, pairs, counters = run_scan_bitset(emu_scan, codes, 30)
+    assert pairs == P0 == int(counters[0]) and np.array_equal(M, M0) and np.array_equal(A, A0)
+    assert int(counters[1]) < P0                                          # pruning skipped exact evaluations
+    Mm, Am, Pm = np.zeros_like(M0), np.full_like(A0, -1), 0
+    for part in range(2):
+        Mp, Ap, pp, cp = run_scan_bitset(emu_scan, codes, 30, part=(part, 2))
+        assert pp == int(cp[0])
+        better = (Mp > Mm) | ((Mp == Mm) & (Mp > 0) & (Ap >= 0) & ((Am < 0) | (Ap < Am)))
+        Mm, Am = np.where(better, Mp, Mm), np.where(better, Ap, Am)
+        Pm += pp
+    assert Pm == P0 and np.array_equal(Mm, M0) and np.array_equal(Am, A0)
