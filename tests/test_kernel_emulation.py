@@ -304,3 +304,23 @@ def test_bitset_scan_kernel_two_length_classes_and_parts(emu_scan):
         Mm, Am = np.where(better, Mp, Mm), np.where(better, Ap, Am)
         Pm += pp
     assert Pm == P0 and np.array_equal(Mm, M0) and np.array_equal(Am, A0)
+
+
+def test_bitset_scan_kernel_on_a_window_of_the_real_pipeline_msa(emu_scan):
+    """1 000 columns from the middle of the MSA the reference's own pipeline produced (tests/golden/real_pipeline_msareal):
+    real coverage structure - 312 reads with spans of 20 to 15 909 columns, a third of the cells blank"""
+    text = golden_msa("real_pipeline_msareal")
+    rows = text.split(b"\n")[:-1]
+    cells = np.frombuffer(b"".join(rows), dtype=np.uint8).reshape(len(rows), -1)[:, 9000:10000]
+    table = np.full(256, 5, dtype=np.uint8)
+    for ch, k in ((b"aA", 0), (b"cC", 1), (b"gG", 2), (b"tT", 3), (b"-_", 4)):
+        for c in ch:
+            table[c] = k
+    codes = table[cells]
+    codes = np.ascontiguousarray(codes[(codes < 5).any(1)])              # reads that reach the window
+    assert codes.shape[0] > 150
+    o = O.Oracle.from_codes(codes)
+    M0, A0, P0 = o.scan(30)
+    assert P0 > 2e5 and (M0 > 3).sum() > 20
+    M, A, pairs, counters = run_scan_bitset(emu_scan, codes, 30, blocks=4)
+    assert pairs == P0 == int(counters[0]) and np.array_equal(M, M0) and np.array_equal(A, A0)
