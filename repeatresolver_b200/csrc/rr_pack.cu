@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(256) rr_k_pack_int8(const uint8_t *__restrict_
     }
 }
 
+#ifndef RR_CPU_EMU   // tests/emu compiles the kernels above with a host compiler; the launch syntax below is nvcc only
 // ---- launchers -------------------------------------------------------------------------
 cudaError_t rr_launch_row_spans(const uint8_t *cells, int R, int N, int codes, int32_t *start, int32_t *end,
                                 int32_t *ncov, cudaStream_t st)
@@ -274,3 +275,4 @@ cudaError_t rr_launch_pack_int8(const uint8_t *cells, const int32_t *perm, int R
     rr_count_launch(1);
     return cudaGetLastError();
 }
+#endif

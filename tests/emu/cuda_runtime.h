@@ -17,6 +17,8 @@ enum { cudaSuccess = 0, cudaErrorInvalidValue = 1 };
 struct uint3 { unsigned x, y, z; };
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct int4 { int x, y, z, w; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 v = {x, y, z, w}; return v; }
 static inline int4 make_int4(int x, int y, int z, int w) { int4 v = {x, y, z, w}; return v; }
 
 #define __global__

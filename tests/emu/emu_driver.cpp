@@ -15,6 +15,7 @@ alignas(16) unsigned char emu_dynamic_smem[256 << 10];
 
 #include <mutex>
 #include "../../repeatresolver_b200/csrc/rr_plan.cpp"           /* the host plan, as rr_scan builds it */
+#include "../../repeatresolver_b200/csrc/rr_pack.cu"
 #include "../../repeatresolver_b200/csrc/rr_scan_bitset.cu"
 #include "../../repeatresolver_b200/csrc/rr_cliquer.cu"
 #include "../../repeatresolver_b200/csrc/rr_relvars.cu"
@@ -78,6 +79,36 @@ static void emu_launch(dim3 grid, unsigned threads, F body)
 }
 
 extern "C" {
+
+/* the packing kernels of rr_pack.cu with the grids their launchers use */
+void emu_row_spans(const uint8_t *cells, int R, int N, int codes, int32_t *start, int32_t *end, int32_t *ncov)
+{
+    if (R > 0) emu_launch(dim3((unsigned)R), 256, [&] { rr_k_row_spans(cells, R, N, codes, start, end, ncov); });
+}
+void emu_pack_bits(const uint8_t *cells, const int32_t *perm, int R, int N, int codes, uint32_t *bits, uint32_t *covbits, int W32)
+{
+    if (N <= 0 || W32 <= 0) return;
+    emu_launch(dim3((unsigned)((N + PK_COLS - 1) / PK_COLS), (unsigned)(W32 / 4)), PK_COLS,
+               [&] { rr_k_pack_bits(cells, perm, R, N, codes, bits, covbits, W32); });
+}
+void emu_bitset_sizes(const uint32_t *sets, long long nsets, int W32, int32_t *sizes)
+{
+    if (nsets > 0) emu_launch(dim3((unsigned)((nsets + 7) / 8)), 256, [&] { rr_k_bitset_sizes(sets, nsets, W32, sizes); });
+}
+void emu_pair_counts(const uint32_t *bits, const uint32_t *covbits, int W32, long long n, const int32_t *gi, const int32_t *gj, int32_t *out)
+{
+    if (n > 0) emu_launch(dim3((unsigned)((n + 7) / 8)), 256, [&] { rr_k_pair_counts(bits, covbits, W32, n, gi, gj, out); });
+}
+void emu_general_break(const uint32_t *covbits, int W32, int N, int mincov, int32_t *breakcol)
+{
+    if (N > 0) emu_launch(dim3((unsigned)((N + 7) / 8)), 256, [&] { rr_k_general_break(covbits, W32, N, mincov, breakcol); });
+}
+void emu_pack_int8(const uint8_t *cells, const int32_t *perm, int R, int N, int codes, int8_t *xb, long long Kp, int fp4)
+{
+    if (N <= 0 || Kp <= 0) return;
+    emu_launch(dim3((unsigned)((N + PX_COLS - 1) / PX_COLS), (unsigned)(Kp / PX_ROWS)), 256,
+               [&] { rr_k_pack_int8(cells, perm, R, N, codes, xb, Kp, fp4); });
+}
 
 /* The AND+POPC variant of the scan, set up as rr_scan (rr_abi.cu) sets it up: plan from the spans in rank order, then
  * rr_k_scan_bitset over `blocks` persistent blocks.  bits/gsize/coverage in rank order as rr_pack leaves them; best:

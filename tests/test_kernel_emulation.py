@@ -324,3 +324,117 @@ def test_bitset_scan_kernel_on_a_window_of_the_real_pipeline_msa(emu_scan):
     assert P0 > 2e5 and (M0 > 3).sum() > 20
     M, A, pairs, counters = run_scan_bitset(emu_scan, codes, 30, blocks=4)
     assert pairs == P0 == int(counters[0]) and np.array_equal(M, M0) and np.array_equal(A, A0)
+
+
+# ---- the packing kernels (rr_pack.cu) and the whole device pipeline of the bitset variant ---------------------------------
+@pytest.fixture(scope="module")
+def emu_pack(emu_scan):
+    vp, i, i64 = C.c_void_p, C.c_int, C.c_longlong
+    e = emu_scan
+    e.emu_row_spans.argtypes = [vp, i, i, i, vp, vp, vp]
+    e.emu_pack_bits.argtypes = [vp, vp, i, i, i, vp, vp, i]
+    e.emu_bitset_sizes.argtypes = [vp, i64, i, vp]
+    e.emu_pair_counts.argtypes = [vp, vp, i, i64, vp, vp, vp]
+    e.emu_general_break.argtypes = [vp, i, i, i, vp]
+    e.emu_pack_int8.argtypes = [vp, vp, i, i, i, vp, i64, i]
+    return e
+
+
+def device_pack(e, cells, codes_flag):
+    """what pack_impl (rr_abi.cu) does, with the kernels emulated: spans -> row order -> bitsets -> sizes"""
+    cells = np.ascontiguousarray(cells, dtype=np.uint8)
+    R, N = cells.shape
+    start, end, ncov = (np.zeros(R, dtype=np.int32) for _ in range(3))
+    e.emu_row_spans(cells.ctypes.data, R, N, codes_flag, start.ctypes.data, end.ctypes.data, ncov.ctypes.data)
+    split = (R * 3 // 4 // 256 * 256) if R >= 1024 else 0
+    cls = np.ones(R, dtype=np.int64)
+    if split:
+        cls[np.lexsort((np.arange(R), start, end - start))[:split]] = 0
+    perm = np.lexsort((np.arange(R), end, start, cls)).astype(np.int32)
+    W32 = 4 * ((R + 127) // 128)
+    bits = np.zeros((5 * N, W32), dtype=np.uint32)
+    cov = np.zeros((N, W32), dtype=np.uint32)
+    e.emu_pack_bits(cells.ctypes.data, perm.ctypes.data, R, N, codes_flag, bits.ctypes.data, cov.ctypes.data, W32)
+    gs = np.zeros(5 * N, dtype=np.int32)
+    cv = np.zeros(N, dtype=np.int32)
+    e.emu_bitset_sizes(bits.ctypes.data, 5 * N, W32, gs.ctypes.data)
+    e.emu_bitset_sizes(cov.ctypes.data, N, W32, cv.ctypes.data)
+    return dict(R=R, N=N, W32=W32, start=start, end=end, ncov=ncov, perm=perm, split=split, bits=bits, cov=cov, gs=gs, cv=cv)
+
+
+def test_packing_kernels_on_raw_text(emu_pack, tmp_path):
+    """raw characters (lower case, '_' gaps, junk) through rr_k_row_spans / rr_k_pack_bits / rr_k_bitset_sizes /
+    rr_k_pair_counts / rr_k_general_break / rr_k_pack_int8 against numpy and the oracle"""
+    text = golden_msa("ragged")
+    o = O.Oracle.from_text(text, tmp_path)
+    msa = rr.MSA.from_text(text)
+    cells = msa.cells().copy()
+    msa.close()
+    table = np.full(256, 5, dtype=np.uint8)
+    for ch, k in ((b"aA", 0), (b"cC", 1), (b"gG", 2), (b"tT", 3), (b"-_", 4)):
+        for c in ch:
+            table[c] = k
+    codes = table[cells]
+    p = device_pack(emu_pack, cells, 0)
+    covd = codes < 5
+    assert np.array_equal(p["start"], covd.argmax(1)) and np.array_equal(p["end"], codes.shape[1] - 1 - covd[:, ::-1].argmax(1))
+    assert np.array_equal(p["ncov"], covd.sum(1))
+    want_bits, want_cov, W32 = pack_bits(codes[p["perm"]])
+    assert W32 == p["W32"] and np.array_equal(p["bits"], want_bits) and np.array_equal(p["cov"], want_cov)
+    assert np.array_equal(p["gs"], o.gsize()) and np.array_equal(p["cv"], o.coverage())
+    # the four counts of explicit pairs
+    rng = np.random.default_rng(3)
+    gi = rng.integers(0, 5 * p["N"], 300).astype(np.int32)
+    gj = rng.integers(0, 5 * p["N"], 300).astype(np.int32)
+    out = np.zeros((300, 4), dtype=np.int32)
+    emu_pack.emu_pair_counts(p["bits"].ctypes.data, p["cov"].ctypes.data, W32, 300, gi.ctypes.data, gj.ctypes.data, out.ctypes.data)
+    for k in range(0, 300, 3):
+        assert list(out[k]) == o.counts(int(gi[k]), int(gj[k]))
+    # the general first-break kernel against the closed form for single-span rows
+    # (on the first 90 sites only: a warp walks the columns one shuffle reduction at a time, slow under emulation)
+    n90 = 90
+    brk = np.zeros(n90, dtype=np.int32)
+    emu_pack.emu_general_break(p["cov"].ctypes.data, W32, n90, 20, brk.ctypes.data)
+    shared = covd[:, :n90].T.astype(np.int32) @ covd[:, :n90].astype(np.int32)       # |C[ii] & C[jj]|
+    for ii in range(n90):
+        below = [jj for jj in range(ii + 20, n90) if shared[ii, jj] < 20]
+        assert brk[ii] == (below[0] if below else max(n90, ii + 20)), ii                # MaxCorrelation.c:804-810
+    # the 0/1 operands of the tensor path: int8 and packed e2m1 (1.0 = 0b0010), K-major
+    Kp = 128 * ((p["R"] + 127) // 128)
+    member = np.zeros((5 * p["N"], Kp), dtype=np.uint8)
+    rc = codes[p["perm"]]
+    for k in range(5):
+        member[k::5, :p["R"]] = (rc == k).T
+    xb = np.zeros((5 * p["N"], Kp), dtype=np.int8)
+    emu_pack.emu_pack_int8(cells.ctypes.data, p["perm"].ctypes.data, p["R"], p["N"], 0, xb.ctypes.data, Kp, 0)
+    assert np.array_equal(xb.view(np.uint8), member)
+    x4 = np.zeros((5 * p["N"], Kp // 2), dtype=np.uint8)
+    emu_pack.emu_pack_int8(cells.ctypes.data, p["perm"].ctypes.data, p["R"], p["N"], 0, x4.ctypes.data, Kp, 1)
+    assert np.array_equal(x4, (member[:, 0::2] * 2) | (member[:, 1::2] * 2 << 4))
+
+
+@pytest.mark.parametrize("name,cov", [("kat_appendix_g", 30), ("initial_aligner_style", 30)])
+def test_whole_device_pipeline_of_the_bitset_variant(emu_pack, name, cov, tmp_path):
+    """cells as read from the text -> spans -> row order -> bitsets -> sizes -> host plan -> scan kernel: every device
+    step of the hot path's AND+POPC variant emulated, result = the oracle's and, formatted, the unmodified reference's file"""
+    from conftest import golden_maxcorrs
+    text = golden_msa(name)
+    o = O.Oracle.from_text(text, tmp_path)
+    msa = rr.MSA.from_text(text)
+    cells = msa.cells().copy()
+    msa.close()
+    p = device_pack(emu_pack, cells, 0)
+    R, N = p["R"], p["N"]
+    start, end = p["start"][p["perm"]].copy(), p["end"][p["perm"]].copy()
+    brk = np.ascontiguousarray(rr.breakcols_from_spans(start, end, N, cov), dtype=np.int32)
+    lnf = rr.lnfact_table(R + 2)
+    best = np.zeros(5 * N, dtype=[("z", "<u8"), ("p", "<u8")])
+    best["p"] = np.uint64(2 ** 64 - 1)
+    counters = np.zeros(8, dtype=np.uint64)
+    pairs = emu_pack.emu_scan_bitset(R, N, p["W32"], cov, 0, p["bits"].ctypes.data, p["gs"].ctypes.data, p["cv"].ctypes.data,
+                                     brk.ctypes.data, start.ctypes.data, end.ctypes.data, p["split"], lnf.ctypes.data,
+                                     best.ctypes.data, counters.ctypes.data, 3, 0, 1)
+    M = best["z"].view(np.float64)
+    M0, A0, P0 = o.scan(cov)
+    assert pairs == P0 == int(counters[0]) and np.array_equal(M, M0)
+    assert O.fmt_lines(M) == golden_maxcorrs(name, cov)
