@@ -438,3 +438,27 @@ def test_whole_device_pipeline_of_the_bitset_variant(emu_pack, name, cov, tmp_pa
     M0, A0, P0 = o.scan(cov)
     assert pairs == P0 == int(counters[0]) and np.array_equal(M, M0)
     assert O.fmt_lines(M) == golden_maxcorrs(name, cov)
+
+
+def test_bitset_scan_kernel_edge_shapes(emu_scan):
+    """shapes without a single pair test (fewer rows than the coverage floor, fewer than 21 columns, one row, one base
+    everywhere), and small random shapes with unusual coverage floors"""
+    rng = np.random.default_rng(0)
+    for codes, cov in [(np.zeros((5, 100), np.uint8), 30), (rng.integers(0, 5, (64, 20)).astype(np.uint8), 4),
+                       (np.zeros((1, 50), np.uint8), 1), (np.zeros((40, 60), np.uint8), 10)]:
+        M, A, pairs, counters = run_scan_bitset(emu_scan, codes, cov)
+        assert pairs == 0 and int(counters[0]) == 0 and not M.any() and (A == -1).all()
+    for R, N, cov in [(64, 21, 4), (33, 45, 1), (70, 40, 0), (130, 64, 9)]:
+        codes = rng.integers(0, 6, (R, N)).astype(np.uint8)
+        codes[:, : N // 2][rng.random((R, N // 2)) < 0.5] = 0             # some structure: a dominant base
+        keep = (codes < 5).any(1)
+        codes = codes[keep]
+        # rows must be single spans for the closed-form first-break: blank only outside [first, last]
+        cov_mask = codes < 5
+        first, last = cov_mask.argmax(1), codes.shape[1] - 1 - cov_mask[:, ::-1].argmax(1)
+        inner = (np.arange(codes.shape[1])[None, :] >= first[:, None]) & (np.arange(codes.shape[1])[None, :] <= last[:, None])
+        codes = np.where(inner & (codes == 5), 4, codes).astype(np.uint8)
+        o = O.Oracle.from_codes(codes)
+        M0, A0, P0 = o.scan(cov)
+        M, A, pairs, counters = run_scan_bitset(emu_scan, codes, cov)
+        assert pairs == P0 == int(counters[0]) and np.array_equal(M, M0) and np.array_equal(A, A0), (R, N, cov)
