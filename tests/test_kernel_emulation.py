@@ -462,3 +462,25 @@ def test_bitset_scan_kernel_edge_shapes(emu_scan):
         M0, A0, P0 = o.scan(cov)
         M, A, pairs, counters = run_scan_bitset(emu_scan, codes, cov)
         assert pairs == P0 == int(counters[0]) and np.array_equal(M, M0) and np.array_equal(A, A0), (R, N, cov)
+
+
+@pytest.mark.parametrize("kind,seed", [("Distributed", 52), ("EquiDistant", 53)])
+def test_bitset_scan_kernel_copy_families_with_exact_ties(emu_scan, kind, seed):
+    """BASELINE.json configs[2] in miniature: the other two copy-difference structures, with a stretch of columns
+    duplicated so that different partners attain exactly the same maximum - the smallest partner must win whatever the
+    order in which the (really concurrent) emulated threads reach the 16-byte compare-and-swap"""
+    g = rr.MsaGen(type=kind, copies=4, coverage=14, repeat_len=260, diff=0.04, seed=seed, flank=120, min_overlap=50)
+    codes = g.codes()
+    codes[:, 200:215] = codes[:, 90:105]
+    cov = codes < 5                                                       # keep rows single spans after the copy
+    first, last = cov.argmax(1), codes.shape[1] - 1 - cov[:, ::-1].argmax(1)
+    col = np.arange(codes.shape[1])[None, :]
+    inner = (col >= first[:, None]) & (col <= last[:, None])
+    codes = np.where(inner & (codes == 5), 4, np.where(inner, codes, 5)).astype(np.uint8)
+    o = O.Oracle.from_codes(codes)
+    M0, A0, P0 = o.scan(12)
+    # a partner inside the source stretch has a twin in the copy that attains the same score: the smaller id won
+    ties = int(((M0 > 0) & (A0 >= 90 * 5) & (A0 < 105 * 5)).sum())
+    M, A, pairs, counters = run_scan_bitset(emu_scan, codes, 12, blocks=5)
+    assert pairs == P0 == int(counters[0]) and np.array_equal(M, M0) and np.array_equal(A, A0)
+    assert ties > 0 and not ((A0 >= 200 * 5) & (A0 < 215 * 5) & (np.arange(len(A0)) < 90 * 5)).any()
