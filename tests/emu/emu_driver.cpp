@@ -80,6 +80,26 @@ static void emu_launch(dim3 grid, unsigned threads, F body)
 
 extern "C" {
 
+/* The pruning tiers of the fused epilogue (rr_device.cuh) as plain functions, called the way rr_scan_umma.cu calls them:
+ * tier 1 on a float copy of the ln n! table with the host-computed rounding margin, tier 2 on the double table.
+ * quads: n x {s, gr1, gr2, cov}; best: n running maxima; keep1 / keep2: 1 = the pair survives the tier. */
+void emu_tiers(const double *lnf, int max_cov, long long n, const uint32_t *quads, const double *best, unsigned char *keep1,
+               unsigned char *keep2)
+{
+    std::vector<float> lnf32((size_t)max_cov + 2);
+    for (int k = 0; k < max_cov + 2; k++) lnf32[k] = (float)lnf[k];
+    const float margin = (float)(16.0 * 5.9604645e-8 * lnf[std::max(max_cov, 1)] * 0.4342944819 + 2e-6);   // rr_scan_umma.cu: U.t1_margin
+    auto LT = [&](unsigned k) { return lnf32[k]; };
+    rr_lnf_global T2{lnf};
+    for (long long i = 0; i < n; i++) {
+        const unsigned sc = quads[4 * i], gr1 = quads[4 * i + 1], gr2 = quads[4 * i + 2], cov = quads[4 * i + 3];
+        const float lnc3 = (LT(cov) - LT(gr1)) - LT(cov - gr1);
+        const float meanfac = (1.0f / (float)std::max(cov, 1u)) * (float)gr1;
+        keep1[i] = rr_tier1_f32(LT, sc, gr1, gr2, cov, rr_thr_f32(best[i], false), lnc3, meanfac, margin) ? 1 : 0;
+        keep2[i] = rr_tier2(T2, sc, gr1, gr2, cov, best[i]) ? 1 : 0;
+    }
+}
+
 /* the packing kernels of rr_pack.cu with the grids their launchers use */
 void emu_row_spans(const uint8_t *cells, int R, int N, int codes, int32_t *start, int32_t *end, int32_t *ncov)
 {

@@ -484,3 +484,38 @@ def test_bitset_scan_kernel_copy_families_with_exact_ties(emu_scan, kind, seed):
     M, A, pairs, counters = run_scan_bitset(emu_scan, codes, 12, blocks=5)
     assert pairs == P0 == int(counters[0]) and np.array_equal(M, M0) and np.array_equal(A, A0)
     assert ties > 0 and not ((A0 >= 200 * 5) & (A0 < 215 * 5) & (np.arange(len(A0)) < 90 * 5)).any()
+
+
+def test_pruning_tiers_of_the_fused_epilogue_never_drop_a_pair_that_matters(emu):
+    """rr_tier1_f32 (FP32, float table, rounding margin) and rr_tier2 (windowed partial sum) of rr_device.cuh, called as
+    rr_scan_umma.cu calls them, at depths up to 40 000 reads: a pair whose exact score reaches the running maximum must
+    survive both; against a maximum well above the score most pairs must be dropped (the tiers do prune)"""
+    vp = C.c_void_p
+    emu.emu_tiers.argtypes = [vp, C.c_int, C.c_longlong, vp, vp, vp, vp]
+    rng = np.random.default_rng(23)
+    for max_cov in (300, 4000, 40000):
+        lnf = rr.lnfact_table(max_cov + 2)
+        quads, scores = [], []
+        while len(quads) < 4000:
+            cov = int(rng.integers(max(2, max_cov // 50), max_cov + 1))
+            gr1 = int(rng.integers(1, cov + 1)) if rng.random() < 0.5 else int(rng.integers(1, max(2, cov // 20)))
+            gr2 = int(rng.integers(1, cov + 1)) if rng.random() < 0.5 else int(rng.integers(1, max(2, cov // 20)))
+            lo, hi = max(1, gr1 + gr2 - cov), min(gr1, gr2)
+            if lo > hi:
+                continue
+            mean = gr1 * gr2 / cov
+            s = int(min(hi, max(lo, round(mean + rng.normal() * 3 * (mean ** 0.5 + 1)))))      # around the mean and in the tail
+            z = O.score(s, gr1, gr2, cov, gr1 + 3, gr2 + 5)
+            quads.append((s, gr1, gr2, cov))
+            scores.append(z)
+        q = np.array(quads, dtype=np.uint32)
+        z = np.array(scores)
+        k1, k2 = np.zeros(len(q), dtype=np.uint8), np.zeros(len(q), dtype=np.uint8)
+        # at the lower end of the support the score is exactly 0 and the kernels drop the pair before the tiers (tier 1b)
+        live = z > 0
+        for best in (z, z * (1 - 1e-12), z * 0.999, np.maximum(z - 1e-6, 0)):
+            emu.emu_tiers(lnf.ctypes.data, max_cov, len(q), q.ctypes.data, np.ascontiguousarray(best).ctypes.data, k1.ctypes.data, k2.ctypes.data)
+            assert k1[live].all() and k2[live].all(), (max_cov, int((~k1[live].astype(bool)).sum()), int((~k2[live].astype(bool)).sum()))
+        emu.emu_tiers(lnf.ctypes.data, max_cov, len(q), q.ctypes.data, np.ascontiguousarray(z + 3.0).ctypes.data, k1.ctypes.data, k2.ctypes.data)
+        unsat = z < 90
+        assert k1[unsat].mean() < 0.5 and (k1 & k2)[unsat].mean() < 0.3, (max_cov, k1[unsat].mean(), (k1 & k2)[unsat].mean())
