@@ -214,6 +214,10 @@ int rr_cliquer_from_hits(int64_t n_queries, const int32_t *query_groups, int64_t
  * from rr_pair_counts and scores on the host with the same libm as the reference (bit-identical). */
 int rr_relative_vars(const rr_msa *msa, int device, const int32_t *unterteilung, int u_no, const double *maxcorrs,
                      double cutoff, int mingroup, int32_t *vars, int *n_vars, int64_t *pairs_tested /* may be NULL */);
+/* EXPERIMENTAL (never run on a GPU): the same on the packed copy of the whole MSA already on the device (e.g. after
+ * rr_scan): nothing is packed again, the part is applied as a mask; unterteilung indexes the rows of the MSA pk was made of */
+int rr_relative_vars_packed(rr_packed *pk, const int32_t *unterteilung, int u_no, const double *maxcorrs, double cutoff,
+                            int mingroup, int32_t *vars, int *n_vars, int64_t *pairs_tested /* may be NULL */);
 /* the host half on given counts (tests): gsize_u[g] = |G_g & U|, cov_u = |U|; with S == NULL only the selection
  * (sel_out, n_sel) is returned, else S[n_sel][n_sel] holds |G_sel[a] & G_sel[b] & U| */
 int rr_relative_vars_from_counts(int64_t n_groups, const double *maxcorrs, const int32_t *gsize_u, int cov_u, double cutoff,

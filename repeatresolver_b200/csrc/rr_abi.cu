@@ -230,6 +230,7 @@ struct rr_packed {
     rr_best_t *d_best = nullptr;
     unsigned long long *d_counters = nullptr;
     std::vector<int32_t> h_start, h_end;  // spans in rank order: (length class, span start, span end)
+    std::vector<int32_t> h_perm;          // rank -> row of the MSA
     int class_split = 0;                  // ranks [0, class_split) = the short rows
     std::vector<int32_t> h_gsize, h_coverage;
     bool contiguous = true;
@@ -419,6 +420,7 @@ static int pack_impl(const rr_msa *msa, int device, rr_packed *pk)
         pk->h_start[k] = sst[r]; pk->h_end[k] = sen[r];
         if (scn[r] > 0 && scn[r] != sen[r] - sst[r] + 1) pk->contiguous = false;
     }
+    pk->h_perm = perm;
     if ((rc = dev_alloc(&pk->d_perm, (size_t)R))) return rc;
     if (R) RR_CUDA(cudaMemcpyAsync(pk->d_perm, perm.data(), sizeof(int32_t) * R, cudaMemcpyHostToDevice, pk->st));
 
@@ -911,8 +913,8 @@ extern "C" int rr_relative_vars_from_counts(int64_t n_groups, const double *maxc
     return RR_OK;
 }
 
-static int relvars_device_pairs(rr_packed *pk, const std::vector<int32_t> &sel, int cov_u, double cutoff, std::vector<uint8_t> &mark,
-                                int64_t *pairs_tested)
+static int relvars_device_pairs(rr_packed *pk, const uint32_t *d_umask, const int32_t *gsize_u, const std::vector<int32_t> &sel, int cov_u,
+                                double cutoff, std::vector<uint8_t> &mark, int64_t *pairs_tested)
 {
     const int nsel = (int)sel.size();
     std::vector<int32_t> first((size_t)nsel);
@@ -925,19 +927,20 @@ static int relvars_device_pairs(rr_packed *pk, const std::vector<int32_t> &sel, 
     rr_alloc_stream(pk->st);
     dev_scope scope;
     constexpr unsigned UNSURE_CAP = 1u << 20;
-    int32_t *d_sel = nullptr, *d_first = nullptr;
+    int32_t *d_sel = nullptr, *d_first = nullptr, *d_gu = nullptr;
     unsigned char *d_mark = nullptr;
     int4 *d_unsure = nullptr;
     unsigned int *d_count = nullptr, count = 0;
     int rc;
     if ((rc = scope.alloc(&d_sel, (size_t)nsel)) || (rc = scope.alloc(&d_first, (size_t)nsel)) || (rc = scope.alloc(&d_mark, (size_t)nsel)) ||
-        (rc = scope.alloc(&d_unsure, (size_t)UNSURE_CAP)) || (rc = scope.alloc(&d_count, 1)))
+        (rc = scope.alloc(&d_unsure, (size_t)UNSURE_CAP)) || (rc = scope.alloc(&d_count, 1)) || (rc = scope.alloc(&d_gu, (size_t)5 * pk->N)))
         return rc;
+    RR_CUDA(cudaMemcpyAsync(d_gu, gsize_u, sizeof(int32_t) * (size_t)5 * pk->N, cudaMemcpyHostToDevice, pk->st));
     RR_CUDA(cudaMemcpyAsync(d_sel, sel.data(), sizeof(int32_t) * (size_t)nsel, cudaMemcpyHostToDevice, pk->st));
     RR_CUDA(cudaMemcpyAsync(d_first, first.data(), sizeof(int32_t) * (size_t)nsel, cudaMemcpyHostToDevice, pk->st));
     RR_CUDA(cudaMemsetAsync(d_mark, 0, (size_t)nsel, pk->st));
     RR_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned int), pk->st));
-    RR_CUDA(rr_launch_relvars_pairs(pk->d_bits, pk->W32, d_sel, nsel, d_first, pk->d_gsize, cov_u, pk->d_lnfact, cutoff, d_mark, d_unsure,
+    RR_CUDA(rr_launch_relvars_pairs(pk->d_bits, d_umask, pk->W32, d_sel, nsel, d_first, d_gu, cov_u, pk->d_lnfact, cutoff, d_mark, d_unsure,
                                     UNSURE_CAP, d_count, pk->st));
     RR_CUDA(cudaMemcpyAsync(mark.data(), d_mark, (size_t)nsel, cudaMemcpyDeviceToHost, pk->st));
     RR_CUDA(cudaMemcpyAsync(&count, d_count, sizeof(count), cudaMemcpyDeviceToHost, pk->st));
@@ -949,10 +952,57 @@ static int relvars_device_pairs(rr_packed *pk, const std::vector<int32_t> &sel, 
         RR_CUDA(cudaStreamSynchronize(pk->st));
     }
     for (const int4 &u : unsure) {
-        const double Z = rr_relative_score_host((uint32_t)u.z, (uint32_t)pk->h_gsize[sel[u.y]], (uint32_t)pk->h_gsize[sel[u.x]], (uint32_t)cov_u);
+        const double Z = rr_relative_score_host((uint32_t)u.z, (uint32_t)gsize_u[sel[u.y]], (uint32_t)gsize_u[sel[u.x]], (uint32_t)cov_u);
         if (Z > cutoff) mark[u.x] = mark[u.y] = 1;
     }
     if (pairs_tested) *pairs_tested = pairs;
+    return RR_OK;
+}
+
+// EXPERIMENTAL (never run on a GPU): Relative_Vars on the packed copy of the WHOLE MSA as it sits on the device after the
+// scan - nothing is packed again; the part is a bitset over the packed row order, |G & U| comes from rr_k_masked_sizes and
+// the all-pairs step from the tiled kernel with the mask ANDed into one operand.
+extern "C" int rr_relative_vars_packed(rr_packed *pk, const int32_t *unterteilung, int u_no, const double *maxcorrs, double cutoff,
+                                       int mingroup, int32_t *vars, int *n_vars, int64_t *pairs_tested)
+{
+    if (pairs_tested) *pairs_tested = 0;
+    if (!pk || !unterteilung || !maxcorrs || !vars || !n_vars || mingroup < 1 || !(cutoff >= 0.0)) {
+        rr_set_error("rr_relative_vars_packed: bad arguments");
+        return RR_E_ARG;
+    }
+    vars[0] = -1;
+    *n_vars = 0;
+    const int R = pk->R, N = pk->N;
+    if ((int)pk->h_perm.size() != R) { rr_set_error("rr_relative_vars_packed: the packed MSA carries no row order"); return RR_E_ARG; }
+    std::vector<uint32_t> umask((size_t)pk->W32, 0u);
+    int cov_u = 0;
+    for (int rank = 0; rank < R; rank++)
+        if (unterteilung[pk->h_perm[rank]] == u_no) { umask[rank >> 5] |= 1u << (rank & 31); cov_u++; }   // 2438, in packed row order
+    if (cov_u < mingroup || N == 0) return RR_OK;
+    RR_CUDA(cudaSetDevice(pk->device));
+    rr_alloc_stream(pk->st);
+    std::vector<int32_t> gsize_u((size_t)5 * N);
+    std::vector<int32_t> sel;
+    std::vector<uint8_t> mark;
+    int rc;
+    {
+        dev_scope scope;
+        uint32_t *d_umask = nullptr;
+        int32_t *d_gu = nullptr;
+        if ((rc = scope.alloc(&d_umask, umask.size())) || (rc = scope.alloc(&d_gu, gsize_u.size()))) return rc;
+        RR_CUDA(cudaMemcpyAsync(d_umask, umask.data(), sizeof(uint32_t) * umask.size(), cudaMemcpyHostToDevice, pk->st));
+        RR_CUDA(rr_launch_masked_sizes(pk->d_bits, d_umask, (int64_t)5 * N, pk->W32, d_gu, pk->st));
+        RR_CUDA(cudaMemcpyAsync(gsize_u.data(), d_gu, sizeof(int32_t) * gsize_u.size(), cudaMemcpyDeviceToHost, pk->st));
+        RR_CUDA(cudaStreamSynchronize(pk->st));
+        relvars_select((int64_t)5 * N, maxcorrs, gsize_u.data(), cutoff, mingroup, sel);
+        mark.assign(sel.size(), 0);
+        if (!sel.empty() && (rc = relvars_device_pairs(pk, d_umask, gsize_u.data(), sel, cov_u, cutoff, mark, pairs_tested))) return rc;
+    }
+    int n = 0;
+    for (size_t a = 0; a < sel.size(); a++)
+        if (mark[a]) vars[n++] = sel[a];
+    vars[n] = -1;
+    *n_vars = n;
     return RR_OK;
 }
 
@@ -988,7 +1038,7 @@ extern "C" int rr_relative_vars(const rr_msa *msa, int device, const int32_t *un
     if (getenv("RR_RELVARS_KERNEL") && atoi(getenv("RR_RELVARS_KERNEL")) == 1 && !sel.empty()) {
         // EXPERIMENTAL (rr_relvars.cu, not yet run on a GPU): the all-pairs step in one tiled kernel; pairs it cannot decide
         // (score within 1e-9 of the cutoff) come back in a list and are scored here with the host libm
-        rc = relvars_device_pairs(pk, sel, cov_u, cutoff, mark, pairs_tested);
+        rc = relvars_device_pairs(pk, nullptr, gsize_u, sel, cov_u, cutoff, mark, pairs_tested);
         rr_packed_free(pk);
         if (rc) return rc;
         int n = 0;

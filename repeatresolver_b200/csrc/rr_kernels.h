@@ -48,7 +48,8 @@ cudaError_t rr_launch_cliquer(int kernel /* 1: one-step counts, 2: two-step */, 
                               unsigned long long *counters, int n_sm, cudaStream_t st);
 
 // Relative_Vars (rr_relvars.cu, experimental): the all-pairs step on the packed rows of one part
-cudaError_t rr_launch_relvars_pairs(const uint32_t *bits, int W32, const int32_t *sel, int nsel, const int32_t *first_partner,
+cudaError_t rr_launch_masked_sizes(const uint32_t *bits, const uint32_t *umask, int64_t nsets, int W32, int32_t *sizes, cudaStream_t st);
+cudaError_t rr_launch_relvars_pairs(const uint32_t *bits, const uint32_t *umask /* NULL: bits are the part's own rows */, int W32, const int32_t *sel, int nsel, const int32_t *first_partner,
                                     const int32_t *gsize_u, int cov_u, const double *lnf, double cutoff, unsigned char *mark,
                                     int4 *unsure, unsigned int unsure_cap, unsigned int *unsure_count, cudaStream_t st);
 

@@ -2,8 +2,10 @@
 // (SURVEY.md section 8f, row 3).  EXPERIMENTAL: selected with RR_RELVARS_KERNEL=1, written when the round's GPU minutes
 // were spent and not yet run on a GPU (its logic passes under the CPU emulation of tests/emu); the default path of rr_relative_vars (rr_abi.cu) uses rr_pair_counts instead.
 //
-// Input is the packed copy of the part's rows (rr_pack of the reads with Unterteilung == u_no), so a group bitset is
-// already G & U, its size |G & U|, and |Gi & Gj & U| (Triple_Schnitt 150-161) a plain AND+POPC of two rows of `bits`.
+// Input is either the packed copy of the part's rows (rr_pack of the reads with Unterteilung == u_no, umask == NULL): a
+// group bitset is then already G & U, its size |G & U|, and |Gi & Gj & U| (Triple_Schnitt 150-161) a plain AND+POPC of two
+// rows of `bits`; or the packed copy of the WHOLE MSA, as it sits on the device after the scan, with the part as a bitset
+// `umask` over the same row order: the mask is ANDed into one operand while it is staged, rr_k_masked_sizes gives |G & U|.
 // One block = a 64 x 64 tile of (earlier group a, later group b) of the selected list; the 2 x 64 bitsets go through
 // shared memory 32 words at a time (coalesced 128-byte row segments), a thread accumulates a 4 x 4 block of counts in
 // registers (POPC-issue bound, every staged word is used 64 times).  Tail, per pair with b at least 100 group ids after
@@ -17,7 +19,7 @@
 constexpr int RV_TILE = 64;
 
 __global__ void __launch_bounds__(256)
-rr_k_relvars_pairs(const uint32_t *__restrict__ bits, int W32, const int32_t *__restrict__ sel, int nsel,
+rr_k_relvars_pairs(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ umask, int W32, const int32_t *__restrict__ sel, int nsel,
                    const int32_t *__restrict__ first_partner, const int32_t *__restrict__ gsize_u, int cov_u,
                    const double *__restrict__ lnf, double cutoff, unsigned char *mark,
                    int4 *__restrict__ unsure, unsigned int unsure_cap, unsigned int *__restrict__ unsure_count)
@@ -40,7 +42,8 @@ rr_k_relvars_pairs(const uint32_t *__restrict__ bits, int W32, const int32_t *__
         __syncthreads();
         for (int r = warp; r < RV_TILE; r += 8) {              // a warp stages one row segment of each operand
             const int a = a0 + r, b = b0 + r;
-            A[r][lane] = (a < nsel && w < W32) ? __ldg(bits + (size_t)sel[a] * W32 + w) : 0u;
+            const uint32_t u = w < W32 ? (umask ? __ldg(umask + w) : 0xffffffffu) : 0u;   // G & U: the mask goes into one operand
+            A[r][lane] = (a < nsel && w < W32) ? __ldg(bits + (size_t)sel[a] * W32 + w) & u : 0u;
             B[r][lane] = (b < nsel && w < W32) ? __ldg(bits + (size_t)sel[b] * W32 + w) : 0u;
         }
         __syncthreads();
@@ -77,14 +80,35 @@ rr_k_relvars_pairs(const uint32_t *__restrict__ bits, int W32, const int32_t *__
         }
 }
 
+// |G & U| for every group (2449: Schnitt(U_Group, Groups[i])): one warp per bitset, as rr_k_bitset_sizes with a mask
+__global__ void __launch_bounds__(256) rr_k_masked_sizes(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ umask,
+                                                          int64_t nsets, int W32, int32_t *__restrict__ sizes)
+{
+    const int64_t g = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (g >= nsets) return;
+    const uint32_t *p = bits + (size_t)g * W32;
+    unsigned n = 0;
+    for (int w = threadIdx.x & 31; w < W32; w += 32) n += __popc(__ldg(p + w) & __ldg(umask + w));
+    n = __reduce_add_sync(0xffffffffu, n);
+    if ((threadIdx.x & 31) == 0) sizes[g] = (int32_t)n;
+}
+
 #ifndef RR_CPU_EMU   // tests/emu compiles the kernels above with a host compiler; the launch syntax below is nvcc only
-cudaError_t rr_launch_relvars_pairs(const uint32_t *bits, int W32, const int32_t *sel, int nsel, const int32_t *first_partner,
+cudaError_t rr_launch_masked_sizes(const uint32_t *bits, const uint32_t *umask, int64_t nsets, int W32, int32_t *sizes, cudaStream_t st)
+{
+    if (nsets <= 0) return cudaSuccess;
+    rr_k_masked_sizes<<<(unsigned)((nsets + 7) / 8), 256, 0, st>>>(bits, umask, nsets, W32, sizes);
+    rr_count_launch(1);
+    return cudaGetLastError();
+}
+
+cudaError_t rr_launch_relvars_pairs(const uint32_t *bits, const uint32_t *umask, int W32, const int32_t *sel, int nsel, const int32_t *first_partner,
                                     const int32_t *gsize_u, int cov_u, const double *lnf, double cutoff, unsigned char *mark,
                                     int4 *unsure, unsigned int unsure_cap, unsigned int *unsure_count, cudaStream_t st)
 {
     if (nsel <= 0) return cudaSuccess;
     const unsigned nt = (unsigned)((nsel + RV_TILE - 1) / RV_TILE);
-    rr_k_relvars_pairs<<<dim3(nt, nt), 256, 0, st>>>(bits, W32, sel, nsel, first_partner, gsize_u, cov_u, lnf, cutoff, mark, unsure,
+    rr_k_relvars_pairs<<<dim3(nt, nt), 256, 0, st>>>(bits, umask, W32, sel, nsel, first_partner, gsize_u, cov_u, lnf, cutoff, mark, unsure,
                                                      unsure_cap, unsure_count);
     rr_count_launch(1);
     return cudaGetLastError();

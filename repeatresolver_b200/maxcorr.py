@@ -162,6 +162,18 @@ class Packed:
                "rr_cliquer_batch")
         return members, scores, n, st.as_dict()
 
+    def relative_vars(self, Unterteilung, u_no, MaxCorrs, cutoff, mingroup):
+        """Relative_Vars (RepeatResolver.c:2424-2493) on this packed MSA, the part applied as a mask (EXPERIMENTAL,
+        rr_relative_vars_packed): ascending group ids"""
+        u = np.ascontiguousarray(Unterteilung, dtype=np.int32)
+        M = np.ascontiguousarray(MaxCorrs, dtype=np.float64)
+        assert len(u) == self.rows and len(M) == 5 * self.cols
+        out = np.zeros(5 * self.cols + 1, dtype=np.int32)
+        n, pairs = C.c_int(0), C.c_int64(0)
+        _check(lib.rr_relative_vars_packed(self._h, u.ctypes.data, int(u_no), M.ctypes.data, float(cutoff), int(mingroup),
+                                           out.ctypes.data, C.byref(n), C.byref(pairs)), "rr_relative_vars_packed")
+        return out[:n.value].copy()
+
     def pair_counts(self, gi, gj):
         gi = np.ascontiguousarray(gi, dtype=np.int32)
         gj = np.ascontiguousarray(gj, dtype=np.int32)

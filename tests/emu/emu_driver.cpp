@@ -177,13 +177,18 @@ int emu_cliquer(int kernel, const uint32_t *bits, const uint32_t *covbits, const
     return 0;
 }
 
-int emu_relvars_pairs(const uint32_t *bits, int W32, const int32_t *sel, int nsel, const int32_t *first_partner, const int32_t *gsize_u,
+void emu_masked_sizes(const uint32_t *bits, const uint32_t *umask, long long nsets, int W32, int32_t *sizes)
+{
+    if (nsets > 0) emu_launch(dim3((unsigned)((nsets + 7) / 8)), 256, [&] { rr_k_masked_sizes(bits, umask, nsets, W32, sizes); });
+}
+
+int emu_relvars_pairs(const uint32_t *bits, const uint32_t *umask, int W32, const int32_t *sel, int nsel, const int32_t *first_partner, const int32_t *gsize_u,
                       int cov_u, const double *lnf, double cutoff, unsigned char *mark, int4 *unsure, unsigned unsure_cap,
                       unsigned *unsure_count)
 {
     if (nsel <= 0) return 0;
     const unsigned nt = (unsigned)((nsel + RV_TILE - 1) / RV_TILE);
-    emu_launch(dim3(nt, nt), 256, [&] { rr_k_relvars_pairs(bits, W32, sel, nsel, first_partner, gsize_u, cov_u, lnf, cutoff, mark, unsure, unsure_cap, unsure_count); });
+    emu_launch(dim3(nt, nt), 256, [&] { rr_k_relvars_pairs(bits, umask, W32, sel, nsel, first_partner, gsize_u, cov_u, lnf, cutoff, mark, unsure, unsure_cap, unsure_count); });
     return 0;
 }
 

@@ -38,7 +38,8 @@ def emu():
     lib = C.CDLL(out)
     vp, i, d, u64, u32 = C.c_void_p, C.c_int, C.c_double, C.c_ulonglong, C.c_uint
     lib.emu_cliquer.argtypes = [i, vp, vp, vp, vp, i, vp, i, i, i, i, d, d, vp, vp, u64, vp]
-    lib.emu_relvars_pairs.argtypes = [vp, i, vp, i, vp, vp, i, vp, d, vp, vp, u32, vp]
+    lib.emu_relvars_pairs.argtypes = [vp, vp, i, vp, i, vp, vp, i, vp, d, vp, vp, u32, vp]
+    lib.emu_masked_sizes.argtypes = [vp, vp, C.c_longlong, i, vp]
     lib.emu_kmeans_sweeps.argtypes = [vp, i, i, i, vp, vp, vp]
     return lib
 
@@ -132,23 +133,38 @@ def test_cliquer_count_kernels_with_several_chunks_and_ragged_coverage(emu, kern
         assert list(members[k, :n[k]]) == list(m0) and np.array_equal(scores[k, :n[k]], z0), qq
 
 
-def run_relvars(emu, codes, ut, u_no, M, cutoff, mingroup):
-    sub = np.ascontiguousarray(codes[ut == u_no])
-    cov_u = len(sub)
+def run_relvars(emu, codes, ut, u_no, M, cutoff, mingroup, masked=False):
+    """masked=False: the part's rows packed on their own (rr_relative_vars with RR_RELVARS_KERNEL=1);
+    masked=True: the whole MSA packed once, the part as a bitset (rr_relative_vars_packed)"""
+    part = ut == u_no
+    cov_u = int(part.sum())
     if cov_u < mingroup:
         return np.zeros(0, dtype=np.int32), 0
-    bits, _, W32 = pack_bits(sub)
-    gu = np.stack([(sub == k).sum(0) for k in range(5)], 1).reshape(-1).astype(np.int32)
+    if masked:
+        bits, _, W32 = pack_bits(codes)
+        mbits = np.zeros(W32 * 32, dtype=np.uint8)
+        mbits[:len(part)] = part
+        umask = np.ascontiguousarray(np.packbits(mbits, bitorder="little").view(np.uint32))
+        gu = np.zeros(5 * codes.shape[1], dtype=np.int32)
+        emu.emu_masked_sizes(bits.ctypes.data, umask.ctypes.data, 5 * codes.shape[1], W32, gu.ctypes.data)
+        sub = codes[part]
+        assert np.array_equal(gu, np.stack([(sub == k).sum(0) for k in range(5)], 1).reshape(-1))
+        umask_ptr = umask.ctypes.data
+    else:
+        sub = np.ascontiguousarray(codes[part])
+        bits, _, W32 = pack_bits(sub)
+        gu = np.stack([(sub == k).sum(0) for k in range(5)], 1).reshape(-1).astype(np.int32)
+        umask_ptr = None
     sel = rr.relative_vars_from_counts(M, gu, cov_u, cutoff, mingroup)
     if len(sel) == 0:
         return sel, 0
     first = np.searchsorted(sel, sel + 100, side="left").astype(np.int32)
-    lnf = rr.lnfact_table(cov_u + 2)
+    lnf = rr.lnfact_table(codes.shape[0] + 2)
     mark = np.zeros(len(sel), dtype=np.uint8)
     unsure = np.zeros((4096, 4), dtype=np.int32)
     count = np.zeros(1, dtype=np.uint32)
-    emu.emu_relvars_pairs(bits.ctypes.data, W32, sel.ctypes.data, len(sel), first.ctypes.data, gu.ctypes.data, cov_u, lnf.ctypes.data,
-                          cutoff, mark.ctypes.data, unsure.ctypes.data, 4096, count.ctypes.data)
+    emu.emu_relvars_pairs(bits.ctypes.data, umask_ptr, W32, sel.ctypes.data, len(sel), first.ctypes.data, gu.ctypes.data, cov_u,
+                          lnf.ctypes.data, cutoff, mark.ctypes.data, unsure.ctypes.data, 4096, count.ctypes.data)
     assert count[0] <= 4096
     for a, b, s, _ in unsure[:int(count[0])]:                           # what rr_abi.cu does with the undecided pairs
         if rr.relative_score_host(int(s), int(gu[sel[b]]), int(gu[sel[a]]), cov_u) > cutoff:
@@ -156,7 +172,8 @@ def run_relvars(emu, codes, ut, u_no, M, cutoff, mingroup):
     return sel[mark > 0], int(count[0])
 
 
-def test_relvars_pair_kernel_on_the_golden_cases(emu):
+@pytest.mark.parametrize("masked", [False, True], ids=["part_packed", "whole_msa_masked"])
+def test_relvars_pair_kernel_on_the_golden_cases(emu, masked):
     checked = 0
     for name, case in sorted(relvars_cases().items()):
         codes = window_codes(golden_msa(name), case["von"], case["bis"])
@@ -164,20 +181,21 @@ def test_relvars_pair_kernel_on_the_golden_cases(emu):
         M, _, _ = o.scan(case["mincov"])
         ut, _ = partition_by_site(codes, M)
         for u_no, want in case["parts"].items():
-            got, _ = run_relvars(emu, codes, ut, int(u_no), M, case["cutoff"], case["mingroup"])
+            got, _ = run_relvars(emu, codes, ut, int(u_no), M, case["cutoff"], case["mingroup"], masked)
             assert list(got) == want["vars"], (name, u_no)
             checked += len(got) > 0
     assert checked >= 4
 
 
-def test_relvars_pair_kernel_with_several_chunks_and_a_cutoff_hit_exactly(emu):
+@pytest.mark.parametrize("masked", [False, True], ids=["part_packed", "whole_msa_masked"])
+def test_relvars_pair_kernel_with_several_chunks_and_a_cutoff_hit_exactly(emu, masked):
     codes = two_family_msa(1200, 90, seed=43, variant_every=4)
     o = O.Oracle.from_codes(codes)
     rng = np.random.default_rng(2)
     M = np.where(rng.random(5 * codes.shape[1]) < 0.8, 9.0, 0.0)
     ut = (rng.random(codes.shape[0]) < 0.1).astype(np.int32)             # part 0 holds ~1080 reads: two chunks
     for cutoff, mingroup in ((3.0, 8), (8.5, 30)):
-        got, _ = run_relvars(emu, codes, ut, 0, M, cutoff, mingroup)
+        got, _ = run_relvars(emu, codes, ut, 0, M, cutoff, mingroup, masked)
         want = o.relative_vars(ut, 0, M, cutoff, mingroup)
         assert list(got) == list(want) and len(want) > 5, (cutoff, mingroup)
     # a cutoff equal to a score that occurs: the pair is undecided on the device and settled by the host (Z > cutoff is strict)
@@ -188,7 +206,7 @@ def test_relvars_pair_kernel_with_several_chunks_and_a_cutoff_hit_exactly(emu):
     ga, gb = sub[:, a // 5] == a % 5, sub[:, b // 5] == b % 5
     z = O.relative_score(int((ga & gb).sum()), int(gb.sum()), int(ga.sum()), len(sub))
     if z > 0.5:
-        got, undecided = run_relvars(emu, codes, ut, 0, M, z, 8)
+        got, undecided = run_relvars(emu, codes, ut, 0, M, z, 8, masked)
         assert list(got) == list(o.relative_vars(ut, 0, M, z, 8)) and undecided >= 1
 
 

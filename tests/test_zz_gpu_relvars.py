@@ -69,4 +69,11 @@ def test_relative_vars_experimental_pair_kernel():
                 assert list(got) == list(want), (u_no, cutoff, mingroup)
     finally:
         del os.environ["RR_RELVARS_KERNEL"]
+    # the same on the packed copy of the whole MSA, the part applied as a mask (rr_relative_vars_packed)
+    pk = rr.Packed(msa, 0)
+    for u_no in sorted(set(int(x) for x in ut)):
+        for cutoff, mingroup in ((3.0, 8), (6.0, 20)):
+            want = o.relative_vars(ut, u_no, M, cutoff, mingroup)
+            assert list(pk.relative_vars(ut, u_no, M, cutoff, mingroup)) == list(want), (u_no, cutoff, mingroup)
+    pk.close()
     msa.close()

@@ -1,6 +1,6 @@
 """Timing probe for the rows after Cliquer on a generated MSA, for the next round's first GPU
 call: Relative_Vars through its default path (part packed on the device, rr_pair_counts, host scores) and through the tiled
-kernel of csrc/rr_relvars.cu (RR_RELVARS_KERNEL=1), and Kmeans (csrc/rr_kmeans.cu) on the groups it selects.  The read
+kernel of csrc/rr_relvars.cu (RR_RELVARS_KERNEL=1; and on the packed whole MSA with the part as a mask), and Kmeans (csrc/rr_kmeans.cu) on the groups it selects.  The read
 partition is the reads' symbol at the most significant site (MaxCorrs from a scan on the same GPU).  Wall times of the C-ABI
 calls; the two Relative_Vars paths must agree.  Usage: python tools/probe_rows.py [copies] [repeat_len] [out.json]"""
 import json
@@ -24,6 +24,7 @@ def main():
     M, A, st = rr.Parallel_AllMaxCorrsRechner(msa, 30, 1)
     site = int(np.argmax(M)) // 5
     ut = codes[:, site].astype(np.int32)
+    pk = rr.Packed(msa, 0)
     res = {"rows": int(codes.shape[0]), "cols": int(codes.shape[1]), "scan_kernel_ms": st["kernel_ms"], "partition_site": site, "parts": {}}
     for u_no in sorted(set(int(x) for x in ut)):
         size = int((ut == u_no).sum())
@@ -39,8 +40,11 @@ def main():
         v1 = rr.Relative_Vars(msa, ut, u_no, M, 3.0, 8)
         part["relvars_kernel_ms"] = round((time.time() - t) * 1e3, 2)
         os.environ.pop("RR_RELVARS_KERNEL", None)
+        t = time.time()
+        v2 = pk.relative_vars(ut, u_no, M, 3.0, 8)
+        part["relvars_masked_ms"] = round((time.time() - t) * 1e3, 2)
         part["vars"] = int(len(v0))
-        part["paths_agree"] = bool(np.array_equal(v0, v1))
+        part["paths_agree"] = bool(np.array_equal(v0, v1) and np.array_equal(v0, v2))
         if len(v0):
             t = time.time()
             n, after = rr.Kmeans(msa, ut, u_no, v0, 8)
