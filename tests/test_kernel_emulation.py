@@ -539,3 +539,28 @@ def test_pruning_tiers_of_the_fused_epilogue_never_drop_a_pair_that_matters(emu)
         emu.emu_tiers(lnf.ctypes.data, max_cov, len(q), q.ctypes.data, np.ascontiguousarray(z + 3.0).ctypes.data, k1.ctypes.data, k2.ctypes.data)
         unsat = z < 90
         assert k1[unsat].mean() < 0.5 and (k1 & k2)[unsat].mean() < 0.3, (max_cov, k1[unsat].mean(), (k1 & k2)[unsat].mean())
+
+
+def test_relvars_default_composition_with_the_emulated_kernels(emu_pack):
+    """what rr_relative_vars does by default, step for step, with its device steps emulated: the part's rows packed as an
+    MSA of their own (row spans, bitsets, sizes = |G & U|), |Gi & Gj & U| as the first count of rr_k_pair_counts for
+    (later group, earlier group), selection and marks by the library's host half"""
+    case = relvars_cases()["saturated"]
+    codes = window_codes(golden_msa("saturated"), case["von"], case["bis"])
+    o = O.Oracle.from_codes(codes)
+    M, _, _ = o.scan(case["mincov"])
+    ut, _ = partition_by_site(codes, M)
+    for u_no, want in case["parts"].items():
+        sub = np.ascontiguousarray(codes[ut == int(u_no)])
+        p = device_pack(emu_pack, sub, 1)
+        sel = rr.relative_vars_from_counts(M, p["gs"], len(sub), case["cutoff"], case["mingroup"])
+        first = np.searchsorted(sel, sel + 100, side="left")
+        pa = np.concatenate([np.full(len(sel) - f, a) for a, f in enumerate(first)]).astype(np.int64)
+        pb = np.concatenate([np.arange(f, len(sel)) for f in first]).astype(np.int64)
+        gi, gj = sel[pb].astype(np.int32), sel[pa].astype(np.int32)      # Group1 = the later group (2465)
+        out = np.zeros((len(gi), 4), dtype=np.int32)
+        emu_pack.emu_pair_counts(p["bits"].ctypes.data, p["cov"].ctypes.data, p["W32"], len(gi), gi.ctypes.data, gj.ctypes.data, out.ctypes.data)
+        S = np.zeros((len(sel), len(sel)), dtype=np.int32)
+        S[pa, pb] = out[:, 0]
+        got = rr.relative_vars_from_counts(M, p["gs"], len(sub), case["cutoff"], case["mingroup"], lambda s_: S)
+        assert list(got) == want["vars"], u_no
