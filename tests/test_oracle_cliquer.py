@@ -239,3 +239,22 @@ def test_batch_host_half_is_immune_to_the_saturation_switch_on_the_device():
             members, scores, n = rr.cliquer_from_hits(queries, h, o.gsize(), case["mincov"], maxclique, case["greedy"])
             for k, (m0, z0) in enumerate(want):
                 assert list(members[k, :n[k]]) == list(m0) and np.array_equal(scores[k, :n[k]], z0), (maxclique, k)
+
+
+@pytest.mark.parametrize("greedy", [97.0, 97.95, 98.3, 98.89])
+def test_batch_host_half_with_a_threshold_inside_the_saturation_band(greedy):
+    """greedy next to or inside (97.90, 98.90]: the device threshold is clamped to 97.89 so that both formulas' values reach
+    the host, which applies Z > greedy itself"""
+    import repeatresolver_b200 as rr
+    case = cliquer_cases()["saturated"]
+    codes = window_codes(golden_msa("saturated"), case["von"], case["bis"])
+    o = O.Oracle.from_codes(codes)
+    queries = [int(q) for q in case["queries"]]
+    hits = emulated_hits(o, queries, case["mincov"], greedy, np.random.default_rng(10))
+    members, scores, n = rr.cliquer_from_hits(queries, hits, o.gsize(), case["mincov"], 6, greedy)
+    some = 0
+    for k, q in enumerate(queries):
+        m0, z0 = o.cliquer(q, case["mincov"], 6, greedy)
+        assert list(members[k, :n[k]]) == list(m0) and np.array_equal(scores[k, :n[k]], z0), (greedy, q)
+        some += len(m0) > 1
+    assert some > 0 or greedy > 98.5
