@@ -111,6 +111,23 @@ def test_cliquer_count_kernels_on_the_golden_cases(emu, kernel):
             assert list(members[k, :n[k]]) == list(m0) and np.array_equal(scores[k, :n[k]], z0), (name, qq)
 
 
+@pytest.mark.parametrize("kernel", [1, 3])
+def test_cliquer_count_kernels_with_greedy_inside_the_saturation_band(emu, kernel):
+    """a bound above 98 proves nothing (486), a bound below it prunes against greedy = 98.1: only saturated pairs survive"""
+    case = cliquer_cases()["saturated"]
+    codes = window_codes(golden_msa("saturated"), case["von"], case["bis"])[:, :200]
+    o = O.Oracle.from_codes(codes)
+    M0, _, _ = o.scan(case["mincov"])
+    queries = [int(q) for q in np.argsort(-M0, kind="stable")[:6]]
+    o, members, scores, n, nc, nh = run_cliquer(emu, kernel, codes, queries, case["mincov"], 6, 98.1)
+    sat = 0
+    for k, qq in enumerate(queries):
+        m0, z0 = o.cliquer(qq, case["mincov"], 6, 98.1)
+        assert list(members[k, :n[k]]) == list(m0) and np.array_equal(scores[k, :n[k]], z0), qq
+        sat += len(m0) - 1
+    assert sat > 0 and (scores[:, 1:][scores[:, 1:] > 0] > 98.1).all()
+
+
 @pytest.mark.parametrize("kernel", [1, 2, 3])
 def test_cliquer_count_kernels_with_several_chunks_and_ragged_coverage(emu, kernel):
     """more than 1024 reads = two 32-word chunks per bitset; spans so that chunks are skipped on either side"""
