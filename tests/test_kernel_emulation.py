@@ -26,9 +26,14 @@ CSRC = os.path.join(ROOT, "repeatresolver_b200", "csrc")
 
 @pytest.fixture(scope="module")
 def emu():
-    out = os.path.join(EMU_DIR, "_build", "libemu.so")
-    srcs = [os.path.join(EMU_DIR, f) for f in ("emu_driver.cpp", "cuda_runtime.h")] + \
-           [os.path.join(CSRC, f) for f in ("rr_cliquer.cu", "rr_relvars.cu", "rr_kmeans.cu", "rr_score.h", "rr_kmeans.h", "rr_kernels.h")]
+    if os.environ.get("RR_EMU_LIB"):                  # e.g. an AddressSanitizer build of the same driver (tools/emu_asan.sh)
+        out = os.environ["RR_EMU_LIB"]
+        srcs = []
+    else:
+        out = os.path.join(EMU_DIR, "_build", "libemu.so")
+        srcs = [os.path.join(EMU_DIR, f) for f in ("emu_driver.cpp", "cuda_runtime.h")] + \
+               [os.path.join(CSRC, f) for f in ("rr_pack.cu", "rr_scan_bitset.cu", "rr_device.cuh", "rr_plan.cpp", "rr_cliquer.cu", "rr_relvars.cu",
+                                                "rr_kmeans.cu", "rr_score.h", "rr_kmeans.h", "rr_kernels.h")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         # -Bsymbolic: librr_maxcorr.so (loaded RTLD_GLOBAL by the package) exports nvcc's host stubs under the very names of
@@ -551,9 +556,11 @@ def test_pruning_tiers_of_the_fused_epilogue_never_drop_a_pair_that_matters(emu)
         # at the lower end of the support the score is exactly 0 and the kernels drop the pair before the tiers (tier 1b)
         live = z > 0
         for best in (z, z * (1 - 1e-12), z * 0.999, np.maximum(z - 1e-6, 0)):
-            emu.emu_tiers(lnf.ctypes.data, max_cov, len(q), q.ctypes.data, np.ascontiguousarray(best).ctypes.data, k1.ctypes.data, k2.ctypes.data)
+            best = np.ascontiguousarray(best)                            # keep the buffer alive across the call
+            emu.emu_tiers(lnf.ctypes.data, max_cov, len(q), q.ctypes.data, best.ctypes.data, k1.ctypes.data, k2.ctypes.data)
             assert k1[live].all() and k2[live].all(), (max_cov, int((~k1[live].astype(bool)).sum()), int((~k2[live].astype(bool)).sum()))
-        emu.emu_tiers(lnf.ctypes.data, max_cov, len(q), q.ctypes.data, np.ascontiguousarray(z + 3.0).ctypes.data, k1.ctypes.data, k2.ctypes.data)
+        far = np.ascontiguousarray(z + 3.0)
+        emu.emu_tiers(lnf.ctypes.data, max_cov, len(q), q.ctypes.data, far.ctypes.data, k1.ctypes.data, k2.ctypes.data)
         unsat = z < 90
         assert k1[unsat].mean() < 0.5 and (k1 & k2)[unsat].mean() < 0.3, (max_cov, k1[unsat].mean(), (k1 & k2)[unsat].mean())
 
