@@ -65,6 +65,8 @@ rr_k_relvars_pairs(const uint32_t *__restrict__ bits, const uint32_t *__restrict
         for (int j = 0; j < 4; j++) {
             const int a = a0 + i * 16 + ty, b = b0 + j * 16 + tx;
             if (a >= nsel || b >= nsel || b < first_partner[a]) continue;               // 2461: j >= i + 100
+            // mark[] is racy by design: byte flags that are only ever set to 1, read here as a hint (a stale 0 costs a
+            // redundant evaluation, never a wrong result)
             if (mark[a] && mark[b]) continue;                                           // the pair could only set marks that are set
             // Relative_Group_Significance(Groups[j], Groups[i], U): Group1 = the later group (2465)
             const unsigned gr1 = (unsigned)gsize_u[sel[b]], gr2 = (unsigned)gsize_u[sel[a]], sc = s[i][j];
