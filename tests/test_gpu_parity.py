@@ -47,9 +47,18 @@ def check_against_oracle(M, A, P, oracle, mincov, M0=None, A0=None, P0=None):
 _ORACLE_SCANS = {}
 
 
+# the MSA made by the reference's own pipeline joined the fixtures after the round's last GPU call: it is run from a file
+# that sorts last (tests/test_zz_gpu_real_pipeline.py), so that a first failure there cannot hide this file under `-x`
+LATE_CASES = {"real_pipeline_msareal"}
+
+
 @pytest.mark.parametrize("variant", VARIANTS)
-@pytest.mark.parametrize("name,cov", GOLDEN_CASES)
+@pytest.mark.parametrize("name,cov", [c for c in GOLDEN_CASES if c[0] not in LATE_CASES])
 def test_golden_cases(name, cov, variant, tmp_path):
+    run_golden_case(name, cov, variant, tmp_path)
+
+
+def run_golden_case(name, cov, variant, tmp_path):
     text = golden_msa(name)
     msa = rr.MSA.from_text(text)
     oracle = O.Oracle.from_text(text, tmp_path)

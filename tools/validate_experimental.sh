@@ -10,7 +10,7 @@ set -u
 mkdir -p gpurun_out
 python -m pytest tests/test_zz_gpu_relvars.py -m gpu -q -p no:cacheprovider > gpurun_out/exp_relvars_default.log 2>&1
 echo "relvars default rc=$?" | tee -a gpurun_out/exp_relvars_default.log
-python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -k real_pipeline > gpurun_out/exp_real_pipeline.log 2>&1
+python -m pytest tests/test_zz_gpu_real_pipeline.py -m gpu -q -p no:cacheprovider > gpurun_out/exp_real_pipeline.log 2>&1
 echo "real pipeline golden rc=$?" | tee -a gpurun_out/exp_real_pipeline.log
 RR_TEST_UNVALIDATED=1 python -m pytest tests/test_zz_gpu_cliquer.py tests/test_zz_gpu_relvars.py tests/test_zz_gpu_kmeans.py -m gpu -q \
     -p no:cacheprovider > gpurun_out/exp_unvalidated.log 2>&1
