@@ -264,7 +264,10 @@ rr_k_cliquer_counts2(const uint32_t *__restrict__ bits, const uint32_t *__restri
 //     loads per word instead of 12 and six;
 //   * a chunk is skipped unless some read is covered by the candidate site AND by one of the block's queries (word-wise
 //     AND with the union of the queries' coverage, instead of the two chunk-level tests);
-//   * three blocks per SM (launch bound 85 registers) instead of two.
+//   * three blocks per SM (launch bound 85 registers) instead of two;
+//   * the coverage word of the next chunk is requested while the current chunk is counted: in the SASS view of the
+//     one-step kernel 21 % of the warp-state samples sit on the consumers of the two dependent loads per chunk
+//     (profiles/r1_cliquer_source_hotspots.txt), and with 4 warps per scheduler nothing hides them.
 __global__ void __launch_bounds__(CLQ_WARPS * 32, 3)
 rr_k_cliquer_counts3(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ covbits, int W32,
                      const int32_t *__restrict__ queries, int nq, int anfang, int ende, int min_s, double greedy,
@@ -303,27 +306,37 @@ rr_k_cliquer_counts3(const uint32_t *__restrict__ bits, const uint32_t *__restri
         }
         const uint32_t *cb = covbits + (size_t)ii * W32;
         const uint32_t *gb = bits + (size_t)ii * 5 * W32;
-        for (int c = 0; c < nchunks; c++) {
+        // chunks no query of the block touches are stepped over; the coverage word of the NEXT chunk is requested before
+        // the current one is counted, so that its round trip to L2 overlaps the counting (in the one-step kernel the two
+        // dependent loads per chunk - coverage word, then group words - are what the warps wait for)
+        int c = 0;
+        while (c < nchunks && qmask[c] == 0u) c++;
+        uint32_t cx = (c < nchunks && c * 32 + lane < W32) ? __ldg(cb + c * 32 + lane) : 0u;
+        while (c < nchunks) {
+            int cn = c + 1;
+            while (cn < nchunks && qmask[cn] == 0u) cn++;
+            const uint32_t cx_next = (cn < nchunks && cn * 32 + lane < W32) ? __ldg(cb + cn * 32 + lane) : 0u;
             const unsigned m = qmask[c];
-            if (m == 0u) continue;
             const int w = c * 32 + lane;
-            const uint32_t cx = w < W32 ? __ldg(cb + w) : 0u;
-            if (__ballot_sync(CLQ_FULL, (cx & qany[w]) != 0u) == 0u) continue;   // no read covered on both sides
-            uint32_t x[4];
+            if (__ballot_sync(CLQ_FULL, (cx & qany[w]) != 0u) != 0u) {           // else: no read covered on both sides
+                uint32_t x[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) x[k] = w < W32 ? __ldg(gb + (size_t)k * W32 + w) : 0u;
+                for (int k = 0; k < 4; k++) x[k] = w < W32 ? __ldg(gb + (size_t)k * W32 + w) : 0u;
 #pragma unroll
-            for (int q = 0; q < CLQ_QB; q++) {
-                if (!((m >> q) & 1u)) continue;                      // warp-uniform
-                const uint32_t y = qg[q * W32p + w], cy = qc[q * W32p + w];
+                for (int q = 0; q < CLQ_QB; q++) {
+                    if (!((m >> q) & 1u)) continue;                              // warp-uniform
+                    const uint32_t y = qg[q * W32p + w], cy = qc[q * W32p + w];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    s[q][k] += __popc(x[k] & y);
-                    g1[q][k] += __popc(x[k] & cy);
+                    for (int k = 0; k < 4; k++) {
+                        s[q][k] += __popc(x[k] & y);
+                        g1[q][k] += __popc(x[k] & cy);
+                    }
+                    g2[q] += __popc(y & cx);
+                    cv[q] += __popc(cx & cy);
                 }
-                g2[q] += __popc(y & cx);
-                cv[q] += __popc(cx & cy);
             }
+            c = cn;
+            cx = cx_next;
         }
         int ms = 0, mg1 = 0, mg2 = 0, mcv = 0;
 #pragma unroll
