@@ -56,13 +56,14 @@ enum {
 
 /* flags */
 #define RR_FLAG_NO_PRUNE 1u      /* evaluate the exact score of every pair test (no bound-based skipping) */
-#define RR_FLAG_HOST_FINALIZE 2u /* re-evaluate each group's winning pair with the host libm so that the
-                                    "%f" text is byte-identical to the reference's (device exp/log10
-                                    differ from glibc by <= 2 ulp) */
+#define RR_FLAG_HOST_FINALIZE 2u /* rr_maxcorr_run only: re-evaluate each group's winning pair with the host libm so
+                                    that the "%f" text is byte-identical to the reference's (device exp/log10 differ
+                                    from glibc by <= 2 ulp).  rr_scan rejects it: callers that merge several rr_scan
+                                    results themselves call rr_scan_finalize after their merge */
 #define RR_FLAG_GENERAL_BREAK 4u /* force the general first-break computation (MaxCorrelation.c:807-810)
                                     even when every row is one contiguous span */
 
-#define RR_FLAG_SEED_ONLY 8u     /* run only the seeding pass (every 32nd row tile): multi-GPU runs
+#define RR_FLAG_SEED_ONLY 8u     /* run only the seeding pass (every 64th row tile): multi-GPU runs
                                     exchange the resulting maxima as thresholds before the full pass */
 #define RR_FLAG_SKIP_SEED 16u    /* keep the running maxima already on the device (previous RR_FLAG_SEED_ONLY
                                     scan and/or rr_scan_set_thresholds) and go straight to the full pass */
@@ -122,6 +123,10 @@ int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *stats);
 /* copy the last scan's result to the host: maxcorr[5*cols] (line g of MaxCorrsOf_*,
  * g = 5*site + {A,C,G,T,gap}); argmax[5*cols] = partner group id or -1 (may be NULL) */
 int rr_scan_fetch(rr_packed *pk, double *maxcorr, int32_t *argmax);
+/* RR_FLAG_HOST_FINALIZE as a call: maxcorr[g] of every group with a partner (argmax[g] >= 0) is re-evaluated with
+ * the host libm from the pair's device-side counts; maxcorr / argmax as returned by rr_scan_fetch or merged from
+ * several parts (element-wise max, ties to the smaller partner) */
+int rr_scan_finalize(rr_packed *pk, double *maxcorr, const int32_t *argmax);
 /* raise the running maxima on the device to at least thr[5*cols] (e.g. the max over all GPUs' seeding passes);
  * a value taken from thr carries no partner: it only prunes, and loses every tie against a real pair */
 int rr_scan_set_thresholds(rr_packed *pk, const double *thr);
@@ -204,18 +209,20 @@ int rr_cliquer_from_hits(int64_t n_queries, const int32_t *query_groups, int64_t
                          const int32_t *gsize, int64_t n_groups, int mincov, int maxclique, double greedy,
                          int32_t *members, double *scores, int32_t *n_members);
 
-/* ---- scope row 8f-3: Relative_Vars (RepeatResolver.c:2424-2493), first version ------------------------------------
+/* ---- scope row 8f-3: Relative_Vars (RepeatResolver.c:2424-2493) ----------------------------------------------------
  * Which groups vary inside part u_no of a read partition: groups with MaxCorrs > cutoff that hold at least mingroup
  * reads of the part and have a partner at least 100 group ids away whose two-sided hypergeometric score restricted
  * to the part's reads (Relative_Group_Significance 506-523, CumHypGeo_Log 490-504) exceeds cutoff.
  * unterteilung: [rows of msa] part number of every read; maxcorrs: [5 * cols]; vars: [5 * cols + 1], receives the
  * ascending group ids followed by -1 (the reference's terminator, 2483).  mingroup >= 1 and cutoff >= 0 are required.
- * This version packs the part's rows as an MSA of their own on `device` (rr_pack), takes the triple intersections
- * from rr_pair_counts and scores on the host with the same libm as the reference (bit-identical). */
+ * rr_relative_vars packs the part's rows as an MSA of their own on `device` (rr_pack), which turns the triple
+ * intersections into pair intersections; counts, score bound, exact score and marks run in one tiled kernel
+ * (csrc/rr_relvars.cu); pairs whose device score lies within 1e-9 of the cutoff are decided with the host libm, so the
+ * selection is identical to the reference's. */
 int rr_relative_vars(const rr_msa *msa, int device, const int32_t *unterteilung, int u_no, const double *maxcorrs,
                      double cutoff, int mingroup, int32_t *vars, int *n_vars, int64_t *pairs_tested /* may be NULL */);
-/* EXPERIMENTAL (never run on a GPU): the same on the packed copy of the whole MSA already on the device (e.g. after
- * rr_scan): nothing is packed again, the part is applied as a mask; unterteilung indexes the rows of the MSA pk was made of */
+/* the same on the packed copy of the whole MSA already on the device (e.g. after rr_scan): nothing is packed again, the
+ * part is applied as a mask inside the kernel; unterteilung indexes the rows of the MSA pk was made of */
 int rr_relative_vars_packed(rr_packed *pk, const int32_t *unterteilung, int u_no, const double *maxcorrs, double cutoff,
                             int mingroup, int32_t *vars, int *n_vars, int64_t *pairs_tested /* may be NULL */);
 /* the host half on given counts (tests): gsize_u[g] = |G_g & U|, cov_u = |U|; with S == NULL only the selection
@@ -224,7 +231,7 @@ int rr_relative_vars_from_counts(int64_t n_groups, const double *maxcorrs, const
                                  int mingroup, const int32_t *S, int32_t *sel_out, int *n_sel, int32_t *vars, int *n_vars);
 double rr_relative_score_host(uint32_t schnitt, uint32_t gr1, uint32_t gr2, uint32_t cov);
 
-/* ---- scope row 8f-4: Kmeans (RepeatResolver.c:2604-2821), EXPERIMENTAL (device part never run on a GPU yet) --------
+/* ---- scope row 8f-4: Kmeans (RepeatResolver.c:2604-2821) ------------------------------------------------------------
  * Splits part u_no of the read partition by the reads' signatures over the groups `vars` (the output of Relative_Vars):
  * unterteilung[rows of msa] is updated in place exactly as the reference does (the part's reads get cluster + max + 1,
  * 2814-2815), *n_clusters = the reference's return value (non-empty clusters).  All arithmetic is integer: bit-exact. */

@@ -17,7 +17,7 @@
  * oracle/gsl_shim.c, exactly as MaxCorrelation.c:415 goes through GSL
  * (GSL version unpinned by the reference -> parity unpinned at that boundary,
  * see gsl_shim.c).  This restatement is validated against the UNMODIFIED
- * reference compiled into oracle/_ref (tests/test_oracle_vs_ref.py, and the
+ * reference compiled into oracle/_ref (tests/test_oracle.py, and the
  * committed fixtures under tests/golden/ made by oracle/gen_golden.py).
  */
 #include <stdio.h>
@@ -140,6 +140,15 @@ void rr_oracle_counts(const rr_oracle *o, int i, int j, int out[4])
     out[3] = rr_isect(ci, cj, sc);
     out[1] = rr_isect(gi, cj, sc);
     out[2] = rr_isect(gj, ci, sc);
+}
+
+/* Schnitt (114-125) for every pair of two group lists: out[a * nc + b] = |G_rows[a] & G_cols[b]| */
+void rr_oracle_count_matrix(const rr_oracle *o, int nr, const int32_t *rows, int nc, const int32_t *cols, int32_t *out)
+{
+    int a, b, sc = o->sc;
+    for (a = 0; a < nr; a++)
+        for (b = 0; b < nc; b++)
+            out[(size_t)a * nc + b] = rr_isect(o->groups + (size_t)rows[a] * sc, o->groups + (size_t)cols[b] * sc, sc);
 }
 
 /* MaxCorrelation.c:413-434 (PositiveCumHypGeo_Log + PositiveSignificance tail)

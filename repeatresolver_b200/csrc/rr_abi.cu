@@ -18,6 +18,7 @@
 #include "rr_device.cuh"
 #include "rr_plan.h"
 #include "rr_kmeans.h"
+#include "../../include/rr_debug.h"
 
 #include <chrono>
 static double rr_now_ms()
@@ -254,6 +255,30 @@ static int dev_alloc(T **p, size_t count)
     return RR_OK;
 }
 
+// device buffers of one call, returned to the pool on every exit path
+struct dev_scope {
+    std::vector<void *> ptrs;
+    template <typename T>
+    int alloc(T **p, size_t count)
+    {
+        int rc = dev_alloc(p, count);
+        if (!rc) ptrs.push_back(*p);
+        return rc;
+    }
+    ~dev_scope() { for (void *p : ptrs) rr_dev_free(p); }
+};
+
+struct event_scope {
+    std::vector<cudaEvent_t> evs;
+    int create(cudaEvent_t *e)
+    {
+        if (cudaEventCreate(e) != cudaSuccess) { cudaGetLastError(); return 1; }
+        evs.push_back(*e);
+        return 0;
+    }
+    ~event_scope() { for (cudaEvent_t e : evs) cudaEventDestroy(e); }
+};
+
 extern "C" void rr_packed_free(rr_packed *pk)
 {
     if (!pk) return;
@@ -367,8 +392,9 @@ static int pack_impl(const rr_msa *msa, int device, rr_packed *pk)
     if (pk->W32 == 0) pk->W32 = 4;
     RR_CUDA(cudaStreamCreateWithFlags(&pk->st, cudaStreamNonBlocking));
     rr_alloc_stream(pk->st);
+    event_scope ev;                                                      // destroyed on every exit path
     cudaEvent_t e0, e1, e2;
-    RR_CUDA(cudaEventCreate(&e0)); RR_CUDA(cudaEventCreate(&e1)); RR_CUDA(cudaEventCreate(&e2));
+    if (ev.create(&e0) || ev.create(&e1) || ev.create(&e2)) { rr_set_error("cudaEventCreate failed"); return RR_E_CUDA; }
 
     const size_t ncell = (size_t)R * N;
     int rc;
@@ -384,12 +410,12 @@ static int pack_impl(const rr_msa *msa, int device, rr_packed *pk)
     RR_TRACE("pack: h2d issued");
     // spans -> row order (by span start, then end; uncovered rows last)
     int32_t *d_span = nullptr;
-    if ((rc = dev_alloc(&d_span, (size_t)3 * std::max(R, 1)))) return rc;
+    dev_scope span_scope;                                                // d_span goes back to the pool on every exit path
+    if ((rc = span_scope.alloc(&d_span, (size_t)3 * std::max(R, 1)))) return rc;
     RR_CUDA(rr_launch_row_spans(pk->d_cells, R, N, codes, d_span, d_span + R, d_span + 2 * (size_t)R, pk->st));
     std::vector<int32_t> span((size_t)3 * std::max(R, 1));
     RR_CUDA(cudaMemcpyAsync(span.data(), d_span, sizeof(int32_t) * 3 * (size_t)R, cudaMemcpyDeviceToHost, pk->st));
     RR_CUDA(cudaStreamSynchronize(pk->st));
-    rr_dev_free(d_span);
     RR_TRACE("pack: spans back");
     std::vector<int32_t> perm(R);
     std::iota(perm.begin(), perm.end(), 0);
@@ -451,7 +477,6 @@ static int pack_impl(const rr_msa *msa, int device, rr_packed *pk)
     RR_CUDA(cudaEventElapsedTime(&pk->h2d_ms, e0, e1));
     RR_CUDA(cudaEventElapsedTime(&pk->pack_ms, e1, e2));
     if (rr_trace_on()) fprintf(stderr, "[rr trace] h2d %.3f ms (%.1f GB/s), pack %.3f ms\n", pk->h2d_ms, ncell / (pk->h2d_ms * 1e6), pk->pack_ms);
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     return RR_OK;
 }
 
@@ -491,19 +516,6 @@ extern "C" int rr_packed_sizes(rr_packed *pk, int32_t *gsize, int32_t *coverage)
     if (coverage) memcpy(coverage, pk->h_coverage.data(), sizeof(int32_t) * pk->h_coverage.size());
     return RR_OK;
 }
-
-// device buffers of one call, returned to the pool on every exit path
-struct dev_scope {
-    std::vector<void *> ptrs;
-    template <typename T>
-    int alloc(T **p, size_t count)
-    {
-        int rc = dev_alloc(p, count);
-        if (!rc) ptrs.push_back(*p);
-        return rc;
-    }
-    ~dev_scope() { for (void *p : ptrs) rr_dev_free(p); }
-};
 
 extern "C" int rr_pair_counts(rr_packed *pk, int64_t n, const int32_t *gi, const int32_t *gj, int32_t *out)
 {
@@ -576,7 +588,7 @@ extern "C" int rr_cliquer_from_counts(int query_group, int64_t n, const int32_t 
                                       const int32_t *sizes, int size_query, int mincov, int maxclique, double greedy,
                                       int32_t *members, double *scores, int *n_members)
 {
-    if (n < 0 || maxclique < 1 || mincov < 0 || !members || !scores || !n_members || (n && (!groups || !counts || !sizes))) {
+    if (n < 0 || maxclique < 1 || mincov < 0 || !(greedy >= 0.0) || !members || !scores || !n_members || (n && (!groups || !counts || !sizes))) {
         rr_set_error("rr_cliquer_from_counts: bad arguments");
         return RR_E_ARG;
     }
@@ -591,7 +603,9 @@ extern "C" int rr_cliquer_from_counts(int query_group, int64_t n, const int32_t 
 extern "C" int rr_cliquer(rr_packed *pk, int query_group, int anfang, int ende, int mincov, int maxclique, double greedy,
                           int32_t *members, double *scores, int *n_members)
 {
-    if (!pk || maxclique < 1 || mincov < 0 || !members || !scores || !n_members) { rr_set_error("rr_cliquer: bad arguments"); return RR_E_ARG; }
+    // greedy >= 0: TheBestUpdater only ever replaces entries of Best_Corrs that start at 0.0 (1156-1176), so no score <= 0 can
+    // enter a clique; a negative greedy would let the candidates skipped by 1210/1215 (scored 0 here) in
+    if (!pk || maxclique < 1 || mincov < 0 || !(greedy >= 0.0) || !members || !scores || !n_members) { rr_set_error("rr_cliquer: bad arguments"); return RR_E_ARG; }
     if (query_group < 0 || query_group >= 5 * pk->N) { rr_set_error("rr_cliquer: group %d out of range", query_group); return RR_E_ARG; }
     anfang = std::max(anfang, 0);
     ende = std::min(ende, pk->N);
@@ -696,7 +710,7 @@ extern "C" int rr_cliquer_from_hits(int64_t nq, const int32_t *queries, int64_t 
                                     const int32_t *gsize, int64_t n_groups, int mincov, int maxclique, double greedy,
                                     int32_t *members, double *scores, int32_t *n_members)
 {
-    if (nq < 0 || nq > 0x7fffffff || n_hits < 0 || maxclique < 1 || mincov < 0 || !gsize || (n_hits && !hit_records) ||
+    if (nq < 0 || nq > 0x7fffffff || n_hits < 0 || maxclique < 1 || mincov < 0 || !(greedy >= 0.0) || !gsize || (n_hits && !hit_records) ||
         (nq && (!queries || !members || !scores || !n_members))) {
         rr_set_error("rr_cliquer_from_hits: bad arguments");
         return RR_E_ARG;
@@ -715,7 +729,10 @@ extern "C" int rr_cliquer_from_hits(int64_t nq, const int32_t *queries, int64_t 
     return RR_OK;
 }
 
-#define RR_CLIQUER_KERNEL_DEFAULT 1
+// capacity of the candidate / hit lists of rr_cliquer_batch (records of 32 bytes); tests lower it to force the retry path
+static std::atomic<unsigned long long> g_cliquer_cap{1ull << 24};
+extern "C" void rr_debug_set_cliquer_cap(unsigned long long cap) { g_cliquer_cap = cap ? cap : (1ull << 24); }
+
 static void clq_release(int32_t *q, unsigned long long *c, rr_clq_rec *a, rr_clq_rec *b, cudaEvent_t e0, cudaEvent_t e1)
 {
     rr_dev_free(q); rr_dev_free(c); rr_dev_free(a); rr_dev_free(b);
@@ -728,7 +745,7 @@ extern "C" int rr_cliquer_batch(rr_packed *pk, int64_t nq, const int32_t *querie
                                 rr_cliquer_stats *stats)
 {
     if (stats) memset(stats, 0, sizeof(*stats));
-    if (!pk || nq < 0 || nq > 0x7fffffff || maxclique < 1 || mincov < 0 || std::isnan(greedy) ||
+    if (!pk || nq < 0 || nq > 0x7fffffff || maxclique < 1 || mincov < 0 || !(greedy >= 0.0) ||
         (nq && (!queries || !members || !scores || !n_members))) {
         rr_set_error("rr_cliquer_batch: bad arguments");
         return RR_E_ARG;
@@ -747,10 +764,7 @@ extern "C" int rr_cliquer_batch(rr_packed *pk, int64_t nq, const int32_t *querie
     RR_CUDA(cudaSetDevice(pk->device));
     rr_alloc_stream(pk->st);
 
-    int kernel = RR_CLIQUER_KERNEL_DEFAULT;
-    if (const char *e = getenv("RR_CLIQUER_KERNEL")) kernel = atoi(e) == 2 ? 2 : atoi(e) == 3 ? 3 : 1;   // tests / probes: both count kernels
-    unsigned long long cap = 1ull << 24;                                 // entries of 32 bytes per list
-    if (const char *e = getenv("RR_CLIQUER_CAP")) cap = std::max(1ull, strtoull(e, nullptr, 10));   // tests: force the retry path
+    unsigned long long cap = g_cliquer_cap;                              // entries of 32 bytes per list
     int64_t group_len = std::min<int64_t>(nq, 4096);
     cap = std::min(cap, (unsigned long long)group_len * n_cand_groups);
 
@@ -787,7 +801,7 @@ extern "C" int rr_cliquer_batch(rr_packed *pk, int64_t nq, const int32_t *querie
         float ms = 0.f;
         CLQ_CUDA(cudaMemsetAsync(d_counters, 0, 2 * sizeof(unsigned long long), pk->st));
         CLQ_CUDA(cudaEventRecord(ev0, pk->st));
-        CLQ_CUDA(rr_launch_cliquer(kernel, pk->d_bits, pk->d_covbits, pk->d_gsize, pk->d_lnfact, pk->W32, d_queries + q0, n, anfang, ende,
+        CLQ_CUDA(rr_launch_cliquer(pk->d_bits, pk->d_covbits, pk->d_gsize, pk->d_lnfact, pk->W32, d_queries + q0, n, anfang, ende,
                                    mincov / 4, greedy, thr, d_cand, d_hits, cap, d_counters, pk->n_sm, pk->st));
         CLQ_CUDA(cudaEventRecord(ev1, pk->st));
         CLQ_CUDA(cudaMemcpyAsync(cnt, d_counters, sizeof(cnt), cudaMemcpyDeviceToHost, pk->st));
@@ -830,9 +844,11 @@ extern "C" int rr_cliquer_batch(rr_packed *pk, int64_t nq, const int32_t *querie
 }
 
 // ---------------------------------------------------------------------------------------
-// Relative_Vars (RepeatResolver.c:2424-2493), first version: the rows of the part are packed as an MSA of their own, so
-// that the triple intersections |Gi & Gj & U| are plain pair intersections of that MSA (rr_pair_counts) and |Gi & U|
-// its group sizes; selection, the two-sided score (rr_relative_significance) and the marks are host code.
+// Relative_Vars (RepeatResolver.c:2424-2493): the masked Gram matrix X^T diag(u) X over the selected groups.  Either the
+// rows of the part are packed as an MSA of their own (rr_relative_vars: the triple intersections |Gi & Gj & U| become plain
+// pair intersections and |Gi & U| its group sizes), or the part is a mask over the packed copy of the whole MSA
+// (rr_relative_vars_packed).  Selection on the host; counts, the two-sided score bound, the exact score and the marks in
+// the tiled kernel of rr_relvars.cu; pairs within 1e-9 of the cutoff are decided with the host libm.
 // ---------------------------------------------------------------------------------------
 extern "C" double rr_relative_score_host(uint32_t s, uint32_t gr1, uint32_t gr2, uint32_t cov)
 {
@@ -959,8 +975,7 @@ static int relvars_device_pairs(rr_packed *pk, const uint32_t *d_umask, const in
     return RR_OK;
 }
 
-// EXPERIMENTAL (never run on a GPU): Relative_Vars on the packed copy of the WHOLE MSA as it sits on the device after the
-// scan - nothing is packed again; the part is a bitset over the packed row order, |G & U| comes from rr_k_masked_sizes and
+// Relative_Vars on the packed copy of the WHOLE MSA as it sits on the device after the scan - nothing is packed again; the part is a bitset over the packed row order, |G & U| comes from rr_k_masked_sizes and
 // the all-pairs step from the tiled kernel with the mask ANDed into one operand.
 extern "C" int rr_relative_vars_packed(rr_packed *pk, const int32_t *unterteilung, int u_no, const double *maxcorrs, double cutoff,
                                        int mingroup, int32_t *vars, int *n_vars, int64_t *pairs_tested)
@@ -1035,40 +1050,9 @@ extern "C" int rr_relative_vars(const rr_msa *msa, int device, const int32_t *un
     std::vector<int32_t> sel;
     relvars_select((int64_t)5 * N, maxcorrs, gsize_u, cutoff, mingroup, sel);
     std::vector<uint8_t> mark(sel.size(), 0);
-    if (getenv("RR_RELVARS_KERNEL") && atoi(getenv("RR_RELVARS_KERNEL")) == 1 && !sel.empty()) {
-        // EXPERIMENTAL (rr_relvars.cu, not yet run on a GPU): the all-pairs step in one tiled kernel; pairs it cannot decide
-        // (score within 1e-9 of the cutoff) come back in a list and are scored here with the host libm
-        rc = relvars_device_pairs(pk, nullptr, gsize_u, sel, cov_u, cutoff, mark, pairs_tested);
-        rr_packed_free(pk);
-        if (rc) return rc;
-        int n = 0;
-        for (size_t a = 0; a < sel.size(); a++)
-            if (mark[a]) vars[n++] = sel[a];
-        vars[n] = -1;
-        *n_vars = n;
-        return RR_OK;
-    }
-    constexpr int64_t CHUNK = (int64_t)4 << 20;                          // pairs per rr_pair_counts call
-    std::vector<int32_t> pa, pb, gi, gj, cnt;
-    int64_t tested = 0;
-    auto flush = [&]() -> int {
-        if (pa.empty()) return RR_OK;
-        cnt.resize(4 * pa.size());
-        int e = rr_pair_counts(pk, (int64_t)pa.size(), gi.data(), gj.data(), cnt.data());
-        if (e) return e;
-        relvars_mark(sel, (int64_t)pa.size(), pa.data(), pb.data(), cnt.data(), 4, gsize_u, cov_u, cutoff, mark);
-        tested += (int64_t)pa.size();
-        pa.clear(); pb.clear(); gi.clear(); gj.clear();
-        return RR_OK;
-    };
-    for (size_t a = 0; a < sel.size() && !rc; a++)
-        for (size_t b = relvars_first_partner(sel, a); b < sel.size() && !rc; b++) {
-            if (mark[a] && mark[b]) continue;                            // the pair could only set marks that are set
-            pa.push_back((int32_t)a); pb.push_back((int32_t)b);
-            gi.push_back(sel[b]); gj.push_back(sel[a]);                  // counts[0] = |G_b & G_a| within the part's rows
-            if ((int64_t)pa.size() >= CHUNK) rc = flush();
-        }
-    if (!rc) rc = flush();
+    // the all-pairs step in one tiled kernel (rr_relvars.cu); pairs it cannot decide (score within 1e-9 of the cutoff)
+    // come back in a list and are scored with the host libm
+    if (!sel.empty()) rc = relvars_device_pairs(pk, nullptr, gsize_u, sel, cov_u, cutoff, mark, pairs_tested);
     rr_packed_free(pk);
     if (rc) return rc;
     int n = 0;
@@ -1076,14 +1060,13 @@ extern "C" int rr_relative_vars(const rr_msa *msa, int device, const int32_t *un
         if (mark[a]) vars[n++] = sel[a];
     vars[n] = -1;
     *n_vars = n;
-    if (pairs_tested) *pairs_tested = tested;
     return RR_OK;
 }
 
 // ---------------------------------------------------------------------------------------
-// Kmeans (RepeatResolver.c:2604-2821), EXPERIMENTAL: signatures and the dissolution of small clusters on the host, the
-// two read x read sweeps and the centroids on the device (rr_kmeans.cu, never run on a GPU yet).  The host pieces and the
-// integer rules shared with the kernels (rr_kmeans.h) are pinned against the unmodified reference on the CPU.
+// Kmeans (RepeatResolver.c:2604-2821): signatures and the dissolution of small clusters on the host, the two read x read
+// sweeps and the centroids on the device (rr_kmeans.cu).  The host pieces and the integer rules shared with the kernels
+// (rr_kmeans.h) are pinned against the unmodified reference on the CPU, the device path on a B200 (tests/test_zz_gpu_kmeans.py).
 // ---------------------------------------------------------------------------------------
 static inline int host_class(uint8_t c, int codes)                       // 304-329, as rr_classify in rr_pack.cu
 {
@@ -1241,19 +1224,25 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
         rr_set_error("rr_scan: part %d of %d", opts->part_index, opts->part_count);
         return RR_E_ARG;
     }
+    if (opts->flags & RR_FLAG_HOST_FINALIZE) {
+        rr_set_error("rr_scan: RR_FLAG_HOST_FINALIZE is a flag of rr_maxcorr_run; after rr_scan + rr_scan_fetch call rr_scan_finalize");
+        return RR_E_ARG;
+    }
     RR_CUDA(cudaSetDevice(pk->device));
     rr_alloc_stream(pk->st);
     const int R = pk->R, N = pk->N, mincov = opts->mincov;
+    event_scope ev;                                                      // destroyed on every exit path
     cudaEvent_t e0, e1, e2;
-    RR_CUDA(cudaEventCreate(&e0)); RR_CUDA(cudaEventCreate(&e1)); RR_CUDA(cudaEventCreate(&e2));
+    if (ev.create(&e0) || ev.create(&e1) || ev.create(&e2)) { rr_set_error("cudaEventCreate failed"); return RR_E_CUDA; }
     RR_CUDA(cudaEventRecord(e0, pk->st));
 
     int variant = opts->variant;
     if (variant == RR_VARIANT_AUTO) variant = rr_umma_available() ? RR_VARIANT_UMMA_MXF4 : RR_VARIANT_BITSET;
     if (variant != RR_VARIANT_BITSET && variant != RR_VARIANT_UMMA && variant != RR_VARIANT_UMMA_F4 && variant != RR_VARIANT_UMMA_MXF4) { rr_set_error("unknown variant %d", variant); return RR_E_ARG; }
 
-    // fp32 accumulation of 0/1 products is exact only below 2^24 reads: deeper MSAs use the int8/int32 coding
-    if ((variant == RR_VARIANT_UMMA_MXF4 || variant == RR_VARIANT_UMMA_F4) && R >= (1 << 24)) variant = RR_VARIANT_UMMA;
+    // the accumulators hold 4 x count (operand elements 0 / 2); fp32 accumulation is exact only below 2^24, i.e. 2^22
+    // reads: deeper MSAs use the int8/int32 coding
+    if ((variant == RR_VARIANT_UMMA_MXF4 || variant == RR_VARIANT_UMMA_F4) && R >= (1 << 22)) variant = RR_VARIANT_UMMA;
     const int umma_mode = variant == RR_VARIANT_UMMA_MXF4 ? 2 : variant == RR_VARIANT_UMMA_F4 ? 1 : 0;
     // ---- host plan: filters, first-break columns, tiles, partition (O(N)); cached between scans ----
     const bool general = !pk->contiguous || (opts->flags & RR_FLAG_GENERAL_BREAK);
@@ -1336,9 +1325,6 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
     pk->have_result = true;
     executed = plan.executed_ops;
 
-    if (opts->flags & 0x800u)
-        fprintf(stderr, "[rr stats] tier2 evals %llu, exact evals %llu, series iterations %llu (lower-tail candidates %llu), sum of per-batch max iterations %llu\n",
-                counters[4], counters[1], counters[5], counters[6], counters[7]);
     if (stats) {
         memset(stats, 0, sizeof *stats);
         stats->pair_tests = (int64_t)counters[0];
@@ -1353,14 +1339,10 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
         cudaEventElapsedTime(&stats->prepare_ms, e0, e1);
         cudaEventElapsedTime(&stats->kernel_ms, e1, e2);
     }
-#ifndef RR_EXP   // (timing-experiment builds change the counts on purpose)
-    if ((int64_t)counters[0] != plan.part_pairs && !(opts->flags & (0x700u | RR_FLAG_SEED_ONLY))) {
+    if ((int64_t)counters[0] != plan.part_pairs && !(opts->flags & (RR_DEBUG_MMA_ONLY | RR_FLAG_SEED_ONLY))) {
         rr_set_error("pair-test count mismatch: device %llu, host plan %lld", counters[0], (long long)plan.part_pairs);
-        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
         return RR_E_CUDA;
     }
-#endif
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     return RR_OK;
 }
 
@@ -1420,6 +1402,92 @@ extern "C" int rr_scan_fetch(rr_packed *pk, double *maxcorr, int32_t *argmax)
     return RR_OK;
 }
 
+// RR_FLAG_HOST_FINALIZE as a call of its own (rr_maxcorr_run uses it after its merge; one-process-per-GPU callers after
+// theirs): maxcorr[g] of every group with a partner is re-evaluated with the host libm from the pair's counts, which
+// come from the device bitsets (rr_pair_counts) - so the "%f" text is byte-identical to the reference's.
+extern "C" int rr_scan_finalize(rr_packed *pk, double *maxcorr, const int32_t *argmax)
+{
+    if (!pk || ((!maxcorr || !argmax) && pk->N > 0)) { rr_set_error("rr_scan_finalize: bad arguments"); return RR_E_ARG; }
+    const size_t G = (size_t)5 * pk->N;
+    std::vector<int32_t> gi, gj;
+    std::vector<size_t> idx;
+    for (size_t g = 0; g < G; g++)
+        if (argmax[g] >= 0) {
+            if ((size_t)argmax[g] >= G) { rr_set_error("rr_scan_finalize: partner %d out of range", argmax[g]); return RR_E_ARG; }
+            const int32_t a = (int32_t)g, b = argmax[g];
+            gi.push_back(std::min(a, b)); gj.push_back(std::max(a, b)); idx.push_back(g);
+        }
+    std::vector<int32_t> cnt(4 * gi.size());
+    int rc = rr_pair_counts(pk, (int64_t)gi.size(), gi.data(), gj.data(), cnt.data());
+    if (rc) return rc;
+    const std::vector<int32_t> &gs = pk->h_gsize;
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>({(size_t)8, (size_t)std::thread::hardware_concurrency(), idx.size() / 4096 + 1}));
+    auto work = [&](int t) {
+        for (size_t k = idx.size() * t / nt; k < idx.size() * (t + 1) / nt; k++)
+            maxcorr[idx[k]] = rr_score_host((uint32_t)cnt[4 * k], (uint32_t)cnt[4 * k + 1], (uint32_t)cnt[4 * k + 2],
+                                            (uint32_t)cnt[4 * k + 3], gs[gi[k]], gs[gj[k]]);
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) th.emplace_back(work, t);
+        for (auto &t : th) t.join();
+    }
+    return RR_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// test hook (include/rr_debug.h): one accumulator tile of the tcgen05 kernel
+// ---------------------------------------------------------------------------------------
+extern "C" int rr_debug_umma_counts(rr_packed *pk, const rr_scan_opts *opts, int row_tile, int col_tile, int32_t *counts,
+                                    int32_t *row_groups, int32_t *col_groups, int *n_row_tiles, int *n_col_tiles)
+{
+    if (!pk || !opts) { rr_set_error("rr_debug_umma_counts: bad arguments"); return RR_E_ARG; }
+    scan_cache &C = pk->cache;
+    int variant = opts->variant == RR_VARIANT_AUTO ? RR_VARIANT_UMMA_MXF4 : opts->variant;
+    if (!C.valid || !pk->umma || C.variant != variant || C.mincov != opts->mincov || C.part_index != opts->part_index ||
+        C.part_count != opts->part_count || variant == RR_VARIANT_BITSET) {
+        rr_set_error("rr_debug_umma_counts: call rr_scan with the same options (a tcgen05 variant) first");
+        return RR_E_ARG;
+    }
+    if (n_row_tiles) *n_row_tiles = C.plan.n_rowblocks;
+    if (n_col_tiles) *n_col_tiles = C.plan.n_colblocks;
+    if (!counts) return RR_OK;
+    RR_CUDA(cudaSetDevice(pk->device));
+    rr_alloc_stream(pk->st);
+    const int mode = variant == RR_VARIANT_UMMA_MXF4 ? 2 : variant == RR_VARIANT_UMMA_F4 ? 1 : 0;
+    const int M = 128, NC = 5 * rr_umma_col_sites(), RS = rr_umma_row_sites();
+    dev_scope scope;
+    int32_t *d_out = nullptr;
+    unsigned long long *d_cnt = nullptr;
+    int rc;
+    if ((rc = scope.alloc(&d_out, (size_t)M * NC)) || (rc = scope.alloc(&d_cnt, 8))) return rc;
+    RR_CUDA(cudaMemsetAsync(d_cnt, 0, 8 * sizeof(unsigned long long), pk->st));
+    rr_scan_params P;
+    memset(&P, 0, sizeof P);
+    scan_buffers &sb = C.sb;
+    P.R = pk->R; P.N = pk->N; P.W32 = pk->W32; P.mincov = opts->mincov; P.flags = 0;
+    P.bits = pk->d_bits; P.gsize = pk->d_gsize; P.rowok = sb.rowok; P.colok = sb.colok;
+    P.breakcol = sb.breakcol; P.rowsites = sb.rowsites; P.n_rowsites = C.plan.n_rowsites;
+    P.lnfact = pk->d_lnfact; P.best = pk->d_best; P.counters = d_cnt;
+    P.n_rowblocks = C.plan.n_rowblocks; P.n_colblocks = C.plan.n_colblocks;
+    if ((rc = rr_umma_dump_tile(pk->umma, mode, C.plan_id, P, C.plan, row_tile, col_tile, d_out, pk->n_sm, pk->st))) return rc;
+    RR_CUDA(cudaMemcpyAsync(counts, d_out, sizeof(int32_t) * (size_t)M * NC, cudaMemcpyDeviceToHost, pk->st));
+    RR_CUDA(cudaStreamSynchronize(pk->st));
+    if (row_groups)
+        for (int r = 0; r < M; r++) {
+            const int l = r & 31, slab = r >> 5;
+            const int site = l < 30 ? C.plan.rowsites[(size_t)row_tile * RS + slab * 6 + l / 5] : -1;
+            row_groups[r] = site >= 0 ? 5 * site + l % 5 : -1;
+        }
+    if (col_groups)
+        for (int c = 0; c < NC; c++) {
+            const int64_t g = (int64_t)col_tile * NC + c;
+            col_groups[c] = g < (int64_t)5 * pk->N ? (int32_t)g : -1;
+        }
+    return RR_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // the whole path: pack on n GPUs, scan one part each, merge (882-891)
 // ---------------------------------------------------------------------------------------
@@ -1454,11 +1522,12 @@ extern "C" int rr_maxcorr_run(const rr_msa *msa, int mincov, int n_gpus, int var
 
     auto worker = [&](int d) {
         rr_scan_opts o;
-        o.mincov = mincov; o.variant = variant; o.flags = flags; o.part_index = d; o.part_count = n_gpus;
+        const unsigned scan_flags = flags & ~RR_FLAG_HOST_FINALIZE;
+        o.mincov = mincov; o.variant = variant; o.flags = scan_flags; o.part_index = d; o.part_count = n_gpus;
         int rc = rr_pack(msa, d, &PK[d]);
         if (n_gpus > 1) {
             // seeding pass on every GPU, max over GPUs as common thresholds, then the full pass
-            if (!rc) { o.flags = flags | RR_FLAG_SEED_ONLY; rc = rr_scan(PK[d], &o, &S[d]); }
+            if (!rc) { o.flags = scan_flags | RR_FLAG_SEED_ONLY; rc = rr_scan(PK[d], &o, &S[d]); }
             if (!rc) rc = rr_scan_fetch(PK[d], M[d].data(), nullptr);
             RC[d] = rc;
             barrier();
@@ -1473,7 +1542,7 @@ extern "C" int rr_maxcorr_run(const rr_msa *msa, int mincov, int n_gpus, int var
             barrier();
             if (!all_ok) { if (rc) ERR[d] = rr_last_error(); return; }
             rc = rr_scan_set_thresholds(PK[d], thr.data());
-            o.flags = flags | RR_FLAG_SKIP_SEED;
+            o.flags = scan_flags | RR_FLAG_SKIP_SEED;
         }
         if (!rc) rc = rr_scan(PK[d], &o, &S[d]);
         if (!rc) {
@@ -1527,27 +1596,11 @@ extern "C" int rr_maxcorr_run(const rr_msa *msa, int mincov, int n_gpus, int var
         }
         RR_TRACE("run: merged");
         if (flags & RR_FLAG_HOST_FINALIZE) {
-            // the winners' counts come from the device bitsets; only exp/log10 of the 5N winning
-            // pairs are redone with the host libm
-            std::vector<int32_t> gi, gj;
-            std::vector<size_t> idx;
-            for (size_t g = 0; g < G; g++)
-                if (A[0][g] >= 0) {
-                    const int32_t a = (int32_t)g, b = A[0][g];
-                    gi.push_back(std::min(a, b)); gj.push_back(std::max(a, b)); idx.push_back(g);
-                }
-            std::vector<int32_t> cnt(4 * gi.size());
             cudaEvent_t a, b;
             cudaSetDevice(PK[0]->device);
             cudaEventCreate(&a); cudaEventCreate(&b);
             cudaEventRecord(a, PK[0]->st);
-            rc = rr_pair_counts(PK[0], (int64_t)gi.size(), gi.data(), gj.data(), cnt.data());
-            if (!rc) {
-                const std::vector<int32_t> &gs = PK[0]->h_gsize;
-                for (size_t k = 0; k < idx.size(); k++)
-                    maxcorr_out[idx[k]] = rr_score_host((uint32_t)cnt[4 * k], (uint32_t)cnt[4 * k + 1], (uint32_t)cnt[4 * k + 2],
-                                                        (uint32_t)cnt[4 * k + 3], gs[gi[k]], gs[gj[k]]);
-            }
+            rc = rr_scan_finalize(PK[0], maxcorr_out, A[0].data());
             cudaEventRecord(b, PK[0]->st);
             cudaEventSynchronize(b);
             if (stats) cudaEventElapsedTime(&stats->finalize_ms, a, b);

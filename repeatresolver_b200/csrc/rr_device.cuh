@@ -33,7 +33,7 @@ struct rr_scan_params {
     int n_rowsites;
     const double *lnfact;        // [R+2] ln(n!)
     rr_best_t *best;             // [5N]
-    unsigned long long *counters; // [4]: pair tests, exact evals, bound evals, work units
+    unsigned long long *counters; // [8]: pair tests, exact evals, bound evals, work units, tier-2 evals
     // work decomposition (bitset kernel): row blocks x column blocks
     const int64_t *unit_prefix;  // [n_rowblocks+1] prefix sum of column-block counts
     const int32_t *unit_cb0;     // [n_rowblocks] first column block of each row block
@@ -182,6 +182,24 @@ __device__ __forceinline__ bool rr_tier1_f32(const LTF &T, unsigned s, unsigned 
     return nz & !(U < thr);
 }
 
+// The same test on counts scaled by 2^QSHIFT (the tcgen05 kernel's accumulators hold count << 2 = the byte offset of
+// ln(count!) in the float table): T is addressed by the scaled value, every difference of scaled counts is a scaled
+// count, and x is kept a multiple of 2^QSHIFT.  Decides exactly as rr_tier1_f32 on the unscaled counts.
+template <int QSHIFT, class LTQ>
+__device__ __forceinline__ bool rr_tier1_q(const LTQ &T, unsigned s, unsigned gr1, unsigned gr2, unsigned cov,
+                                           float thr, float lnc3, float meanfac, float margin)
+{
+    constexpr unsigned ONE = 1u << QSHIFT;
+    const bool nz = s != 0u;
+    const unsigned hi = gr1 < gr2 ? gr1 : gr2;
+    unsigned x = ((unsigned)(meanfac * (float)gr2) & ~(ONE - 1u)) + ONE;   // (floor(mean) + 1) << QSHIFT
+    x = x > s ? x : s;
+    x = x < hi ? x : hi;
+    const float lp = ((T(gr2) - T(x)) - T(gr2 - x)) + ((T(cov - gr2) - T(gr1 - x)) - T((cov + x) - (gr1 + gr2))) - lnc3;
+    const float U = -(float)RR_LOG10E * lp + margin;
+    return nz & !(U < thr);
+}
+
 // tier 2: P[X >= s] >= sum_{x = x0}^{x0+m} pmf(x) for any x0 >= s; the window starts next to the mean
 // (or at s above it) and the term ratios are accumulated in FP32, every factor rounded down.
 template <class LT>
@@ -229,21 +247,10 @@ static __device__ __noinline__ void rr_drain_exact(const rr_scan_params &P, rr_c
         if (lane < take) {
             const rr_cand c = q[count - take + lane];
             n_exact++;
-            if (!(P.flags & 0x100u)) {  // 0x100: timing experiment, skip the evaluation
-                int iters = 0;
-                const double Z = rr_positive_significance(P.lnfact, c.s, c.gr1, c.gr2, c.cov, __ldg(P.gsize + c.gi),
-                                                          __ldg(P.gsize + c.gj), (P.flags & 0x800u) ? &iters : nullptr);
-                if (P.flags & 0x800u) {  // 0x800: statistics on the series lengths
-                    atomicAdd(P.counters + 5, (unsigned long long)(iters < 0 ? -iters : iters));
-                    if (iters < 0) atomicAdd(P.counters + 6, 1ull);
-                    int mx = iters < 0 ? -iters : iters;
-                    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(__activemask(), mx, o));
-                    if (lane == 0) atomicAdd(P.counters + 7, (unsigned long long)mx);
-                }
-                if (Z > 0.0) {
-                    if (Z >= rr_best_value(P.best + c.gi)) rr_best_update(P.best, c.gi, Z, c.gj);
-                    if (Z >= rr_best_value(P.best + c.gj)) rr_best_update(P.best, c.gj, Z, c.gi);
-                }
+            const double Z = rr_positive_significance(P.lnfact, c.s, c.gr1, c.gr2, c.cov, __ldg(P.gsize + c.gi), __ldg(P.gsize + c.gj));
+            if (Z > 0.0) {
+                if (Z >= rr_best_value(P.best + c.gi)) rr_best_update(P.best, c.gi, Z, c.gj);
+                if (Z >= rr_best_value(P.best + c.gj)) rr_best_update(P.best, c.gj, Z, c.gi);
             }
         }
         count -= take;

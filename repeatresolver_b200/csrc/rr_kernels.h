@@ -35,25 +35,24 @@ cudaError_t rr_launch_pack_int8(const uint8_t *cells, const int32_t *perm, int R
 
 // Cliquer (rr_cliquer.cu): one listed (query slot, candidate group) pair with its four counts and, once scored, Z
 #define RR_CLQ_QB 4      // queries per block of rr_k_cliquer_counts
-#define RR_CLQ_QB2 6     // queries per block of rr_k_cliquer_counts2
 #define RR_CLQ_SLAB 256  // candidate sites per block
 struct rr_clq_rec {
     int32_t slot, group, s, gr1, gr2, cov;
     double z;
 };
 size_t rr_cliquer_smem_bytes(int W32);
-cudaError_t rr_launch_cliquer(int kernel /* 1: one-step counts, 2: two-step */, const uint32_t *bits, const uint32_t *covbits, const int32_t *gsize, const double *lnf,
+cudaError_t rr_launch_cliquer(const uint32_t *bits, const uint32_t *covbits, const int32_t *gsize, const double *lnf,
                               int W32, const int32_t *queries, int nq, int anfang, int ende, int min_s, double greedy,
                               double threshold, rr_clq_rec *cand, rr_clq_rec *hits, unsigned long long cap,
                               unsigned long long *counters, int n_sm, cudaStream_t st);
 
-// Relative_Vars (rr_relvars.cu, experimental): the all-pairs step on the packed rows of one part
+// Relative_Vars (rr_relvars.cu): the all-pairs step on the packed rows of one part
 cudaError_t rr_launch_masked_sizes(const uint32_t *bits, const uint32_t *umask, int64_t nsets, int W32, int32_t *sizes, cudaStream_t st);
 cudaError_t rr_launch_relvars_pairs(const uint32_t *bits, const uint32_t *umask /* NULL: bits are the part's own rows */, int W32, const int32_t *sel, int nsel, const int32_t *first_partner,
                                     const int32_t *gsize_u, int cov_u, const double *lnf, double cutoff, unsigned char *mark,
                                     int4 *unsure, unsigned int unsure_cap, unsigned int *unsure_count, cudaStream_t st);
 
-// Kmeans (rr_kmeans.cu, experimental): the two read x read sweeps and the centroids on the part's signatures
+// Kmeans (rr_kmeans.cu): the two read x read sweeps and the centroids on the part's signatures
 cudaError_t rr_launch_kmeans_sweeps(const uint64_t *sig, int anzahl, int scv, int32_t *best_j, uint64_t *cen, int32_t *cluster,
                                     cudaStream_t st);
 

@@ -208,13 +208,13 @@ __global__ void __launch_bounds__(256) rr_k_pack_int8(const uint8_t *__restrict_
         if (!fp4) {
             uint32_t v = 0;
 #pragma unroll
-            for (int b = 0; b < 4; b++) v |= (tile[lane * 4 + b][cl] == k ? 1u : 0u) << (8 * b);
+            for (int b = 0; b < 4; b++) v |= (tile[lane * 4 + b][cl] == k ? 2u : 0u) << (8 * b);   // elements 0 / 2: see rr_scan_umma.cu
             *reinterpret_cast<uint32_t *>(xb + ((size_t)5 * col + k) * Kp + r0 + lane * 4) = v;
         } else {
-            // packed e2m1: 1.0 = 0b0010, two reads per byte, row stride Kp/2 bytes
+            // packed e2m1: 2.0 = 0b0100, two reads per byte, row stride Kp/2 bytes
             uint32_t v = 0;
 #pragma unroll
-            for (int b = 0; b < 4; b++) v |= (tile[lane * 4 + b][cl] == k ? 2u : 0u) << (4 * b);
+            for (int b = 0; b < 4; b++) v |= (tile[lane * 4 + b][cl] == k ? 4u : 0u) << (4 * b);
             *reinterpret_cast<uint16_t *>(xb + ((size_t)5 * col + k) * (Kp / 2) + r0 / 2 + lane * 2) = (uint16_t)v;
         }
     }

@@ -14,8 +14,12 @@
 //   K          reads in span-start order; only the K blocks [k_lo(col tile), k_hi(row tile)) (128 reads, 256 for
 //              mxf4) can hold a read covering both tiles, the rest is skipped exactly.
 //
+// Operand elements are 0 / 2 (not 0 / 1): a product is 4 = sizeof(float), so an accumulator holds 4 x count, which is
+// the byte offset of ln(count!) in the float table the epilogue's bounds look up - no shift-and-add per look-up.
+//
 // Warp roles (one persistent CTA per SM, 640 threads):
-//   warp 0      TMA producer (one elected lane): A and B boxes of a K block -> smem stage
+//   warp 0      producer (one elected lane): per tile one bulk copy of the tile's 240 running maxima + admissibility
+//               masks into a 2-deep shared-memory ring, then per K block the A and B boxes by TMA -> smem stage
 //   warp 1      TMEM allocator + MMA issuer (one elected lane): 4 x tcgen05.mma per stage,
 //               tcgen05.commit frees the stage / publishes the accumulator
 //   warps 2-3   idle (keep the epilogue warps aligned to the TMEM lane quarters); warps 0-3 give their registers
@@ -32,6 +36,7 @@
 #include "rr_kernels.h"
 #include "rr_device.cuh"
 #include "rr_plan.h"
+#include "../../include/rr_debug.h"
 
 namespace {
 
@@ -46,12 +51,14 @@ constexpr int UM_B_BYTES = UM_N * UM_KB;         // 30720
 constexpr int UM_STAGE_BYTES = UM_A_BYTES + UM_B_BYTES;  // 47104 = 46 * 1024
 constexpr int UM_FIRST_EPI_WARP = 4;
 constexpr int UM_EPI_WARPS = 16;
-constexpr int UM_THREADS = (UM_FIRST_EPI_WARP + UM_EPI_WARPS) * 32;  // 512
+constexpr int UM_THREADS = (UM_FIRST_EPI_WARP + UM_EPI_WARPS) * 32;  // 640
 constexpr int UM_SUB = UM_EPI_WARPS / 4;         // epilogue warps per TMEM lane quarter
-constexpr int UM_WSITES = UM_COL_SITES / UM_SUB; // column sites per warp and tile (16)
+constexpr int UM_WSITES = UM_COL_SITES / UM_SUB; // column sites per warp and tile (12)
 constexpr int UM_TMEM_COLS = 512;
 constexpr int UM_ACC_STRIDE = 256;               // TMEM columns between the two accumulators
 constexpr int UM_SF_COL = 240;                   // 16 spare TMEM columns behind accumulator 0: unit block scales (mxf4)
+constexpr int UM_QSHIFT = 2;                     // accumulators hold count << UM_QSHIFT (operand elements are 2)
+constexpr int UM_CMASK_BYTES = 48;               // admissibility masks of a tile's column sites (one byte per site)
 
 struct __align__(16) um_wsite {                   // one column site: read by the whole warp as two 16-byte broadcasts
     float mj[5];                                  // running maxima, rounded down to float (thresholds only)
@@ -61,12 +68,17 @@ struct __align__(16) um_wsite {                   // one column site: read by th
 struct um_wmeta {                                 // per epilogue warp: metadata of its column sites in the tile
     um_wsite site[UM_WSITES];
 };
+struct __align__(16) um_thr_buf {                 // per tile, written by the producer's bulk copies
+    rr_best_t best[UM_N];                         // running maxima of the tile's column groups as they are in HBM
+    uint8_t cmask[64];                            // [UM_COL_SITES] bit b: group b of the site is admissible (817)
+};
 
 struct um_smem_tail {
     um_wmeta meta[UM_EPI_WARPS];
     rr_cand q1[UM_EPI_WARPS][RR_QUEUE_CAP];       // tier-1 survivors, one queue per epilogue warp
     rr_cand q2[UM_EPI_WARPS][RR_QUEUE_CAP];       // tier-2 survivors (exact evaluation pending)
-    unsigned long long full[UM_STAGES], empty[UM_STAGES], tfull[2], tempty[2];
+    um_thr_buf thr[2];
+    unsigned long long full[UM_STAGES], empty[UM_STAGES], tfull[2], tempty[2], bfull[2], bempty[2];
     uint32_t tmem_base;
 };
 
@@ -74,6 +86,7 @@ constexpr size_t UM_TAIL_OFF = (size_t)UM_STAGES * UM_STAGE_BYTES;
 constexpr size_t UM_LNF_OFF = (UM_TAIL_OFF + sizeof(um_smem_tail) + 15) & ~(size_t)15;
 constexpr size_t UM_SMEM_MAX = 227 * 1024;
 constexpr int UM_LNF_MAX = (int)((UM_SMEM_MAX - UM_LNF_OFF) / sizeof(float));  // ln(n!) float entries that fit
+static_assert(UM_LNF_MAX >= 4096, "the float ln(n!) table should hold the depths of the bench workloads");
 
 struct um_unit { int32_t rt, ct0, ct1; };         // row tile, column tiles [ct0, ct1)
 
@@ -84,8 +97,11 @@ struct um_params {
     const int32_t *k_hi;      // [2][n_rt] exclusive K-block bound per length class of rows (rr_plan.h) and row tile
     const int32_t *k_lo;      // [2][n_ct] inclusive K-block bound per class and column tile
     int n_rt, n_ct;
+    const uint8_t *colmask;   // [n_ct * 48 (+ padding)] per column site: bit b = group b admissible as a column group
     int lnf_smem;             // ln(n!) entries (as float) staged in shared memory
     float t1_margin;          // FP32 tier-1 rounding margin, log10 units (see rr_tier1_f32)
+    int preseed;              // pre-seed launch: subsample the rows of first-visit columns
+    int32_t *dump;            // DUMP instantiation only: [UM_M][UM_N] counts of the (single) tile processed
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -122,18 +138,21 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 // for the single-lane producer / MMA warps: back off so the spin does not steal issue slots from the epilogue
 __device__ __forceinline__ void mbar_wait_sleep(unsigned long long *bar, uint32_t parity, unsigned ns)
 {
-#ifdef RR_NO_SLEEP
-    (void)ns;
-    while (!mbar_try_wait(bar, parity)) {}
-#else
     while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
-#endif
 }
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1)
 {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+// plain bulk copy global -> shared (16-byte aligned on both sides, size a multiple of 16), completion on an mbarrier
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -205,16 +224,13 @@ __device__ __forceinline__ uint32_t make_idesc()
 // sum of x over the 5 lanes of a site (lanes 5t..5t+4), returned in every lane of the site
 __device__ __forceinline__ int site_sum5(int x, int base_lane)
 {
-#if defined(RR_EXP) && (RR_EXP & 2)   // timing experiment only (wrong results): no shuffles
-    return x * 5 + base_lane;
-#endif
     int s1 = x + __shfl_down_sync(0xffffffffu, x, 1);
     int s2 = s1 + __shfl_down_sync(0xffffffffu, s1, 2);
     int s = s2 + __shfl_down_sync(0xffffffffu, x, 4);
     return __shfl_sync(0xffffffffu, s, base_lane);
 }
 
-// the same for two counts at once, packed 16 + 16 bits (every sum is <= the shared coverage <= R < 65536)
+// the same for two counts at once, packed 16 + 16 bits (every sum is <= 4 x the shared coverage <= 4 R < 65536)
 __device__ __forceinline__ void site_sum5_x2(int x0, int x1, int base_lane, int &s0, int &s1)
 {
     const int s = site_sum5(x0 | (x1 << 16), base_lane);
@@ -224,33 +240,41 @@ __device__ __forceinline__ void site_sum5_x2(int x0, int x1, int base_lane, int 
 
 extern __shared__ __align__(1024) uint8_t um_smem[];
 
-// ln(n!) for the bounds.  ALL_SMEM: every argument (<= largest column coverage) is inside the table staged in
-// shared memory; otherwise the tail of the table is read from HBM/L2.
+// ln(n!) for the bounds, addressed by the BYTE OFFSET 4 n (what the accumulators hold).  ALL_SMEM: every argument
+// (<= largest column coverage) is inside the table staged in shared memory; otherwise the tail of the table is read
+// from HBM/L2.
 template <bool ALL_SMEM>
 struct um_lnf {
-    uint32_t base;   // shared-window address of the float table (computed once: every look-up is LEA + LDS)
-    int n_smem;
+    uint32_t base;   // shared-window address of the float table
+    unsigned smem_bytes;
     const double *gmem;
-    __device__ __forceinline__ float lds(unsigned n) const
+    __device__ __forceinline__ float lds(unsigned off) const
     {
-#if defined(RR_EXP) && (RR_EXP & 1)   // timing experiment only (wrong results): no table look-ups
-        return __uint_as_float(base + 4u * n);
-#endif
-#if defined(RR_EXP) && (RR_EXP & 2)
-        n &= 511u;
-#endif
         float v;
-        asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + 4u * n));
+        asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + off));
         return v;
     }
-    __device__ __forceinline__ float operator()(unsigned n) const
+    __device__ __forceinline__ float operator()(unsigned off) const
     {
-        if constexpr (ALL_SMEM) return lds(n);
-        else return n < (unsigned)n_smem ? lds(n) : (float)__ldg(gmem + n);
+        if constexpr (ALL_SMEM) return lds(off);
+        else return off < smem_bytes ? lds(off) : (float)__ldg(gmem + (off >> UM_QSHIFT));
     }
 };
 
-template <bool ALL_SMEM, int MODE>
+// a threshold from the high word of a running maximum (a non-negative double): dropping the low word and rounding
+// down can only lower it (thresholds may be stale or low, never high)
+__device__ __forceinline__ float um_thr_hi(uint32_t hi, bool no_prune)
+{
+    return rr_thr_f32(__hiloint2double((int)hi, 0), no_prune);
+}
+__device__ __forceinline__ uint32_t um_best_hi(const rr_best_t *p)
+{
+    uint32_t hi;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(hi) : "l"(reinterpret_cast<const char *>(p) + 4));
+    return hi;
+}
+
+template <bool ALL_SMEM, int MODE, bool DUMP>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const um_params U)
 {
@@ -261,11 +285,15 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // the warp index through a shuffle: the compiler then keeps it (and what derives from it) in uniform registers
     // instead of re-reading SR_TID inside the epilogue loop
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const bool mma_only = (P.flags & RR_DEBUG_MMA_ONLY) != 0;   // timing decomposition: accumulators released unread
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();  // the swizzled operand tiles need a 1024-byte aligned base
         for (int s = 0; s < UM_STAGES; s++) { mbar_init(&T->full[s], 1); mbar_init(&T->empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&T->tfull[a], 1); mbar_init(&T->tempty[a], UM_EPI_WARPS); }
+        for (int a = 0; a < 2; a++) {
+            mbar_init(&T->tfull[a], 1); mbar_init(&T->tempty[a], UM_EPI_WARPS);
+            mbar_init(&T->bfull[a], 1); mbar_init(&T->bempty[a], UM_EPI_WARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -297,16 +325,23 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp < UM_FIRST_EPI_WARP) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == 0) {
-        // ================= TMA producer =================
+        // ================= producer =================
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
-            uint32_t it = 0;
+            uint32_t it = 0, tix = 0;
             for (int u = blockIdx.x; u < U.n_units; u += gridDim.x) {
                 const um_unit un = U.units[u];
                 const int khi[2] = {U.k_hi[un.rt], U.k_hi[U.n_rt + un.rt]};
-                for (int ct = un.ct0; ct < un.ct1; ct++) {
-                    if (U.P.flags & 0x8000u) continue;  // timing experiment: epilogue only
+                for (int ct = un.ct0; ct < un.ct1; ct++, tix++) {
+                    {   // the tile's running maxima and admissibility masks, one tile ahead of the epilogue at least
+                        const int tb = tix & 1;
+                        mbar_wait_sleep(&T->bempty[tb], ((tix >> 1) & 1) ^ 1, 64);
+                        const int ng = min(UM_N, 5 * U.P.N - ct * UM_N);
+                        mbar_expect_tx(&T->bfull[tb], (uint32_t)(ng * sizeof(rr_best_t) + UM_CMASK_BYTES));
+                        bulk_load(&T->thr[tb].best[0], U.P.best + (size_t)ct * UM_N, (uint32_t)(ng * sizeof(rr_best_t)), &T->bfull[tb]);
+                        bulk_load(&T->thr[tb].cmask[0], U.colmask + (size_t)ct * UM_CMASK_BYTES, UM_CMASK_BYTES, &T->bfull[tb]);
+                    }
                     for (int seg = 0; seg < 2; seg++)
                     for (int kb = U.k_lo[seg * U.n_ct + ct]; kb < khi[seg]; kb++, it++) {
                         const int s = it % UM_STAGES;
@@ -333,7 +368,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int ct = un.ct0; ct < un.ct1; ct++) {
                     const int klo[2] = {U.k_lo[ct], U.k_lo[U.n_ct + ct]};
                     // no read covers both tiles: the epilogue uses zeros
-                    if ((klo[0] >= khi[0] && klo[1] >= khi[1]) || (U.P.flags & 0x8000u)) continue;
+                    if (klo[0] >= khi[0] && klo[1] >= khi[1]) continue;
                     const int acc = tile & 1;
                     const uint32_t aph = (tile >> 1) & 1;
                     mbar_wait_sleep(&T->tempty[acc], aph ^ 1, 128);
@@ -367,6 +402,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
         // ================= epilogue =================
+        // all counts below are in units of 1/4 (count << UM_QSHIFT), as the accumulators deliver them
         const int ew = warp - UM_FIRST_EPI_WARP;  // 0..UM_EPI_WARPS-1
         const int quarter = warp & 3;            // TMEM lane quarter this warp may access
         const int sub = ew >> 2;                 // which of the UM_SUB warps of the quarter
@@ -374,16 +410,16 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int a = lane - site_l * 5;         // group within the site
         const int base_lane = site_l * 5;
         const bool lane_row = lane < 30;
-        unsigned n_pairs = 0, n_exact = 0, n_bound = 0, n_units = 0, n_tier2 = 0;
-        uint32_t tile = 0;
+        unsigned n_pairs = 0, n_exact = 0, n_units = 0, n_tier2 = 0;
+        uint32_t tile = 0, tix = 0;
         rr_cand *q1 = T->q1[ew], *q2 = T->q2[ew];
         um_wmeta &M = T->meta[ew];
         int c1n = 0, c2n = 0;
         const bool no_prune = (P.flags & RR_FLAG_NO_PRUNE) != 0;
-        const bool pack16 = P.R < 65536;
-        const bool subsample = (P.flags & 0x2000u) != 0;  // set by the host for the pre-seed launch only
+        const bool pack16 = P.R < (65536 >> UM_QSHIFT);
+        const bool subsample = U.preseed != 0;   // set by the host for the pre-seed launch only
         um_lnf<ALL_SMEM> LT;     // float table, tier 1
-        LT.base = (uint32_t)__shfl_sync(0xffffffffu, (int)smem_u32(lnf_s), 0); LT.n_smem = U.lnf_smem; LT.gmem = P.lnfact;
+        LT.base = (uint32_t)__shfl_sync(0xffffffffu, (int)smem_u32(lnf_s), 0); LT.smem_bytes = (unsigned)U.lnf_smem << UM_QSHIFT; LT.gmem = P.lnfact;
         rr_lnf_global LG;        // double table in HBM/L2, tier 2 (rare, evaluated 32 at a time)
         LG.gmem = P.lnfact;
         const float margin = U.t1_margin;
@@ -397,73 +433,76 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int gi = ii >= 0 ? 5 * ii + a : -1;
             const bool row_ok = gi >= 0 && P.rowok[gi] != 0;
             const int brk = ii >= 0 ? min(P.breakcol[ii], P.N) : 0;
-            float thr_i = 0.0f;                    // running max of row group i, rounded down (refreshed from HBM)
+            uint32_t row_hi = row_ok ? um_best_hi(P.best + gi) : 0u;   // running max of row group i (high word), refreshed per tile
 
-            for (int ct = un.ct0; ct < un.ct1; ct++) {
-                const bool has_counts = (U.k_lo[ct] < khi0 || U.k_lo[U.n_ct + ct] < khi1) && !(P.flags & 0x8000u);
+            for (int ct = un.ct0; ct < un.ct1; ct++, tix++) {
+                const bool has_counts = U.k_lo[ct] < khi0 || U.k_lo[U.n_ct + ct] < khi1;
                 const int jsite0 = ct * UM_COL_SITES;
-                // ---- this warp's column groups: sites sub, sub+UM_SUB, ... (slot w <-> site sub + w*UM_SUB)
-                // all loads of the tile's thresholds are issued back to back (the maximum is read whether or not the
-                // group is admissible) so that one L2 round trip covers them
-                __syncwarp();
+                // ---- this warp's column groups: sites sub, sub+UM_SUB, ... (slot w <-> site sub + w*UM_SUB), from the
+                // copy of the tile's running maxima the producer has put into shared memory
+                float thr_i = um_thr_hi(row_hi, no_prune);
                 {
+                    const int tb = tix & 1;
+                    const um_thr_buf &B = T->thr[tb];
+                    mbar_wait(&T->bfull[tb], (tix >> 1) & 1);
+                    __syncwarp();
                     static_assert(UM_WSITES * 5 <= 64, "two metadata entries per lane");
                     const int w0 = lane / 5, b0 = lane - w0 * 5;
                     const int e1 = lane + 32, w1 = e1 / 5, b1 = e1 - w1 * 5;
                     const bool has1 = e1 < UM_WSITES * 5;
-                    const int j0 = 5 * (jsite0 + sub + w0 * UM_SUB) + b0, j1 = 5 * (jsite0 + sub + w1 * UM_SUB) + b1;
-                    const bool in0 = j0 < 5 * P.N, in1 = has1 && j1 < 5 * P.N;
-                    const double z0 = in0 ? rr_best_value(P.best + j0) : 0.0;
-                    const double z1 = in1 ? rr_best_value(P.best + j1) : 0.0;
-                    const double zi = row_ok ? rr_best_value(P.best + gi) : 0.0;
-                    const bool ok0 = in0 && P.colok[j0] != 0, ok1 = in1 && P.colok[j1] != 0;
-                    M.site[w0].mj[b0] = ok0 ? rr_thr_f32(z0, no_prune) : -1.0f;   // -1: not admissible (817)
-                    if (has1) M.site[w1].mj[b1] = ok1 ? rr_thr_f32(z1, no_prune) : -1.0f;
-                    if (row_ok) thr_i = rr_thr_f32(zi, no_prune);
+                    const int t0 = sub + w0 * UM_SUB, t1 = sub + w1 * UM_SUB;
+                    const bool ok0 = jsite0 + t0 < P.N && ((B.cmask[t0] >> b0) & 1) != 0;
+                    const bool ok1 = has1 && jsite0 + t1 < P.N && ((B.cmask[has1 ? t1 : 0] >> b1) & 1) != 0;
+                    const uint32_t h0 = (uint32_t)(B.best[5 * t0 + b0].z >> 32);
+                    const uint32_t h1 = has1 ? (uint32_t)(B.best[5 * t1 + b1].z >> 32) : 0u;
+                    M.site[w0].mj[b0] = ok0 ? um_thr_hi(h0, no_prune) : -1.0f;   // -1: not admissible (817)
+                    if (has1) M.site[w1].mj[b1] = ok1 ? um_thr_hi(h1, no_prune) : -1.0f;
+                    if (lane < UM_WSITES) M.site[lane].vmask = jsite0 + sub + lane * UM_SUB < P.N ? (int)(B.cmask[sub + lane * UM_SUB] & 31u) : 0;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&T->bempty[tb]);
+                    // the row group's maximum for the next tile of this unit (consumed at the top of the next iteration)
+                    if (row_ok && ct + 1 < un.ct1) row_hi = um_best_hi(P.best + gi);
                 }
-                __syncwarp();
-                if (lane < UM_WSITES) {
-                    int vm = 0;
-#pragma unroll
-                    for (int b = 0; b < 5; b++) vm |= (M.site[lane].mj[b] >= 0.0f) ? (1 << b) : 0;
-                    M.site[lane].vmask = vm;
-                }
-                __syncwarp();
 
-                int acc = 0;
+                const int acc = tile & 1;
                 if (has_counts) {
-                    acc = tile & 1;
-                    const uint32_t aph = (tile >> 1) & 1;
-                    mbar_wait(&T->tfull[acc], aph);
+                    mbar_wait(&T->tfull[acc], (tile >> 1) & 1);
                     tc_fence_after();
                 }
-                const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * UM_ACC_STRIDE);
+                const int t_end = mma_only ? 0 : min(UM_COL_SITES, P.N - jsite0);
+                if (!has_counts) {
+                    // no read covers both tiles: every count is 0, no pair can score, but the pair tests are counted
+                    for (int w = 0, t = sub; t < t_end; w++, t += UM_SUB) {
+                        const int jj = jsite0 + t;
+                        if (row_ok && jj >= ii + 20 && jj < brk) n_pairs += __popc(M.site[w].vmask);
+                        if constexpr (DUMP)
+                            for (int b = 0; b < 5; b++) U.dump[(size_t)(quarter * 32 + lane) * UM_N + 5 * t + b] = 0;
+                    }
+                    continue;
+                }
                 // 8 TMEM columns are fetched per site (5 used); the load of the next site is in flight
                 // while the current one is processed
                 uint32_t v[8];
-                const int t_end = (P.flags & 0x400u) ? 0 : min(UM_COL_SITES, P.N - jsite0);  // 0x400: MMA only
-                if (has_counts && sub < t_end) TMEM_LD_8(v, taddr0 + 5 * sub);
+                uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * UM_ACC_STRIDE) + 5 * sub;
+                if (sub < t_end) TMEM_LD_8(v, taddr);
 #pragma unroll 1
                 for (int w = 0, t = sub; t < t_end; w++, t += UM_SUB) {
                     int c[5];
-                    if (has_counts) {
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                        for (int b = 0; b < 5; b++) c[b] = MODE != 0 ? (int)__uint_as_float(v[b]) : (int)v[b];
-                        if (t + UM_SUB < t_end) TMEM_LD_8(v, taddr0 + 5 * (t + UM_SUB));
-                    } else {
+                    for (int b = 0; b < 5; b++) c[b] = MODE != 0 ? (int)__uint_as_float(v[b]) : (int)v[b];
+                    taddr += 5 * UM_SUB;
+                    if (t + UM_SUB < t_end) TMEM_LD_8(v, taddr);
+                    if constexpr (DUMP) {
 #pragma unroll
-                        for (int b = 0; b < 5; b++) c[b] = 0;
+                        for (int b = 0; b < 5; b++) U.dump[(size_t)(quarter * 32 + lane) * UM_N + 5 * t + b] = c[b] >> UM_QSHIFT;
                     }
-#if defined(RR_EXP) && (RR_EXP & 8)   // timing experiment: half of the epilogue work
-                    if (w & 1) continue;
-#endif
                     const int jj = jsite0 + t;
                     const bool pair_site = row_ok && jj >= ii + 20 && jj < brk;
                     if (!__any_sync(0xffffffffu, pair_site)) continue;
                     const int rowsum = c[0] + c[1] + c[2] + c[3] + c[4];  // gr1 = |Gi & Cjj|
                     int colsum[5];                                          // gr2 = |Gj & Cii| per column group
-                    if (pack16) {   // R < 65536 (warp-uniform): three shuffle rounds instead of five
+                    if (pack16) {   // 4 R < 65536 (warp-uniform): three shuffle rounds instead of five
                         site_sum5_x2(c[0], c[1], base_lane, colsum[0], colsum[1]);
                         site_sum5_x2(c[2], c[3], base_lane, colsum[2], colsum[3]);
                         colsum[4] = site_sum5(c[4], base_lane);
@@ -492,18 +531,17 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (vmask == 31) {
 #pragma unroll
                         for (int b = 0; b < 5; b++)
-                            need[b] = pair_site & rr_tier1_f32(LT, (unsigned)c[b], (unsigned)rowsum, (unsigned)colsum[b],
-                                                               (unsigned)cov, fminf(thr_i, mjw[b]), lnc3,
-                                                               meanfac, margin);
+                            need[b] = pair_site & rr_tier1_q<UM_QSHIFT>(LT, (unsigned)c[b], (unsigned)rowsum, (unsigned)colsum[b],
+                                                                        (unsigned)cov, fminf(thr_i, mjw[b]), lnc3, meanfac, margin);
                         n_pairs += pair_site ? 5 : 0;
                     } else {
 #pragma unroll
                         for (int b = 0; b < 5; b++) {
                             need[b] = false;
                             if (vmask & (1 << b)) {  // warp-uniform
-                                need[b] = pair_site & rr_tier1_f32(LT, (unsigned)c[b], (unsigned)rowsum,
-                                                                   (unsigned)colsum[b], (unsigned)cov,
-                                                                   fminf(thr_i, mjw[b]), lnc3, meanfac, margin);
+                                need[b] = pair_site & rr_tier1_q<UM_QSHIFT>(LT, (unsigned)c[b], (unsigned)rowsum,
+                                                                            (unsigned)colsum[b], (unsigned)cov,
+                                                                            fminf(thr_i, mjw[b]), lnc3, meanfac, margin);
                                 n_pairs += pair_site;
                             }
                         }
@@ -522,8 +560,9 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         // 88 % of its exact evaluations.  (Kept under RR_FLAG_NO_PRUNE: the exhaustive scan.)
                         need[b] &= no_prune || c[b] + cov != rowsum + colsum[b];
                         rr_cand cand;
-                        cand.s = (uint32_t)c[b]; cand.gr1 = (uint32_t)rowsum; cand.gr2 = (uint32_t)colsum[b];
-                        cand.cov = (uint32_t)cov; cand.gi = gi; cand.gj = 5 * jj + b;
+                        cand.s = (uint32_t)c[b] >> UM_QSHIFT; cand.gr1 = (uint32_t)rowsum >> UM_QSHIFT;
+                        cand.gr2 = (uint32_t)colsum[b] >> UM_QSHIFT; cand.cov = (uint32_t)cov >> UM_QSHIFT;
+                        cand.gi = gi; cand.gj = 5 * jj + b;
                         rr_queue_push(q1, c1n, need[b], cand, lane);
                         if (c1n >= 32) {
                             rr_drain_tier2(P, LG, q1, c1n, q2, c2n, lane, n_tier2, n_exact, false);
@@ -536,28 +575,24 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         }
                     }
                 }
-                if (has_counts) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&T->tempty[acc]);
-                    tile++;
-                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&T->tempty[acc]);
+                tile++;
             }
             rr_drain_tier2(P, LG, q1, c1n, q2, c2n, lane, n_tier2, n_exact, true);
         }
 
-        unsigned long long v0 = n_pairs, v1 = n_exact, v2 = n_bound, v3 = n_units, v4 = n_tier2;
+        unsigned long long v0 = n_pairs, v1 = n_exact, v3 = n_units, v4 = n_tier2;
         for (int o = 16; o > 0; o >>= 1) {
             v0 += __shfl_xor_sync(0xffffffffu, v0, o);
             v1 += __shfl_xor_sync(0xffffffffu, v1, o);
-            v2 += __shfl_xor_sync(0xffffffffu, v2, o);
             v3 += __shfl_xor_sync(0xffffffffu, v3, o);
             v4 += __shfl_xor_sync(0xffffffffu, v4, o);
         }
         if (lane == 0) {
             if (v0) atomicAdd(P.counters + 0, v0);
             if (v1) atomicAdd(P.counters + 1, v1);
-            if (v2) atomicAdd(P.counters + 2, v2);
             if (v3) atomicAdd(P.counters + 3, v3);
             if (v4) atomicAdd(P.counters + 4, v4);
         }
@@ -619,15 +654,16 @@ static int make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t Kp, ui
 }  // namespace
 
 struct rr_umma_state {
-    int8_t *xb[2] = {nullptr, nullptr};   // [0] int8, [1] packed e2m1
+    int8_t *xb[2] = {nullptr, nullptr};   // [0] int8, [1] packed e2m1 (elements 0 / 2)
     int8_t *xa[2] = {nullptr, nullptr};
     size_t xa_rows_cap[2] = {0, 0};
     int64_t Kp = 0;
     um_unit *d_units = nullptr;
     size_t units_cap = 0;
+    uint8_t *d_colmask = nullptr;
+    size_t colmask_cap = 0;
     int32_t *d_khi = nullptr, *d_klo = nullptr;
     size_t khi_cap = 0, klo_cap = 0;
-    bool attr_set = false;
     // what was built for the plan last seen (reused while plan_id and operand coding stay the same)
     uint64_t built_plan_id = 0;
     int built_md = -1;
@@ -645,7 +681,7 @@ void rr_umma_free(rr_umma_state *s)
 {
     if (!s) return;
     for (int m = 0; m < 2; m++) { rr_dev_free(s->xb[m]); rr_dev_free(s->xa[m]); }
-    rr_dev_free(s->d_units); rr_dev_free(s->d_khi); rr_dev_free(s->d_klo);
+    rr_dev_free(s->d_units); rr_dev_free(s->d_khi); rr_dev_free(s->d_klo); rr_dev_free(s->d_colmask);
     delete s;
 }
 
@@ -673,6 +709,53 @@ static int grow(T **p, size_t *cap, size_t need)
     return RR_OK;
 }
 
+// kernel parameters shared by every launch on the plan last built
+static int um_fill_params(rr_umma_state *S, const rr_scan_params &P, const rr_plan &plan, um_params &U, size_t &smem_bytes, bool &all_smem)
+{
+    U.P = P;
+    U.units = S->d_units;
+    U.n_units = S->n_units;
+    U.k_hi = S->d_khi;
+    U.k_lo = S->d_klo;
+    U.n_rt = std::max(plan.n_rowblocks, 1);
+    U.n_ct = std::max(plan.n_colblocks, 1);
+    U.colmask = S->d_colmask;
+    U.preseed = 0;
+    U.dump = nullptr;
+    U.lnf_smem = std::min(std::min(plan.max_cov + 2, P.R + 2), UM_LNF_MAX);
+    smem_bytes = UM_LNF_OFF + (size_t)U.lnf_smem * sizeof(float);
+    // FP32 tier-1 margin: 8 roundings of magnitude <= 2^-24 * ln(maxcov!) each (7 table entries, 6 additions,
+    // generously doubled), in log10 units, plus the 1e-6 of the double-precision version
+    U.t1_margin = (float)(16.0 * 5.9604645e-8 * rr_lnfact((unsigned)std::max(plan.max_cov, 1)) * 0.4342944819 + 2e-6);
+    all_smem = U.lnf_smem >= plan.max_cov + 1;
+    return RR_OK;
+}
+
+template <bool ALL_SMEM, int MODE, bool DUMP>
+static cudaError_t um_launch_one(int grid, size_t smem_bytes, cudaStream_t st, const CUtensorMap &map_a, const CUtensorMap &map_b,
+                                 const um_params &prm)
+{
+    // per device, so set on every launch (a few microseconds)
+    cudaError_t e = cudaFuncSetAttribute(rr_k_scan_umma<ALL_SMEM, MODE, DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX);
+    if (e != cudaSuccess) return e;
+    rr_k_scan_umma<ALL_SMEM, MODE, DUMP><<<grid, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
+    rr_count_launch(1);
+    return cudaGetLastError();
+}
+
+static cudaError_t um_launch(int mode, bool all_smem, bool dump, int grid, size_t smem_bytes, cudaStream_t st, const CUtensorMap &map_a,
+                             const CUtensorMap &map_b, const um_params &prm)
+{
+    if (dump) {   // test hook: any table size, one tile
+        return mode == 2 ? um_launch_one<false, 2, true>(grid, smem_bytes, st, map_a, map_b, prm)
+             : mode == 1 ? um_launch_one<false, 1, true>(grid, smem_bytes, st, map_a, map_b, prm)
+                         : um_launch_one<false, 0, true>(grid, smem_bytes, st, map_a, map_b, prm);
+    }
+    if (mode == 2) return all_smem ? um_launch_one<true, 2, false>(grid, smem_bytes, st, map_a, map_b, prm) : um_launch_one<false, 2, false>(grid, smem_bytes, st, map_a, map_b, prm);
+    if (mode == 1) return all_smem ? um_launch_one<true, 1, false>(grid, smem_bytes, st, map_a, map_b, prm) : um_launch_one<false, 1, false>(grid, smem_bytes, st, map_a, map_b, prm);
+    return all_smem ? um_launch_one<true, 0, false>(grid, smem_bytes, st, map_a, map_b, prm) : um_launch_one<false, 0, false>(grid, smem_bytes, st, map_a, map_b, prm);
+}
+
 int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &P, rr_plan &plan, const uint8_t *d_cells,
                  const int32_t *d_perm, int codes, int n_sm, cudaStream_t st)
 {
@@ -694,7 +777,7 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
         }
         UM_CUDA(rr_launch_pack_int8(d_cells, d_perm, P.R, P.N, codes, S->xb[md], S->Kp, fp4, st));
     }
-    const bool seeding = !(P.flags & (RR_FLAG_NO_PRUNE | RR_FLAG_SKIP_SEED | 0x1000u));
+    const bool seeding = !(P.flags & (RR_FLAG_NO_PRUNE | RR_FLAG_SKIP_SEED));
     if (S->built_plan_id != plan_id || S->built_md != mode) {
         // A operand for this plan's row sites
         const size_t xa_rows = (size_t)std::max(plan.n_rowblocks, 1) * UM_M;
@@ -716,9 +799,7 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
         // work units: (row tile, aligned chunk of UNIT_CT column tiles), this part's row tiles only, ordered in
         // 2-D blocks of GR (48) row tiles x GC (3) chunks so that the ~148 units in flight at any time share a working set
         // (GR A row-tiles + GC*UNIT_CT B column-tiles, a few tens of MB) that stays resident in the 126 MB L2.
-        constexpr int UNIT_CT = 4;
-        static const int GR = getenv("RR_GR") ? atoi(getenv("RR_GR")) : 48;   // tuning knobs (debug)
-        static const int GC = getenv("RR_GC") ? atoi(getenv("RR_GC")) : 3;
+        constexpr int UNIT_CT = 4, GR = 48, GC = 3;   // measured best of six block shapes at config 2
         struct keyed { int64_t key; um_unit u; };
         // generated directly in block order (row group, chunk group, row tile, chunk): no sort needed
         std::vector<um_unit> units;
@@ -752,8 +833,7 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
         // exchange the seeded maxima (all-reduce MAX) before their full passes.
         // The seeding pass itself starts from zero thresholds; a pre-seed over every PRESEED-th seed row tile
         // takes that warm-up on ~1/512 of the row tiles instead of 1/64.
-        static const int SEED = getenv("RR_SEED") ? atoi(getenv("RR_SEED")) : 64;        // tuning knobs (debug)
-        static const int PRESEED = getenv("RR_PRESEED") ? atoi(getenv("RR_PRESEED")) : 8;
+        constexpr int SEED = 64, PRESEED = 8;
         std::vector<um_unit> seed_units, preseed_units;
         if (plan.n_rowblocks >= 2 * SEED) {
             std::vector<keyed> ks;
@@ -782,6 +862,12 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
             if ((rc = grow(&S->d_units, &S->units_cap, units.size() + seed_units.size()))) return rc;
             if ((rc = grow(&S->d_khi, &S->khi_cap, plan.k_hi.size()))) return rc;
             if ((rc = grow(&S->d_klo, &S->klo_cap, plan.k_lo.size()))) return rc;
+            // one byte per column site: which of its groups are admissible column groups (817); padded to whole tiles
+            std::vector<uint8_t> colmask((size_t)std::max(plan.n_colblocks, 1) * UM_CMASK_BYTES + 16, 0);
+            for (int j = 0; j < P.N; j++)
+                for (int b = 0; b < 5; b++) colmask[j] |= (uint8_t)((plan.colok[(size_t)5 * j + b] ? 1 : 0) << b);
+            if ((rc = grow(&S->d_colmask, &S->colmask_cap, colmask.size()))) return rc;
+            UM_CUDA(cudaMemcpyAsync(S->d_colmask, colmask.data(), colmask.size(), cudaMemcpyHostToDevice, st));
             UM_CUDA(cudaMemcpyAsync(S->d_units, units.data(), sizeof(um_unit) * units.size(), cudaMemcpyHostToDevice, st));
             if (!seed_units.empty())
                 UM_CUDA(cudaMemcpyAsync(S->d_units + units.size(), seed_units.data(), sizeof(um_unit) * seed_units.size(),
@@ -801,65 +887,60 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
     plan.executed_ops = S->executed_ops;
     if (S->n_units == 0) return RR_OK;
 
-    if (!S->attr_set) {
-        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
-        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
-        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
-        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
-        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
-        UM_CUDA(cudaFuncSetAttribute(rr_k_scan_umma<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX));
-        S->attr_set = true;
-        rr_trace_mark("umma: func attributes");
-    }
     um_params U;
-    U.P = P;
-    U.units = S->d_units;
-    U.n_units = S->n_units;
-    U.k_hi = S->d_khi;
-    U.k_lo = S->d_klo;
-    U.n_rt = std::max(plan.n_rowblocks, 1);
-    U.n_ct = std::max(plan.n_colblocks, 1);
     const int grid = std::min<int>(n_sm, S->n_units);
-    U.lnf_smem = std::min(std::min(plan.max_cov + 2, P.R + 2), UM_LNF_MAX);
-    const size_t smem_bytes = UM_LNF_OFF + (size_t)U.lnf_smem * sizeof(float);
-    // FP32 tier-1 margin: 8 roundings of magnitude <= 2^-24 * ln(maxcov!) each (7 table entries, 6 additions,
-    // generously doubled), in log10 units, plus the 1e-6 of the double-precision version
-    U.t1_margin = (float)(16.0 * 5.9604645e-8 * rr_lnfact((unsigned)std::max(plan.max_cov, 1)) * 0.4342944819 + 2e-6);
-    const bool all_smem = U.lnf_smem >= plan.max_cov + 1;
-    const CUtensorMap &map_a = S->map_a, &map_b = S->map_b;
-    auto launch = [&](int g, const um_params &prm) {
-        if (mode == 2) {
-            if (all_smem) rr_k_scan_umma<true, 2><<<g, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
-            else rr_k_scan_umma<false, 2><<<g, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
-        } else if (mode == 1) {
-            if (all_smem) rr_k_scan_umma<true, 1><<<g, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
-            else rr_k_scan_umma<false, 1><<<g, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
-        } else {
-            if (all_smem) rr_k_scan_umma<true, 0><<<g, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
-            else rr_k_scan_umma<false, 0><<<g, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
-        }
-    };
+    size_t smem_bytes;
+    bool all_smem;
+    if ((rc = um_fill_params(S, P, plan, U, smem_bytes, all_smem))) return rc;
     if (seeding && S->n_seed > 0) {
         um_params V = U;
         if (S->n_preseed > 0) {
             V.units = S->d_units + S->n_units + S->n_seed;
             V.n_units = S->n_preseed;
-            V.P.flags |= 0x2000u;  // subsample first-visit columns
-            launch(std::min<int>(n_sm, V.n_units), V);
-            V.P.flags &= ~0x2000u;
-            rr_count_launch(1);
-            UM_CUDA(cudaGetLastError());
+            V.preseed = 1;  // subsample first-visit columns
+            UM_CUDA(um_launch(mode, all_smem, false, std::min<int>(n_sm, V.n_units), smem_bytes, st, S->map_a, S->map_b, V));
+            V.preseed = 0;
         }
         V.units = S->d_units + S->n_units;
         V.n_units = S->n_seed;
-        launch(std::min<int>(n_sm, V.n_units), V);
-        rr_count_launch(1);
-        UM_CUDA(cudaGetLastError());
+        UM_CUDA(um_launch(mode, all_smem, false, std::min<int>(n_sm, V.n_units), smem_bytes, st, S->map_a, S->map_b, V));
         UM_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(unsigned long long) * 8, st));
     }
     if (P.flags & RR_FLAG_SEED_ONLY) return RR_OK;
-    launch(grid, U);
-    rr_count_launch(1);
-    UM_CUDA(cudaGetLastError());
+    UM_CUDA(um_launch(mode, all_smem, false, grid, smem_bytes, st, S->map_a, S->map_b, U));
     return RR_OK;
+}
+
+// Test hook (include/rr_debug.h): the raw accumulator of ONE (row tile, column tile) pair as the tcgen05 kernel's
+// epilogue reads it from TMEM, through the same producer / MMA code as the scan (DUMP instantiation of the kernel).
+// Requires a preceding rr_umma_scan with the same mode and plan (operands, tensor maps and ranges are reused).
+int rr_umma_dump_tile(rr_umma_state *S, int mode, uint64_t plan_id, rr_scan_params &P, rr_plan &plan, int rt, int ct,
+                      int32_t *d_out /* device, [128][240] */, int n_sm, cudaStream_t st)
+{
+    int rc;
+    if (!S || S->built_plan_id != plan_id || S->built_md != mode || S->n_units == 0) {
+        rr_set_error("rr_debug_umma_counts: run rr_scan with this variant first");
+        return RR_E_ARG;
+    }
+    if (rt < 0 || rt >= plan.n_rowblocks || ct < 0 || ct >= plan.n_colblocks) { rr_set_error("rr_debug_umma_counts: tile out of range"); return RR_E_ARG; }
+    um_unit one = {rt, ct, ct + 1}, *d_one = nullptr;
+    if (rr_dev_malloc((void **)&d_one, sizeof one) != cudaSuccess) { cudaGetLastError(); rr_set_error("out of device memory"); return RR_E_NOMEM; }
+    um_params U;
+    size_t smem_bytes;
+    bool all_smem;
+    rc = um_fill_params(S, P, plan, U, smem_bytes, all_smem);
+    cudaError_t e = cudaSuccess;
+    if (!rc) {
+        U.units = d_one;
+        U.n_units = 1;
+        U.dump = d_out;
+        U.P.flags |= RR_FLAG_NO_PRUNE;   // thresholds play no part
+        e = cudaMemcpyAsync(d_one, &one, sizeof one, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_out, 0xff, sizeof(int32_t) * UM_M * UM_N, st);
+        if (e == cudaSuccess) e = um_launch(mode, false, true, 1, smem_bytes, st, S->map_a, S->map_b, U);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    rr_dev_free(d_one);
+    if (e != cudaSuccess) { rr_set_error("CUDA error %s in rr_debug_umma_counts", cudaGetErrorString(e)); return RR_E_CUDA; }
+    return rc;
 }

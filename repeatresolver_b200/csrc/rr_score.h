@@ -81,8 +81,7 @@ RR_HD double rr_hyper_pdf(const double *lnf, unsigned int k, unsigned int n1, un
 
 /* gsl_cdf_hypergeometric_Q(k, n1, n2, t), including GSL's mixed int/unsigned/double
  * sub-expressions in lower_tail / upper_tail. */
-RR_HD double rr_hyper_Q(const double *lnf, unsigned int k, unsigned int n1, unsigned int n2, unsigned int t,
-                        int *iters = 0)
+RR_HD double rr_hyper_Q(const double *lnf, unsigned int k, unsigned int n1, unsigned int n2, unsigned int t)
 {
     double midpoint;
     if (k >= n1 || k >= t) return 0.0;
@@ -104,7 +103,6 @@ RR_HD double rr_hyper_Q(const double *lnf, unsigned int k, unsigned int n1, unsi
             if (relerr < DBL_EPSILON) break;
             i--;
         }
-        if (iters) *iters = -((int)k - i + 1);  /* statistics only: negative = lower tail */
         return RR_SUB(1.0, P);
     } else {
         /* Q = upper_tail(k, n1, n2, t) */
@@ -123,7 +121,6 @@ RR_HD double rr_hyper_Q(const double *lnf, unsigned int k, unsigned int n1, unsi
             if (relerr < DBL_EPSILON) break;
             i++;
         }
-        if (iters) *iters = (int)(i - k);
         return Q;
     }
 }
@@ -142,12 +139,12 @@ RR_HD double rr_saturated(unsigned int s, int sizei, int sizej)
 
 /* PositiveSignificance on counts: s=|Gi&Gj|, gr1=|Gi&Cj|, gr2=|Gj&Ci|, cov=|Ci&Cj|. */
 RR_HD double rr_positive_significance(const double *lnf, unsigned int s, unsigned int gr1, unsigned int gr2,
-                                      unsigned int cov, int sizei, int sizej, int *iters = 0)
+                                      unsigned int cov, int sizei, int sizej)
 {
     double Q, Z;
     if (gr1 == 0 || gr2 == 0) return 0.0;
     if (s < 1) return 0.0;
-    Q = rr_hyper_Q(lnf, s - 1, gr2, cov - gr2, gr1, iters);
+    Q = rr_hyper_Q(lnf, s - 1, gr2, cov - gr2, gr1);
     Z = RR_MUL(-1.0, log10(Q));
     if (isinf(Z) || Z > 99) Z = 99.0;
     if (isinf(Z) || Z > 98.0) Z = rr_saturated(s, sizei, sizej);
@@ -161,7 +158,7 @@ RR_HD double rr_group_significance(const double *lnf, unsigned int s, unsigned i
 {
     double Q, Z;
     if (gr1 == 0 || gr2 == 0) return 0.0;
-    Q = rr_hyper_Q(lnf, s - 1, gr2, cov - gr2, gr1, 0);
+    Q = rr_hyper_Q(lnf, s - 1, gr2, cov - gr2, gr1);
     Z = RR_MUL(-1.0, log10(Q));
     if (isinf(Z) || Z > 99) Z = 99.0;
     if (isinf(Z) || Z > 98.0) {

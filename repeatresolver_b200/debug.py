@@ -1,0 +1,35 @@
+"""Test and measurement hooks of librr_maxcorr.so (include/rr_debug.h).  Not part of the drop-in interface."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import lib, ScanOpts
+from .maxcorr import VARIANTS, _check
+
+DEBUG_MMA_ONLY = 0x400      # scan flag: producer + MMA pipeline only (timing decomposition; leaves no result)
+
+
+def set_cliquer_cap(cap):
+    """capacity (records) of the candidate / hit lists of rr_cliquer_batch; 0 restores the default"""
+    lib.rr_debug_set_cliquer_cap(int(cap))
+
+
+def umma_tiles(packed, mincov=30, variant="umma_mxf4", part_index=0, part_count=1):
+    """(row tiles, column tiles) of the plan of the last scan with these options"""
+    opts = ScanOpts(mincov, VARIANTS[variant], 0, part_index, part_count)
+    nr, nc = C.c_int(0), C.c_int(0)
+    _check(lib.rr_debug_umma_counts(packed._h, C.byref(opts), 0, 0, None, None, None, C.byref(nr), C.byref(nc)), "rr_debug_umma_counts")
+    return nr.value, nc.value
+
+
+def umma_counts(packed, row_tile, col_tile, mincov=30, variant="umma_mxf4", part_index=0, part_count=1):
+    """The accumulator of one (row tile, column tile) pair of the tcgen05 scan kernel as its epilogue reads it from
+    TMEM: (counts [128][240], row group ids [128] (-1 = padding row), column group ids [240] (-1 = beyond the MSA)).
+    Call after packed.scan(...) with the same options."""
+    opts = ScanOpts(mincov, VARIANTS[variant], 0, part_index, part_count)
+    counts = np.zeros((128, 240), dtype=np.int32)
+    rg = np.zeros(128, dtype=np.int32)
+    cg = np.zeros(240, dtype=np.int32)
+    _check(lib.rr_debug_umma_counts(packed._h, C.byref(opts), int(row_tile), int(col_tile), counts.ctypes.data, rg.ctypes.data,
+                                    cg.ctypes.data, None, None), "rr_debug_umma_counts")
+    return counts, rg, cg

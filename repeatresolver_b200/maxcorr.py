@@ -126,6 +126,14 @@ class Packed:
         _check(lib.rr_scan_fetch(self._h, M.ctypes.data, A.ctypes.data), "rr_scan_fetch")
         return M, A
 
+    def finalize(self, M, A):
+        """RR_FLAG_HOST_FINALIZE as a call (rr_scan_finalize): the maxima of groups with a partner re-evaluated with the
+        host libm from device-side counts, in place; M / A as fetched or merged over parts"""
+        assert M.dtype == np.float64 and A.dtype == np.int32 and M.flags.c_contiguous and A.flags.c_contiguous
+        assert len(M) == 5 * self.cols and len(A) == 5 * self.cols
+        _check(lib.rr_scan_finalize(self._h, M.ctypes.data, A.ctypes.data), "rr_scan_finalize")
+        return M
+
     def set_thresholds(self, thr):
         thr = np.ascontiguousarray(thr, dtype=np.float64)
         assert len(thr) == 5 * self.cols
@@ -163,8 +171,8 @@ class Packed:
         return members, scores, n, st.as_dict()
 
     def relative_vars(self, Unterteilung, u_no, MaxCorrs, cutoff, mingroup):
-        """Relative_Vars (RepeatResolver.c:2424-2493) on this packed MSA, the part applied as a mask (EXPERIMENTAL,
-        rr_relative_vars_packed): ascending group ids"""
+        """Relative_Vars (RepeatResolver.c:2424-2493) on this packed MSA, the part applied as a mask
+        (rr_relative_vars_packed): ascending group ids"""
         u = np.ascontiguousarray(Unterteilung, dtype=np.int32)
         M = np.ascontiguousarray(MaxCorrs, dtype=np.float64)
         assert len(u) == self.rows and len(M) == 5 * self.cols

@@ -96,6 +96,11 @@ void emu_tiers(const double *lnf, int max_cov, long long n, const uint32_t *quad
         const float lnc3 = (LT(cov) - LT(gr1)) - LT(cov - gr1);
         const float meanfac = (1.0f / (float)std::max(cov, 1u)) * (float)gr1;
         keep1[i] = rr_tier1_f32(LT, sc, gr1, gr2, cov, rr_thr_f32(best[i], false), lnc3, meanfac, margin) ? 1 : 0;
+        // the form the tcgen05 kernel uses: counts scaled by 4 (= byte offsets into the float table), same decision
+        auto LTQ = [&](unsigned off) { return lnf32[off >> 2]; };
+        const float meanfac_q = (1.0f / (float)std::max(4u * cov, 1u)) * (float)(4u * gr1);
+        const bool kq = rr_tier1_q<2>(LTQ, 4u * sc, 4u * gr1, 4u * gr2, 4u * cov, rr_thr_f32(best[i], false), lnc3, meanfac_q, margin);
+        if (kq != (keep1[i] != 0)) keep1[i] = 2;   // the test fails on any value but 0 / 1
         keep2[i] = rr_tier2(T2, sc, gr1, gr2, cov, best[i]) ? 1 : 0;
     }
 }
@@ -155,24 +160,18 @@ long long emu_scan_bitset(int R, int N, int W32, int mincov, unsigned flags, con
     return (long long)plan.part_pairs;
 }
 
-int emu_clq_qb(int kernel) { return kernel == 2 ? CLQ_QB2 : CLQ_QB; }
+int emu_clq_qb(void) { return CLQ_QB; }
 int emu_clq_slab(void) { return CLQ_SLAB; }
 
-/* rr_launch_cliquer's grid, one of the three count kernels, then the score kernel */
-int emu_cliquer(int kernel, const uint32_t *bits, const uint32_t *covbits, const int32_t *gsize, const double *lnf, int W32,
+/* rr_launch_cliquer's grid: the count kernel, then the score kernel */
+int emu_cliquer(const uint32_t *bits, const uint32_t *covbits, const int32_t *gsize, const double *lnf, int W32,
                 const int32_t *queries, int nq, int anfang, int ende, int min_s, double greedy, double threshold,
                 rr_clq_rec *cand, rr_clq_rec *hits, unsigned long long cap, unsigned long long *counters)
 {
-    const int qb = kernel == 2 ? CLQ_QB2 : CLQ_QB;
-    const size_t smem = kernel == 3 ? clq_smem_bytes3(W32) : clq_smem_bytes(W32, qb);
+    const size_t smem = rr_cliquer_smem_bytes(W32);
     if (smem > sizeof(emu_dynamic_smem) || nq <= 0 || ende <= anfang) return 1;
-    dim3 grid((unsigned)((nq + qb - 1) / qb), (unsigned)((ende - anfang + CLQ_SLAB - 1) / CLQ_SLAB));
-    if (kernel == 3)
-        emu_launch(grid, CLQ_WARPS * 32, [&] { rr_k_cliquer_counts3(bits, covbits, W32, queries, nq, anfang, ende, min_s, greedy, lnf, cand, cap, counters); });
-    else if (kernel == 2)
-        emu_launch(grid, CLQ_WARPS * 32, [&] { rr_k_cliquer_counts2(bits, covbits, W32, queries, nq, anfang, ende, min_s, greedy, lnf, cand, cap, counters); });
-    else
-        emu_launch(grid, CLQ_WARPS * 32, [&] { rr_k_cliquer_counts(bits, covbits, W32, queries, nq, anfang, ende, min_s, greedy, lnf, cand, cap, counters); });
+    dim3 grid((unsigned)((nq + CLQ_QB - 1) / CLQ_QB), (unsigned)((ende - anfang + CLQ_SLAB - 1) / CLQ_SLAB));
+    emu_launch(grid, CLQ_WARPS * 32, [&] { rr_k_cliquer_counts(bits, covbits, W32, queries, nq, anfang, ende, min_s, greedy, lnf, cand, cap, counters); });
     emu_launch(dim3(3), 128, [&] { rr_k_cliquer_score(cand, cap, counters, queries, gsize, lnf, threshold, hits, counters + 1); });
     return 0;
 }

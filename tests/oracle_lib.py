@@ -29,6 +29,8 @@ def lib():
         L.rr_oracle_coverage.restype = C.POINTER(C.c_int)
         L.rr_oracle_coverage.argtypes = [C.c_void_p]
         L.rr_oracle_counts.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.rr_oracle_count_matrix.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.rr_oracle_count_matrix.restype = None
         L.rr_oracle_score.restype = C.c_double
         L.rr_oracle_score.argtypes = [C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_int]
         L.rr_oracle_scan.restype = C.c_int64
@@ -88,6 +90,14 @@ class Oracle:
         out = (C.c_int * 4)()
         lib().rr_oracle_counts(self._h, int(i), int(j), out)
         return list(out)
+
+    def count_matrix(self, rows, cols):
+        """|G_r & G_c| (Schnitt, MaxCorrelation.c:114-125) for every pair of two lists of group ids: [len(rows)][len(cols)]"""
+        r = np.ascontiguousarray(rows, dtype=np.int32)
+        c = np.ascontiguousarray(cols, dtype=np.int32)
+        out = np.zeros((len(r), len(c)), dtype=np.int32)
+        lib().rr_oracle_count_matrix(self._h, len(r), r.ctypes.data, len(c), c.ctypes.data, out.ctypes.data)
+        return out
 
     def scan(self, mincov=30, modulus=None, res_lo=0, res_hi=None, threads=8):
         """full scan when modulus is None (threads pthreads), else rows ii % modulus in [res_lo,res_hi)"""

@@ -86,18 +86,77 @@ def run_golden_case(name, cov, variant, tmp_path):
     assert (Mf == M0).all() and (Af == A0).all()
 
 
+def check_umma_tiles(pk, oracle, variant, mincov, tiles):
+    """the tcgen05 kernel's own accumulators (rr_debug_umma_counts: read back from TMEM by the kernel's epilogue after its
+    producer / MMA code) against the oracle's Schnitt, entry by entry"""
+    n_rt, n_ct = rr.debug.umma_tiles(pk, mincov, variant)
+    checked = nonzero = 0
+    for rt, ct in tiles(n_rt, n_ct):
+        counts, rg, cg = rr.debug.umma_counts(pk, rt, ct, mincov, variant)
+        rows = np.flatnonzero(rg >= 0)
+        cols = np.flatnonzero(cg >= 0)
+        assert (counts[rg < 0] == 0).all(), "padding rows of the A operand must give zero counts"
+        assert (counts[:, cg < 0] == 0).all(), "columns beyond the MSA must give zero counts"
+        want = oracle.count_matrix(rg[rows], cg[cols])
+        got = counts[np.ix_(rows, cols)]
+        assert np.array_equal(got, want), (variant, rt, ct, int((got != want).sum()))
+        checked += got.size
+        nonzero += int((want > 0).sum())
+    return checked, nonzero
+
+
 @pytest.mark.parametrize("variant", VARIANTS)
 def test_counts_bit_exact(variant, tmp_path):
+    """BASELINE.json: "intersection counts are bit-exact".  AND+POPC path: rr_k_pair_counts on random pairs; tcgen05 paths
+    (all three operand codings): whole accumulator tiles of the scan kernel, first / middle / last row and column tiles"""
     g = rr.MsaGen(type="Tree", copies=6, coverage=25, repeat_len=1500, diff=0.02, seed=21, flank=800, min_overlap=100)
     codes = g.codes()
     oracle = O.Oracle.from_codes(codes)
     pk = rr.Packed(rr.MSA.from_cells(codes), 0)
-    rng = np.random.default_rng(1)
-    gi = rng.integers(0, 5 * g.cols, 4000).astype(np.int32)
-    gj = rng.integers(0, 5 * g.cols, 4000).astype(np.int32)
-    got = pk.pair_counts(gi, gj)
-    for k in range(0, 4000, 7):
-        assert list(got[k]) == oracle.counts(gi[k], gj[k])
+    if variant == "bitset":
+        rng = np.random.default_rng(1)
+        gi = rng.integers(0, 5 * g.cols, 4000).astype(np.int32)
+        gj = rng.integers(0, 5 * g.cols, 4000).astype(np.int32)
+        got = pk.pair_counts(gi, gj)
+        for k in range(0, 4000, 7):
+            assert list(got[k]) == oracle.counts(gi[k], gj[k])
+    else:
+        pk.scan(mincov=20, variant=variant)
+
+        def tiles(n_rt, n_ct):
+            assert n_rt >= 3 and n_ct >= 3
+            return [(0, 0), (0, 1), (n_rt // 2, n_ct // 2), (n_rt // 2, n_ct // 2 + 1), (n_rt - 1, n_ct - 1), (1, n_ct - 1), (n_rt - 1, 0)]
+        checked, nonzero = check_umma_tiles(pk, oracle, variant, 20, tiles)
+        assert checked > 100000 and nonzero > 10000
+    pk.close()
+
+
+@pytest.mark.parametrize("variant", [v for v in VARIANTS if v != "bitset"])
+def test_tcgen05_counts_on_golden_and_two_length_classes(variant, tmp_path):
+    """the same check on a committed golden MSA (every tile pair) and on an MSA deep enough for two length classes of rows
+    (>= 1024 reads: the K ranges of the two classes are skipped separately) with ragged spans"""
+    text = golden_msa("tree_small")
+    oracle = O.Oracle.from_text(text, tmp_path)
+    pk = rr.Packed(rr.MSA.from_text(text), 0)
+    pk.scan(mincov=30, variant=variant)
+    checked, nonzero = check_umma_tiles(pk, oracle, variant, 30, lambda n_rt, n_ct: [(r, c) for r in range(n_rt) for c in range(n_ct)])
+    assert nonzero > 0
+    pk.close()
+    g = rr.MsaGen(type="Tree", copies=40, coverage=40, repeat_len=1500, diff=0.02, seed=77, flank=700, min_overlap=100)
+    codes = g.codes()
+    assert codes.shape[0] >= 1300
+    oracle = O.Oracle.from_codes(codes)
+    pk = rr.Packed(rr.MSA.from_cells(codes), 0)
+    pk.scan(mincov=30, variant=variant)
+    rng = np.random.default_rng(5)
+
+    def tiles(n_rt, n_ct):
+        picks = {(0, 0), (n_rt - 1, n_ct - 1), (0, n_ct - 1), (n_rt - 1, 0)}
+        while len(picks) < 12:
+            picks.add((int(rng.integers(0, n_rt)), int(rng.integers(0, n_ct))))
+        return sorted(picks)
+    checked, nonzero = check_umma_tiles(pk, oracle, variant, 30, tiles)
+    assert nonzero > 50000
     pk.close()
 
 

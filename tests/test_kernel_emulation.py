@@ -3,9 +3,7 @@ rr_device.cuh), rr_cliquer.cu, rr_relvars.cu and rr_kmeans.cu, compiled by the H
 stand-in CUDA header of tests/emu (every CUDA thread a pthread, __syncthreads and the warp primitives as barriers) and run
 on small inputs against the oracle.  This checks the kernels' logic - indexing, staging, skips, reductions, tails - on the
 CPU, in the build container, every round; it is test infrastructure, says nothing about speed and does not replace the GPU
-tests.  The two Cliquer count kernels that ARE validated on a B200 (tests/test_zz_gpu_cliquer.py) run here too: they pin the
-emulation itself.  For count kernel 3, the tiled Relative_Vars kernel and the Kmeans sweeps - written after the round's last
-GPU call - this is the only execution so far."""
+tests.  All of these kernels are also validated on a B200 (tests/test_zz_gpu_*.py); what runs here is the same source."""
 import ctypes as C
 import os
 import subprocess
@@ -42,7 +40,7 @@ def emu():
                                "-I" + CSRC, "-o", out, os.path.join(EMU_DIR, "emu_driver.cpp"), "-lpthread"])
     lib = C.CDLL(out)
     vp, i, d, u64, u32 = C.c_void_p, C.c_int, C.c_double, C.c_ulonglong, C.c_uint
-    lib.emu_cliquer.argtypes = [i, vp, vp, vp, vp, i, vp, i, i, i, i, d, d, vp, vp, u64, vp]
+    lib.emu_cliquer.argtypes = [vp, vp, vp, vp, i, vp, i, i, i, i, d, d, vp, vp, u64, vp]
     lib.emu_relvars_pairs.argtypes = [vp, vp, i, vp, i, vp, vp, i, vp, d, vp, vp, u32, vp]
     lib.emu_masked_sizes.argtypes = [vp, vp, C.c_longlong, i, vp]
     lib.emu_kmeans_sweeps.argtypes = [vp, i, i, i, vp, vp, vp]
@@ -79,7 +77,7 @@ def two_family_msa(R, N, seed, variant_every=3):
     return codes[np.argsort(start, kind="stable")]
 
 
-def run_cliquer(emu, kernel, codes, queries, mincov, maxclique, greedy, anfang=0, ende=None):
+def run_cliquer(emu, codes, queries, mincov, maxclique, greedy, anfang=0, ende=None):
     o = O.Oracle.from_codes(codes)
     bits, cov, W32 = pack_bits(codes)
     gs = o.gsize().astype(np.int32)
@@ -91,7 +89,7 @@ def run_cliquer(emu, kernel, codes, queries, mincov, maxclique, greedy, anfang=0
     hits = np.zeros(cap, dtype=rr.HIT_DTYPE)
     counters = np.zeros(2, dtype=np.uint64)
     thr = min(greedy - 1e-9 * max(1.0, abs(greedy)), 97.89)
-    rc = emu.emu_cliquer(kernel, bits.ctypes.data, cov.ctypes.data, gs.ctypes.data, lnf.ctypes.data, W32, q.ctypes.data, len(q),
+    rc = emu.emu_cliquer(bits.ctypes.data, cov.ctypes.data, gs.ctypes.data, lnf.ctypes.data, W32, q.ctypes.data, len(q),
                          anfang, ende, mincov // 4, greedy, thr, cand.ctypes.data, hits.ctypes.data,
                          cap, counters.ctypes.data)
     assert rc == 0 and counters[1] <= counters[0] <= cap
@@ -103,28 +101,26 @@ def run_cliquer(emu, kernel, codes, queries, mincov, maxclique, greedy, anfang=0
     return o, members, scores, n, len(cand), len(hits)
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3])
-def test_cliquer_count_kernels_on_the_golden_cases(emu, kernel):
+def test_cliquer_count_kernel_on_the_golden_cases(emu):
     for name in ("tree_small", "saturated"):
         case = cliquer_cases()[name]
         codes = window_codes(golden_msa(name), case["von"], case["bis"])[:, :330]       # a slab and a partial one
         queries = [int(x) for x in case["queries"] if int(x) < 5 * codes.shape[1]][:5]
-        o, members, scores, n, nc, nh = run_cliquer(emu, kernel, codes, queries, case["mincov"], case["maxclique"], case["greedy"])
+        o, members, scores, n, nc, nh = run_cliquer(emu, codes, queries, case["mincov"], case["maxclique"], case["greedy"])
         assert nh > 0
         for k, qq in enumerate(queries):
             m0, z0 = o.cliquer(qq, case["mincov"], case["maxclique"], case["greedy"])
             assert list(members[k, :n[k]]) == list(m0) and np.array_equal(scores[k, :n[k]], z0), (name, qq)
 
 
-@pytest.mark.parametrize("kernel", [1, 3])
-def test_cliquer_count_kernels_with_greedy_inside_the_saturation_band(emu, kernel):
+def test_cliquer_count_kernel_with_greedy_inside_the_saturation_band(emu):
     """a bound above 98 proves nothing (486), a bound below it prunes against greedy = 98.1: only saturated pairs survive"""
     case = cliquer_cases()["saturated"]
     codes = window_codes(golden_msa("saturated"), case["von"], case["bis"])[:, :200]
     o = O.Oracle.from_codes(codes)
     M0, _, _ = o.scan(case["mincov"])
     queries = [int(q) for q in np.argsort(-M0, kind="stable")[:6]]
-    o, members, scores, n, nc, nh = run_cliquer(emu, kernel, codes, queries, case["mincov"], 6, 98.1)
+    o, members, scores, n, nc, nh = run_cliquer(emu, codes, queries, case["mincov"], 6, 98.1)
     sat = 0
     for k, qq in enumerate(queries):
         m0, z0 = o.cliquer(qq, case["mincov"], 6, 98.1)
@@ -133,15 +129,14 @@ def test_cliquer_count_kernels_with_greedy_inside_the_saturation_band(emu, kerne
     assert sat > 0 and (scores[:, 1:][scores[:, 1:] > 0] > 98.1).all()
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3])
-def test_cliquer_count_kernels_with_several_chunks_and_ragged_coverage(emu, kernel):
+def test_cliquer_count_kernel_with_several_chunks_and_ragged_coverage(emu):
     """more than 1024 reads = two 32-word chunks per bitset; spans so that chunks are skipped on either side"""
     codes = two_family_msa(1300, 70, seed=41)
     o = O.Oracle.from_codes(codes)
     gs = o.gsize()
     cand = np.flatnonzero((gs > 40) & (gs < 600))
     queries = [int(x) for x in cand[:: len(cand) // 9][:9]] + [0]                      # 10 queries: partial last block
-    o, members, scores, n, nc, nh = run_cliquer(emu, kernel, codes, queries, 30, 8, 3.0)
+    o, members, scores, n, nc, nh = run_cliquer(emu, codes, queries, 30, 8, 3.0)
     sizes = set()
     for k, qq in enumerate(queries):
         m0, z0 = o.cliquer(qq, 30, 8, 3.0)
@@ -149,7 +144,7 @@ def test_cliquer_count_kernels_with_several_chunks_and_ragged_coverage(emu, kern
         sizes.add(len(m0))
     assert max(sizes) == 8 and nh > 50
     # a sub-range of candidate columns
-    o, members, scores, n, _, _ = run_cliquer(emu, kernel, codes, queries[:3], 30, 5, 2.0, anfang=11, ende=52)
+    o, members, scores, n, _, _ = run_cliquer(emu, codes, queries[:3], 30, 5, 2.0, anfang=11, ende=52)
     for k, qq in enumerate(queries[:3]):
         m0, z0 = o.cliquer(qq, 30, 5, 2.0, 11, 52)
         assert list(members[k, :n[k]]) == list(m0) and np.array_equal(scores[k, :n[k]], z0), qq
@@ -441,7 +436,7 @@ def test_packing_kernels_on_raw_text(emu_pack, tmp_path):
     for ii in range(n90):
         below = [jj for jj in range(ii + 20, n90) if shared[ii, jj] < 20]
         assert brk[ii] == (below[0] if below else max(n90, ii + 20)), ii                # MaxCorrelation.c:804-810
-    # the 0/1 operands of the tensor path: int8 and packed e2m1 (1.0 = 0b0010), K-major
+    # the 0/2 operands of the tensor path (a product is 4, see rr_scan_umma.cu): int8 and packed e2m1 (2.0 = 0b0100), K-major
     Kp = 128 * ((p["R"] + 127) // 128)
     member = np.zeros((5 * p["N"], Kp), dtype=np.uint8)
     rc = codes[p["perm"]]
@@ -449,10 +444,10 @@ def test_packing_kernels_on_raw_text(emu_pack, tmp_path):
         member[k::5, :p["R"]] = (rc == k).T
     xb = np.zeros((5 * p["N"], Kp), dtype=np.int8)
     emu_pack.emu_pack_int8(cells.ctypes.data, p["perm"].ctypes.data, p["R"], p["N"], 0, xb.ctypes.data, Kp, 0)
-    assert np.array_equal(xb.view(np.uint8), member)
+    assert np.array_equal(xb.view(np.uint8), member * 2)
     x4 = np.zeros((5 * p["N"], Kp // 2), dtype=np.uint8)
     emu_pack.emu_pack_int8(cells.ctypes.data, p["perm"].ctypes.data, p["R"], p["N"], 0, x4.ctypes.data, Kp, 1)
-    assert np.array_equal(x4, (member[:, 0::2] * 2) | (member[:, 1::2] * 2 << 4))
+    assert np.array_equal(x4, (member[:, 0::2] * 4) | (member[:, 1::2] * 4 << 4))
 
 
 @pytest.mark.parametrize("name,cov", [("kat_appendix_g", 30), ("initial_aligner_style", 30)])
@@ -558,6 +553,7 @@ def test_pruning_tiers_of_the_fused_epilogue_never_drop_a_pair_that_matters(emu)
         for best in (z, z * (1 - 1e-12), z * 0.999, np.maximum(z - 1e-6, 0)):
             best = np.ascontiguousarray(best)                            # keep the buffer alive across the call
             emu.emu_tiers(lnf.ctypes.data, max_cov, len(q), q.ctypes.data, best.ctypes.data, k1.ctypes.data, k2.ctypes.data)
+            assert (k1 <= 1).all(), "rr_tier1_q (scaled counts) decides differently from rr_tier1_f32"
             assert k1[live].all() and k2[live].all(), (max_cov, int((~k1[live].astype(bool)).sum()), int((~k2[live].astype(bool)).sum()))
         far = np.ascontiguousarray(z + 3.0)
         emu.emu_tiers(lnf.ctypes.data, max_cov, len(q), q.ctypes.data, far.ctypes.data, k1.ctypes.data, k2.ctypes.data)

@@ -3,11 +3,9 @@ called through the C ABI (rr_cliquer_batch = device path, rr_cliquer = plain pat
   * the committed output of the UNMODIFIED RepeatResolver.c (tests/golden/cliquer.json), bit for bit;
   * the oracle's restatement on a flanked MSA deep enough for several 32-word chunks per bitset (the kernel's two
     exact skips), with a query count that is not a multiple of the batch, sub-ranges [anfang, ende), small cliques,
-    and the list-overflow retry forced through RR_CLIQUER_CAP.
+    and the list-overflow retry forced through the debug hook rr_debug_set_cliquer_cap.
 Bar: members identical, scores identical as doubles (integer counts on the device, final scores with the host libm).
 The file sorts last on purpose: a first failure here must not hide the scan's parity tests under `-x`."""
-import os
-
 import numpy as np
 import pytest
 
@@ -17,23 +15,6 @@ import oracle_lib as O
 from test_oracle_cliquer import cliquer_cases, window_codes
 
 pytestmark = pytest.mark.gpu
-
-
-# kernel 3 (partition identity, joint coverage skip, three blocks per SM) has never run on a GPU: opt in with RR_TEST_UNVALIDATED=1
-KERNELS = ["1", "2"] + (["3"] if os.environ.get("RR_TEST_UNVALIDATED") == "1" else [])
-KERNEL_IDS = {"1": "one_step_counts", "2": "two_step_counts", "3": "experimental_counts3"}
-
-
-@pytest.fixture(autouse=True, params=KERNELS, ids=[KERNEL_IDS[k] for k in KERNELS])
-def count_kernel(request):
-    """the count kernels of csrc/rr_cliquer.cu (RR_CLIQUER_KERNEL is read at every rr_cliquer_batch call)"""
-    old = os.environ.get("RR_CLIQUER_KERNEL")
-    os.environ["RR_CLIQUER_KERNEL"] = request.param
-    yield request.param
-    if old is None:
-        del os.environ["RR_CLIQUER_KERNEL"]
-    else:
-        os.environ["RR_CLIQUER_KERNEL"] = old
 
 
 def check(members, scores, n, k, oracle_members, oracle_scores):
@@ -110,11 +91,11 @@ def test_cliquer_batch_subranges_and_small_cliques(deep, anfang, ende, maxclique
 def test_cliquer_batch_list_overflow_retries(deep):
     codes, o, pk, queries = deep
     want = pk.cliquer_batch(queries[:13], 30, 30, 3.0)
-    os.environ["RR_CLIQUER_CAP"] = "700"
+    rr.debug.set_cliquer_cap(700)
     try:
         got = pk.cliquer_batch(queries[:13], 30, 30, 3.0)
     finally:
-        del os.environ["RR_CLIQUER_CAP"]
+        rr.debug.set_cliquer_cap(0)
     assert got[3]["retries"] > 0 and want[3]["retries"] == 0
     for a, b in zip(want[:3], got[:3]):
         assert np.array_equal(a, b)

@@ -2,10 +2,7 @@
 the C ABI (rr_kmeans: signatures and dissolution on the host, the two read x read sweeps and the centroids in
 csrc/rr_kmeans.cu) against the committed output of the UNMODIFIED RepeatResolver.c (tests/golden/kmeans.json) and the
 oracle on a fresh input.  Bar: the partition after the call identical, integer for integer.
-The kernels have NEVER RUN ON A GPU (written after the round's last GPU call): opt in with RR_TEST_UNVALIDATED=1 - the first
-thing to do next round.  Everything these kernels share with the host is pinned on the CPU (tests/test_oracle_kmeans.py)."""
-import os
-
+Everything these kernels share with the host is pinned on the CPU as well (tests/test_oracle_kmeans.py)."""
 import numpy as np
 import pytest
 
@@ -15,9 +12,7 @@ import oracle_lib as O
 from test_oracle_kmeans import kmeans_cases
 from test_oracle_relvars import partition_by_site, relvars_cases, window_codes
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("RR_TEST_UNVALIDATED") != "1",
-                                 reason="csrc/rr_kmeans.cu has never run on a GPU: opt in with RR_TEST_UNVALIDATED=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", sorted(kmeans_cases()))
