@@ -100,67 +100,93 @@ def make_msa(rr, workload):
     return g, msa
 
 
-def reference_sample(rr, msa, workload, seconds_target, tmpdir):
-    """Time the reference's CPU implementation on a bounded sample of the workload: a column
-    window of the MSA holding ALL rows (same R, hence the same per-intersection cost: the
-    reference touches R/64+1 words per Schnitt whatever the window).  Returns a dict."""
-    import numpy as np
-    cores = os.cpu_count() or 1
-    threads = max(1, min(cores, 128))
-    cells = msa.cells()
-    R, N = cells.shape
-    drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver_big")
-    kind = "reference" if os.path.exists(drv) else "port"
-    # window width: pair tests grow ~ quadratically with the width; ~0.4 M pair tests/s/core at R ~ 13.7k
-    rate_guess = 0.45e6 * (13700.0 / max(R, 300)) * threads
-    want_pairs = rate_guess * seconds_target
-    width = int(min(N, max(200, (want_pairs / 3.5) ** 0.5)))
-    c0 = max(0, N // 2 - width // 2)
-    win = np.ascontiguousarray(cells[:, c0:c0 + width])
-    text = np.full((R, width + 1), ord("\n"), dtype=np.uint8)
-    text[:, :width] = np.frombuffer(b"ACGT- ", dtype=np.uint8)[win]
-    path = os.path.join(tmpdir, "sample.msa")
-    text.tofile(path)
-    sample = f"columns [{c0},{c0 + width}) of {workload}, all {R} rows, -c {MINCOV}, {threads} threads"
-    # pair tests of the sample: counted by the restatement's own filter logic on the CPU
-    import oracle_lib as O
-    if kind == "reference":
-        out = subprocess.run([drv, path, str(MINCOV), str(threads), "0", str(threads)], capture_output=True, text=True)
-        line = [l for l in out.stdout.splitlines() if l.startswith("REF ")]
-        if out.returncode != 0 or not line:
-            raise RuntimeError("ref_driver failed: " + out.stderr[-500:])
-        scan_s = float(line[-1].split()[4])
-        P = count_pairs_host(win, MINCOV)
-    else:
-        o = O.Oracle.from_codes(win)
-        t0 = time.perf_counter()
-        _, _, P = o.scan(MINCOV, threads=threads)
-        scan_s = time.perf_counter() - t0
-    return {"value": P / scan_s, "unit": "pair tests/s", "cores": threads, "kind": kind, "sample": sample,
-            "pair_tests": P, "seconds": scan_s}
-
-
-def count_pairs_host(codes, mincov):
-    """number of PositiveSignificance calls (MaxCorrelation.c:820) for a code matrix whose rows are
-    single spans, from the filters alone (numpy; no intersections are evaluated)."""
+def site_pair_counts(codes, mincov):
+    """per site ii, the number of PositiveSignificance calls (MaxCorrelation.c:820) its row groups make, for a code matrix
+    whose rows are single spans, from the filters alone (numpy + the product's first-break sweep; no intersections)"""
     import numpy as np
     import repeatresolver_b200 as rr
     R, N = codes.shape
-    covd = codes < 5
-    gs = np.stack([(codes == k).sum(0) for k in range(5)], 1)  # [N][5]
-    coverage = covd.sum(0)
+    gs = np.zeros((N, 5), dtype=np.int64)
+    start = np.full(R, 2 ** 31 - 1, dtype=np.int32)
+    end = np.full(R, -1, dtype=np.int32)
+    for r0 in range(0, R, 512):                      # in row slabs: the config-2 matrix is 1.8 GB
+        blk = codes[r0:r0 + 512]
+        for k in range(5):
+            gs[:, k] += (blk == k).sum(0)
+        covd = blk < 5
+        anyc = covd.any(1)
+        start[r0:r0 + 512] = np.where(anyc, covd.argmax(1), 2 ** 31 - 1)
+        end[r0:r0 + 512] = np.where(anyc, N - 1 - covd[:, ::-1].argmax(1), -1)
+    coverage = gs.sum(1)
     q = mincov // 4
     colok = (gs > q) & (gs < R)
     basey = gs[:, :4].sum(1) > coverage // 2
     nrow = (colok & basey[:, None]).sum(1)
-    ncol = colok.sum(1)
-    pref = np.concatenate([[0], np.cumsum(ncol)])
-    anyc = covd.any(1)
-    start = np.where(anyc, covd.argmax(1), 2 ** 31 - 1).astype(np.int32)
-    end = np.where(anyc, N - 1 - covd[:, ::-1].argmax(1), -1).astype(np.int32)
+    pref = np.concatenate([[0], np.cumsum(colok.sum(1))])
     brk = np.minimum(rr.breakcols_from_spans(start, end, N, mincov), N)
     lo = np.minimum(np.arange(N) + 20, N)
-    return int((nrow * np.maximum(0, pref[np.maximum(brk, lo)] - pref[lo])).sum())
+    return nrow * np.maximum(0, pref[np.maximum(brk, lo)] - pref[lo])
+
+
+def count_pairs_host(codes, mincov):
+    return int(site_pair_counts(codes, mincov).sum())
+
+
+def reference_samples(rr, g, msa, workload, seconds_target, tmpdir, reps=1):
+    """Time the reference's CPU implementation on bounded samples of the workload, BASELINE.md section 3.4: the WHOLE MSA
+    (written as the text file the reference reads), an exact 1/k cyclic sample of its row sites (ii % k == thread,
+    MaxCorrelation.c:796) on all host cores, through the unmodified reference's own Einlesen and HilfsMaxCorrsRechner
+    (oracle/_ref/ref_driver_big); the oracle port when that binary is absent.  The pair tests of a sample are counted twice and
+    must agree: by the oracle's instrumented loop (rr_oracle_count_pairs: the reference's loops and filters without the score)
+    and from the product's own filters / first-break sweep.  Returns a list of dicts, one per repetition."""
+    import numpy as np
+    import oracle_lib as O
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, 64))
+    cells = msa.cells()
+    R, N = cells.shape
+    drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver_big")
+    kind = "reference" if os.path.exists(drv) else "port"
+    per_site = site_pair_counts(cells, MINCOV)
+    P_total = int(per_site.sum())
+    # 1/k of the row sites per thread: ~0.45 M pair tests/s/core at R ~ 13.7k, cost per pair test ~ R
+    rate_guess = 0.45e6 * (13700.0 / max(R, 300)) * threads
+    want_pairs = rate_guess * seconds_target
+    modulus = int(max(threads, round(P_total / max(want_pairs, 1.0) * threads)))
+    oracle = O.Oracle.from_codes(cells)
+    out = []
+    reps_per_run = max(1, min(reps, (min(128, modulus) // threads))) if kind == "reference" else 1
+    path = os.path.join(tmpdir, "workload.msa")
+    if kind == "reference" and not os.path.exists(path):
+        g.write(path)
+    while len(out) < reps:
+        n = min(reps_per_run, reps - len(out))
+        if kind == "reference":
+            run = subprocess.run([drv, path, str(MINCOV), str(modulus), "0", str(threads), "-", str(n)], capture_output=True, text=True)
+            lines = [l.split() for l in run.stdout.splitlines() if l.startswith("REF ")]
+            if run.returncode != 0 or len(lines) != n:
+                raise RuntimeError("ref_driver failed: " + run.stderr[-500:])
+            runs = [(float(l[4]), int(l[6])) for l in lines]
+        else:
+            runs = []
+            for r in range(n):
+                t0 = time.perf_counter()
+                oracle.scan(MINCOV, modulus, r * threads, (r + 1) * threads)
+                runs.append((time.perf_counter() - t0, r * threads))
+        for scan_s, lo in runs:
+            P_oracle = oracle.count_pairs(MINCOV, modulus, lo, lo + threads)
+            sel = (np.arange(N) % modulus >= lo) & (np.arange(N) % modulus < lo + threads)
+            P_product = int(per_site[sel].sum())
+            if P_oracle != P_product:
+                raise RuntimeError(f"pair-test count of the CPU sample: oracle {P_oracle}, product filters {P_product}")
+            out.append({"value": P_oracle / scan_s, "unit": "pair tests/s", "cores": threads, "kind": kind,
+                        "sample": f"row sites ii % {modulus} in [{lo},{lo + threads}) of the whole {workload} MSA ({R} x {N}), "
+                                  f"-c {MINCOV}, {threads} threads = {threads}/{modulus} of the rows; pair tests counted by the "
+                                  f"oracle's instrumented loop = product filters ({P_oracle})",
+                        "pair_tests": P_oracle, "seconds": scan_s, "extrapolation_factor": modulus / threads,
+                        "pair_tests_whole_msa": P_total})
+    oracle.close()
+    return out
 
 
 def cliquer_queries(np, pk, R, nq):
@@ -322,7 +348,8 @@ def main():
     ap.add_argument("--workload", default="Tree_1perc_30000", choices=sorted(WORKLOADS))
     ap.add_argument("--variant", default="auto", choices=["auto", "bitset", "umma", "umma_f4", "umma_mxf4"])
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-e2e-file", dest="e2e_file", action="store_false", help="skip the run of the drop-in program")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -333,21 +360,14 @@ def main():
     import repeatresolver_b200 as rr
     if args.path == "cliquer":
         return bench_cliquer(args, rr)
-    from repeatresolver_b200.dist import merge_over_ranks, scan_part
+    from repeatresolver_b200.dist import merge_over_ranks, pack_over_ranks, scan_part
 
     if args.impl == "reference":
         if rank != 0:
             return 0
         g, msa = make_msa(rr, args.workload)
-        vals = []
         with tempfile.TemporaryDirectory() as d:
-            for s in range(args.warmup + args.steps):
-                r = reference_sample(rr, msa, args.workload, args.cpu_seconds, d)
-                if s >= args.warmup:
-                    vals.append(r)
-                if s == 0 and args.warmup + args.steps > 2 and r["seconds"] > 60:
-                    vals = [r]
-                    break
+            vals = reference_samples(rr, g, msa, args.workload, args.cpu_seconds, d, reps=args.warmup + args.steps)[args.warmup:]
         tot_p = sum(v["pair_tests"] for v in vals)
         tot_s = sum(v["seconds"] for v in vals)
         v = tot_p / tot_s
@@ -416,20 +436,25 @@ def main():
     clocks = sampler.finish()
     loop_ms = allmax(loop_ms)
     P_total = int(allsum(st["pair_tests"]))
+    executed_total = allsum(st["executed_ops"])          # every rank's own part, summed
     k_ms = allmax(sum(kernel_ms) / len(kernel_ms))
     ms_per_step = loop_ms / args.steps
     value = P_total / (ms_per_step * 1e-3)
     variant_used = rr.VARIANT_NAMES[st["variant"]]
 
     # ---- e2e: host buffers through the C ABI -------------------------------------------------
+    # every rank holds the cell matrix in page-locked host memory; a step = upload + device pack + scan + D2H + merge.
+    # With N ranks the upload and the packing are shared (rank r pushes R/N rows through PCIe, the packed bitsets are merged
+    # with one NCCL all-reduce over NVLink: dist.pack_over_ranks); the bytes below are per rank.
     G = 5 * N
     e2e_ms = []
-    h2d = R * N + 4 * R + 8 * (R + 2)
-    d2h = 16 * G + 4 * 3 * R + 4 * 6 * N
+    rows_mine = R * (rank + 1) // world - R * rank // world
+    h2d = rows_mine * N + 4 * R + 8 * (R + 2)
+    d2h = 16 * G + 4 * 3 * rows_mine + 4 * 6 * N
     for s in range(args.e2e_steps + 1):
         barrier()
         t0 = time.perf_counter()
-        pk2 = rr.Packed(msa, local_rank)                      # H2D (pinned) + device pack
+        pk2 = pack_over_ranks(msa, local_rank)                # H2D (pinned) of this rank's rows + device pack (+ all-reduce OR)
         scan_part(pk2, MINCOV, variant)
         M, A = pk2.fetch()                                    # D2H of the per-group result
         M, A = merge_over_ranks(M, A)                         # element-wise max over ranks (882-891)
@@ -440,6 +465,29 @@ def main():
             e2e_ms.append(allmax(dt * 1e3))
     e2e_value = P_total / (sum(e2e_ms) / len(e2e_ms) * 1e-3) if e2e_ms else None
 
+    # ---- e2e_file: the drop-in program itself, text file in, MaxCorrsOf_* out (parse, upload, pack, scan on N GPUs, host
+    # finalisation, "%f" text), wall clock of a fresh process; run by rank 0 while the other ranks wait
+    e2e_file = None
+    if args.e2e_file:
+        barrier()
+        if rank == 0:
+            exe = os.path.join(ROOT, "repeatresolver_b200", "bin", "MaxCorrelation")
+            with tempfile.TemporaryDirectory() as d:
+                g.write(os.path.join(d, "MSAreal"))
+                walls = []
+                for _ in range(2):                            # the first run also warms the page cache
+                    t0 = time.perf_counter()
+                    r = subprocess.run([exe, "MSAreal", "-c", str(MINCOV), "-p", str(world)], cwd=d, capture_output=True, text=True)
+                    walls.append(time.perf_counter() - t0)
+                    if r.returncode != 0 or not os.path.exists(os.path.join(d, "MaxCorrsOf_MSAreal")):
+                        raise SystemExit("bin/MaxCorrelation failed: " + r.stderr[-400:])
+                e2e_file = {"value": P_total / walls[-1], "unit": "pair tests/s", "wall_s": walls[-1], "first_run_wall_s": walls[0],
+                            "command": f"bin/MaxCorrelation MSAreal -c {MINCOV} -p {world}",
+                            "input_bytes": os.path.getsize(os.path.join(d, "MSAreal")),
+                            "output_bytes": os.path.getsize(os.path.join(d, "MaxCorrsOf_MSAreal")),
+                            "includes": "process start, CUDA start-up, text parse, upload, pack, scan, host finalisation, text output"}
+        barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -448,25 +496,49 @@ def main():
     # ---- roofline of the dominant kernel -------------------------------------------------------
     peaks, peak_src = load_peaks()
     if variant_used in ("umma", "umma_f4", "umma_mxf4"):
-        # algorithmic work: 2*R 8-bit-rate tensor ops per pair test (the reference touches all
-        # R/64+1 words per intersection); peak: dense INT8/FP8-rate = 2 x the measured bf16 cuBLAS burst
-        # (MEASURED_PEAKS.json has no 8-bit figure; the datasheet ratio is exactly 2)
+        # Hardware fraction: the MACs the kernel EXECUTES (padding, masked entries and K skipping included) against the
+        # MEASURED rate of the tensor pipe for the MMA kind it uses - a bare tcgen05.mma loop of the same kind, tile shape
+        # and operand layout in this library (rr_debug_mma_peak), taken here on the same GPU right after the timed loop.
+        # Beside it the algorithmic figure of SURVEY.md 8d: 2*R 8-bit-rate ops per pair test (the reference touches all
+        # R/64+1 words per intersection) against the dense INT8 peak measured with torch._int_mm 8192^3 (cuBLASLt).
+        psamp = ClockSampler(local_rank)
+        psamp.start()
+        pipe = rr.debug.mma_peak(variant_used, local_rank)
+        pipe_i8 = rr.debug.mma_peak("umma", local_rank) if variant_used != "umma" else pipe
+        a8 = torch.randint(-2, 3, (8192, 8192), dtype=torch.int8, device="cuda")
+        b8 = torch.randint(-2, 3, (8192, 8192), dtype=torch.int8, device="cuda")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        int8_ms = []
+        for _ in range(12):
+            e0.record()
+            torch._int_mm(a8, b8)
+            e1.record()
+            e1.synchronize()
+            int8_ms.append(e0.elapsed_time(e1))
+        del a8, b8
+        pclk = psamp.finish()
+        int8_tops = 2.0 * 8192 ** 3 / (min(int8_ms[2:]) * 1e-3) / 1e12
         algo = 2.0 * R * P_total
-        achieved = algo / (k_ms * 1e-3) / 1e12
-        peak = 2.0 * peaks["bf16_tflops"] * world
-        ops = {"umma": "int8 mul+add (tcgen05 kind::i8), 2*R per pair test",
-               "umma_f4": "0/1 as e2m1 mul+add at the 8-bit rate (tcgen05 kind::f8f6f4, fp32 accumulate), 2*R per pair test",
-               "umma_mxf4": "0/1 as packed e2m1 with unit block scales (tcgen05 kind::mxf4.block_scale, fp32 accumulate; "
-                            "this kind runs at twice the 8-bit rate), 2*R per pair test; peak kept at the 8-bit (INT8) rate "
-                            "the north star names"}[variant_used]
+        executed = executed_total
+        achieved = executed / (k_ms * 1e-3) / 1e12
+        peak = pipe["tflops"] * world
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": TRAFFIC.get(args.workload), "ops": ops,
-                "peak_source": f"2 x {peak_src} bf16 burst ({peaks['bf16_tflops']} TF/s) per GPU",
-                "executed_ops_per_step": st["executed_ops"] * world,
-                "executed_frac_of_algorithmic": st["executed_ops"] * world / algo if algo else None,
-                "executed_tflops": st["executed_ops"] * world / (k_ms * 1e-3) / 1e12}
-        if variant_used == "umma_mxf4":
-            roof["frac_of_fp4_rate"] = achieved / (2.0 * peak)
+                "traffic": TRAFFIC.get(args.workload),
+                "ops": "EXECUTED tensor-core multiply-adds x 2 (every K block issued: padding rows, masked entries and the exact "
+                       "K-range skipping included) / kernel time, against the measured rate of the pipe used",
+                "pipe": {"umma": "tcgen05.mma kind::i8 (int32 accumulate)", "umma_f4": "tcgen05.mma kind::f8f6f4 on e2m1 (fp32 accumulate)",
+                         "umma_mxf4": "tcgen05.mma kind::mxf4.block_scale on packed e2m1, unit scales (fp32 accumulate)"}[variant_used],
+                "peak_source": f"measured here: bare tcgen05.mma loop of this kind, M=128 N=240, all SMs (rr_debug_mma_peak): "
+                               f"{pipe['tflops']:.1f} TFLOP/s per GPU; SM clock median {pclk['sm_mhz']} MHz while measuring",
+                "peaks_measured": {"pipe_used_tflops": pipe["tflops"], "tcgen05_i8_loop_tops": pipe_i8["tflops"],
+                                   "int8_cublaslt_8192_tops": int8_tops, "bf16_cublas_burst_tflops": peaks["bf16_tflops"],
+                                   "bf16_source": peak_src, "clocks_while_measuring": pclk},
+                "executed_ops_per_step": executed, "executed_frac_of_algorithmic": executed / algo if algo else None,
+                "algorithmic": {"ops_per_step": algo, "tflops": algo / (k_ms * 1e-3) / 1e12,
+                                "frac_of_int8_peak": algo / (k_ms * 1e-3) / 1e12 / (int8_tops * world),
+                                "note": "2*R 8-bit-rate ops per pair test x pair tests / kernel time: a speed metric (K skipping and "
+                                        "the 4-bit pipe make it exceed what an INT8 GEMM of the full shape could reach), not a "
+                                        "hardware fraction"}}
     else:
         # AND+POPC variant: issue-bound on the POPC pipe (16 lanes/clk/SM); reported against that peak
         words = P_total * ((R + 31) // 32)
@@ -479,8 +551,10 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         with tempfile.TemporaryDirectory() as d:
-            cpu = reference_sample(rr, msa, args.workload, args.cpu_seconds, d)
-            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            cpu = reference_samples(rr, g, msa, args.workload, args.cpu_seconds, d)[0]
+            if cpu["pair_tests_whole_msa"] != P_total:
+                raise SystemExit(f"pair tests: device {P_total}, host filters {cpu['pair_tests_whole_msa']}")
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "extrapolation_factor")}
 
     line = {"metric": "site-group pair tests/sec (MaxCorrelation)", "value": value, "unit": "pair tests/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -495,7 +569,10 @@ def main():
             "kernel_ms": k_ms, "exact_evals": st["exact_evals"], "bound_evals": st["bound_evals"],
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "pair tests/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": sum(e2e_ms) / len(e2e_ms) if e2e_ms else None},
+                    "ms_per_step": sum(e2e_ms) / len(e2e_ms) if e2e_ms else None,
+                    "path": "C ABI: rr_pack (N > 1: rr_pack_rows + NCCL all-reduce OR of the bitsets + rr_pack_finish), rr_scan, "
+                            "rr_scan_fetch, max-merge"},
+            "e2e_file": e2e_file,
             "gpu_launches": launches}
     print(json.dumps(line))
     if world > 1:

@@ -30,6 +30,12 @@ void rr_debug_set_cliquer_cap(unsigned long long cap);
 int rr_debug_umma_counts(rr_packed *pk, const rr_scan_opts *opts, int row_tile, int col_tile, int32_t *counts,
                          int32_t *row_groups, int32_t *col_groups, int *n_row_tiles, int *n_col_tiles);
 
+/* The tensor pipe's rate for the MMA kind, tile shape (M = 128, N = 240) and operand layout of RR_VARIANT_UMMA*: a
+ * bare loop of back-to-back tcgen05.mma on every SM, nothing loaded, nothing read back.  *macs = multiply-accumulates
+ * of one launch, *best_ms = fastest of reps launches (CUDA events); peak = 2 * macs / best_ms.  bench.py reports the
+ * scan's executed MACs against this. */
+int rr_debug_mma_peak(int device, int variant, int kblocks_per_sm, int reps, float *best_ms, double *macs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -118,6 +118,25 @@ int rr_variant_available(int variant);
  * coverage, read spans) */
 int rr_pack(const rr_msa *msa, int device, rr_packed **out);
 void rr_packed_free(rr_packed *pk);
+/* The same in phases, so that n GPUs share the upload and the packing (each GPU still ends up with the whole packed
+ * MSA; Einlesen's GrAdd loop 366-384 is the part that is split):
+ *   rr_pack_rows        upload the rows [row_lo, row_hi) only and find their covered spans
+ *   rr_pack_slice_spans start / end / covered cells of those rows (host arrays of row_hi - row_lo entries) - the
+ *                       caller gathers them from all slices
+ *   rr_pack_set_spans   the spans of ALL rows (host arrays of rows entries, in row order): fixes the row order and
+ *                       packs this slice's rows into full-size group / coverage bitsets, zero for all other rows
+ *   rr_pack_bits_device device pointer and size of that buffer ([5 cols][W] group words, then [cols][W] coverage
+ *                       words, 32-bit); the caller ORs the buffers of all slices into it (the slices are disjoint, so
+ *                       an integer SUM all-reduce - e.g. NCCL on this pointer - is an OR)
+ *   rr_pack_finish      group sizes, coverage and result buffers from the merged bitsets; the handle is then what
+ *                       rr_pack returns
+ * rr_maxcorr_run does this between the GPUs of one process with peer copies; repeatresolver_b200/dist.py between
+ * one-process-per-GPU ranks with NCCL. */
+int rr_pack_rows(const rr_msa *msa, int device, int row_lo, int row_hi, rr_packed **out);
+int rr_pack_slice_spans(rr_packed *pk, int32_t *start, int32_t *end, int32_t *count);
+int rr_pack_set_spans(rr_packed *pk, const int32_t *start, const int32_t *end, const int32_t *count);
+int rr_pack_bits_device(rr_packed *pk, void **d_bits, size_t *bytes);
+int rr_pack_finish(rr_packed *pk);
 /* run the scan on the packed MSA; results stay on the device */
 int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *stats);
 /* copy the last scan's result to the host: maxcorr[5*cols] (line g of MaxCorrsOf_*,

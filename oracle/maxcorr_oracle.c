@@ -178,6 +178,7 @@ double rr_oracle_score(unsigned int schnitt, unsigned int gr1, unsigned int gr2,
 typedef struct {
     const rr_oracle *o;
     int mincov, nthreads, thread;
+    int count_only;  /* walk the loops of 796-817 and count the calls of 820 without making them */
     double *M;       /* [5N] private maxima          (768-770) */
     int32_t *arg;    /* [5N] private arg-max partner (A9) */
     int64_t pairs;   /* number of PositiveSignificance calls (820) */
@@ -211,6 +212,7 @@ static void *rr_scan_thread(void *x)
                     int j = 5 * jj + kk, c[4];
                     double Z;
                     if (!(o->gsize[j] > q && o->gsize[j] < R)) continue;            /* 817 */
+                    if (job->count_only) { job->pairs++; continue; }
                     rr_oracle_counts(o, i, j, c);
                     Z = rr_oracle_score(c[0], c[1], c[2], c[3], o->gsize[i], o->gsize[j]); /* 820 */
                     job->pairs++;
@@ -255,6 +257,25 @@ int64_t rr_oracle_scan(const rr_oracle *o, int mincov, int modulus, int res_lo, 
         pairs += jobs[t].pairs;
         free(jobs[t].M); free(jobs[t].arg);
     }
+    free(jobs); free(th);
+    return pairs;
+}
+
+/* The number of PositiveSignificance calls (820) the scan of the rows ii with (ii % modulus) in [res_lo, res_hi) makes:
+ * the same loops, filters and first-break test as rr_scan_thread, without the calls themselves (bench.py: the pair-test
+ * count of a CPU sample, next to the product's own count). */
+int64_t rr_oracle_count_pairs(const rr_oracle *o, int mincov, int modulus, int res_lo, int res_hi)
+{
+    int nt = res_hi - res_lo, t;
+    pthread_t *th = (pthread_t *)calloc(nt, sizeof(pthread_t));
+    rr_scan_job *jobs = (rr_scan_job *)calloc(nt, sizeof(rr_scan_job));
+    int64_t pairs = 0;
+    for (t = 0; t < nt; t++) {
+        jobs[t].o = o; jobs[t].mincov = mincov; jobs[t].nthreads = modulus; jobs[t].thread = res_lo + t;
+        jobs[t].count_only = 1;
+        pthread_create(&th[t], NULL, rr_scan_thread, &jobs[t]);
+    }
+    for (t = 0; t < nt; t++) { pthread_join(th[t], NULL); pairs += jobs[t].pairs; }
     free(jobs); free(th);
     return pairs;
 }

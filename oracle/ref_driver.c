@@ -5,8 +5,10 @@
  *   - the scan can be timed without the parse, and
  *   - an exact 1/k cyclic row sample can be run (ii % NTHREADS == thread, line 796):
  *     NTHREADS = modulus, threads res_lo..res_hi-1.
- * usage: ref_driver MSA cov modulus res_lo res_hi [outfile]
- * prints one line:  REF R N threads scan_seconds parse_seconds
+ * usage: ref_driver MSA cov modulus res_lo res_hi [outfile|-] [reps]
+ * prints one line per repetition:  REF R N threads scan_seconds parse_seconds first_residue
+ * Repetition r scans the residues res_lo + r * threads .. (the file is parsed once); residues must stay below
+ * min(modulus, 128), the size of the reference's HilfsMaxCorr[] (MaxCorrelation.c:36).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -27,36 +29,43 @@ static double now(void)
 
 int main(int argc, char **argv)
 {
-    int cov, modulus, lo, hi, nt, t, i;
+    int cov, modulus, lo, hi, nt, t, i, reps = 1, rep;
     pthread_t th[128];
     int *args[128];
     double t0, t1, t2;
     if (argc < 6) { fprintf(stderr, "usage: ref_driver MSA cov modulus res_lo res_hi [out]\n"); return 2; }
     cov = atoi(argv[2]); modulus = atoi(argv[3]); lo = atoi(argv[4]); hi = atoi(argv[5]);
     nt = hi - lo;
-    if (nt < 1 || nt > 128 || lo != 0) { fprintf(stderr, "need res_lo == 0 and 1..128 threads\n"); return 2; }
+    if (argc > 7) reps = atoi(argv[7]);
+    if (nt < 1 || reps < 1 || lo < 0 || lo + reps * nt > 128 || lo + reps * nt > modulus) {
+        fprintf(stderr, "need 0 <= res_lo and res_lo + reps * threads <= min(modulus, 128)\n");
+        return 2;
+    }
     t0 = now();
     Einlesen(argv[1], -1, -1);
     t1 = now();
+    for (rep = 0; rep < reps; rep++, lo += nt) {
+    if (rep > 0) t1 = now();
     for (t = 0; t < nt; t++) {
         /* same 7-int argument block as Parallel_AllMaxCorrsRechner builds (853-860) */
         args[t] = (int *)malloc(sizeof(int) * 7);
         args[t][0] = 0; args[t][1] = siglength; args[t][2] = cov; args[t][3] = signumber;
-        args[t][4] = 0; args[t][5] = modulus; args[t][6] = t;
+        args[t][4] = 0; args[t][5] = modulus; args[t][6] = lo + t;
         pthread_create(&th[t], NULL, HilfsMaxCorrsRechner, args[t]);
     }
     for (t = 0; t < nt; t++) pthread_join(th[t], NULL);
     for (i = 0; i < siglength * 5; i++)            /* merge, 882-891 */
         for (t = 1; t < nt; t++)
-            if (HilfsMaxCorr[t][i] > HilfsMaxCorr[0][i]) HilfsMaxCorr[0][i] = HilfsMaxCorr[t][i];
+            if (HilfsMaxCorr[lo + t][i] > HilfsMaxCorr[lo][i]) HilfsMaxCorr[lo][i] = HilfsMaxCorr[lo + t][i];
     t2 = now();
-    if (argc > 6) {
+    if (rep == 0 && argc > 6 && argv[6][0] != '-') {
         FILE *f = fopen(argv[6], "w");
         if (!f) return 1;
-        for (i = 0; i < siglength * 5; i++) fprintf(f, "%f\n", HilfsMaxCorr[0][i]);
+        for (i = 0; i < siglength * 5; i++) fprintf(f, "%f\n", HilfsMaxCorr[lo][i]);
         fclose(f);
     }
+    printf("REF %d %d %d %.6f %.6f %d\n", signumber, siglength, nt, t2 - t1, rep == 0 ? t1 - t0 : 0.0, lo);
     fflush(stdout);
-    printf("REF %d %d %d %.6f %.6f\n", signumber, siglength, nt, t2 - t1, t1 - t0);
+    }
     return 0;
 }

@@ -64,7 +64,7 @@ def _sig(fn, res, args):
 # every symbol include/rr_maxcorr.h declares
 ABI_SYMBOLS = [
     "rr_msa_read", "rr_msa_from_text", "rr_msa_from_cells", "rr_msa_alloc", "rr_msa_rows", "rr_msa_cols",
-    "rr_msa_cells", "rr_msa_free", "rr_device_count", "rr_variant_available", "rr_pack", "rr_packed_free", "rr_scan", "rr_scan_fetch", "rr_scan_finalize", "rr_scan_set_thresholds", "rr_scan_values_device", "rr_scan_set_thresholds_device",
+    "rr_msa_cells", "rr_msa_free", "rr_device_count", "rr_variant_available", "rr_pack", "rr_pack_rows", "rr_pack_slice_spans", "rr_pack_set_spans", "rr_pack_bits_device", "rr_pack_finish", "rr_packed_free", "rr_scan", "rr_scan_fetch", "rr_scan_finalize", "rr_scan_set_thresholds", "rr_scan_values_device", "rr_scan_set_thresholds_device",
     "rr_pair_counts", "rr_packed_sizes", "rr_maxcorr_run", "rr_maxcorr_write", "rr_argmax_write", "rr_maxcorr_write_bin", "rr_maxcorr_read_bin", "rr_lnfact",
     "rr_lnfact_table", "rr_score_host", "rr_score_bound_host", "rr_below_median_host", "rr_breakcols_from_spans", "rr_contraction_ranges", "rr_cliquer", "rr_cliquer_batch", "rr_cliquer_from_counts", "rr_cliquer_from_hits", "rr_relative_vars", "rr_relative_vars_packed", "rr_relative_vars_from_counts", "rr_relative_score_host", "rr_kmeans", "rr_kmeans_signatures", "rr_kmeans_finish", "rr_kmeans_top5_host", "rr_kmeans_majority5_host", "rr_group_score_host",
     "rr_timer_start", "rr_timer_stop", "rr_launch_count", "rr_last_error", "rr_version",
@@ -83,6 +83,11 @@ _sig(lib.rr_msa_free, None, [_vp])
 _sig(lib.rr_device_count, _i, [])
 _sig(lib.rr_variant_available, _i, [_i])
 _sig(lib.rr_pack, _i, [_vp, _i, _P(_vp)])
+_sig(lib.rr_pack_rows, _i, [_vp, _i, _i, _i, _P(_vp)])
+_sig(lib.rr_pack_slice_spans, _i, [_vp, _vp, _vp, _vp])
+_sig(lib.rr_pack_set_spans, _i, [_vp, _vp, _vp, _vp])
+_sig(lib.rr_pack_bits_device, _i, [_vp, _P(_vp), _P(C.c_size_t)])
+_sig(lib.rr_pack_finish, _i, [_vp])
 _sig(lib.rr_packed_free, None, [_vp])
 _sig(lib.rr_scan, _i, [_vp, _P(ScanOpts), _P(ScanStats)])
 _sig(lib.rr_scan_fetch, _i, [_vp, _vp, _vp])
@@ -125,8 +130,9 @@ _sig(lib.rr_last_error, C.c_char_p, [])
 _sig(lib.rr_version, C.c_char_p, [])
 
 # include/rr_debug.h: test / measurement hooks, not part of the drop-in boundary
-DEBUG_SYMBOLS = ["rr_debug_set_cliquer_cap", "rr_debug_umma_counts"]
+DEBUG_SYMBOLS = ["rr_debug_set_cliquer_cap", "rr_debug_umma_counts", "rr_debug_mma_peak"]
 _sig(lib.rr_debug_set_cliquer_cap, None, [C.c_ulonglong])
+_sig(lib.rr_debug_mma_peak, _i, [_i, _i, _i, _i, _P(C.c_float), _P(C.c_double)])
 _sig(lib.rr_debug_umma_counts, _i, [_vp, _P(ScanOpts), _i, _i, _vp, _vp, _vp, _P(_i), _P(_i)])
 
 _sig(gen.rr_msagen_create, _vp, [_P(MsagenParams)])

@@ -222,10 +222,14 @@ struct scan_cache {
 struct rr_packed {
     int device = 0, n_sm = 148;
     int R = 0, N = 0, W32 = 0, codes = 0;
+    int phase = 0;                        // 1: rows uploaded, 2: bitsets packed (this slice), 3: complete
+    int row_lo = 0, row_hi = 0;           // the rows this handle uploaded (rr_pack_rows)
+    std::vector<int32_t> slice_spans;     // [3][row_hi - row_lo] start, end, covered cells
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr, pe2 = nullptr;
     cudaStream_t st = nullptr;
     uint8_t *d_cells = nullptr;
     int32_t *d_perm = nullptr;
-    uint32_t *d_bits = nullptr, *d_covbits = nullptr;
+    uint32_t *d_bits = nullptr, *d_covbits = nullptr;   // one allocation: [5N][W32] then [N][W32]
     int32_t *d_gsize = nullptr, *d_coverage = nullptr;
     double *d_lnfact = nullptr;
     rr_best_t *d_best = nullptr;
@@ -285,11 +289,14 @@ extern "C" void rr_packed_free(rr_packed *pk)
     cudaSetDevice(pk->device);
     rr_alloc_stream(pk->st);
     rr_umma_free(pk->umma);
-    rr_dev_free(pk->d_cells); rr_dev_free(pk->d_perm); rr_dev_free(pk->d_bits); rr_dev_free(pk->d_covbits);
+    rr_dev_free(pk->d_cells); rr_dev_free(pk->d_perm); rr_dev_free(pk->d_bits);
     rr_dev_free(pk->d_gsize); rr_dev_free(pk->d_coverage); rr_dev_free(pk->d_lnfact); rr_dev_free(pk->d_best);
     rr_dev_free(pk->d_counters);
     pk->cache.sb.release();  // while the stream still exists
     if (pk->t0) { cudaEventDestroy(pk->t0); cudaEventDestroy(pk->t1); }
+    if (pk->pe0) cudaEventDestroy(pk->pe0);
+    if (pk->pe1) cudaEventDestroy(pk->pe1);
+    if (pk->pe2) cudaEventDestroy(pk->pe2);
     if (pk->st) { cudaStreamSynchronize(pk->st); cudaStreamDestroy(pk->st); }
     rr_alloc_stream(nullptr);
     delete pk;
@@ -301,9 +308,9 @@ extern "C" void rr_msa_gather_rows(const rr_msa *m, int r0, int r1, uint8_t *dst
 // Rows of a text-backed or pageable host MSA -> d_cells through a small page-locked ring: a few host threads gather
 // whole rows into ring slots (this is the only host copy the rows ever see) while earlier slots are in flight on the
 // copy engine.  Page-locking the whole 1-2 GB matrix instead costs ~1 s per GB.
-static int staged_upload(const rr_msa *msa, uint8_t *d_cells, int device, cudaStream_t st)
+static int staged_upload(const rr_msa *msa, int row_lo, int row_hi, uint8_t *d_cells, int device, cudaStream_t st)
 {
-    const int R = msa->rows;
+    const int R = row_hi - row_lo;                                       // rows [row_lo, row_hi) -> d_cells[0 .. R)
     const size_t N = (size_t)msa->cols;
     constexpr int NSLOT = 6, NTHREAD = 6;
     constexpr size_t SLOT_BYTES = (size_t)8 << 20;
@@ -337,7 +344,7 @@ static int staged_upload(const rr_msa *msa, uint8_t *d_cells, int device, cudaSt
             if (use > 0 && cudaEventSynchronize(ev[slot]) != cudaSuccess) { failed = 1; cv.notify_all(); return; }
             const int r0 = c * rows_per_slot, r1 = std::min(R, r0 + rows_per_slot);
             uint8_t *buf = ring + (size_t)slot * slot_bytes;
-            rr_msa_gather_rows(msa, r0, r1, buf, 1);
+            rr_msa_gather_rows(msa, row_lo + r0, row_lo + r1, buf, 1);
             cudaError_t e = cudaMemcpyAsync(d_cells + (size_t)r0 * N, buf, (size_t)(r1 - r0) * N, cudaMemcpyHostToDevice, cst);
             {
                 std::lock_guard<std::mutex> lk(mu);   // record under the lock: events of one stream stay in issue order
@@ -370,10 +377,17 @@ static int staged_upload(const rr_msa *msa, uint8_t *d_cells, int device, cudaSt
     return RR_OK;
 }
 
-static int pack_impl(const rr_msa *msa, int device, rr_packed *pk)
+// Packing runs in three phases so that several GPUs can share the work (rr_pack_rows / rr_pack_set_spans / rr_pack_finish,
+// include/rr_maxcorr.h); rr_pack is the three in a row for the whole MSA on one GPU.
+//   A  upload the rows [row_lo, row_hi) and find their covered spans
+//   B  given the spans of ALL rows: row order (length class, span start, span end), then the group / coverage bitsets of
+//      the uploaded rows at their ranks, zero elsewhere - the buffers of all slices OR (= add) to the full bitsets
+//   C  group sizes, coverage, ln n! table, result buffers
+static int pack_phase_a(const rr_msa *msa, int device, int row_lo, int row_hi, rr_packed *pk)
 {
     const uint8_t *cells = msa->cells;
     const int R = msa->rows, N = msa->cols, codes = msa->codes;
+    if (row_lo < 0 || row_hi > R || row_lo > row_hi) { rr_set_error("rr_pack_rows: rows [%d, %d) of %d", row_lo, row_hi, R); return RR_E_ARG; }
     rr_cuda_warmup_end();
     RR_TRACE("pack: context ready");
     int ndev = rr_device_count();
@@ -388,38 +402,47 @@ static int pack_impl(const rr_msa *msa, int device, rr_packed *pk)
     if (cc_major < 10) { rr_set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, cc_major, cc_minor); return RR_E_NODEV; }
     pk->device = device; pk->n_sm = n_sm;
     pk->R = R; pk->N = N; pk->codes = codes;
+    pk->row_lo = row_lo; pk->row_hi = row_hi;
     pk->W32 = ((R + 127) / 128) * 4;
     if (pk->W32 == 0) pk->W32 = 4;
     RR_CUDA(cudaStreamCreateWithFlags(&pk->st, cudaStreamNonBlocking));
     rr_alloc_stream(pk->st);
-    event_scope ev;                                                      // destroyed on every exit path
-    cudaEvent_t e0, e1, e2;
-    if (ev.create(&e0) || ev.create(&e1) || ev.create(&e2)) { rr_set_error("cudaEventCreate failed"); return RR_E_CUDA; }
-
-    const size_t ncell = (size_t)R * N;
+    if (cudaEventCreate(&pk->pe0) != cudaSuccess || cudaEventCreate(&pk->pe1) != cudaSuccess || cudaEventCreate(&pk->pe2) != cudaSuccess) {
+        cudaGetLastError(); rr_set_error("cudaEventCreate failed"); return RR_E_CUDA;
+    }
+    const int n = row_hi - row_lo;
+    const size_t ncell = (size_t)n * N;
     int rc;
     if ((rc = dev_alloc(&pk->d_cells, ncell))) return rc;
     RR_TRACE("pack: cells allocated");
-    RR_CUDA(cudaEventRecord(e0, pk->st));
+    RR_CUDA(cudaEventRecord(pk->pe0, pk->st));
     if (ncell) {
-        if (cells && msa->pinned) RR_CUDA(cudaMemcpyAsync(pk->d_cells, cells, ncell, cudaMemcpyHostToDevice, pk->st));
-        else if ((rc = staged_upload(msa, pk->d_cells, device, pk->st))) return rc;
+        if (cells && msa->pinned) RR_CUDA(cudaMemcpyAsync(pk->d_cells, cells + (size_t)row_lo * N, ncell, cudaMemcpyHostToDevice, pk->st));
+        else if ((rc = staged_upload(msa, row_lo, row_hi, pk->d_cells, device, pk->st))) return rc;
     }
-    RR_CUDA(cudaEventRecord(e1, pk->st));
-
+    RR_CUDA(cudaEventRecord(pk->pe1, pk->st));
     RR_TRACE("pack: h2d issued");
-    // spans -> row order (by span start, then end; uncovered rows last)
     int32_t *d_span = nullptr;
     dev_scope span_scope;                                                // d_span goes back to the pool on every exit path
-    if ((rc = span_scope.alloc(&d_span, (size_t)3 * std::max(R, 1)))) return rc;
-    RR_CUDA(rr_launch_row_spans(pk->d_cells, R, N, codes, d_span, d_span + R, d_span + 2 * (size_t)R, pk->st));
-    std::vector<int32_t> span((size_t)3 * std::max(R, 1));
-    RR_CUDA(cudaMemcpyAsync(span.data(), d_span, sizeof(int32_t) * 3 * (size_t)R, cudaMemcpyDeviceToHost, pk->st));
+    if ((rc = span_scope.alloc(&d_span, (size_t)3 * std::max(n, 1)))) return rc;
+    RR_CUDA(rr_launch_row_spans(pk->d_cells, n, N, codes, d_span, d_span + n, d_span + 2 * (size_t)n, pk->st));
+    pk->slice_spans.assign((size_t)3 * std::max(n, 1), 0);
+    RR_CUDA(cudaMemcpyAsync(pk->slice_spans.data(), d_span, sizeof(int32_t) * 3 * (size_t)n, cudaMemcpyDeviceToHost, pk->st));
     RR_CUDA(cudaStreamSynchronize(pk->st));
     RR_TRACE("pack: spans back");
+    pk->phase = 1;
+    return RR_OK;
+}
+
+// spans: start[R], end[R], covered cells[R] of ALL rows of the MSA (in row order)
+static int pack_phase_b(rr_packed *pk, const int32_t *sst, const int32_t *sen, const int32_t *scn)
+{
+    if (pk->phase != 1) { rr_set_error("rr_pack_set_spans: call rr_pack_rows first (once)"); return RR_E_ARG; }
+    RR_CUDA(cudaSetDevice(pk->device));
+    rr_alloc_stream(pk->st);
+    const int R = pk->R, N = pk->N;
     std::vector<int32_t> perm(R);
     std::iota(perm.begin(), perm.end(), 0);
-    const int32_t *sst = span.data(), *sen = span.data() + R, *scn = span.data() + 2 * (size_t)R;
     // Row order = (length class, span start, span end).  The class of the "short" rows is the 3/4 of the rows with
     // the shortest spans, rounded down to whole 256-row K blocks (none below 1024 rows): see rr_plan.cpp for why the
     // very long rows are kept apart.  Any order gives the same counts; this one gives the tightest K ranges.
@@ -447,16 +470,36 @@ static int pack_impl(const rr_msa *msa, int device, rr_packed *pk)
         if (scn[r] > 0 && scn[r] != sen[r] - sst[r] + 1) pk->contiguous = false;
     }
     pk->h_perm = perm;
+    int rc;
     if ((rc = dev_alloc(&pk->d_perm, (size_t)R))) return rc;
     if (R) RR_CUDA(cudaMemcpyAsync(pk->d_perm, perm.data(), sizeof(int32_t) * R, cudaMemcpyHostToDevice, pk->st));
-
-    // bitsets, sizes
+    // bitsets: one allocation, groups then coverage, so that a merge over slices is one reduction
     const size_t G = (size_t)5 * N;
-    if ((rc = dev_alloc(&pk->d_bits, G * pk->W32))) return rc;
-    if ((rc = dev_alloc(&pk->d_covbits, (size_t)N * pk->W32))) return rc;
+    if ((rc = dev_alloc(&pk->d_bits, (G + (size_t)N) * pk->W32))) return rc;
+    pk->d_covbits = pk->d_bits + G * pk->W32;
+    RR_CUDA(rr_launch_pack_bits(pk->d_cells, pk->d_perm, R, N, pk->codes, pk->d_bits, pk->d_covbits, pk->W32, pk->row_lo, pk->row_hi, pk->st));
+    RR_CUDA(cudaEventRecord(pk->pe2, pk->st));
+    RR_CUDA(cudaStreamSynchronize(pk->st));                              // perm is a local; the caller may merge the bitsets next
+    rr_dev_free(pk->d_cells);                                            // everything downstream works on the bitsets
+    pk->d_cells = nullptr;
+    pk->phase = 2;
+    return RR_OK;
+}
+
+static int pack_phase_c(rr_packed *pk)
+{
+    if (pk->phase != 2) { rr_set_error("rr_pack_finish: call rr_pack_set_spans first (once)"); return RR_E_ARG; }
+    RR_CUDA(cudaSetDevice(pk->device));
+    rr_alloc_stream(pk->st);
+    const int R = pk->R, N = pk->N;
+    const size_t G = (size_t)5 * N;
+    int rc;
+    cudaEvent_t e3 = nullptr;
+    event_scope ev;
+    if (ev.create(&e3)) { rr_set_error("cudaEventCreate failed"); return RR_E_CUDA; }
+    RR_CUDA(cudaEventRecord(e3, pk->st));
     if ((rc = dev_alloc(&pk->d_gsize, G))) return rc;
     if ((rc = dev_alloc(&pk->d_coverage, (size_t)N))) return rc;
-    RR_CUDA(rr_launch_pack_bits(pk->d_cells, pk->d_perm, R, N, codes, pk->d_bits, pk->d_covbits, pk->W32, pk->st));
     RR_CUDA(rr_launch_bitset_sizes(pk->d_bits, (int64_t)G, pk->W32, pk->d_gsize, pk->st));
     RR_CUDA(rr_launch_bitset_sizes(pk->d_covbits, (int64_t)N, pk->W32, pk->d_coverage, pk->st));
     pk->h_gsize.resize(G); pk->h_coverage.resize(N);
@@ -471,20 +514,72 @@ static int pack_impl(const rr_msa *msa, int device, rr_packed *pk)
 
     if ((rc = dev_alloc(&pk->d_best, G))) return rc;
     if ((rc = dev_alloc(&pk->d_counters, (size_t)8))) return rc;
-    RR_CUDA(cudaEventRecord(e2, pk->st));
+    cudaEvent_t e4 = nullptr;
+    if (ev.create(&e4)) { rr_set_error("cudaEventCreate failed"); return RR_E_CUDA; }
+    RR_CUDA(cudaEventRecord(e4, pk->st));
     RR_CUDA(cudaStreamSynchronize(pk->st));
     RR_TRACE("pack: done");
-    RR_CUDA(cudaEventElapsedTime(&pk->h2d_ms, e0, e1));
-    RR_CUDA(cudaEventElapsedTime(&pk->pack_ms, e1, e2));
-    if (rr_trace_on()) fprintf(stderr, "[rr trace] h2d %.3f ms (%.1f GB/s), pack %.3f ms\n", pk->h2d_ms, ncell / (pk->h2d_ms * 1e6), pk->pack_ms);
+    float ab = 0.f, c = 0.f;
+    RR_CUDA(cudaEventElapsedTime(&pk->h2d_ms, pk->pe0, pk->pe1));
+    RR_CUDA(cudaEventElapsedTime(&ab, pk->pe1, pk->pe2));
+    RR_CUDA(cudaEventElapsedTime(&c, e3, e4));
+    pk->pack_ms = ab + c;
+    if (rr_trace_on()) fprintf(stderr, "[rr trace] h2d %.3f ms, pack %.3f ms\n", pk->h2d_ms, pk->pack_ms);
+    pk->phase = 3;
     return RR_OK;
+}
+
+extern "C" int rr_pack_rows(const rr_msa *msa, int device, int row_lo, int row_hi, rr_packed **out)
+{
+    if (!msa || !out) { rr_set_error("rr_pack_rows: bad arguments"); return RR_E_ARG; }
+    rr_packed *pk = new rr_packed();
+    int rc = pack_phase_a(msa, device, row_lo, row_hi, pk);
+    if (rc) { rr_packed_free(pk); *out = nullptr; return rc; }
+    *out = pk;
+    return RR_OK;
+}
+
+extern "C" int rr_pack_slice_spans(rr_packed *pk, int32_t *start, int32_t *end, int32_t *count)
+{
+    if (!pk || pk->phase < 1 || !start || !end || !count) { rr_set_error("rr_pack_slice_spans: bad arguments"); return RR_E_ARG; }
+    const size_t n = (size_t)(pk->row_hi - pk->row_lo);
+    memcpy(start, pk->slice_spans.data(), sizeof(int32_t) * n);
+    memcpy(end, pk->slice_spans.data() + n, sizeof(int32_t) * n);
+    memcpy(count, pk->slice_spans.data() + 2 * n, sizeof(int32_t) * n);
+    return RR_OK;
+}
+
+extern "C" int rr_pack_set_spans(rr_packed *pk, const int32_t *start, const int32_t *end, const int32_t *count)
+{
+    if (!pk || !start || !end || !count) { rr_set_error("rr_pack_set_spans: bad arguments"); return RR_E_ARG; }
+    return pack_phase_b(pk, start, end, count);
+}
+
+extern "C" int rr_pack_bits_device(rr_packed *pk, void **d_bits, size_t *bytes)
+{
+    if (!pk || pk->phase < 2 || !d_bits || !bytes) { rr_set_error("rr_pack_bits_device: bad arguments"); return RR_E_ARG; }
+    *d_bits = pk->d_bits;
+    *bytes = (size_t)6 * pk->N * pk->W32 * sizeof(uint32_t);
+    return RR_OK;
+}
+
+extern "C" int rr_pack_finish(rr_packed *pk)
+{
+    if (!pk) { rr_set_error("rr_pack_finish: bad arguments"); return RR_E_ARG; }
+    return pack_phase_c(pk);
 }
 
 extern "C" int rr_pack(const rr_msa *msa, int device, rr_packed **out)
 {
     if (!msa || !out) { rr_set_error("rr_pack: bad arguments"); return RR_E_ARG; }
     rr_packed *pk = new rr_packed();
-    int rc = pack_impl(msa, device, pk);
+    int rc = pack_phase_a(msa, device, 0, msa->rows, pk);
+    if (!rc) {
+        const size_t n = (size_t)msa->rows;
+        const int32_t *sp = pk->slice_spans.data();
+        rc = pack_phase_b(pk, sp, sp + n, sp + 2 * n);
+    }
+    if (!rc) rc = pack_phase_c(pk);
     if (rc) { rr_packed_free(pk); *out = nullptr; return rc; }
     *out = pk;
     return RR_OK;
@@ -511,7 +606,7 @@ extern "C" int rr_timer_stop(rr_packed *pk, float *elapsed_ms)
 
 extern "C" int rr_packed_sizes(rr_packed *pk, int32_t *gsize, int32_t *coverage)
 {
-    if (!pk) return RR_E_ARG;
+    if (!pk || pk->phase != 3) { rr_set_error("rr_packed_sizes: the packed MSA is incomplete"); return RR_E_ARG; }
     if (gsize) memcpy(gsize, pk->h_gsize.data(), sizeof(int32_t) * pk->h_gsize.size());
     if (coverage) memcpy(coverage, pk->h_coverage.data(), sizeof(int32_t) * pk->h_coverage.size());
     return RR_OK;
@@ -519,7 +614,7 @@ extern "C" int rr_packed_sizes(rr_packed *pk, int32_t *gsize, int32_t *coverage)
 
 extern "C" int rr_pair_counts(rr_packed *pk, int64_t n, const int32_t *gi, const int32_t *gj, int32_t *out)
 {
-    if (!pk || n < 0 || (n && (!gi || !gj || !out))) return RR_E_ARG;
+    if (!pk || pk->phase != 3 || n < 0 || (n && (!gi || !gj || !out))) { rr_set_error("rr_pair_counts: bad arguments"); return RR_E_ARG; }
     if (n == 0) return RR_OK;
     RR_CUDA(cudaSetDevice(pk->device));
     rr_alloc_stream(pk->st);
@@ -745,7 +840,7 @@ extern "C" int rr_cliquer_batch(rr_packed *pk, int64_t nq, const int32_t *querie
                                 rr_cliquer_stats *stats)
 {
     if (stats) memset(stats, 0, sizeof(*stats));
-    if (!pk || nq < 0 || nq > 0x7fffffff || maxclique < 1 || mincov < 0 || !(greedy >= 0.0) ||
+    if (!pk || pk->phase != 3 || nq < 0 || nq > 0x7fffffff || maxclique < 1 || mincov < 0 || !(greedy >= 0.0) ||
         (nq && (!queries || !members || !scores || !n_members))) {
         rr_set_error("rr_cliquer_batch: bad arguments");
         return RR_E_ARG;
@@ -981,7 +1076,7 @@ extern "C" int rr_relative_vars_packed(rr_packed *pk, const int32_t *unterteilun
                                        int mingroup, int32_t *vars, int *n_vars, int64_t *pairs_tested)
 {
     if (pairs_tested) *pairs_tested = 0;
-    if (!pk || !unterteilung || !maxcorrs || !vars || !n_vars || mingroup < 1 || !(cutoff >= 0.0)) {
+    if (!pk || pk->phase != 3 || !unterteilung || !maxcorrs || !vars || !n_vars || mingroup < 1 || !(cutoff >= 0.0)) {
         rr_set_error("rr_relative_vars_packed: bad arguments");
         return RR_E_ARG;
     }
@@ -1224,6 +1319,7 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
         rr_set_error("rr_scan: part %d of %d", opts->part_index, opts->part_count);
         return RR_E_ARG;
     }
+    if (pk->phase != 3) { rr_set_error("rr_scan: the packed MSA is incomplete (rr_pack_rows without rr_pack_set_spans / rr_pack_finish)"); return RR_E_ARG; }
     if (opts->flags & RR_FLAG_HOST_FINALIZE) {
         rr_set_error("rr_scan: RR_FLAG_HOST_FINALIZE is a flag of rr_maxcorr_run; after rr_scan + rr_scan_fetch call rr_scan_finalize");
         return RR_E_ARG;
@@ -1311,7 +1407,7 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
         if (variant == RR_VARIANT_BITSET) {
             if (!(opts->flags & RR_FLAG_SEED_ONLY)) RR_CUDA(rr_launch_scan_bitset(P, pk->n_sm, pk->st));  // no seeding pass in this variant
         } else {
-            rc = rr_umma_scan(pk->umma, umma_mode, C.plan_id, P, plan, pk->d_cells, pk->d_perm, pk->codes, pk->n_sm, pk->st);
+            rc = rr_umma_scan(pk->umma, umma_mode, C.plan_id, P, plan, pk->n_sm, pk->st);
             if (rc) return rc;
         }
     }
@@ -1488,6 +1584,34 @@ extern "C" int rr_debug_umma_counts(rr_packed *pk, const rr_scan_opts *opts, int
     return RR_OK;
 }
 
+// measurement hook (include/rr_debug.h): bare tcgen05.mma loop of the scan's MMA kind on every SM, best of `reps`
+extern "C" int rr_debug_mma_peak(int device, int variant, int kblocks_per_sm, int reps, float *best_ms, double *macs)
+{
+    if (!best_ms || !macs || reps < 1 || kblocks_per_sm < 1) { rr_set_error("rr_debug_mma_peak: bad arguments"); return RR_E_ARG; }
+    if (variant != RR_VARIANT_UMMA && variant != RR_VARIANT_UMMA_F4 && variant != RR_VARIANT_UMMA_MXF4) { rr_set_error("rr_debug_mma_peak: a tcgen05 variant is required"); return RR_E_ARG; }
+    const int ndev = rr_device_count();
+    if (ndev <= 0) { rr_set_error("no CUDA device"); return RR_E_NODEV; }
+    if (device < 0 || device >= ndev) { rr_set_error("device %d out of range", device); return RR_E_ARG; }
+    RR_CUDA(cudaSetDevice(device));
+    int n_sm = 0;
+    RR_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    const int mode = variant == RR_VARIANT_UMMA_MXF4 ? 2 : variant == RR_VARIANT_UMMA_F4 ? 1 : 0;
+    event_scope ev;
+    cudaEvent_t a, b;
+    if (ev.create(&a) || ev.create(&b)) { rr_set_error("cudaEventCreate failed"); return RR_E_CUDA; }
+    *best_ms = 0.f;
+    for (int r = 0; r <= reps; r++) {                                    // r = 0: warm-up
+        float ms = 0.f;
+        RR_CUDA(cudaEventRecord(a, nullptr));
+        RR_CUDA(rr_umma_mma_peak(mode, n_sm, kblocks_per_sm, macs, nullptr));
+        RR_CUDA(cudaEventRecord(b, nullptr));
+        RR_CUDA(cudaEventSynchronize(b));
+        RR_CUDA(cudaEventElapsedTime(&ms, a, b));
+        if (r > 0 && (*best_ms == 0.f || ms < *best_ms)) *best_ms = ms;
+    }
+    return RR_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // the whole path: pack on n GPUs, scan one part each, merge (882-891)
 // ---------------------------------------------------------------------------------------
@@ -1518,30 +1642,92 @@ extern "C" int rr_maxcorr_run(const rr_msa *msa, int mincov, int n_gpus, int var
         if (++arrived == n_gpus) { arrived = 0; generation++; cv.notify_all(); }
         else cv.wait(lk, [&] { return generation != gen; });
     };
-    std::vector<double> thr(G, 0.0);
+    // spans of all rows, filled slice by slice by the workers; per-GPU export buffers of the seeded maxima
+    std::vector<int32_t> spans((size_t)3 * std::max(msa->rows, 1), 0);
+    std::vector<double *> d_vals(n_gpus, nullptr);
+    auto all_ok = [&]() { for (int e = 0; e < n_gpus; e++) if (RC[e] != RR_OK) return false; return true; };
 
     auto worker = [&](int d) {
         rr_scan_opts o;
         const unsigned scan_flags = flags & ~RR_FLAG_HOST_FINALIZE;
         o.mincov = mincov; o.variant = variant; o.flags = scan_flags; o.part_index = d; o.part_count = n_gpus;
-        int rc = rr_pack(msa, d, &PK[d]);
-        if (n_gpus > 1) {
-            // seeding pass on every GPU, max over GPUs as common thresholds, then the full pass
-            if (!rc) { o.flags = scan_flags | RR_FLAG_SEED_ONLY; rc = rr_scan(PK[d], &o, &S[d]); }
-            if (!rc) rc = rr_scan_fetch(PK[d], M[d].data(), nullptr);
+        int rc;
+        if (n_gpus == 1) {
+            rc = rr_pack(msa, d, &PK[d]);
+        } else {
+            // ---- the packing is shared: GPU d uploads and packs the rows [lo, hi) only, the bitsets are merged over NVLink
+            // (reduce-scatter + all-gather with peer copies and a word-wise OR), then every GPU finishes on the whole MSA
+            const int R = msa->rows, lo = (int)((int64_t)R * d / n_gpus), hi = (int)((int64_t)R * (d + 1) / n_gpus);
+            rc = rr_pack_rows(msa, d, lo, hi, &PK[d]);
+            if (!rc) rc = rr_pack_slice_spans(PK[d], spans.data() + lo, spans.data() + R + lo, spans.data() + 2 * (size_t)R + lo);
             RC[d] = rc;
             barrier();
-            bool all_ok = true;
-            for (int e = 0; e < n_gpus; e++) all_ok = all_ok && RC[e] == RR_OK;
-            if (d == 0 && all_ok)
-                for (size_t g = 0; g < G; g++) {
-                    double z = M[0][g];
-                    for (int e = 1; e < n_gpus; e++) z = std::max(z, M[e][g]);
-                    thr[g] = z;
+            if (!all_ok()) { if (rc) ERR[d] = rr_last_error(); return; }
+            rc = rr_pack_set_spans(PK[d], spans.data(), spans.data() + R, spans.data() + 2 * (size_t)R);
+            RC[d] = rc;
+            barrier();                                                   // every slice is packed (the call drains its stream)
+            if (!all_ok()) { if (rc) ERR[d] = rr_last_error(); return; }
+            rr_packed *me = PK[d];
+            cudaSetDevice(d);
+            rr_alloc_stream(me->st);
+            for (int e = 0; e < n_gpus; e++)
+                if (e != d && cudaDeviceEnablePeerAccess(e, 0) != cudaSuccess) cudaGetLastError();   // already enabled / not possible: copies still work
+            const size_t total16 = (size_t)6 * me->N * me->W32 * sizeof(uint32_t) / 16;   // W32 is a multiple of 4
+            auto chunk_lo = [&](int c) { return total16 * (size_t)c / n_gpus * 16; };
+            const size_t my_lo = chunk_lo(d), my_bytes = chunk_lo(d + 1) - my_lo;
+            cudaError_t ce = cudaSuccess;
+            {
+                dev_scope scope;
+                uint8_t *tmp = nullptr;
+                rc = scope.alloc(&tmp, std::max<size_t>(my_bytes, 16));
+                for (int k = 1; k < n_gpus && !rc && ce == cudaSuccess; k++) {   // my chunk of every peer's buffer, ORed into mine
+                    const int e = (d + k) % n_gpus;
+                    ce = cudaMemcpyPeerAsync(tmp, d, (const uint8_t *)PK[e]->d_bits + my_lo, e, my_bytes, me->st);
+                    if (ce == cudaSuccess) ce = rr_launch_or_words((uint8_t *)me->d_bits + my_lo, tmp, my_bytes, me->st);
                 }
+                if (ce == cudaSuccess) ce = cudaStreamSynchronize(me->st);
+            }
+            if (ce != cudaSuccess && !rc) { rr_set_error("CUDA error %s while merging the packed bitsets", cudaGetErrorString(ce)); rc = RR_E_CUDA; }
+            RC[d] = rc;
+            barrier();                                                   // every GPU's own chunk is final
+            if (!all_ok()) { if (rc) ERR[d] = rr_last_error(); return; }
+            for (int k = 1; k < n_gpus && ce == cudaSuccess; k++) {      // the other chunks from their owners
+                const int e = (d + k) % n_gpus;
+                const size_t lo_e = chunk_lo(e), bytes_e = chunk_lo(e + 1) - lo_e;
+                ce = cudaMemcpyPeerAsync((uint8_t *)me->d_bits + lo_e, d, (const uint8_t *)PK[e]->d_bits + lo_e, e, bytes_e, me->st);
+            }
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(me->st);
+            if (ce != cudaSuccess) { rr_set_error("CUDA error %s while gathering the packed bitsets", cudaGetErrorString(ce)); rc = RR_E_CUDA; }
+            RC[d] = rc;
+            barrier();                                                   // nobody reads a peer's buffer any more
+            if (!all_ok()) { if (rc) ERR[d] = rr_last_error(); return; }
+            rc = rr_pack_finish(PK[d]);
+            // ---- seeding pass on every GPU (column chunks split between them); the maxima are exchanged device to device and
+            // raised on every GPU as common thresholds (values only: they prune, and lose every tie against a real pair)
+            if (!rc) { o.flags = scan_flags | RR_FLAG_SEED_ONLY; rc = rr_scan(PK[d], &o, &S[d]); }
+            const size_t Gd = (size_t)5 * msa->cols;
+            if (!rc) rc = dev_alloc(&d_vals[d], Gd);
+            if (!rc && rr_launch_best_values(me->d_best, d_vals[d], (int64_t)Gd, me->st) != cudaSuccess) { rr_set_error("CUDA error exporting the seeded maxima"); rc = RR_E_CUDA; }
+            if (!rc && cudaStreamSynchronize(me->st) != cudaSuccess) { rr_set_error("CUDA error exporting the seeded maxima"); rc = RR_E_CUDA; }
+            RC[d] = rc;
             barrier();
-            if (!all_ok) { if (rc) ERR[d] = rr_last_error(); return; }
-            rc = rr_scan_set_thresholds(PK[d], thr.data());
+            if (!all_ok()) { if (rc) ERR[d] = rr_last_error(); rr_dev_free(d_vals[d]); return; }
+            {
+                dev_scope scope;
+                double *tmp = nullptr;
+                rc = scope.alloc(&tmp, Gd);
+                for (int k = 1; k < n_gpus && !rc && ce == cudaSuccess; k++) {
+                    const int e = (d + k) % n_gpus;
+                    ce = cudaMemcpyPeerAsync(tmp, d, d_vals[e], e, Gd * sizeof(double), me->st);
+                    if (ce == cudaSuccess) ce = rr_launch_raise_best(me->d_best, tmp, (int64_t)Gd, me->st);
+                }
+                if (ce == cudaSuccess) ce = cudaStreamSynchronize(me->st);
+            }
+            if (ce != cudaSuccess && !rc) { rr_set_error("CUDA error %s while exchanging the seeded maxima", cudaGetErrorString(ce)); rc = RR_E_CUDA; }
+            RC[d] = rc;
+            barrier();                                                   // peers are done reading d_vals[d]
+            rr_dev_free(d_vals[d]);
+            if (!all_ok()) { if (rc) ERR[d] = rr_last_error(); return; }
             o.flags = scan_flags | RR_FLAG_SKIP_SEED;
         }
         if (!rc) rc = rr_scan(PK[d], &o, &S[d]);

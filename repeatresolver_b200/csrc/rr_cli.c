@@ -8,8 +8,12 @@
  * 299); the result goes to the literal concatenation "MaxCorrsOf_" + argv[1] (991-993) as
  * 5*siglength lines "%f\n" (516-532); exit code 0, or 1 with "MA is missing." when the file
  * cannot be opened (284).  Differences: -p is the number of B200s to use (the reference's
- * thread count has no meaning here; values above the device count are clamped, -p 0 means
- * 1); the arg-max partners go to a side file "MaxCorrsArgOf_" + argv[1] (never into
+ * thread count has no meaning here; values above the device count are clamped).  -p 0 is
+ * REFUSED: in the reference it selects a different routine (AllMaxCorrsRechner, 575-635:
+ * no base-count filter, groups with fewer than 5 correlations above the cutoff zeroed, 1010-
+ * 1013), which this program does not implement - silently running the -p >= 1 semantics
+ * would write a different file.  Only the first -p devices are made visible to CUDA before
+ * its first call.  The arg-max partners go to a side file "MaxCorrsArgOf_" + argv[1] (never into
  * MaxCorrsOf_*); --variant bitset|umma, --no-finalize and --bin (also write the binary side
  * file "MaxCorrsBinOf_" + argv[1]) are extra switches.
  */
@@ -57,6 +61,28 @@ int main(int argc, char *argv[])
         if (!strcmp(argv[i], "--no-finalize")) flags &= ~RR_FLAG_HOST_FINALIZE;
         if (!strcmp(argv[i], "--no-prune")) flags |= RR_FLAG_NO_PRUNE;
     }
+    if (parallel < 1) {
+        fprintf(stderr, "\nError in MaxCorrelation\n   -p %d: the serial routine of the reference (AllMaxCorrsRechner, its count filter and "
+                        "printing) is not implemented; use -p 1..8 = number of GPUs\n", parallel);
+        exit(1);
+    }
+    {   /* make only the first -p devices visible: driver start-up and context creation scale with the visible devices */
+        const char *vis = getenv("CUDA_VISIBLE_DEVICES");
+        char buf[512];
+        size_t n = 0;
+        int k;
+        if (vis && *vis) {
+            int commas = 0;
+            for (n = 0; vis[n] && n + 1 < sizeof buf; n++) {
+                if (vis[n] == ',' && ++commas == parallel) break;
+                buf[n] = vis[n];
+            }
+            buf[n] = 0;
+        } else {
+            for (k = 0; k < parallel && n + 8 < sizeof buf; k++) n += (size_t)snprintf(buf + n, sizeof buf - n, k ? ",%d" : "%d", k);
+        }
+        setenv("CUDA_VISIBLE_DEVICES", buf, 1);
+    }
     rr_trace_mark("cli: start");
     rc = rr_msa_read(path, &msa);
     rr_trace_mark("cli: MSA read");
@@ -66,7 +92,6 @@ int main(int argc, char *argv[])
     printf("Siglength is %d.\n", rr_msa_cols(msa));
     ndev = rr_device_count();
     if (ndev < 1) { fprintf(stderr, "\nError in MaxCorrelation\n   no CUDA device (there is no CPU path)\n"); exit(1); }
-    if (parallel < 1) parallel = 1;
     if (parallel > ndev) parallel = ndev;
     G = 5L * rr_msa_cols(msa);
     M = (double *)calloc((size_t)G + 1, sizeof(double));

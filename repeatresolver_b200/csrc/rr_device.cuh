@@ -182,17 +182,19 @@ __device__ __forceinline__ bool rr_tier1_f32(const LTF &T, unsigned s, unsigned 
     return nz & !(U < thr);
 }
 
-// The same test on counts scaled by 2^QSHIFT (the tcgen05 kernel's accumulators hold count << 2 = the byte offset of
+// The same test on counts scaled by 4 (the tcgen05 kernel's accumulators hold 4 x count = the byte offset of
 // ln(count!) in the float table): T is addressed by the scaled value, every difference of scaled counts is a scaled
-// count, and x is kept a multiple of 2^QSHIFT.  Decides exactly as rr_tier1_f32 on the unscaled counts.
-template <int QSHIFT, class LTQ>
+// count, and x is kept a multiple of 4.  x = (round(mean) + 1) << 2 comes out of one FFMA: adding 2^25 to
+// meanfac * gr2 (= 4 x mean < 2^25) leaves round(mean) in the mantissa bits (ulp 4 there), so
+// x = 4 * bits + (4 - 4 * 0x4C000000) in wrap-around arithmetic.  Any x >= s inside the support gives a valid bound; this
+// one differs from rr_tier1_f32's floor(mean) + 1 by at most one.  thr = +inf (row group not in range) never survives.
+template <class LTQ>
 __device__ __forceinline__ bool rr_tier1_q(const LTQ &T, unsigned s, unsigned gr1, unsigned gr2, unsigned cov,
                                            float thr, float lnc3, float meanfac, float margin)
 {
-    constexpr unsigned ONE = 1u << QSHIFT;
     const bool nz = s != 0u;
     const unsigned hi = gr1 < gr2 ? gr1 : gr2;
-    unsigned x = ((unsigned)(meanfac * (float)gr2) & ~(ONE - 1u)) + ONE;   // (floor(mean) + 1) << QSHIFT
+    unsigned x = __float_as_uint(__fmaf_rn(meanfac, (float)gr2, 33554432.0f)) * 4u + 0xD0000004u;
     x = x > s ? x : s;
     x = x < hi ? x : hi;
     const float lp = ((T(gr2) - T(x)) - T(gr2 - x)) + ((T(cov - gr2) - T(gr1 - x)) - T((cov + x) - (gr1 + gr2))) - lnc3;

@@ -23,15 +23,15 @@ struct rr_umma_plan;
 
 cudaError_t rr_launch_row_spans(const uint8_t *cells, int R, int N, int codes, int32_t *start, int32_t *end,
                                 int32_t *ncov, cudaStream_t st);
-cudaError_t rr_launch_pack_bits(const uint8_t *cells, const int32_t *perm, int R, int N, int codes, uint32_t *bits,
-                                uint32_t *covbits, int W32, cudaStream_t st);
+cudaError_t rr_launch_pack_bits(const uint8_t *cells /* rows [row_lo, row_hi) */, const int32_t *perm, int R, int N, int codes, uint32_t *bits,
+                                uint32_t *covbits, int W32, int row_lo, int row_hi, cudaStream_t st);
 cudaError_t rr_launch_bitset_sizes(const uint32_t *sets, int64_t nsets, int W32, int32_t *sizes, cudaStream_t st);
 cudaError_t rr_launch_pair_counts(const uint32_t *bits, const uint32_t *covbits, int W32, int64_t n,
                                   const int32_t *gi, const int32_t *gj, int32_t *out, cudaStream_t st);
 cudaError_t rr_launch_general_break(const uint32_t *covbits, int W32, int N, int mincov, int32_t *breakcol,
                                     cudaStream_t st);
-cudaError_t rr_launch_pack_int8(const uint8_t *cells, const int32_t *perm, int R, int N, int codes, int8_t *xb,
-                                int64_t Kp, int fp4, cudaStream_t st);
+cudaError_t rr_launch_bits_to_operand(const uint32_t *bits, int64_t nsets, int W32, int8_t *xb, int64_t Kp, int fp4, cudaStream_t st);
+cudaError_t rr_launch_or_words(void *dst, const void *src, size_t bytes /* multiple of 16 */, cudaStream_t st);
 
 // Cliquer (rr_cliquer.cu): one listed (query slot, candidate group) pair with its four counts and, once scored, Z
 #define RR_CLQ_QB 4      // queries per block of rr_k_cliquer_counts

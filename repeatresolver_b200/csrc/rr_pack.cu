@@ -62,10 +62,13 @@ __global__ void __launch_bounds__(256) rr_k_row_spans(const uint8_t *__restrict_
 constexpr int PK_ROWS = 128;
 constexpr int PK_COLS = 128;
 
+// cells holds the rows [row_lo, row_hi) of the MSA only (a rank's slice of a row-sliced pack; the whole MSA for
+// row_lo = 0, row_hi = R): ranks whose row lies outside the slice contribute no bit, so the buffers of all slices OR
+// (= add) to the full bitsets.
 __global__ void __launch_bounds__(PK_COLS) rr_k_pack_bits(const uint8_t *__restrict__ cells,
                                                            const int32_t *__restrict__ perm, int R, int N, int codes,
                                                            uint32_t *__restrict__ bits, uint32_t *__restrict__ covbits,
-                                                           int W32)
+                                                           int W32, int row_lo, int row_hi)
 {
     __shared__ uint8_t tile[PK_ROWS][PK_COLS + 4];
     const int c0 = blockIdx.x * PK_COLS;
@@ -73,7 +76,8 @@ __global__ void __launch_bounds__(PK_COLS) rr_k_pack_bits(const uint8_t *__restr
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int rr = warp; rr < PK_ROWS; rr += PK_COLS / 32) {
         const int rank = r0 + rr;
-        const uint8_t *row = rank < R ? cells + (size_t)perm[rank] * N : nullptr;
+        const int src = rank < R ? perm[rank] : -1;
+        const uint8_t *row = src >= row_lo && src < row_hi ? cells + (size_t)(src - row_lo) * N : nullptr;
 #pragma unroll
         for (int q = 0; q < PK_COLS / 32; q++) {
             const int c = c0 + q * 32 + lane;
@@ -174,49 +178,60 @@ __global__ void __launch_bounds__(256) rr_k_general_break(const uint32_t *__rest
     if (lane == 0) breakcol[ii] = jj < ii + 20 ? ii + 20 : jj;
 }
 
-// ---- cells -> 0/1 int8 operand, K-major: x[(5*col+k)][rank] -------------------------------
-// One block: 128 ranks x 64 columns; every (column, code) row of the output gets one
-// contiguous 128-byte store per block.
-constexpr int PX_ROWS = 128;
-constexpr int PX_COLS = 64;
-__global__ void __launch_bounds__(256) rr_k_pack_int8(const uint8_t *__restrict__ cells,
-                                                       const int32_t *__restrict__ perm, int R, int N, int codes,
-                                                       int8_t *__restrict__ xb, int64_t Kp, int fp4)
+// ---- bitsets -> 0/2 operand of the tcgen05 variant, K-major: x[group][rank] ---------------------------------------
+// (elements are 0 / 2 so that a product is 4 = sizeof(float): rr_scan_umma.cu).  One warp per group bitset; a lane
+// expands one u32 word (32 ranks) per step into 32 int8 (two 16-byte stores) or 32 packed e2m1 nibbles (one 16-byte
+// store; 2.0 = 0b0100, the lower rank in the low nibble).  HBM-bound: reads 5N W32 4 bytes, writes 5N Kp (or Kp / 2).
+__device__ __forceinline__ uint32_t rr_spread8_nibbles(uint32_t b)   // bit i of b -> bit 4 i
 {
-    __shared__ uint8_t tile[PX_ROWS][PX_COLS + 4];
-    const int c0 = blockIdx.x * PX_COLS;
-    const int r0 = blockIdx.y * PX_ROWS;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int rr = warp; rr < PX_ROWS; rr += 8) {
-        const int rank = r0 + rr;
-        const uint8_t *row = rank < R ? cells + (size_t)perm[rank] * N : nullptr;
-#pragma unroll
-        for (int q = 0; q < PX_COLS / 32; q++) {
-            const int c = c0 + q * 32 + lane;
-            int code = 5;
-            if (row && c < N) code = rr_classify(row[c], codes);
-            tile[rr][q * 32 + lane] = (uint8_t)code;
+    uint32_t t = b & 0xffu;
+    t = (t | (t << 12)) & 0x000F000Fu;
+    t = (t | (t << 6)) & 0x03030303u;
+    t = (t | (t << 3)) & 0x11111111u;
+    return t;
+}
+__device__ __forceinline__ uint32_t rr_spread4_bytes(uint32_t b)     // bit i of b -> bit 8 i
+{
+    uint32_t t = b & 0xfu;
+    t = (t | (t << 14)) & 0x00030003u;
+    t = (t | (t << 7)) & 0x01010101u;
+    return t;
+}
+
+__global__ void __launch_bounds__(256) rr_k_bits_to_operand(const uint32_t *__restrict__ bits, int64_t nsets, int W32,
+                                                             int8_t *__restrict__ xb, int64_t Kp, int fp4)
+{
+    const int64_t g = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (g >= nsets) return;
+    const uint32_t *p = bits + (size_t)g * W32;
+    const int words = (int)(Kp / 32);                 // Kp is a multiple of 256; words >= W32, the tail is zero
+    if (fp4) {
+        uint4 *out = reinterpret_cast<uint4 *>(xb + (size_t)g * (Kp / 2));
+        for (int w = threadIdx.x & 31; w < words; w += 32) {
+            const uint32_t x = w < W32 ? p[w] : 0u;
+            out[w] = make_uint4(rr_spread8_nibbles(x) << 2, rr_spread8_nibbles(x >> 8) << 2, rr_spread8_nibbles(x >> 16) << 2,
+                                rr_spread8_nibbles(x >> 24) << 2);
+        }
+    } else {
+        uint4 *out = reinterpret_cast<uint4 *>(xb + (size_t)g * Kp);
+        for (int w = threadIdx.x & 31; w < words; w += 32) {
+            const uint32_t x = w < W32 ? p[w] : 0u;
+            out[2 * w] = make_uint4(rr_spread4_bytes(x) << 1, rr_spread4_bytes(x >> 4) << 1, rr_spread4_bytes(x >> 8) << 1,
+                                    rr_spread4_bytes(x >> 12) << 1);
+            out[2 * w + 1] = make_uint4(rr_spread4_bytes(x >> 16) << 1, rr_spread4_bytes(x >> 20) << 1, rr_spread4_bytes(x >> 24) << 1,
+                                        rr_spread4_bytes(x >> 28) << 1);
         }
     }
-    __syncthreads();
-    // 64 columns x 5 codes = 320 output rows of 128 bytes; a warp writes one row per step
-    // (lane -> 4 consecutive ranks packed in one u32)
-    for (int o = warp; o < PX_COLS * 5; o += 8) {
-        const int cl = o / 5, k = o - cl * 5;
-        const int col = c0 + cl;
-        if (col >= N) continue;
-        if (!fp4) {
-            uint32_t v = 0;
-#pragma unroll
-            for (int b = 0; b < 4; b++) v |= (tile[lane * 4 + b][cl] == k ? 2u : 0u) << (8 * b);   // elements 0 / 2: see rr_scan_umma.cu
-            *reinterpret_cast<uint32_t *>(xb + ((size_t)5 * col + k) * Kp + r0 + lane * 4) = v;
-        } else {
-            // packed e2m1: 2.0 = 0b0100, two reads per byte, row stride Kp/2 bytes
-            uint32_t v = 0;
-#pragma unroll
-            for (int b = 0; b < 4; b++) v |= (tile[lane * 4 + b][cl] == k ? 4u : 0u) << (4 * b);
-            *reinterpret_cast<uint16_t *>(xb + ((size_t)5 * col + k) * (Kp / 2) + r0 / 2 + lane * 2) = (uint16_t)v;
-        }
+}
+
+// word-wise OR of two bitset buffers (the merge step of a row-sliced pack inside one process)
+__global__ void __launch_bounds__(256) rr_k_or_words(uint4 *__restrict__ dst, const uint4 *__restrict__ src, int64_t n16)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+        uint4 a = dst[i];
+        const uint4 b = src[i];
+        a.x |= b.x; a.y |= b.y; a.z |= b.z; a.w |= b.w;
+        dst[i] = a;
     }
 }
 
@@ -231,11 +246,11 @@ cudaError_t rr_launch_row_spans(const uint8_t *cells, int R, int N, int codes, i
 }
 
 cudaError_t rr_launch_pack_bits(const uint8_t *cells, const int32_t *perm, int R, int N, int codes, uint32_t *bits,
-                                uint32_t *covbits, int W32, cudaStream_t st)
+                                uint32_t *covbits, int W32, int row_lo, int row_hi, cudaStream_t st)
 {
     if (N <= 0 || W32 <= 0) return cudaSuccess;
-    dim3 grid((N + PK_COLS - 1) / PK_COLS, W32 / 4);
-    rr_k_pack_bits<<<grid, PK_COLS, 0, st>>>(cells, perm, R, N, codes, bits, covbits, W32);
+    dim3 grid((unsigned)((N + PK_COLS - 1) / PK_COLS), (unsigned)(W32 / 4));
+    rr_k_pack_bits<<<grid, PK_COLS, 0, st>>>(cells, perm, R, N, codes, bits, covbits, W32, row_lo, row_hi);
     rr_count_launch(1);
     return cudaGetLastError();
 }
@@ -266,12 +281,18 @@ cudaError_t rr_launch_general_break(const uint32_t *covbits, int W32, int N, int
     return cudaGetLastError();
 }
 
-cudaError_t rr_launch_pack_int8(const uint8_t *cells, const int32_t *perm, int R, int N, int codes, int8_t *xb,
-                                int64_t Kp, int fp4, cudaStream_t st)
+cudaError_t rr_launch_bits_to_operand(const uint32_t *bits, int64_t nsets, int W32, int8_t *xb, int64_t Kp, int fp4, cudaStream_t st)
 {
-    if (N <= 0 || Kp <= 0) return cudaSuccess;
-    dim3 grid((N + PX_COLS - 1) / PX_COLS, (unsigned)(Kp / PX_ROWS));
-    rr_k_pack_int8<<<grid, 256, 0, st>>>(cells, perm, R, N, codes, xb, Kp, fp4);
+    if (nsets <= 0) return cudaSuccess;
+    rr_k_bits_to_operand<<<(unsigned)((nsets + 7) / 8), 256, 0, st>>>(bits, nsets, W32, xb, Kp, fp4);
+    rr_count_launch(1);
+    return cudaGetLastError();
+}
+
+cudaError_t rr_launch_or_words(void *dst, const void *src, size_t bytes, cudaStream_t st)
+{
+    if (bytes == 0) return cudaSuccess;
+    rr_k_or_words<<<1184, 256, 0, st>>>(reinterpret_cast<uint4 *>(dst), reinterpret_cast<const uint4 *>(src), (int64_t)(bytes / 16));
     rr_count_launch(1);
     return cudaGetLastError();
 }

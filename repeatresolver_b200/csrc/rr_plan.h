@@ -51,7 +51,8 @@ int rr_umma_row_sites(void);
 int rr_umma_col_sites(void);
 int rr_umma_kblock(int mode);
 void rr_umma_free(rr_umma_state *s);
-int rr_umma_scan(rr_umma_state *&s, int mode /* 0 int8, 1 e2m1 f8f6f4, 2 e2m1 mxf4 */, uint64_t plan_id, rr_scan_params &P, rr_plan &plan, const uint8_t *d_cells,
-                 const int32_t *d_perm, int codes, int n_sm, cudaStream_t st);
+int rr_umma_scan(rr_umma_state *&s, int mode /* 0 int8, 1 e2m1 f8f6f4, 2 e2m1 mxf4 */, uint64_t plan_id, rr_scan_params &P, rr_plan &plan,
+                 int n_sm, cudaStream_t st);
 int rr_umma_dump_tile(rr_umma_state *s, int mode, uint64_t plan_id, rr_scan_params &P, rr_plan &plan, int rt, int ct,
                       int32_t *d_out /* device, [128][240] */, int n_sm, cudaStream_t st);
+cudaError_t rr_umma_mma_peak(int mode, int n_sm, int kblocks_per_sm, double *macs, cudaStream_t st);

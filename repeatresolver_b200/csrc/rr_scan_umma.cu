@@ -57,7 +57,7 @@ constexpr int UM_WSITES = UM_COL_SITES / UM_SUB; // column sites per warp and ti
 constexpr int UM_TMEM_COLS = 512;
 constexpr int UM_ACC_STRIDE = 256;               // TMEM columns between the two accumulators
 constexpr int UM_SF_COL = 240;                   // 16 spare TMEM columns behind accumulator 0: unit block scales (mxf4)
-constexpr int UM_QSHIFT = 2;                     // accumulators hold count << UM_QSHIFT (operand elements are 2)
+constexpr int UM_QSHIFT = 2;                     // accumulators hold count << UM_QSHIFT (operand elements are 2); rr_tier1_q assumes 2
 constexpr int UM_CMASK_BYTES = 48;               // admissibility masks of a tile's column sites (one byte per site)
 
 struct __align__(16) um_wsite {                   // one column site: read by the whole warp as two 16-byte broadcasts
@@ -70,7 +70,9 @@ struct um_wmeta {                                 // per epilogue warp: metadata
 };
 struct __align__(16) um_thr_buf {                 // per tile, written by the producer's bulk copies
     rr_best_t best[UM_N];                         // running maxima of the tile's column groups as they are in HBM
-    uint8_t cmask[64];                            // [UM_COL_SITES] bit b: group b of the site is admissible (817)
+    uint8_t cmask[UM_CMASK_BYTES];                // [UM_COL_SITES] bit b: group b of the site is admissible (817)
+    int32_t has_counts;                           // written by the producer: some read covers both tiles (K blocks were issued)
+    int32_t pad[3];
 };
 
 struct um_smem_tail {
@@ -274,7 +276,8 @@ __device__ __forceinline__ uint32_t um_best_hi(const rr_best_t *p)
     return hi;
 }
 
-template <bool ALL_SMEM, int MODE, bool DUMP>
+// PACK16: 4 R < 65536 is known at compile time (the fast path of the bench workloads); otherwise decided at run time
+template <bool ALL_SMEM, int MODE, bool DUMP, bool PACK16>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const um_params U)
 {
@@ -338,6 +341,8 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const int tb = tix & 1;
                         mbar_wait_sleep(&T->bempty[tb], ((tix >> 1) & 1) ^ 1, 64);
                         const int ng = min(UM_N, 5 * U.P.N - ct * UM_N);
+                        // plain store, ordered before the waiters' reads by the release of the arrive below
+                        T->thr[tb].has_counts = (U.k_lo[ct] < khi[0] || U.k_lo[U.n_ct + ct] < khi[1]) ? 1 : 0;
                         mbar_expect_tx(&T->bfull[tb], (uint32_t)(ng * sizeof(rr_best_t) + UM_CMASK_BYTES));
                         bulk_load(&T->thr[tb].best[0], U.P.best + (size_t)ct * UM_N, (uint32_t)(ng * sizeof(rr_best_t)), &T->bfull[tb]);
                         bulk_load(&T->thr[tb].cmask[0], U.colmask + (size_t)ct * UM_CMASK_BYTES, UM_CMASK_BYTES, &T->bfull[tb]);
@@ -416,7 +421,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         um_wmeta &M = T->meta[ew];
         int c1n = 0, c2n = 0;
         const bool no_prune = (P.flags & RR_FLAG_NO_PRUNE) != 0;
-        const bool pack16 = P.R < (65536 >> UM_QSHIFT);
+        const bool pack16 = PACK16 || P.R < (65536 >> UM_QSHIFT);
         const bool subsample = U.preseed != 0;   // set by the host for the pre-seed launch only
         um_lnf<ALL_SMEM> LT;     // float table, tier 1
         LT.base = (uint32_t)__shfl_sync(0xffffffffu, (int)smem_u32(lnf_s), 0); LT.smem_bytes = (unsigned)U.lnf_smem << UM_QSHIFT; LT.gmem = P.lnfact;
@@ -426,7 +431,6 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
         for (int u = blockIdx.x; u < U.n_units; u += gridDim.x) {
             const um_unit un = U.units[u];
-            const int khi0 = U.k_hi[un.rt], khi1 = U.k_hi[U.n_rt + un.rt];
             n_units += (ew == 0 && lane == 0);
             // ---- row-side state of this thread (one output row = one group of one row site) ----
             const int ii = lane_row ? P.rowsites[un.rt * UM_ROW_SITES + quarter * 6 + site_l] : -1;
@@ -436,8 +440,8 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint32_t row_hi = row_ok ? um_best_hi(P.best + gi) : 0u;   // running max of row group i (high word), refreshed per tile
 
             for (int ct = un.ct0; ct < un.ct1; ct++, tix++) {
-                const bool has_counts = U.k_lo[ct] < khi0 || U.k_lo[U.n_ct + ct] < khi1;
                 const int jsite0 = ct * UM_COL_SITES;
+                bool has_counts;
                 // ---- this warp's column groups: sites sub, sub+UM_SUB, ... (slot w <-> site sub + w*UM_SUB), from the
                 // copy of the tile's running maxima the producer has put into shared memory
                 float thr_i = um_thr_hi(row_hi, no_prune);
@@ -446,6 +450,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const um_thr_buf &B = T->thr[tb];
                     mbar_wait(&T->bfull[tb], (tix >> 1) & 1);
                     __syncwarp();
+                    has_counts = B.has_counts != 0;
                     static_assert(UM_WSITES * 5 <= 64, "two metadata entries per lane");
                     const int w0 = lane / 5, b0 = lane - w0 * 5;
                     const int e1 = lane + 32, w1 = e1 / 5, b1 = e1 - w1 * 5;
@@ -511,7 +516,10 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         for (int b = 0; b < 5; b++) colsum[b] = site_sum5(c[b], base_lane);
                     }
                     const int cov = colsum[0] + colsum[1] + colsum[2] + colsum[3] + colsum[4];
-                    const float lnc3 = (LT((unsigned)cov) - LT((unsigned)rowsum)) - LT((unsigned)(cov - rowsum));
+                    // rows without a pair test at this site (filters 802 / 804-810) get ln C = -inf: their bound is -inf, below
+                    // every threshold (0 included), so they never survive tier 1
+                    const float lnc3 = pair_site ? (LT((unsigned)cov) - LT((unsigned)rowsum)) - LT((unsigned)(cov - rowsum))
+                                                 : __int_as_float(0xff800000);
                     float meanfac;   // ~ gr1 / cov (only steers where the pmf bound is evaluated; cov = 0 has no pair test)
                     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(meanfac) : "f"((float)max(cov, 1)));
                     meanfac *= (float)rowsum;
@@ -531,17 +539,16 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (vmask == 31) {
 #pragma unroll
                         for (int b = 0; b < 5; b++)
-                            need[b] = pair_site & rr_tier1_q<UM_QSHIFT>(LT, (unsigned)c[b], (unsigned)rowsum, (unsigned)colsum[b],
-                                                                        (unsigned)cov, fminf(thr_i, mjw[b]), lnc3, meanfac, margin);
+                            need[b] = rr_tier1_q(LT, (unsigned)c[b], (unsigned)rowsum, (unsigned)colsum[b], (unsigned)cov,
+                                                 fminf(thr_i, mjw[b]), lnc3, meanfac, margin);
                         n_pairs += pair_site ? 5 : 0;
                     } else {
 #pragma unroll
                         for (int b = 0; b < 5; b++) {
                             need[b] = false;
                             if (vmask & (1 << b)) {  // warp-uniform
-                                need[b] = pair_site & rr_tier1_q<UM_QSHIFT>(LT, (unsigned)c[b], (unsigned)rowsum,
-                                                                            (unsigned)colsum[b], (unsigned)cov,
-                                                                            fminf(thr_i, mjw[b]), lnc3, meanfac, margin);
+                                need[b] = rr_tier1_q(LT, (unsigned)c[b], (unsigned)rowsum, (unsigned)colsum[b], (unsigned)cov,
+                                                     fminf(thr_i, mjw[b]), lnc3, meanfac, margin);
                                 n_pairs += pair_site;
                             }
                         }
@@ -731,14 +738,14 @@ static int um_fill_params(rr_umma_state *S, const rr_scan_params &P, const rr_pl
     return RR_OK;
 }
 
-template <bool ALL_SMEM, int MODE, bool DUMP>
+template <bool ALL_SMEM, int MODE, bool DUMP, bool PACK16 = false>
 static cudaError_t um_launch_one(int grid, size_t smem_bytes, cudaStream_t st, const CUtensorMap &map_a, const CUtensorMap &map_b,
                                  const um_params &prm)
 {
     // per device, so set on every launch (a few microseconds)
-    cudaError_t e = cudaFuncSetAttribute(rr_k_scan_umma<ALL_SMEM, MODE, DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX);
+    cudaError_t e = cudaFuncSetAttribute(rr_k_scan_umma<ALL_SMEM, MODE, DUMP, PACK16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX);
     if (e != cudaSuccess) return e;
-    rr_k_scan_umma<ALL_SMEM, MODE, DUMP><<<grid, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
+    rr_k_scan_umma<ALL_SMEM, MODE, DUMP, PACK16><<<grid, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
     rr_count_launch(1);
     return cudaGetLastError();
 }
@@ -751,13 +758,13 @@ static cudaError_t um_launch(int mode, bool all_smem, bool dump, int grid, size_
              : mode == 1 ? um_launch_one<false, 1, true>(grid, smem_bytes, st, map_a, map_b, prm)
                          : um_launch_one<false, 0, true>(grid, smem_bytes, st, map_a, map_b, prm);
     }
+    if (mode == 2 && all_smem && prm.P.R < (65536 >> UM_QSHIFT)) return um_launch_one<true, 2, false, true>(grid, smem_bytes, st, map_a, map_b, prm);
     if (mode == 2) return all_smem ? um_launch_one<true, 2, false>(grid, smem_bytes, st, map_a, map_b, prm) : um_launch_one<false, 2, false>(grid, smem_bytes, st, map_a, map_b, prm);
     if (mode == 1) return all_smem ? um_launch_one<true, 1, false>(grid, smem_bytes, st, map_a, map_b, prm) : um_launch_one<false, 1, false>(grid, smem_bytes, st, map_a, map_b, prm);
     return all_smem ? um_launch_one<true, 0, false>(grid, smem_bytes, st, map_a, map_b, prm) : um_launch_one<false, 0, false>(grid, smem_bytes, st, map_a, map_b, prm);
 }
 
-int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &P, rr_plan &plan, const uint8_t *d_cells,
-                 const int32_t *d_perm, int codes, int n_sm, cudaStream_t st)
+int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &P, rr_plan &plan, int n_sm, cudaStream_t st)
 {
     int rc;
     const int fp4 = mode != 0;            // modes 1 and 2 share the packed e2m1 operands
@@ -775,7 +782,7 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
             rr_set_error("out of device memory for the B operand (%zu bytes)", rows * (size_t)row_bytes);
             return RR_E_NOMEM;
         }
-        UM_CUDA(rr_launch_pack_int8(d_cells, d_perm, P.R, P.N, codes, S->xb[md], S->Kp, fp4, st));
+        UM_CUDA(rr_launch_bits_to_operand(P.bits, (int64_t)rows, P.W32, S->xb[md], S->Kp, fp4, st));
     }
     const bool seeding = !(P.flags & (RR_FLAG_NO_PRUNE | RR_FLAG_SKIP_SEED));
     if (S->built_plan_id != plan_id || S->built_md != mode) {
@@ -943,4 +950,88 @@ int rr_umma_dump_tile(rr_umma_state *S, int mode, uint64_t plan_id, rr_scan_para
     rr_dev_free(d_one);
     if (e != cudaSuccess) { rr_set_error("CUDA error %s in rr_debug_umma_counts", cudaGetErrorString(e)); return RR_E_CUDA; }
     return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Measurement hook (include/rr_debug.h): the tensor pipe's rate for the MMA kind, shape and operand layout the scan
+// uses, with nothing else running - one CTA per SM issues back-to-back tcgen05.mma (M = 128, N = 240, both operands
+// from the same shared-memory tile, two TMEM accumulators alternating) and nothing is loaded or read back.  This is
+// the denominator of the hardware fraction bench.py reports (executed MACs / this rate).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int PK_BATCH = 16;   // K blocks per commit
+template <int MODE>
+__global__ void __launch_bounds__(128, 1) rr_k_mma_peak(int batches)
+{
+    uint8_t *smem = um_smem;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + UM_STAGE_BYTES);   // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + UM_STAGE_BYTES + 16);
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < UM_STAGE_BYTES / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = MODE == 0 ? 0x02020202u : 0x44444444u;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes above, async-proxy reads by the MMA
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(UM_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if constexpr (MODE == 2) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)UM_SF_COL;
+        const uint32_t one = 0x7F7F7F7Fu;
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+            ::"r"(taddr), "r"(one) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc<MODE>();
+        const uint32_t sa = smem_u32(smem);
+        const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + UM_A_BYTES);
+        for (int b = 0; b < batches; b++) {
+            const uint32_t tmem_d = tmem_base + (uint32_t)((b & 1) * UM_ACC_STRIDE);
+            for (int kb = 0; kb < PK_BATCH; kb++)
+#pragma unroll
+                for (int k = 0; k < UM_KB / 32; k++)
+                    tc_mma<MODE>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u,
+                                 tmem_base + UM_SF_COL, tmem_base + UM_SF_COL + 8);
+            tc_commit(&bar[b & 1]);
+            if (b >= 1) mbar_wait(&bar[(b - 1) & 1], ((b - 1) >> 1) & 1);   // at most two batches in flight
+        }
+        if (batches >= 1) mbar_wait(&bar[(batches - 1) & 1], ((batches - 1) >> 1) & 1);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(UM_TMEM_COLS) : "memory");
+    }
+}
+
+template <int MODE>
+cudaError_t mma_peak_launch(int grid, int batches, cudaStream_t st)
+{
+    const int smem_bytes = UM_STAGE_BYTES + 64;
+    cudaError_t e = cudaFuncSetAttribute(rr_k_mma_peak<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    rr_k_mma_peak<MODE><<<grid, 128, smem_bytes, st>>>(batches);
+    rr_count_launch(1);
+    return cudaGetLastError();
+}
+}  // namespace
+
+// mode as in rr_umma_scan; returns the MACs one launch executes (all CTAs) through *macs
+cudaError_t rr_umma_mma_peak(int mode, int n_sm, int kblocks_per_sm, double *macs, cudaStream_t st)
+{
+    const int batches = std::max(1, kblocks_per_sm / PK_BATCH);
+    *macs = (double)n_sm * batches * PK_BATCH * (double)UM_M * UM_N * UM_KB * (mode == 2 ? 2 : 1);
+    return mode == 2 ? mma_peak_launch<2>(n_sm, batches, st) : mode == 1 ? mma_peak_launch<1>(n_sm, batches, st) : mma_peak_launch<0>(n_sm, batches, st);
 }

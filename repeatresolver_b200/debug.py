@@ -33,3 +33,11 @@ def umma_counts(packed, row_tile, col_tile, mincov=30, variant="umma_mxf4", part
     _check(lib.rr_debug_umma_counts(packed._h, C.byref(opts), int(row_tile), int(col_tile), counts.ctypes.data, rg.ctypes.data,
                                     cg.ctypes.data, None, None), "rr_debug_umma_counts")
     return counts, rg, cg
+
+
+def mma_peak(variant="umma_mxf4", device=0, kblocks_per_sm=16384, reps=5):
+    """The tensor pipe's rate for the MMA kind / tile shape / operand layout of the scan (bare tcgen05.mma loop on every
+    SM, csrc/rr_scan_umma.cu): {"tflops": 2 * MACs / s / 1e12, "ms": best launch, "macs": per launch}"""
+    ms, macs = C.c_float(0), C.c_double(0)
+    _check(lib.rr_debug_mma_peak(device, VARIANTS[variant], kblocks_per_sm, reps, C.byref(ms), C.byref(macs)), "rr_debug_mma_peak")
+    return {"tflops": 2.0 * macs.value / (ms.value * 1e-3) / 1e12, "ms": ms.value, "macs": macs.value}

@@ -107,11 +107,40 @@ class MSA:
 class Packed:
     """One GPU's packed copy of an MSA (the packing half of Einlesen, on the device)."""
 
-    def __init__(self, msa, device=0):
+    def __init__(self, msa, device=0, rows=None):
+        """rows = None: the whole MSA packed on `device` (rr_pack).  rows = (lo, hi): only those rows are uploaded
+        (rr_pack_rows); the caller then exchanges the spans (slice_spans / set_spans), merges the bitsets of all slices
+        (bits_device) and calls finish() - repeatresolver_b200.dist.pack_over_ranks does that between ranks."""
         h = C.c_void_p()
-        _check(lib.rr_pack(msa._h, device, C.byref(h)), "rr_pack")
-        self._h = h
         self.rows, self.cols = msa.rows, msa.cols
+        if rows is None:
+            _check(lib.rr_pack(msa._h, device, C.byref(h)), "rr_pack")
+            self.slice = (0, msa.rows)
+        else:
+            _check(lib.rr_pack_rows(msa._h, device, int(rows[0]), int(rows[1]), C.byref(h)), "rr_pack_rows")
+            self.slice = (int(rows[0]), int(rows[1]))
+        self._h = h
+
+    def slice_spans(self):
+        """[3][hi - lo] int32: first / last covered column and covered cells of the uploaded rows"""
+        n = self.slice[1] - self.slice[0]
+        sp = np.zeros((3, max(n, 1)), dtype=np.int32)
+        _check(lib.rr_pack_slice_spans(self._h, sp[0].ctypes.data, sp[1].ctypes.data, sp[2].ctypes.data), "rr_pack_slice_spans")
+        return sp[:, :n]
+
+    def set_spans(self, spans):
+        sp = np.ascontiguousarray(spans, dtype=np.int32)
+        assert sp.shape == (3, self.rows)
+        _check(lib.rr_pack_set_spans(self._h, sp[0].ctypes.data, sp[1].ctypes.data, sp[2].ctypes.data), "rr_pack_set_spans")
+
+    def bits_device(self):
+        """(device pointer, bytes) of this slice's group + coverage bitsets: to be OR-merged (integer SUM) over the slices"""
+        p, n = C.c_void_p(), C.c_size_t(0)
+        _check(lib.rr_pack_bits_device(self._h, C.byref(p), C.byref(n)), "rr_pack_bits_device")
+        return p.value, n.value
+
+    def finish(self):
+        _check(lib.rr_pack_finish(self._h), "rr_pack_finish")
 
     def scan(self, mincov=30, variant="auto", flags=0, part_index=0, part_count=1):
         opts = ScanOpts(mincov, VARIANTS[variant] if isinstance(variant, str) else variant, flags, part_index, part_count)

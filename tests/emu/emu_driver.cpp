@@ -84,7 +84,7 @@ extern "C" {
  * tier 1 on a float copy of the ln n! table with the host-computed rounding margin, tier 2 on the double table.
  * quads: n x {s, gr1, gr2, cov}; best: n running maxima; keep1 / keep2: 1 = the pair survives the tier. */
 void emu_tiers(const double *lnf, int max_cov, long long n, const uint32_t *quads, const double *best, unsigned char *keep1,
-               unsigned char *keep2)
+               unsigned char *keep2, unsigned char *keepq)
 {
     std::vector<float> lnf32((size_t)max_cov + 2);
     for (int k = 0; k < max_cov + 2; k++) lnf32[k] = (float)lnf[k];
@@ -96,11 +96,10 @@ void emu_tiers(const double *lnf, int max_cov, long long n, const uint32_t *quad
         const float lnc3 = (LT(cov) - LT(gr1)) - LT(cov - gr1);
         const float meanfac = (1.0f / (float)std::max(cov, 1u)) * (float)gr1;
         keep1[i] = rr_tier1_f32(LT, sc, gr1, gr2, cov, rr_thr_f32(best[i], false), lnc3, meanfac, margin) ? 1 : 0;
-        // the form the tcgen05 kernel uses: counts scaled by 4 (= byte offsets into the float table), same decision
+        // the form the tcgen05 kernel uses: counts scaled by 4 (= byte offsets into the float table)
         auto LTQ = [&](unsigned off) { return lnf32[off >> 2]; };
         const float meanfac_q = (1.0f / (float)std::max(4u * cov, 1u)) * (float)(4u * gr1);
-        const bool kq = rr_tier1_q<2>(LTQ, 4u * sc, 4u * gr1, 4u * gr2, 4u * cov, rr_thr_f32(best[i], false), lnc3, meanfac_q, margin);
-        if (kq != (keep1[i] != 0)) keep1[i] = 2;   // the test fails on any value but 0 / 1
+        keepq[i] = rr_tier1_q(LTQ, 4u * sc, 4u * gr1, 4u * gr2, 4u * cov, rr_thr_f32(best[i], false), lnc3, meanfac_q, margin) ? 1 : 0;
         keep2[i] = rr_tier2(T2, sc, gr1, gr2, cov, best[i]) ? 1 : 0;
     }
 }
@@ -110,11 +109,13 @@ void emu_row_spans(const uint8_t *cells, int R, int N, int codes, int32_t *start
 {
     if (R > 0) emu_launch(dim3((unsigned)R), 256, [&] { rr_k_row_spans(cells, R, N, codes, start, end, ncov); });
 }
-void emu_pack_bits(const uint8_t *cells, const int32_t *perm, int R, int N, int codes, uint32_t *bits, uint32_t *covbits, int W32)
+/* cells = the rows [row_lo, row_hi) of the MSA only (a slice of a row-sliced pack; 0, R for the whole MSA) */
+void emu_pack_bits(const uint8_t *cells, const int32_t *perm, int R, int N, int codes, uint32_t *bits, uint32_t *covbits, int W32,
+                   int row_lo, int row_hi)
 {
     if (N <= 0 || W32 <= 0) return;
     emu_launch(dim3((unsigned)((N + PK_COLS - 1) / PK_COLS), (unsigned)(W32 / 4)), PK_COLS,
-               [&] { rr_k_pack_bits(cells, perm, R, N, codes, bits, covbits, W32); });
+               [&] { rr_k_pack_bits(cells, perm, R, N, codes, bits, covbits, W32, row_lo, row_hi); });
 }
 void emu_bitset_sizes(const uint32_t *sets, long long nsets, int W32, int32_t *sizes)
 {
@@ -128,11 +129,9 @@ void emu_general_break(const uint32_t *covbits, int W32, int N, int mincov, int3
 {
     if (N > 0) emu_launch(dim3((unsigned)((N + 7) / 8)), 256, [&] { rr_k_general_break(covbits, W32, N, mincov, breakcol); });
 }
-void emu_pack_int8(const uint8_t *cells, const int32_t *perm, int R, int N, int codes, int8_t *xb, long long Kp, int fp4)
+void emu_bits_to_operand(const uint32_t *bits, long long nsets, int W32, int8_t *xb, long long Kp, int fp4)
 {
-    if (N <= 0 || Kp <= 0) return;
-    emu_launch(dim3((unsigned)((N + PX_COLS - 1) / PX_COLS), (unsigned)(Kp / PX_ROWS)), 256,
-               [&] { rr_k_pack_int8(cells, perm, R, N, codes, xb, Kp, fp4); });
+    if (nsets > 0) emu_launch(dim3((unsigned)((nsets + 7) / 8)), 256, [&] { rr_k_bits_to_operand(bits, nsets, W32, xb, Kp, fp4); });
 }
 
 /* The AND+POPC variant of the scan, set up as rr_scan (rr_abi.cu) sets it up: plan from the spans in rank order, then

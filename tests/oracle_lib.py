@@ -35,6 +35,8 @@ def lib():
         L.rr_oracle_score.argtypes = [C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_int]
         L.rr_oracle_scan.restype = C.c_int64
         L.rr_oracle_scan.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.rr_oracle_count_pairs.restype = C.c_int64
+        L.rr_oracle_count_pairs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.rr_oracle_write.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
         L.rr_oracle_group_score.restype = C.c_double
         L.rr_oracle_group_score.argtypes = [C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_int]
@@ -108,6 +110,11 @@ class Oracle:
         A = np.zeros(G + 1, dtype=np.int32)
         P = lib().rr_oracle_scan(self._h, mincov, modulus, res_lo, res_hi, M.ctypes.data, A.ctypes.data)
         return M[:G], A[:G], int(P)
+
+    def count_pairs(self, mincov=30, modulus=1, res_lo=0, res_hi=1):
+        """PositiveSignificance calls (MaxCorrelation.c:820) of the rows ii % modulus in [res_lo, res_hi), from the loops and
+        filters alone (no score is evaluated); one thread per residue"""
+        return int(lib().rr_oracle_count_pairs(self._h, mincov, modulus, res_lo, res_hi))
 
     def cliquer(self, a, mincov=30, maxclique=30, greedy=3.0, anfang=0, ende=None):
         """RepeatResolver.c:1179-1240 for query group a: (members incl. a, scores with best[0] = 100)"""

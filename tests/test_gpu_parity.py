@@ -95,8 +95,8 @@ def check_umma_tiles(pk, oracle, variant, mincov, tiles):
         counts, rg, cg = rr.debug.umma_counts(pk, rt, ct, mincov, variant)
         rows = np.flatnonzero(rg >= 0)
         cols = np.flatnonzero(cg >= 0)
-        assert (counts[rg < 0] == 0).all(), "padding rows of the A operand must give zero counts"
-        assert (counts[:, cg < 0] == 0).all(), "columns beyond the MSA must give zero counts"
+        assert (counts[np.ix_(rg < 0, cg >= 0)] == 0).all(), "padding rows of the A operand must give zero counts"
+        assert (counts[:, cg < 0] == -1).all(), "columns beyond the MSA are not touched (the buffer is preset to -1)"
         want = oracle.count_matrix(rg[rows], cg[cols])
         got = counts[np.ix_(rows, cols)]
         assert np.array_equal(got, want), (variant, rt, ct, int((got != want).sum()))
@@ -158,6 +158,45 @@ def test_tcgen05_counts_on_golden_and_two_length_classes(variant, tmp_path):
     checked, nonzero = check_umma_tiles(pk, oracle, variant, 30, tiles)
     assert nonzero > 50000
     pk.close()
+
+
+def test_row_sliced_pack_merges_to_the_plain_pack():
+    """rr_pack_rows / rr_pack_set_spans / rr_pack_finish: three slices of the rows (one of them empty) packed by handles of
+    their own and OR-merged (here with torch on one GPU; between GPUs by NCCL or peer copies) give the plain pack: sizes,
+    coverage, pair tests, maxima and partners identical"""
+    import torch
+    from repeatresolver_b200.dist import _DevBuf
+    g = rr.MsaGen(type="Tree", copies=30, coverage=40, repeat_len=1200, diff=0.02, seed=61, flank=600, min_overlap=100)
+    codes = g.codes()
+    assert codes.shape[0] >= 1100                              # two length classes of rows
+    msa = rr.MSA.from_cells(codes)
+    pk0 = rr.Packed(msa, 0)
+    st0 = pk0.scan(mincov=30)
+    M0, A0 = pk0.fetch()
+    gs0, cv0 = pk0.sizes()
+    R = codes.shape[0]
+    cuts = [0, R // 3, R // 3, R]
+    parts = [rr.Packed(msa, 0, rows=(cuts[k], cuts[k + 1])) for k in range(3)]
+    spans = np.concatenate([p.slice_spans() for p in parts], axis=1)
+    assert spans.shape == (3, R)
+    for p in parts:
+        p.set_spans(spans)
+    bufs = [torch.as_tensor(_DevBuf(*p.bits_device()), device="cuda:0") for p in parts]
+    assert not (bufs[0] & bufs[2]).any()                       # disjoint rows: the integer sum is the OR
+    bufs[0] += bufs[1]
+    bufs[0] += bufs[2]
+    torch.cuda.synchronize()
+    parts[0].finish()
+    gs, cv = parts[0].sizes()
+    assert (gs == gs0).all() and (cv == cv0).all()
+    st = parts[0].scan(mincov=30)
+    M, A = parts[0].fetch()
+    assert st["pair_tests"] == st0["pair_tests"] and (M == M0).all() and (A == A0).all()
+    with pytest.raises(rr.RRError):
+        parts[1].scan(mincov=30)                               # a handle that was never finished holds no packed MSA
+    for p in parts:
+        p.close()
+    pk0.close()
 
 
 @pytest.mark.parametrize("variant", VARIANTS)

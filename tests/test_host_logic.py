@@ -287,6 +287,10 @@ def test_cli_without_gpu_reports_and_fails(tmp_path):
     assert r.returncode == 0 and "Usage: ./MaxCorrelation MSApath <options>" in r.stdout
     r = subprocess.run([exe, "nope"], capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 1 and "MA is missing." in r.stdout
+    # -p 0 selects a different routine in the reference (AllMaxCorrsRechner, MaxCorrelation.c:1010-1013): refused, nothing written
+    (tmp_path / "M0").write_bytes(golden_msa("kat_appendix_g"))
+    r = subprocess.run([exe, "M0", "-c", "30", "-p", "0"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1 and "-p 0" in r.stderr and not (tmp_path / "MaxCorrsOf_M0").exists()
     if rr.device_count() == 0:
         (tmp_path / "M").write_bytes(golden_msa("kat_appendix_g"))
         r = subprocess.run([exe, "M", "-c", "30"], capture_output=True, text=True, cwd=tmp_path)

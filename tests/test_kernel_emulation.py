@@ -369,11 +369,11 @@ def emu_pack(emu_scan):
     vp, i, i64 = C.c_void_p, C.c_int, C.c_longlong
     e = emu_scan
     e.emu_row_spans.argtypes = [vp, i, i, i, vp, vp, vp]
-    e.emu_pack_bits.argtypes = [vp, vp, i, i, i, vp, vp, i]
+    e.emu_pack_bits.argtypes = [vp, vp, i, i, i, vp, vp, i, i, i]
     e.emu_bitset_sizes.argtypes = [vp, i64, i, vp]
     e.emu_pair_counts.argtypes = [vp, vp, i, i64, vp, vp, vp]
     e.emu_general_break.argtypes = [vp, i, i, i, vp]
-    e.emu_pack_int8.argtypes = [vp, vp, i, i, i, vp, i64, i]
+    e.emu_bits_to_operand.argtypes = [vp, i64, i, vp, i64, i]
     return e
 
 
@@ -391,7 +391,19 @@ def device_pack(e, cells, codes_flag):
     W32 = 4 * ((R + 127) // 128)
     bits = np.zeros((5 * N, W32), dtype=np.uint32)
     cov = np.zeros((N, W32), dtype=np.uint32)
-    e.emu_pack_bits(cells.ctypes.data, perm.ctypes.data, R, N, codes_flag, bits.ctypes.data, cov.ctypes.data, W32)
+    # as a row-sliced pack (rr_pack_rows): two slices of the rows, each packed into buffers of its own, merged by OR
+    cut = R // 3
+    for lo, hi in ((0, cut), (cut, R)):
+        b1, c1 = np.zeros_like(bits), np.zeros_like(cov)
+        part = np.ascontiguousarray(cells[lo:hi])
+        if hi > lo:
+            e.emu_pack_bits(part.ctypes.data, perm.ctypes.data, R, N, codes_flag, b1.ctypes.data, c1.ctypes.data, W32, lo, hi)
+        assert not (bits & b1).any() and not (cov & c1).any()          # disjoint: OR = sum
+        bits |= b1
+        cov |= c1
+    whole_b, whole_c = np.zeros_like(bits), np.zeros_like(cov)
+    e.emu_pack_bits(cells.ctypes.data, perm.ctypes.data, R, N, codes_flag, whole_b.ctypes.data, whole_c.ctypes.data, W32, 0, R)
+    assert np.array_equal(whole_b, bits) and np.array_equal(whole_c, cov)
     gs = np.zeros(5 * N, dtype=np.int32)
     cv = np.zeros(N, dtype=np.int32)
     e.emu_bitset_sizes(bits.ctypes.data, 5 * N, W32, gs.ctypes.data)
@@ -401,7 +413,7 @@ def device_pack(e, cells, codes_flag):
 
 def test_packing_kernels_on_raw_text(emu_pack, tmp_path):
     """raw characters (lower case, '_' gaps, junk) through rr_k_row_spans / rr_k_pack_bits / rr_k_bitset_sizes /
-    rr_k_pair_counts / rr_k_general_break / rr_k_pack_int8 against numpy and the oracle"""
+    rr_k_pair_counts / rr_k_general_break / rr_k_bits_to_operand against numpy and the oracle"""
     text = golden_msa("ragged")
     o = O.Oracle.from_text(text, tmp_path)
     msa = rr.MSA.from_text(text)
@@ -437,16 +449,16 @@ def test_packing_kernels_on_raw_text(emu_pack, tmp_path):
         below = [jj for jj in range(ii + 20, n90) if shared[ii, jj] < 20]
         assert brk[ii] == (below[0] if below else max(n90, ii + 20)), ii                # MaxCorrelation.c:804-810
     # the 0/2 operands of the tensor path (a product is 4, see rr_scan_umma.cu): int8 and packed e2m1 (2.0 = 0b0100), K-major
-    Kp = 128 * ((p["R"] + 127) // 128)
+    Kp = 256 * ((p["R"] + 255) // 256)
     member = np.zeros((5 * p["N"], Kp), dtype=np.uint8)
     rc = codes[p["perm"]]
     for k in range(5):
         member[k::5, :p["R"]] = (rc == k).T
     xb = np.zeros((5 * p["N"], Kp), dtype=np.int8)
-    emu_pack.emu_pack_int8(cells.ctypes.data, p["perm"].ctypes.data, p["R"], p["N"], 0, xb.ctypes.data, Kp, 0)
+    emu_pack.emu_bits_to_operand(p["bits"].ctypes.data, 5 * p["N"], p["W32"], xb.ctypes.data, Kp, 0)
     assert np.array_equal(xb.view(np.uint8), member * 2)
     x4 = np.zeros((5 * p["N"], Kp // 2), dtype=np.uint8)
-    emu_pack.emu_pack_int8(cells.ctypes.data, p["perm"].ctypes.data, p["R"], p["N"], 0, x4.ctypes.data, Kp, 1)
+    emu_pack.emu_bits_to_operand(p["bits"].ctypes.data, 5 * p["N"], p["W32"], x4.ctypes.data, Kp, 1)
     assert np.array_equal(x4, (member[:, 0::2] * 4) | (member[:, 1::2] * 4 << 4))
 
 
@@ -528,7 +540,7 @@ def test_pruning_tiers_of_the_fused_epilogue_never_drop_a_pair_that_matters(emu)
     rr_scan_umma.cu calls them, at depths up to 40 000 reads: a pair whose exact score reaches the running maximum must
     survive both; against a maximum well above the score most pairs must be dropped (the tiers do prune)"""
     vp = C.c_void_p
-    emu.emu_tiers.argtypes = [vp, C.c_int, C.c_longlong, vp, vp, vp, vp]
+    emu.emu_tiers.argtypes = [vp, C.c_int, C.c_longlong, vp, vp, vp, vp, vp]
     rng = np.random.default_rng(23)
     for max_cov in (300, 4000, 40000):
         lnf = rr.lnfact_table(max_cov + 2)
@@ -547,17 +559,19 @@ def test_pruning_tiers_of_the_fused_epilogue_never_drop_a_pair_that_matters(emu)
             scores.append(z)
         q = np.array(quads, dtype=np.uint32)
         z = np.array(scores)
-        k1, k2 = np.zeros(len(q), dtype=np.uint8), np.zeros(len(q), dtype=np.uint8)
+        k1, k2, kq = np.zeros(len(q), dtype=np.uint8), np.zeros(len(q), dtype=np.uint8), np.zeros(len(q), dtype=np.uint8)
         # at the lower end of the support the score is exactly 0 and the kernels drop the pair before the tiers (tier 1b)
         live = z > 0
         for best in (z, z * (1 - 1e-12), z * 0.999, np.maximum(z - 1e-6, 0)):
             best = np.ascontiguousarray(best)                            # keep the buffer alive across the call
-            emu.emu_tiers(lnf.ctypes.data, max_cov, len(q), q.ctypes.data, best.ctypes.data, k1.ctypes.data, k2.ctypes.data)
-            assert (k1 <= 1).all(), "rr_tier1_q (scaled counts) decides differently from rr_tier1_f32"
+            emu.emu_tiers(lnf.ctypes.data, max_cov, len(q), q.ctypes.data, best.ctypes.data, k1.ctypes.data, k2.ctypes.data, kq.ctypes.data)
+            assert kq[live].all(), "rr_tier1_q (the scaled form the tcgen05 kernel uses) dropped a pair that matters"
+            assert (kq != k1).mean() < 0.01          # the two forms differ only where round(mean) != floor(mean) matters
             assert k1[live].all() and k2[live].all(), (max_cov, int((~k1[live].astype(bool)).sum()), int((~k2[live].astype(bool)).sum()))
         far = np.ascontiguousarray(z + 3.0)
-        emu.emu_tiers(lnf.ctypes.data, max_cov, len(q), q.ctypes.data, far.ctypes.data, k1.ctypes.data, k2.ctypes.data)
+        emu.emu_tiers(lnf.ctypes.data, max_cov, len(q), q.ctypes.data, far.ctypes.data, k1.ctypes.data, k2.ctypes.data, kq.ctypes.data)
         unsat = z < 90
+        assert kq[unsat].mean() < 0.5
         assert k1[unsat].mean() < 0.5 and (k1 & k2)[unsat].mean() < 0.3, (max_cov, k1[unsat].mean(), (k1 & k2)[unsat].mean())
 
 
