@@ -480,8 +480,9 @@ static int pack_phase_b(rr_packed *pk, const int32_t *sst, const int32_t *sen, c
     RR_CUDA(rr_launch_pack_bits(pk->d_cells, pk->d_perm, R, N, pk->codes, pk->d_bits, pk->d_covbits, pk->W32, pk->row_lo, pk->row_hi, pk->st));
     RR_CUDA(cudaEventRecord(pk->pe2, pk->st));
     RR_CUDA(cudaStreamSynchronize(pk->st));                              // perm is a local; the caller may merge the bitsets next
-    rr_dev_free(pk->d_cells);                                            // everything downstream works on the bitsets
-    pk->d_cells = nullptr;
+    // d_cells is not needed any more (everything downstream works on the bitsets) but stays allocated until the handle is
+    // freed: returning 1.8 GB to the stream-ordered pool here and taking 4.6 GB for the operand a moment later made the pool
+    // re-map physical memory on every pack when a second handle was alive (measured: +70..1900 ms per rr_pack + rr_scan)
     pk->phase = 2;
     return RR_OK;
 }

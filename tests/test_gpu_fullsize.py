@@ -55,27 +55,66 @@ def test_config2_properties(config2):
         Mm = np.where(better, Mp, Mm); Am = np.where(better, Ap, Am)
     assert Pm == st["pair_tests"] and (Mm == M).all() and (Am == A).all()
     # (b), (c): oracle on the same code matrix
-    oracle = O.Oracle.from_codes(msa.cells())
-    gs, cv = pk.sizes()
-    assert (gs == oracle.gsize()).all() and (cv == oracle.coverage()).all()
-    k = 9973
-    Ms, As, Ps = oracle.scan(30, modulus=k, res_lo=0, res_hi=1)
-    assert Ps > 1e6
-    assert (M >= Ms * (1 - REL_TOL)).all()
-    rows = np.nonzero((Ms > 0) & ((np.arange(len(Ms)) // 5) % k == 0))[0]
-    right = rows[(As[rows] > rows) & (A[rows] > rows)]
-    assert len(right) >= 5
-    assert (np.abs(M[right] - Ms[right]) <= REL_TOL * Ms[right]).all()
-    rng = np.random.default_rng(7)
-    for gidx in rng.choice(np.nonzero(M > 0)[0], 400, replace=False):
-        i, j = min(gidx, A[gidx]), max(gidx, A[gidx])
-        c = oracle.counts(i, j)
-        z = O.score(c[0], c[1], c[2], c[3], gs[i], gs[j])
-        assert abs(z - M[gidx]) <= REL_TOL * z
+    oracle_row_sample_checks(pk, msa, M, A)
     # saturated scores exist at this depth and follow 98 + 2s/(|Gi|+|Gj|)
+    oracle = O.Oracle.from_codes(msa.cells())
+    gs, _ = pk.sizes()
     sat = np.nonzero(M > 98)[0]
     assert len(sat) > 100
     for gidx in sat[:50]:
         i, j = min(gidx, A[gidx]), max(gidx, A[gidx])
         c = oracle.counts(i, j)
         assert M[gidx] == 98.0 + 2.0 * c[0] / (gs[i] + gs[j])
+
+
+def oracle_row_sample_checks(pk, msa, M, A, one_in=500, threads=16, winners=400):
+    """(b) an exact cyclic row sample of the oracle - the sites ii % (one_in * threads) < threads, one oracle thread per
+    residue, the reference's own split (MaxCorrelation.c:796): about one row site in `one_in`, a few seconds on the box's
+    cores - is a lower bound on every maximum and is attained, value and partner, on the sampled rows whose best partner
+    lies to their right; (c) a sample of the reported maxima is reproduced from the reported partner by the oracle's
+    counts and score; the device's group sizes / coverage equal the oracle's"""
+    oracle = O.Oracle.from_codes(msa.cells())
+    gs, cv = pk.sizes()
+    assert (gs == oracle.gsize()).all() and (cv == oracle.coverage()).all()
+    k = one_in * threads
+    Ms, As, Ps = oracle.scan(30, modulus=k, res_lo=0, res_hi=threads)
+    assert Ps > 2e7, Ps
+    assert (M >= Ms * (1 - REL_TOL)).all()
+    site = np.arange(len(Ms)) // 5
+    rows = np.nonzero((Ms > 0) & (site % k < threads))[0]
+    right = rows[(As[rows] > rows) & (A[rows] > rows)]
+    assert len(right) >= 100, len(right)
+    assert (np.abs(M[right] - Ms[right]) <= REL_TOL * Ms[right]).all()
+    # partner: identical, or an exact tie the sample cannot see (a partner to the left of the row belongs to another row's sweep)
+    same = A[right] == As[right]
+    assert same.mean() > 0.99, same.mean()
+    rng = np.random.default_rng(7)
+    nz = np.nonzero(M > 0)[0]
+    for gidx in rng.choice(nz, min(winners, len(nz)), replace=False):
+        i, j = min(gidx, A[gidx]), max(gidx, A[gidx])
+        c = oracle.counts(i, j)
+        z = O.score(c[0], c[1], c[2], c[3], gs[i], gs[j])
+        assert abs(z - M[gidx]) <= REL_TOL * z
+    oracle.close()
+    return Ps
+
+
+@pytest.mark.parametrize("kind", ["Distributed", "EquiDistant"])
+def test_config3_copy_families_full_size(kind):
+    """BASELINE.json configs[2]: the Distributed and EquiDistant 1perc 30000 MSAs (same shape as config 2, different
+    copy-difference structure -> different group-size spectrum, tie and saturation mix) at full size against the oracle:
+    the cyclic row sample of the oracle (lower bound everywhere, attained with its partner on the sampled rows), winners
+    re-evaluated by the oracle, and the independent AND+POPC count kernel bitwise equal on all 5N maxima and partners"""
+    g = rr.MsaGen(type=kind, copies=100, coverage=40, repeat_len=30000, diff=0.01, seed=1003, threads=16)
+    msa = rr.MSA.alloc(g.rows, g.cols, codes=True)
+    g.codes(out=msa.cells())
+    pk = rr.Packed(msa, 0)
+    st = pk.scan(mincov=30)
+    M, A = pk.fetch()
+    assert st["pair_tests"] > 3e10
+    oracle_row_sample_checks(pk, msa, M, A)
+    stb = pk.scan(mincov=30, variant="bitset")
+    Mb, Ab = pk.fetch()
+    assert stb["pair_tests"] == st["pair_tests"] and (Mb == M).all() and (Ab == A).all()
+    pk.close()
+    msa.close()

@@ -399,6 +399,19 @@ def test_whole_path_on_several_gpus(n_gpus, tmp_path):
     assert (tmp_path / "MaxCorrsOf_MSAreal").read_bytes() == O.fmt_lines(M0)
 
 
+@pytest.mark.parametrize("n_gpus", [2, 4, 8])
+def test_one_process_per_gpu_shares_the_packing(n_gpus):
+    """torchrun, NCCL: dist.pack_over_ranks (row slices, all-reduce OR of the bitsets) + scan_part + merge_over_ranks +
+    host finalisation = the single-GPU result, bit for bit (tests/helpers/dist_pack_scan.py)"""
+    if rr.device_count() < n_gpus:
+        pytest.skip(f"needs {n_gpus} GPUs")
+    import sys
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n_gpus}", "--master-addr", "127.0.0.1",
+                        "--master-port", str(29500 + n_gpus), os.path.join(ROOT, "tests", "helpers", "dist_pack_scan.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DIST_OK" in r.stdout, (r.stdout[-800:], r.stderr[-1500:])
+
+
 def test_pruning_is_sound_at_depth_with_saturation():
     """R ~ 1.8k rows, 1.2e9 pair tests, thousands of saturated (> 98) maxima: the pruned scans of all variants
     must be bitwise equal to the scan that evaluates every pair exactly (RR_FLAG_NO_PRUNE).  Regression test
