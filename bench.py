@@ -324,7 +324,7 @@ def bench_cliquer(args, rr):
                       "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                       "dtype": "u32 bitset counts, f64 score", "data": "synthetic",
                       "config": {"workload": args.workload, "path": "cliquer", "rows": R, "cols": N, "queries": int(len(queries)),
-                                 "mincov": MINCOV, "maxclique": 30, "greedy": 3.0, "kernel": os.environ.get("RR_CLIQUER_KERNEL", "default"),
+                                 "mincov": MINCOV, "maxclique": 30, "greedy": 3.0,
                                  "l2": "candidate bitsets larger than L2 at config 2; smaller workloads are L2-resident"},
                       "candidates": st["candidates"], "hits": st["hits"], "host_evals": st["host_evals"],
                       "mean_clique": float(n.mean()) if len(n) else 0.0, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
@@ -336,10 +336,126 @@ def bench_cliquer(args, rr):
     return 0
 
 
+def bench_rows(args, rr):
+    """--path relvars | kmeans: the rows after Cliquer on one GPU.  The read partition is the reads'
+    symbol at the most significant site of a scan of the same MSA (what the first split of RepeatResolver's clustering sees).
+    relvars: a step = Relative_Vars (RepeatResolver.c:2424-2493) for every part, on the packed MSA with the part as a mask
+             (rr_relative_vars_packed); unit: group pairs tested/s (one pair = one Triple_Schnitt + score of line 2465).
+    kmeans:  a step = Kmeans (2604-2821) for every part on the groups Relative_Vars selected; unit: read pairs compared/s
+             (GrMatch calls of the two sweeps, 2 x anzahl^2 per part).
+    CPU baseline: the oracle port (pinned against the unmodified RepeatResolver.c) on one core, on the smallest part."""
+    import numpy as np
+    import oracle_lib as O
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    if rr.device_count() < 1 and args.impl != "reference":
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU path")
+    g, msa = make_msa(rr, args.workload)
+    codes = msa.cells()
+    R, N = codes.shape
+    CUTOFF, MINGROUP = 3.0, 8
+
+    def cpu_leg(M, ut, parts, pk):
+        """bounded CPU sample: the smallest part, and for Relative_Vars only the groups of a window of columns (MaxCorrs zeroed
+        outside it) sized for a few million group pairs - each costs the oracle two hypergeometric tails"""
+        o = O.Oracle.from_codes(codes)
+        u_no = min(parts, key=lambda u: int((ut == u).sum()))
+        width = N
+        Mw = M
+        while True:
+            Mw = np.where(np.arange(5 * N) // 5 < width, M, 0.0)
+            vw, pw = pk.relative_vars(ut, u_no, Mw, CUTOFF, MINGROUP, with_pairs=True)
+            if pw <= 3_000_000 or width <= 200:
+                break
+            width = max(200, width // 2)
+        t0 = time.perf_counter()
+        v = o.relative_vars(ut, u_no, Mw, CUTOFF, MINGROUP)
+        t_rel = time.perf_counter() - t0
+        assert list(v) == list(vw), "device selection differs from the oracle's"
+        t0 = time.perf_counter()
+        o.kmeans(ut, u_no, v, MINGROUP)
+        t_km = time.perf_counter() - t0
+        return u_no, width, pw, len(v), t_rel, t_km
+
+    if args.impl == "reference":
+        # partition from the oracle's own scan is too slow at bench sizes: the sample MSA is scanned by the library when a GPU
+        # is present, else the reference arm is unavailable
+        if rr.device_count() < 1:
+            print(json.dumps({"impl": "reference", "unavailable": "the read partition of this path comes from a scan; no GPU here"}))
+            return 0
+    pk = rr.Packed(msa, 0)
+    pk.scan(mincov=MINCOV)
+    M, A = pk.fetch()
+    site = int(np.argmax(M)) // 5
+    ut = codes[:, site].astype(np.int32)
+    parts = [u for u in sorted(set(int(x) for x in ut)) if int((ut == u).sum()) >= 40]
+    sel = {u: pk.relative_vars(ut, u, M, CUTOFF, MINGROUP, with_pairs=True) for u in parts}
+    pairs_rel = sum(p for _, p in sel.values())
+    sizes = {u: int((ut == u).sum()) for u in parts}
+    pairs_km = sum(2 * sizes[u] * sizes[u] for u in parts if len(sel[u][0]))
+    words_rel = pairs_rel * ((R + 31) // 32)
+    scv = {u: len(sel[u][0]) // 64 + 1 for u in parts}
+    words_km = sum(2 * sizes[u] * sizes[u] * 2 * scv[u] for u in parts if len(sel[u][0]))   # 64-bit XOR+POPC = 2 x 32-bit
+
+    def step():
+        if args.path == "relvars":
+            for u in parts:
+                pk.relative_vars(ut, u, M, CUTOFF, MINGROUP)
+        else:
+            for u in parts:
+                if len(sel[u][0]):
+                    rr.Kmeans(msa, ut, u, sel[u][0], MINGROUP)
+
+    u_small, width, pw, nv, t_rel, t_km = cpu_leg(M, ut, parts, pk)
+    cpu_pairs = pw if args.path == "relvars" else 2 * sizes[u_small] ** 2
+    cpu = {"value": cpu_pairs / max(t_rel if args.path == "relvars" else t_km, 1e-9), "unit": "pairs/s", "cores": 1, "kind": "port",
+           "sample": f"part {u_small} ({sizes[u_small]} reads) of the partition at site {site}, groups of columns [0, {width}) "
+                     f"({pw} group pairs, {nv} groups selected), cutoff {CUTOFF}, mingroup {MINGROUP}"}
+    metric = "Relative_Vars group pairs/sec" if args.path == "relvars" else "Kmeans read pairs/sec"
+    if args.impl == "reference":
+        print(json.dumps({"impl": "reference", "metric": metric, "value": cpu["value"], "unit": "pairs/s", "n_gpus": args.gpus, "steps": 1,
+                          "warmup": 0, "ms_per_step": 1e3 * (t_rel if args.path == "relvars" else t_km), "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                          "config": {"workload": args.workload, "path": args.path, "rows": R, "cols": N}, "cpu_baseline": cpu,
+                          "e2e": {"value": cpu["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return 0
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(0)
+    sampler.start()
+    launches0 = rr.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    ms = (time.perf_counter() - t0) * 1e3 / args.steps           # the C-ABI calls return with their streams drained
+    launches = rr.launch_count() - launches0
+    clocks = sampler.finish()
+    pairs = pairs_rel if args.path == "relvars" else pairs_km
+    words = words_rel if args.path == "relvars" else words_km
+    peak = 148 * 16 * (clocks["sm_mhz"] or 1965) * 1e6 / 1e12
+    achieved = words / (ms * 1e-3) / 1e12
+    print(json.dumps({"metric": metric, "value": pairs / (ms * 1e-3), "unit": "pairs/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                      "dtype": "u32 bitset counts, f64 score" if args.path == "relvars" else "u64 signatures, integer", "data": "synthetic",
+                      "config": {"workload": args.workload, "path": args.path, "rows": R, "cols": N, "partition_site": site,
+                                 "parts": {str(u): {"reads": sizes[u], "vars": int(len(sel[u][0]))} for u in parts}, "cutoff": CUTOFF, "mingroup": MINGROUP,
+                                 "timing": "wall clock of the C-ABI calls (host selection / signatures / dissolution included)"},
+                      "clocks": clocks,
+                      "roofline": {"bound": "popc-issue", "achieved": achieved, "peak": peak, "unit": "Tpopc32/s", "frac": achieved / peak, "traffic": None,
+                                   "ops": "32-bit AND+POPC per pair: ceil(R/32) (relvars, whole-MSA bitsets under the part's mask) / "
+                                          "2 x (vars/64+1) per read pair and sweep (kmeans)",
+                                   "peak_source": "148 SMs x 16 POPC lanes/clk x median SM clock under load"},
+                      "cpu_baseline": cpu, "e2e": {"value": pairs / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
+                                                   "h2d_bytes_per_step": int(4 * R * len(parts)), "d2h_bytes_per_step": int(4 * 5 * N * len(parts))},
+                      "gpu_launches": launches}))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--path", default="scan", choices=["scan", "cliquer"],
-                    help="scan = the north-star hot path (default); cliquer = the next scope row (SURVEY.md 8f, 2)")
+    ap.add_argument("--path", default="scan", choices=["scan", "cliquer", "relvars", "kmeans"],
+                    help="scan = the north-star hot path (default); cliquer / relvars / kmeans = the next scope rows (SURVEY.md 8f, 2-4)")
     ap.add_argument("--queries", type=int, default=1024, help="--path cliquer: query groups per step")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -360,6 +476,8 @@ def main():
     import repeatresolver_b200 as rr
     if args.path == "cliquer":
         return bench_cliquer(args, rr)
+    if args.path in ("relvars", "kmeans"):
+        return bench_rows(args, rr)
     from repeatresolver_b200.dist import merge_over_ranks, pack_over_ranks, scan_part
 
     if args.impl == "reference":

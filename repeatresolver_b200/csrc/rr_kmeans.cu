@@ -1,7 +1,7 @@
 // rr_kmeans.cu -- the read x read sweeps of Kmeans (/root/reference/RepeatResolver.c:2604-2821) on the device
-// ("the transposed Gram problem").  EXPERIMENTAL: written when the round's GPU minutes
-// were spent, never run on a GPU (the logic passes under the CPU emulation of tests/emu); its test is opt-in (RR_TEST_UNVALIDATED=1).  The integer rules are shared with the
-// host through rr_kmeans.h and pinned there against the unmodified reference (tests/test_oracle_kmeans.py).
+// ("the transposed Gram problem"); parity on a B200 in tests/test_zz_gpu_kmeans.py, the same
+// source under the CPU emulation of tests/emu.  The integer rules are shared with the host through rr_kmeans.h and pinned
+// there against the unmodified reference (tests/test_oracle_kmeans.py).
 //
 // sig[anzahl][scv]: the signatures of the part's reads over the selected groups (64-bit words, padding 0).
 //   rr_k_km_top5       one thread per read i, all reads j in order (tiles of signatures through shared memory, every

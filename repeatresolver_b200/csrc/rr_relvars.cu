@@ -1,6 +1,6 @@
 // rr_relvars.cu -- the all-pairs step of Relative_Vars (/root/reference/RepeatResolver.c:2455-2476) on the device
-// (SURVEY.md section 8f, row 3).  EXPERIMENTAL: selected with RR_RELVARS_KERNEL=1, written when the round's GPU minutes
-// were spent and not yet run on a GPU (its logic passes under the CPU emulation of tests/emu); the default path of rr_relative_vars (rr_abi.cu) uses rr_pair_counts instead.
+// (SURVEY.md section 8f, row 3), the path behind rr_relative_vars and rr_relative_vars_packed; parity on a B200 in
+// tests/test_zz_gpu_relvars.py, the same source under the CPU emulation of tests/emu.
 //
 // Input is either the packed copy of the part's rows (rr_pack of the reads with Unterteilung == u_no, umask == NULL): a
 // group bitset is then already G & U, its size |G & U|, and |Gi & Gj & U| (Triple_Schnitt 150-161) a plain AND+POPC of two

@@ -507,26 +507,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (!__any_sync(0xffffffffu, pair_site)) continue;
                     const int rowsum = c[0] + c[1] + c[2] + c[3] + c[4];  // gr1 = |Gi & Cjj|
                     int colsum[5];                                          // gr2 = |Gj & Cii| per column group
-                    if (pack16) {   // 4 R < 65536 (warp-uniform): three shuffle rounds instead of five
-                        site_sum5_x2(c[0], c[1], base_lane, colsum[0], colsum[1]);
-                        site_sum5_x2(c[2], c[3], base_lane, colsum[2], colsum[3]);
-                        colsum[4] = site_sum5(c[4], base_lane);
-                    } else {
-#pragma unroll
-                        for (int b = 0; b < 5; b++) colsum[b] = site_sum5(c[b], base_lane);
-                    }
-                    const int cov = colsum[0] + colsum[1] + colsum[2] + colsum[3] + colsum[4];
-                    // rows without a pair test at this site (filters 802 / 804-810) get ln C = -inf: their bound is -inf, below
-                    // every threshold (0 included), so they never survive tier 1
-                    const float lnc3 = pair_site ? (LT((unsigned)cov) - LT((unsigned)rowsum)) - LT((unsigned)(cov - rowsum))
-                                                 : __int_as_float(0xff800000);
-                    float meanfac;   // ~ gr1 / cov (only steers where the pmf bound is evaluated; cov = 0 has no pair test)
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(meanfac) : "f"((float)max(cov, 1)));
-                    meanfac *= (float)rowsum;
-                    // tier 0/1 for the admissible column groups of the site, then the queue pushes.  Sites whose
-                    // five groups are all admissible (template columns, first insertion columns: ~2/3 of the pair
-                    // tests) take a straight-line path so that the 30 table look-ups of the site overlap; the
-                    // others skip their inadmissible groups with warp-uniform branches (817).
+                    int cov;
                     bool need[5];
                     float mjw[5];
                     int vmask;
@@ -536,20 +517,63 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         mjw[0] = m0.x; mjw[1] = m0.y; mjw[2] = m0.z; mjw[3] = m0.w; mjw[4] = m1.x;
                         vmask = __float_as_int(m1.y);
                     }
-                    if (vmask == 31) {
+                    if (pack16 && (vmask & (vmask - 1)) == 0) {
+                        // ---- a site with ONE admissible column group (the deep insertion columns: only their gap group is
+                        // large enough, 817): the shared coverage is the site sum of the row sums (the five groups of a site
+                        // partition its coverage), so one packed shuffle round gives cov and the group's column sum
+                        if (vmask == 0) continue;                           // warp-uniform: no admissible group, no pair test
+                        const int b1 = __ffs(vmask) - 1;                    // warp-uniform
+                        const int cb = b1 == 0 ? c[0] : b1 == 1 ? c[1] : b1 == 2 ? c[2] : b1 == 3 ? c[3] : c[4];
+                        const float mj1 = b1 == 0 ? mjw[0] : b1 == 1 ? mjw[1] : b1 == 2 ? mjw[2] : b1 == 3 ? mjw[3] : mjw[4];
+                        int cs1;
+                        site_sum5_x2(rowsum, cb, base_lane, cov, cs1);
+                        const float lnc3 = pair_site ? (LT((unsigned)cov) - LT((unsigned)rowsum)) - LT((unsigned)(cov - rowsum))
+                                                     : __int_as_float(0xff800000);
+                        float meanfac;
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(meanfac) : "f"((float)max(cov, 1)));
+                        meanfac *= (float)rowsum;
+                        const bool n1 = rr_tier1_q(LT, (unsigned)cb, (unsigned)rowsum, (unsigned)cs1, (unsigned)cov, fminf(thr_i, mj1), lnc3,
+                                                   meanfac, margin);
+                        n_pairs += pair_site;
+                        if (!__any_sync(0xffffffffu, n1)) continue;
 #pragma unroll
-                        for (int b = 0; b < 5; b++)
-                            need[b] = rr_tier1_q(LT, (unsigned)c[b], (unsigned)rowsum, (unsigned)colsum[b], (unsigned)cov,
-                                                 fminf(thr_i, mjw[b]), lnc3, meanfac, margin);
-                        n_pairs += pair_site ? 5 : 0;
+                        for (int k = 0; k < 5; k++) { need[k] = n1 && b1 == k; colsum[k] = cs1; }
                     } else {
+                        if (pack16) {   // 4 R < 65536 (warp-uniform): three shuffle rounds instead of five
+                            site_sum5_x2(c[0], c[1], base_lane, colsum[0], colsum[1]);
+                            site_sum5_x2(c[2], c[3], base_lane, colsum[2], colsum[3]);
+                            colsum[4] = site_sum5(c[4], base_lane);
+                        } else {
 #pragma unroll
-                        for (int b = 0; b < 5; b++) {
-                            need[b] = false;
-                            if (vmask & (1 << b)) {  // warp-uniform
+                            for (int b = 0; b < 5; b++) colsum[b] = site_sum5(c[b], base_lane);
+                        }
+                        cov = colsum[0] + colsum[1] + colsum[2] + colsum[3] + colsum[4];
+                        // rows without a pair test at this site (filters 802 / 804-810) get ln C = -inf: their bound is -inf,
+                        // below every threshold (0 included), so they never survive tier 1
+                        const float lnc3 = pair_site ? (LT((unsigned)cov) - LT((unsigned)rowsum)) - LT((unsigned)(cov - rowsum))
+                                                     : __int_as_float(0xff800000);
+                        float meanfac;   // ~ gr1 / cov (only steers where the pmf bound is evaluated; cov = 0 has no pair test)
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(meanfac) : "f"((float)max(cov, 1)));
+                        meanfac *= (float)rowsum;
+                        // tier 0/1 for the admissible column groups of the site, then the queue pushes.  Sites whose
+                        // five groups are all admissible (template columns, first insertion columns: ~2/3 of the pair
+                        // tests) take a straight-line path so that the 30 table look-ups of the site overlap; the
+                        // others skip their inadmissible groups with warp-uniform branches (817).
+                        if (vmask == 31) {
+#pragma unroll
+                            for (int b = 0; b < 5; b++)
                                 need[b] = rr_tier1_q(LT, (unsigned)c[b], (unsigned)rowsum, (unsigned)colsum[b], (unsigned)cov,
                                                      fminf(thr_i, mjw[b]), lnc3, meanfac, margin);
-                                n_pairs += pair_site;
+                            n_pairs += pair_site ? 5 : 0;
+                        } else {
+#pragma unroll
+                            for (int b = 0; b < 5; b++) {
+                                need[b] = false;
+                                if (vmask & (1 << b)) {  // warp-uniform
+                                    need[b] = rr_tier1_q(LT, (unsigned)c[b], (unsigned)rowsum, (unsigned)colsum[b], (unsigned)cov,
+                                                         fminf(thr_i, mjw[b]), lnc3, meanfac, margin);
+                                    n_pairs += pair_site;
+                                }
                             }
                         }
                     }

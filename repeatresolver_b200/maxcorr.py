@@ -199,7 +199,7 @@ class Packed:
                "rr_cliquer_batch")
         return members, scores, n, st.as_dict()
 
-    def relative_vars(self, Unterteilung, u_no, MaxCorrs, cutoff, mingroup):
+    def relative_vars(self, Unterteilung, u_no, MaxCorrs, cutoff, mingroup, with_pairs=False):
         """Relative_Vars (RepeatResolver.c:2424-2493) on this packed MSA, the part applied as a mask
         (rr_relative_vars_packed): ascending group ids"""
         u = np.ascontiguousarray(Unterteilung, dtype=np.int32)
@@ -209,7 +209,7 @@ class Packed:
         n, pairs = C.c_int(0), C.c_int64(0)
         _check(lib.rr_relative_vars_packed(self._h, u.ctypes.data, int(u_no), M.ctypes.data, float(cutoff), int(mingroup),
                                            out.ctypes.data, C.byref(n), C.byref(pairs)), "rr_relative_vars_packed")
-        return out[:n.value].copy()
+        return (out[:n.value].copy(), pairs.value) if with_pairs else out[:n.value].copy()
 
     def pair_counts(self, gi, gj):
         gi = np.ascontiguousarray(gi, dtype=np.int32)
@@ -359,7 +359,7 @@ def relative_vars_from_counts(maxcorrs, gsize_u, cov_u, cutoff, mingroup, triple
 
 
 def Kmeans(msa, Unterteilung, u_no, Vars, mingroup, device=0):
-    """RepeatResolver.c:2604-2821 with the reference's argument order (EXPERIMENTAL, rr_kmeans): splits part u_no of the
+    """RepeatResolver.c:2604-2821 with the reference's argument order (rr_kmeans): splits part u_no of the
     read partition; returns (number of non-empty clusters, the new partition) - the reference updates Unterteilung in place"""
     u = np.array(Unterteilung, dtype=np.int32)
     v = np.ascontiguousarray(Vars, dtype=np.int32)
