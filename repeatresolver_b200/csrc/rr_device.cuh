@@ -137,6 +137,31 @@ struct __align__(8) rr_cand {
 };
 constexpr int RR_QUEUE_CAP = 64;
 
+// a queued candidate in 20 bytes (the per-warp queues are the largest shared-memory item of the tcgen05 kernel after the
+// operand stages): four counts of 22 bits (the tcgen05 variants take R < 2^22) and two group ids of 26 bits (5N < 2^26)
+struct rr_cand_p { uint32_t w[5]; };
+__device__ __forceinline__ rr_cand_p rr_cand_pack(const rr_cand &c)
+{
+    rr_cand_p p;
+    p.w[0] = c.s | (c.gr1 << 22);                                        // s[0:22) gr1[0:10)
+    p.w[1] = (c.gr1 >> 10) | (c.gr2 << 12);                              // gr1[10:22) gr2[0:20)
+    p.w[2] = (c.gr2 >> 20) | (c.cov << 2) | ((uint32_t)c.gi << 24);      // gr2[20:22) cov[0:22) gi[0:8)
+    p.w[3] = ((uint32_t)c.gi >> 8) | ((uint32_t)c.gj << 18);             // gi[8:26) gj[0:14)
+    p.w[4] = (uint32_t)c.gj >> 14;                                       // gj[14:26)
+    return p;
+}
+__device__ __forceinline__ rr_cand rr_cand_unpack(const rr_cand_p &p)
+{
+    rr_cand c;
+    c.s = p.w[0] & 0x3fffffu;
+    c.gr1 = (p.w[0] >> 22) | ((p.w[1] & 0xfffu) << 10);
+    c.gr2 = (p.w[1] >> 12) | ((p.w[2] & 0x3u) << 20);
+    c.cov = (p.w[2] >> 2) & 0x3fffffu;
+    c.gi = (int32_t)((p.w[2] >> 24) | ((p.w[3] & 0x3ffffu) << 8));
+    c.gj = (int32_t)((p.w[3] >> 18) | (p.w[4] << 14));
+    return c;
+}
+
 // ln(n!) look-up for the bounds: LT is a callable `double operator()(unsigned n)` supplied by the kernel
 // (shared-memory table, HBM table, or both).
 struct rr_lnf_global {
@@ -230,24 +255,24 @@ __device__ __forceinline__ bool rr_tier2(const LT &T, unsigned s, unsigned gr1, 
     return !(rr_bound_effective(U2) < thr);
 }
 
-__device__ __forceinline__ void rr_queue_push(rr_cand *q, int &count, bool need, const rr_cand &c, int lane)
+__device__ __forceinline__ void rr_queue_push(rr_cand_p *q, int &count, bool need, const rr_cand &c, int lane)
 {
     const unsigned mask = __ballot_sync(0xffffffffu, need);
     if (mask == 0u) return;
-    if (need) q[count + __popc(mask & ((1u << lane) - 1u))] = c;
+    if (need) q[count + __popc(mask & ((1u << lane) - 1u))] = rr_cand_pack(c);
     count += __popc(mask);
 }
 
 // tier 3 on queued candidates, 32 per round (all of them when flush is set); both groups' maxima
 // are folded in with the 128-bit CAS
-static __device__ __noinline__ void rr_drain_exact(const rr_scan_params &P, rr_cand *q, int &count, int lane,
+static __device__ __noinline__ void rr_drain_exact(const rr_scan_params &P, rr_cand_p *q, int &count, int lane,
                                                    unsigned &n_exact, bool flush)
 {
     while (count >= 32 || (flush && count > 0)) {
         __syncwarp();
         const int take = count < 32 ? count : 32;
         if (lane < take) {
-            const rr_cand c = q[count - take + lane];
+            const rr_cand c = rr_cand_unpack(q[count - take + lane]);
             n_exact++;
             const double Z = rr_positive_significance(P.lnfact, c.s, c.gr1, c.gr2, c.cov, __ldg(P.gsize + c.gi), __ldg(P.gsize + c.gj));
             if (Z > 0.0) {
@@ -262,8 +287,8 @@ static __device__ __noinline__ void rr_drain_exact(const rr_scan_params &P, rr_c
 
 // tier 2 on queued tier-1 survivors; what survives moves on to the exact queue
 template <class LT>
-static __device__ __noinline__ void rr_drain_tier2(const rr_scan_params &P, const LT &T, rr_cand *q1, int &c1,
-                                                   rr_cand *q2, int &c2, int lane, unsigned &n_tier2, unsigned &n_exact,
+static __device__ __noinline__ void rr_drain_tier2(const rr_scan_params &P, const LT &T, rr_cand_p *q1, int &c1,
+                                                   rr_cand_p *q2, int &c2, int lane, unsigned &n_tier2, unsigned &n_exact,
                                                    bool flush)
 {
     while (c1 >= 32 || (flush && c1 > 0)) {
@@ -273,7 +298,7 @@ static __device__ __noinline__ void rr_drain_tier2(const rr_scan_params &P, cons
         rr_cand c;
         c.s = c.gr1 = c.gr2 = c.cov = 0u; c.gi = c.gj = 0;
         if (lane < take) {
-            c = q1[c1 - take + lane];
+            c = rr_cand_unpack(q1[c1 - take + lane]);
             n_tier2++;
             need = true;
             if (!(P.flags & RR_FLAG_NO_PRUNE)) {

@@ -50,10 +50,19 @@ constexpr int UM_A_BYTES = UM_M * UM_KB;         // 16384
 constexpr int UM_B_BYTES = UM_N * UM_KB;         // 30720
 constexpr int UM_STAGE_BYTES = UM_A_BYTES + UM_B_BYTES;  // 47104 = 46 * 1024
 constexpr int UM_FIRST_EPI_WARP = 4;
-constexpr int UM_EPI_WARPS = 16;
+#ifndef RR_UM_EPI_WARPS
+#define RR_UM_EPI_WARPS 16
+#endif
+constexpr int UM_EPI_WARPS = RR_UM_EPI_WARPS;    // 16 (four per scheduler) or 20
+// registers: the CTA's pool is what it is launched with (96 per thread at 640 threads, 80 at 768); the four control warps
+// drop to 32 and the epilogue warps can only take what that frees, in steps of 8 (16 warps: 96 + 4*64/16 = 112; 20 warps:
+// 80 + 4*48/20 -> 88).  Asking for more blocks forever.
+constexpr int UM_EPI_REGS = UM_EPI_WARPS == 16 ? 112 : 88;
+static_assert((UM_FIRST_EPI_WARP + UM_EPI_WARPS) * (UM_EPI_WARPS == 16 ? 96 : 80) >= UM_FIRST_EPI_WARP * 32 + UM_EPI_WARPS * UM_EPI_REGS,
+              "setmaxnreg.inc would wait for registers the CTA does not have");
 constexpr int UM_THREADS = (UM_FIRST_EPI_WARP + UM_EPI_WARPS) * 32;  // 640
 constexpr int UM_SUB = UM_EPI_WARPS / 4;         // epilogue warps per TMEM lane quarter
-constexpr int UM_WSITES = UM_COL_SITES / UM_SUB; // column sites per warp and tile (12)
+constexpr int UM_WSITES = (UM_COL_SITES + UM_SUB - 1) / UM_SUB;   // column sites per warp and tile (at most)
 constexpr int UM_TMEM_COLS = 512;
 constexpr int UM_ACC_STRIDE = 256;               // TMEM columns between the two accumulators
 constexpr int UM_SF_COL = 240;                   // 16 spare TMEM columns behind accumulator 0: unit block scales (mxf4)
@@ -77,8 +86,8 @@ struct __align__(16) um_thr_buf {                 // per tile, written by the pr
 
 struct um_smem_tail {
     um_wmeta meta[UM_EPI_WARPS];
-    rr_cand q1[UM_EPI_WARPS][RR_QUEUE_CAP];       // tier-1 survivors, one queue per epilogue warp
-    rr_cand q2[UM_EPI_WARPS][RR_QUEUE_CAP];       // tier-2 survivors (exact evaluation pending)
+    rr_cand_p q1[UM_EPI_WARPS][RR_QUEUE_CAP];     // tier-1 survivors, one queue per epilogue warp
+    rr_cand_p q2[UM_EPI_WARPS][RR_QUEUE_CAP];     // tier-2 survivors (exact evaluation pending)
     um_thr_buf thr[2];
     unsigned long long full[UM_STAGES], empty[UM_STAGES], tfull[2], tempty[2], bfull[2], bempty[2];
     uint32_t tmem_base;
@@ -121,15 +130,17 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait suspends the thread until the phase completes or a time limit passes (the hint, in ns, asks for a long one), so
+// a waiting warp issues an instruction per wake-up instead of polling
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, uint32_t parity)
 {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
         : "memory");
     return ok != 0;
 }
@@ -137,7 +148,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 {
     while (!mbar_try_wait(bar, parity)) {}
 }
-// for the single-lane producer / MMA warps: back off so the spin does not steal issue slots from the epilogue
+// the single-lane producer / MMA warps: back off between wake-ups so that they leave the issue slots to the epilogue
 __device__ __forceinline__ void mbar_wait_sleep(unsigned long long *bar, uint32_t parity, unsigned ns)
 {
     while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
@@ -405,7 +416,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(UM_EPI_REGS));
         // ================= epilogue =================
         // all counts below are in units of 1/4 (count << UM_QSHIFT), as the accumulators deliver them
         const int ew = warp - UM_FIRST_EPI_WARP;  // 0..UM_EPI_WARPS-1
@@ -417,7 +428,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const bool lane_row = lane < 30;
         unsigned n_pairs = 0, n_exact = 0, n_units = 0, n_tier2 = 0;
         uint32_t tile = 0, tix = 0;
-        rr_cand *q1 = T->q1[ew], *q2 = T->q2[ew];
+        rr_cand_p *q1 = T->q1[ew], *q2 = T->q2[ew];
         um_wmeta &M = T->meta[ew];
         int c1n = 0, c2n = 0;
         const bool no_prune = (P.flags & RR_FLAG_NO_PRUNE) != 0;
@@ -456,13 +467,17 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const int e1 = lane + 32, w1 = e1 / 5, b1 = e1 - w1 * 5;
                     const bool has1 = e1 < UM_WSITES * 5;
                     const int t0 = sub + w0 * UM_SUB, t1 = sub + w1 * UM_SUB;
-                    const bool ok0 = jsite0 + t0 < P.N && ((B.cmask[t0] >> b0) & 1) != 0;
-                    const bool ok1 = has1 && jsite0 + t1 < P.N && ((B.cmask[has1 ? t1 : 0] >> b1) & 1) != 0;
-                    const uint32_t h0 = (uint32_t)(B.best[5 * t0 + b0].z >> 32);
-                    const uint32_t h1 = has1 ? (uint32_t)(B.best[5 * t1 + b1].z >> 32) : 0u;
-                    M.site[w0].mj[b0] = ok0 ? um_thr_hi(h0, no_prune) : -1.0f;   // -1: not admissible (817)
+                    const bool in0 = w0 < UM_WSITES && t0 < UM_COL_SITES, in1 = has1 && t1 < UM_COL_SITES;
+                    const bool ok0 = in0 && jsite0 + t0 < P.N && ((B.cmask[in0 ? t0 : 0] >> b0) & 1) != 0;
+                    const bool ok1 = in1 && jsite0 + t1 < P.N && ((B.cmask[in1 ? t1 : 0] >> b1) & 1) != 0;
+                    const uint32_t h0 = in0 ? (uint32_t)(B.best[5 * t0 + b0].z >> 32) : 0u;
+                    const uint32_t h1 = in1 ? (uint32_t)(B.best[5 * t1 + b1].z >> 32) : 0u;
+                    if (w0 < UM_WSITES) M.site[w0].mj[b0] = ok0 ? um_thr_hi(h0, no_prune) : -1.0f;   // -1: not admissible (817)
                     if (has1) M.site[w1].mj[b1] = ok1 ? um_thr_hi(h1, no_prune) : -1.0f;
-                    if (lane < UM_WSITES) M.site[lane].vmask = jsite0 + sub + lane * UM_SUB < P.N ? (int)(B.cmask[sub + lane * UM_SUB] & 31u) : 0;
+                    if (lane < UM_WSITES) {
+                        const int tl = sub + lane * UM_SUB;
+                        M.site[lane].vmask = tl < UM_COL_SITES && jsite0 + tl < P.N ? (int)(B.cmask[tl] & 31u) : 0;
+                    }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&T->bempty[tb]);
                     // the row group's maximum for the next tile of this unit (consumed at the top of the next iteration)
@@ -600,7 +615,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             // pick up what this and the other warps / CTAs have found meanwhile
                             if (row_ok) thr_i = rr_thr_f32(rr_best_value(P.best + gi), no_prune);
                             for (int e = lane; e < UM_WSITES * 5; e += 32)
-                                if (M.site[e / 5].mj[e % 5] >= 0.0f)
+                                if (M.site[e / 5].mj[e % 5] >= 0.0f)   // (admissible implies inside the tile and the MSA)
                                     M.site[e / 5].mj[e % 5] = rr_thr_f32(rr_best_value(P.best + 5 * (jsite0 + sub + (e / 5) * UM_SUB) + (e % 5)), no_prune);
                             __syncwarp();
                         }
