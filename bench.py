@@ -40,7 +40,7 @@ WORKLOADS = {
 MINCOV = 30
 # dram__bytes_read.sum + dram__bytes_write.sum of the scan kernel, per launch, from the committed ncu capture
 # (profiles/); None until measured for that workload
-TRAFFIC = {"Tree_1perc_30000": 1.092e11}  # profiles/r1_scan_metrics_config2_final.csv (ID 2 = full pass): dram read 107.9 GB + write 1.3 GB, mxf4 operands
+TRAFFIC = {"Tree_1perc_30000": 1.227e11}  # profiles/r2_final_ncu_full_summary.csv (full pass, --set full, cold L2): dram read 121.5 GB + write 1.2 GB, mxf4 operands
 
 
 def load_peaks():

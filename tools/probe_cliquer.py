@@ -1,8 +1,7 @@
 """Timing probe for rr_cliquer_batch: a generated MSA, the queries a Group_Refinement pass
 would issue (minor groups of a plausible size), device time of the two kernels and wall time of the whole call.
 Usage: python tools/probe_cliquer.py [copies] [repeat_len] [n_queries] [out.json] [reps]
-Both count kernels of csrc/rr_cliquer.cu are run in one process (RR_CLIQUER_KERNEL is read at every call), so that one
-ncu run (`-k regex:rr_k_cliquer_counts -c 2`, reps = 1) captures a launch of each.
+(`ncu -k regex:rr_k_cliquer_counts -c 1` with reps = 1 captures the count kernel.)
 The figures it prints: candidate pairs per second (one pair = one Schnitt of RepeatResolver.c:1213) and the bytes of
 bitsets one launch has to stream at least once (6 bitsets per candidate site), i.e. the HBM floor of the count kernel."""
 import json
@@ -33,15 +32,14 @@ def main():
     res = {"rows": int(codes.shape[0]), "cols": int(codes.shape[1]), "queries": int(len(queries)), "gen_s": round(t_gen, 2)}
     w32 = 4 * ((codes.shape[0] + 127) // 128)
     res["bitset_bytes_one_pass"] = int(6 * codes.shape[1] * w32 * 4)
-    for kernel in ("1", "2") + (("3",) if os.environ.get("RR_TEST_UNVALIDATED") == "1" else ()):
-        os.environ["RR_CLIQUER_KERNEL"] = kernel
+    for kernel in ("",):
         runs = []
         for rep in range(reps):
             t = time.time()
             members, scores, n, st = pk.cliquer_batch(queries, 30, 30, 3.0)
             runs.append(dict(st, wall_ms=round((time.time() - t) * 1e3, 2), mean_clique=float(n.mean())))
         st = runs[-1]
-        res["kernel" + kernel] = {"last_run": st, "kernel_ms_all": [round(r["kernel_ms"], 3) for r in runs],
+        res["kernel"] = {"last_run": st, "kernel_ms_all": [round(r["kernel_ms"], 3) for r in runs],
                                   "pairs_per_s_kernel": st["pairs"] / (st["kernel_ms"] * 1e-3),
                                   "pairs_per_s_call": st["pairs"] / (st["wall_ms"] * 1e-3),
                                   "us_per_query_kernel": st["kernel_ms"] * 1e3 / len(queries),

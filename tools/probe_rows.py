@@ -1,8 +1,8 @@
-"""Timing probe for the rows after Cliquer on a generated MSA, for the next round's first GPU
-call: Relative_Vars through its default path (part packed on the device, rr_pair_counts, host scores) and through the tiled
-kernel of csrc/rr_relvars.cu (RR_RELVARS_KERNEL=1; and on the packed whole MSA with the part as a mask), and Kmeans (csrc/rr_kmeans.cu) on the groups it selects.  The read
-partition is the reads' symbol at the most significant site (MaxCorrs from a scan on the same GPU).  Wall times of the C-ABI
-calls; the two Relative_Vars paths must agree.  Usage: python tools/probe_rows.py [copies] [repeat_len] [out.json]"""
+"""Timing probe for the rows after Cliquer on a generated MSA: Relative_Vars with the part's rows
+packed as an MSA of their own (rr_relative_vars) and as a mask over the packed whole MSA (rr_relative_vars_packed), which must
+agree, and Kmeans (csrc/rr_kmeans.cu) on the groups it selects.  The read partition is the reads' symbol at the most
+significant site (MaxCorrs from a scan on the same GPU).  Wall times of the C-ABI calls.
+Usage: python tools/probe_rows.py [copies] [repeat_len] [out.json]"""
 import json
 import os
 import sys
@@ -31,15 +31,10 @@ def main():
         if size < 40:
             continue
         part = {"reads": size}
-        os.environ.pop("RR_RELVARS_KERNEL", None)
         t = time.time()
         v0 = rr.Relative_Vars(msa, ut, u_no, M, 3.0, 8)
-        part["relvars_default_ms"] = round((time.time() - t) * 1e3, 2)
-        os.environ["RR_RELVARS_KERNEL"] = "1"
-        t = time.time()
-        v1 = rr.Relative_Vars(msa, ut, u_no, M, 3.0, 8)
-        part["relvars_kernel_ms"] = round((time.time() - t) * 1e3, 2)
-        os.environ.pop("RR_RELVARS_KERNEL", None)
+        part["relvars_packed_per_part_ms"] = round((time.time() - t) * 1e3, 2)
+        v1 = v0
         t = time.time()
         v2 = pk.relative_vars(ut, u_no, M, 3.0, 8)
         part["relvars_masked_ms"] = round((time.time() - t) * 1e3, 2)
