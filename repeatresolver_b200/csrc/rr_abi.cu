@@ -1194,11 +1194,25 @@ extern "C" int rr_kmeans_signatures(const rr_msa *msa, const int32_t *unterteilu
     *anzahl_out = anzahl;
     if (!sig_out) return RR_OK;
     std::fill(sig_out, sig_out + (size_t)anzahl * scv, (uint64_t)0);
-    for (int i = 0; i < anzahl; i++) {
-        const uint8_t *row = rr_msa_row(msa, reads_out[i]);
-        uint64_t *sg = sig_out + (size_t)i * scv;
-        for (int j = 0; j < n_vars; j++)
-            if (host_class(row[vars[j] / 5], msa->codes) == vars[j] % 5) sg[j / 64] |= (uint64_t)1 << (j % 64);
+    // site and symbol of every selected group once, then the reads in parallel (one read = one row of the matrix)
+    std::vector<int32_t> vsite((size_t)n_vars);
+    std::vector<uint8_t> vsym((size_t)n_vars);
+    for (int j = 0; j < n_vars; j++) { vsite[j] = vars[j] / 5; vsym[j] = (uint8_t)(vars[j] % 5); }
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)16, (int64_t)std::thread::hardware_concurrency(),
+                                                                  (int64_t)anzahl * n_vars / 2000000 + 1}));
+    auto work = [&](int t) {
+        for (int i = (int)((int64_t)anzahl * t / nt); i < (int)((int64_t)anzahl * (t + 1) / nt); i++) {
+            const uint8_t *row = rr_msa_row(msa, reads_out[i]);
+            uint64_t *sg = sig_out + (size_t)i * scv;
+            for (int j = 0; j < n_vars; j++)
+                if (host_class(row[vsite[j]], msa->codes) == vsym[j]) sg[j / 64] |= (uint64_t)1 << (j % 64);
+        }
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) th.emplace_back(work, t);
+        for (auto &t : th) t.join();
     }
     return RR_OK;
 }
@@ -1218,15 +1232,32 @@ extern "C" int rr_kmeans_finish(int anzahl, int scv, const uint64_t *sig, const 
         cluster_out[i] = cluster_in[i];
         size[cluster_in[i]]++;
     }
+    // the reads are visited in order and the sizes change as they go (that order is part of the reference's result); the
+    // search for one read's best cluster is independent work over j and is what costs: anzahl x scv word operations
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)16, (int64_t)std::thread::hardware_concurrency(),
+                                                                  (int64_t)anzahl * scv / 200000 + 1}));
+    std::vector<int> tb((size_t)nt), tj((size_t)nt);
     for (int min = 2; min < mingroup; min++)
         for (int i = 0; i < anzahl; i++)
             if (size[cluster_out[i]] <= min) {
+                auto search = [&](int t) {
+                    int best = 0, best_j = 0;                            // first best in ascending j, as the serial loop
+                    for (int j = (int)((int64_t)anzahl * t / nt); j < (int)((int64_t)anzahl * (t + 1) / nt); j++)
+                        if (size[j] >= min && cluster_out[i] != j) {
+                            const int score = rr_km_match(cen + (size_t)j * scv, sig + (size_t)i * scv, scv);
+                            if (score > best && i != j) { best = score; best_j = j; }
+                        }
+                    tb[t] = best; tj[t] = best_j;
+                };
+                if (nt == 1) search(0);
+                else {
+                    std::vector<std::thread> th;
+                    for (int t = 0; t < nt; t++) th.emplace_back(search, t);
+                    for (auto &t : th) t.join();
+                }
                 int best = 0, best_j = 0;
-                for (int j = 0; j < anzahl; j++)
-                    if (size[j] >= min && cluster_out[i] != j) {
-                        const int score = rr_km_match(cen + (size_t)j * scv, sig + (size_t)i * scv, scv);
-                        if (score > best && i != j) { best = score; best_j = j; }
-                    }
+                for (int t = 0; t < nt; t++)
+                    if (tb[t] > best) { best = tb[t]; best_j = tj[t]; }  // strict >: the earliest slice wins ties
                 size[cluster_out[i]]--;
                 cluster_out[i] = best_j;
                 size[best_j]++;

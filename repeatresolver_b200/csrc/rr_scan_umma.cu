@@ -889,8 +889,14 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
                 if (ncb <= 0) continue;
                 for (int cc = cb0 / UNIT_CT; cc <= (cb0 + ncb - 1) / UNIT_CT; cc++) {
                     if (cc % plan.part_count != plan.part_index) continue;
-                    um_unit un = {rb, std::max(cb0, cc * UNIT_CT), std::min(cb0 + ncb, (cc + 1) * UNIT_CT)};
-                    ks.push_back({((int64_t)(cc / GC) << 32) + ((int64_t)rb << 12) + (cc % (GC * 64)), un});
+                    // with several parts a GPU owns 1/parts of the chunks: one column tile per unit then, so that the few seed
+                    // row tiles still fill its SMs (8 parts at config 2: 190 four-tile units for 148 SMs = two uneven waves)
+                    const int c_lo = std::max(cb0, cc * UNIT_CT), c_hi = std::min(cb0 + ncb, (cc + 1) * UNIT_CT);
+                    const int step = plan.part_count > 1 ? 1 : UNIT_CT;
+                    for (int c = c_lo; c < c_hi; c += step) {
+                        um_unit un = {rb, c, std::min(c_hi, c + step)};
+                        ks.push_back({((int64_t)(cc / GC) << 32) + ((int64_t)rb << 12) + ((int64_t)(cc % (GC * 64)) << 3) + (c - c_lo), un});
+                    }
                 }
             }
             std::sort(ks.begin(), ks.end(), [](const keyed &x, const keyed &y) { return x.key < y.key; });
