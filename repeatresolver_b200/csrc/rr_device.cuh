@@ -207,24 +207,51 @@ __device__ __forceinline__ bool rr_tier1_f32(const LTF &T, unsigned s, unsigned 
     return nz & !(U < thr);
 }
 
-// The same test on counts scaled by 4 (the tcgen05 kernel's accumulators hold 4 x count = the byte offset of
-// ln(count!) in the float table): T is addressed by the scaled value, every difference of scaled counts is a scaled
-// count, and x is kept a multiple of 4.  x = (round(mean) + 1) << 2 comes out of one FFMA: adding 2^25 to
-// meanfac * gr2 (= 4 x mean < 2^25) leaves round(mean) in the mantissa bits (ulp 4 there), so
-// x = 4 * bits + (4 - 4 * 0x4C000000) in wrap-around arithmetic.  Any x >= s inside the support gives a valid bound; this
-// one differs from rr_tier1_f32's floor(mean) + 1 by at most one.  thr = +inf (row group not in range) never survives.
+// Tier 1 of the tcgen05 kernel: the same bound in FIXED POINT.  The table holds q(n) = round(ln(n!) * S), S a power of two
+// with ln(maxcov!) * S < 2^30, addressed by 4 n (the accumulators hold 4 x count = the byte offset of an entry; every
+// difference of scaled counts is again one, and x is kept a multiple of 4).  Sums and differences of entries are exact in
+// integer arithmetic and take 3-input adds; what is left to cover is the rounding of the nine entries of ln pmf
+// (|error| <= 4.5 units): RR_T1Q_SLACK.  A running maximum becomes the integer nq = SLACK - thrq, thrq = the threshold in
+// table units rounded DOWN (rr_thr_q); the pair survives iff lnpmf_q <= max(nq_i, nq_j), i.e. unless
+//   -log10 pmf  <=  log10(e) (thrq - 1.5) / S  <  min(threshold_i, threshold_j).
+// x = (round(mean) + 1) << 2 comes out of one FFMA: adding 2^25 to meanfac * gr2 (= 4 x mean < 2^25) leaves round(mean) in
+// the mantissa bits (ulp 4 there), so x = 4 * bits + (4 - 4 * 0x4C000000) in wrap-around arithmetic; any x >= s inside the
+// support gives a valid bound.  lnc3q = q(cov) - q(gr1) - q(cov - gr1), or RR_T1Q_NEVER for rows without a pair test at the
+// site (their ln pmf then comes out far above every nq).
+constexpr int RR_T1Q_SLACK = 5;
+constexpr int RR_T1Q_NEVER = -(1 << 30);
+constexpr int RR_T1Q_INADMISSIBLE = -0x7fffffff;   // nq of a column group that is not admissible: nothing survives it
+
+// S = 2^k, the largest with ln(maxcov!) * S < 2^30 (k <= 20)
+RR_HD int rr_t1q_shift(double lnfact_maxcov)
+{
+    int k = 20;
+    while (k > 0 && lnfact_maxcov * (double)(1 << k) >= 1073741824.0) k--;
+    return k;
+}
+
+// nq of a running maximum; qscale = ln(10) * S rounded down to float.  A maximum of 0 ("none yet") and the exhaustive scan
+// give nq = SLACK: ln pmf <= 0 always survives.  The clamp at 98 is rr_bound_effective folded in (a raw score above 98 is
+// replaced by 98 + F, which can exceed it).  -2: the float product and qscale may each be up to one unit too high.
+__device__ __forceinline__ int rr_thr_q(double best, bool no_prune, float qscale)
+{
+    if (no_prune) return RR_T1Q_SLACK;
+    const float t = fminf(__double2float_rd(best), (float)RR_SATURATION_START);
+    const int thrq = __float2int_rd(t * qscale) - 2;
+    return RR_T1Q_SLACK - (thrq > 0 ? thrq : 0);
+}
+
 template <class LTQ>
-__device__ __forceinline__ bool rr_tier1_q(const LTQ &T, unsigned s, unsigned gr1, unsigned gr2, unsigned cov,
-                                           float thr, float lnc3, float meanfac, float margin)
+__device__ __forceinline__ bool rr_tier1_q(const LTQ &T, unsigned s, unsigned gr1, unsigned gr2, unsigned cov, int nq, int lnc3q,
+                                           float meanfac)
 {
     const bool nz = s != 0u;
     const unsigned hi = gr1 < gr2 ? gr1 : gr2;
     unsigned x = __float_as_uint(__fmaf_rn(meanfac, (float)gr2, 33554432.0f)) * 4u + 0xD0000004u;
     x = x > s ? x : s;
     x = x < hi ? x : hi;
-    const float lp = ((T(gr2) - T(x)) - T(gr2 - x)) + ((T(cov - gr2) - T(gr1 - x)) - T((cov + x) - (gr1 + gr2))) - lnc3;
-    const float U = -(float)RR_LOG10E * lp + margin;
-    return nz & !(U < thr);
+    const int lp = ((T(gr2) - T(x) - T(gr2 - x)) + (T(cov - gr2) - T(gr1 - x) - T((cov + x) - (gr1 + gr2)))) - lnc3q;
+    return nz & (lp <= nq);
 }
 
 // tier 2: P[X >= s] >= sum_{x = x0}^{x0+m} pmf(x) for any x0 >= s; the window starts next to the mean

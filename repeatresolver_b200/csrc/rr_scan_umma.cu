@@ -32,6 +32,7 @@
 #include <cuda.h>
 #include <vector>
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include "rr_kernels.h"
 #include "rr_device.cuh"
@@ -70,7 +71,7 @@ constexpr int UM_QSHIFT = 2;                     // accumulators hold count << U
 constexpr int UM_CMASK_BYTES = 48;               // admissibility masks of a tile's column sites (one byte per site)
 
 struct __align__(16) um_wsite {                   // one column site: read by the whole warp as two 16-byte broadcasts
-    float mj[5];                                  // running maxima, rounded down to float (thresholds only)
+    int nq[5];                                    // running maxima as fixed-point tier-1 limits (rr_thr_q); inadmissible: never
     int vmask;                                    // bit b set: group b of the site is admissible (817)
     int pad[2];
 };
@@ -96,7 +97,7 @@ struct um_smem_tail {
 constexpr size_t UM_TAIL_OFF = (size_t)UM_STAGES * UM_STAGE_BYTES;
 constexpr size_t UM_LNF_OFF = (UM_TAIL_OFF + sizeof(um_smem_tail) + 15) & ~(size_t)15;
 constexpr size_t UM_SMEM_MAX = 227 * 1024;
-constexpr int UM_LNF_MAX = (int)((UM_SMEM_MAX - UM_LNF_OFF) / sizeof(float));  // ln(n!) float entries that fit
+constexpr int UM_LNF_MAX = (int)((UM_SMEM_MAX - UM_LNF_OFF) / sizeof(int));  // ln(n!) table entries that fit
 static_assert(UM_LNF_MAX >= 4096, "the float ln(n!) table should hold the depths of the bench workloads");
 
 struct um_unit { int32_t rt, ct0, ct1; };         // row tile, column tiles [ct0, ct1)
@@ -109,8 +110,9 @@ struct um_params {
     const int32_t *k_lo;      // [2][n_ct] inclusive K-block bound per class and column tile
     int n_rt, n_ct;
     const uint8_t *colmask;   // [n_ct * 48 (+ padding)] per column site: bit b = group b admissible as a column group
-    int lnf_smem;             // ln(n!) entries (as float) staged in shared memory
-    float t1_margin;          // FP32 tier-1 rounding margin, log10 units (see rr_tier1_f32)
+    int lnf_smem;             // ln(n!) entries (fixed point, rr_tier1_q) staged in shared memory
+    int t1q_shift;            // their scale S = 2^shift
+    float t1q_scale;          // ln(10) * S rounded down: thresholds -> table units
     int preseed;              // pre-seed launch: subsample the rows of first-visit columns
     int32_t *dump;            // DUMP instantiation only: [UM_M][UM_N] counts of the (single) tile processed
 };
@@ -253,32 +255,33 @@ __device__ __forceinline__ void site_sum5_x2(int x0, int x1, int base_lane, int 
 
 extern __shared__ __align__(1024) uint8_t um_smem[];
 
-// ln(n!) for the bounds, addressed by the BYTE OFFSET 4 n (what the accumulators hold).  ALL_SMEM: every argument
-// (<= largest column coverage) is inside the table staged in shared memory; otherwise the tail of the table is read
-// from HBM/L2.
+// round(ln(n!) * S) for the bounds (rr_tier1_q), addressed by the BYTE OFFSET 4 n (what the accumulators hold).
+// ALL_SMEM: every argument (<= largest column coverage) is inside the table staged in shared memory; otherwise the tail
+// is computed from the double table in HBM/L2 with the same rounding.
 template <bool ALL_SMEM>
 struct um_lnf {
-    uint32_t base;   // shared-window address of the float table
+    uint32_t base;   // shared-window address of the table
     unsigned smem_bytes;
     const double *gmem;
-    __device__ __forceinline__ float lds(unsigned off) const
+    double scale;
+    __device__ __forceinline__ int lds(unsigned off) const
     {
-        float v;
-        asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + off));
+        int v;
+        asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(base + off));
         return v;
     }
-    __device__ __forceinline__ float operator()(unsigned off) const
+    __device__ __forceinline__ int operator()(unsigned off) const
     {
         if constexpr (ALL_SMEM) return lds(off);
-        else return off < smem_bytes ? lds(off) : (float)__ldg(gmem + (off >> UM_QSHIFT));
+        else return off < smem_bytes ? lds(off) : __double2int_rn(__ldg(gmem + (off >> UM_QSHIFT)) * scale);
     }
 };
 
-// a threshold from the high word of a running maximum (a non-negative double): dropping the low word and rounding
-// down can only lower it (thresholds may be stale or low, never high)
-__device__ __forceinline__ float um_thr_hi(uint32_t hi, bool no_prune)
+// a tier-1 limit from the high word of a running maximum (a non-negative double): dropping the low word can only lower the
+// maximum (thresholds may be stale or low, never high)
+__device__ __forceinline__ int um_nq_hi(uint32_t hi, bool no_prune, float qscale)
 {
-    return rr_thr_f32(__hiloint2double((int)hi, 0), no_prune);
+    return rr_thr_q(__hiloint2double((int)hi, 0), no_prune, qscale);
 }
 __device__ __forceinline__ uint32_t um_best_hi(const rr_best_t *p)
 {
@@ -294,7 +297,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 {
     uint8_t *smem = um_smem;
     um_smem_tail *T = reinterpret_cast<um_smem_tail *>(smem + UM_TAIL_OFF);
-    float *lnf_s = reinterpret_cast<float *>(smem + UM_LNF_OFF);
+    int *lnf_s = reinterpret_cast<int *>(smem + UM_LNF_OFF);
     const rr_scan_params &P = U.P;
     // the warp index through a shuffle: the compiler then keeps it (and what derives from it) in uniform registers
     // instead of re-reading SR_TID inside the epilogue loop
@@ -314,7 +317,10 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&T->tmem_base)), "n"(UM_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int n = threadIdx.x; n < U.lnf_smem; n += UM_THREADS) lnf_s[n] = (float)U.P.lnfact[n];
+    {
+        const double scale = (double)(1 << U.t1q_shift);
+        for (int n = threadIdx.x; n < U.lnf_smem; n += UM_THREADS) lnf_s[n] = __double2int_rn(U.P.lnfact[n] * scale);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -434,11 +440,12 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const bool no_prune = (P.flags & RR_FLAG_NO_PRUNE) != 0;
         const bool pack16 = PACK16 || P.R < (65536 >> UM_QSHIFT);
         const bool subsample = U.preseed != 0;   // set by the host for the pre-seed launch only
-        um_lnf<ALL_SMEM> LT;     // float table, tier 1
+        um_lnf<ALL_SMEM> LT;     // fixed-point table, tier 1
         LT.base = (uint32_t)__shfl_sync(0xffffffffu, (int)smem_u32(lnf_s), 0); LT.smem_bytes = (unsigned)U.lnf_smem << UM_QSHIFT; LT.gmem = P.lnfact;
+        LT.scale = (double)(1 << U.t1q_shift);
+        const float qscale = U.t1q_scale;
         rr_lnf_global LG;        // double table in HBM/L2, tier 2 (rare, evaluated 32 at a time)
         LG.gmem = P.lnfact;
-        const float margin = U.t1_margin;
 
         for (int u = blockIdx.x; u < U.n_units; u += gridDim.x) {
             const um_unit un = U.units[u];
@@ -455,7 +462,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 bool has_counts;
                 // ---- this warp's column groups: sites sub, sub+UM_SUB, ... (slot w <-> site sub + w*UM_SUB), from the
                 // copy of the tile's running maxima the producer has put into shared memory
-                float thr_i = um_thr_hi(row_hi, no_prune);
+                int nq_i = um_nq_hi(row_hi, no_prune, qscale);
                 {
                     const int tb = tix & 1;
                     const um_thr_buf &B = T->thr[tb];
@@ -472,8 +479,8 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const bool ok1 = in1 && jsite0 + t1 < P.N && ((B.cmask[in1 ? t1 : 0] >> b1) & 1) != 0;
                     const uint32_t h0 = in0 ? (uint32_t)(B.best[5 * t0 + b0].z >> 32) : 0u;
                     const uint32_t h1 = in1 ? (uint32_t)(B.best[5 * t1 + b1].z >> 32) : 0u;
-                    if (w0 < UM_WSITES) M.site[w0].mj[b0] = ok0 ? um_thr_hi(h0, no_prune) : -1.0f;   // -1: not admissible (817)
-                    if (has1) M.site[w1].mj[b1] = ok1 ? um_thr_hi(h1, no_prune) : -1.0f;
+                    if (w0 < UM_WSITES) M.site[w0].nq[b0] = ok0 ? um_nq_hi(h0, no_prune, qscale) : RR_T1Q_INADMISSIBLE;   // (817)
+                    if (has1) M.site[w1].nq[b1] = ok1 ? um_nq_hi(h1, no_prune, qscale) : RR_T1Q_INADMISSIBLE;
                     if (lane < UM_WSITES) {
                         const int tl = sub + lane * UM_SUB;
                         M.site[lane].vmask = tl < UM_COL_SITES && jsite0 + tl < P.N ? (int)(B.cmask[tl] & 31u) : 0;
@@ -524,13 +531,13 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     int colsum[5];                                          // gr2 = |Gj & Cii| per column group
                     int cov;
                     bool need[5];
-                    float mjw[5];
+                    int mjw[5];
                     int vmask;
                     {
-                        const float4 m0 = *reinterpret_cast<const float4 *>(&M.site[w].mj[0]);
-                        const float4 m1 = *reinterpret_cast<const float4 *>(&M.site[w].mj[4]);
+                        const int4 m0 = *reinterpret_cast<const int4 *>(&M.site[w].nq[0]);
+                        const int2 m1 = *reinterpret_cast<const int2 *>(&M.site[w].nq[4]);
                         mjw[0] = m0.x; mjw[1] = m0.y; mjw[2] = m0.z; mjw[3] = m0.w; mjw[4] = m1.x;
-                        vmask = __float_as_int(m1.y);
+                        vmask = m1.y;
                     }
                     if (pack16 && (vmask & (vmask - 1)) == 0) {
                         // ---- a site with ONE admissible column group (the deep insertion columns: only their gap group is
@@ -539,16 +546,14 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         if (vmask == 0) continue;                           // warp-uniform: no admissible group, no pair test
                         const int b1 = __ffs(vmask) - 1;                    // warp-uniform
                         const int cb = b1 == 0 ? c[0] : b1 == 1 ? c[1] : b1 == 2 ? c[2] : b1 == 3 ? c[3] : c[4];
-                        const float mj1 = b1 == 0 ? mjw[0] : b1 == 1 ? mjw[1] : b1 == 2 ? mjw[2] : b1 == 3 ? mjw[3] : mjw[4];
+                        const int mj1 = b1 == 0 ? mjw[0] : b1 == 1 ? mjw[1] : b1 == 2 ? mjw[2] : b1 == 3 ? mjw[3] : mjw[4];
                         int cs1;
                         site_sum5_x2(rowsum, cb, base_lane, cov, cs1);
-                        const float lnc3 = pair_site ? (LT((unsigned)cov) - LT((unsigned)rowsum)) - LT((unsigned)(cov - rowsum))
-                                                     : __int_as_float(0xff800000);
+                        const int lnc3 = pair_site ? LT((unsigned)cov) - LT((unsigned)rowsum) - LT((unsigned)(cov - rowsum)) : RR_T1Q_NEVER;
                         float meanfac;
                         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(meanfac) : "f"((float)max(cov, 1)));
                         meanfac *= (float)rowsum;
-                        const bool n1 = rr_tier1_q(LT, (unsigned)cb, (unsigned)rowsum, (unsigned)cs1, (unsigned)cov, fminf(thr_i, mj1), lnc3,
-                                                   meanfac, margin);
+                        const bool n1 = rr_tier1_q(LT, (unsigned)cb, (unsigned)rowsum, (unsigned)cs1, (unsigned)cov, max(nq_i, mj1), lnc3, meanfac);
                         n_pairs += pair_site;
                         if (!__any_sync(0xffffffffu, n1)) continue;
 #pragma unroll
@@ -563,10 +568,8 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             for (int b = 0; b < 5; b++) colsum[b] = site_sum5(c[b], base_lane);
                         }
                         cov = colsum[0] + colsum[1] + colsum[2] + colsum[3] + colsum[4];
-                        // rows without a pair test at this site (filters 802 / 804-810) get ln C = -inf: their bound is -inf,
-                        // below every threshold (0 included), so they never survive tier 1
-                        const float lnc3 = pair_site ? (LT((unsigned)cov) - LT((unsigned)rowsum)) - LT((unsigned)(cov - rowsum))
-                                                     : __int_as_float(0xff800000);
+                        // rows without a pair test at this site (filters 802 / 804-810) never survive tier 1 (RR_T1Q_NEVER)
+                        const int lnc3 = pair_site ? LT((unsigned)cov) - LT((unsigned)rowsum) - LT((unsigned)(cov - rowsum)) : RR_T1Q_NEVER;
                         float meanfac;   // ~ gr1 / cov (only steers where the pmf bound is evaluated; cov = 0 has no pair test)
                         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(meanfac) : "f"((float)max(cov, 1)));
                         meanfac *= (float)rowsum;
@@ -578,7 +581,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                             for (int b = 0; b < 5; b++)
                                 need[b] = rr_tier1_q(LT, (unsigned)c[b], (unsigned)rowsum, (unsigned)colsum[b], (unsigned)cov,
-                                                     fminf(thr_i, mjw[b]), lnc3, meanfac, margin);
+                                                     max(nq_i, mjw[b]), lnc3, meanfac);
                             n_pairs += pair_site ? 5 : 0;
                         } else {
 #pragma unroll
@@ -586,7 +589,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 need[b] = false;
                                 if (vmask & (1 << b)) {  // warp-uniform
                                     need[b] = rr_tier1_q(LT, (unsigned)c[b], (unsigned)rowsum, (unsigned)colsum[b], (unsigned)cov,
-                                                         fminf(thr_i, mjw[b]), lnc3, meanfac, margin);
+                                                         max(nq_i, mjw[b]), lnc3, meanfac);
                                     n_pairs += pair_site;
                                 }
                             }
@@ -598,7 +601,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (int b = 0; b < 5; b++) {
                         // pre-seed pass only: a column seen for the first time (no maximum yet) would make every row
                         // of the tile a candidate at once; one row in eight is enough to seed it
-                        if (subsample) need[b] &= mjw[b] > 0.0f || ((lane + t) & 7) == 0;
+                        if (subsample) need[b] &= mjw[b] < RR_T1Q_SLACK || ((lane + t) & 7) == 0;   // (< SLACK: the group has a maximum)
                         // s at the lower end of the support (s = gr1 + gr2 - cov >= 1): P[X >= s] = 1 and GSL returns
                         // exactly that (its lower-tail sum starts from pdf(s-1) = 0), so the score is 0 and the pair can
                         // change nothing.  Without this test such pairs are candidates for every group whose maximum is
@@ -613,10 +616,10 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         if (c1n >= 32) {
                             rr_drain_tier2(P, LG, q1, c1n, q2, c2n, lane, n_tier2, n_exact, false);
                             // pick up what this and the other warps / CTAs have found meanwhile
-                            if (row_ok) thr_i = rr_thr_f32(rr_best_value(P.best + gi), no_prune);
+                            if (row_ok) nq_i = rr_thr_q(rr_best_value(P.best + gi), no_prune, qscale);
                             for (int e = lane; e < UM_WSITES * 5; e += 32)
-                                if (M.site[e / 5].mj[e % 5] >= 0.0f)   // (admissible implies inside the tile and the MSA)
-                                    M.site[e / 5].mj[e % 5] = rr_thr_f32(rr_best_value(P.best + 5 * (jsite0 + sub + (e / 5) * UM_SUB) + (e % 5)), no_prune);
+                                if (M.site[e / 5].nq[e % 5] != RR_T1Q_INADMISSIBLE)   // (admissible implies inside the tile and the MSA)
+                                    M.site[e / 5].nq[e % 5] = rr_thr_q(rr_best_value(P.best + 5 * (jsite0 + sub + (e / 5) * UM_SUB) + (e % 5)), no_prune, qscale);
                             __syncwarp();
                         }
                     }
@@ -769,10 +772,10 @@ static int um_fill_params(rr_umma_state *S, const rr_scan_params &P, const rr_pl
     U.preseed = 0;
     U.dump = nullptr;
     U.lnf_smem = std::min(std::min(plan.max_cov + 2, P.R + 2), UM_LNF_MAX);
-    smem_bytes = UM_LNF_OFF + (size_t)U.lnf_smem * sizeof(float);
-    // FP32 tier-1 margin: 8 roundings of magnitude <= 2^-24 * ln(maxcov!) each (7 table entries, 6 additions,
-    // generously doubled), in log10 units, plus the 1e-6 of the double-precision version
-    U.t1_margin = (float)(16.0 * 5.9604645e-8 * rr_lnfact((unsigned)std::max(plan.max_cov, 1)) * 0.4342944819 + 2e-6);
+    smem_bytes = UM_LNF_OFF + (size_t)U.lnf_smem * sizeof(int);
+    // fixed-point scale of the tier-1 table (rr_tier1_q): the largest power of two that keeps ln(maxcov!) below 2^30
+    U.t1q_shift = rr_t1q_shift(rr_lnfact((unsigned)std::max(std::min(plan.max_cov + 1, P.R + 1), 1)));
+    U.t1q_scale = std::nextafterf((float)(2.302585092994046 * (double)(1 << U.t1q_shift)), 0.0f);
     all_smem = U.lnf_smem >= plan.max_cov + 1;
     return RR_OK;
 }

@@ -81,6 +81,7 @@ static inline long long __double_as_longlong(double d) { long long x; memcpy(&x,
 static inline double __longlong_as_double(long long x) { double d; memcpy(&d, &x, 8); return d; }
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline int __float2int_rd(float f) { return (int)floorf(f); }
 static inline unsigned __float_as_uint(float f) { unsigned x; memcpy(&x, &f, 4); return x; }
 static inline float emu_log2f(float x) { return log2f(x); }
 #define __log2f emu_log2f             /* glibc declares a __log2f of its own */

@@ -90,16 +90,22 @@ void emu_tiers(const double *lnf, int max_cov, long long n, const uint32_t *quad
     for (int k = 0; k < max_cov + 2; k++) lnf32[k] = (float)lnf[k];
     const float margin = (float)(16.0 * 5.9604645e-8 * lnf[std::max(max_cov, 1)] * 0.4342944819 + 2e-6);   // rr_scan_umma.cu: U.t1_margin
     auto LT = [&](unsigned k) { return lnf32[k]; };
+    const int shift = rr_t1q_shift(lnf[std::max(max_cov + 1, 1)]);
+    std::vector<int> lnfq((size_t)max_cov + 2);
+    for (int k = 0; k < max_cov + 2; k++) lnfq[k] = (int)nearbyint(lnf[k] * (double)(1 << shift));
+    const float qscale = nextafterf((float)(2.302585092994046 * (double)(1 << shift)), 0.0f);
     rr_lnf_global T2{lnf};
     for (long long i = 0; i < n; i++) {
         const unsigned sc = quads[4 * i], gr1 = quads[4 * i + 1], gr2 = quads[4 * i + 2], cov = quads[4 * i + 3];
         const float lnc3 = (LT(cov) - LT(gr1)) - LT(cov - gr1);
         const float meanfac = (1.0f / (float)std::max(cov, 1u)) * (float)gr1;
         keep1[i] = rr_tier1_f32(LT, sc, gr1, gr2, cov, rr_thr_f32(best[i], false), lnc3, meanfac, margin) ? 1 : 0;
-        // the form the tcgen05 kernel uses: counts scaled by 4 (= byte offsets into the float table)
-        auto LTQ = [&](unsigned off) { return lnf32[off >> 2]; };
+        // the form the tcgen05 kernel uses (rr_scan_umma.cu): counts scaled by 4 (= byte offsets into the table), the table in
+        // fixed point with the scale um_fill_params chooses, thresholds as integer limits
+        auto LTQ = [&](unsigned off) { return lnfq[off >> 2]; };
         const float meanfac_q = (1.0f / (float)std::max(4u * cov, 1u)) * (float)(4u * gr1);
-        keepq[i] = rr_tier1_q(LTQ, 4u * sc, 4u * gr1, 4u * gr2, 4u * cov, rr_thr_f32(best[i], false), lnc3, meanfac_q, margin) ? 1 : 0;
+        const int lnc3q = LTQ(4u * cov) - LTQ(4u * gr1) - LTQ(4u * (cov - gr1));
+        keepq[i] = rr_tier1_q(LTQ, 4u * sc, 4u * gr1, 4u * gr2, 4u * cov, rr_thr_q(best[i], false, qscale), lnc3q, meanfac_q) ? 1 : 0;
         keep2[i] = rr_tier2(T2, sc, gr1, gr2, cov, best[i]) ? 1 : 0;
     }
 }
