@@ -267,13 +267,16 @@ int rr_kmeans_top5_host(int anzahl, int scv, const uint64_t *sig, int i, int32_t
 uint64_t rr_kmeans_majority5_host(uint64_t a, uint64_t b, uint64_t c, uint64_t d, uint64_t e);
 
 /* the exact contraction ranges of the scan plan (csrc/rr_plan.h), for tests: rows in rank order with spans
- * start[r]..end[r] (inclusive), ranks [0, class_split) and [class_split, rows) each sorted by start; every site is
- * taken as a row site, ti / tj sites per row / column block, kunit rows per contraction unit.  A row of class c can
+ * start[r]..end[r] (inclusive); class c = ranks [class_start[c], class_start[c + 1]), each class sorted by start; every site
+ * is taken as a row site, ti / tj sites per row / column block, kunit rows per contraction unit.  A row of class c can
  * only contribute to (row block rb, column block cb) if its rank lies in
- * [k_lo[c * n_colblocks + cb] * kunit, k_hi[c * n_rowblocks + rb] * kunit).  k_lo: [2 * ceil(cols / tj)],
- * k_hi: [2 * n_rowblocks] with n_rowblocks = ceil(max(cols - 20, 0) / ti) returned through *n_rowblocks. */
-int rr_contraction_ranges(const int32_t *start, const int32_t *end, int rows, int cols, int class_split, int ti, int tj,
-                          int kunit, int32_t *k_lo, int32_t *k_hi, int *n_rowblocks);
+ * [k_lo[c * n_colblocks + cb] * kunit, k_hi[c * n_rowblocks + rb] * kunit).  k_lo: [n_classes * ceil(cols / tj)],
+ * k_hi: [n_classes * n_rowblocks] with n_rowblocks = ceil(max(cols - 20, 0) / ti) returned through *n_rowblocks. */
+int rr_contraction_ranges(const int32_t *start, const int32_t *end, int rows, int cols, int n_classes, const int32_t *class_start,
+                          int ti, int tj, int kunit, int32_t *k_lo, int32_t *k_hi, int *n_rowblocks);
+/* the length classes rr_pack sorts the rows into (rows sorted by span length, cut at fixed fractions rounded down to whole
+ * 256-row blocks; one class below 1024 rows): returns the number of classes, class_start[that + 1] (room for 9) */
+int rr_length_classes(int rows, int32_t *class_start);
 
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* CUDA events on the stream every kernel of this handle is launched on */

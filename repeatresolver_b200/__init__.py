@@ -9,7 +9,7 @@ from .maxcorr import (MSA, Packed, RRError, Einlesen, Parallel_AllMaxCorrsRechne
                       MaxCorrelation, Cliquer, Group_Refinement_Cliques, Relative_Vars, Kmeans, kmeans_signatures, kmeans_top5_host, kmeans_majority5_host, kmeans_finish,
                       relative_score_host,
                       relative_vars_from_counts, device_count, variant_available, launch_count, lnfact_table, score_host, score_bound_host,
-                      below_median_host, breakcols_from_spans, contraction_ranges, cliquer_from_counts, cliquer_from_hits, HIT_DTYPE, group_score_host, VARIANTS, VARIANT_NAMES,
+                      below_median_host, breakcols_from_spans, contraction_ranges, length_classes, rank_rows, cliquer_from_counts, cliquer_from_hits, HIT_DTYPE, group_score_host, VARIANTS, VARIANT_NAMES,
                       FLAG_NO_PRUNE, FLAG_HOST_FINALIZE, FLAG_GENERAL_BREAK, FLAG_SEED_ONLY, FLAG_SKIP_SEED)
 from .msagen import MsaGen
 from . import debug
@@ -18,5 +18,5 @@ __all__ = ["MSA", "Packed", "RRError", "Einlesen", "Parallel_AllMaxCorrsRechner"
            "MaxCorrelation", "Cliquer", "Group_Refinement_Cliques", "Relative_Vars", "Kmeans", "kmeans_signatures", "kmeans_top5_host", "kmeans_majority5_host", "kmeans_finish",
            "relative_score_host",
            "relative_vars_from_counts", "device_count", "variant_available", "launch_count", "lnfact_table", "score_host", "score_bound_host",
-           "below_median_host", "breakcols_from_spans", "contraction_ranges", "cliquer_from_counts", "cliquer_from_hits", "HIT_DTYPE", "group_score_host", "MsaGen", "debug", "VARIANTS", "VARIANT_NAMES",
+           "below_median_host", "breakcols_from_spans", "contraction_ranges", "length_classes", "rank_rows", "cliquer_from_counts", "cliquer_from_hits", "HIT_DTYPE", "group_score_host", "MsaGen", "debug", "VARIANTS", "VARIANT_NAMES",
            "FLAG_NO_PRUNE", "FLAG_HOST_FINALIZE", "FLAG_GENERAL_BREAK", "FLAG_SEED_ONLY", "FLAG_SKIP_SEED"]

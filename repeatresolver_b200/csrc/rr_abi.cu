@@ -124,17 +124,36 @@ void rr_dev_free(void *p)
     if (p) cudaFreeAsync(p, g_alloc_stream);
 }
 
-extern "C" int rr_contraction_ranges(const int32_t *start, const int32_t *end, int rows, int cols, int class_split,
-                                     int ti, int tj, int kunit, int32_t *k_lo, int32_t *k_hi, int *n_rowblocks)
+// The length classes of the row order (rr_plan.h): rows sorted by span length are cut at fixed fractions, rounded down to
+// whole 256-row K blocks; below 1024 rows everything is one class (the last).  class_start[RR_LENGTH_CLASSES + 1].
+static const double RR_CLASS_FRACTION[RR_LENGTH_CLASSES] = RR_LENGTH_CLASS_FRACTIONS;
+extern "C" int rr_length_classes(int rows, int32_t *class_start)
 {
-    if (rows < 0 || cols < 0 || ti < 1 || tj < 1 || kunit < 1 || !k_lo || !k_hi || !n_rowblocks || (rows && (!start || !end))) {
+    if (rows < 0 || !class_start) { rr_set_error("rr_length_classes: bad arguments"); return -1; }
+    class_start[0] = 0;
+    double f = 0.0;
+    for (int c = 1; c < RR_LENGTH_CLASSES; c++) {
+        f += RR_CLASS_FRACTION[c - 1];
+        class_start[c] = rows >= 1024 ? (int)((int64_t)((double)rows * f) / 256 * 256) : 0;
+        if (class_start[c] < class_start[c - 1]) class_start[c] = class_start[c - 1];
+    }
+    class_start[RR_LENGTH_CLASSES] = rows;
+    return RR_LENGTH_CLASSES;
+}
+
+extern "C" int rr_contraction_ranges(const int32_t *start, const int32_t *end, int rows, int cols, int n_classes,
+                                     const int32_t *class_start, int ti, int tj, int kunit, int32_t *k_lo, int32_t *k_hi,
+                                     int *n_rowblocks)
+{
+    if (rows < 0 || cols < 0 || ti < 1 || tj < 1 || kunit < 1 || n_classes < 1 || n_classes > RR_MAX_CLASSES || !class_start ||
+        !k_lo || !k_hi || !n_rowblocks || (rows && (!start || !end))) {
         rr_set_error("rr_contraction_ranges: bad arguments");
         return RR_E_ARG;
     }
     const int ncb = std::max((cols + tj - 1) / tj, 1);
     if (rows < 4) {   // too few rows for an admissible group (size < R): no row site, nothing contributes
-        std::fill(k_lo, k_lo + 2 * ncb, 0);
-        k_hi[0] = k_hi[1] = 0;
+        std::fill(k_lo, k_lo + (size_t)n_classes * ncb, 0);
+        std::fill(k_hi, k_hi + n_classes, 0);
         *n_rowblocks = 0;
         return RR_OK;
     }
@@ -143,9 +162,9 @@ extern "C" int rr_contraction_ranges(const int32_t *start, const int32_t *end, i
     std::vector<int32_t> gsize((size_t)5 * cols), coverage(cols, 20), breakcol(cols, cols);
     for (size_t g = 0; g < gsize.size(); g++) gsize[g] = (g % 5 < 4) ? 3 : 2;   // mincov/4 < size < rows; 4 x 3 bases > 20 / 2
     rr_plan plan;
-    rr_plan_build(plan, rows, cols, mincov, gsize.data(), coverage.data(), breakcol.data(), start, end,
-                  class_split, ti, tj, kunit, 1, 0, 0, 1);
-    if ((int)plan.k_lo.size() != 2 * std::max(plan.n_colblocks, 1) || (int)plan.k_hi.size() != 2 * std::max(plan.n_rowblocks, 1)) {
+    rr_plan_build(plan, rows, cols, mincov, gsize.data(), coverage.data(), breakcol.data(), start, end, class_start, n_classes,
+                  ti, tj, kunit, 1, 0, 0, 1);
+    if ((int)plan.k_lo.size() != n_classes * std::max(plan.n_colblocks, 1) || (int)plan.k_hi.size() != n_classes * std::max(plan.n_rowblocks, 1)) {
         rr_set_error("rr_contraction_ranges: unexpected plan shape");
         return RR_E_ARG;
     }
@@ -236,7 +255,8 @@ struct rr_packed {
     unsigned long long *d_counters = nullptr;
     std::vector<int32_t> h_start, h_end;  // spans in rank order: (length class, span start, span end)
     std::vector<int32_t> h_perm;          // rank -> row of the MSA
-    int class_split = 0;                  // ranks [0, class_split) = the short rows
+    int32_t class_start[RR_MAX_CLASSES + 1] = {0};   // rank boundaries of the length classes (rr_length_classes)
+    int n_classes = 1;
     std::vector<int32_t> h_gsize, h_coverage;
     bool contiguous = true;
     float h2d_ms = 0.f, pack_ms = 0.f;
@@ -443,19 +463,20 @@ static int pack_phase_b(rr_packed *pk, const int32_t *sst, const int32_t *sen, c
     const int R = pk->R, N = pk->N;
     std::vector<int32_t> perm(R);
     std::iota(perm.begin(), perm.end(), 0);
-    // Row order = (length class, span start, span end).  The class of the "short" rows is the 3/4 of the rows with
-    // the shortest spans, rounded down to whole 256-row K blocks (none below 1024 rows): see rr_plan.cpp for why the
-    // very long rows are kept apart.  Any order gives the same counts; this one gives the tightest K ranges.
-    std::vector<uint8_t> cls(std::max(R, 1), 1);
-    pk->class_split = R >= 1024 ? (int)((int64_t)R * 3 / 4 / 256 * 256) : 0;
-    if (pk->class_split > 0) {
+    // Row order = (length class, span start, span end).  The classes cut the rows sorted by span length at fixed
+    // fractions, rounded down to whole 256-row K blocks (one class below 1024 rows): see rr_plan.cpp for why rows of
+    // different lengths are kept apart.  Any order gives the same counts; this one gives tight K ranges.
+    std::vector<uint8_t> cls(std::max(R, 1), 0);
+    pk->n_classes = rr_length_classes(R, pk->class_start);
+    {
         std::vector<int32_t> by_len(perm);
         std::stable_sort(by_len.begin(), by_len.end(), [&](int32_t a, int32_t b) {
             const int la = sen[a] - sst[a], lb = sen[b] - sst[b];
             if (la != lb) return la < lb;
             return sst[a] < sst[b];
         });
-        for (int k = 0; k < pk->class_split; k++) cls[by_len[k]] = 0;
+        for (int c = 0; c < pk->n_classes; c++)
+            for (int k = pk->class_start[c]; k < pk->class_start[c + 1]; k++) cls[by_len[k]] = (uint8_t)c;
     }
     std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) {
         if (cls[a] != cls[b]) return cls[a] < cls[b];
@@ -1396,7 +1417,7 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
         const int tj = variant == RR_VARIANT_BITSET ? rr_bitset_tj() : rr_umma_col_sites();
         rr_plan_build(C.plan, R, N, mincov, pk->h_gsize.data(), pk->h_coverage.data(), breakcol.data(),
                       pk->contiguous && !general ? pk->h_start.data() : nullptr,
-                      pk->contiguous && !general ? pk->h_end.data() : nullptr, pk->class_split, ti, tj, variant == RR_VARIANT_BITSET ? 32 : rr_umma_kblock(umma_mode),
+                      pk->contiguous && !general ? pk->h_end.data() : nullptr, pk->class_start, pk->n_classes, ti, tj, variant == RR_VARIANT_BITSET ? 32 : rr_umma_kblock(umma_mode),
                       // epilogue of a tile in K-block equivalents / overlap: 8.3e-5 ms per tile against 3.4e-6 (mxf4),
                       // 2.4e-6 (e2m1) and 4.2e-6 ms (int8) per K block, measured part by part at config 2
                       variant == RR_VARIANT_BITSET ? 8 : umma_mode == 2 ? 25 : umma_mode == 1 ? 34 : 20,
@@ -1432,6 +1453,7 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
     P.unit_prefix = sb.unit_prefix; P.unit_cb0 = sb.unit_cb0; P.n_rowblocks = plan.n_rowblocks;
     P.rb_lo = plan.rb_lo; P.rb_hi = plan.rb_hi; P.word_hi = sb.word_hi; P.word_lo = sb.word_lo;
     P.n_colblocks = plan.n_colblocks;
+    P.n_classes = plan.n_classes;
 
     RR_CUDA(cudaEventRecord(e1, pk->st));
     int64_t executed = 0;
@@ -1598,7 +1620,7 @@ extern "C" int rr_debug_umma_counts(rr_packed *pk, const rr_scan_opts *opts, int
     P.bits = pk->d_bits; P.gsize = pk->d_gsize; P.rowok = sb.rowok; P.colok = sb.colok;
     P.breakcol = sb.breakcol; P.rowsites = sb.rowsites; P.n_rowsites = C.plan.n_rowsites;
     P.lnfact = pk->d_lnfact; P.best = pk->d_best; P.counters = d_cnt;
-    P.n_rowblocks = C.plan.n_rowblocks; P.n_colblocks = C.plan.n_colblocks;
+    P.n_rowblocks = C.plan.n_rowblocks; P.n_colblocks = C.plan.n_colblocks; P.n_classes = C.plan.n_classes;
     if ((rc = rr_umma_dump_tile(pk->umma, mode, C.plan_id, P, C.plan, row_tile, col_tile, d_out, pk->n_sm, pk->st))) return rc;
     RR_CUDA(cudaMemcpyAsync(counts, d_out, sizeof(int32_t) * (size_t)M * NC, cudaMemcpyDeviceToHost, pk->st));
     RR_CUDA(cudaStreamSynchronize(pk->st));

@@ -39,9 +39,10 @@ struct rr_scan_params {
     const int32_t *unit_cb0;     // [n_rowblocks] first column block of each row block
     int n_rowblocks;
     int rb_lo, rb_hi;            // this part's row blocks
-    const int32_t *word_hi;      // [2][n_rowblocks] exclusive upper u32-word bound of contributing rows, per length
-    const int32_t *word_lo;      // [2][n_colblocks] inclusive lower u32-word bound               class (rr_plan.h)
+    const int32_t *word_hi;      // [n_classes][n_rowblocks] exclusive upper u32-word bound of contributing rows, per
+    const int32_t *word_lo;      // [n_classes][n_colblocks] inclusive lower u32-word bound      length class (rr_plan.h)
     int n_colblocks;
+    int n_classes;
 };
 
 #ifndef RR_CPU_EMU

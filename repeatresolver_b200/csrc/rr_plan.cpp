@@ -4,8 +4,8 @@
 #include "rr_plan.h"
 
 void rr_plan_build(rr_plan &plan, int R, int N, int mincov, const int32_t *gsize, const int32_t *coverage,
-                   const int32_t *breakcol, const int32_t *start, const int32_t *end, int class_split, int ti, int tj, int kunit,
-                   int tile_cost, int overlap_pct, int part_index, int part_count)
+                   const int32_t *breakcol, const int32_t *start, const int32_t *end, const int32_t *class_start, int n_classes,
+                   int ti, int tj, int kunit, int tile_cost, int overlap_pct, int part_index, int part_count)
 {
     const int q = mincov / 4;  // integer division, MaxCorrelation.c:802/817
     const size_t G = (size_t)5 * N;
@@ -35,19 +35,26 @@ void rr_plan_build(rr_plan &plan, int R, int N, int mincov, const int32_t *gsize
     plan.n_colblocks = (N + tj - 1) / tj;
     plan.rowsites.resize((size_t)std::max(plan.n_rowblocks, 1) * ti, -1);
 
-    // contraction range bounds from the row order.  Rows come in two length classes, each sorted by span start: in a
-    // class whose longest row spans L columns the rows that can reach a column block start at most L before it, so
-    // keeping the few very long rows (an MSA of long reads always has rows spanning most of it) out of the class of
-    // the short ones keeps the ranges of the short ones tight.  At config 2 this takes 43 % off the K blocks.
+    // contraction range bounds from the row order.  Rows come in length classes, each sorted by span start: in a class
+    // whose longest row spans L columns the rows that can reach a column block start at most L before it, so keeping the
+    // long rows (an MSA of long reads always has rows spanning most of it) out of the classes of the short ones keeps the
+    // ranges of the short ones tight.
     const int kunits_all = (R + kunit - 1) / kunit;
     const int nrb = std::max(plan.n_rowblocks, 1), ncb_all = std::max(plan.n_colblocks, 1);
-    plan.k_lo.assign((size_t)2 * ncb_all, 0);
-    plan.k_hi.assign((size_t)2 * nrb, 0);
-    const int split = (start && end) ? std::min(std::max(class_split, 0), R) : 0;
-    const int cls_r0[2] = {0, split}, cls_r1[2] = {split, R};
-    if (start && end) {
+    const bool spans = start && end;
+    const int ncls = spans ? std::min(std::max(n_classes, 1), RR_MAX_CLASSES) : 1;
+    plan.n_classes = ncls;
+    plan.k_lo.assign((size_t)ncls * ncb_all, 0);
+    plan.k_hi.assign((size_t)ncls * nrb, 0);
+    std::vector<int> cls_r0(ncls, 0), cls_r1(ncls, R);
+    if (spans)
+        for (int c = 0; c < ncls; c++) {
+            cls_r0[c] = std::min(std::max(class_start ? class_start[c] : 0, 0), R);
+            cls_r1[c] = std::min(std::max(class_start ? class_start[c + 1] : R, cls_r0[c]), R);
+        }
+    if (spans) {
         std::vector<int32_t> minrank_end_ge((size_t)N + 1);
-        for (int c = 0; c < 2; c++) {
+        for (int c = 0; c < ncls; c++) {
             const int r0 = cls_r0[c], r1 = cls_r1[c];
             std::fill(minrank_end_ge.begin(), minrank_end_ge.end(), r1);   // none: the empty range at the class's end
             int maxend = -1;
@@ -87,14 +94,14 @@ void rr_plan_build(rr_plan &plan, int R, int N, int mincov, const int32_t *gsize
         plan.unit_prefix[rb + 1] = plan.unit_prefix[rb] + std::max(0, cb1 - cb0);
         plan.rb_pairs[rb] = pairs;
         plan.total_pairs += pairs;
-        if (start && end) {
-            for (int c = 0; c < 2; c++) {
+        if (spans) {
+            for (int c = 0; c < ncls; c++) {
                 const int r0 = cls_r0[c], r1 = cls_r1[c];
                 const int p = (int)(std::upper_bound(start + r0, start + r1, ii_max) - start);   // ranks [r0, p) start <= ii_max
                 plan.k_hi[(size_t)c * nrb + rb] = p > r0 ? (p + kunit - 1) / kunit : r0 / kunit;
             }
         } else {
-            plan.k_hi[(size_t)nrb + rb] = kunits_all;   // no skipping: everything as one class-1 range from k-unit 0
+            plan.k_hi[rb] = kunits_all;   // no skipping: everything as one range from k-unit 0
         }
     }
 

@@ -14,15 +14,20 @@ struct rr_plan {
     int n_rowsites = 0, n_rowblocks = 0, n_colblocks = 0;
     std::vector<int64_t> unit_prefix;   // [n_rowblocks+1] prefix sum of column blocks per row block
     std::vector<int32_t> unit_cb0;      // [n_rowblocks] first column block
-    // contraction ranges, one per LENGTH CLASS of rows (c = 0: ranks [0, class_split), c = 1: the rest; each class
-    // sorted by span start): the k-units of class c that can contribute to (row block rb, column block cb) are
-    // [k_lo[c * n_colblocks + cb], k_hi[c * n_rowblocks + rb]) - empty when lo >= hi
-    std::vector<int32_t> k_hi;          // [2][n_rowblocks] exclusive upper bound of contributing k-units
-    std::vector<int32_t> k_lo;          // [2][n_colblocks] inclusive lower bound
+    // contraction ranges, one per LENGTH CLASS of rows (class c = ranks [class_start[c], class_start[c + 1]), each class
+    // sorted by span start; boundaries are multiples of 256 rows): the k-units of class c that can contribute to (row block
+    // rb, column block cb) are [k_lo[c * n_colblocks + cb], k_hi[c * n_rowblocks + rb]) - empty when lo >= hi
+    int n_classes = 1;
+    std::vector<int32_t> k_hi;          // [n_classes][n_rowblocks] exclusive upper bound of contributing k-units
+    std::vector<int32_t> k_lo;          // [n_classes][n_colblocks] inclusive lower bound
     int kunits(int rb, int cb) const
     {
-        const int a = k_hi[rb] - k_lo[cb], b = k_hi[(size_t)std::max(n_rowblocks, 1) + rb] - k_lo[(size_t)std::max(n_colblocks, 1) + cb];
-        return (a > 0 ? a : 0) + (b > 0 ? b : 0);
+        int sum = 0;
+        for (int c = 0; c < n_classes; c++) {
+            const int a = k_hi[(size_t)c * std::max(n_rowblocks, 1) + rb] - k_lo[(size_t)c * std::max(n_colblocks, 1) + cb];
+            sum += a > 0 ? a : 0;
+        }
+        return sum;
     }
     std::vector<int64_t> rb_pairs;      // [n_rowblocks] pair tests per row block
     int rb_lo = 0, rb_hi = 0;           // this part's row blocks
@@ -37,11 +42,15 @@ struct rr_plan {
 // (32 = one u32 word for the bitset kernel, the K block for the tcgen05 kernel); tile_cost: cost of a tile's
 // epilogue in k-unit equivalents, overlap_pct: how much of the smaller of (epilogue, contraction) hides behind the
 // larger one, 0 = none (multi-GPU balance).
-// start/end: spans in rank order, or NULL when rows are not single spans (no skipping); class_split: ranks
-// [0, class_split) are the short rows, the rest the long ones, each class sorted by span start (a multiple of 256).
+// start/end: spans in rank order, or NULL when rows are not single spans (no skipping: one class over all rows);
+// class_start[n_classes + 1]: rank boundaries of the length classes (rr_length_classes), each class sorted by span start.
+constexpr int RR_MAX_CLASSES = 8;
+// the rule rr_pack applies (rr_length_classes): the rows sorted by span length are cut at these cumulative fractions
+#define RR_LENGTH_CLASSES 2
+#define RR_LENGTH_CLASS_FRACTIONS {0.75, 0.25}
 void rr_plan_build(rr_plan &plan, int R, int N, int mincov, const int32_t *gsize, const int32_t *coverage,
-                   const int32_t *breakcol, const int32_t *start, const int32_t *end, int class_split, int ti, int tj, int kunit,
-                   int tile_cost, int overlap_pct, int part_index, int part_count);
+                   const int32_t *breakcol, const int32_t *start, const int32_t *end, const int32_t *class_start, int n_classes,
+                   int ti, int tj, int kunit, int tile_cost, int overlap_pct, int part_index, int part_count);
 
 // ---- tcgen05 variant hooks (rr_scan_umma.cu) ---------------------------------------------
 struct rr_umma_state;

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(BS_TI * 32, 2) rr_k_scan_bitset(const rr_scan_
 #pragma unroll
             for (int b = 0; b < 5; b++) c[a][b] = 0;
 
-        for (int seg = 0; seg < 2; seg++) {   // the two length classes of rows (rr_plan.h)
+        for (int seg = 0; seg < P.n_classes; seg++) {   // the length classes of rows (rr_plan.h)
         const int w_lo = P.word_lo[seg * max(P.n_colblocks, 1) + cb], w_hi = P.word_hi[seg * max(P.n_rowblocks, 1) + rb];
         for (int w0 = w_lo; w0 < w_hi; w0 += BS_CH) {
             __syncthreads();

@@ -106,8 +106,9 @@ struct um_params {
     rr_scan_params P;
     const um_unit *units;
     int n_units;
-    const int32_t *k_hi;      // [2][n_rt] exclusive K-block bound per length class of rows (rr_plan.h) and row tile
-    const int32_t *k_lo;      // [2][n_ct] inclusive K-block bound per class and column tile
+    const int32_t *k_hi;      // [n_cls][n_rt] exclusive K-block bound per length class of rows (rr_plan.h) and row tile
+    const int32_t *k_lo;      // [n_cls][n_ct] inclusive K-block bound per class and column tile
+    int n_cls;
     int n_rt, n_ct;
     const uint8_t *colmask;   // [n_ct * 48 (+ padding)] per column site: bit b = group b admissible as a column group
     int lnf_smem;             // ln(n!) entries (fixed point, rr_tier1_q) staged in shared memory
@@ -352,20 +353,21 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint32_t it = 0, tix = 0;
             for (int u = blockIdx.x; u < U.n_units; u += gridDim.x) {
                 const um_unit un = U.units[u];
-                const int khi[2] = {U.k_hi[un.rt], U.k_hi[U.n_rt + un.rt]};
                 for (int ct = un.ct0; ct < un.ct1; ct++, tix++) {
                     {   // the tile's running maxima and admissibility masks, one tile ahead of the epilogue at least
                         const int tb = tix & 1;
                         mbar_wait_sleep(&T->bempty[tb], ((tix >> 1) & 1) ^ 1, 64);
                         const int ng = min(UM_N, 5 * U.P.N - ct * UM_N);
                         // plain store, ordered before the waiters' reads by the release of the arrive below
-                        T->thr[tb].has_counts = (U.k_lo[ct] < khi[0] || U.k_lo[U.n_ct + ct] < khi[1]) ? 1 : 0;
+                        int any = 0;
+                        for (int seg = 0; seg < U.n_cls; seg++) any |= U.k_lo[seg * U.n_ct + ct] < U.k_hi[seg * U.n_rt + un.rt];
+                        T->thr[tb].has_counts = any;
                         mbar_expect_tx(&T->bfull[tb], (uint32_t)(ng * sizeof(rr_best_t) + UM_CMASK_BYTES));
                         bulk_load(&T->thr[tb].best[0], U.P.best + (size_t)ct * UM_N, (uint32_t)(ng * sizeof(rr_best_t)), &T->bfull[tb]);
                         bulk_load(&T->thr[tb].cmask[0], U.colmask + (size_t)ct * UM_CMASK_BYTES, UM_CMASK_BYTES, &T->bfull[tb]);
                     }
-                    for (int seg = 0; seg < 2; seg++)
-                    for (int kb = U.k_lo[seg * U.n_ct + ct]; kb < khi[seg]; kb++, it++) {
+                    for (int seg = 0; seg < U.n_cls; seg++)
+                    for (int kb = U.k_lo[seg * U.n_ct + ct], ke = U.k_hi[seg * U.n_rt + un.rt]; kb < ke; kb++, it++) {
                         const int s = it % UM_STAGES;
                         const uint32_t ph = (it / UM_STAGES) & 1;
                         mbar_wait_sleep(&T->empty[s], ph ^ 1, 64);
@@ -386,19 +388,18 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint32_t it = 0, tile = 0;
             for (int u = blockIdx.x; u < U.n_units; u += gridDim.x) {
                 const um_unit un = U.units[u];
-                const int khi[2] = {U.k_hi[un.rt], U.k_hi[U.n_rt + un.rt]};
                 for (int ct = un.ct0; ct < un.ct1; ct++) {
-                    const int klo[2] = {U.k_lo[ct], U.k_lo[U.n_ct + ct]};
-                    // no read covers both tiles: the epilogue uses zeros
-                    if (klo[0] >= khi[0] && klo[1] >= khi[1]) continue;
+                    int any = 0;
+                    for (int seg = 0; seg < U.n_cls; seg++) any |= U.k_lo[seg * U.n_ct + ct] < U.k_hi[seg * U.n_rt + un.rt];
+                    if (!any) continue;   // no read covers both tiles: the epilogue uses zeros
                     const int acc = tile & 1;
                     const uint32_t aph = (tile >> 1) & 1;
                     mbar_wait_sleep(&T->tempty[acc], aph ^ 1, 128);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(acc * UM_ACC_STRIDE);
                     uint32_t accumulate = 0;   // the first MMA of a tile overwrites the accumulator
-                    for (int seg = 0; seg < 2; seg++)
-                    for (int kb = klo[seg]; kb < khi[seg]; kb++, it++) {
+                    for (int seg = 0; seg < U.n_cls; seg++)
+                    for (int kb = U.k_lo[seg * U.n_ct + ct], ke = U.k_hi[seg * U.n_rt + un.rt]; kb < ke; kb++, it++) {
                         const int s = it % UM_STAGES;
                         const uint32_t ph = (it / UM_STAGES) & 1;
                         mbar_wait_sleep(&T->full[s], ph, 32);
@@ -768,6 +769,7 @@ static int um_fill_params(rr_umma_state *S, const rr_scan_params &P, const rr_pl
     U.k_lo = S->d_klo;
     U.n_rt = std::max(plan.n_rowblocks, 1);
     U.n_ct = std::max(plan.n_colblocks, 1);
+    U.n_cls = plan.n_classes;
     U.colmask = S->d_colmask;
     U.preseed = 0;
     U.dump = nullptr;

@@ -466,19 +466,45 @@ def cliquer_from_hits(query_groups, hits, gsize, mincov=30, maxclique=30, greedy
     return members, scores, n
 
 
-def contraction_ranges(start, end, cols, class_split, ti, tj, kunit):
-    """k_lo [2][ceil(cols/tj)], k_hi [2][n_rowblocks] of the scan plan for rows given in rank order (test hook)"""
+def length_classes(rows):
+    """rank boundaries [n_classes + 1] of the length classes rr_pack sorts `rows` rows into (rr_length_classes)"""
+    cs = np.zeros(9, dtype=np.int32)
+    n = lib.rr_length_classes(int(rows), cs.ctypes.data)
+    if n < 1:
+        raise RRError(n, "rr_length_classes")
+    return cs[:n + 1].copy()
+
+
+def rank_rows(start, end):
+    """the row order of rr_pack for spans start[r]..end[r]: (length class, span start, span end), classes by span length
+    (ties: start, then original order); returns (perm [rank -> row], class of every rank, class_start)"""
+    start = np.asarray(start, dtype=np.int64)
+    end = np.asarray(end, dtype=np.int64)
+    R = len(start)
+    cs = length_classes(R)
+    by_len = np.lexsort((np.arange(R), start, end - start))
+    cls = np.zeros(R, dtype=np.int64)
+    for c in range(len(cs) - 1):
+        cls[by_len[cs[c]:cs[c + 1]]] = c
+    perm = np.lexsort((np.arange(R), end, start, cls))
+    return perm, cls[perm], cs
+
+
+def contraction_ranges(start, end, cols, class_start, ti, tj, kunit):
+    """k_lo [n_classes][ceil(cols/tj)], k_hi [n_classes][n_rowblocks] of the scan plan for rows given in rank order (test hook)"""
     start = np.ascontiguousarray(start, dtype=np.int32)
     end = np.ascontiguousarray(end, dtype=np.int32)
+    cs = np.ascontiguousarray(class_start, dtype=np.int32)
+    ncls = len(cs) - 1
     ncb = max((cols + tj - 1) // tj, 1)
-    nrb_max = max((max(cols - 20, 0) + ti - 1) // ti, 1)
-    k_lo = np.zeros(2 * ncb, dtype=np.int32)
-    k_hi = np.zeros(2 * nrb_max, dtype=np.int32)
+    nrb_max = max((cols + ti - 1) // ti, 1)
+    k_lo = np.zeros(ncls * ncb, dtype=np.int32)
+    k_hi = np.zeros(ncls * nrb_max, dtype=np.int32)
     nrb = C.c_int(0)
-    _check(lib.rr_contraction_ranges(start.ctypes.data, end.ctypes.data, len(start), cols, class_split, ti, tj, kunit,
+    _check(lib.rr_contraction_ranges(start.ctypes.data, end.ctypes.data, len(start), cols, ncls, cs.ctypes.data, ti, tj, kunit,
                                      k_lo.ctypes.data, k_hi.ctypes.data, C.byref(nrb)), "rr_contraction_ranges")
     n = max(nrb.value, 1)
-    return k_lo.reshape(2, ncb), k_hi[:2 * n].reshape(2, n), nrb.value
+    return k_lo.reshape(ncls, ncb), k_hi[:ncls * n].reshape(ncls, n), nrb.value
 
 
 def breakcols_from_spans(start, end, cols, mincov):

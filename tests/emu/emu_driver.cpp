@@ -145,11 +145,11 @@ void emu_bits_to_operand(const uint32_t *bits, long long nsets, int W32, int8_t 
  * [5N] {value bits, partner}; counters: [8]; returns the plan's pair count (what the device count must equal). */
 long long emu_scan_bitset(int R, int N, int W32, int mincov, unsigned flags, const uint32_t *bits, const int32_t *gsize,
                           const int32_t *coverage, const int32_t *breakcol, const int32_t *start, const int32_t *end,
-                          int class_split, const double *lnfact, rr_best_t *best, unsigned long long *counters, int blocks,
+                          const int32_t *class_start, int n_classes, const double *lnfact, rr_best_t *best, unsigned long long *counters, int blocks,
                           int part_index, int part_count)
 {
     rr_plan plan;
-    rr_plan_build(plan, R, N, mincov, gsize, coverage, breakcol, start, end, class_split, rr_bitset_ti(), rr_bitset_tj(), 32, 8, 0,
+    rr_plan_build(plan, R, N, mincov, gsize, coverage, breakcol, start, end, class_start, n_classes, rr_bitset_ti(), rr_bitset_tj(), 32, 8, 0,
                   part_index, part_count);
     rr_scan_params P;
     memset(&P, 0, sizeof P);
@@ -160,6 +160,7 @@ long long emu_scan_bitset(int R, int N, int W32, int mincov, unsigned flags, con
     P.unit_prefix = plan.unit_prefix.data(); P.unit_cb0 = plan.unit_cb0.data(); P.n_rowblocks = plan.n_rowblocks;
     P.rb_lo = plan.rb_lo; P.rb_hi = plan.rb_hi; P.word_hi = plan.k_hi.data(); P.word_lo = plan.k_lo.data();
     P.n_colblocks = plan.n_colblocks;
+    P.n_classes = plan.n_classes;
     if (plan.rb_hi > plan.rb_lo && plan.unit_prefix[plan.rb_hi] > plan.unit_prefix[plan.rb_lo])
         emu_launch(dim3((unsigned)blocks), BS_TI * 32, [&] { rr_k_scan_bitset(P); });
     return (long long)plan.part_pairs;

@@ -247,7 +247,7 @@ def test_breakcols_from_spans(mincov):
 @pytest.mark.parametrize("seed,kunit,ti,tj", [(1, 256, 24, 48), (2, 128, 24, 48), (3, 32, 8, 32), (4, 256, 24, 48)])
 def test_contraction_ranges_cover_every_contributing_row(seed, kunit, ti, tj):
     """K-range skipping is exact only if every row that covers a site of the row block AND a site of the column block
-    lies inside the two rank ranges the plan keeps (one per length class of rows) - checked exhaustively on random
+    lies inside the rank ranges the plan keeps (one per length class of rows) - checked exhaustively on random
     spans with a few MSA-spanning rows, rows are ordered as rr_pack orders them"""
     rng = np.random.default_rng(seed)
     R, N = (1500, 2600) if seed != 4 else (700, 1900)   # seed 4: below 1024 rows -> a single class
@@ -255,14 +255,16 @@ def test_contraction_ranges_cover_every_contributing_row(seed, kunit, ti, tj):
     ln[rng.integers(0, R, 12)] = N                                        # rows spanning everything
     st = (rng.random(R) * (N - ln + 1)).astype(np.int64)
     en = st + ln - 1
-    split = (R * 3 // 4 // 256 * 256) if R >= 1024 else 0                  # rr_pack's rule
-    by_len = np.lexsort((st, en - st))
-    cls = np.ones(R, dtype=np.int64)
-    cls[by_len[:split]] = 0
-    order = np.lexsort((en, st, cls))
-    st, en, cls = st[order], en[order], cls[order]
-    assert (cls[:split] == 0).all() and (cls[split:] == 1).all()
-    k_lo, k_hi, nrb = rr.contraction_ranges(st, en, N, split, ti, tj, kunit)
+    perm, cls, cs = rr.rank_rows(st, en)                                   # rr_pack's order and classes
+    ncls = len(cs) - 1
+    st, en = st[perm], en[perm]
+    assert cs[0] == 0 and cs[-1] == R and (np.diff(cs) >= 0).all() and (cs[1:-1] % 256 == 0).all()
+    if R < 1024:
+        assert (cs[:-1] == 0).all()                                       # everything in the last class
+    for c in range(ncls):
+        assert (cls[cs[c]:cs[c + 1]] == c).all()
+        assert (np.diff(st[cs[c]:cs[c + 1]]) >= 0).all()                  # each class sorted by span start
+    k_lo, k_hi, nrb = rr.contraction_ranges(st, en, N, cs, ti, tj, kunit)
     assert nrb == (N - 20 + ti - 1) // ti
     rank = np.arange(R)
     checked = 0
@@ -271,13 +273,13 @@ def test_contraction_ranges_cover_every_contributing_row(seed, kunit, ti, tj):
         for cb in range((s_lo + 20) // tj, k_lo.shape[1], 5):
             c_lo = cb * tj
             contributes = (st <= s_hi) & (en >= max(c_lo, s_lo))         # covers some site of both blocks
-            for c in (0, 1):
+            for c in range(ncls):
                 r = rank[contributes & (cls == c)]
                 if len(r):
                     assert k_lo[c, cb] * kunit <= r.min() and r.max() < k_hi[c, rb] * kunit, (rb, cb, c)
                     checked += 1
-            # and the ranges stay inside their class
-            assert k_hi[0, rb] * kunit <= max(split, 0) + kunit - 1 and k_lo[1, cb] * kunit >= split - (split % kunit)
+                # and the ranges stay inside their class (up to the k-unit rounding)
+                assert k_hi[c, rb] * kunit <= cs[c + 1] + kunit - 1 and k_lo[c, cb] * kunit >= cs[c] - (cs[c] % kunit)
     assert checked > 40
 
 

@@ -257,22 +257,17 @@ def test_kmeans_sweeps_on_the_golden_cases(emu, tile_reads):
 
 # ---- the AND+POPC variant of the scan itself (rr_k_scan_bitset with the fused epilogue of rr_device.cuh) ---------------
 def ranked(codes):
-    """rows in the order rr_pack leaves them: (length class, span start, span end); returns codes, start, end, class_split"""
+    """rows in the order rr_pack leaves them: (length class, span start, span end); returns codes, start, end, class_start"""
     R, N = codes.shape
     cov = codes < 5
     start = cov.argmax(1).astype(np.int32)
     end = (N - 1 - cov[:, ::-1].argmax(1)).astype(np.int32)
-    split = (R * 3 // 4 // 256 * 256) if R >= 1024 else 0
-    cls = np.ones(R, dtype=np.int64)
-    if split:
-        by_len = np.lexsort((np.arange(R), start, end - start))          # stable: (length, start, original order)
-        cls[by_len[:split]] = 0
-    perm = np.lexsort((np.arange(R), end, start, cls))
-    return np.ascontiguousarray(codes[perm]), start[perm].copy(), end[perm].copy(), split
+    perm, _, cs = rr.rank_rows(start, end)
+    return np.ascontiguousarray(codes[perm]), start[perm].copy(), end[perm].copy(), np.ascontiguousarray(cs, dtype=np.int32)
 
 
 def run_scan_bitset(emu, codes, mincov, flags=0, blocks=3, part=(0, 1)):
-    rc, start, end, split = ranked(codes)
+    rc, start, end, cs = ranked(codes)
     R, N = rc.shape
     bits, _, W32 = pack_bits(rc)
     gs = np.stack([(rc == k).sum(0) for k in range(5)], 1).reshape(-1).astype(np.int32)
@@ -283,7 +278,7 @@ def run_scan_bitset(emu, codes, mincov, flags=0, blocks=3, part=(0, 1)):
     best["p"] = np.uint64(2 ** 64 - 1)
     counters = np.zeros(8, dtype=np.uint64)
     pairs = emu.emu_scan_bitset(R, N, W32, mincov, flags, bits.ctypes.data, gs.ctypes.data, coverage.ctypes.data, brk.ctypes.data,
-                                start.ctypes.data, end.ctypes.data, split, lnf.ctypes.data, best.ctypes.data, counters.ctypes.data,
+                                start.ctypes.data, end.ctypes.data, cs.ctypes.data, len(cs) - 1, lnf.ctypes.data, best.ctypes.data, counters.ctypes.data,
                                 blocks, part[0], part[1])
     M = best["z"].view(np.float64).copy()
     A = np.where(best["p"] == np.uint64(2 ** 64 - 1), -1, best["p"].astype(np.int64)).astype(np.int32)
@@ -294,7 +289,7 @@ def run_scan_bitset(emu, codes, mincov, flags=0, blocks=3, part=(0, 1)):
 def emu_scan(emu):
     vp, i, u32 = C.c_void_p, C.c_int, C.c_uint
     emu.emu_scan_bitset.restype = C.c_longlong
-    emu.emu_scan_bitset.argtypes = [i, i, i, i, u32, vp, vp, vp, vp, vp, vp, i, vp, vp, vp, i, i, i]
+    emu.emu_scan_bitset.argtypes = [i, i, i, i, u32, vp, vp, vp, vp, vp, vp, vp, i, vp, vp, vp, i, i, i]
     return emu
 
 
@@ -322,11 +317,12 @@ def test_bitset_scan_kernel_on_golden_cases(emu_scan, name, cov, tmp_path):
             assert int(counters[1]) >= int((M0 > 0).sum()) // 2            # exact evaluations happened
 
 
-def test_bitset_scan_kernel_two_length_classes_and_parts(emu_scan):
-    """1 300 reads: two length classes of rows (class split at 768), word ranges per class, and a two-way partition of the
+def test_bitset_scan_kernel_length_classes_and_parts(emu_scan):
+    """1 300 reads: several length classes of rows (boundaries on whole 256-row blocks), word ranges per class, and a two-way partition of the
     row blocks whose element-wise max (ties to the smaller partner) is the full result"""
     codes = two_family_msa(1300, 75, seed=47)
-    assert ranked(codes)[3] == 768
+    cs = ranked(codes)[3]
+    assert len(cs) >= 3 and (cs[1:-1] % 256 == 0).all() and 0 < cs[1] < 1300
     o = O.Oracle.from_codes(codes)
     M0, A0, P0 = o.scan(30)
     assert (M0 > 0).sum() > 50
@@ -383,11 +379,9 @@ def device_pack(e, cells, codes_flag):
     R, N = cells.shape
     start, end, ncov = (np.zeros(R, dtype=np.int32) for _ in range(3))
     e.emu_row_spans(cells.ctypes.data, R, N, codes_flag, start.ctypes.data, end.ctypes.data, ncov.ctypes.data)
-    split = (R * 3 // 4 // 256 * 256) if R >= 1024 else 0
-    cls = np.ones(R, dtype=np.int64)
-    if split:
-        cls[np.lexsort((np.arange(R), start, end - start))[:split]] = 0
-    perm = np.lexsort((np.arange(R), end, start, cls)).astype(np.int32)
+    perm, _, cs = rr.rank_rows(start, end)
+    perm = perm.astype(np.int32)
+    cs = np.ascontiguousarray(cs, dtype=np.int32)
     W32 = 4 * ((R + 127) // 128)
     bits = np.zeros((5 * N, W32), dtype=np.uint32)
     cov = np.zeros((N, W32), dtype=np.uint32)
@@ -408,7 +402,7 @@ def device_pack(e, cells, codes_flag):
     cv = np.zeros(N, dtype=np.int32)
     e.emu_bitset_sizes(bits.ctypes.data, 5 * N, W32, gs.ctypes.data)
     e.emu_bitset_sizes(cov.ctypes.data, N, W32, cv.ctypes.data)
-    return dict(R=R, N=N, W32=W32, start=start, end=end, ncov=ncov, perm=perm, split=split, bits=bits, cov=cov, gs=gs, cv=cv)
+    return dict(R=R, N=N, W32=W32, start=start, end=end, ncov=ncov, perm=perm, cs=cs, bits=bits, cov=cov, gs=gs, cv=cv)
 
 
 def test_packing_kernels_on_raw_text(emu_pack, tmp_path):
@@ -481,7 +475,7 @@ def test_whole_device_pipeline_of_the_bitset_variant(emu_pack, name, cov, tmp_pa
     best["p"] = np.uint64(2 ** 64 - 1)
     counters = np.zeros(8, dtype=np.uint64)
     pairs = emu_pack.emu_scan_bitset(R, N, p["W32"], cov, 0, p["bits"].ctypes.data, p["gs"].ctypes.data, p["cv"].ctypes.data,
-                                     brk.ctypes.data, start.ctypes.data, end.ctypes.data, p["split"], lnf.ctypes.data,
+                                     brk.ctypes.data, start.ctypes.data, end.ctypes.data, p["cs"].ctypes.data, len(p["cs"]) - 1, lnf.ctypes.data,
                                      best.ctypes.data, counters.ctypes.data, 3, 0, 1)
     M = best["z"].view(np.float64)
     M0, A0, P0 = o.scan(cov)
