@@ -22,7 +22,9 @@
 //               masks into a 2-deep shared-memory ring, then per K block the A and B boxes by TMA -> smem stage
 //   warp 1      TMEM allocator + MMA issuer (one elected lane): 4 x tcgen05.mma per stage,
 //               tcgen05.commit frees the stage / publishes the accumulator
-//   warps 2-3   idle (keep the epilogue warps aligned to the TMEM lane quarters); warps 0-3 give their registers
+//   warp 2      per tile: turns the producer's copy of the 240 running maxima and the admissibility masks into the
+//               tier-1 limits every epilogue warp reads (2-deep ring of its own), one tile ahead of the epilogue
+//   warp 3      idle (keeps the epilogue warps aligned to the TMEM lane quarters); warps 0-3 give their registers
 //               to the epilogue (setmaxnreg 32 / 112)
 //   warps 4-19  epilogue, four warps per 32-lane TMEM quarter, each taking every fourth column site:
 //               tcgen05.ld of the site's 5 counts, 5x5 block sums (in-thread row sum, 5-lane shuffle
@@ -70,13 +72,15 @@ constexpr int UM_SF_COL = 240;                   // 16 spare TMEM columns behind
 constexpr int UM_QSHIFT = 2;                     // accumulators hold count << UM_QSHIFT (operand elements are 2); rr_tier1_q assumes 2
 constexpr int UM_CMASK_BYTES = 48;               // admissibility masks of a tile's column sites (one byte per site)
 
-struct __align__(16) um_wsite {                   // one column site: read by the whole warp as two 16-byte broadcasts
+struct __align__(16) um_wsite {                   // one column site: read by the whole warp as two broadcasts (16 + 8 bytes)
     int nq[5];                                    // running maxima as fixed-point tier-1 limits (rr_thr_q); inadmissible: never
-    int vmask;                                    // bit b set: group b of the site is admissible (817)
+    int vmask;                                    // bit b set: group b of the site is admissible (817); 0 outside the MSA
     int pad[2];
 };
-struct um_wmeta {                                 // per epilogue warp: metadata of its column sites in the tile
-    um_wsite site[UM_WSITES];
+struct __align__(16) um_tile_meta {               // per tile, written by the converter warp, read by every epilogue warp
+    um_wsite site[UM_COL_SITES];
+    int32_t has_counts;                           // some read covers both tiles (K blocks were issued)
+    int32_t pad[3];
 };
 struct __align__(16) um_thr_buf {                 // per tile, written by the producer's bulk copies
     rr_best_t best[UM_N];                         // running maxima of the tile's column groups as they are in HBM
@@ -86,11 +90,11 @@ struct __align__(16) um_thr_buf {                 // per tile, written by the pr
 };
 
 struct um_smem_tail {
-    um_wmeta meta[UM_EPI_WARPS];
+    um_tile_meta tmeta[2];
     rr_cand_p q1[UM_EPI_WARPS][RR_QUEUE_CAP];     // tier-1 survivors, one queue per epilogue warp
     rr_cand_p q2[UM_EPI_WARPS][RR_QUEUE_CAP];     // tier-2 survivors (exact evaluation pending)
     um_thr_buf thr[2];
-    unsigned long long full[UM_STAGES], empty[UM_STAGES], tfull[2], tempty[2], bfull[2], bempty[2];
+    unsigned long long full[UM_STAGES], empty[UM_STAGES], tfull[2], tempty[2], bfull[2], bempty[2], mfull[2], mempty[2];
     uint32_t tmem_base;
 };
 
@@ -310,7 +314,8 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int s = 0; s < UM_STAGES; s++) { mbar_init(&T->full[s], 1); mbar_init(&T->empty[s], 1); }
         for (int a = 0; a < 2; a++) {
             mbar_init(&T->tfull[a], 1); mbar_init(&T->tempty[a], UM_EPI_WARPS);
-            mbar_init(&T->bfull[a], 1); mbar_init(&T->bempty[a], UM_EPI_WARPS);
+            mbar_init(&T->bfull[a], 1); mbar_init(&T->bempty[a], 1);
+            mbar_init(&T->mfull[a], 1); mbar_init(&T->mempty[a], UM_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -421,6 +426,37 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
             }
         }
+    } else if (warp == 2) {
+        // ================= tile metadata =================
+        // the tile's running maxima as they were in HBM when the producer copied them (one to two tiles ago: thresholds may
+        // be stale or low, never high) -> fixed-point tier-1 limits, once per tile for all sixteen epilogue warps
+        const bool no_prune = (P.flags & RR_FLAG_NO_PRUNE) != 0;
+        const float qscale = U.t1q_scale;
+        uint32_t tix = 0;
+        for (int u = blockIdx.x; u < U.n_units; u += gridDim.x) {
+            const um_unit un = U.units[u];
+            for (int ct = un.ct0; ct < un.ct1; ct++, tix++) {
+                const int tb = tix & 1;
+                const uint32_t ph = (tix >> 1) & 1;
+                const um_thr_buf &B = T->thr[tb];
+                um_tile_meta &TM = T->tmeta[tb];
+                mbar_wait_sleep(&T->mempty[tb], ph ^ 1, 64);   // the epilogue is done with the tile that used this slot
+                mbar_wait_sleep(&T->bfull[tb], ph, 32);        // the producer's copy has landed
+                __syncwarp();
+                const int n_in = min(UM_COL_SITES, P.N - ct * UM_COL_SITES);   // column sites of the tile inside the MSA
+#pragma unroll 1
+                for (int e = lane; e < UM_N; e += 32) {
+                    const int t = e / 5, b = e - 5 * t;
+                    const bool ok = t < n_in && ((B.cmask[t] >> b) & 1) != 0;                            // (817)
+                    const uint32_t hi = t < n_in ? (uint32_t)(B.best[e].z >> 32) : 0u;
+                    TM.site[t].nq[b] = ok ? um_nq_hi(hi, no_prune, qscale) : RR_T1Q_INADMISSIBLE;
+                }
+                for (int t = lane; t < UM_COL_SITES; t += 32) TM.site[t].vmask = t < n_in ? (int)(B.cmask[t] & 31u) : 0;
+                if (lane == 0) TM.has_counts = B.has_counts;
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&T->mfull[tb]); mbar_arrive(&T->bempty[tb]); }
+            }
+        }
     }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(UM_EPI_REGS));
@@ -436,7 +472,6 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         unsigned n_pairs = 0, n_exact = 0, n_units = 0, n_tier2 = 0;
         uint32_t tile = 0, tix = 0;
         rr_cand_p *q1 = T->q1[ew], *q2 = T->q2[ew];
-        um_wmeta &M = T->meta[ew];
         int c1n = 0, c2n = 0;
         const bool no_prune = (P.flags & RR_FLAG_NO_PRUNE) != 0;
         const bool pack16 = PACK16 || P.R < (65536 >> UM_QSHIFT);
@@ -456,41 +491,20 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int gi = ii >= 0 ? 5 * ii + a : -1;
             const bool row_ok = gi >= 0 && P.rowok[gi] != 0;
             const int brk = ii >= 0 ? min(P.breakcol[ii], P.N) : 0;
+            const int row_lo = row_ok ? ii + 20 : 0x7fffffff;   // first column site this row group is tested against (796)
             uint32_t row_hi = row_ok ? um_best_hi(P.best + gi) : 0u;   // running max of row group i (high word), refreshed per tile
 
             for (int ct = un.ct0; ct < un.ct1; ct++, tix++) {
                 const int jsite0 = ct * UM_COL_SITES;
                 bool has_counts;
-                // ---- this warp's column groups: sites sub, sub+UM_SUB, ... (slot w <-> site sub + w*UM_SUB), from the
-                // copy of the tile's running maxima the producer has put into shared memory
+                // ---- the tile's column groups: tier-1 limits and admissibility masks as the converter warp left them
                 int nq_i = um_nq_hi(row_hi, no_prune, qscale);
-                {
-                    const int tb = tix & 1;
-                    const um_thr_buf &B = T->thr[tb];
-                    mbar_wait(&T->bfull[tb], (tix >> 1) & 1);
-                    __syncwarp();
-                    has_counts = B.has_counts != 0;
-                    static_assert(UM_WSITES * 5 <= 64, "two metadata entries per lane");
-                    const int w0 = lane / 5, b0 = lane - w0 * 5;
-                    const int e1 = lane + 32, w1 = e1 / 5, b1 = e1 - w1 * 5;
-                    const bool has1 = e1 < UM_WSITES * 5;
-                    const int t0 = sub + w0 * UM_SUB, t1 = sub + w1 * UM_SUB;
-                    const bool in0 = w0 < UM_WSITES && t0 < UM_COL_SITES, in1 = has1 && t1 < UM_COL_SITES;
-                    const bool ok0 = in0 && jsite0 + t0 < P.N && ((B.cmask[in0 ? t0 : 0] >> b0) & 1) != 0;
-                    const bool ok1 = in1 && jsite0 + t1 < P.N && ((B.cmask[in1 ? t1 : 0] >> b1) & 1) != 0;
-                    const uint32_t h0 = in0 ? (uint32_t)(B.best[5 * t0 + b0].z >> 32) : 0u;
-                    const uint32_t h1 = in1 ? (uint32_t)(B.best[5 * t1 + b1].z >> 32) : 0u;
-                    if (w0 < UM_WSITES) M.site[w0].nq[b0] = ok0 ? um_nq_hi(h0, no_prune, qscale) : RR_T1Q_INADMISSIBLE;   // (817)
-                    if (has1) M.site[w1].nq[b1] = ok1 ? um_nq_hi(h1, no_prune, qscale) : RR_T1Q_INADMISSIBLE;
-                    if (lane < UM_WSITES) {
-                        const int tl = sub + lane * UM_SUB;
-                        M.site[lane].vmask = tl < UM_COL_SITES && jsite0 + tl < P.N ? (int)(B.cmask[tl] & 31u) : 0;
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&T->bempty[tb]);
-                    // the row group's maximum for the next tile of this unit (consumed at the top of the next iteration)
-                    if (row_ok && ct + 1 < un.ct1) row_hi = um_best_hi(P.best + gi);
-                }
+                const int tb = tix & 1;
+                um_tile_meta &TM = T->tmeta[tb];
+                mbar_wait(&T->mfull[tb], (tix >> 1) & 1);
+                has_counts = TM.has_counts != 0;
+                // the row group's maximum for the next tile of this unit (consumed at the top of the next iteration)
+                if (row_ok && ct + 1 < un.ct1) row_hi = um_best_hi(P.best + gi);
 
                 const int acc = tile & 1;
                 if (has_counts) {
@@ -500,12 +514,15 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int t_end = mma_only ? 0 : min(UM_COL_SITES, P.N - jsite0);
                 if (!has_counts) {
                     // no read covers both tiles: every count is 0, no pair can score, but the pair tests are counted
-                    for (int w = 0, t = sub; t < t_end; w++, t += UM_SUB) {
+#pragma unroll 1
+                    for (int t = sub; t < t_end; t += UM_SUB) {
                         const int jj = jsite0 + t;
-                        if (row_ok && jj >= ii + 20 && jj < brk) n_pairs += __popc(M.site[w].vmask);
+                        if (row_ok && jj >= ii + 20 && jj < brk) n_pairs += __popc(TM.site[t].vmask);
                         if constexpr (DUMP)
                             for (int b = 0; b < 5; b++) U.dump[(size_t)(quarter * 32 + lane) * UM_N + 5 * t + b] = 0;
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&T->mempty[tb]);
                     continue;
                 }
                 // 8 TMEM columns are fetched per site (5 used); the load of the next site is in flight
@@ -513,20 +530,24 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 uint32_t v[8];
                 uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * UM_ACC_STRIDE) + 5 * sub;
                 if (sub < t_end) TMEM_LD_8(v, taddr);
+                // a counted loop over this warp's sites t = sub, sub + UM_SUB, ...: column jj, metadata *sp
+                int jj = jsite0 + sub - UM_SUB;
+                const um_wsite *sp = &TM.site[sub] - UM_SUB;
 #pragma unroll 1
-                for (int w = 0, t = sub; t < t_end; w++, t += UM_SUB) {
+                for (int n_left = t_end > sub ? (t_end - sub + UM_SUB - 1) / UM_SUB : 0; n_left > 0; n_left--) {
                     int c[5];
+                    jj += UM_SUB;
+                    sp += UM_SUB;
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                     for (int b = 0; b < 5; b++) c[b] = MODE != 0 ? (int)__uint_as_float(v[b]) : (int)v[b];
                     taddr += 5 * UM_SUB;
-                    if (t + UM_SUB < t_end) TMEM_LD_8(v, taddr);
+                    if (n_left > 1) TMEM_LD_8(v, taddr);
                     if constexpr (DUMP) {
 #pragma unroll
-                        for (int b = 0; b < 5; b++) U.dump[(size_t)(quarter * 32 + lane) * UM_N + 5 * t + b] = c[b] >> UM_QSHIFT;
+                        for (int b = 0; b < 5; b++) U.dump[(size_t)(quarter * 32 + lane) * UM_N + 5 * (jj - jsite0) + b] = c[b] >> UM_QSHIFT;
                     }
-                    const int jj = jsite0 + t;
-                    const bool pair_site = row_ok && jj >= ii + 20 && jj < brk;
+                    const bool pair_site = jj >= row_lo && jj < brk;   // (row_lo: never for rows that are no row groups)
                     if (!__any_sync(0xffffffffu, pair_site)) continue;
                     const int rowsum = c[0] + c[1] + c[2] + c[3] + c[4];  // gr1 = |Gi & Cjj|
                     int colsum[5];                                          // gr2 = |Gj & Cii| per column group
@@ -535,8 +556,8 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     int mjw[5];
                     int vmask;
                     {
-                        const int4 m0 = *reinterpret_cast<const int4 *>(&M.site[w].nq[0]);
-                        const int2 m1 = *reinterpret_cast<const int2 *>(&M.site[w].nq[4]);
+                        const int4 m0 = *reinterpret_cast<const int4 *>(&sp->nq[0]);
+                        const int2 m1 = *reinterpret_cast<const int2 *>(&sp->nq[4]);
                         mjw[0] = m0.x; mjw[1] = m0.y; mjw[2] = m0.z; mjw[3] = m0.w; mjw[4] = m1.x;
                         vmask = m1.y;
                     }
@@ -602,7 +623,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (int b = 0; b < 5; b++) {
                         // pre-seed pass only: a column seen for the first time (no maximum yet) would make every row
                         // of the tile a candidate at once; one row in eight is enough to seed it
-                        if (subsample) need[b] &= mjw[b] < RR_T1Q_SLACK || ((lane + t) & 7) == 0;   // (< SLACK: the group has a maximum)
+                        if (subsample) need[b] &= mjw[b] < RR_T1Q_SLACK || ((lane + jj) & 7) == 0;   // (< SLACK: the group has a maximum)
                         // s at the lower end of the support (s = gr1 + gr2 - cov >= 1): P[X >= s] = 1 and GSL returns
                         // exactly that (its lower-tail sum starts from pdf(s-1) = 0), so the score is 0 and the pair can
                         // change nothing.  Without this test such pairs are candidates for every group whose maximum is
@@ -618,16 +639,20 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             rr_drain_tier2(P, LG, q1, c1n, q2, c2n, lane, n_tier2, n_exact, false);
                             // pick up what this and the other warps / CTAs have found meanwhile
                             if (row_ok) nq_i = rr_thr_q(rr_best_value(P.best + gi), no_prune, qscale);
-                            for (int e = lane; e < UM_WSITES * 5; e += 32)
-                                if (M.site[e / 5].nq[e % 5] != RR_T1Q_INADMISSIBLE)   // (admissible implies inside the tile and the MSA)
-                                    M.site[e / 5].nq[e % 5] = rr_thr_q(rr_best_value(P.best + 5 * (jsite0 + sub + (e / 5) * UM_SUB) + (e % 5)), no_prune, qscale);
+                            // (the other warps of the same sites may do the same at the same time: every value written is a
+                            // true maximum of its group, and a limit is read whole or not at all)
+                            for (int e = lane; e < UM_WSITES * 5; e += 32) {
+                                const int ts = sub + (e / 5) * UM_SUB;
+                                if (ts < UM_COL_SITES && TM.site[ts].nq[e % 5] != RR_T1Q_INADMISSIBLE)   // (admissible implies inside the MSA)
+                                    TM.site[ts].nq[e % 5] = rr_thr_q(rr_best_value(P.best + 5 * (jsite0 + ts) + (e % 5)), no_prune, qscale);
+                            }
                             __syncwarp();
                         }
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&T->tempty[acc]);
+                if (lane == 0) { mbar_arrive(&T->tempty[acc]); mbar_arrive(&T->mempty[tb]); }
                 tile++;
             }
             rr_drain_tier2(P, LG, q1, c1n, q2, c2n, lane, n_tier2, n_exact, true);
