@@ -1,7 +1,7 @@
 #!/bin/bash
 # Timing experiments on the scan kernel OUTSIDE the product tree: copies the package to exp/pkg_<name>, applies a sed script to
 # the kernel sources there (results become wrong on purpose), builds that copy's librr_maxcorr.so.  Nothing under exp/ is
-# tracked or shipped.  usage: tools/exp_build.sh NAME 'sed-script for rr_scan_umma.cu' ['sed-script for rr_device.cuh' ['sed-script for rr_plan.h']]
+# tracked or shipped.  EXP_EXTRA='-DNAME=value ...' adds compiler flags.  usage: tools/exp_build.sh NAME 'sed-script for rr_scan_umma.cu' ['sed-script for rr_device.cuh' ['sed-script for rr_plan.h']]
 set -e
 NAME=$1
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
@@ -17,5 +17,5 @@ sed -i 's#"../../include/#"'"$D"'/include/#' *.cu *.h *.cuh *.c *.cpp 2>/dev/nul
 [ -n "${4:-}" ] && sed -i "$4" rr_plan.h
 # experiments change the pair counts: no count check
 sed -i 's#if ((int64_t)counters\[0\] != plan.part_pairs#if (false \&\& (int64_t)counters[0] != plan.part_pairs#' rr_abi.cu
-make -j8 ../librr_maxcorr.so > /dev/null 2>&1 || { echo "build failed: $NAME"; make ../librr_maxcorr.so 2>&1 | tail -20; exit 1; }
+make -j8 EXTRA="${EXP_EXTRA:-}" ../librr_maxcorr.so > /dev/null 2>&1 || { echo "build failed: $NAME"; make EXTRA="${EXP_EXTRA:-}" ../librr_maxcorr.so 2>&1 | tail -20; exit 1; }
 echo "built $D"
