@@ -35,6 +35,10 @@ int rr_debug_umma_counts(rr_packed *pk, const rr_scan_opts *opts, int row_tile, 
  * of one launch, *best_ms = fastest of reps launches (CUDA events); peak = 2 * macs / best_ms.  bench.py reports the
  * scan's executed MACs against this. */
 int rr_debug_mma_peak(int device, int variant, int kblocks_per_sm, int reps, float *best_ms, double *macs);
+/* the same loop for other issue forms: cta_group 1 (M = 128, n_cols = 240) or cta_group 2 (a CTA pair, M = 256, n_cols a
+ * multiple of 16 in 32..256, each CTA holding half of the B tile) */
+int rr_debug_mma_peak_shape(int device, int variant, int cta_group, int n_cols, int kblocks_per_sm, int reps, float *best_ms,
+                            double *macs);
 
 #ifdef __cplusplus
 }

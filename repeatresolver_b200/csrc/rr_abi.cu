@@ -1639,9 +1639,19 @@ extern "C" int rr_debug_umma_counts(rr_packed *pk, const rr_scan_opts *opts, int
 }
 
 // measurement hook (include/rr_debug.h): bare tcgen05.mma loop of the scan's MMA kind on every SM, best of `reps`
+extern "C" int rr_debug_mma_peak_shape(int device, int variant, int cta_group, int n_cols, int kblocks_per_sm, int reps, float *best_ms, double *macs);
 extern "C" int rr_debug_mma_peak(int device, int variant, int kblocks_per_sm, int reps, float *best_ms, double *macs)
 {
+    return rr_debug_mma_peak_shape(device, variant, 1, 240, kblocks_per_sm, reps, best_ms, macs);
+}
+
+extern "C" int rr_debug_mma_peak_shape(int device, int variant, int cta_group, int n_cols, int kblocks_per_sm, int reps, float *best_ms, double *macs)
+{
     if (!best_ms || !macs || reps < 1 || kblocks_per_sm < 1) { rr_set_error("rr_debug_mma_peak: bad arguments"); return RR_E_ARG; }
+    if (!(cta_group == 1 && n_cols == 240) && !(cta_group == 2 && n_cols >= 32 && n_cols <= 256 && n_cols % 16 == 0)) {
+        rr_set_error("rr_debug_mma_peak_shape: cta_group 1 with 240 columns, or cta_group 2 with 32..256 columns in steps of 16");
+        return RR_E_ARG;
+    }
     if (variant != RR_VARIANT_UMMA && variant != RR_VARIANT_UMMA_F4 && variant != RR_VARIANT_UMMA_MXF4) { rr_set_error("rr_debug_mma_peak: a tcgen05 variant is required"); return RR_E_ARG; }
     const int ndev = rr_device_count();
     if (ndev <= 0) { rr_set_error("no CUDA device"); return RR_E_NODEV; }
@@ -1657,7 +1667,8 @@ extern "C" int rr_debug_mma_peak(int device, int variant, int kblocks_per_sm, in
     for (int r = 0; r <= reps; r++) {                                    // r = 0: warm-up
         float ms = 0.f;
         RR_CUDA(cudaEventRecord(a, nullptr));
-        RR_CUDA(rr_umma_mma_peak(mode, n_sm, kblocks_per_sm, macs, nullptr));
+        if (cta_group == 2) RR_CUDA(rr_umma_mma_peak_pair(mode, n_sm, kblocks_per_sm, n_cols, macs, nullptr));
+        else RR_CUDA(rr_umma_mma_peak(mode, n_sm, kblocks_per_sm, macs, nullptr));
         RR_CUDA(cudaEventRecord(b, nullptr));
         RR_CUDA(cudaEventSynchronize(b));
         RR_CUDA(cudaEventElapsedTime(&ms, a, b));

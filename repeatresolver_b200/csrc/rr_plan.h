@@ -67,3 +67,4 @@ int rr_umma_scan(rr_umma_state *&s, int mode /* 0 int8, 1 e2m1 f8f6f4, 2 e2m1 mx
 int rr_umma_dump_tile(rr_umma_state *s, int mode, uint64_t plan_id, rr_scan_params &P, rr_plan &plan, int rt, int ct,
                       int32_t *d_out /* device, [128][240] */, int n_sm, cudaStream_t st);
 cudaError_t rr_umma_mma_peak(int mode, int n_sm, int kblocks_per_sm, double *macs, cudaStream_t st);
+cudaError_t rr_umma_mma_peak_pair(int mode, int n_sm, int kblocks_per_sm, int n_cols, double *macs, cudaStream_t st);

@@ -36,6 +36,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstdio>
 #include "rr_kernels.h"
 #include "rr_device.cuh"
 #include "rr_plan.h"
@@ -48,10 +49,12 @@ constexpr int UM_M = 128;                        // rows per A tile (4 slabs x 3
 constexpr int UM_COL_SITES = 48;                 // column sites per tile
 constexpr int UM_N = UM_COL_SITES * 5;           // 240 columns per B tile
 constexpr int UM_KB = 128;                       // reads per K block (= 128 B swizzle span)
-constexpr int UM_STAGES = 3;
-constexpr int UM_A_BYTES = UM_M * UM_KB;         // 16384
-constexpr int UM_B_BYTES = UM_N * UM_KB;         // 30720
-constexpr int UM_STAGE_BYTES = UM_A_BYTES + UM_B_BYTES;  // 47104 = 46 * 1024
+constexpr int UM_STAGES = 4;
+constexpr int UM_A_BYTES = UM_M * UM_KB;         // 16384: this CTA's row tile
+constexpr int UM_BH = UM_N / 2;                  // 120: the half of the B tile this CTA of the pair holds (cta_group::2)
+constexpr int UM_B_BYTES = UM_BH * UM_KB;        // 15360
+constexpr int UM_STAGE_BYTES = UM_A_BYTES + UM_B_BYTES;  // 31744 = 31 * 1024
+static_assert(UM_STAGE_BYTES % 1024 == 0 && UM_BH % 8 == 0, "swizzled operand tiles are whole 1024-byte atoms");
 constexpr int UM_FIRST_EPI_WARP = 4;
 #ifndef RR_UM_EPI_WARPS
 #define RR_UM_EPI_WARPS 16
@@ -114,7 +117,9 @@ constexpr size_t UM_SMEM_MAX = 227 * 1024;
 constexpr int UM_LNF_MAX = (int)((UM_SMEM_MAX - UM_LNF_OFF) / sizeof(int));  // ln(n!) table entries that fit
 static_assert(UM_LNF_MAX >= 4096, "the float ln(n!) table should hold the depths of the bench workloads");
 
-struct um_unit { int32_t rt, ct0, ct1; };         // row tile, column tiles [ct0, ct1)
+// a work unit of a CTA pair: row tile rt0 for the CTA of rank 0, rt1 for rank 1 (-1: none, that CTA only lends its tensor
+// core and its half of the B tiles), column tiles [ct0, ct1) for both
+struct um_unit { int32_t rt0, rt1, ct0, ct1; };
 
 struct um_params {
     rr_scan_params P;
@@ -130,6 +135,7 @@ struct um_params {
     float t1q_scale;          // ln(10) * S rounded down: thresholds -> table units
     int preseed;              // pre-seed launch: subsample the rows of first-visit columns
     int32_t *dump;            // DUMP instantiation only: [UM_M][UM_N] counts of the (single) tile processed
+    int dump_rank;            //   ... by the CTA of this rank in the pair
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -190,6 +196,73 @@ __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+// ---- CTA pair (cluster of two, cta_group::2) ----
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same variable in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank)
+{
+    uint32_t a;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(cta_addr), "r"(rank));
+    return a;
+}
+// arrive on a barrier of the other CTA of the pair.  No cluster-scope release: nothing written through the generic proxy is
+// handed over with these arrivals (TMEM reads are ordered by tcgen05.wait::ld + tcgen05.fence, operand tiles by the TMA's own
+// completion), and the .release.cluster form costs a MEMBAR.ALL.GPU per arrival (measured: 10 % of all warp samples)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// a box of this CTA's operand half into its own shared memory; the bytes are counted on the LEADER CTA's mbarrier
+// (cluster address), which the 2-CTA MMA waits for
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+// completion of every MMA issued so far -> one arrival on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(unsigned long long *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// D[tmem of both CTAs, 2 x 128 rows] (+)= A[both CTAs' row tiles] * B[the two halves of the column tile]; issued by the leader
+template <int MODE>
+__device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                            uint32_t tsfa, uint32_t tsfb)
+{
+    if constexpr (MODE == 2)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tsfa), "r"(tsfb)
+            : "memory");
+    else if constexpr (MODE == 1)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(unsigned long long *bar)
@@ -241,14 +314,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr)
 //   kind::i8      D = S32 (2), A = B = unsigned 8 bit (0)
 //   kind::f8f6f4  D = F32 (1), A = B = E2M1 (5)
 //   kind::mxf4    block-scaled descriptor: A = B = E2M1 (1), scale format UE8M0 (bit 23), scale ids 0, K = 64
-template <int MODE>
+template <int MODE, int M = UM_M>
 __device__ __forceinline__ uint32_t make_idesc()
 {
     if constexpr (MODE == 2)
-        return (1u << 7) | (1u << 10) | ((uint32_t)(UM_N >> 3) << 17) | (1u << 23) | ((uint32_t)(UM_M >> 4) << 24);
+        return (1u << 7) | (1u << 10) | ((uint32_t)(UM_N >> 3) << 17) | (1u << 23) | ((uint32_t)(M >> 4) << 24);
     const uint32_t cfmt = MODE == 1 ? 1u : 2u, abfmt = MODE == 1 ? 5u : 0u;
     return (cfmt << 4) | (abfmt << 7) | (abfmt << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(UM_N >> 3) << 17) |
-           ((uint32_t)(UM_M >> 4) << 24);
+           ((uint32_t)(M >> 4) << 24);
 }
 
 #define TMEM_LD_8(v, addr)                                                                          \
@@ -310,6 +383,15 @@ __device__ __forceinline__ uint32_t um_best_hi(const rr_best_t *p)
     return hi;
 }
 
+// exclusive K-block bound of length class seg for a unit: both CTAs of the pair run the same K blocks, the union of what
+// their two row tiles need
+__device__ __forceinline__ int um_khi(const um_params &U, int seg, const um_unit &un)
+{
+    int k = U.k_hi[seg * U.n_rt + un.rt0];
+    if (un.rt1 >= 0) k = max(k, U.k_hi[seg * U.n_rt + un.rt1]);
+    return k;
+}
+
 // PACK16: 4 R < 65536 is known at compile time (the fast path of the bench workloads); otherwise decided at run time
 template <bool ALL_SMEM, int MODE, bool DUMP, bool PACK16>
 __global__ void __launch_bounds__(UM_THREADS, 1)
@@ -323,27 +405,33 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // instead of re-reading SR_TID inside the epilogue loop
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const bool mma_only = (P.flags & RR_DEBUG_MMA_ONLY) != 0;   // timing decomposition: accumulators released unread
+    // the CTA pair: rank 0 (the leader) issues the MMAs for both; rank r owns one row tile of the unit and half r of every B tile
+    const int cta_rank = (int)cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs_grid = gridDim.x >> 1;
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();  // the swizzled operand tiles need a 1024-byte aligned base
-        for (int s = 0; s < UM_STAGES; s++) { mbar_init(&T->full[s], 1); mbar_init(&T->empty[s], 1); }
+        // full: the leader's counts both producers (its own arrive + expect_tx, the peer's remote arrive) and the bytes of
+        // both CTAs' boxes; empty / tfull: one multicast commit of the leader's MMA thread; tempty: the leader's counts the
+        // epilogue warps of both CTAs
+        for (int s = 0; s < UM_STAGES; s++) { mbar_init(&T->full[s], 2); mbar_init(&T->empty[s], 1); }
         for (int a = 0; a < 2; a++) {
-            mbar_init(&T->tfull[a], 1); mbar_init(&T->tempty[a], UM_EPI_WARPS);
+            mbar_init(&T->tfull[a], 1); mbar_init(&T->tempty[a], 2 * UM_EPI_WARPS);
             mbar_init(&T->bfull[a], 1); mbar_init(&T->bempty[a], 1);
             mbar_init(&T->mfull[a], 1); mbar_init(&T->mempty[a], UM_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&T->tmem_base)), "n"(UM_TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (warp == 1) {   // the same warp of both CTAs
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&T->tmem_base)), "n"(UM_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     {
         const double scale = (double)(1 << U.t1q_shift);
         for (int n = threadIdx.x; n < U.lnf_smem; n += UM_THREADS) lnf_s[n] = __double2int_rn(U.P.lnfact[n] * scale);
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();   // barriers of both CTAs initialised before either signals the other's
     tc_fence_after();
     const uint32_t tmem_base = T->tmem_base;
     if constexpr (MODE == 2) {
@@ -371,7 +459,8 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
             uint32_t it = 0, tix = 0;
-            for (int u = blockIdx.x; u < U.n_units; u += gridDim.x) {
+            const uint32_t leader_full0 = mapa_u32(smem_u32(&T->full[0]), 0);
+            for (int u = pair; u < U.n_units; u += n_pairs_grid) {
                 const um_unit un = U.units[u];
                 for (int ct = un.ct0; ct < un.ct1; ct++, tix++) {
                     {   // the tile's running maxima and admissibility masks, one tile ahead of the epilogue at least
@@ -380,37 +469,40 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const int ng = min(UM_N, 5 * U.P.N - ct * UM_N);
                         // plain store, ordered before the waiters' reads by the release of the arrive below
                         int any = 0;
-                        for (int seg = 0; seg < U.n_cls; seg++) any |= U.k_lo[seg * U.n_ct + ct] < U.k_hi[seg * U.n_rt + un.rt];
+                        for (int seg = 0; seg < U.n_cls; seg++) any |= U.k_lo[seg * U.n_ct + ct] < um_khi(U, seg, un);
                         T->thr[tb].has_counts = any;
                         mbar_expect_tx(&T->bfull[tb], (uint32_t)(ng * sizeof(rr_best_t) + UM_CMASK_BYTES));
                         bulk_load(&T->thr[tb].best[0], U.P.best + (size_t)ct * UM_N, (uint32_t)(ng * sizeof(rr_best_t)), &T->bfull[tb]);
                         bulk_load(&T->thr[tb].cmask[0], U.colmask + (size_t)ct * UM_CMASK_BYTES, UM_CMASK_BYTES, &T->bfull[tb]);
                     }
                     for (int seg = 0; seg < U.n_cls; seg++)
-                    for (int kb = U.k_lo[seg * U.n_ct + ct], ke = U.k_hi[seg * U.n_rt + un.rt]; kb < ke; kb++, it++) {
+                    for (int kb = U.k_lo[seg * U.n_ct + ct], ke = um_khi(U, seg, un); kb < ke; kb++, it++) {
                         const int s = it % UM_STAGES;
                         const uint32_t ph = (it / UM_STAGES) & 1;
                         mbar_wait_sleep(&T->empty[s], ph ^ 1, 64);
-                        // the transaction count is in HBM-side bytes: packed e2m1 delivers half the smem footprint
-                        mbar_expect_tx(&T->full[s], MODE == 1 ? UM_STAGE_BYTES / 2 : UM_STAGE_BYTES);
+                        // the leader's barrier expects the boxes of both CTAs; the transaction count is in HBM-side bytes:
+                        // packed e2m1 delivers half the smem footprint
+                        const uint32_t lfull = leader_full0 + (uint32_t)(s * sizeof(unsigned long long));
+                        if (cta_rank == 0) mbar_expect_tx(&T->full[s], 2 * (MODE == 1 ? UM_STAGE_BYTES / 2 : UM_STAGE_BYTES));
+                        else mbar_arrive_cluster(lfull);
                         uint8_t *sa = smem + (size_t)s * UM_STAGE_BYTES;
                         constexpr int KREADS = MODE == 2 ? 2 * UM_KB : UM_KB;  // reads per 128-byte smem row
-                        tma_load_2d(sa, &map_a, &T->full[s], kb * KREADS, un.rt * UM_M);
-                        tma_load_2d(sa + UM_A_BYTES, &map_b, &T->full[s], kb * KREADS, ct * UM_N);
+                        tma_load_2d_pair(sa, &map_a, lfull, kb * KREADS, (cta_rank == 0 || un.rt1 < 0 ? un.rt0 : un.rt1) * UM_M);
+                        tma_load_2d_pair(sa + UM_A_BYTES, &map_b, lfull, kb * KREADS, ct * UM_N + cta_rank * UM_BH);
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc<MODE>();
+        if (lane == 0 && cta_rank == 0) {
+            const uint32_t idesc = make_idesc<MODE, 2 * UM_M>();
             uint32_t it = 0, tile = 0;
-            for (int u = blockIdx.x; u < U.n_units; u += gridDim.x) {
+            for (int u = pair; u < U.n_units; u += n_pairs_grid) {
                 const um_unit un = U.units[u];
                 for (int ct = un.ct0; ct < un.ct1; ct++) {
                     int any = 0;
-                    for (int seg = 0; seg < U.n_cls; seg++) any |= U.k_lo[seg * U.n_ct + ct] < U.k_hi[seg * U.n_rt + un.rt];
+                    for (int seg = 0; seg < U.n_cls; seg++) any |= U.k_lo[seg * U.n_ct + ct] < um_khi(U, seg, un);
                     if (!any) continue;   // no read covers both tiles: the epilogue uses zeros
                     const int acc = tile & 1;
                     const uint32_t aph = (tile >> 1) & 1;
@@ -419,7 +511,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const uint32_t tmem_d = tmem_base + (uint32_t)(acc * UM_ACC_STRIDE);
                     uint32_t accumulate = 0;   // the first MMA of a tile overwrites the accumulator
                     for (int seg = 0; seg < U.n_cls; seg++)
-                    for (int kb = U.k_lo[seg * U.n_ct + ct], ke = U.k_hi[seg * U.n_rt + un.rt]; kb < ke; kb++, it++) {
+                    for (int kb = U.k_lo[seg * U.n_ct + ct], ke = um_khi(U, seg, un); kb < ke; kb++, it++) {
                         const int s = it % UM_STAGES;
                         const uint32_t ph = (it / UM_STAGES) & 1;
                         mbar_wait_sleep(&T->full[s], ph, 32);
@@ -430,13 +522,13 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                         for (int k = 0; k < UM_KB / 32; k++) {
                             // advance 32 bytes (one K=32 slice) inside the 128 B swizzle span: +2 in 16 B units
-                            tc_mma<MODE>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate,
-                                         tmem_base + UM_SF_COL, tmem_base + UM_SF_COL + 8);
+                            tc_mma_pair<MODE>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate,
+                                              tmem_base + UM_SF_COL, tmem_base + UM_SF_COL + 8);
                             accumulate = 1u;
                         }
-                        tc_commit(&T->empty[s]);  // frees the smem stage when these MMAs retire
+                        tc_commit_pair(&T->empty[s]);  // frees the stage in both CTAs when these MMAs retire
                     }
-                    tc_commit(&T->tfull[acc]);    // accumulator complete
+                    tc_commit_pair(&T->tfull[acc]);    // accumulator complete, in both CTAs
                     tile++;
                 }
             }
@@ -448,7 +540,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const bool no_prune = (P.flags & RR_FLAG_NO_PRUNE) != 0;
         const float qscale = U.t1q_scale;
         uint32_t tix = 0;
-        for (int u = blockIdx.x; u < U.n_units; u += gridDim.x) {
+        for (int u = pair; u < U.n_units; u += n_pairs_grid) {
             const um_unit un = U.units[u];
             for (int ct = un.ct0; ct < un.ct1; ct++, tix++) {
                 const int tb = tix & 1;
@@ -498,11 +590,13 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         rr_lnf_global LG;        // double table in HBM/L2, tier 2 (rare, evaluated 32 at a time)
         LG.gmem = P.lnfact;
 
-        for (int u = blockIdx.x; u < U.n_units; u += gridDim.x) {
+        const uint32_t leader_tempty0 = mapa_u32(smem_u32(&T->tempty[0]), 0);
+        for (int u = pair; u < U.n_units; u += n_pairs_grid) {
             const um_unit un = U.units[u];
-            n_units += (ew == 0 && lane == 0);
+            n_units += (ew == 0 && lane == 0 && cta_rank == 0);
             // ---- row-side state of this thread (one output row = one group of one row site) ----
-            const int ii = lane_row ? P.rowsites[un.rt * UM_ROW_SITES + quarter * 6 + site_l] : -1;
+            const int rt = cta_rank == 0 ? un.rt0 : un.rt1;   // this CTA's row tile; a unit with one row tile leaves rank 1 without rows
+            const int ii = lane_row && rt >= 0 ? P.rowsites[rt * UM_ROW_SITES + quarter * 6 + site_l] : -1;
             const int gi = ii >= 0 ? 5 * ii + a : -1;
             const bool row_ok = gi >= 0 && P.rowok[gi] != 0;
             const int brk = ii >= 0 ? min(P.breakcol[ii], P.N) : 0;
@@ -534,7 +628,8 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const int jj = jsite0 + t;
                         if (row_ok && jj >= ii + 20 && jj < brk) n_pairs += __popc(TM.site[t].vmask);
                         if constexpr (DUMP)
-                            for (int b = 0; b < 5; b++) U.dump[(size_t)(quarter * 32 + lane) * UM_N + 5 * t + b] = 0;
+                            if (cta_rank == U.dump_rank)
+                                for (int b = 0; b < 5; b++) U.dump[(size_t)(quarter * 32 + lane) * UM_N + 5 * t + b] = 0;
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&T->mempty[tb]);
@@ -559,8 +654,10 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     taddr += 5 * UM_SUB;
                     if (n_left > 1) TMEM_LD_8(v, taddr);
                     if constexpr (DUMP) {
+                        if (cta_rank == U.dump_rank) {
 #pragma unroll
-                        for (int b = 0; b < 5; b++) U.dump[(size_t)(quarter * 32 + lane) * UM_N + 5 * (jj - jsite0) + b] = c[b] >> UM_QSHIFT;
+                            for (int b = 0; b < 5; b++) U.dump[(size_t)(quarter * 32 + lane) * UM_N + 5 * (jj - jsite0) + b] = c[b] >> UM_QSHIFT;
+                        }
                     }
                     const bool pair_site = jj >= row_lo && jj < brk;   // (row_lo: never for rows that are no row groups)
                     if (!__any_sync(0xffffffffu, pair_site)) continue;
@@ -668,7 +765,10 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(&T->tempty[acc]); mbar_arrive(&T->mempty[tb]); }
+                if (lane == 0) {
+                    mbar_arrive_cluster(leader_tempty0 + (uint32_t)(acc * sizeof(unsigned long long)));   // the leader's MMA thread waits for both CTAs
+                    mbar_arrive(&T->mempty[tb]);
+                }
                 tile++;
             }
             // candidates stay queued across units (entries carry their group ids): evaluating what a unit leaves behind at
@@ -693,10 +793,10 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
 
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();   // neither CTA leaves while the other may still signal its barriers or read its operands
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(UM_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(UM_TMEM_COLS) : "memory");
     }
 }
 
@@ -817,6 +917,7 @@ static int um_fill_params(rr_umma_state *S, const rr_scan_params &P, const rr_pl
     U.colmask = S->d_colmask;
     U.preseed = 0;
     U.dump = nullptr;
+    U.dump_rank = 0;
     U.lnf_smem = std::min(std::min(plan.max_cov + 2, P.R + 2), UM_LNF_MAX);
     smem_bytes = UM_LNF_OFF + (size_t)U.lnf_smem * sizeof(int);
     // fixed-point scale of the tier-1 table (rr_tier1_q): the largest power of two that keeps ln(maxcov!) below 2^30
@@ -826,30 +927,55 @@ static int um_fill_params(rr_umma_state *S, const rr_scan_params &P, const rr_pl
     return RR_OK;
 }
 
+// One launch over n_units work units: a persistent grid of CTA pairs (clusters of two), as many as the device runs at once
 template <bool ALL_SMEM, int MODE, bool DUMP, bool PACK16 = false>
-static cudaError_t um_launch_one(int grid, size_t smem_bytes, cudaStream_t st, const CUtensorMap &map_a, const CUtensorMap &map_b,
+static cudaError_t um_launch_one(int n_units, size_t smem_bytes, cudaStream_t st, const CUtensorMap &map_a, const CUtensorMap &map_b,
                                  const um_params &prm)
 {
     // per device, so set on every launch (a few microseconds)
     cudaError_t e = cudaFuncSetAttribute(rr_k_scan_umma<ALL_SMEM, MODE, DUMP, PACK16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_MAX);
     if (e != cudaSuccess) return e;
-    rr_k_scan_umma<ALL_SMEM, MODE, DUMP, PACK16><<<grid, UM_THREADS, smem_bytes, st>>>(map_a, map_b, prm);
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(UM_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // how many pairs are resident at once (units are dealt out round robin: a pair that had to wait for a free SM pair would
+    // run its share after everybody else's); asked once per device and instantiation
+    static int resident_pairs[64] = {0};
+    int dev = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    int &cached = resident_pairs[dev & 63];
+    if (cached == 0) {
+        int n_sm = 0, n = 0;
+        if ((e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        cfg.gridDim = dim3((unsigned)(n_sm / 2 * 2));
+        if ((e = cudaOccupancyMaxActiveClusters(&n, rr_k_scan_umma<ALL_SMEM, MODE, DUMP, PACK16>, &cfg)) != cudaSuccess) return e;
+        cached = std::max(1, std::min(n, n_sm / 2));
+        if (getenv("RR_TRACE")) fprintf(stderr, "[rr trace] scan kernel: %d CTA pairs resident on device %d (%d SMs)\n", n, dev, n_sm);
+    }
+    cfg.gridDim = dim3((unsigned)(2 * std::max(1, std::min(cached, n_units))));
+    e = cudaLaunchKernelEx(&cfg, rr_k_scan_umma<ALL_SMEM, MODE, DUMP, PACK16>, map_a, map_b, prm);
     rr_count_launch(1);
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-static cudaError_t um_launch(int mode, bool all_smem, bool dump, int grid, size_t smem_bytes, cudaStream_t st, const CUtensorMap &map_a,
+static cudaError_t um_launch(int mode, bool all_smem, bool dump, int n_units, size_t smem_bytes, cudaStream_t st, const CUtensorMap &map_a,
                              const CUtensorMap &map_b, const um_params &prm)
 {
     if (dump) {   // test hook: any table size, one tile
-        return mode == 2 ? um_launch_one<false, 2, true>(grid, smem_bytes, st, map_a, map_b, prm)
-             : mode == 1 ? um_launch_one<false, 1, true>(grid, smem_bytes, st, map_a, map_b, prm)
-                         : um_launch_one<false, 0, true>(grid, smem_bytes, st, map_a, map_b, prm);
+        return mode == 2 ? um_launch_one<false, 2, true>(n_units, smem_bytes, st, map_a, map_b, prm)
+             : mode == 1 ? um_launch_one<false, 1, true>(n_units, smem_bytes, st, map_a, map_b, prm)
+                         : um_launch_one<false, 0, true>(n_units, smem_bytes, st, map_a, map_b, prm);
     }
-    if (mode == 2 && all_smem && prm.P.R < (65536 >> UM_QSHIFT)) return um_launch_one<true, 2, false, true>(grid, smem_bytes, st, map_a, map_b, prm);
-    if (mode == 2) return all_smem ? um_launch_one<true, 2, false>(grid, smem_bytes, st, map_a, map_b, prm) : um_launch_one<false, 2, false>(grid, smem_bytes, st, map_a, map_b, prm);
-    if (mode == 1) return all_smem ? um_launch_one<true, 1, false>(grid, smem_bytes, st, map_a, map_b, prm) : um_launch_one<false, 1, false>(grid, smem_bytes, st, map_a, map_b, prm);
-    return all_smem ? um_launch_one<true, 0, false>(grid, smem_bytes, st, map_a, map_b, prm) : um_launch_one<false, 0, false>(grid, smem_bytes, st, map_a, map_b, prm);
+    if (mode == 2 && all_smem && prm.P.R < (65536 >> UM_QSHIFT)) return um_launch_one<true, 2, false, true>(n_units, smem_bytes, st, map_a, map_b, prm);
+    if (mode == 2) return all_smem ? um_launch_one<true, 2, false>(n_units, smem_bytes, st, map_a, map_b, prm) : um_launch_one<false, 2, false>(n_units, smem_bytes, st, map_a, map_b, prm);
+    if (mode == 1) return all_smem ? um_launch_one<true, 1, false>(n_units, smem_bytes, st, map_a, map_b, prm) : um_launch_one<false, 1, false>(n_units, smem_bytes, st, map_a, map_b, prm);
+    return all_smem ? um_launch_one<true, 0, false>(n_units, smem_bytes, st, map_a, map_b, prm) : um_launch_one<false, 0, false>(n_units, smem_bytes, st, map_a, map_b, prm);
 }
 
 int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &P, rr_plan &plan, int n_sm, cudaStream_t st)
@@ -891,59 +1017,91 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
         rr_count_launch(1);
         UM_CUDA(cudaGetLastError());
 
-        // work units: (row tile, aligned chunk of UNIT_CT column tiles), this part's row tiles only, ordered in
-        // 2-D blocks of GR (48) row tiles x GC (3) chunks so that the ~148 units in flight at any time share a working set
-        // (GR A row-tiles + GC*UNIT_CT B column-tiles, a few tens of MB) that stays resident in the 126 MB L2.
-        constexpr int UNIT_CT = 4, GR = 48, GC = 3;   // measured best of six block shapes at config 2
+        // work units of a CTA pair: (two adjacent row tiles rb, rb + 1 of this part - the last pair of an odd part has
+        // one -, aligned chunk of UNIT_CT column tiles over the union of the two tiles' column ranges; the epilogue's own
+        // range test keeps a row out of the column tiles that are only the other tile's), ordered in 2-D blocks of GR (48)
+        // row tiles x GC (3) chunks so that the units in flight at any time share a working set (GR A row-tiles +
+        // GC*UNIT_CT B column-tiles, a few tens of MB) that stays resident in the 126 MB L2.
+#ifndef RR_UM_GR
+#define RR_UM_GR 48
+#define RR_UM_GC 3
+#define RR_UM_UNIT_CT 4
+#endif
+        constexpr int UNIT_CT = RR_UM_UNIT_CT, GR = RR_UM_GR, GC = RR_UM_GC;   // measured best of six block shapes at config 2
+        static_assert(GR % 2 == 0, "row-tile pairs do not straddle a block");
         struct keyed { int64_t key; um_unit u; };
-        // generated directly in block order (row group, chunk group, row tile, chunk): no sort needed
+        struct colrange { int cb0, cb1; };      // column tiles [cb0, cb1) of a pair of row tiles (rb1 < 0: one tile)
+        auto pair_range = [&](int rb0, int rb1) {
+            colrange r = {0x7fffffff, -1};
+            for (int t : {rb0, rb1}) {
+                if (t < 0) continue;
+                const int cb0 = plan.unit_cb0[t];
+                const int ncb = (int)(plan.unit_prefix[t + 1] - plan.unit_prefix[t]);
+                if (ncb <= 0) continue;
+                r.cb0 = std::min(r.cb0, cb0);
+                r.cb1 = std::max(r.cb1, cb0 + ncb);
+            }
+            return r;
+        };
+        auto pair_kblocks = [&](int rb0, int rb1, int cb) {   // K blocks both CTAs of the pair run for column tile cb
+            int sum = 0;
+            const int nrb = std::max(plan.n_rowblocks, 1), ncb = std::max(plan.n_colblocks, 1);
+            for (int c = 0; c < plan.n_classes; c++) {
+                int hi = plan.k_hi[(size_t)c * nrb + rb0];
+                if (rb1 >= 0) hi = std::max(hi, plan.k_hi[(size_t)c * nrb + rb1]);
+                sum += std::max(0, hi - plan.k_lo[(size_t)c * ncb + cb]);
+            }
+            return sum;
+        };
+        auto second = [&](int rb, int rb_end) { return rb + 1 < rb_end ? rb + 1 : -1; };   // the main pass pairs adjacent row tiles
+        // generated directly in block order (row group, chunk group, row-tile pair, chunk): no sort needed
         std::vector<um_unit> units;
-        int64_t kblocks = 0;
+        int64_t kblocks = 0;   // K blocks issued, counted per CTA (a pair's K block is two)
         {
             int cc_min = 0x7fffffff, cc_max = -1;
-            for (int rb = plan.rb_lo; rb < plan.rb_hi; rb++) {
-                const int cb0 = plan.unit_cb0[rb];
-                const int ncb = (int)(plan.unit_prefix[rb + 1] - plan.unit_prefix[rb]);
-                if (ncb <= 0) continue;
-                cc_min = std::min(cc_min, cb0 / UNIT_CT);
-                cc_max = std::max(cc_max, (cb0 + ncb - 1) / UNIT_CT);
-                for (int c = 0; c < ncb; c++) kblocks += plan.kunits(rb, cb0 + c);
+            for (int rb = plan.rb_lo; rb < plan.rb_hi; rb += 2) {
+                const colrange r = pair_range(rb, second(rb, plan.rb_hi));
+                if (r.cb1 <= r.cb0) continue;
+                cc_min = std::min(cc_min, r.cb0 / UNIT_CT);
+                cc_max = std::max(cc_max, (r.cb1 - 1) / UNIT_CT);
+                for (int c = r.cb0; c < r.cb1; c++) kblocks += 2 * (int64_t)pair_kblocks(rb, second(rb, plan.rb_hi), c);
             }
             for (int rg = plan.rb_lo; rg < plan.rb_hi; rg += GR)
                 for (int cg = cc_max < 0 ? 1 : cc_min / GC; cc_max >= 0 && cg <= cc_max / GC; cg++)
-                    for (int rb = rg; rb < std::min(rg + GR, plan.rb_hi); rb++) {
-                        const int cb0 = plan.unit_cb0[rb];
-                        const int ncb = (int)(plan.unit_prefix[rb + 1] - plan.unit_prefix[rb]);
-                        if (ncb <= 0) continue;
-                        const int c_lo = std::max(cg * GC, cb0 / UNIT_CT), c_hi = std::min(cg * GC + GC - 1, (cb0 + ncb - 1) / UNIT_CT);
+                    for (int rb = rg; rb < std::min(rg + GR, plan.rb_hi); rb += 2) {
+                        const colrange r = pair_range(rb, second(rb, plan.rb_hi));
+                        if (r.cb1 <= r.cb0) continue;
+                        const int c_lo = std::max(cg * GC, r.cb0 / UNIT_CT), c_hi = std::min(cg * GC + GC - 1, (r.cb1 - 1) / UNIT_CT);
                         for (int cc = c_lo; cc <= c_hi; cc++)
-                            units.push_back({rb, std::max(cb0, cc * UNIT_CT), std::min(cb0 + ncb, (cc + 1) * UNIT_CT)});
+                            units.push_back({rb, second(rb, plan.rb_hi), std::max(r.cb0, cc * UNIT_CT), std::min(r.cb1, (cc + 1) * UNIT_CT)});
                     }
         }
-        // Seeding pass: the same kernel over every SEED-th row tile of the WHOLE MSA first.  It leaves true
-        // (lower-bound) maxima in best[] for all column groups, so the full pass starts with thresholds close
+        // Seeding pass: the same kernel over every SEED-th row tile of the WHOLE MSA first (a CTA pair takes two of them, SEED
+        // row tiles apart: with two adjacent tiles every 2*SEED instead, a column's nearest seed row is twice as far away and
+        // the full pass evaluates 2.2 x the candidates - measured).  It leaves
+        // true (lower-bound) maxima in best[] for all column groups, so the full pass starts with thresholds close
         // to the final ones instead of 0 and the bounds prune from the first pair on.  Its pair statistics are
         // discarded.  With several parts (GPUs) the seed tiles are split by COLUMN chunk (chunk % parts == part):
         // a column's first visit, where every pair is a candidate, then happens on one GPU only, and the GPUs
         // exchange the seeded maxima (all-reduce MAX) before their full passes.
-        // The seeding pass itself starts from zero thresholds; a pre-seed over every PRESEED-th seed row tile
+        // The seeding pass itself starts from zero thresholds; a pre-seed over every PRESEED-th seed pair
         // takes that warm-up on ~1/512 of the row tiles instead of 1/64.
         constexpr int SEED = 64, PRESEED = 8;
         std::vector<um_unit> seed_units, preseed_units;
         if (plan.n_rowblocks >= 2 * SEED) {
             std::vector<keyed> ks;
-            for (int rb = SEED / 2; rb < plan.n_rowblocks; rb += SEED) {
-                const int cb0 = plan.unit_cb0[rb];
-                const int ncb = (int)(plan.unit_prefix[rb + 1] - plan.unit_prefix[rb]);
-                if (ncb <= 0) continue;
-                for (int cc = cb0 / UNIT_CT; cc <= (cb0 + ncb - 1) / UNIT_CT; cc++) {
+            for (int rb = SEED / 2; rb < plan.n_rowblocks; rb += 2 * SEED) {
+                const int rb1 = rb + SEED < plan.n_rowblocks ? rb + SEED : -1;
+                const colrange r = pair_range(rb, rb1);
+                if (r.cb1 <= r.cb0) continue;
+                for (int cc = r.cb0 / UNIT_CT; cc <= (r.cb1 - 1) / UNIT_CT; cc++) {
                     if (cc % plan.part_count != plan.part_index) continue;
                     // with several parts a GPU owns 1/parts of the chunks: one column tile per unit then, so that the few seed
-                    // row tiles still fill its SMs (8 parts at config 2: 190 four-tile units for 148 SMs = two uneven waves)
-                    const int c_lo = std::max(cb0, cc * UNIT_CT), c_hi = std::min(cb0 + ncb, (cc + 1) * UNIT_CT);
+                    // row tiles still fill its SMs
+                    const int c_lo = std::max(r.cb0, cc * UNIT_CT), c_hi = std::min(r.cb1, (cc + 1) * UNIT_CT);
                     const int step = plan.part_count > 1 ? 1 : UNIT_CT;
                     for (int c = c_lo; c < c_hi; c += step) {
-                        um_unit un = {rb, c, std::min(c_hi, c + step)};
+                        um_unit un = {rb, rb1, c, std::min(c_hi, c + step)};
                         ks.push_back({((int64_t)(cc / GC) << 32) + ((int64_t)rb << 12) + ((int64_t)(cc % (GC * 64)) << 3) + (c - c_lo), un});
                     }
                 }
@@ -951,7 +1109,7 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
             std::sort(ks.begin(), ks.end(), [](const keyed &x, const keyed &y) { return x.key < y.key; });
             for (const keyed &k : ks) {
                 seed_units.push_back(k.u);
-                if ((k.u.rt / SEED) % PRESEED == 0) preseed_units.push_back(k.u);
+                if ((k.u.rt0 / (2 * SEED)) % PRESEED == 0) preseed_units.push_back(k.u);
             }
         }
         seed_units.insert(seed_units.end(), preseed_units.begin(), preseed_units.end());  // stored behind the seed list
@@ -979,7 +1137,7 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
             UM_CUDA(cudaStreamSynchronize(st));  // units[] is a local
             rr_trace_mark("umma: uploads synced");
             if ((rc = make_map(&S->map_a, S->xa[md], xa_rows, (uint64_t)S->Kp, UM_M, mode))) return rc;
-            if ((rc = make_map(&S->map_b, S->xb[md], (uint64_t)5 * P.N, (uint64_t)S->Kp, UM_N, mode))) return rc;
+            if ((rc = make_map(&S->map_b, S->xb[md], (uint64_t)5 * P.N, (uint64_t)S->Kp, UM_BH, mode))) return rc;   // one CTA's half of a column tile
         }
         rr_trace_mark("umma: tensor maps");
         S->built_plan_id = plan_id;
@@ -989,7 +1147,6 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
     if (S->n_units == 0) return RR_OK;
 
     um_params U;
-    const int grid = std::min<int>(n_sm, S->n_units);
     size_t smem_bytes;
     bool all_smem;
     if ((rc = um_fill_params(S, P, plan, U, smem_bytes, all_smem))) return rc;
@@ -999,16 +1156,16 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
             V.units = S->d_units + S->n_units + S->n_seed;
             V.n_units = S->n_preseed;
             V.preseed = 1;  // subsample first-visit columns
-            UM_CUDA(um_launch(mode, all_smem, false, std::min<int>(n_sm, V.n_units), smem_bytes, st, S->map_a, S->map_b, V));
+            UM_CUDA(um_launch(mode, all_smem, false, V.n_units, smem_bytes, st, S->map_a, S->map_b, V));
             V.preseed = 0;
         }
         V.units = S->d_units + S->n_units;
         V.n_units = S->n_seed;
-        UM_CUDA(um_launch(mode, all_smem, false, std::min<int>(n_sm, V.n_units), smem_bytes, st, S->map_a, S->map_b, V));
+        UM_CUDA(um_launch(mode, all_smem, false, V.n_units, smem_bytes, st, S->map_a, S->map_b, V));
         UM_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(unsigned long long) * 8, st));
     }
     if (P.flags & RR_FLAG_SEED_ONLY) return RR_OK;
-    UM_CUDA(um_launch(mode, all_smem, false, grid, smem_bytes, st, S->map_a, S->map_b, U));
+    UM_CUDA(um_launch(mode, all_smem, false, U.n_units, smem_bytes, st, S->map_a, S->map_b, U));
     return RR_OK;
 }
 
@@ -1024,7 +1181,10 @@ int rr_umma_dump_tile(rr_umma_state *S, int mode, uint64_t plan_id, rr_scan_para
         return RR_E_ARG;
     }
     if (rt < 0 || rt >= plan.n_rowblocks || ct < 0 || ct >= plan.n_colblocks) { rr_set_error("rr_debug_umma_counts: tile out of range"); return RR_E_ARG; }
-    um_unit one = {rt, ct, ct + 1}, *d_one = nullptr;
+    // odd row tiles are dumped by rank 1 of the pair (rt - 1, rt), even ones by rank 0 of (rt, rt + 1) - or of (rt) alone
+    const int dump_rank = rt & 1;
+    const int rt0 = rt - dump_rank;
+    um_unit one = {rt0, rt0 + 1 < plan.n_rowblocks ? rt0 + 1 : -1, ct, ct + 1}, *d_one = nullptr;
     if (rr_dev_malloc((void **)&d_one, sizeof one) != cudaSuccess) { cudaGetLastError(); rr_set_error("out of device memory"); return RR_E_NOMEM; }
     um_params U;
     size_t smem_bytes;
@@ -1035,6 +1195,7 @@ int rr_umma_dump_tile(rr_umma_state *S, int mode, uint64_t plan_id, rr_scan_para
         U.units = d_one;
         U.n_units = 1;
         U.dump = d_out;
+        U.dump_rank = dump_rank;
         U.P.flags |= RR_FLAG_NO_PRUNE;   // thresholds play no part
         e = cudaMemcpyAsync(d_one, &one, sizeof one, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(d_out, 0xff, sizeof(int32_t) * UM_M * UM_N, st);
@@ -1054,14 +1215,15 @@ int rr_umma_dump_tile(rr_umma_state *S, int mode, uint64_t plan_id, rr_scan_para
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
 constexpr int PK_BATCH = 16;   // K blocks per commit
+constexpr int PK_TILE_BYTES = (UM_M + UM_N) * UM_KB;   // one A tile (128 rows) and one whole B tile (240 rows) of 128 bytes per row
 template <int MODE>
 __global__ void __launch_bounds__(128, 1) rr_k_mma_peak(int batches)
 {
     uint8_t *smem = um_smem;
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + UM_STAGE_BYTES);   // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + UM_STAGE_BYTES + 16);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + PK_TILE_BYTES);   // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + PK_TILE_BYTES + 16);
     const int warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < UM_STAGE_BYTES / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = MODE == 0 ? 0x02020202u : 0x44444444u;
+    for (int i = threadIdx.x; i < PK_TILE_BYTES / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = MODE == 0 ? 0x02020202u : 0x44444444u;
     if (threadIdx.x == 0) {
         mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1110,10 +1272,91 @@ __global__ void __launch_bounds__(128, 1) rr_k_mma_peak(int batches)
     }
 }
 
+// the same for a CTA pair: the leader issues tcgen05.mma.cta_group::2 (M = 256: 128 rows per CTA; N = n_cols, each CTA holding
+// n_cols / 2 rows of B), nothing loaded, nothing read back
+template <int MODE>
+__global__ void __launch_bounds__(128, 1) rr_k_mma_peak_pair(int batches, int n_cols)
+{
+    uint8_t *smem = um_smem;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + PK_TILE_BYTES);   // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + PK_TILE_BYTES + 16);
+    const int warp = threadIdx.x >> 5;
+    const int rank = (int)cluster_ctarank();
+    for (int i = threadIdx.x; i < PK_TILE_BYTES / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = MODE == 0 ? 0x02020202u : 0x44444444u;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(UM_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if constexpr (MODE == 2) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)UM_SF_COL;
+        const uint32_t one = 0x7F7F7F7Fu;
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+            ::"r"(taddr), "r"(one) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    if (threadIdx.x == 0 && rank == 0) {
+        const uint32_t idesc = (make_idesc<MODE, 2 * UM_M>() & ~(0x3Fu << 17)) | ((uint32_t)(n_cols >> 3) << 17);
+        const uint32_t sa = smem_u32(smem);
+        const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + UM_A_BYTES);
+        for (int b = 0; b < batches; b++) {
+            const uint32_t tmem_d = tmem_base + (uint32_t)((b & 1) * UM_ACC_STRIDE);
+            for (int kb = 0; kb < PK_BATCH; kb++)
+#pragma unroll
+                for (int k = 0; k < UM_KB / 32; k++)
+                    tc_mma_pair<MODE>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u,
+                                      tmem_base + UM_SF_COL, tmem_base + UM_SF_COL + 8);
+            asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                         ::"r"(smem_u32(&bar[b & 1])), "h"((uint16_t)1) : "memory");
+            if (b >= 1) mbar_wait(&bar[(b - 1) & 1], ((b - 1) >> 1) & 1);
+        }
+        if (batches >= 1) mbar_wait(&bar[(batches - 1) & 1], ((batches - 1) >> 1) & 1);
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(UM_TMEM_COLS) : "memory");
+    }
+}
+
+template <int MODE>
+cudaError_t mma_peak_pair_launch(int grid, int batches, int n_cols, cudaStream_t st)
+{
+    const int smem_bytes = PK_TILE_BYTES + 64;
+    cudaError_t e = cudaFuncSetAttribute(rr_k_mma_peak_pair<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(grid / 2 * 2));
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, rr_k_mma_peak_pair<MODE>, batches, n_cols);
+    rr_count_launch(1);
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
 template <int MODE>
 cudaError_t mma_peak_launch(int grid, int batches, cudaStream_t st)
 {
-    const int smem_bytes = UM_STAGE_BYTES + 64;
+    const int smem_bytes = PK_TILE_BYTES + 64;
     cudaError_t e = cudaFuncSetAttribute(rr_k_mma_peak<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
     rr_k_mma_peak<MODE><<<grid, 128, smem_bytes, st>>>(batches);
@@ -1121,6 +1364,15 @@ cudaError_t mma_peak_launch(int grid, int batches, cudaStream_t st)
     return cudaGetLastError();
 }
 }  // namespace
+
+// CTA pairs, N = n_cols (a multiple of 16, 32..256): returns the MACs one launch executes through *macs
+cudaError_t rr_umma_mma_peak_pair(int mode, int n_sm, int kblocks_per_sm, int n_cols, double *macs, cudaStream_t st)
+{
+    const int batches = std::max(1, kblocks_per_sm / PK_BATCH);
+    *macs = (double)(n_sm / 2 * 2) * batches * PK_BATCH * (double)UM_M * n_cols * UM_KB * (mode == 2 ? 2 : 1);
+    return mode == 2 ? mma_peak_pair_launch<2>(n_sm, batches, n_cols, st) : mode == 1 ? mma_peak_pair_launch<1>(n_sm, batches, n_cols, st)
+                                                                                         : mma_peak_pair_launch<0>(n_sm, batches, n_cols, st);
+}
 
 // mode as in rr_umma_scan; returns the MACs one launch executes (all CTAs) through *macs
 cudaError_t rr_umma_mma_peak(int mode, int n_sm, int kblocks_per_sm, double *macs, cudaStream_t st)

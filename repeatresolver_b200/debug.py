@@ -41,3 +41,11 @@ def mma_peak(variant="umma_mxf4", device=0, kblocks_per_sm=16384, reps=5):
     ms, macs = C.c_float(0), C.c_double(0)
     _check(lib.rr_debug_mma_peak(device, VARIANTS[variant], kblocks_per_sm, reps, C.byref(ms), C.byref(macs)), "rr_debug_mma_peak")
     return {"tflops": 2.0 * macs.value / (ms.value * 1e-3) / 1e12, "ms": ms.value, "macs": macs.value}
+
+
+def mma_peak_shape(variant="umma_mxf4", cta_group=2, n_cols=240, device=0, kblocks_per_sm=16384, reps=5):
+    """mma_peak for another issue form: cta_group 2 = a CTA pair issuing M = 256 x n_cols (each CTA holds half of B)"""
+    ms, macs = C.c_float(0), C.c_double(0)
+    _check(lib.rr_debug_mma_peak_shape(device, VARIANTS[variant], cta_group, n_cols, kblocks_per_sm, reps, C.byref(ms), C.byref(macs)),
+           "rr_debug_mma_peak_shape")
+    return {"tflops": 2.0 * macs.value / (ms.value * 1e-3) / 1e12, "ms": ms.value, "macs": macs.value}

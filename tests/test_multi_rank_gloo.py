@@ -14,6 +14,14 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _free_port():
+    """a port nobody listens on right now (the tests may run side by side under pytest-xdist)"""
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
 def _worker(rank, world, port, codes, mincov, out_dir):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -43,7 +51,7 @@ def test_merge_over_ranks_gloo(world, tmp_path):
     codes = g.codes()
     # duplicate a few columns so that exact ties between different partners exist
     codes[:, 300:320] = codes[:, 100:120]
-    port = 29500 + (os.getpid() % 500) + world
+    port = _free_port()
     mp.spawn(_worker, args=(world, port, codes, 12, str(tmp_path)), nprocs=world, join=True)
     got = np.load(tmp_path / "merged.npz")
     M0, A0, P0 = O.Oracle.from_codes(codes).scan(12)
@@ -99,7 +107,7 @@ def test_cliquer_over_ranks_gloo(world, nq, tmp_path):
     o = O.Oracle.from_codes(codes)
     M0, _, _ = o.scan(12)
     queries = np.argsort(-M0, kind="stable")[:nq].astype(np.int32)
-    port = 29100 + (os.getpid() % 500) + 7 * world + nq
+    port = _free_port()
     mp.spawn(_cliquer_worker, args=(world, port, codes, queries, str(tmp_path)), nprocs=world, join=True)
     results = [np.load(tmp_path / f"clq{r}.npz") for r in range(world)]
     for k, q in enumerate(queries):
