@@ -11,16 +11,24 @@
 //              32-row slab (5 groups each + 2 zero rows) so that a site never straddles a warp
 //              of the epilogue; 24 sites per 128-row tile.
 //   B operand  xb[5N][Kp]             every group, 48 sites = 240 columns per tile.
-//   K          reads in span-start order; only the K blocks [k_lo(col tile), k_hi(row tile)) (128 reads, 256 for
-//              mxf4) can hold a read covering both tiles, the rest is skipped exactly.
+//   K          reads in (length class, span start) order; only the K blocks [k_lo(col tile), k_hi(row tile)) of every class
+//              (128 reads, 256 for mxf4) can hold a read covering both tiles, the rest is skipped exactly.
 //
 // Operand elements are 0 / 2 (not 0 / 1): a product is 4 = sizeof(float), so an accumulator holds 4 x count, which is
-// the byte offset of ln(count!) in the float table the epilogue's bounds look up - no shift-and-add per look-up.
+// the byte offset of ln(count!) in the table the epilogue's bounds look up - no shift-and-add per look-up.
+//
+// The kernel runs on CTA PAIRS (clusters of two = the two SMs of a TPC, tcgen05 cta_group::2): one MMA of M = 256 covers
+// the row tiles of both CTAs (128 accumulator rows in each CTA's TMEM) against one B tile of which each CTA loads and holds
+// HALF (120 rows) - a third less TMA traffic into and tensor-core traffic out of every SM's shared memory than two
+// independent CTAs, and half the L2 -> SM traffic for B.  Rank 0 of the pair (the leader) issues the MMAs; both producers'
+// boxes are counted on the leader's barrier; one multicast tcgen05.commit releases a stage / publishes an accumulator in
+// both CTAs; the epilogue warps of both CTAs release an accumulator on the leader's barrier.
 //
 // Warp roles (one persistent CTA per SM, 640 threads):
 //   warp 0      producer (one elected lane): per tile one bulk copy of the tile's 240 running maxima + admissibility
-//               masks into a 2-deep shared-memory ring, then per K block the A and B boxes by TMA -> smem stage
-//   warp 1      TMEM allocator + MMA issuer (one elected lane): 4 x tcgen05.mma per stage,
+//               masks into a 2-deep shared-memory ring, then per K block this CTA's A box and its half of the B box by TMA
+//               -> smem stage (4 stages of 31 KB)
+//   warp 1      TMEM allocator (both CTAs) + MMA issuer (one elected lane of the leader): 4 x tcgen05.mma per stage,
 //               tcgen05.commit frees the stage / publishes the accumulator
 //   warp 2      per tile: turns the producer's copy of the 240 running maxima and the admissibility masks into the
 //               tier-1 limits every epilogue warp reads (2-deep ring of its own), one tile ahead of the epilogue
@@ -180,13 +188,6 @@ __device__ __forceinline__ void mbar_wait_epi(unsigned long long *bar, uint32_t 
 {
     if constexpr (RR_UM_NS_EPI > 0) mbar_wait_sleep(bar, parity, RR_UM_NS_EPI);
     else mbar_wait(bar, parity);
-}
-__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
 }
 // plain bulk copy global -> shared (16-byte aligned on both sides, size a multiple of 16), completion on an mbarrier
 __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes, unsigned long long *bar)
