@@ -214,6 +214,17 @@ int rr_cliquer_batch(rr_packed *pk, int64_t n_queries, const int32_t *query_grou
                      int maxclique, double greedy, int32_t *members /*[n_queries][maxclique+1]*/,
                      double *scores /*[n_queries][maxclique]*/, int32_t *n_members /*[n_queries]*/,
                      rr_cliquer_stats *stats /* may be NULL */);
+/* CliqueGroup / CliqueCoverage (RepeatResolver.c:976-1008, 1064-1096), the step that follows Cliquer in Group_Refinement
+ * (1662-1664), for a batch of cliques: members[q * stride + m], m < n_members[q] (at most 100, the reference's own limit
+ * 986), are the clique's groups - the query itself first, as Cliquer returns it.
+ *   groups[q]   = the reads contained in MORE than cutoffs[q] of the member groups
+ *   coverage[q] = the reads covered at more than cutoffs[q] of the members' sites
+ * each as sc = rows / 64 + 1 words (RepeatResolver.c:59) in the reference's layout: read r (row of the MSA pk was made of)
+ * is bit r % 64 of word r / 64 (GrAdd 211-217).  Either output may be NULL.  A negative cutoff selects every read, as
+ * the reference's loop does.  Device work on the packed bitsets: 32 reads per instruction with bit-sliced counters
+ * (csrc/rr_cliquer.cu), every member word read once. */
+int rr_clique_groups(rr_packed *pk, int64_t n_cliques, const int32_t *members, int stride, const int32_t *n_members,
+                     const int32_t *cutoffs, uint64_t *groups /*[n_cliques][sc]*/, uint64_t *coverage /*[n_cliques][sc]*/);
 int rr_cliquer(rr_packed *pk, int query_group, int anfang, int ende, int mincov, int maxclique, double greedy,
                int32_t *members, double *scores, int *n_members);
 /* the host half on given counts (tests): groups[k] ascending candidate ids, counts[4k..4k+3] =

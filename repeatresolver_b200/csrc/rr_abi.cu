@@ -717,6 +717,57 @@ extern "C" int rr_cliquer_from_counts(int query_group, int64_t n, const int32_t 
 
 // one query, every candidate's counts from rr_pair_counts, every score on the host: the plain second implementation
 // the tests hold rr_cliquer_batch against
+// ---------------------------------------------------------------------------------------
+// CliqueGroup / CliqueCoverage for a batch of cliques (RepeatResolver.c:976-1008, 1064-1096; called 1662-1664)
+// ---------------------------------------------------------------------------------------
+extern "C" int rr_clique_groups(rr_packed *pk, int64_t n_cliques, const int32_t *members, int stride, const int32_t *n_members,
+                                const int32_t *cutoffs, uint64_t *groups, uint64_t *coverage)
+{
+    if (!pk || pk->phase != 3 || n_cliques < 0 || stride < 1 || (n_cliques && (!members || !n_members || !cutoffs))) {
+        rr_set_error("rr_clique_groups: bad arguments");
+        return RR_E_ARG;
+    }
+    if ((int)pk->h_perm.size() != pk->R) { rr_set_error("rr_clique_groups: the packed MSA carries no row order"); return RR_E_ARG; }
+    for (int64_t q = 0; q < n_cliques; q++) {
+        // the reference sizes a clique by its first negative entry among 100 (986-993)
+        if (n_members[q] < 0 || n_members[q] > stride || n_members[q] > 100) { rr_set_error("rr_clique_groups: clique %lld has %d members (0..min(stride, 100))", (long long)q, n_members[q]); return RR_E_ARG; }
+        for (int m = 0; m < n_members[q]; m++)
+            if (members[q * stride + m] < 0 || members[q * stride + m] >= 5 * pk->N) { rr_set_error("rr_clique_groups: group %d out of range", members[q * stride + m]); return RR_E_ARG; }
+    }
+    const int R = pk->R;
+    const size_t sc = (size_t)R / 64 + 1;                                // words of a group (RepeatResolver.c:59)
+    if (n_cliques == 0 || (!groups && !coverage)) return RR_OK;
+    RR_CUDA(cudaSetDevice(pk->device));
+    rr_alloc_stream(pk->st);
+    dev_scope scope;
+    int rc;
+    int32_t *d_members = nullptr, *d_nm = nullptr, *d_cut = nullptr, *d_rank = nullptr;
+    uint32_t *d_tmp = nullptr, *d_out = nullptr;
+    // cliques in slices that keep the device buffers small
+    const int64_t slice = std::max<int64_t>(1, std::min<int64_t>(n_cliques, ((int64_t)256 << 20) / (int64_t)(8 * sc + 4 * pk->W32)));
+    if ((rc = scope.alloc(&d_members, (size_t)slice * stride)) || (rc = scope.alloc(&d_nm, (size_t)slice)) || (rc = scope.alloc(&d_cut, (size_t)slice)) ||
+        (rc = scope.alloc(&d_rank, (size_t)std::max(R, 1))) || (rc = scope.alloc(&d_tmp, (size_t)slice * pk->W32)) || (rc = scope.alloc(&d_out, (size_t)slice * 2 * sc)))
+        return rc;
+    std::vector<int32_t> rank_of_row(std::max(R, 1), 0);
+    for (int r = 0; r < R; r++) rank_of_row[pk->h_perm[r]] = r;
+    RR_CUDA(cudaMemcpyAsync(d_rank, rank_of_row.data(), sizeof(int32_t) * std::max(R, 1), cudaMemcpyHostToDevice, pk->st));
+    for (int64_t q0 = 0; q0 < n_cliques; q0 += slice) {
+        const int64_t n = std::min(slice, n_cliques - q0);
+        RR_CUDA(cudaMemcpyAsync(d_members, members + q0 * stride, sizeof(int32_t) * n * stride, cudaMemcpyHostToDevice, pk->st));
+        RR_CUDA(cudaMemcpyAsync(d_nm, n_members + q0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, pk->st));
+        RR_CUDA(cudaMemcpyAsync(d_cut, cutoffs + q0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, pk->st));
+        for (int which = 0; which < 2; which++) {
+            uint64_t *dst = which ? coverage : groups;
+            if (!dst) continue;
+            RR_CUDA(rr_launch_clique_members(pk->d_bits, pk->d_covbits, pk->W32, n, d_members, stride, d_nm, d_cut, which, d_rank, R,
+                                             (int)(2 * sc), d_tmp, d_out, pk->st));
+            RR_CUDA(cudaMemcpyAsync(dst + q0 * sc, d_out, sizeof(uint64_t) * n * sc, cudaMemcpyDeviceToHost, pk->st));
+            RR_CUDA(cudaStreamSynchronize(pk->st));
+        }
+    }
+    return RR_OK;
+}
+
 extern "C" int rr_cliquer(rr_packed *pk, int query_group, int anfang, int ende, int mincov, int maxclique, double greedy,
                           int32_t *members, double *scores, int *n_members)
 {

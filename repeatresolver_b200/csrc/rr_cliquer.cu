@@ -199,6 +199,77 @@ rr_k_cliquer_score(const rr_clq_rec *__restrict__ cand, unsigned long long cap, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CliqueGroup / CliqueCoverage (/root/reference/RepeatResolver.c:976-1008, 1064-1096), the step of Group_Refinement
+// that follows Cliquer (1662-1664): the reads contained in MORE than c of a clique's member groups, and the reads
+// covered at more than c of the members' sites.  The reference walks every read and tests it against every member
+// (signumber x |clique| GrElement calls per clique); here a thread owns 32 reads = one word of the device bitsets and
+// adds the members' words into bit-sliced counters (7 planes: a clique has at most 100 members, 986), then compares the
+// counters with c plane by plane - 32 reads per instruction, every member word read once, coalesced over the block.
+//   which = 0: member groups (bits), which = 1: the members' sites (covbits)
+//   out[clique][W32] in RANK order (the order of the device bitsets); rr_k_rank_bits_to_rows turns it into the
+//   reference's layout (read r = bit r % 64 of word r / 64 in MSA row order, GrAdd 211-217).
+// HBM-bound integer work: |clique| x W32 words read per clique and kind.
+constexpr int CLG_PLANES = 7;
+__global__ void __launch_bounds__(128)
+rr_k_clique_members(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ covbits, int W32, int64_t n_cliques,
+                    const int32_t *__restrict__ members, int stride, const int32_t *__restrict__ n_members,
+                    const int32_t *__restrict__ cutoffs, int which, uint32_t *__restrict__ out)
+{
+    const int64_t q = blockIdx.y;
+    if (q >= n_cliques) return;
+    const int nm = min(n_members[q], stride);
+    const int c = cutoffs[q];
+    const int32_t *mem = members + q * stride;
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < W32; w += gridDim.x * blockDim.x) {
+        uint32_t cnt[CLG_PLANES];
+#pragma unroll
+        for (int k = 0; k < CLG_PLANES; k++) cnt[k] = 0u;
+        for (int m = 0; m < nm; m++) {
+            const int g = mem[m];
+            uint32_t x = which ? covbits[(size_t)(g / 5) * W32 + w] : bits[(size_t)g * W32 + w];
+#pragma unroll
+            for (int k = 0; k < CLG_PLANES; k++) {   // ripple-carry add of one bit per read
+                const uint32_t carry = cnt[k] & x;
+                cnt[k] ^= x;
+                x = carry;
+            }
+        }
+        // count > c, 32 reads at once: the first plane (from the top) where count and c differ decides
+        uint32_t gt = 0u, eq = 0xffffffffu;
+        if (c < 0) gt = 0xffffffffu;                       // every read, covered or not (986-1003 with c < 0)
+        else if (c < (1 << CLG_PLANES) - 1) {
+#pragma unroll
+            for (int k = CLG_PLANES - 1; k >= 0; k--) {
+                const uint32_t cb = (c >> k) & 1 ? 0xffffffffu : 0u;
+                gt |= eq & cnt[k] & ~cb;
+                eq &= ~(cnt[k] ^ cb);
+            }
+        }
+        out[q * W32 + w] = gt;
+    }
+}
+
+// rank-order result words -> the reference's bitsets over MSA rows: one warp per 32 consecutive rows of one clique
+__global__ void __launch_bounds__(256)
+rr_k_rank_bits_to_rows(const uint32_t *__restrict__ in, int W32, int64_t n_cliques, const int32_t *__restrict__ rank_of_row,
+                       int R, int words32 /* 2 * sc */, uint32_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t q = warp / words32;
+    if (q >= n_cliques) return;                            // warp-uniform
+    const int w = (int)(warp - q * words32);
+    const int row = w * 32 + lane;
+    int bit = 0;
+    if (row < R) {
+        const int r = rank_of_row[row];
+        bit = (in[q * W32 + (r >> 5)] >> (r & 31)) & 1u;
+    }
+    const unsigned word = __ballot_sync(CLQ_FULL, bit);
+    if (lane == 0) out[q * words32 + w] = word;
+}
+
 // query bitsets [2][CLQ_QB][W32p], the per-chunk query masks and the union of the queries' coverage [W32p]
 size_t rr_cliquer_smem_bytes(int W32)
 {
@@ -224,5 +295,28 @@ cudaError_t rr_launch_cliquer(const uint32_t *bits, const uint32_t *covbits, con
     rr_k_cliquer_score<<<n_sm * 8, 128, 0, st>>>(cand, cap, counters, queries, gsize, lnf, threshold, hits, counters + 1);
     rr_count_launch(2);
     return cudaGetLastError();
+}
+// CliqueGroup (which = 0) or CliqueCoverage (which = 1) of n_cliques cliques: tmp [n_cliques][W32] rank-order words,
+// out [n_cliques][words32] words of 32 rows each (two per unsigned long of the reference)
+cudaError_t rr_launch_clique_members(const uint32_t *bits, const uint32_t *covbits, int W32, int64_t n_cliques,
+                                     const int32_t *members, int stride, const int32_t *n_members, const int32_t *cutoffs,
+                                     int which, const int32_t *rank_of_row, int R, int words32, uint32_t *tmp, uint32_t *out,
+                                     cudaStream_t st)
+{
+    if (n_cliques <= 0) return cudaSuccess;
+    for (int64_t q0 = 0; q0 < n_cliques; q0 += 65535) {   // grid.y limit
+        const int64_t nq = std::min<int64_t>(65535, n_cliques - q0);
+        dim3 grid((unsigned)std::max(1, std::min((W32 + 127) / 128, 64)), (unsigned)nq);
+        rr_k_clique_members<<<grid, 128, 0, st>>>(bits, covbits, W32, nq, members + q0 * stride, stride, n_members + q0,
+                                                  cutoffs + q0, which, tmp + q0 * W32);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        const int64_t warps = nq * words32;
+        rr_k_rank_bits_to_rows<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(tmp + q0 * W32, W32, nq, rank_of_row, R, words32,
+                                                                                  out + q0 * words32);
+        rr_count_launch(2);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 #endif

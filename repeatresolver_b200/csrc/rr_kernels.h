@@ -45,6 +45,11 @@ cudaError_t rr_launch_cliquer(const uint32_t *bits, const uint32_t *covbits, con
                               int W32, const int32_t *queries, int nq, int anfang, int ende, int min_s, double greedy,
                               double threshold, rr_clq_rec *cand, rr_clq_rec *hits, unsigned long long cap,
                               unsigned long long *counters, int n_sm, cudaStream_t st);
+// CliqueGroup / CliqueCoverage of a batch of cliques (rr_cliquer.cu)
+cudaError_t rr_launch_clique_members(const uint32_t *bits, const uint32_t *covbits, int W32, int64_t n_cliques,
+                                     const int32_t *members, int stride, const int32_t *n_members, const int32_t *cutoffs,
+                                     int which, const int32_t *rank_of_row, int R, int words32, uint32_t *tmp, uint32_t *out,
+                                     cudaStream_t st);
 
 // Relative_Vars (rr_relvars.cu): the all-pairs step on the packed rows of one part
 cudaError_t rr_launch_masked_sizes(const uint32_t *bits, const uint32_t *umask, int64_t nsets, int W32, int32_t *sizes, cudaStream_t st);

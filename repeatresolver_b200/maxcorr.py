@@ -199,6 +199,31 @@ class Packed:
                "rr_cliquer_batch")
         return members, scores, n, st.as_dict()
 
+    def clique_groups(self, cliques, cutoffs, want_groups=True, want_coverage=True):
+        """CliqueGroup / CliqueCoverage (RepeatResolver.c:976-1008, 1064-1096) for a batch of cliques on the device
+        (rr_clique_groups).  cliques: [n][stride] int32 in the reference's layout (members first, the first negative entry
+        ends a clique, 986-993) or a list of member lists; cutoffs: [n].  Returns (groups, coverage): uint64 [n][rows/64+1]
+        bitsets over the MSA's rows (read r = bit r % 64 of word r / 64, GrAdd 211-217), None for a kind not asked for."""
+        if isinstance(cliques, np.ndarray) and cliques.ndim == 2:
+            mem = np.ascontiguousarray(cliques, dtype=np.int32)
+            neg = mem < 0
+            nm = np.where(neg.any(1), neg.argmax(1), mem.shape[1]).astype(np.int32)
+        else:
+            lists = [[int(g) for g in c] for c in cliques]
+            stride = max([len(c) for c in lists] + [1])
+            mem = np.full((len(lists), stride), -1, dtype=np.int32)
+            for k, c in enumerate(lists):
+                mem[k, :len(c)] = c
+            nm = np.array([len(c) for c in lists], dtype=np.int32)
+        cut = np.ascontiguousarray(np.broadcast_to(np.asarray(cutoffs, dtype=np.int32), (len(mem),)), dtype=np.int32)
+        sc = self.rows // 64 + 1
+        G = np.zeros((len(mem), sc), dtype=np.uint64) if want_groups else None
+        Cv = np.zeros((len(mem), sc), dtype=np.uint64) if want_coverage else None
+        _check(lib.rr_clique_groups(self._h, len(mem), mem.ctypes.data, max(mem.shape[1], 1) if mem.ndim == 2 else 1, nm.ctypes.data,
+                                    cut.ctypes.data, G.ctypes.data if G is not None else None, Cv.ctypes.data if Cv is not None else None),
+               "rr_clique_groups")
+        return G, Cv
+
     def relative_vars(self, Unterteilung, u_no, MaxCorrs, cutoff, mingroup, with_pairs=False):
         """Relative_Vars (RepeatResolver.c:2424-2493) on this packed MSA, the part applied as a mask
         (rr_relative_vars_packed): ascending group ids"""
@@ -304,6 +329,23 @@ def Cliquer(packed, anfang, ende, mincov, maxclique, greedy, a):
     columns [anfang, ende) as the reference's int[maxclique+1] (Clique[0] = a, best partner first, -1 after the last)."""
     members, _, _, _ = packed.cliquer_batch([a], mincov, maxclique, greedy, anfang, ende)
     return members[0]
+
+
+def CliqueGroup(packed, Clique, c):
+    """RepeatResolver.c:976-1008 with the reference's argument order: the reads contained in more than c of the clique's
+    groups, as the reference's unsigned long[sc] bitset (uint64 array)."""
+    return packed.clique_groups(np.asarray(Clique, dtype=np.int32).reshape(1, -1), [c], want_coverage=False)[0][0]
+
+
+def CliqueCoverage(packed, Clique, c):
+    """RepeatResolver.c:1064-1096: the reads covered at more than c of the sites of the clique's groups (uint64 bitset)."""
+    return packed.clique_groups(np.asarray(Clique, dtype=np.int32).reshape(1, -1), [c], want_groups=False)[1][0]
+
+
+def group_reads(bitset, rows):
+    """the reads of a reference-layout bitset (GrElement, RepeatResolver.c:262-269) as ascending row numbers"""
+    bits = np.unpackbits(np.ascontiguousarray(bitset, dtype="<u8").view(np.uint8), bitorder="little")[:rows]
+    return np.flatnonzero(bits)
 
 
 def Group_Refinement_Cliques(packed, MaxCorrs, cutoff, anfang, ende, mincov, maxclique, greedy):

@@ -131,6 +131,20 @@ void emu_pair_counts(const uint32_t *bits, const uint32_t *covbits, int W32, lon
 {
     if (n > 0) emu_launch(dim3((unsigned)((n + 7) / 8)), 256, [&] { rr_k_pair_counts(bits, covbits, W32, n, gi, gj, out); });
 }
+/* CliqueGroup (which = 0) / CliqueCoverage (which = 1) as rr_launch_clique_members runs them: counts + threshold in rank
+ * order, then the reference's row-order words */
+void emu_clique_members(const uint32_t *bits, const uint32_t *covbits, int W32, long long n_cliques, const int32_t *members,
+                        int stride, const int32_t *n_members, const int32_t *cutoffs, int which, const int32_t *rank_of_row, int R,
+                        int words32, uint32_t *tmp, uint32_t *out)
+{
+    if (n_cliques <= 0) return;
+    emu_launch(dim3(2, (unsigned)n_cliques), 128, [&] {
+        rr_k_clique_members(bits, covbits, W32, n_cliques, members, stride, n_members, cutoffs, which, tmp);
+    });
+    emu_launch(dim3((unsigned)((n_cliques * words32 * 32 + 255) / 256)), 256, [&] {
+        rr_k_rank_bits_to_rows(tmp, W32, n_cliques, rank_of_row, R, words32, out);
+    });
+}
 void emu_general_break(const uint32_t *covbits, int W32, int N, int mincov, int32_t *breakcol)
 {
     if (N > 0) emu_launch(dim3((unsigned)((N + 7) / 8)), 256, [&] { rr_k_general_break(covbits, W32, N, mincov, breakcol); });

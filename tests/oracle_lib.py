@@ -183,3 +183,36 @@ def lnfact(n):
 def fmt_lines(M):
     """the reference's "%f\\n" text (MaxCorrsRausschreiben, 527-530)"""
     return "".join("%f\n" % v for v in M).encode()
+
+
+# ---- CliqueGroup / CliqueCoverage (RepeatResolver.c:976-1008, 1064-1096), plain numpy on the code matrix ----
+def clique_group(codes, clique, c):
+    """the reads contained in more than c of the clique's groups (976-1008): per read the number of members g with
+    Signatures[read][g / 5] == g % 5 (GrElement of Groups[g], filled at 405-411); bool [rows]"""
+    codes = np.asarray(codes)
+    score = np.zeros(codes.shape[0], dtype=np.int64)
+    for g in clique:
+        if g < 0:
+            break                                    # the first negative entry ends the clique (986-993)
+        score += codes[:, g // 5] == g % 5
+    return score > c
+
+
+def clique_coverage(codes, clique, c):
+    """the reads covered (a symbol, not a blank) at more than c of the sites of the clique's groups (1064-1096)"""
+    codes = np.asarray(codes)
+    score = np.zeros(codes.shape[0], dtype=np.int64)
+    for g in clique:
+        if g < 0:
+            break
+        score += codes[:, g // 5] < 5
+    return score > c
+
+
+def bitset_words(mask):
+    """a bool [rows] as the reference's group words: read r = bit r % 64 of word r / 64 (GrAdd 211-217), rows / 64 + 1 words"""
+    mask = np.asarray(mask, dtype=bool)
+    sc = len(mask) // 64 + 1
+    bits = np.zeros(sc * 64, dtype=np.uint8)
+    bits[:len(mask)] = mask
+    return np.packbits(bits, bitorder="little").view("<u8").copy()

@@ -594,3 +594,40 @@ def test_relvars_default_composition_with_the_emulated_kernels(emu_pack):
         S[pa, pb] = out[:, 0]
         got = rr.relative_vars_from_counts(M, p["gs"], len(sub), case["cutoff"], case["mingroup"], lambda s_: S)
         assert list(got) == want["vars"], u_no
+
+
+# ---- CliqueGroup / CliqueCoverage (rr_k_clique_members + rr_k_rank_bits_to_rows, csrc/rr_cliquer.cu) ---------------------
+def test_clique_group_kernels_against_the_oracle(emu_pack):
+    """bit-sliced member counts and the rank -> row transposition on a packed MSA with several 32-read words, cliques of 0 to
+    100 members (repeats allowed: the reference counts a group as often as it is listed), every kind of cutoff"""
+    rng = np.random.default_rng(5)
+    codes = two_family_msa(150, 60, seed=9)
+    R, N = codes.shape
+    p = device_pack(emu_pack, codes, 1)
+    W32 = p["W32"]
+    sizes = [0, 1, 2, 5, 12, 31, 32, 64, 100]
+    stride = 100
+    members = np.full((len(sizes) * 3, stride), -1, dtype=np.int32)
+    nm = np.zeros(len(members), dtype=np.int32)
+    cut = np.zeros(len(members), dtype=np.int32)
+    for k, n in enumerate(sizes * 3):
+        members[k, :n] = rng.integers(0, 5 * N, n)
+        if n >= 5:
+            members[k, 1] = members[k, 0]                                   # a repeated member
+        nm[k] = n
+        cut[k] = [-1, 0, max(n // 3, 1)][k // len(sizes)] if k % 7 else [127, n, n - 1][k // len(sizes)]
+    rank_of_row = np.zeros(R, dtype=np.int32)
+    rank_of_row[p["perm"]] = np.arange(R, dtype=np.int32)
+    sc = R // 64 + 1
+    vp, i, i64 = C.c_void_p, C.c_int, C.c_longlong
+    emu_pack.emu_clique_members.argtypes = [vp, vp, i, i64, vp, i, vp, vp, i, vp, i, i, vp, vp]
+    for which, fn in ((0, O.clique_group), (1, O.clique_coverage)):
+        tmp = np.zeros((len(members), W32), dtype=np.uint32)
+        out = np.full((len(members), 2 * sc), 0xdeadbeef, dtype=np.uint32)
+        emu_pack.emu_clique_members(p["bits"].ctypes.data, p["cov"].ctypes.data, W32, len(members), members.ctypes.data, stride,
+                                    nm.ctypes.data, cut.ctypes.data, which, rank_of_row.ctypes.data, R, 2 * sc, tmp.ctypes.data,
+                                    out.ctypes.data)
+        got = out.view("<u8")
+        for k in range(len(members)):
+            want = O.bitset_words(fn(codes, members[k, :nm[k]], int(cut[k])))
+            assert np.array_equal(got[k], want), (which, k, int(nm[k]), int(cut[k]))

@@ -123,3 +123,64 @@ def test_cliquer_argument_errors(deep):
         pk.cliquer_batch([0], 30, 0, 3.0)
     members, scores, n, st = pk.cliquer_batch([], 30, 30, 3.0)
     assert members.shape == (0, 31) and st["launches"] == 0
+
+
+# ---- CliqueGroup / CliqueCoverage (RepeatResolver.c:976-1008, 1064-1096) through rr_clique_groups ------------------------
+def _golden_words(hexes):
+    return np.array([int(h, 16) for h in hexes], dtype=np.uint64)
+
+
+@pytest.mark.parametrize("name", ["tree_small", "distributed_small", "saturated"])
+def test_clique_groups_golden(name):
+    """the device path against the committed output of the UNMODIFIED RepeatResolver.c (tests/golden/cliquegroup.json): the
+    clique comes from the product's own Cliquer, group and coverage words must be identical"""
+    from test_oracle_cliquegroup import cliquegroup_cases
+    case = cliquegroup_cases()[name]
+    codes = window_codes(golden_msa(name), case["von"], case["bis"])
+    pk = rr.Packed(rr.MSA.from_cells(codes, codes=True), 0)
+    for q, rec in case["queries"].items():
+        clique = rr.Cliquer(pk, 0, codes.shape[1], case["mincov"], case["maxclique"], case["greedy"], int(q))
+        n = int(np.argmax(clique < 0)) if (clique < 0).any() else len(clique)
+        assert list(clique[:n]) == rec["clique"]
+        cuts = sorted(int(c) for c in rec["cutoffs"])
+        G, V = pk.clique_groups(np.tile(clique, (len(cuts), 1)), cuts)
+        for k, c in enumerate(cuts):
+            assert np.array_equal(G[k], _golden_words(rec["cutoffs"][str(c)]["group"])), (name, q, c)
+            assert np.array_equal(V[k], _golden_words(rec["cutoffs"][str(c)]["coverage"])), (name, q, c)
+            assert np.array_equal(rr.CliqueGroup(pk, clique, c), G[k]) and np.array_equal(rr.CliqueCoverage(pk, clique, c), V[k])
+    pk.close()
+
+
+def test_clique_groups_deep_against_the_oracle(deep):
+    """several 32-read words per bitset, cliques of 0 .. 100 members (random, repeated and the product's own cliques), every
+    kind of cutoff; one output at a time as well"""
+    codes, o, pk = deep[0], deep[1], deep[2]
+    R, N = codes.shape
+    rng = np.random.default_rng(3)
+    cliques, cuts = [], []
+    for n in (0, 1, 2, 7, 30, 31, 64, 99, 100):
+        for c in (-1, 0, 1, n // 2, n - 1, n, 127, 1000):
+            m = [int(x) for x in rng.integers(0, 5 * N, n)]
+            if n > 3:
+                m[2] = m[0]
+            cliques.append(m)
+            cuts.append(c)
+    G, V = pk.clique_groups(cliques, cuts)
+    for k, (m, c) in enumerate(zip(cliques, cuts)):
+        assert np.array_equal(G[k], O.bitset_words(O.clique_group(codes, m, c))), (k, len(m), c)
+        assert np.array_equal(V[k], O.bitset_words(O.clique_coverage(codes, m, c))), (k, len(m), c)
+        assert list(rr.group_reads(G[k], R)) == list(np.flatnonzero(O.clique_group(codes, m, c)))
+    G2, none = pk.clique_groups(cliques, cuts, want_coverage=False)
+    assert none is None and np.array_equal(G2, G)
+    none, V2 = pk.clique_groups(cliques, cuts, want_groups=False)
+    assert none is None and np.array_equal(V2, V)
+
+
+def test_clique_groups_bad_arguments(deep):
+    pk = deep[2]
+    with pytest.raises(rr.RRError):
+        pk.clique_groups([[5 * deep[0].shape[1]]], [0])                      # group out of range
+    with pytest.raises(rr.RRError):
+        pk.clique_groups([list(range(101))], [0])                            # more members than the reference's limit (986)
+    G, V = pk.clique_groups(np.zeros((0, 4), dtype=np.int32), [])
+    assert G.shape[0] == 0 and V.shape[0] == 0
