@@ -40,7 +40,7 @@ WORKLOADS = {
 MINCOV = 30
 # dram__bytes_read.sum + dram__bytes_write.sum of the scan kernel, per launch, from the committed ncu capture
 # (profiles/); None until measured for that workload
-TRAFFIC = {"Tree_1perc_30000": 1.227e11}  # profiles/r2_final_ncu_full_summary.csv (full pass, --set full, cold L2): dram read 121.5 GB + write 1.2 GB, mxf4 operands
+TRAFFIC = {"Tree_1perc_30000": 1.174e11}  # profiles/r2_final_ncu_full_summary.csv (full pass, --set full, cold L2): dram read 116.4 GB + write 1.0 GB, mxf4 operands, CTA pairs
 
 
 def load_peaks():
@@ -319,6 +319,32 @@ def bench_cliquer(args, rr):
     if world == 1 and not args.no_cpu_baseline:
         cpu = cliquer_cpu_sample(np, g.codes(), queries, args.cpu_seconds)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    # the step that follows Cliquer in Group_Refinement (1662-1664): CliqueGroup + CliqueCoverage of every clique found
+    # (rr_clique_groups), cutoff = a third of the clique; HBM-bound: every member's bitset word is read once per kind
+    cg = None
+    if world == 1:
+        cut = np.maximum(n // 3, 1).astype(np.int32)
+        for _ in range(2):
+            pk.clique_groups(members, cut)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            Gq, Vq = pk.clique_groups(members, cut)
+        cg_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        cg_bytes = int(2 * (int(n.sum()) * w32 * 4 + len(n) * w32 * 4 * 2 + len(n) * (R // 64 + 1) * 8))
+        cg = {"cliques": int(len(n)), "members": int(n.sum()), "ms_per_call": cg_ms, "algorithmic_bytes": cg_bytes,
+              "gbs": cg_bytes / (cg_ms * 1e-3) / 1e9, "frac_of_hbm_peak": cg_bytes / (cg_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+              "note": "wall time of the C-ABI call (uploads of the clique lists, 4 kernels, download of the bitsets, host sync)"}
+        if not args.no_cpu_baseline:
+            import oracle_lib as O
+            codes_h = g.codes()
+            t0 = time.perf_counter()
+            k_cpu = 0
+            while time.perf_counter() - t0 < min(args.cpu_seconds, 3.0) and k_cpu < len(n):
+                O.clique_group(codes_h, members[k_cpu, :n[k_cpu]], int(cut[k_cpu]))
+                O.clique_coverage(codes_h, members[k_cpu, :n[k_cpu]], int(cut[k_cpu]))
+                k_cpu += 1
+            cg["cpu_port_cliques_per_s"] = k_cpu / (time.perf_counter() - t0)
+            cg["gpu_cliques_per_s"] = len(n) / (cg_ms * 1e-3)
     print(json.dumps({"metric": "Cliquer candidate pairs/sec (Group_Refinement)", "value": pairs / (kernel_ms * 1e-3),
                       "unit": "candidate pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                       "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -328,6 +354,7 @@ def bench_cliquer(args, rr):
                                  "l2": "candidate bitsets larger than L2 at config 2; smaller workloads are L2-resident"},
                       "candidates": st["candidates"], "hits": st["hits"], "host_evals": st["host_evals"],
                       "mean_clique": float(n.mean()) if len(n) else 0.0, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                      "clique_groups": cg,
                       "e2e": {"value": pairs / (call_ms * 1e-3), "unit": "candidate pairs/s", "ms_per_step": call_ms,
                               "h2d_bytes_per_step": int(4 * len(mine)), "d2h_bytes_per_step": int(32 * st["hits"] + 16)},
                       "gpu_launches": launches}))
