@@ -649,6 +649,10 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     int c[5];
                     jj += UM_SUB;
                     sp += UM_SUB;
+                    // the site's limits and mask, requested before the wait for its counts (behind the vote below they sit in
+                    // front of the first branch that needs them)
+                    const int4 m0 = *reinterpret_cast<const int4 *>(&sp->nq[0]);
+                    const int2 m1 = *reinterpret_cast<const int2 *>(&sp->nq[4]);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                     for (int b = 0; b < 5; b++) c[b] = MODE != 0 ? (int)__uint_as_float(v[b]) : (int)v[b];
@@ -669,8 +673,6 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     int mjw[5];
                     int vmask;
                     {
-                        const int4 m0 = *reinterpret_cast<const int4 *>(&sp->nq[0]);
-                        const int2 m1 = *reinterpret_cast<const int2 *>(&sp->nq[4]);
                         mjw[0] = m0.x; mjw[1] = m0.y; mjw[2] = m0.z; mjw[3] = m0.w; mjw[4] = m1.x;
                         vmask = m1.y;
                     }
