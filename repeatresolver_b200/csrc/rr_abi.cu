@@ -253,6 +253,8 @@ struct rr_packed {
     double *d_lnfact = nullptr;
     rr_best_t *d_best = nullptr;
     unsigned long long *d_counters = nullptr;
+    rr_cand_p *d_deferred = nullptr;      // candidates of the tcgen05 scan awaiting their exact evaluation (rr_device.cuh)
+    size_t deferred_cap = 0;
     std::vector<int32_t> h_start, h_end;  // spans in rank order: (length class, span start, span end)
     std::vector<int32_t> h_perm;          // rank -> row of the MSA
     int32_t class_start[RR_MAX_CLASSES + 1] = {0};   // rank boundaries of the length classes (rr_length_classes)
@@ -311,7 +313,7 @@ extern "C" void rr_packed_free(rr_packed *pk)
     rr_umma_free(pk->umma);
     rr_dev_free(pk->d_cells); rr_dev_free(pk->d_perm); rr_dev_free(pk->d_bits);
     rr_dev_free(pk->d_gsize); rr_dev_free(pk->d_coverage); rr_dev_free(pk->d_lnfact); rr_dev_free(pk->d_best);
-    rr_dev_free(pk->d_counters);
+    rr_dev_free(pk->d_counters); rr_dev_free(pk->d_deferred);
     pk->cache.sb.release();  // while the stream still exists
     if (pk->t0) { cudaEventDestroy(pk->t0); cudaEventDestroy(pk->t1); }
     if (pk->pe0) cudaEventDestroy(pk->pe0);
@@ -1505,6 +1507,21 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
     P.rb_lo = plan.rb_lo; P.rb_hi = plan.rb_hi; P.word_hi = sb.word_hi; P.word_lo = sb.word_lo;
     P.n_colblocks = plan.n_colblocks;
     P.n_classes = plan.n_classes;
+
+    if (variant != RR_VARIANT_BITSET && !(opts->flags & (RR_FLAG_NO_PRUNE | RR_DEBUG_MMA_ONLY))) {
+        // deferred exact evaluation: room for one candidate per ~2 500 pair tests of this part (config 2: one per 6 000
+        // survives tier 2), 20 bytes each; what does not fit is evaluated in place by the scan kernel
+        const size_t want = (size_t)std::min<int64_t>(std::max<int64_t>(plan.part_pairs / 2500, (int64_t)1 << 20), (int64_t)96 << 20);
+        if (want > pk->deferred_cap) {
+            rr_dev_free(pk->d_deferred);
+            pk->d_deferred = nullptr; pk->deferred_cap = 0;
+            if (rr_dev_malloc((void **)&pk->d_deferred, want * sizeof(rr_cand_p)) == cudaSuccess) pk->deferred_cap = want;
+            else cudaGetLastError();       // no list: the kernel evaluates in place
+        }
+        P.deferred = pk->d_deferred;
+        P.deferred_cap = pk->d_deferred ? pk->deferred_cap : 0;
+        P.defer_mode = 1;
+    }
 
     RR_CUDA(cudaEventRecord(e1, pk->st));
     int64_t executed = 0;

@@ -18,6 +18,8 @@ struct __align__(16) rr_best_t {
     unsigned long long p;  // partner group id, ~0ull = none
 };
 
+struct rr_cand_p;
+
 // everything a scan kernel needs, passed by value (kernel parameter)
 struct rr_scan_params {
     int R, N;                    // rows kept, columns
@@ -43,6 +45,13 @@ struct rr_scan_params {
     const int32_t *word_lo;      // [n_classes][n_colblocks] inclusive lower u32-word bound      length class (rr_plan.h)
     int n_colblocks;
     int n_classes;
+    // deferred exact evaluation (tcgen05 kernel): what survives tier 2 raises the groups' maxima by a rigorous LOWER bound
+    // of its score (a partner-less entry of best[], like an exchanged threshold) and is appended here; rr_k_deferred_exact
+    // evaluates the list after the scan.  defer_mode 0: evaluate in place (RR_FLAG_NO_PRUNE, no list); 1: raise + append
+    // (in place once the list is full); 2: raise only (seeding passes: their pairs come again in the full pass)
+    rr_cand_p *deferred;
+    unsigned long long deferred_cap;
+    int defer_mode;
 };
 
 #ifndef RR_CPU_EMU
@@ -95,6 +104,22 @@ __device__ __forceinline__ void rr_best_update(rr_best_t *best, int g, double Z,
     nw.p = (unsigned long long)(unsigned int)partner;
     rr_best_t cur = rr_best_load(best + g);
     while (nw.z > cur.z || (nw.z == cur.z && nw.p < cur.p)) {
+        rr_best_t old;
+        if (rr_cas128(best + g, cur, nw, &old)) break;
+        cur = old;
+    }
+}
+
+// a LOWER bound of a score some pair of group g attains: raises the group's maximum as a partner-less entry (it prunes
+// like a maximum, loses every tie against a real pair and is overwritten by the pair's exact score, which is larger)
+__device__ __forceinline__ void rr_best_raise(rr_best_t *best, int g, double lb)
+{
+    if (!(lb > 0.0)) return;
+    rr_best_t nw;
+    nw.z = (unsigned long long)__double_as_longlong(lb);
+    nw.p = ~0ull;
+    rr_best_t cur = rr_best_load(best + g);
+    while (nw.z > cur.z) {
         rr_best_t old;
         if (rr_cas128(best + g, cur, nw, &old)) break;
         cur = old;
@@ -283,6 +308,57 @@ __device__ __forceinline__ bool rr_tier2(const LT &T, unsigned s, unsigned gr1, 
     return !(rr_bound_effective(U2) < thr);
 }
 
+// Tier 2 with both ends: the pair survives unless an UPPER bound of its score is below thr (as rr_tier2), and *zlb receives
+// a LOWER bound of its final score (0 if none is available), i.e. an upper bound of P[X >= s] = pmf(s) * (1 + r1 + r1 r2 +
+// ...): the term ratios r_k = (gr1 - x)(gr2 - x) / ((x + 1)(cov + x + 1 - gr1 - gr2)) fall with x, so what lies behind the
+// last term added is at most term * r / (1 - r) with the next ratio r < 1.  The upper sum takes every factor rounded up;
+// the final value is lowered by 2e-5 relative + 2e-5 (FP32 accumulation over <= 24 factors of (1 + 2^-23)(1 + 1e-5), log2f
+// to 2 ulp; the exact score's own error is orders below) and clamped at 98: a raw score above 98 becomes 98 + F > 98 (432).
+template <class LT>
+__device__ __forceinline__ bool rr_tier2_interval(const LT &T, unsigned s, unsigned gr1, unsigned gr2, unsigned cov, double thr,
+                                                  double *zlb)
+{
+    *zlb = 0.0;
+    const unsigned hi = gr1 < gr2 ? gr1 : gr2;
+    const unsigned lo = gr1 + gr2 > cov ? gr1 + gr2 - cov : 0u;
+    int xm = (int)__fdividef((float)gr1 * (float)gr2, (float)cov) - 3;
+    unsigned x0 = xm > (int)s ? (unsigned)xm : s;
+    if (x0 > hi) x0 = hi;
+    if (x0 < lo) x0 = lo;
+    const double lp = rr_lnchoose_t(T, gr2, x0) + rr_lnchoose_t(T, cov - gr2, gr1 - x0) - rr_lnchoose_t(T, cov, gr1);
+    float S = 1.0f, term = 1.0f, Su = 1.0f, termu = 1.0f, r_next = 0.0f;
+    unsigned x = x0;
+#pragma unroll 1
+    for (int m = 0; m < 24; m++, x++) {
+        if (x >= hi) { r_next = 0.0f; break; }
+        const float num = (float)(gr2 - x) * (float)(gr1 - x);
+        const float den = (float)(x + 1u) * (float)((cov + x + 1u) - gr1 - gr2);
+        const float r = __fdividef(num, den);
+        r_next = r * 1.00002f;             // ratio of the term after `termu` to it, rounded up; ratios fall with x
+        if (term < 1e-3f * S) break;
+        term *= r * 0.99999f;
+        termu *= r * 1.00002f;
+        S += term;
+        Su += termu;
+        if (m == 23) {                     // ran out of terms: the ratio behind the last one
+            const unsigned x1 = x + 1u;
+            r_next = x1 >= hi ? 0.0f
+                              : __fdividef((float)(gr2 - x1) * (float)(gr1 - x1), (float)(x1 + 1u) * (float)((cov + x1 + 1u) - gr1 - gr2)) * 1.00002f;
+        }
+    }
+    const double U2 = -RR_LOG10E * lp - (double)(__log2f(S) * 0.30103f * 0.99999f) + 2e-5;
+    const bool keep = !(thr > 0.0) || !(rr_bound_effective(U2) < thr);
+    if (keep && x0 == s && r_next < 0.9f) {
+        // P[X >= s] <= pmf(s) * (Su + termu * r / (1 - r))
+        const float tail = termu * r_next / (1.0f - r_next) * 1.00002f;
+        const float Sall = (Su + tail) * 1.00002f;
+        double L = -RR_LOG10E * lp - (double)(__log2f(Sall) * 0.30103f * 1.00002f);
+        L = L * (1.0 - 2e-5) - 2e-5;
+        *zlb = L > RR_SATURATION_START ? RR_SATURATION_START : (L > 0.0 ? L : 0.0);
+    }
+    return keep;
+}
+
 __device__ __forceinline__ void rr_queue_push(rr_cand_p *q, int &count, bool need, const rr_cand &c, int lane)
 {
     const unsigned mask = __ballot_sync(0xffffffffu, need);
@@ -313,7 +389,10 @@ static __device__ __noinline__ void rr_drain_exact(const rr_scan_params &P, rr_c
     }
 }
 
-// tier 2 on queued tier-1 survivors; what survives moves on to the exact queue
+// tier 2 on queued tier-1 survivors; what survives moves on to the exact queue - or, with deferred evaluation
+// (rr_scan_params::defer_mode), raises the two groups' maxima by a lower bound of its score and goes to the global list
+// that rr_k_deferred_exact evaluates after the scan.  An epilogue warp then never sits in the FP64 series while the other
+// warps of its CTA pair wait for it at the next tile.
 template <class LT>
 static __device__ __noinline__ void rr_drain_tier2(const rr_scan_params &P, const LT &T, rr_cand_p *q1, int &c1,
                                                    rr_cand_p *q2, int &c2, int lane, unsigned &n_tier2, unsigned &n_exact,
@@ -323,6 +402,7 @@ static __device__ __noinline__ void rr_drain_tier2(const rr_scan_params &P, cons
         __syncwarp();
         const int take = c1 < 32 ? c1 : 32;
         bool need = false;
+        double zlb = 0.0;
         rr_cand c;
         c.s = c.gr1 = c.gr2 = c.cov = 0u; c.gi = c.gj = 0;
         if (lane < take) {
@@ -331,11 +411,26 @@ static __device__ __noinline__ void rr_drain_tier2(const rr_scan_params &P, cons
             need = true;
             if (!(P.flags & RR_FLAG_NO_PRUNE)) {
                 const double thr = fmin(rr_best_value(P.best + c.gi), rr_best_value(P.best + c.gj));
-                need = rr_tier2(T, c.s, c.gr1, c.gr2, c.cov, thr);
+                need = rr_tier2_interval(T, c.s, c.gr1, c.gr2, c.cov, thr, &zlb);
             }
         }
         c1 -= take;
         __syncwarp();
+        if (P.defer_mode != 0) {
+            if (need && zlb > 0.0) { rr_best_raise(P.best, c.gi, zlb); rr_best_raise(P.best, c.gj, zlb); }
+            if (P.defer_mode == 2) need = false;            // seeding pass: thresholds only, the pair comes again
+            else {
+                const unsigned mask = __ballot_sync(0xffffffffu, need);
+                if (mask != 0u) {
+                    unsigned long long base = 0ull;
+                    if (lane == 0) base = atomicAdd(P.counters + 5, (unsigned long long)__popc(mask));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    const unsigned long long idx = base + (unsigned long long)__popc(mask & ((1u << lane) - 1u));
+                    if (need && idx < P.deferred_cap) { P.deferred[idx] = rr_cand_pack(c); need = false; }
+                    // (entries past the capacity are evaluated in place, below)
+                }
+            }
+        }
         rr_queue_push(q2, c2, need, c, lane);
         if (c2 >= 32) rr_drain_exact(P, q2, c2, lane, n_exact, false);
     }

@@ -803,6 +803,37 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
 }
 
+// ---- deferred exact evaluation: the candidates the scan has listed (rr_drain_tier2), one per thread ----------------
+// Every listed pair survived tiers 1 and 2 against the maxima of its time; by now the maxima hold lower bounds of every
+// listed pair's score (and, as this kernel proceeds, exact scores), so tier 2 is asked again before the FP64 series.
+__global__ void __launch_bounds__(128) rr_k_deferred_exact(const rr_scan_params P)
+{
+    const unsigned long long n = min(P.counters[5], P.deferred_cap);
+    rr_lnf_global LG;
+    LG.gmem = P.lnfact;
+    unsigned n_exact = 0, n_tier2 = 0;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (unsigned long long)gridDim.x * blockDim.x) {
+        const rr_cand c = rr_cand_unpack(P.deferred[t]);
+        const double thr = fmin(rr_best_value(P.best + c.gi), rr_best_value(P.best + c.gj));
+        n_tier2++;
+        if (!rr_tier2(LG, c.s, c.gr1, c.gr2, c.cov, thr)) continue;
+        n_exact++;
+        const double Z = rr_positive_significance(P.lnfact, c.s, c.gr1, c.gr2, c.cov, __ldg(P.gsize + c.gi), __ldg(P.gsize + c.gj));
+        if (Z > 0.0) {
+            if (Z >= rr_best_value(P.best + c.gi)) rr_best_update(P.best, c.gi, Z, c.gj);
+            if (Z >= rr_best_value(P.best + c.gj)) rr_best_update(P.best, c.gj, Z, c.gi);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        n_exact += __shfl_xor_sync(0xffffffffu, n_exact, o);
+        n_tier2 += __shfl_xor_sync(0xffffffffu, n_tier2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_exact) atomicAdd(P.counters + 1, (unsigned long long)n_exact);
+        if (n_tier2) atomicAdd(P.counters + 4, (unsigned long long)n_tier2);
+    }
+}
+
 // ---- A operand: gather the row sites' groups from xb into 32-row slabs -----------------------
 __global__ void __launch_bounds__(256) rr_k_build_xa(const int8_t *__restrict__ xb, const int32_t *__restrict__ rowsites,
                                                       int64_t n_rows, int64_t Kp /* bytes per row */, int8_t *__restrict__ xa)
@@ -981,6 +1012,13 @@ static cudaError_t um_launch(int mode, bool all_smem, bool dump, int n_units, si
     return all_smem ? um_launch_one<true, 0, false>(n_units, smem_bytes, st, map_a, map_b, prm) : um_launch_one<false, 0, false>(n_units, smem_bytes, st, map_a, map_b, prm);
 }
 
+static cudaError_t rr_launch_deferred_exact(const rr_scan_params &P, int n_sm, cudaStream_t st)
+{
+    rr_k_deferred_exact<<<n_sm * 16, 128, 0, st>>>(P);
+    rr_count_launch(1);
+    return cudaGetLastError();
+}
+
 int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &P, rr_plan &plan, int n_sm, cudaStream_t st)
 {
     int rc;
@@ -1155,6 +1193,7 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
     if ((rc = um_fill_params(S, P, plan, U, smem_bytes, all_smem))) return rc;
     if (seeding && S->n_seed > 0) {
         um_params V = U;
+        if (V.P.defer_mode) V.P.defer_mode = 2;   // thresholds only: the seed tiles' pairs come again in the full pass
         if (S->n_preseed > 0) {
             V.units = S->d_units + S->n_units + S->n_seed;
             V.n_units = S->n_preseed;
@@ -1169,6 +1208,8 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
     }
     if (P.flags & RR_FLAG_SEED_ONLY) return RR_OK;
     UM_CUDA(um_launch(mode, all_smem, false, U.n_units, smem_bytes, st, S->map_a, S->map_b, U));
+    // the exact scores of the candidates the full pass has listed (rr_device.cuh: defer_mode)
+    if (P.defer_mode == 1 && P.deferred_cap > 0) UM_CUDA(rr_launch_deferred_exact(P, n_sm, st));
     return RR_OK;
 }
 

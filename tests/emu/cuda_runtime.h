@@ -74,6 +74,20 @@ template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int lane_ma
     memcpy(&out, &raw, sizeof(T));
     return out;
 }
+template <typename T> static inline T __shfl_sync(unsigned, T v, int src_lane)
+{
+    static_assert(sizeof(T) <= 8, "one 64-bit slot per lane");
+    emu_warp *w = emu_my_warp();
+    unsigned long long raw = 0;
+    memcpy(&raw, &v, sizeof(T));
+    w->buf[threadIdx.x & 31] = raw;
+    pthread_barrier_wait(&w->bar);
+    raw = w->buf[(unsigned)src_lane & 31u];
+    pthread_barrier_wait(&w->bar);
+    T out;
+    memcpy(&out, &raw, sizeof(T));
+    return out;
+}
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
 static inline void __syncwarp() { pthread_barrier_wait(&emu_my_warp()->bar); }
 static inline unsigned __activemask() { return 0xffffffffu; }     /* only meaningful where the whole warp is active */

@@ -110,6 +110,15 @@ void emu_tiers(const double *lnf, int max_cov, long long n, const uint32_t *quad
     }
 }
 
+/* rr_tier2_interval (rr_device.cuh): keep[i] = the pair survives against best[i]; zlb[i] = the lower bound of its score the
+ * scan kernel raises the groups' maxima by (0 = none) */
+void emu_tier2_interval(const double *lnf, long long n, const uint32_t *quads, const double *best, unsigned char *keep, double *zlb)
+{
+    rr_lnf_global T2{lnf};
+    for (long long i = 0; i < n; i++)
+        keep[i] = rr_tier2_interval(T2, quads[4 * i], quads[4 * i + 1], quads[4 * i + 2], quads[4 * i + 3], best[i], zlb + i) ? 1 : 0;
+}
+
 /* the packing kernels of rr_pack.cu with the grids their launchers use */
 void emu_row_spans(const uint8_t *cells, int R, int N, int codes, int32_t *start, int32_t *end, int32_t *ncov)
 {

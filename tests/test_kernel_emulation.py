@@ -569,6 +569,56 @@ def test_pruning_tiers_of_the_fused_epilogue_never_drop_a_pair_that_matters(emu)
         assert k1[unsat].mean() < 0.5 and (k1 & k2)[unsat].mean() < 0.3, (max_cov, k1[unsat].mean(), (k1 & k2)[unsat].mean())
 
 
+def test_lower_bound_of_the_deferred_evaluation_is_sound_and_tight(emu):
+    """rr_tier2_interval (rr_device.cuh): the value the scan kernel raises a group's maximum by BEFORE the pair's exact
+    score exists must never exceed that score (it prunes other pairs and must lose against the pair's own exact value),
+    at depths up to 40 000 reads, near the mean, in the tail and in the saturated range; and it must be tight where the
+    score matters (within 1e-3 relative + 1e-3 for most pairs above the mean), or the thresholds it gives are useless"""
+    vp = C.c_void_p
+    emu.emu_tier2_interval.argtypes = [vp, C.c_longlong, vp, vp, vp, vp]
+    rng = np.random.default_rng(29)
+    for max_cov in (60, 300, 4000, 40000):
+        lnf = rr.lnfact_table(max_cov + 2)
+        quads, scores = [], []
+        while len(quads) < 5000:
+            cov = int(rng.integers(max(2, max_cov // 50), max_cov + 1))
+            gr1 = int(rng.integers(1, cov + 1)) if rng.random() < 0.5 else int(rng.integers(1, max(2, cov // 20)))
+            gr2 = int(rng.integers(1, cov + 1)) if rng.random() < 0.5 else int(rng.integers(1, max(2, cov // 20)))
+            lo, hi = max(1, gr1 + gr2 - cov), min(gr1, gr2)
+            if lo > hi:
+                continue
+            mean = gr1 * gr2 / cov
+            kind = rng.random()
+            if kind < 0.5:
+                s = int(min(hi, max(lo, round(mean + abs(rng.normal()) * 4 * (mean ** 0.5 + 1)))))   # in the upper tail
+            elif kind < 0.8:
+                s = int(rng.integers(lo, hi + 1))                                                    # anywhere, incl. saturated
+            else:
+                s = hi                                                                               # the end of the support
+            quads.append((s, gr1, gr2, cov))
+            scores.append(O.score(s, gr1, gr2, cov, gr1 + 3, gr2 + 5))
+        q = np.array(quads, dtype=np.uint32)
+        z = np.array(scores)
+        keep = np.zeros(len(q), dtype=np.uint8)
+        zlb = np.zeros(len(q), dtype=np.float64)
+        best = np.zeros(len(q), dtype=np.float64)                         # no maximum yet: everything survives
+        emu.emu_tier2_interval(lnf.ctypes.data, len(q), q.ctypes.data, best.ctypes.data, keep.ctypes.data, zlb.ctypes.data)
+        assert keep.all()
+        assert (zlb >= 0).all() and (zlb <= 98.0).all()
+        bad = zlb > z
+        assert not bad.any(), (max_cov, q[bad][:5], zlb[bad][:5], z[bad][:5])
+        assert (zlb < z)[zlb > 0].all()                                   # strictly below: the exact value must win the update
+        useful = (z > 1.0) & (z < 98.0)
+        tight = zlb[useful] >= z[useful] * (1 - 1e-3) - 1e-3
+        assert tight.mean() > 0.9, (max_cov, tight.mean())
+        sat = z >= 98.0
+        if sat.any():
+            assert (zlb[sat] == 98.0).mean() > 0.9                        # saturated scores give the clamp (432: 98 + F > 98)
+        # against a maximum equal to the pair's own score the pair must survive (it may tie or beat it)
+        emu.emu_tier2_interval(lnf.ctypes.data, len(q), q.ctypes.data, np.ascontiguousarray(z).ctypes.data, keep.ctypes.data, zlb.ctypes.data)
+        assert keep[z > 0].all()
+
+
 def test_relvars_default_composition_with_the_emulated_kernels(emu_pack):
     """what rr_relative_vars does by default, step for step, with its device steps emulated: the part's rows packed as an
     MSA of their own (row spans, bitsets, sizes = |G & U|), |Gi & Gj & U| as the first count of rr_k_pair_counts for
