@@ -1127,7 +1127,11 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
         // exchange the seeded maxima (all-reduce MAX) before their full passes.
         // The seeding pass itself starts from zero thresholds; a pre-seed over every PRESEED-th seed pair
         // takes that warm-up on ~1/512 of the row tiles instead of 1/64.
-        constexpr int SEED = 64, PRESEED = 8;
+#ifndef RR_UM_SEED
+#define RR_UM_SEED 64        // measured with deferred evaluation: 32 -> 109.7 ms, 16 -> 112.7, 128 -> 110.3 against 109.2
+#define RR_UM_PRESEED 8      // no pre-seed launch at all (0): 115.4 ms
+#endif
+        constexpr int SEED = RR_UM_SEED, PRESEED = RR_UM_PRESEED;   // PRESEED 0: no pre-seed launch
         std::vector<um_unit> seed_units, preseed_units;
         if (plan.n_rowblocks >= 2 * SEED) {
             std::vector<keyed> ks;
@@ -1150,7 +1154,7 @@ int rr_umma_scan(rr_umma_state *&S, int mode, uint64_t plan_id, rr_scan_params &
             std::sort(ks.begin(), ks.end(), [](const keyed &x, const keyed &y) { return x.key < y.key; });
             for (const keyed &k : ks) {
                 seed_units.push_back(k.u);
-                if ((k.u.rt0 / (2 * SEED)) % PRESEED == 0) preseed_units.push_back(k.u);
+                if (PRESEED > 0 && (k.u.rt0 / (2 * SEED)) % (PRESEED > 0 ? PRESEED : 1) == 0) preseed_units.push_back(k.u);
             }
         }
         seed_units.insert(seed_units.end(), preseed_units.begin(), preseed_units.end());  // stored behind the seed list
