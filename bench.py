@@ -40,7 +40,7 @@ WORKLOADS = {
 MINCOV = 30
 # dram__bytes_read.sum + dram__bytes_write.sum of the scan kernel, per launch, from the committed ncu capture
 # (profiles/); None until measured for that workload
-TRAFFIC = {"Tree_1perc_30000": 1.174e11}  # profiles/r2_final_ncu_full_summary.csv (full pass, --set full, cold L2): dram read 116.4 GB + write 1.0 GB, mxf4 operands, CTA pairs
+TRAFFIC = {"Tree_1perc_30000": 1.048e11}  # profiles/r2_final_ncu_full_summary.csv (full pass, --set full, cold L2): dram read 103.6 GB + write 1.2 GB, mxf4 operands, CTA pairs
 
 
 def load_peaks():

@@ -156,7 +156,9 @@ __device__ __forceinline__ double rr_pair_score(const rr_scan_params &P, unsigne
 //   tier 3  the exact score (exp + hypergeometric series + log10)            10^3..10^4 FP64 ops
 // Tiers 2 and 3 are needed by a few percent / per mille of the pairs.  Evaluating them in place
 // would serialise the warp behind single lanes, so survivors are pushed into per-warp shared
-// memory queues and evaluated 32 at a time, one candidate per lane.
+// memory queues and evaluated 32 at a time, one candidate per lane.  In the tcgen05 kernel tier 3 does
+// not run inside the scan at all (rr_scan_params::defer_mode): tier 2 leaves a lower bound of the score
+// in the two maxima and the candidate in a list that a dense kernel evaluates after the scan.
 struct __align__(8) rr_cand {
     uint32_t s, gr1, gr2, cov;   // the four counts of PositiveSignificance (423-426)
     int32_t gi, gj;              // row group, column group
