@@ -20,6 +20,11 @@ extern "C" {
  * force the list-overflow retry path. */
 void rr_debug_set_cliquer_cap(unsigned long long cap);
 
+/* capacity (candidates of 20 bytes) of the list in which the tcgen05 scan leaves the pairs whose exact score it evaluates
+ * after the scan (csrc/rr_device.cuh: defer_mode); 0 restores the sizing from the plan.  Tests lower it so that the list
+ * overflows and the kernel's in-place evaluation takes over in the middle of a scan. */
+void rr_debug_set_deferred_cap(unsigned long long cap);
+
 /* The raw accumulator of one (row tile, column tile) pair of the tcgen05 scan kernel, read back from TMEM by the
  * kernel's own epilogue after its own producer / MMA code (a separate instantiation of the same kernel template that
  * also stores what it reads).  Call after rr_scan(pk, opts) with a tcgen05 variant and the same opts.

@@ -901,6 +901,11 @@ extern "C" int rr_cliquer_from_hits(int64_t nq, const int32_t *queries, int64_t 
 
 // capacity of the candidate / hit lists of rr_cliquer_batch (records of 32 bytes); tests lower it to force the retry path
 static std::atomic<unsigned long long> g_cliquer_cap{1ull << 24};
+// capacity (candidates) of the deferred-evaluation list of the tcgen05 scan; 0 = sized from the plan.  Tests lower it so
+// that the list overflows and the kernel's in-place evaluation takes over mid-scan.
+static unsigned long long g_deferred_cap = 0;
+extern "C" void rr_debug_set_deferred_cap(unsigned long long cap) { g_deferred_cap = cap; }
+
 extern "C" void rr_debug_set_cliquer_cap(unsigned long long cap) { g_cliquer_cap = cap ? cap : (1ull << 24); }
 
 static void clq_release(int32_t *q, unsigned long long *c, rr_clq_rec *a, rr_clq_rec *b, cudaEvent_t e0, cudaEvent_t e1)
@@ -1511,7 +1516,8 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
     if (variant != RR_VARIANT_BITSET && !(opts->flags & (RR_FLAG_NO_PRUNE | RR_DEBUG_MMA_ONLY))) {
         // deferred exact evaluation: room for one candidate per ~2 500 pair tests of this part (config 2: one per 6 000
         // survives tier 2), 20 bytes each; what does not fit is evaluated in place by the scan kernel
-        const size_t want = (size_t)std::min<int64_t>(std::max<int64_t>(plan.part_pairs / 2500, (int64_t)1 << 20), (int64_t)96 << 20);
+        size_t want = (size_t)std::min<int64_t>(std::max<int64_t>(plan.part_pairs / 2500, (int64_t)1 << 20), (int64_t)96 << 20);
+        if (g_deferred_cap) want = (size_t)g_deferred_cap;               // test hook: a list that overflows
         if (want > pk->deferred_cap) {
             rr_dev_free(pk->d_deferred);
             pk->d_deferred = nullptr; pk->deferred_cap = 0;
@@ -1519,7 +1525,7 @@ extern "C" int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *s
             else cudaGetLastError();       // no list: the kernel evaluates in place
         }
         P.deferred = pk->d_deferred;
-        P.deferred_cap = pk->d_deferred ? pk->deferred_cap : 0;
+        P.deferred_cap = pk->d_deferred ? std::min(pk->deferred_cap, want) : 0;
         P.defer_mode = 1;
     }
 

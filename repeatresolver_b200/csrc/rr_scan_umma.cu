@@ -82,16 +82,6 @@ constexpr int UM_ACC_STRIDE = 256;               // TMEM columns between the two
 constexpr int UM_SF_COL = 240;                   // 16 spare TMEM columns behind accumulator 0: unit block scales (mxf4)
 constexpr int UM_QSHIFT = 2;                     // accumulators hold count << UM_QSHIFT (operand elements are 2); rr_tier1_q assumes 2
 constexpr int UM_CMASK_BYTES = 48;               // admissibility masks of a tile's column sites (one byte per site)
-// back-off (ns) between polls of an mbarrier: a waiting warp shares its scheduler with epilogue warps that still work
-#ifndef RR_UM_NS_EPI
-#define RR_UM_NS_EPI 0       // epilogue warps waiting for a tile's metadata / accumulator (0: no back-off)
-#endif
-#ifndef RR_UM_UNIT_FLUSH
-#define RR_UM_UNIT_FLUSH 0   // 1: evaluate every queued candidate at the end of each work unit
-#endif
-#ifndef RR_UM_NS_META
-#define RR_UM_NS_META 64     // the converter warp (a whole tile time ahead of the epilogue)
-#endif
 
 struct __align__(16) um_wsite {                   // one column site: read by the whole warp as two broadcasts (16 + 8 bytes)
     int nq[5];                                    // running maxima as fixed-point tier-1 limits (rr_thr_q); inadmissible: never
@@ -183,11 +173,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 __device__ __forceinline__ void mbar_wait_sleep(unsigned long long *bar, uint32_t parity, unsigned ns)
 {
     while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
-}
-__device__ __forceinline__ void mbar_wait_epi(unsigned long long *bar, uint32_t parity)
-{
-    if constexpr (RR_UM_NS_EPI > 0) mbar_wait_sleep(bar, parity, RR_UM_NS_EPI);
-    else mbar_wait(bar, parity);
 }
 // plain bulk copy global -> shared (16-byte aligned on both sides, size a multiple of 16), completion on an mbarrier
 __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes, unsigned long long *bar)
@@ -548,8 +533,8 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const uint32_t ph = (tix >> 1) & 1;
                 const um_thr_buf &B = T->thr[tb];
                 um_tile_meta &TM = T->tmeta[tb];
-                mbar_wait_sleep(&T->mempty[tb], ph ^ 1, RR_UM_NS_META);   // the epilogue is done with the tile that used this slot
-                mbar_wait_sleep(&T->bfull[tb], ph, RR_UM_NS_META);        // the producer's copy has landed
+                mbar_wait_sleep(&T->mempty[tb], ph ^ 1, 64);   // the epilogue is done with the tile that used this slot
+                mbar_wait_sleep(&T->bfull[tb], ph, 64);        // the producer's copy has landed
                 __syncwarp();
                 const int n_in = min(UM_COL_SITES, P.N - ct * UM_COL_SITES);   // column sites of the tile inside the MSA
 #pragma unroll 1
@@ -611,14 +596,14 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 int nq_i = um_nq_hi(row_hi, no_prune, qscale);
                 const int tb = tix & 1;
                 um_tile_meta &TM = T->tmeta[tb];
-                mbar_wait_epi(&T->mfull[tb], (tix >> 1) & 1);
+                mbar_wait(&T->mfull[tb], (tix >> 1) & 1);
                 has_counts = TM.has_counts != 0;
                 // the row group's maximum for the next tile of this unit (consumed at the top of the next iteration)
                 if (row_ok && ct + 1 < un.ct1) row_hi = um_best_hi(P.best + gi);
 
                 const int acc = tile & 1;
                 if (has_counts) {
-                    mbar_wait_epi(&T->tfull[acc], (tile >> 1) & 1);
+                    mbar_wait(&T->tfull[acc], (tile >> 1) & 1);
                     tc_fence_after();
                 }
                 const int t_end = mma_only ? 0 : min(UM_COL_SITES, P.N - jsite0);
@@ -774,9 +759,7 @@ rr_k_scan_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
                 tile++;
             }
-            // candidates stay queued across units (entries carry their group ids): evaluating what a unit leaves behind at
-            // once would run tiers 2 and 3 with a lane or two per batch
-            if (RR_UM_UNIT_FLUSH) rr_drain_tier2(P, LG, q1, c1n, q2, c2n, lane, n_tier2, n_exact, true);
+            // (candidates stay queued across units - entries carry their group ids -, so tier 2 always runs 32 at a time)
         }
         rr_drain_tier2(P, LG, q1, c1n, q2, c2n, lane, n_tier2, n_exact, true);
 

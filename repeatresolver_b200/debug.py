@@ -14,6 +14,11 @@ def set_cliquer_cap(cap):
     lib.rr_debug_set_cliquer_cap(int(cap))
 
 
+def set_deferred_cap(cap):
+    """capacity (candidates) of the deferred-evaluation list of the tcgen05 scan; 0 restores the default"""
+    lib.rr_debug_set_deferred_cap(int(cap))
+
+
 def umma_tiles(packed, mincov=30, variant="umma_mxf4", part_index=0, part_count=1):
     """(row tiles, column tiles) of the plan of the last scan with these options"""
     opts = ScanOpts(mincov, VARIANTS[variant], 0, part_index, part_count)

@@ -412,6 +412,40 @@ def test_one_process_per_gpu_shares_the_packing(n_gpus):
     assert r.returncode == 0 and "DIST_OK" in r.stdout, (r.stdout[-800:], r.stderr[-1500:])
 
 
+@pytest.mark.parametrize("variant", [v for v in VARIANTS if v != "bitset"])
+def test_deferred_exact_evaluation_and_its_overflow(variant):
+    """the tcgen05 scan leaves the exact scores to a kernel behind it (a list of candidates, lower bounds in the maxima
+    meanwhile): the result must be bit-identical to the exhaustive scan (which evaluates in place), every group with a
+    maximum must have a partner (no bound may survive as a value), the number of exact evaluations must be far below the
+    in-place count (and about the same from scan to scan: it depends on the order in which the list is evaluated only
+    through ties with the final bounds), and a list that overflows in the middle of the scan (debug hook) must change
+    nothing"""
+    g = rr.MsaGen(type="Tree", copies=25, coverage=40, repeat_len=6000, diff=0.01, seed=1004)
+    msa = rr.MSA.alloc(g.rows, g.cols, codes=True)
+    g.codes(out=msa.cells())
+    pk = rr.Packed(msa, 0)
+    st0 = pk.scan(mincov=30, variant=variant, flags=rr.FLAG_NO_PRUNE)
+    M0, A0 = pk.fetch()
+    s1 = pk.scan(mincov=30, variant=variant)
+    M1, A1 = pk.fetch()
+    s2 = pk.scan(mincov=30, variant=variant)
+    M2, A2 = pk.fetch()
+    assert (M1 == M0).all() and (A1 == A0).all() and (M2 == M0).all() and (A2 == A0).all()
+    assert ((M1 > 0) == (A1 >= 0)).all()
+    assert abs(s1["exact_evals"] - s2["exact_evals"]) <= 0.02 * s1["exact_evals"] + 10, (s1["exact_evals"], s2["exact_evals"])
+    assert 0 < s1["exact_evals"] < 0.01 * st0["exact_evals"], (s1["exact_evals"], st0["exact_evals"])
+    try:
+        for cap in (1, 1000, 50000):
+            rr.debug.set_deferred_cap(cap)
+            s3 = pk.scan(mincov=30, variant=variant)
+            M3, A3 = pk.fetch()
+            assert (M3 == M0).all() and (A3 == A0).all(), (variant, cap)
+            assert s3["pair_tests"] == st0["pair_tests"] and s3["exact_evals"] >= 0.9 * s1["exact_evals"], (cap, s3["exact_evals"], s1["exact_evals"])
+    finally:
+        rr.debug.set_deferred_cap(0)
+    pk.close()
+
+
 def test_pruning_is_sound_at_depth_with_saturation():
     """R ~ 1.8k rows, 1.2e9 pair tests, thousands of saturated (> 98) maxima: the pruned scans of all variants
     must be bitwise equal to the scan that evaluates every pair exactly (RR_FLAG_NO_PRUNE).  Regression test
