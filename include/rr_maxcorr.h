@@ -64,7 +64,10 @@ enum {
                                     even when every row is one contiguous span */
 
 #define RR_FLAG_SEED_ONLY 8u     /* run only the seeding pass (every 64th row tile): multi-GPU runs
-                                    exchange the resulting maxima as thresholds before the full pass */
+                                    exchange the resulting maxima as thresholds before the full pass.  With the
+                                    tcgen05 variants the seeded values are rigorous LOWER bounds of scores that
+                                    pairs of the seed tiles attain (within ~1e-3 of them), entries without a
+                                    partner: good for thresholds, not results */
 #define RR_FLAG_SKIP_SEED 16u    /* keep the running maxima already on the device (previous RR_FLAG_SEED_ONLY
                                     scan and/or rr_scan_set_thresholds) and go straight to the full pass */
 
@@ -140,7 +143,10 @@ int rr_pack_finish(rr_packed *pk);
 /* run the scan on the packed MSA; results stay on the device */
 int rr_scan(rr_packed *pk, const rr_scan_opts *opts, rr_scan_stats *stats);
 /* copy the last scan's result to the host: maxcorr[5*cols] (line g of MaxCorrsOf_*,
- * g = 5*site + {A,C,G,T,gap}); argmax[5*cols] = partner group id or -1 (may be NULL) */
+ * g = 5*site + {A,C,G,T,gap}); argmax[5*cols] = partner group id or -1 (may be NULL).  After a scan of the whole MSA
+ * every group with a maximum has its partner.  After a scan of one part (part_count > 1) an entry without a partner
+ * (argmax -1, value > 0) is a threshold this part was given or derived - a lower bound of the group's maximum, attained
+ * or exceeded in another part - and disappears in the element-wise max over the parts */
 int rr_scan_fetch(rr_packed *pk, double *maxcorr, int32_t *argmax);
 /* RR_FLAG_HOST_FINALIZE as a call: maxcorr[g] of every group with a partner (argmax[g] >= 0) is re-evaluated with
  * the host libm from the pair's device-side counts; maxcorr / argmax as returned by rr_scan_fetch or merged from
