@@ -231,6 +231,37 @@ int rr_cliquer_batch(rr_packed *pk, int64_t n_queries, const int32_t *query_grou
  * (csrc/rr_cliquer.cu), every member word read once. */
 int rr_clique_groups(rr_packed *pk, int64_t n_cliques, const int32_t *members, int stride, const int32_t *n_members,
                      const int32_t *cutoffs, uint64_t *groups /*[n_cliques][sc]*/, uint64_t *coverage /*[n_cliques][sc]*/);
+/* Group_Refinement as a whole (RepeatResolver.c:1634-1693; Parallel_Group_Refinement 1770-1821 computes the same, group by
+ * group, on threads - note that its int argument array truncates cutoff and greedy, 1793-1794: callers that replace the
+ * parallel form pass (double)(int)cutoff and (double)(int)greedy).  For every group i with maxcorrs[i] > cutoff, in
+ * ascending order (slot q):
+ *   query_groups[q] = i
+ *   cliques[q][maxclique + 1] = Cliquer(anfang, ende, mincov, maxclique, greedy, i)                              (1649)
+ *   sizes[q]     = Sizes[i]: the members before the first entry <= 0 - group 0 ends the count like the -1 does     (1650)
+ *   where sizes[q] > 5:
+ *     cutoffs[q]  = Cutoffs[i] = Dropoff_Cutoff(i, 0) (1460-1522): the k in [1, Sizes - 1) that minimises
+ *                   (n[k-1] - n[k+1]) / min(rows - n[k], n[k]), n[k] = the reads contained in more than k of the first
+ *                   Sizes members; the first minimum wins, 1 if no k is admissible.  (The reference evaluates BestCutoff
+ *                   530-548 and KorrMaxCutoff 1393-1457 first; both results are overwritten at 1662, neither has a side
+ *                   effect, so they are not evaluated here.)
+ *     drop_off[q] = Drop_Off[i], the minimum itself (1e6 if no k is admissible)
+ *     c_groups[q][sc], c_coverage[q][sc] = CliqueGroup / CliqueCoverage of the clique at that cutoff             (1663-1665)
+ *   else cutoffs[q] = 0, drop_off[q] = 1000.0 (1641-1645), c_groups[q] / c_coverage[q] all zero (the reference leaves NULL)
+ *     and maxcorrs[i] = 0.0                                                                                       (1685)
+ * capacity = slots the caller provides; *n_queries = groups above the cutoff, also when that exceeds the capacity (then
+ * RR_E_ARG; maxcorrs is untouched and only query_groups has been written to).  c_groups / c_coverage may be NULL.  maxclique <= 100 (the reference's array of
+ * 100 cutoff groups, 1463).  The reference's two "Group Precision" printouts per refined group (1678-1679) are diagnostics
+ * of the caller's (repeatresolver_b200.GroupPrecision computes the same two numbers from a bitset).
+ * Device work: rr_cliquer_batch, the member counts n[k] of all refined cliques in one kernel (bit-sliced counters, one
+ * comparison per k on 32 reads at a time), rr_clique_groups; the cutoff rule itself runs on the host in IEEE double on
+ * exact integers, so Cutoffs and Drop_Off are bit-identical to the reference's. */
+int rr_group_refinement(rr_packed *pk, double *maxcorrs /* [5 * cols], in/out */, double cutoff, int anfang, int ende, int mincov,
+                        int maxclique, double greedy, int64_t capacity, int32_t *query_groups /*[capacity]*/,
+                        int32_t *cliques /*[capacity][maxclique+1]*/, int32_t *sizes /*[capacity]*/, int32_t *cutoffs /*[capacity]*/,
+                        double *drop_off /*[capacity]*/, uint64_t *c_groups /*[capacity][sc]*/, uint64_t *c_coverage /*[capacity][sc]*/,
+                        int64_t *n_queries, rr_cliquer_stats *stats /* may be NULL */);
+/* the cutoff rule alone (tests): sizes[k] = reads in more than k of the `size` members, k < size; returns the cutoff */
+int rr_dropoff_cutoff_host(const uint32_t *sizes, int size, int signumber, int c, double *drop_off);
 int rr_cliquer(rr_packed *pk, int query_group, int anfang, int ende, int mincov, int maxclique, double greedy,
                int32_t *members, double *scores, int *n_members);
 /* the host half on given counts (tests): groups[k] ascending candidate ids, counts[4k..4k+3] =

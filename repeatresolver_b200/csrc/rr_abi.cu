@@ -1019,6 +1019,129 @@ extern "C" int rr_cliquer_batch(rr_packed *pk, int64_t nq, const int32_t *querie
 }
 
 // ---------------------------------------------------------------------------------------
+// Group_Refinement (RepeatResolver.c:1634-1693; Parallel_Group_Refinement 1770-1821 does the same group by group): Cliquer
+// for every group above the cutoff in one device batch, Sizes (1650), Dropoff_Cutoff(i, 0) on the device's member counts -
+// BestCutoff and KorrMaxCutoff run before it in the reference, but their results are overwritten at 1662 and they have no
+// side effect - then CliqueGroup and CliqueCoverage at that cutoff; MaxCorrs zeroed where Sizes <= 5 (1685).
+// ---------------------------------------------------------------------------------------
+// Dropoff_Cutoff 1488-1509 on sizes[k] = reads contained in more than k of the clique's first `size` members
+extern "C" int rr_dropoff_cutoff_host(const uint32_t *sizes, int size, int signumber, int c, double *drop_off)
+{
+    const int c0 = std::max(1, c);
+    int drop_c = c0;
+    double min_drop = 1000000.0;
+    for (int i = c0; i < size - 1; i++) {
+        const double si = (double)sizes[i];
+        const double den = std::min((double)signumber - si, si);
+        if (den > 0) {
+            const double drop = ((double)sizes[i - 1] - (double)sizes[i + 1]) / den;
+            if (drop < min_drop) { min_drop = drop; drop_c = i; }       // the first minimum wins
+        }
+    }
+    if (drop_off) *drop_off = min_drop;
+    return drop_c;
+}
+
+extern "C" int rr_group_refinement(rr_packed *pk, double *maxcorrs, double cutoff, int anfang, int ende, int mincov, int maxclique,
+                                   double greedy, int64_t capacity, int32_t *query_groups, int32_t *cliques, int32_t *sizes,
+                                   int32_t *cutoffs, double *drop_off, uint64_t *c_groups, uint64_t *c_coverage,
+                                   int64_t *n_queries, rr_cliquer_stats *stats)
+{
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (n_queries) *n_queries = 0;
+    // Dropoff_Cutoff keeps one group per member in an array of 100 (1463)
+    if (!pk || pk->phase != 3 || !n_queries || capacity < 0 || maxclique < 1 || maxclique > 100 || mincov < 0 || !(greedy >= 0.0) ||
+        (pk->N > 0 && !maxcorrs) || (capacity && (!query_groups || !cliques || !sizes || !cutoffs || !drop_off))) {
+        rr_set_error("rr_group_refinement: bad arguments");
+        return RR_E_ARG;
+    }
+    if ((int)pk->h_perm.size() != pk->R) { rr_set_error("rr_group_refinement: the packed MSA carries no row order"); return RR_E_ARG; }
+    const int64_t G = (int64_t)5 * pk->N;
+    int64_t nq = 0;
+    for (int64_t i = 0; i < G; i++)
+        if (maxcorrs[i] > cutoff) {                                      // 1647
+            if (nq < capacity) query_groups[nq] = (int32_t)i;
+            nq++;
+        }
+    *n_queries = nq;
+    if (nq > capacity) {
+        rr_set_error("rr_group_refinement: %lld groups above the cutoff, room for %lld", (long long)nq, (long long)capacity);
+        return RR_E_ARG;
+    }
+    const int stride = maxclique + 1;
+    const size_t sc = (size_t)pk->R / 64 + 1;
+    if (c_groups) memset(c_groups, 0, sizeof(uint64_t) * (size_t)nq * sc);
+    if (c_coverage) memset(c_coverage, 0, sizeof(uint64_t) * (size_t)nq * sc);
+    if (nq == 0) return RR_OK;
+    int rc;
+    {
+        std::vector<double> scores((size_t)nq * maxclique);
+        std::vector<int32_t> nmem((size_t)nq);
+        if ((rc = rr_cliquer_batch(pk, nq, query_groups, anfang, ende, mincov, maxclique, greedy, cliques, scores.data(), nmem.data(), stats)))
+            return rc;
+    }
+    std::vector<int64_t> refined;                                        // slots with Sizes > 5 (1652)
+    for (int64_t q = 0; q < nq; q++) {
+        const int32_t *m = cliques + q * stride;
+        int n = 0;
+        while (n < maxclique && m[n] > 0) n++;                           // 1650: group 0 ends the count like the -1 does
+        sizes[q] = n;
+        cutoffs[q] = 0;
+        drop_off[q] = 1000.0;                                            // 1645
+        if (n > 5) refined.push_back(q);
+        else maxcorrs[query_groups[q]] = 0.0;                            // 1685
+    }
+    const int64_t nr = (int64_t)refined.size();
+    if (nr == 0) return RR_OK;
+    // member lists of the refined cliques: Dropoff_Cutoff sees the first Sizes members, CliqueGroup / CliqueCoverage every
+    // member up to the first negative entry (986-993)
+    std::vector<int32_t> mem((size_t)nr * stride), n_drop((size_t)nr), n_all((size_t)nr), cut((size_t)nr);
+    for (int64_t k = 0; k < nr; k++) {
+        const int32_t *m = cliques + refined[k] * stride;
+        memcpy(&mem[(size_t)k * stride], m, sizeof(int32_t) * stride);
+        int n = 0;
+        while (n < stride && m[n] >= 0) n++;
+        n_drop[k] = sizes[refined[k]];
+        n_all[k] = n;
+    }
+    RR_CUDA(cudaSetDevice(pk->device));
+    rr_alloc_stream(pk->st);
+    {
+        dev_scope scope;
+        int32_t *d_mem = nullptr, *d_n = nullptr;
+        uint32_t *d_sizes = nullptr;
+        const int64_t slice = std::min<int64_t>(nr, (int64_t)1 << 20);
+        if ((rc = scope.alloc(&d_mem, (size_t)slice * stride)) || (rc = scope.alloc(&d_n, (size_t)slice)) ||
+            (rc = scope.alloc(&d_sizes, (size_t)slice * stride)))
+            return rc;
+        std::vector<uint32_t> h_sizes((size_t)slice * stride);
+        for (int64_t k0 = 0; k0 < nr; k0 += slice) {
+            const int64_t n = std::min(slice, nr - k0);
+            RR_CUDA(cudaMemcpyAsync(d_mem, &mem[(size_t)k0 * stride], sizeof(int32_t) * n * stride, cudaMemcpyHostToDevice, pk->st));
+            RR_CUDA(cudaMemcpyAsync(d_n, &n_drop[k0], sizeof(int32_t) * n, cudaMemcpyHostToDevice, pk->st));
+            RR_CUDA(rr_launch_clique_sizes(pk->d_bits, pk->W32, n, d_mem, stride, d_n, d_sizes, pk->st));
+            RR_CUDA(cudaMemcpyAsync(h_sizes.data(), d_sizes, sizeof(uint32_t) * n * stride, cudaMemcpyDeviceToHost, pk->st));
+            RR_CUDA(cudaStreamSynchronize(pk->st));
+            if (stats) stats->launches += (int)((n + 65534) / 65535);
+            for (int64_t k = 0; k < n; k++) {
+                const int64_t q = refined[k0 + k];
+                cut[k0 + k] = cutoffs[q] = rr_dropoff_cutoff_host(&h_sizes[(size_t)k * stride], sizes[q], pk->R, 0, &drop_off[q]);  // 1662
+            }
+        }
+    }
+    if (!c_groups && !c_coverage) return RR_OK;
+    std::vector<uint64_t> g(c_groups ? (size_t)nr * sc : 0), v(c_coverage ? (size_t)nr * sc : 0);
+    if ((rc = rr_clique_groups(pk, nr, mem.data(), stride, n_all.data(), cut.data(), c_groups ? g.data() : nullptr,
+                               c_coverage ? v.data() : nullptr)))                                                        // 1663, 1665
+        return rc;
+    for (int64_t k = 0; k < nr; k++) {
+        if (c_groups) memcpy(c_groups + (size_t)refined[k] * sc, &g[(size_t)k * sc], sizeof(uint64_t) * sc);
+        if (c_coverage) memcpy(c_coverage + (size_t)refined[k] * sc, &v[(size_t)k * sc], sizeof(uint64_t) * sc);
+    }
+    return RR_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // Relative_Vars (RepeatResolver.c:2424-2493): the masked Gram matrix X^T diag(u) X over the selected groups.  Either the
 // rows of the part are packed as an MSA of their own (rr_relative_vars: the triple intersections |Gi & Gj & U| become plain
 // pair intersections and |Gi & U| its group sizes), or the part is a mask over the packed copy of the whole MSA

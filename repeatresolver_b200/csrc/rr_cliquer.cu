@@ -250,6 +250,56 @@ rr_k_clique_members(const uint32_t *__restrict__ bits, const uint32_t *__restric
     }
 }
 
+// Dropoff_Cutoff's member counts (RepeatResolver.c:1472-1486) for a batch of cliques: sizes[q * stride + k] = the reads
+// contained in MORE than k of the first n_members[q] members of clique q, k < n_members[q] (at most 100 members, 1463).  One
+// block row per clique, the same bit-sliced counters as above (every member word read once), then one comparison per k on 32
+// reads at a time; a block sums its words in shared memory and adds one value per k to the result.  sizes must be zero on
+// entry.  Bits beyond the last read are zero in every group, so they count nowhere.
+__global__ void __launch_bounds__(128)
+rr_k_clique_sizes(const uint32_t *__restrict__ bits, int W32, int64_t n_cliques, const int32_t *__restrict__ members, int stride,
+                  const int32_t *__restrict__ n_members, uint32_t *__restrict__ sizes)
+{
+    __shared__ unsigned hist[128];
+    const int64_t q = blockIdx.y;
+    if (q >= n_cliques) return;                            // block-uniform
+    const int nm = min(min(n_members[q], stride), 100);
+    const int lane = threadIdx.x & 31;
+    const int32_t *mem = members + q * stride;
+    hist[threadIdx.x] = 0u;
+    __syncthreads();
+    // warp-uniform trip count: the reductions below are over whole warps
+    for (int w0 = blockIdx.x * blockDim.x + (threadIdx.x - lane); w0 < W32; w0 += gridDim.x * blockDim.x) {
+        const int w = w0 + lane;
+        uint32_t cnt[CLG_PLANES];
+#pragma unroll
+        for (int k = 0; k < CLG_PLANES; k++) cnt[k] = 0u;
+        if (w < W32)
+            for (int m = 0; m < nm; m++) {
+                uint32_t x = bits[(size_t)mem[m] * W32 + w];
+#pragma unroll
+                for (int k = 0; k < CLG_PLANES; k++) {
+                    const uint32_t carry = cnt[k] & x;
+                    cnt[k] ^= x;
+                    x = carry;
+                }
+            }
+        for (int c = 0; c < nm; c++) {                     // count > c; c <= 99 < 2^CLG_PLANES - 1
+            uint32_t gt = 0u, eq = 0xffffffffu;
+#pragma unroll
+            for (int k = CLG_PLANES - 1; k >= 0; k--) {
+                const uint32_t cb = (c >> k) & 1 ? 0xffffffffu : 0u;
+                gt |= eq & cnt[k] & ~cb;
+                eq &= ~(cnt[k] ^ cb);
+            }
+            const unsigned n = __reduce_add_sync(CLQ_FULL, (unsigned)__popc(gt));
+            if (n == 0u) break;                            // warp-uniform; no read of these words is in more than c members
+            if (lane == 0) atomicAdd(&hist[c], n);
+        }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nm && hist[threadIdx.x]) atomicAdd(&sizes[q * stride + threadIdx.x], hist[threadIdx.x]);
+}
+
 // rank-order result words -> the reference's bitsets over MSA rows: one warp per 32 consecutive rows of one clique
 __global__ void __launch_bounds__(256)
 rr_k_rank_bits_to_rows(const uint32_t *__restrict__ in, int W32, int64_t n_cliques, const int32_t *__restrict__ rank_of_row,
@@ -295,6 +345,22 @@ cudaError_t rr_launch_cliquer(const uint32_t *bits, const uint32_t *covbits, con
     rr_k_cliquer_score<<<n_sm * 8, 128, 0, st>>>(cand, cap, counters, queries, gsize, lnf, threshold, hits, counters + 1);
     rr_count_launch(2);
     return cudaGetLastError();
+}
+// the member counts Dropoff_Cutoff needs: sizes [n_cliques][stride], zeroed here
+cudaError_t rr_launch_clique_sizes(const uint32_t *bits, int W32, int64_t n_cliques, const int32_t *members, int stride,
+                                   const int32_t *n_members, uint32_t *sizes, cudaStream_t st)
+{
+    if (n_cliques <= 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(sizes, 0, sizeof(uint32_t) * (size_t)n_cliques * stride, st);
+    if (e != cudaSuccess) return e;
+    for (int64_t q0 = 0; q0 < n_cliques; q0 += 65535) {   // grid.y limit
+        const int64_t nq = std::min<int64_t>(65535, n_cliques - q0);
+        dim3 grid((unsigned)std::max(1, std::min((W32 + 127) / 128, 64)), (unsigned)nq);
+        rr_k_clique_sizes<<<grid, 128, 0, st>>>(bits, W32, nq, members + q0 * stride, stride, n_members + q0, sizes + q0 * stride);
+        rr_count_launch(1);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 // CliqueGroup (which = 0) or CliqueCoverage (which = 1) of n_cliques cliques: tmp [n_cliques][W32] rank-order words,
 // out [n_cliques][words32] words of 32 rows each (two per unsigned long of the reference)

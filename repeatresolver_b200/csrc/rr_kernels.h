@@ -50,6 +50,9 @@ cudaError_t rr_launch_clique_members(const uint32_t *bits, const uint32_t *covbi
                                      const int32_t *members, int stride, const int32_t *n_members, const int32_t *cutoffs,
                                      int which, const int32_t *rank_of_row, int R, int words32, uint32_t *tmp, uint32_t *out,
                                      cudaStream_t st);
+// Dropoff_Cutoff's member counts of a batch of cliques (rr_cliquer.cu): sizes[q][k] = reads in more than k of the members
+cudaError_t rr_launch_clique_sizes(const uint32_t *bits, int W32, int64_t n_cliques, const int32_t *members, int stride,
+                                   const int32_t *n_members, uint32_t *sizes, cudaStream_t st);
 
 // Relative_Vars (rr_relvars.cu): the all-pairs step on the packed rows of one part
 cudaError_t rr_launch_masked_sizes(const uint32_t *bits, const uint32_t *umask, int64_t nsets, int W32, int32_t *sizes, cudaStream_t st);

@@ -224,6 +224,35 @@ class Packed:
                "rr_clique_groups")
         return G, Cv
 
+    def group_refinement(self, MaxCorrs, cutoff, mincov=30, maxclique=30, greedy=3.0, anfang=0, ende=None, want_groups=True,
+                         want_coverage=True):
+        """Group_Refinement (RepeatResolver.c:1634-1693) for every group above the cutoff (rr_group_refinement): Cliquer,
+        Sizes, Dropoff_Cutoff, CliqueGroup and CliqueCoverage.  MaxCorrs is not modified; returns a dict with
+        MaxCorrs (the copy with the entries of groups whose Sizes <= 5 zeroed, 1685), groups [nq] (ascending), Cliques
+        [nq][maxclique+1], Sizes, Cutoffs, Drop_Off [nq], C_Groups / C_Coverage uint64 [nq][rows/64+1] (all zero where the
+        reference leaves NULL, i.e. Sizes <= 5; None if not asked for), stats."""
+        M = np.array(MaxCorrs, dtype=np.float64)
+        if len(M) != 5 * self.cols:
+            raise ValueError("MaxCorrs must hold 5 * cols values")
+        nq = int(np.count_nonzero(M > cutoff))
+        sc = self.rows // 64 + 1
+        groups = np.zeros(nq, dtype=np.int32)
+        cliques = np.full((nq, maxclique + 1), -1, dtype=np.int32)
+        sizes = np.zeros(nq, dtype=np.int32)
+        cutoffs = np.zeros(nq, dtype=np.int32)
+        drop = np.zeros(nq, dtype=np.float64)
+        G = np.zeros((nq, sc), dtype=np.uint64) if want_groups else None
+        Cv = np.zeros((nq, sc), dtype=np.uint64) if want_coverage else None
+        n = C.c_int64(0)
+        st = CliquerStats()
+        _check(lib.rr_group_refinement(self._h, M.ctypes.data, float(cutoff), anfang, 2 ** 30 if ende is None else ende, mincov, maxclique,
+                                       float(greedy), nq, groups.ctypes.data, cliques.ctypes.data, sizes.ctypes.data, cutoffs.ctypes.data,
+                                       drop.ctypes.data, G.ctypes.data if G is not None else None,
+                                       Cv.ctypes.data if Cv is not None else None, C.byref(n), C.byref(st)), "rr_group_refinement")
+        assert n.value == nq
+        return {"MaxCorrs": M, "groups": groups, "Cliques": cliques, "Sizes": sizes, "Cutoffs": cutoffs, "Drop_Off": drop,
+                "C_Groups": G, "C_Coverage": Cv, "stats": st.as_dict()}
+
     def relative_vars(self, Unterteilung, u_no, MaxCorrs, cutoff, mingroup, with_pairs=False):
         """Relative_Vars (RepeatResolver.c:2424-2493) on this packed MSA, the part applied as a mask
         (rr_relative_vars_packed): ascending group ids"""
@@ -357,6 +386,39 @@ def Group_Refinement_Cliques(packed, MaxCorrs, cutoff, anfang, ende, mincov, max
     members, scores, _, st = packed.cliquer_batch(groups, mincov, maxclique, greedy, anfang, ende)
     sizes = np.array([int(np.argmax(row <= 0)) for row in members], dtype=np.int32)     # while(Cliques[i][Sizes[i]]>0)
     return groups, members, sizes, scores, st
+
+
+def Group_Refinement(packed, MaxCorrs, cutoff, anfang, ende, mincov, maxclique, greedy):
+    """RepeatResolver.c:1634-1693 with the reference's argument order.  The reference fills its global arrays indexed by
+    group; here they come back for the groups above the cutoff only (see Packed.group_refinement), and MaxCorrs - which
+    the reference modifies in place - as the "MaxCorrs" entry of the result."""
+    return packed.group_refinement(MaxCorrs, cutoff, mincov, maxclique, greedy, anfang, ende)
+
+
+def Parallel_Group_Refinement(packed, MaxCorrs, cutoff, anfang, ende, mincov, maxclique, greedy, NTHREADS=1):
+    """RepeatResolver.c:1770-1821: the same work spread over threads - and, because the thread arguments travel in an int
+    array (1793-1794), with cutoff and greedy truncated towards zero.  NTHREADS is accepted and ignored: all groups go to the
+    device in one batch."""
+    return packed.group_refinement(MaxCorrs, float(int(cutoff)), mincov, maxclique, float(int(greedy)), anfang, ende)
+
+
+def GroupPrecision(bitset, signumber):
+    """RepeatResolver.c:1098-1131, the two numbers of its "Group Precision maj / min" printout: over the blocks of 30
+    consecutive reads (reads of one copy in the simulator's order), members and non-members of the majority side / of the
+    minority side."""
+    bits = np.unpackbits(np.ascontiguousarray(bitset, dtype="<u8").view(np.uint8), bitorder="little")[:signumber]
+    n = signumber // 30
+    drin = bits[:n * 30].reshape(n, 30).sum(axis=1).astype(np.int64)
+    drau = 30 - drin
+    return int(np.where(drin > drau, drin, drau).sum()), int(np.where(drin > drau, drau, drin).sum())
+
+
+def dropoff_cutoff_host(sizes, signumber, c=0):
+    """Dropoff_Cutoff's rule (1488-1509) on given member counts (host half of rr_group_refinement): (cutoff, Drop_Off)"""
+    s = np.ascontiguousarray(sizes, dtype=np.uint32)
+    d = C.c_double(0.0)
+    cut = lib.rr_dropoff_cutoff_host(s.ctypes.data, len(s), int(signumber), int(c), C.byref(d))
+    return cut, d.value
 
 
 def Relative_Vars(msa, Unterteilung, u_no, MaxCorrs, cutoff, mingroup, device=0):

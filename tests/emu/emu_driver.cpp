@@ -154,6 +154,15 @@ void emu_clique_members(const uint32_t *bits, const uint32_t *covbits, int W32, 
         rr_k_rank_bits_to_rows(tmp, W32, n_cliques, rank_of_row, R, words32, out);
     });
 }
+/* Dropoff_Cutoff's member counts as rr_launch_clique_sizes runs them (sizes zeroed by the caller) */
+void emu_clique_sizes(const uint32_t *bits, int W32, long long n_cliques, const int32_t *members, int stride,
+                      const int32_t *n_members, uint32_t *sizes, int grid_x)
+{
+    if (n_cliques <= 0) return;
+    emu_launch(dim3((unsigned)grid_x, (unsigned)n_cliques), 128, [&] {
+        rr_k_clique_sizes(bits, W32, n_cliques, members, stride, n_members, sizes);
+    });
+}
 void emu_general_break(const uint32_t *covbits, int W32, int N, int mincov, int32_t *breakcol)
 {
     if (N > 0) emu_launch(dim3((unsigned)((N + 7) / 8)), 256, [&] { rr_k_general_break(covbits, W32, N, mincov, breakcol); });

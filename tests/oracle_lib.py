@@ -209,6 +209,62 @@ def clique_coverage(codes, clique, c):
     return score > c
 
 
+def dropoff_cutoff(codes, clique, size, c=0):
+    """Dropoff_Cutoff (RepeatResolver.c:1460-1522) on the first `size` members of a clique (Sizes[c_i], 1650): sizes[k] = reads
+    contained in more than k of them (1472-1486); the cutoff k in [max(1, c), size - 1) that minimises
+    (sizes[k-1] - sizes[k+1]) / min(signumber - sizes[k], sizes[k]) where that denominator is positive, the first such k on
+    ties (1494-1509).  Returns (cutoff, Drop_Off)."""
+    codes = np.asarray(codes)
+    signumber = codes.shape[0]
+    score = np.zeros(signumber, dtype=np.int64)
+    for g in clique[:size]:
+        score += codes[:, g // 5] == g % 5
+    sizes = [float(np.count_nonzero(score > k)) for k in range(size)]
+    drop_c = max(1, c)
+    min_drop = 1000000.0
+    for i in range(drop_c, size - 1):
+        den = min(float(signumber) - sizes[i], sizes[i])
+        if den > 0:
+            drop = (sizes[i - 1] - sizes[i + 1]) / den
+            if drop < min_drop:
+                min_drop, drop_c = drop, i
+    return drop_c, min_drop
+
+
+def group_precision(mask):
+    """GroupPrecision (1098-1131): over blocks of 30 consecutive reads, the majority and the minority counts (maj, min)"""
+    mask = np.asarray(mask, dtype=bool)
+    n = len(mask) // 30
+    drin = mask[:n * 30].reshape(n, 30).sum(axis=1)
+    drau = 30 - drin
+    return int(np.where(drin > drau, drin, drau).sum()), int(np.where(drin > drau, drau, drin).sum())
+
+
+def group_refinement(oracle, codes, maxcorrs, cutoff, mincov, maxclique, greedy, anfang=0, ende=None):
+    """Group_Refinement (1634-1693) on the oracle's Cliquer: for every group i with MaxCorrs[i] > cutoff its clique, Sizes[i]
+    (members before the first entry <= 0, 1650) and - where Sizes[i] > 5 - the cutoff of Dropoff_Cutoff(i, 0) (the results of
+    BestCutoff and KorrMaxCutoff are overwritten at 1662 and have no side effect), Drop_Off[i], CliqueGroup and CliqueCoverage
+    at that cutoff; MaxCorrs[i] = 0 where Sizes[i] <= 5 (1685).  Returns (MaxCorrs after, {i: dict})."""
+    M = np.array(maxcorrs, dtype=np.float64)
+    res = {}
+    for i in np.flatnonzero(M > cutoff):
+        members, _ = oracle.cliquer(int(i), mincov, maxclique, greedy, anfang, ende)
+        clique = np.full(maxclique + 1, -1, dtype=np.int32)
+        clique[:len(members)] = members
+        size = 0
+        while clique[size] > 0:
+            size += 1
+        r = {"clique": clique, "size": size, "cutoff": 0, "drop_off": 1000.0, "group": None, "coverage": None}
+        if size > 5:
+            r["cutoff"], r["drop_off"] = dropoff_cutoff(codes, clique, size, 0)
+            r["group"] = clique_group(codes, clique, r["cutoff"])
+            r["coverage"] = clique_coverage(codes, clique, r["cutoff"])
+        else:
+            M[i] = 0.0
+        res[int(i)] = r
+    return M, res
+
+
 def bitset_words(mask):
     """a bool [rows] as the reference's group words: read r = bit r % 64 of word r / 64 (GrAdd 211-217), rows / 64 + 1 words"""
     mask = np.asarray(mask, dtype=bool)

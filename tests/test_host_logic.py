@@ -372,3 +372,34 @@ def test_binary_side_format_rejects_other_files(tmp_path):
     assert list(M) == list(range(10))
     with pytest.raises(rr.RRError):
         rr.MaxCorrsEinlesen_bin(str(tmp_path / "noargs"), 5, 9)         # partners of that window are cut off
+
+
+def test_dropoff_cutoff_host_rule():
+    """rr_dropoff_cutoff_host (the host half of rr_group_refinement) against Dropoff_Cutoff's loop (RepeatResolver.c:1488-1509)
+    restated on random non-increasing member counts, including zero denominators, ties and short cliques"""
+    rng = np.random.default_rng(21)
+
+    def rule(sizes, signumber, c):
+        drop_c = max(1, c)
+        start, min_drop = drop_c, 1000000.0
+        for i in range(start, len(sizes) - 1):
+            den = min(float(signumber) - float(sizes[i]), float(sizes[i]))
+            if den > 0:
+                drop = (float(sizes[i - 1]) - float(sizes[i + 1])) / den
+                if drop < min_drop:
+                    min_drop, drop_c = drop, i
+        return drop_c, min_drop
+
+    for trial in range(400):
+        signumber = int(rng.integers(1, 3000))
+        n = int(rng.integers(0, 101))
+        sizes = np.sort(rng.integers(0, signumber + 1, n))[::-1].astype(np.uint32)
+        if trial % 5 == 0 and n:
+            sizes[:n // 2] = signumber                                      # every read in the first members: denominator 0
+        if trial % 7 == 0 and n:
+            sizes[n // 3:] = sizes[n // 3]                                  # a plateau: ties, the first minimum wins
+        for c in (0, 1, 3):
+            got = rr.dropoff_cutoff_host(sizes, signumber, c)
+            assert got == rule(sizes, signumber, c), (trial, c)
+    assert rr.dropoff_cutoff_host([], 10) == (1, 1000000.0)
+    assert rr.GroupPrecision(np.array([0x3fffffff | (1 << 31), 0], dtype=np.uint64), 70) == (30 + 29, 1)

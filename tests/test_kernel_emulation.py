@@ -681,3 +681,59 @@ def test_clique_group_kernels_against_the_oracle(emu_pack):
         for k in range(len(members)):
             want = O.bitset_words(fn(codes, members[k, :nm[k]], int(cut[k])))
             assert np.array_equal(got[k], want), (which, k, int(nm[k]), int(cut[k]))
+
+
+# ---- Dropoff_Cutoff's member counts (rr_k_clique_sizes, csrc/rr_cliquer.cu) --------------------------------------------
+@pytest.mark.parametrize("grid_x", [1, 3])
+def test_clique_sizes_kernel_against_the_oracle(emu_pack, grid_x):
+    """sizes[k] = reads contained in more than k of a clique's first n members (RepeatResolver.c:1472-1486) on a packed MSA of
+    several 32-read words (more words than one warp pass, and a grid that leaves warps without words), cliques of 0 to 100
+    members with repeats; the cutoff rule on those counts equals the restatement's"""
+    rng = np.random.default_rng(11)
+    codes = two_family_msa(1200, 40, seed=4)
+    R, N = codes.shape
+    p = device_pack(emu_pack, codes, 1)
+    W32 = p["W32"]
+    stride = 101
+    ns = [0, 1, 2, 6, 7, 13, 30, 64, 100]
+    members = np.full((len(ns), stride), -1, dtype=np.int32)
+    for k, n in enumerate(ns):
+        members[k, :n] = rng.integers(5, 5 * N, n)
+        if n >= 6:
+            members[k, 2] = members[k, 0]                                   # a repeated member counts twice
+    nm = np.array(ns, dtype=np.int32)
+    sizes = np.zeros((len(ns), stride), dtype=np.uint32)
+    vp, i, i64 = C.c_void_p, C.c_int, C.c_longlong
+    emu_pack.emu_clique_sizes.argtypes = [vp, i, i64, vp, i, vp, vp, i]
+    emu_pack.emu_clique_sizes(p["bits"].ctypes.data, W32, len(ns), members.ctypes.data, stride, nm.ctypes.data, sizes.ctypes.data, grid_x)
+    for k, n in enumerate(ns):
+        score = np.zeros(R, dtype=np.int64)
+        for g in members[k, :n]:
+            score += codes[:, g // 5] == g % 5
+        want = [int(np.count_nonzero(score > c)) for c in range(n)]
+        assert list(sizes[k, :n]) == want, (k, n)
+        assert not sizes[k, n:].any()
+        if n > 5:
+            assert rr.dropoff_cutoff_host(sizes[k, :n], R, 0) == O.dropoff_cutoff(codes, members[k], n, 0), (k, n)
+
+
+def test_clique_sizes_kernel_walks_every_word(emu_pack):
+    """random bitsets of 300 words: one block of 128 threads needs three passes, two blocks two (the second with idle warps)"""
+    rng = np.random.default_rng(12)
+    G, W32, stride = 60, 300, 41
+    bits = rng.integers(0, 2 ** 32, (G, W32), dtype=np.uint64).astype(np.uint32) & rng.integers(0, 2 ** 32, (G, W32), dtype=np.uint64).astype(np.uint32)
+    ns = [40, 7, 1, 0, 23]
+    members = np.full((len(ns), stride), -1, dtype=np.int32)
+    for k, n in enumerate(ns):
+        members[k, :n] = rng.integers(0, G, n)
+    nm = np.array(ns, dtype=np.int32)
+    unpacked = np.unpackbits(bits.view(np.uint8), axis=1, bitorder="little").astype(np.int64)      # [G][32 * W32]
+    vp, i, i64 = C.c_void_p, C.c_int, C.c_longlong
+    emu_pack.emu_clique_sizes.argtypes = [vp, i, i64, vp, i, vp, vp, i]
+    for grid_x in (1, 2):
+        sizes = np.zeros((len(ns), stride), dtype=np.uint32)
+        emu_pack.emu_clique_sizes(bits.ctypes.data, W32, len(ns), members.ctypes.data, stride, nm.ctypes.data, sizes.ctypes.data, grid_x)
+        for k, n in enumerate(ns):
+            score = unpacked[members[k, :n]].sum(axis=0) if n else np.zeros(32 * W32, dtype=np.int64)
+            assert list(sizes[k, :n]) == [int(np.count_nonzero(score > c)) for c in range(n)], (grid_x, k)
+            assert not sizes[k, n:].any()

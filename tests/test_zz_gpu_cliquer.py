@@ -184,3 +184,128 @@ def test_clique_groups_bad_arguments(deep):
         pk.clique_groups([list(range(101))], [0])                            # more members than the reference's limit (986)
     G, V = pk.clique_groups(np.zeros((0, 4), dtype=np.int32), [])
     assert G.shape[0] == 0 and V.shape[0] == 0
+
+
+# ---- Group_Refinement as a whole (RepeatResolver.c:1634-1693) through rr_group_refinement ------------------------------------
+def _check_refinement(got, records, codes, maxclique):
+    """records: {group: Sizes / Cutoffs / Drop_Off / MaxCorrs / Cliques / C_Groups / C_Coverage of the reference or the oracle}"""
+    R = codes.shape[0]
+    assert [int(g) for g in got["groups"]] == sorted(int(i) for i in records)
+    refined = 0
+    for q, g in enumerate(got["groups"]):
+        want = records[str(int(g))]
+        assert list(got["Cliques"][q]) == list(want["clique"]), g
+        assert int(got["Sizes"][q]) == want["size"] and int(got["Cutoffs"][q]) == want["cutoff"], g
+        assert float(got["Drop_Off"][q]).hex() == want["drop_off"], g
+        assert float(got["MaxCorrs"][g]).hex() == want["maxcorr"], g
+        if want["size"] > 5:
+            refined += 1
+            assert np.array_equal(got["C_Groups"][q], _golden_words(want["group"])), g
+            assert np.array_equal(got["C_Coverage"][q], _golden_words(want["coverage"])), g
+            if "precision" in want:
+                assert list(rr.GroupPrecision(O.bitset_words(codes[:, g // 5] == g % 5), R)) == want["precision"][0]
+                assert list(rr.GroupPrecision(got["C_Groups"][q], R)) == want["precision"][1]
+        else:
+            assert not got["C_Groups"][q].any() and not got["C_Coverage"][q].any() and got["MaxCorrs"][g] == 0.0
+    return refined
+
+
+@pytest.mark.parametrize("name", ["tree_small", "distributed_small", "saturated"])
+def test_group_refinement_golden(name):
+    """the device path against what the UNMODIFIED RepeatResolver.c left in its globals (tests/golden/grouprefine.json)"""
+    from test_oracle_grouprefine import grouprefine_cases, case_inputs
+    case = grouprefine_cases()[name]
+    codes, o, M = case_inputs(name, case)
+    pk = rr.Packed(rr.MSA.from_cells(codes, codes=True), 0)
+    got = rr.Group_Refinement(pk, M, case["cutoff"], 0, codes.shape[1], case["mincov"], case["maxclique"], case["greedy"])
+    assert _check_refinement(got, case["groups"], codes, case["maxclique"]) >= 20
+    untouched = np.ones(len(M), dtype=bool)
+    untouched[got["groups"]] = False
+    assert np.array_equal(got["MaxCorrs"][untouched], M[untouched])
+    # the parallel form truncates cutoff and greedy (1793-1794)
+    par = rr.Parallel_Group_Refinement(pk, M, case["cutoff"], 0, codes.shape[1], case["mincov"], case["maxclique"], case["greedy"], 4)
+    ser = rr.Group_Refinement(pk, M, float(int(case["cutoff"])), 0, codes.shape[1], case["mincov"], case["maxclique"], float(int(case["greedy"])))
+    for key in ("MaxCorrs", "groups", "Cliques", "Sizes", "Cutoffs", "Drop_Off", "C_Groups", "C_Coverage"):
+        assert np.array_equal(par[key], ser[key]), key
+    # only the cutoffs
+    few = pk.group_refinement(M, case["cutoff"], case["mincov"], case["maxclique"], case["greedy"], want_groups=False, want_coverage=False)
+    assert few["C_Groups"] is None and np.array_equal(few["Cutoffs"], got["Cutoffs"]) and np.array_equal(few["Drop_Off"], got["Drop_Off"])
+    pk.close()
+
+
+def test_group_refinement_deep_against_the_oracle(deep):
+    """several 32-read words per bitset, a sub-range of columns, cliques of up to 100 members, queries without partners:
+    everything identical to the restatement on the oracle's Cliquer"""
+    codes, o, pk = deep[0], deep[1], deep[2]
+    R, N = codes.shape
+    gs = o.gsize()
+    rng = np.random.default_rng(8)
+    M = np.zeros(5 * N)
+    cand = np.flatnonzero((gs > 30) & (gs < R // 3))
+    M[cand[::max(1, len(cand) // 90)]] = 50.0
+    M[[0, 5 * N - 1]] = 50.0
+    M[rng.integers(0, 5 * N, 20)] = 50.0                                     # some without partners: Sizes <= 5
+    for anfang, ende, maxclique, greedy in ((0, N, 30, 3.0), (N // 4, 3 * N // 4, 12, 6.5), (0, N, 100, 1.0)):
+        got = pk.group_refinement(M, 7.5, 30, maxclique, greedy, anfang, ende)
+        want_M, want = O.group_refinement(o, codes, M, 7.5, 30, maxclique, greedy, anfang, ende)
+        assert np.array_equal(got["MaxCorrs"], want_M)
+        assert [int(g) for g in got["groups"]] == sorted(want)
+        refined = 0
+        for q, g in enumerate(got["groups"]):
+            w = want[int(g)]
+            assert list(got["Cliques"][q]) == list(w["clique"]) and int(got["Sizes"][q]) == w["size"], g
+            assert int(got["Cutoffs"][q]) == w["cutoff"] and float(got["Drop_Off"][q]).hex() == float(w["drop_off"]).hex(), g
+            if w["size"] > 5:
+                refined += 1
+                assert np.array_equal(got["C_Groups"][q], O.bitset_words(w["group"])), g
+                assert np.array_equal(got["C_Coverage"][q], O.bitset_words(w["coverage"])), g
+            else:
+                assert not got["C_Groups"][q].any() and not got["C_Coverage"][q].any()
+        assert refined >= 20, (anfang, ende, refined)
+
+
+def test_group_refinement_arguments(deep):
+    codes, o, pk = deep[0], deep[1], deep[2]
+    N = codes.shape[1]
+    M = np.zeros(5 * N)
+    got = pk.group_refinement(M, 3.0)                                        # nothing above the cutoff
+    assert len(got["groups"]) == 0 and got["C_Groups"].shape == (0, codes.shape[0] // 64 + 1) and np.array_equal(got["MaxCorrs"], M)
+    with pytest.raises(rr.RRError):
+        pk.group_refinement(M, 3.0, maxclique=101)                           # Dropoff_Cutoff's array of 100 (1463)
+    with pytest.raises(rr.RRError):
+        pk.group_refinement(M, 3.0, greedy=-1.0)
+    with pytest.raises(ValueError):
+        pk.group_refinement(M[:-1], 3.0)
+    # too little room: the count comes back, nothing is written
+    import ctypes as C
+    M[[10, 20, 30]] = 9.0
+    n = C.c_int64(0)
+    buf = np.zeros(64, dtype=np.int64)
+    from repeatresolver_b200._lib import lib
+    rc = lib.rr_group_refinement(pk._h, M.ctypes.data, 3.0, 0, N, 30, 30, 3.0, 2, buf.ctypes.data, buf.ctypes.data, buf.ctypes.data,
+                                    buf.ctypes.data, buf.ctypes.data, None, None, C.byref(n), None)
+    assert rc != 0 and n.value == 3 and M[10] == 9.0
+
+
+def test_group_refinement_with_group_zero_as_a_member():
+    """1650 sizes a clique by its first entry <= 0, CliqueGroup by its first negative entry (986-993): the input of
+    tests/test_oracle_grouprefine.py, where the unmodified reference confirms the restatement on exactly this case"""
+    from test_oracle_grouprefine import group_zero_member_case
+    text, von, bis, codes = group_zero_member_case()
+    o = O.Oracle.from_codes(codes)
+    M, _, _ = o.scan(12)
+    pk = rr.Packed(rr.MSA.from_cells(codes, codes=True), 0)
+    got = pk.group_refinement(M, 6.0, 12, 16, 3.0)
+    want_M, want = O.group_refinement(o, codes, M, 6.0, 12, 16, 3.0)
+    assert np.array_equal(got["MaxCorrs"], want_M) and [int(g) for g in got["groups"]] == sorted(want)
+    seen = set()
+    for q, g in enumerate(got["groups"]):
+        w = want[int(g)]
+        assert list(got["Cliques"][q]) == list(w["clique"]) and int(got["Sizes"][q]) == w["size"] and int(got["Cutoffs"][q]) == w["cutoff"]
+        assert float(got["Drop_Off"][q]).hex() == float(w["drop_off"]).hex()
+        if w["size"] > 5:
+            assert np.array_equal(got["C_Groups"][q], O.bitset_words(w["group"])) and np.array_equal(got["C_Coverage"][q], O.bitset_words(w["coverage"]))
+        if 0 in list(w["clique"][1:]):
+            seen.add(w["size"] > 5)
+    assert seen == {True, False}
+    pk.close()
