@@ -345,6 +345,36 @@ def bench_cliquer(args, rr):
                 k_cpu += 1
             cg["cpu_port_cliques_per_s"] = k_cpu / (time.perf_counter() - t0)
             cg["gpu_cliques_per_s"] = len(n) / (cg_ms * 1e-3)
+    # Group_Refinement as a whole (1634-1693) for the same query groups through rr_group_refinement: Cliquer batch, Sizes,
+    # Dropoff_Cutoff on the device's member counts, CliqueGroup + CliqueCoverage at that cutoff
+    gr = None
+    if world == 1:
+        Mq = np.zeros(5 * N)
+        Mq[queries] = 50.0
+        for _ in range(2):
+            res = pk.group_refinement(Mq, 3.0, MINCOV, 30, 3.0)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = pk.group_refinement(Mq, 3.0, MINCOV, 30, 3.0)
+        gr_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        assert np.array_equal(res["Cliques"], members) and np.array_equal(np.sort(queries), res["groups"])
+        gr = {"groups_above_cutoff": int(len(res["groups"])), "refined": int((res["Sizes"] > 5).sum()), "ms_per_call": gr_ms,
+              "groups_per_s": len(res["groups"]) / (gr_ms * 1e-3),
+              "cutoff_histogram": {str(int(c)): int(k) for c, k in zip(*np.unique(res["Cutoffs"][res["Sizes"] > 5], return_counts=True))},
+              "note": "wall time of the C-ABI call: Cliquer batch + member-count kernel + cutoff rule on the host + CliqueGroup / CliqueCoverage"}
+        if not args.no_cpu_baseline:
+            import oracle_lib as O
+            codes_h = g.codes()
+            o_h = O.Oracle.from_codes(codes_h)
+            t0 = time.perf_counter()
+            k_cpu = 0
+            while time.perf_counter() - t0 < min(args.cpu_seconds, 5.0) and k_cpu < len(queries):
+                Mk = np.zeros(5 * N)
+                Mk[queries[k_cpu]] = 50.0
+                O.group_refinement(o_h, codes_h, Mk, 3.0, MINCOV, 30, 3.0)
+                k_cpu += 1
+            gr["cpu_port_groups_per_s"] = k_cpu / (time.perf_counter() - t0)
+            gr["cpu_port_cores"] = 1
     print(json.dumps({"metric": "Cliquer candidate pairs/sec (Group_Refinement)", "value": pairs / (kernel_ms * 1e-3),
                       "unit": "candidate pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                       "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -354,7 +384,7 @@ def bench_cliquer(args, rr):
                                  "l2": "candidate bitsets larger than L2 at config 2; smaller workloads are L2-resident"},
                       "candidates": st["candidates"], "hits": st["hits"], "host_evals": st["host_evals"],
                       "mean_clique": float(n.mean()) if len(n) else 0.0, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-                      "clique_groups": cg,
+                      "clique_groups": cg, "group_refinement": gr,
                       "e2e": {"value": pairs / (call_ms * 1e-3), "unit": "candidate pairs/s", "ms_per_step": call_ms,
                               "h2d_bytes_per_step": int(4 * len(mine)), "d2h_bytes_per_step": int(32 * st["hits"] + 16)},
                       "gpu_launches": launches}))

@@ -122,26 +122,53 @@ def cliquer_over_ranks(cliquer_batch, query_groups, maxclique=30, **kw):
     groups of one region of the MSA spread over the GPUs), runs `cliquer_batch` on them (Packed.cliquer_batch of the
     rank's own packed copy of the MSA) and one all-gather returns every rank the full result in query order:
     (members [nq][maxclique+1], scores [nq][maxclique], n_members [nq], this rank's stats)."""
-    import torch
-    import torch.distributed as dist
     q = np.ascontiguousarray(query_groups, dtype=np.int32).ravel()
     rank, world = rank_part()
     members, scores, n, st = cliquer_batch(q[rank::world], maxclique=maxclique, **kw)
     if world == 1:
         return members, scores, n, st
-    per = (len(q) + world - 1) // world                     # slices differ by at most one query: pad to the longest
+    return (_gather_cyclic(members, -1, len(q)), _gather_cyclic(scores, 0.0, len(q)), _gather_cyclic(n, 0, len(q)), st)
+
+
+def _gather_cyclic(a, fill, nq):
+    """rank r holds the rows r, r + world, ... of an [nq][...] array: one all-gather gives every rank the whole array"""
+    import torch
+    import torch.distributed as dist
+    rank, world = rank_part()
+    per = (nq + world - 1) // world                         # slices differ by at most one row: pad to the longest
     dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    pad = np.full((per,) + a.shape[1:], fill, dtype=a.dtype)
+    pad[:len(a)] = a
+    as_signed = {np.dtype(np.uint64): np.int64, np.dtype(np.uint32): np.int32}.get(pad.dtype)     # gloo / torch: signed views
+    mine = torch.from_numpy(pad.view(as_signed) if as_signed else pad).to(dev)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    out = np.full((nq,) + a.shape[1:], fill, dtype=a.dtype)
+    for r in range(world):
+        k = len(range(r, nq, world))
+        part = parts[r][:k].cpu().numpy()
+        out[r::world] = part.view(a.dtype) if as_signed else part
+    return out
 
-    def gather(a, fill):
-        pad = np.full((per,) + a.shape[1:], fill, dtype=a.dtype)
-        pad[:len(a)] = a
-        mine = torch.from_numpy(pad).to(dev)
-        parts = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(parts, mine)
-        out = np.full((len(q),) + a.shape[1:], fill, dtype=a.dtype)
-        for r in range(world):
-            k = len(q[r::world])
-            out[r::world] = parts[r][:k].cpu().numpy()
-        return out
 
-    return gather(members, -1), gather(scores, 0.0), gather(n, 0), st
+def group_refinement_over_ranks(group_refinement, MaxCorrs, cutoff, **kw):
+    """Group_Refinement (RepeatResolver.c:1634-1693; the reference's own parallel form 1770-1821 deals the groups to threads
+    by i % NTHREADS, 1717) for MaxCorrs shared by all ranks.  The groups above the cutoff are independent: rank r takes the
+    r-th, (r + world)-th, ... of them - `group_refinement` is Packed.group_refinement of the rank's own packed copy of the MSA
+    and sees MaxCorrs with every other entry lowered to -inf - and one all-gather per result array returns every rank the full
+    result in ascending group order, in the layout of Packed.group_refinement (stats: this rank's)."""
+    M = np.array(MaxCorrs, dtype=np.float64)
+    rank, world = rank_part()
+    if world == 1:
+        return group_refinement(M, cutoff, **kw)
+    q = np.flatnonzero(M > cutoff).astype(np.int32)
+    masked = np.full_like(M, -np.inf)
+    masked[q[rank::world]] = M[q[rank::world]]
+    res = group_refinement(masked, cutoff, **kw)
+    assert np.array_equal(res["groups"], q[rank::world])
+    out = {"groups": q, "stats": res["stats"]}
+    for key, fill in (("Cliques", -1), ("Sizes", 0), ("Cutoffs", 0), ("Drop_Off", 0.0), ("C_Groups", 0), ("C_Coverage", 0)):
+        out[key] = None if res[key] is None else _gather_cyclic(res[key], fill, len(q))
+    M[q[out["Sizes"] <= 5]] = 0.0                            # 1685
+    out["MaxCorrs"] = M
+    return out

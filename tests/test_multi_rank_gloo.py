@@ -117,3 +117,72 @@ def test_cliquer_over_ranks_gloo(world, nq, tmp_path):
             assert list(res["members"][k, :len(m)]) == list(m) and (res["members"][k, len(m):] == -1).all()
             assert np.array_equal(res["scores"][k, :len(z)], z)
     assert max(int(r["n"].max()) for r in results) > 1
+
+
+def _refine_worker(rank, world, port, codes, M, cutoff, out_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle_lib as O
+    from repeatresolver_b200.dist import group_refinement_over_ranks
+    o = O.Oracle.from_codes(codes)
+    R = codes.shape[0]
+    seen = []
+
+    def refine(MaxCorrs, cutoff, mincov, maxclique, greedy):
+        """stands in for Packed.group_refinement on a machine without a GPU: same signature and result layout"""
+        want_M, want = O.group_refinement(o, codes, MaxCorrs, cutoff, mincov, maxclique, greedy)
+        groups = np.array(sorted(want), dtype=np.int32)
+        seen.extend(int(g) for g in groups)
+        sc = R // 64 + 1
+        res = {"MaxCorrs": want_M, "groups": groups, "Cliques": np.array([want[g]["clique"] for g in groups], dtype=np.int32).reshape(len(groups), maxclique + 1),
+               "Sizes": np.array([want[g]["size"] for g in groups], dtype=np.int32), "Cutoffs": np.array([want[g]["cutoff"] for g in groups], dtype=np.int32),
+               "Drop_Off": np.array([want[g]["drop_off"] for g in groups], dtype=np.float64),
+               "C_Groups": np.zeros((len(groups), sc), dtype=np.uint64), "C_Coverage": None, "stats": {"rank": rank}}
+        for k, g in enumerate(groups):
+            if want[g]["size"] > 5:
+                res["C_Groups"][k] = O.bitset_words(want[g]["group"])
+        return res
+
+    res = group_refinement_over_ranks(refine, M, cutoff, mincov=12, maxclique=10, greedy=2.0)
+    q = np.flatnonzero(M > cutoff)
+    assert seen == [int(g) for g in q[rank::world]]
+    assert res["C_Coverage"] is None and res["stats"] == {"rank": rank}
+    np.savez(os.path.join(out_dir, f"gr{rank}.npz"), **{k: v for k, v in res.items() if k not in ("C_Coverage", "stats")})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nq", [(2, 31), (3, 40), (2, 1)])
+def test_group_refinement_over_ranks_gloo(world, nq, tmp_path):
+    """Group_Refinement sharded by group over world ranks (no data-path collective, one all-gather per result array): every
+    rank ends with the single-process result, bitsets with their top bit set included"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    import repeatresolver_b200 as rr
+    g = rr.MsaGen(type="Tree", copies=4, coverage=16, repeat_len=500, diff=0.03, seed=78, flank=300, min_overlap=50)
+    codes = g.codes()
+    o = O.Oracle.from_codes(codes)
+    M, _, _ = o.scan(12)
+    vals = np.unique(M)[::-1]                                # the largest value that leaves at least nq groups above it
+    cutoff = float(next(v for v in vals if np.count_nonzero(M > v) >= nq))
+    nq = int(np.count_nonzero(M > cutoff))
+    port = _free_port()
+    mp.spawn(_refine_worker, args=(world, port, codes, M, cutoff, str(tmp_path)), nprocs=world, join=True)
+    want_M, want = O.group_refinement(o, codes, M, cutoff, 12, 10, 2.0)
+    assert len(want) == nq
+    for r in range(world):
+        res = np.load(tmp_path / f"gr{r}.npz")
+        assert np.array_equal(res["MaxCorrs"], want_M) and [int(x) for x in res["groups"]] == sorted(want)
+        for k, grp in enumerate(res["groups"]):
+            w = want[int(grp)]
+            assert list(res["Cliques"][k]) == list(w["clique"]) and res["Sizes"][k] == w["size"] and res["Cutoffs"][k] == w["cutoff"]
+            assert res["Drop_Off"][k] == w["drop_off"]
+            if w["size"] > 5:
+                assert np.array_equal(res["C_Groups"][k], O.bitset_words(w["group"]))
+            else:
+                assert not res["C_Groups"][k].any()
+    if nq > 4:
+        assert sum(1 for w in want.values() if w["size"] > 5) >= 5
