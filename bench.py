@@ -464,11 +464,13 @@ def bench_rows(args, rr):
                 if len(sel[u][0]):
                     rr.Kmeans(msa, ut, u, sel[u][0], MINGROUP)
 
-    u_small, width, pw, nv, t_rel, t_km = cpu_leg(M, ut, parts, pk)
-    cpu_pairs = pw if args.path == "relvars" else 2 * sizes[u_small] ** 2
-    cpu = {"value": cpu_pairs / max(t_rel if args.path == "relvars" else t_km, 1e-9), "unit": "pairs/s", "cores": 1, "kind": "port",
-           "sample": f"part {u_small} ({sizes[u_small]} reads) of the partition at site {site}, groups of columns [0, {width}) "
-                     f"({pw} group pairs, {nv} groups selected), cutoff {CUTOFF}, mingroup {MINGROUP}"}
+    cpu = None
+    if args.impl == "reference" or not args.no_cpu_baseline:
+        u_small, width, pw, nv, t_rel, t_km = cpu_leg(M, ut, parts, pk)
+        cpu_pairs = pw if args.path == "relvars" else 2 * sizes[u_small] ** 2
+        cpu = {"value": cpu_pairs / max(t_rel if args.path == "relvars" else t_km, 1e-9), "unit": "pairs/s", "cores": 1, "kind": "port",
+               "sample": f"part {u_small} ({sizes[u_small]} reads) of the partition at site {site}, groups of columns [0, {width}) "
+                         f"({pw} group pairs, {nv} groups selected), cutoff {CUTOFF}, mingroup {MINGROUP}"}
     metric = "Relative_Vars group pairs/sec" if args.path == "relvars" else "Kmeans read pairs/sec"
     if args.impl == "reference":
         print(json.dumps({"impl": "reference", "metric": metric, "value": cpu["value"], "unit": "pairs/s", "n_gpus": args.gpus, "steps": 1,

@@ -45,6 +45,11 @@ int rr_debug_mma_peak(int device, int variant, int kblocks_per_sm, int reps, flo
 int rr_debug_mma_peak_shape(int device, int variant, int cta_group, int n_cols, int kblocks_per_sm, int reps, float *best_ms,
                             double *macs);
 
+/* rr_kmeans_finish through the score table rr_kmeans fills on the device (reads x clusters that can ever hold two reads
+ * during the dissolution, RepeatResolver.c:2727-2752), here filled on the host: must give what rr_kmeans_finish gives. */
+int rr_debug_kmeans_finish_table(int anzahl, int scv, const uint64_t *sig, const uint64_t *cen, const int32_t *cluster_in,
+                                 int mingroup, int32_t *cluster_out, int *n_clusters);
+
 #ifdef __cplusplus
 }
 #endif

@@ -134,11 +134,12 @@ _sig(lib.rr_last_error, C.c_char_p, [])
 _sig(lib.rr_version, C.c_char_p, [])
 
 # include/rr_debug.h: test / measurement hooks, not part of the drop-in boundary
-DEBUG_SYMBOLS = ["rr_debug_set_cliquer_cap", "rr_debug_set_deferred_cap", "rr_debug_umma_counts", "rr_debug_mma_peak", "rr_debug_mma_peak_shape"]
+DEBUG_SYMBOLS = ["rr_debug_set_cliquer_cap", "rr_debug_set_deferred_cap", "rr_debug_umma_counts", "rr_debug_mma_peak", "rr_debug_mma_peak_shape", "rr_debug_kmeans_finish_table"]
 _sig(lib.rr_debug_set_cliquer_cap, None, [C.c_ulonglong])
 _sig(lib.rr_debug_set_deferred_cap, None, [C.c_ulonglong])
 _sig(lib.rr_debug_mma_peak, _i, [_i, _i, _i, _i, _P(C.c_float), _P(C.c_double)])
 _sig(lib.rr_debug_mma_peak_shape, _i, [_i, _i, _i, _i, _i, _i, _P(C.c_float), _P(C.c_double)])
+_sig(lib.rr_debug_kmeans_finish_table, _i, [_i, _i, _vp, _vp, _vp, _i, _vp, _P(_i)])
 _sig(lib.rr_debug_umma_counts, _i, [_vp, _P(ScanOpts), _i, _i, _vp, _vp, _vp, _P(_i), _P(_i)])
 
 _sig(gen.rr_msagen_create, _vp, [_P(MsagenParams)])

@@ -1402,12 +1402,18 @@ extern "C" int rr_kmeans_signatures(const rr_msa *msa, const int32_t *unterteilu
     for (int j = 0; j < n_vars; j++) { vsite[j] = vars[j] / 5; vsym[j] = (uint8_t)(vars[j] % 5); }
     const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)16, (int64_t)std::thread::hardware_concurrency(),
                                                                   (int64_t)anzahl * n_vars / 2000000 + 1}));
+    uint8_t cls[256];                                                    // the cell's class once per byte value, no branch per group
+    for (int c = 0; c < 256; c++) cls[c] = (uint8_t)host_class((uint8_t)c, msa->codes);
     auto work = [&](int t) {
         for (int i = (int)((int64_t)anzahl * t / nt); i < (int)((int64_t)anzahl * (t + 1) / nt); i++) {
             const uint8_t *row = rr_msa_row(msa, reads_out[i]);
             uint64_t *sg = sig_out + (size_t)i * scv;
-            for (int j = 0; j < n_vars; j++)
-                if (host_class(row[vsite[j]], msa->codes) == vsym[j]) sg[j / 64] |= (uint64_t)1 << (j % 64);
+            for (int j0 = 0; j0 < n_vars; j0 += 64) {                    // one signature word in a register
+                const int n = std::min(64, n_vars - j0);
+                uint64_t w = 0;
+                for (int b = 0; b < n; b++) w |= (uint64_t)(cls[row[vsite[j0 + b]]] == vsym[j0 + b]) << b;
+                sg[j0 / 64] = w;
+            }
         }
     };
     if (nt == 1) work(0);
@@ -1421,8 +1427,22 @@ extern "C" int rr_kmeans_signatures(const rr_msa *msa, const int32_t *unterteilu
 
 // 2728-2757 and 2790-2797: clusters of at most `min` reads are dissolved into clusters of at least `min`, in read order,
 // sizes updated as it goes; returns the number of non-empty clusters
-extern "C" int rr_kmeans_finish(int anzahl, int scv, const uint64_t *sig, const uint64_t *cen, const int32_t *cluster_in, int mingroup,
-                                int32_t *cluster_out, int *n_clusters)
+// the clusters that can ever hold min >= 2 reads during the dissolution (2727-2752): a cluster only grows when a displaced
+// read picks it, and a read picks an admissible cluster (already >= min) or, when nothing scores above 0, cluster 0
+static void km_candidate_clusters(int anzahl, const int32_t *cluster_in, std::vector<int32_t> &J)
+{
+    std::vector<int> size((size_t)anzahl + 1, 0);
+    for (int i = 0; i < anzahl; i++)
+        if (cluster_in[i] >= 0 && cluster_in[i] < anzahl) size[cluster_in[i]]++;
+    J.clear();
+    for (int j = 0; j < anzahl; j++)
+        if (j == 0 || size[j] >= 2) J.push_back(j);
+}
+
+// J / S: optional table of the scores S[i * nJ + k] = GrMatch(Centroids[J[k]], VarSigs[i]) for the clusters of
+// km_candidate_clusters (ascending), made on the device by rr_kmeans; without it the scores are computed here
+static int km_finish_impl(int anzahl, int scv, const uint64_t *sig, const uint64_t *cen, const int32_t *cluster_in, int mingroup,
+                          int32_t *cluster_out, int *n_clusters, const int32_t *J, int nJ, const int32_t *S)
 {
     if (anzahl < 0 || scv < 1 || !n_clusters || (anzahl && (!sig || !cen || !cluster_in || !cluster_out))) {
         rr_set_error("rr_kmeans_finish: bad arguments");
@@ -1435,13 +1455,28 @@ extern "C" int rr_kmeans_finish(int anzahl, int scv, const uint64_t *sig, const 
         size[cluster_in[i]]++;
     }
     // the reads are visited in order and the sizes change as they go (that order is part of the reference's result); the
-    // search for one read's best cluster is independent work over j and is what costs: anzahl x scv word operations
-    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)16, (int64_t)std::thread::hardware_concurrency(),
-                                                                  (int64_t)anzahl * scv / 200000 + 1}));
-    std::vector<int> tb((size_t)nt), tj((size_t)nt);
-    for (int min = 2; min < mingroup; min++)
+    // search for one read's best cluster is independent work over j: (clusters of at least min reads) x scv word
+    // operations.  Usually that is a few dozen clusters and cheaper than starting threads (measured: 766 reads with 70 k
+    // groups, 120 clusters: 176 ms with five threads started per displaced read, 9 ms serial), so threads are only used where
+    // one search is worth more than a millisecond.
+    const int nt_max = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)16, (int64_t)std::thread::hardware_concurrency()));
+    std::vector<int> tb((size_t)nt_max), tj((size_t)nt_max);
+    for (int min = 2; min < mingroup; min++) {
+        int64_t admissible = 0;                                          // at the start of the level; later moves change it little
+        for (int j = 0; j < anzahl; j++) admissible += size[j] >= min;
+        const int nt = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)nt_max, admissible * scv / 4000000));
         for (int i = 0; i < anzahl; i++)
-            if (size[cluster_out[i]] <= min) {
+            if (size[cluster_out[i]] <= min && S) {                      // scores from the table: the same loop over ascending j
+                int best = 0, best_j = 0;
+                const int32_t *row = S + (size_t)i * nJ;
+                for (int k = 0; k < nJ; k++) {
+                    const int j = J[k];
+                    if (size[j] >= min && cluster_out[i] != j && row[k] > best && i != j) { best = row[k]; best_j = j; }
+                }
+                size[cluster_out[i]]--;
+                cluster_out[i] = best_j;
+                size[best_j]++;
+            } else if (size[cluster_out[i]] <= min) {
                 auto search = [&](int t) {
                     int best = 0, best_j = 0;                            // first best in ascending j, as the serial loop
                     for (int j = (int)((int64_t)anzahl * t / nt); j < (int)((int64_t)anzahl * (t + 1) / nt); j++)
@@ -1464,10 +1499,30 @@ extern "C" int rr_kmeans_finish(int anzahl, int scv, const uint64_t *sig, const 
                 cluster_out[i] = best_j;
                 size[best_j]++;
             }
+    }
     int n = 0;
     for (int i = 0; i < anzahl; i++) n += size[i] > 0;
     *n_clusters = n;
     return RR_OK;
+}
+
+extern "C" int rr_kmeans_finish(int anzahl, int scv, const uint64_t *sig, const uint64_t *cen, const int32_t *cluster_in, int mingroup,
+                                int32_t *cluster_out, int *n_clusters)
+{
+    return km_finish_impl(anzahl, scv, sig, cen, cluster_in, mingroup, cluster_out, n_clusters, nullptr, 0, nullptr);
+}
+
+// test hook: the dissolution with the score table rr_kmeans makes on the device, here filled on the host
+extern "C" int rr_debug_kmeans_finish_table(int anzahl, int scv, const uint64_t *sig, const uint64_t *cen, const int32_t *cluster_in, int mingroup,
+                                      int32_t *cluster_out, int *n_clusters)
+{
+    if (anzahl < 0 || scv < 1 || (anzahl && (!sig || !cen || !cluster_in))) { rr_set_error("rr_debug_kmeans_finish_table: bad arguments"); return RR_E_ARG; }
+    std::vector<int32_t> J;
+    km_candidate_clusters(anzahl, cluster_in, J);
+    std::vector<int32_t> S((size_t)anzahl * J.size());
+    for (int i = 0; i < anzahl; i++)
+        for (size_t k = 0; k < J.size(); k++) S[(size_t)i * J.size() + k] = rr_km_match(cen + (size_t)J[k] * scv, sig + (size_t)i * scv, scv);
+    return km_finish_impl(anzahl, scv, sig, cen, cluster_in, mingroup, cluster_out, n_clusters, J.data(), (int)J.size(), S.data());
 }
 
 // function-level hooks on the rules the kernels share with the host (rr_kmeans.h)
@@ -1496,11 +1551,10 @@ extern "C" int rr_kmeans(const rr_msa *msa, int device, int32_t *unterteilung, i
     const int scv = n_vars / 64 + 1;
     std::vector<int32_t> reads((size_t)std::max(msa->rows, 1));
     int anzahl = 0, rc;
-    if ((rc = rr_kmeans_signatures(msa, unterteilung, u_no, vars, n_vars, reads.data(), &anzahl, nullptr))) return rc;
+    if ((rc = rr_kmeans_signatures(msa, unterteilung, u_no, vars, n_vars, reads.data(), &anzahl, nullptr))) return rc;   // validates; the reads of the part
     if (anzahl == 0) return RR_OK;
     std::vector<uint64_t> sig((size_t)anzahl * scv), cen((size_t)anzahl * scv);
-    if ((rc = rr_kmeans_signatures(msa, unterteilung, u_no, vars, n_vars, reads.data(), &anzahl, sig.data()))) return rc;
-    std::vector<int32_t> cluster((size_t)anzahl), final_cluster((size_t)anzahl);
+    std::vector<int32_t> cluster((size_t)anzahl), final_cluster((size_t)anzahl), J, S;
     RR_CUDA(cudaSetDevice(device));
     cudaStream_t st = nullptr;
     RR_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -1508,25 +1562,67 @@ extern "C" int rr_kmeans(const rr_msa *msa, int device, int32_t *unterteilung, i
     {
         dev_scope scope;
         uint64_t *d_sig = nullptr, *d_cen = nullptr;
-        int32_t *d_best = nullptr, *d_cluster = nullptr;
+        int32_t *d_best = nullptr, *d_cluster = nullptr, *d_vars = nullptr;
+        uint8_t *d_rows = nullptr;
         cudaError_t e = cudaSuccess;
+        // the part's rows go to the device in slices of at most 256 MB; their signatures are made there (the host loop over
+        // reads x groups was most of the call: 5e7 byte classifications for a part of 766 reads and 70 k groups)
+        const size_t N = (size_t)msa->cols;
+        const int slice = (int)std::max<size_t>(1, std::min<size_t>((size_t)anzahl, ((size_t)256 << 20) / std::max<size_t>(N, 1)));
         if ((rc = scope.alloc(&d_sig, sig.size())) || (rc = scope.alloc(&d_cen, cen.size())) || (rc = scope.alloc(&d_best, (size_t)anzahl * 5)) ||
-            (rc = scope.alloc(&d_cluster, (size_t)anzahl))) {
+            (rc = scope.alloc(&d_cluster, (size_t)anzahl)) || (rc = scope.alloc(&d_vars, (size_t)std::max(n_vars, 1))) ||
+            (rc = scope.alloc(&d_rows, (size_t)slice * std::max<size_t>(N, 1)))) {
             // fall through to the clean-up below
-        } else if ((e = cudaMemcpyAsync(d_sig, sig.data(), sizeof(uint64_t) * sig.size(), cudaMemcpyHostToDevice, st)) != cudaSuccess ||
-                   (e = rr_launch_kmeans_sweeps(d_sig, anzahl, scv, d_best, d_cen, d_cluster, st)) != cudaSuccess ||
-                   (e = cudaMemcpyAsync(cen.data(), d_cen, sizeof(uint64_t) * cen.size(), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
-                   (e = cudaMemcpyAsync(cluster.data(), d_cluster, sizeof(int32_t) * (size_t)anzahl, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
-                   (e = cudaStreamSynchronize(st)) != cudaSuccess) {
-            rr_set_error("CUDA error %s in rr_kmeans", cudaGetErrorString(e));
-            rc = RR_E_CUDA;
+        } else {
+            if (n_vars) e = cudaMemcpyAsync(d_vars, vars, sizeof(int32_t) * (size_t)n_vars, cudaMemcpyHostToDevice, st);
+            for (int i0 = 0; i0 < anzahl && e == cudaSuccess; i0 += slice) {
+                const int n = std::min(slice, anzahl - i0);
+                for (int i = i0; i < i0 + n && e == cudaSuccess;) {      // runs of consecutive rows of a matrix in one copy
+                    int k = i + 1;
+                    while (msa->cells && k < i0 + n && reads[k] == reads[k - 1] + 1) k++;
+                    e = cudaMemcpyAsync(d_rows + (size_t)(i - i0) * N, rr_msa_row(msa, reads[i]), (size_t)(k - i) * N, cudaMemcpyHostToDevice, st);
+                    i = k;
+                }
+                if (e == cudaSuccess)
+                    e = rr_launch_kmeans_signatures(d_rows, msa->cols, msa->codes, d_vars, n_vars, n, scv, d_sig + (size_t)i0 * scv, st);
+            }
+            if (e != cudaSuccess ||
+                (e = cudaMemcpyAsync(sig.data(), d_sig, sizeof(uint64_t) * sig.size(), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+                (e = rr_launch_kmeans_sweeps(d_sig, anzahl, scv, d_best, d_cen, d_cluster, st)) != cudaSuccess ||
+                (e = cudaMemcpyAsync(cen.data(), d_cen, sizeof(uint64_t) * cen.size(), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+                (e = cudaMemcpyAsync(cluster.data(), d_cluster, sizeof(int32_t) * (size_t)anzahl, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+                (e = cudaStreamSynchronize(st)) != cudaSuccess) {
+                rr_set_error("CUDA error %s in rr_kmeans", cudaGetErrorString(e));
+                rc = RR_E_CUDA;
+            }
+            // the scores of the dissolution (reads x clusters that can ever be admissible) while signatures and centroids are
+            // still on the device: on the host that search was most of what remained of the call
+            if (!rc) {
+                km_candidate_clusters(anzahl, cluster.data(), J);
+                int32_t *d_J = nullptr, *d_S = nullptr;
+                if ((size_t)anzahl * J.size() <= ((size_t)1 << 28) && !scope.alloc(&d_J, J.size()) && !scope.alloc(&d_S, (size_t)anzahl * J.size())) {
+                    S.resize((size_t)anzahl * J.size());
+                    if ((e = cudaMemcpyAsync(d_J, J.data(), sizeof(int32_t) * J.size(), cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+                        (e = rr_launch_kmeans_scores(d_sig, d_cen, d_J, (int)J.size(), anzahl, scv, d_S, st)) != cudaSuccess ||
+                        (e = cudaMemcpyAsync(S.data(), d_S, sizeof(int32_t) * S.size(), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+                        (e = cudaStreamSynchronize(st)) != cudaSuccess) {
+                        rr_set_error("CUDA error %s in rr_kmeans", cudaGetErrorString(e));
+                        rc = RR_E_CUDA;
+                    }
+                } else {
+                    cudaGetLastError();
+                    S.clear();                                           // too large a table: the host computes the scores as it goes
+                }
+            }
         }
     }   // device buffers go back to the pool while the stream still exists
     cudaStreamSynchronize(st);
     cudaStreamDestroy(st);
     rr_alloc_stream(nullptr);
     if (rc) return rc;
-    if ((rc = rr_kmeans_finish(anzahl, scv, sig.data(), cen.data(), cluster.data(), mingroup, final_cluster.data(), n_clusters))) return rc;
+    if ((rc = km_finish_impl(anzahl, scv, sig.data(), cen.data(), cluster.data(), mingroup, final_cluster.data(), n_clusters,
+                             S.empty() ? nullptr : J.data(), (int)J.size(), S.empty() ? nullptr : S.data())))
+        return rc;
     int max_u = 0;                                                       // 2814-2815
     for (int r = 0; r < msa->rows; r++) max_u = std::max(max_u, unterteilung[r]);
     for (int i = 0; i < anzahl; i++) unterteilung[reads[i]] = final_cluster[i] + max_u + 1;

@@ -12,6 +12,21 @@ extern "C" void rr_count_launch(int n);
 #define RR_DYN_SMEM(type, name) extern __shared__ type name[]
 #endif
 
+// the reference's character classes (MaxCorrelation.c:304-329): aA->0 cC->1 gG->2 tT->3 '-' '_'->4, all else -> 5 (not covered)
+#if defined(__CUDACC__) || defined(RR_CPU_EMU)
+static __device__ __forceinline__ int rr_classify(unsigned int c, int codes)
+{
+    if (codes) return c < 5u ? (int)c : 5;
+    unsigned int l = c | 0x20u;
+    if (l == 'a') return 0;
+    if (l == 'c') return 1;
+    if (l == 'g') return 2;
+    if (l == 't') return 3;
+    if (c == '-' || c == '_') return 4;
+    return 5;
+}
+#endif
+
 // Device memory comes from the device's stream-ordered pool (cudaMallocAsync) with an unlimited release
 // threshold: packing the next MSA reuses the previous one's blocks instead of paying cudaMalloc/cudaFree of
 // multi-GB buffers (measured: 40-160 ms per pack/free cycle at config 2).  All work of a handle is on one
@@ -63,6 +78,11 @@ cudaError_t rr_launch_relvars_pairs(const uint32_t *bits, const uint32_t *umask 
 // Kmeans (rr_kmeans.cu): the two read x read sweeps and the centroids on the part's signatures
 cudaError_t rr_launch_kmeans_sweeps(const uint64_t *sig, int anzahl, int scv, int32_t *best_j, uint64_t *cen, int32_t *cluster,
                                     cudaStream_t st);
+cudaError_t rr_launch_kmeans_scores(const uint64_t *sig, const uint64_t *cen, const int32_t *J, int nJ, int anzahl, int scv, int32_t *S,
+                                    cudaStream_t st);
+// the signatures of the part's reads from their rows on the device: rows [anzahl][cols], sig [anzahl][scv] (every word written)
+cudaError_t rr_launch_kmeans_signatures(const uint8_t *rows, int cols, int codes, const int32_t *vars, int n_vars, int anzahl,
+                                        int scv, uint64_t *sig, cudaStream_t st);
 
 struct rr_best_t;
 cudaError_t rr_launch_init_best(rr_best_t *best, int64_t n, cudaStream_t st);

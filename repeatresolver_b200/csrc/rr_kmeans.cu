@@ -4,17 +4,40 @@
 // there against the unmodified reference (tests/test_oracle_kmeans.py).
 //
 // sig[anzahl][scv]: the signatures of the part's reads over the selected groups (64-bit words, padding 0).
+//   rr_k_km_signatures one warp per (read, 32 groups): the signatures from the part's rows (2626-2650)
 //   rr_k_km_top5       one thread per read i, all reads j in order (tiles of signatures through shared memory, every
 //                      thread of the block reads the same word: a broadcast): GrMatch and the reference's five-slot rule
 //                      (2662-2692), which depends on the order of the reads and so stays sequential per read
 //   rr_k_km_centroids  one thread per (read, word): bitwise majority of the five kept reads' signatures (2697-2705)
 //   rr_k_km_assign     one thread per read i: the first best centroid of another read (2709-2725)
+//   rr_k_km_scores     one warp per (read, candidate cluster): the scores the dissolution of small clusters looks up (2735-2745)
 // XOR+POPC work on a few KB of signatures per tile: POPC-issue bound, anzahl^2 * scv word operations per sweep.
 #include <algorithm>
 #include "rr_kernels.h"
 #include "rr_kmeans.h"
 
 constexpr int KM_THREADS = 128;
+
+// Signatures (2626-2650): bit j of read i = the read carries the symbol of group vars[j] at that group's site.  One warp per
+// (read, 32 selected groups): the group ids are read coalesced (the same for every read: L2), the cells are byte gathers
+// from the read's row (cols bytes, L1-resident), one ballot gives half a signature word.  Every 32-bit half of sig is
+// written, bits beyond n_vars as 0.
+__global__ void __launch_bounds__(256)
+rr_k_km_signatures(const uint8_t *__restrict__ rows, int cols, int codes, const int32_t *__restrict__ vars, int n_vars, int anzahl,
+                   int scv, uint32_t *__restrict__ sig32 /*[anzahl][2 * scv]*/)
+{
+    const int i = blockIdx.y;
+    const int half = blockIdx.x * 8 + (threadIdx.x >> 5);                // 32-bit half word of the signature
+    if (i >= anzahl || half >= 2 * scv) return;                          // warp-uniform
+    const int j = half * 32 + (threadIdx.x & 31);
+    int bit = 0;
+    if (j < n_vars) {
+        const int g = vars[j];
+        bit = rr_classify(rows[(size_t)i * cols + g / 5], codes) == g % 5;
+    }
+    const unsigned word = __ballot_sync(0xffffffffu, bit);
+    if ((threadIdx.x & 31) == 0) sig32[(size_t)i * 2 * scv + half] = word;
+}
 
 // stage signatures [j0, j0 + nj) into shared memory, coalesced
 __device__ __forceinline__ void km_stage(uint64_t *tile, const uint64_t *__restrict__ src, int j0, int nj, int scv)
@@ -81,7 +104,50 @@ rr_k_km_assign(const uint64_t *__restrict__ sig, const uint64_t *__restrict__ ce
     if (i < anzahl) cluster[i] = best_j;
 }
 
+// The scores the dissolution of small clusters asks for (2735-2745): S[i * nJ + k] = GrMatch(Centroids[J[k]], VarSigs[i]) for
+// the clusters J that can ever be admissible there; one warp per (read, cluster), lanes stride over the signature words.
+__global__ void __launch_bounds__(256)
+rr_k_km_scores(const uint64_t *__restrict__ sig, const uint64_t *__restrict__ cen, const int32_t *__restrict__ J, int nJ, int anzahl,
+               int scv, int32_t *__restrict__ S)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= (int64_t)anzahl * nJ) return;                               // warp-uniform
+    const int i = (int)(w / nJ), k = (int)(w - (int64_t)i * nJ);
+    const uint64_t *a = cen + (size_t)J[k] * scv, *b = sig + (size_t)i * scv;
+    unsigned d = 0;
+    for (int z = lane; z < scv; z += 32) d += (unsigned)rr_km_popc64(a[z] ^ b[z]);
+    d = __reduce_add_sync(0xffffffffu, d);
+    if (lane == 0) S[w] = scv * 64 - (int)d;
+}
+
 #ifndef RR_CPU_EMU   // tests/emu compiles the kernels above with a host compiler; the launch syntax below is nvcc only
+cudaError_t rr_launch_kmeans_scores(const uint64_t *sig, const uint64_t *cen, const int32_t *J, int nJ, int anzahl, int scv, int32_t *S,
+                                    cudaStream_t st)
+{
+    const int64_t warps = (int64_t)anzahl * nJ;
+    if (warps <= 0) return cudaSuccess;
+    rr_k_km_scores<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(sig, cen, J, nJ, anzahl, scv, S);
+    rr_count_launch(1);
+    return cudaGetLastError();
+}
+
+cudaError_t rr_launch_kmeans_signatures(const uint8_t *rows, int cols, int codes, const int32_t *vars, int n_vars, int anzahl,
+                                        int scv, uint64_t *sig, cudaStream_t st)
+{
+    if (anzahl <= 0) return cudaSuccess;
+    for (int i0 = 0; i0 < anzahl; i0 += 65535) {                        // grid.y limit
+        const int n = std::min(65535, anzahl - i0);
+        dim3 grid((unsigned)((2 * scv + 7) / 8), (unsigned)n);
+        rr_k_km_signatures<<<grid, 256, 0, st>>>(rows + (size_t)i0 * cols, cols, codes, vars, n_vars, n, scv,
+                                                 (uint32_t *)(sig + (size_t)i0 * scv));
+        rr_count_launch(1);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 cudaError_t rr_launch_kmeans_sweeps(const uint64_t *sig, int anzahl, int scv, int32_t *best_j, uint64_t *cen, int32_t *cluster,
                                     cudaStream_t st)
 {

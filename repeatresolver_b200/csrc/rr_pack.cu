@@ -12,17 +12,7 @@
 // else -> 5 (not covered).
 #include "rr_kernels.h"
 
-__device__ __forceinline__ int rr_classify(unsigned int c, int codes)
-{
-    if (codes) return c < 5u ? (int)c : 5;
-    unsigned int l = c | 0x20u;
-    if (l == 'a') return 0;
-    if (l == 'c') return 1;
-    if (l == 'g') return 2;
-    if (l == 't') return 3;
-    if (c == '-' || c == '_') return 4;
-    return 5;
-}
+// rr_classify: rr_kernels.h (shared with the signature kernel of rr_kmeans.cu)
 
 // ---- per-row span: first / last covered column and number of covered cells ------------
 __global__ void __launch_bounds__(256) rr_k_row_spans(const uint8_t *__restrict__ cells, int R, int N, int codes,

@@ -54,3 +54,16 @@ def mma_peak_shape(variant="umma_mxf4", cta_group=2, n_cols=240, device=0, kbloc
     _check(lib.rr_debug_mma_peak_shape(device, VARIANTS[variant], cta_group, n_cols, kblocks_per_sm, reps, C.byref(ms), C.byref(macs)),
            "rr_debug_mma_peak_shape")
     return {"tflops": 2.0 * macs.value / (ms.value * 1e-3) / 1e12, "ms": ms.value, "macs": macs.value}
+
+
+def kmeans_finish_table(sig, cen, cluster, mingroup):
+    """rr_kmeans_finish with the scores looked up in the table rr_kmeans makes on the device (filled on the host here):
+    (final clusters, number of non-empty ones)"""
+    sig = np.ascontiguousarray(sig, dtype=np.uint64)
+    cen = np.ascontiguousarray(cen, dtype=np.uint64)
+    cl = np.ascontiguousarray(cluster, dtype=np.int32)
+    out = np.zeros(len(cl), dtype=np.int32)
+    n = C.c_int(0)
+    _check(lib.rr_debug_kmeans_finish_table(sig.shape[0], sig.shape[1], sig.ctypes.data, cen.ctypes.data, cl.ctypes.data, int(mingroup),
+                                            out.ctypes.data, C.byref(n)), "rr_debug_kmeans_finish_table")
+    return out, n.value

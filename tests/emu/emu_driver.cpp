@@ -229,6 +229,21 @@ int emu_relvars_pairs(const uint32_t *bits, const uint32_t *umask, int W32, cons
     return 0;
 }
 
+/* the signatures of a part's reads as rr_launch_kmeans_signatures makes them */
+void emu_kmeans_signatures(const uint8_t *rows, int cols, int codes, const int32_t *vars, int n_vars, int anzahl, int scv, uint64_t *sig)
+{
+    if (anzahl <= 0) return;
+    emu_launch(dim3((unsigned)((2 * scv + 7) / 8), (unsigned)anzahl), 256, [&] {
+        rr_k_km_signatures(rows, cols, codes, vars, n_vars, anzahl, scv, (uint32_t *)sig);
+    });
+}
+/* the score table of the dissolution as rr_launch_kmeans_scores fills it */
+void emu_kmeans_scores(const uint64_t *sig, const uint64_t *cen, const int32_t *J, int nJ, int anzahl, int scv, int32_t *S)
+{
+    const long long warps = (long long)anzahl * nJ;
+    if (warps <= 0) return;
+    emu_launch(dim3((unsigned)((warps * 32 + 255) / 256)), 256, [&] { rr_k_km_scores(sig, cen, J, nJ, anzahl, scv, S); });
+}
 /* rr_launch_kmeans_sweeps with a caller-chosen tile size, so that several tiles per sweep are exercised on small inputs */
 int emu_kmeans_sweeps(const uint64_t *sig, int anzahl, int scv, int tile_reads, int32_t *best_j, uint64_t *cen, int32_t *cluster)
 {

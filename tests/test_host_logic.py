@@ -403,3 +403,27 @@ def test_dropoff_cutoff_host_rule():
             assert got == rule(sizes, signumber, c), (trial, c)
     assert rr.dropoff_cutoff_host([], 10) == (1, 1000000.0)
     assert rr.GroupPrecision(np.array([0x3fffffff | (1 << 31), 0], dtype=np.uint64), 70) == (30 + 29, 1)
+
+
+def test_kmeans_dissolution_through_the_score_table():
+    """rr_kmeans looks the dissolution's scores up in a table over the clusters that can ever become admissible (initially two
+    reads or more, and cluster 0, which collects the reads nothing scores for); the result must be the on-the-fly one's -
+    random signatures with a few families, many one-read clusters, reads that match nothing, every mingroup"""
+    rng = np.random.default_rng(33)
+    for trial in range(12):
+        anzahl = int(rng.integers(3, 260))
+        scv = int(rng.integers(1, 5))
+        fam = rng.integers(0, 2 ** 63, (4, scv), dtype=np.int64).astype(np.uint64)
+        sig = fam[rng.integers(0, 4, anzahl)] ^ (rng.integers(0, 2 ** 63, (anzahl, scv), dtype=np.int64).astype(np.uint64)
+                                                 & rng.integers(0, 2 ** 63, (anzahl, scv), dtype=np.int64).astype(np.uint64)
+                                                 & rng.integers(0, 2 ** 63, (anzahl, scv), dtype=np.int64).astype(np.uint64))
+        cen = sig.copy()
+        if trial % 3 == 0:
+            sig[::7] = 0
+            cen[::5] = ~np.uint64(0)                                         # centroids some reads score 0 against
+        hubs = rng.choice(anzahl, max(1, anzahl // 4), replace=False)
+        cluster = np.where(rng.random(anzahl) < 0.7, hubs[rng.integers(0, len(hubs), anzahl)], rng.integers(0, anzahl, anzahl)).astype(np.int32)
+        for mingroup in (2, 3, 5, 9):
+            a, na = rr.kmeans_finish(sig, cen, cluster, mingroup)
+            b, nb = rr.debug.kmeans_finish_table(sig, cen, cluster, mingroup)
+            assert na == nb and np.array_equal(a, b), (trial, mingroup)

@@ -252,7 +252,51 @@ def test_kmeans_sweeps_on_the_golden_cases(emu, tile_reads):
             after = ut.copy()
             after[reads] = final + ut.max() + 1
             assert split == want["split"] and list(after) == want["after"], (name, key)
+            # the dissolution through the device's score table: the kernel's table for the clusters that can become admissible
+            final_t, split_t = rr.debug.kmeans_finish_table(sig, cen, cluster, mingroup)
+            assert split_t == split and np.array_equal(final_t, final), (name, key)
+            J = np.array([j for j in range(n) if j == 0 or np.count_nonzero(cluster == j) >= 2], dtype=np.int32)
+            S = np.full((n, len(J)), -1, dtype=np.int32)
+            emu.emu_kmeans_scores.restype = None
+            emu.emu_kmeans_scores(C.c_void_p(sig.ctypes.data), C.c_void_p(cen.ctypes.data), C.c_void_p(J.ctypes.data), C.c_int(len(J)),
+                                  C.c_int(n), C.c_int(scv), C.c_void_p(S.ctypes.data))
+            want_S = scv * 64 - np.array([[sum(bin(int(x)).count("1") for x in (cen[j] ^ sig[i])) for j in J] for i in range(n)])
+            assert np.array_equal(S, want_S), (name, key)
         msa.close()
+
+
+def test_kmeans_signature_kernel_equals_the_host_signatures(emu):
+    """rr_k_km_signatures (one warp per read and 32 groups, one ballot per half word) against rr_kmeans_signatures on the
+    golden parts - code cells and raw characters, group counts that leave a partial half word, an empty last word
+    (n_vars % 64 == 0) and no groups at all"""
+    vp, i = C.c_void_p, C.c_int
+    emu.emu_kmeans_signatures.argtypes = [vp, i, i, vp, i, i, i, vp]
+    emu.emu_kmeans_signatures.restype = None
+    rng = np.random.default_rng(17)
+    checked = 0
+    for name in sorted(kmeans_cases()):
+        rel = relvars_cases()[name]
+        codes = window_codes(golden_msa(name), rel["von"], rel["bis"])
+        o = O.Oracle.from_codes(codes)
+        M, _, _ = o.scan(rel["mincov"])
+        ut, _ = partition_by_site(codes, M)
+        chars = np.frombuffer(b"ACGT- ", dtype=np.uint8)[codes]
+        chars[::3] = np.frombuffer(b"acgt_n", dtype=np.uint8)[codes[::3]]        # lower case, '_' and an unknown symbol
+        for as_codes, cells in ((1, codes), (0, chars)):
+            msa = rr.MSA.from_cells(cells, codes=bool(as_codes))
+            for u_no in sorted(int(k.split("/")[0]) for k in kmeans_cases()[name]):
+                base = np.array(rel["parts"][str(u_no)]["vars"], dtype=np.int32)
+                for vars_ in (base, base[:0], np.sort(rng.choice(5 * codes.shape[1], 128, replace=False)).astype(np.int32),
+                              np.sort(rng.choice(5 * codes.shape[1], 301, replace=False)).astype(np.int32)):
+                    reads, want = rr.kmeans_signatures(msa, ut, u_no, vars_)
+                    rows = np.ascontiguousarray(cells[reads])
+                    got = np.full_like(want, 0xdeadbeefdeadbeef)
+                    emu.emu_kmeans_signatures(rows.ctypes.data, cells.shape[1], as_codes, vars_.ctypes.data, len(vars_), len(reads),
+                                              want.shape[1], got.ctypes.data)
+                    assert np.array_equal(got, want), (name, as_codes, u_no, len(vars_))
+                    checked += 1
+            msa.close()
+    assert checked >= 8
 
 
 # ---- the AND+POPC variant of the scan itself (rr_k_scan_bitset with the fused epilogue of rr_device.cuh) ---------------
