@@ -1562,8 +1562,10 @@ extern "C" int rr_kmeans(const rr_msa *msa, int device, int32_t *unterteilung, i
     {
         dev_scope scope;
         uint64_t *d_sig = nullptr, *d_cen = nullptr;
-        int32_t *d_best = nullptr, *d_cluster = nullptr, *d_vars = nullptr;
+        int32_t *d_best = nullptr, *d_cluster = nullptr, *d_vars = nullptr, *d_panel = nullptr, *d_state = nullptr;
         uint8_t *d_rows = nullptr;
+        // scores of the two sweeps: panels of rows j, all reads i each; 64 MB at most
+        const int panel_rows = (int)std::max<size_t>(1, std::min<size_t>((size_t)anzahl, ((size_t)16 << 20) / (size_t)anzahl));
         cudaError_t e = cudaSuccess;
         // the part's rows go to the device in slices of at most 256 MB; their signatures are made there (the host loop over
         // reads x groups was most of the call: 5e7 byte classifications for a part of 766 reads and 70 k groups)
@@ -1571,7 +1573,8 @@ extern "C" int rr_kmeans(const rr_msa *msa, int device, int32_t *unterteilung, i
         const int slice = (int)std::max<size_t>(1, std::min<size_t>((size_t)anzahl, ((size_t)256 << 20) / std::max<size_t>(N, 1)));
         if ((rc = scope.alloc(&d_sig, sig.size())) || (rc = scope.alloc(&d_cen, cen.size())) || (rc = scope.alloc(&d_best, (size_t)anzahl * 5)) ||
             (rc = scope.alloc(&d_cluster, (size_t)anzahl)) || (rc = scope.alloc(&d_vars, (size_t)std::max(n_vars, 1))) ||
-            (rc = scope.alloc(&d_rows, (size_t)slice * std::max<size_t>(N, 1)))) {
+            (rc = scope.alloc(&d_rows, (size_t)slice * std::max<size_t>(N, 1))) || (rc = scope.alloc(&d_panel, (size_t)panel_rows * anzahl)) ||
+            (rc = scope.alloc(&d_state, (size_t)6 * anzahl))) {
             // fall through to the clean-up below
         } else {
             if (n_vars) e = cudaMemcpyAsync(d_vars, vars, sizeof(int32_t) * (size_t)n_vars, cudaMemcpyHostToDevice, st);
@@ -1588,7 +1591,7 @@ extern "C" int rr_kmeans(const rr_msa *msa, int device, int32_t *unterteilung, i
             }
             if (e != cudaSuccess ||
                 (e = cudaMemcpyAsync(sig.data(), d_sig, sizeof(uint64_t) * sig.size(), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
-                (e = rr_launch_kmeans_sweeps(d_sig, anzahl, scv, d_best, d_cen, d_cluster, st)) != cudaSuccess ||
+                (e = rr_launch_kmeans_sweeps(d_sig, anzahl, scv, d_best, d_cen, d_cluster, d_panel, panel_rows, d_state, st)) != cudaSuccess ||
                 (e = cudaMemcpyAsync(cen.data(), d_cen, sizeof(uint64_t) * cen.size(), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
                 (e = cudaMemcpyAsync(cluster.data(), d_cluster, sizeof(int32_t) * (size_t)anzahl, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
                 (e = cudaStreamSynchronize(st)) != cudaSuccess) {

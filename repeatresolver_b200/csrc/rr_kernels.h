@@ -76,8 +76,9 @@ cudaError_t rr_launch_relvars_pairs(const uint32_t *bits, const uint32_t *umask 
                                     int4 *unsure, unsigned int unsure_cap, unsigned int *unsure_count, cudaStream_t st);
 
 // Kmeans (rr_kmeans.cu): the two read x read sweeps and the centroids on the part's signatures
+// panel: device room for panel_rows x anzahl int32 scores (any panel_rows >= 1: the sweeps go panel by panel); state: 6 x anzahl int32
 cudaError_t rr_launch_kmeans_sweeps(const uint64_t *sig, int anzahl, int scv, int32_t *best_j, uint64_t *cen, int32_t *cluster,
-                                    cudaStream_t st);
+                                    int32_t *panel, int panel_rows, int32_t *state, cudaStream_t st);
 cudaError_t rr_launch_kmeans_scores(const uint64_t *sig, const uint64_t *cen, const int32_t *J, int nJ, int anzahl, int scv, int32_t *S,
                                     cudaStream_t st);
 // the signatures of the part's reads from their rows on the device: rows [anzahl][cols], sig [anzahl][scv] (every word written)

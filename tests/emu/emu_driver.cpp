@@ -237,22 +237,41 @@ void emu_kmeans_signatures(const uint8_t *rows, int cols, int codes, const int32
         rr_k_km_signatures(rows, cols, codes, vars, n_vars, anzahl, scv, (uint32_t *)sig);
     });
 }
+/* one panel of pair scores as km_launch_pair_scores runs it */
+static void emu_pair_scores(const uint64_t *sig, const uint64_t *X, const int32_t *xrows, int j0, int nj, int anzahl, int scv, int32_t *out,
+                            long long stride_i, long long stride_j)
+{
+    if (anzahl <= 0 || nj <= 0) return;
+    emu_launch(dim3((unsigned)((anzahl + KM_TILE - 1) / KM_TILE), (unsigned)((nj + KM_TILE - 1) / KM_TILE)), 256, [&] {
+        rr_k_km_pair_scores(sig, X, xrows, j0, nj, anzahl, scv, out, stride_i, stride_j);
+    });
+}
 /* the score table of the dissolution as rr_launch_kmeans_scores fills it */
 void emu_kmeans_scores(const uint64_t *sig, const uint64_t *cen, const int32_t *J, int nJ, int anzahl, int scv, int32_t *S)
 {
-    const long long warps = (long long)anzahl * nJ;
-    if (warps <= 0) return;
-    emu_launch(dim3((unsigned)((warps * 32 + 255) / 256)), 256, [&] { rr_k_km_scores(sig, cen, J, nJ, anzahl, scv, S); });
+    emu_pair_scores(sig, cen, J, 0, nJ, anzahl, scv, S, nJ, 1);
 }
-/* rr_launch_kmeans_sweeps with a caller-chosen tile size, so that several tiles per sweep are exercised on small inputs */
-int emu_kmeans_sweeps(const uint64_t *sig, int anzahl, int scv, int tile_reads, int32_t *best_j, uint64_t *cen, int32_t *cluster)
+/* rr_launch_kmeans_sweeps with a caller-chosen panel size, so that several panels per sweep are exercised on small inputs */
+int emu_kmeans_sweeps(const uint64_t *sig, int anzahl, int scv, int panel_rows, int32_t *best_j, uint64_t *cen, int32_t *cluster)
 {
-    if (anzahl <= 0 || (size_t)tile_reads * scv * 8 > sizeof(emu_dynamic_smem)) return 1;
-    const unsigned nb = (unsigned)((anzahl + KM_THREADS - 1) / KM_THREADS);
-    emu_launch(dim3(nb), KM_THREADS, [&] { rr_k_km_top5(sig, anzahl, scv, tile_reads, best_j); });
-    const int64_t nw = (int64_t)anzahl * scv;
+    if (anzahl <= 0 || panel_rows < 1) return 1;
+    std::vector<int32_t> panel((size_t)panel_rows * anzahl), state((size_t)6 * anzahl, 0);
+    int32_t *best_s = state.data(), *best = state.data() + (size_t)5 * anzahl;
+    for (int i = 0; i < 5 * anzahl; i++) best_j[i] = 0;
+    for (int i = 0; i < anzahl; i++) cluster[i] = 0;
+    const unsigned nb = (unsigned)((anzahl + 127) / 128);
+    for (int j0 = 0; j0 < anzahl; j0 += panel_rows) {
+        const int nj = std::min(panel_rows, anzahl - j0);
+        emu_pair_scores(sig, sig, nullptr, j0, nj, anzahl, scv, panel.data(), 1, anzahl);
+        emu_launch(dim3(nb), 128, [&] { rr_k_km_top5_seq(panel.data(), anzahl, j0, nj, best_s, best_j); });
+    }
+    const long long nw = (long long)anzahl * scv;
     emu_launch(dim3((unsigned)((nw + 255) / 256)), 256, [&] { rr_k_km_centroids(sig, best_j, anzahl, scv, cen); });
-    emu_launch(dim3(nb), KM_THREADS, [&] { rr_k_km_assign(sig, cen, anzahl, scv, tile_reads, cluster); });
+    for (int j0 = 0; j0 < anzahl; j0 += panel_rows) {
+        const int nj = std::min(panel_rows, anzahl - j0);
+        emu_pair_scores(sig, cen, nullptr, j0, nj, anzahl, scv, panel.data(), 1, anzahl);
+        emu_launch(dim3(nb), 128, [&] { rr_k_km_assign_seq(panel.data(), anzahl, j0, nj, best, cluster); });
+    }
     return 0;
 }
 

@@ -229,7 +229,7 @@ def test_relvars_pair_kernel_with_several_chunks_and_a_cutoff_hit_exactly(emu, m
         assert list(got) == list(o.relative_vars(ut, 0, M, z, 8)) and undecided >= 1
 
 
-@pytest.mark.parametrize("tile_reads", [5, 64])
+@pytest.mark.parametrize("tile_reads", [5, 64])      # rows per score panel
 def test_kmeans_sweeps_on_the_golden_cases(emu, tile_reads):
     for name in sorted(kmeans_cases()):
         rel = relvars_cases()[name]
@@ -263,6 +263,52 @@ def test_kmeans_sweeps_on_the_golden_cases(emu, tile_reads):
             want_S = scv * 64 - np.array([[sum(bin(int(x)).count("1") for x in (cen[j] ^ sig[i])) for j in J] for i in range(n)])
             assert np.array_equal(S, want_S), (name, key)
         msa.close()
+
+
+def test_kmeans_sweeps_over_several_tiles_and_panels(emu):
+    """random signatures, 150 reads (three 64-read tiles on either side, the last one partial) of 70 words (three staged
+    chunks of 32, the last one partial), panels of 1, 37 and 150 rows: the five kept reads against the host rule, the
+    centroids against the majority, the assignment against numpy, and the dissolution's table for a gathered cluster list"""
+    rng = np.random.default_rng(23)
+    n, scv = 150, 70
+    fam = rng.integers(0, 2 ** 63, (5, scv), dtype=np.int64).astype(np.uint64)
+    noise = (rng.integers(0, 2 ** 63, (n, scv), dtype=np.int64).astype(np.uint64) & rng.integers(0, 2 ** 63, (n, scv), dtype=np.int64).astype(np.uint64)
+             & rng.integers(0, 2 ** 63, (n, scv), dtype=np.int64).astype(np.uint64))
+    sig = np.ascontiguousarray(fam[rng.integers(0, 5, n)] ^ noise)
+    sig[7] = sig[3]                                                          # equal scores: the order of the reads decides
+    sig[140] = sig[3]
+    pop = np.array([bin(x).count("1") for x in range(256)], dtype=np.int64)
+
+    def match(a, b):                                                         # [..., scv] uint64 -> 64 * scv - Hamming distance
+        x = np.ascontiguousarray(a ^ b)
+        return scv * 64 - pop[x.view(np.uint8)].reshape(x.shape[:-1] + (-1,)).sum(-1)
+
+    results = []
+    for panel_rows in (1, 37, 150):
+        best_j = np.full((n, 5), -7, dtype=np.int32)
+        cen = np.zeros_like(sig)
+        cluster = np.full(n, -7, dtype=np.int32)
+        assert emu.emu_kmeans_sweeps(sig.ctypes.data, n, scv, panel_rows, best_j.ctypes.data, cen.ctypes.data, cluster.ctypes.data) == 0
+        results.append((best_j, cen, cluster))
+    best_j, cen, cluster = results[0]
+    for other in results[1:]:
+        assert all(np.array_equal(a, b) for a, b in zip(results[0], other))
+    for i in range(n):
+        assert list(best_j[i]) == list(rr.kmeans_top5_host(sig, i)), i
+        b = best_j[i]
+        assert all(int(cen[i, z]) == rr.kmeans_majority5_host(*(int(sig[k, z]) for k in b)) for z in (0, 31, 32, 69))
+    scores = match(cen[None, :, :], sig[:, None, :])                         # [i][j]
+    for i in range(n):
+        row = scores[i].copy()
+        row[i] = -1                                                          # not itself (2717)
+        want = int(np.argmax(row)) if row.max() > 0 else 0                   # first best
+        assert cluster[i] == want, i
+    J = np.array([0, 3, 64, 65, 127, 128, 149], dtype=np.int32)
+    S = np.full((n, len(J)), -1, dtype=np.int32)
+    emu.emu_kmeans_scores.restype = None
+    emu.emu_kmeans_scores(C.c_void_p(sig.ctypes.data), C.c_void_p(cen.ctypes.data), C.c_void_p(J.ctypes.data), C.c_int(len(J)), C.c_int(n),
+                          C.c_int(scv), C.c_void_p(S.ctypes.data))
+    assert np.array_equal(S, scores[:, J])
 
 
 def test_kmeans_signature_kernel_equals_the_host_signatures(emu):
