@@ -278,28 +278,98 @@ int rr_msa_read(const char *path, rr_msa **out)
 }
 
 /* MaxCorrsRausschreiben (516-532): one "%f\n" per group */
-int rr_maxcorr_write(const char *path, const double *maxcorr, int64_t count)
+/* "%f\n" of one double, exactly as printf rounds it (the exact binary value to six decimals, ties to even), without printf:
+ * v = m * 2^e with a 53-bit m, so m * 10^6 fits 73 bits and one shift with an exact remainder test gives the digits.
+ * Returns the length written to out (at most 25 bytes), 0 for values that do not fit the integer path (|v| >= 2^52, inf,
+ * nan): the caller prints those with fprintf.  The text is MaxCorrsRausschreiben's (MaxCorrelation.c:527-530); 5N lines of it were 50 ms of fprintf. */
+static size_t fmt_f6_line(double v, char *out)
 {
-    FILE *f;
-    int64_t i;
-    if (!path || (!maxcorr && count)) return RR_E_ARG;
-    f = fopen(path, "w");
+    uint64_t bits, m, ip, fp;
+    unsigned __int128 P, q;
+    int ex, sh, n = 0, k;
+    char tmp[24];
+    memcpy(&bits, &v, 8);
+    ex = (int)((bits >> 52) & 0x7ff);
+    m = bits & 0xfffffffffffffull;
+    if (ex >= 1075) return 0;                                             /* |v| >= 2^52, inf, nan */
+    if (ex) m |= 1ull << 52; else ex = 1;                                 /* subnormals: 0.frac * 2^-1022 */
+    sh = 1075 - ex;                                                       /* v = m * 2^-sh, sh in 1 .. 1074 */
+    P = (unsigned __int128)m * 1000000u;
+    if (sh >= 74) q = 0;                                                  /* P < 2^73 <= half of 2^sh */
+    else {
+        const unsigned __int128 one = 1, rem = P & ((one << sh) - 1), half = one << (sh - 1);
+        q = P >> sh;
+        if (rem > half || (rem == half && (q & 1))) q++;
+    }
+    ip = (uint64_t)(q / 1000000u);
+    fp = (uint64_t)(q % 1000000u);
+    if (bits >> 63) out[n++] = '-';
+    k = 0;
+    do { tmp[k++] = (char)('0' + ip % 10); ip /= 10; } while (ip);
+    while (k) out[n++] = tmp[--k];
+    out[n++] = '.';
+    for (k = 5; k >= 0; k--) { out[n + k] = (char)('0' + fp % 10); fp /= 10; }
+    n += 6;
+    out[n++] = '\n';
+    return (size_t)n;
+}
+
+static size_t fmt_int_line(int32_t v, char *out)
+{
+    char tmp[12];
+    int n = 0, k = 0;
+    uint32_t u = v < 0 ? 0u - (uint32_t)v : (uint32_t)v;
+    if (v < 0) out[n++] = '-';
+    do { tmp[k++] = (char)('0' + u % 10); u /= 10; } while (u);
+    while (k) out[n++] = tmp[--k];
+    out[n++] = '\n';
+    return (size_t)n;
+}
+
+/* lines formatted into a block of memory, one fwrite per block */
+static int write_lines(const char *path, const double *d, const int32_t *a, int64_t count)
+{
+    enum { BLOCK = 1 << 15 };
+    FILE *f = fopen(path, "w");
+    char *buf;
+    int64_t i = 0;
     if (!f) { rr_set_error("cannot write %s: %s", path, strerror(errno)); return RR_E_IO; }
-    for (i = 0; i < count; i++) fprintf(f, "%f\n", maxcorr[i]);
+    buf = (char *)malloc((size_t)BLOCK * 32);
+    if (!buf) { fclose(f); rr_set_error("out of host memory"); return RR_E_NOMEM; }
+    while (i < count) {
+        const int64_t n = count - i < BLOCK ? count - i : BLOCK;
+        size_t len = 0;
+        int64_t k;
+        if (d)
+            for (k = 0; k < n; k++) {
+                const size_t l = fmt_f6_line(d[i + k], buf + len);
+                if (l) { len += l; continue; }
+                if (fwrite(buf, 1, len, f) != len) len = (size_t)-1;      /* what precedes the odd value, then the value */
+                else { len = 0; fprintf(f, "%f\n", d[i + k]); }
+                if (len) break;
+            }
+        else
+            for (k = 0; k < n; k++) len += fmt_int_line(a[i + k], buf + len);
+        if (len == (size_t)-1 || fwrite(buf, 1, len, f) != len) {
+            free(buf); fclose(f); rr_set_error("write %s: %s", path, strerror(errno)); return RR_E_IO;
+        }
+        i += n;
+    }
+    free(buf);
     if (fclose(f) != 0) { rr_set_error("write %s: %s", path, strerror(errno)); return RR_E_IO; }
     return RR_OK;
 }
 
+int rr_maxcorr_write(const char *path, const double *maxcorr, int64_t count)
+{
+    if (!path || (!maxcorr && count)) return RR_E_ARG;
+    return write_lines(path, maxcorr, NULL, count);
+}
+
 int rr_argmax_write(const char *path, const int32_t *argmax, int64_t count)
 {
-    FILE *f;
-    int64_t i;
     if (!path || (!argmax && count)) return RR_E_ARG;
-    f = fopen(path, "w");
-    if (!f) { rr_set_error("cannot write %s: %s", path, strerror(errno)); return RR_E_IO; }
-    for (i = 0; i < count; i++) fprintf(f, "%d\n", argmax[i]);
-    if (fclose(f) != 0) return RR_E_IO;
-    return RR_OK;
+    return write_lines(path, NULL, argmax, count);
 }
 
 /* ---- binary side format of the result ("the MaxCorrsOf_* binary side-format to skip text") ----

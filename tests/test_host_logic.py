@@ -427,3 +427,37 @@ def test_kmeans_dissolution_through_the_score_table():
             a, na = rr.kmeans_finish(sig, cen, cluster, mingroup)
             b, nb = rr.debug.kmeans_finish_table(sig, cen, cluster, mingroup)
             assert na == nb and np.array_equal(a, b), (trial, mingroup)
+
+
+def test_text_writer_is_printf_exact(tmp_path):
+    """rr_maxcorr_write formats "%f" itself (exact binary value to six decimals, ties to even, one block write per 32 k lines):
+    byte-identical to printf - here glibc's snprintf through ctypes and Python's own correctly rounded "%f" - on exact ties,
+    values around every rounding edge, subnormals, negatives, values beyond the integer path (>= 2^52, inf, nan: written through
+    fprintf) and random doubles of every magnitude; rr_argmax_write likewise for "%d" """
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    vals = [0.0, -0.0, 0.0078125, 0.5, 1.5e-6, 2.5e-6, 0.5e-6, 0.4999999e-6, 98.897959, 99.0, 98.0, 1e-300, 5e-324, -1.25, 123456789.125,
+            2.0 ** 52 - 1, 2.0 ** 52, 1e15, 1e22, float("inf"), float("-inf"), 4503599627370495.5, 0.0000015, 1.0000005, 9.9999995,
+            99.9999995, 0.9999995]
+    vals += [k / 2.0 ** n for n in range(1, 30) for k in (1, 3, 5, 7, 9, 11)]        # exact ties at the seventh decimal and near misses
+    a = np.concatenate([np.array(vals), rng.random(150000) * 100, rng.random(50000) * 1e-4, 10.0 ** rng.uniform(-12, 14, 50000),
+                        -rng.random(1000) * 50, np.round(rng.random(50000) * 100, 6) + 0.5e-6,
+                        rng.integers(0, 2 ** 63, 20000).astype(np.uint64).view(np.float64)])
+    a = np.ascontiguousarray(a[~np.isnan(a)], dtype=np.float64)
+    p = str(tmp_path / "MaxCorrsOf_x")
+    rr.MaxCorrsRausschreiben(a, p)
+    got = open(p, "rb").read()
+    assert got == b"".join(b"%f\n" % v for v in a)
+    libc = C.CDLL(None)
+    libc.snprintf.restype = C.c_int
+    buf = C.create_string_buffer(512)
+    lines = got.split(b"\n")
+    for i in list(range(len(vals))) + list(rng.integers(0, len(a), 3000)):
+        libc.snprintf(buf, C.c_size_t(512), b"%f", C.c_double(a[i]))
+        assert lines[i] == buf.value, (i, a[i])
+    rr.MaxCorrsRausschreiben(np.array([np.nan, 1.0]), p)                     # nan goes through fprintf as well
+    assert open(p, "rb").read() in (b"nan\n1.000000\n", b"-nan\n1.000000\n")
+    from repeatresolver_b200._lib import lib
+    A = np.concatenate([[-1, 0, 9, 10, 2 ** 31 - 1, -2 ** 31], rng.integers(-1, 3_000_000, 70000)]).astype(np.int32)
+    assert lib.rr_argmax_write(p.encode(), A.ctypes.data, len(A)) == 0
+    assert open(p, "rb").read() == b"".join(b"%d\n" % v for v in A)
