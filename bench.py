@@ -520,13 +520,17 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="Tree_1perc_30000", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: Tree_1perc_30000 (BASELINE.json configs[1]) for --path scan / cliquer, Tree_1perc_10000_25 for "
+                         "relvars / kmeans (their CPU legs and the all-pairs selection of whole parts take minutes at config-2 size)")
     ap.add_argument("--variant", default="auto", choices=["auto", "bitset", "umma", "umma_f4", "umma_mxf4"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e-file", dest="e2e_file", action="store_false", help="skip the run of the drop-in program")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.workload is None:
+        args.workload = "Tree_1perc_10000_25" if args.path in ("relvars", "kmeans") else "Tree_1perc_30000"
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
