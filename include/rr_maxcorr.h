@@ -301,12 +301,16 @@ double rr_relative_score_host(uint32_t schnitt, uint32_t gr1, uint32_t gr2, uint
 /* ---- scope row 8f-4: Kmeans (RepeatResolver.c:2604-2821) ------------------------------------------------------------
  * Splits part u_no of the read partition by the reads' signatures over the groups `vars` (the output of Relative_Vars):
  * unterteilung[rows of msa] is updated in place exactly as the reference does (the part's reads get cluster + max + 1,
- * 2814-2815), *n_clusters = the reference's return value (non-empty clusters).  All arithmetic is integer: bit-exact. */
+ * 2814-2815), *n_clusters = the reference's return value (non-empty clusters).  All arithmetic is integer: bit-exact.
+ * The part's rows are copied to `device` as they are; signatures (2626-2650), the two read x read sweeps (2662-2725), the
+ * centroids and the scores the dissolution of small clusters looks up (2735-2745) are computed there (csrc/rr_kmeans.cu);
+ * the dissolution itself, sequential by definition, runs on the host. */
 int rr_kmeans(const rr_msa *msa, int device, int32_t *unterteilung, int u_no, const int32_t *vars, int n_vars, int mingroup,
               int *n_clusters);
-/* host pieces (tests): the part's reads and signatures ([anzahl][n_vars/64+1] 64-bit words; sig_out may be NULL to get the
- * count), the dissolution of small clusters given the device's first assignment, and the two integer rules the kernels
- * share with the host (csrc/rr_kmeans.h) */
+/* host pieces (tests): the part's reads and - as a second implementation the device's are held against - their signatures
+ * ([anzahl][n_vars/64+1] 64-bit words; sig_out may be NULL to get the count), the dissolution of small clusters given the
+ * device's first assignment (scores computed as it goes), and the two integer rules the kernels share with the host
+ * (csrc/rr_kmeans.h) */
 int rr_kmeans_signatures(const rr_msa *msa, const int32_t *unterteilung, int u_no, const int32_t *vars, int n_vars,
                          int32_t *reads_out /*[rows]*/, int *anzahl_out, uint64_t *sig_out);
 int rr_kmeans_finish(int anzahl, int scv, const uint64_t *sig, const uint64_t *cen, const int32_t *cluster_in, int mingroup,
