@@ -181,6 +181,12 @@ int rr_maxcorr_write_bin(const char *path, const double *maxcorr, const int32_t 
  * file; outputs [5 * (bis - von + 1)] or NULL, *n_out = values delivered; as_text != 0 rounds the values as the "%f"
  * text file would, so a consumer decides exactly as it would on MaxCorrsOf_*. */
 int rr_maxcorr_read_bin(const char *path, int von, int bis, int as_text, double *maxcorr_out, int32_t *argmax_out, int64_t *n_out);
+/* MaxCorrsEinlesen itself (RepeatResolver.c:609-646) on the text file MaxCorrsOf_<MSA>: the values of the lines i with
+ * von <= i / 5 <= bis in file order; a line is what fgets(.., 100, ..) delivers and its value what sscanf("%lf") reads (0.0
+ * where there is no number; the reference leaves that slot uninitialised).  maxcorr_out[capacity] may be NULL to count;
+ * *n_out = values in the window (RR_E_ARG if they exceed the capacity); RR_E_IO if the file cannot be opened (the reference
+ * returns NULL, 619). */
+int rr_maxcorr_read_text(const char *path, int von, int bis, double *maxcorr_out, int64_t capacity, int64_t *n_out);
 
 /* ---- host-side pieces exposed for tests and for RR_FLAG_HOST_FINALIZE ------------------ */
 double rr_lnfact(unsigned int n); /* gsl_sf_lnfact */

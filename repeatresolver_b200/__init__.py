@@ -5,7 +5,7 @@ The package is a thin host-side mirror of the reference interface over the C ABI
 include/rr_maxcorr.h (librr_maxcorr.so: hand-written sm_100a CUDA).  Importing it loads
 the shared library and fails if it has not been built.
 """
-from .maxcorr import (MSA, Packed, RRError, Einlesen, Parallel_AllMaxCorrsRechner, MaxCorrsRausschreiben, MaxCorrsRausschreiben_bin, MaxCorrsEinlesen_bin,
+from .maxcorr import (MSA, Packed, RRError, Einlesen, Parallel_AllMaxCorrsRechner, MaxCorrsRausschreiben, MaxCorrsRausschreiben_bin, MaxCorrsEinlesen_bin, MaxCorrsEinlesen,
                       MaxCorrelation, Cliquer, CliqueGroup, CliqueCoverage, group_reads, Group_Refinement_Cliques, Group_Refinement, Parallel_Group_Refinement, GroupPrecision, dropoff_cutoff_host, Relative_Vars, Kmeans, kmeans_signatures, kmeans_top5_host, kmeans_majority5_host, kmeans_finish,
                       relative_score_host,
                       relative_vars_from_counts, device_count, variant_available, launch_count, lnfact_table, score_host, score_bound_host,
@@ -14,7 +14,7 @@ from .maxcorr import (MSA, Packed, RRError, Einlesen, Parallel_AllMaxCorrsRechne
 from .msagen import MsaGen
 from . import debug
 
-__all__ = ["MSA", "Packed", "RRError", "Einlesen", "Parallel_AllMaxCorrsRechner", "MaxCorrsRausschreiben", "MaxCorrsRausschreiben_bin", "MaxCorrsEinlesen_bin",
+__all__ = ["MSA", "Packed", "RRError", "Einlesen", "Parallel_AllMaxCorrsRechner", "MaxCorrsRausschreiben", "MaxCorrsRausschreiben_bin", "MaxCorrsEinlesen_bin", "MaxCorrsEinlesen",
            "MaxCorrelation", "Cliquer", "CliqueGroup", "CliqueCoverage", "group_reads", "Group_Refinement_Cliques", "Group_Refinement", "Parallel_Group_Refinement", "GroupPrecision", "dropoff_cutoff_host", "Relative_Vars", "Kmeans", "kmeans_signatures", "kmeans_top5_host", "kmeans_majority5_host", "kmeans_finish",
            "relative_score_host",
            "relative_vars_from_counts", "device_count", "variant_available", "launch_count", "lnfact_table", "score_host", "score_bound_host",

@@ -452,6 +452,38 @@ int rr_maxcorr_read_bin(const char *path, int von, int bis, int as_text, double 
     return RR_OK;
 }
 
+/* MaxCorrsEinlesen (RepeatResolver.c:609-646) on the text file: the values of the lines i with von <= i/5 <= bis, in file
+ * order.  A "line" is what fgets(buffer, 100, file) delivers - up to 99 characters, so a longer line counts as several (623) -
+ * and its value what sscanf("%lf") reads at its start: leading white space skipped, the longest valid number, strtod's
+ * correctly rounded result.  Where the reference would leave the slot of a line without a number uninitialised, 0.0 is
+ * stored.  maxcorr_out [capacity] may be NULL to count; *n_out = values in the window, also beyond the capacity (RR_E_ARG
+ * then; the reference writes past its siglength * 5 doubles in that case). */
+int rr_maxcorr_read_text(const char *path, int von, int bis, double *maxcorr_out, int64_t capacity, int64_t *n_out)
+{
+    FILE *f;
+    char buffer[101];
+    int64_t i = 0, j = 0;
+    if (!path || !n_out || capacity < 0 || (capacity && !maxcorr_out)) { rr_set_error("rr_maxcorr_read_text: bad arguments"); return RR_E_ARG; }
+    *n_out = 0;
+    f = fopen(path, "r");
+    if (!f) { rr_set_error("cannot open %s: %s", path, strerror(errno)); return RR_E_IO; }   /* the reference returns NULL (619) */
+    while (fgets(buffer, 100, f) != NULL) {
+        if (i / 5 >= von && i / 5 <= bis) {
+            if (j < capacity) {
+                char *end;
+                const double v = strtod(buffer, &end);
+                maxcorr_out[j] = end == buffer ? 0.0 : v;
+            }
+            j++;
+        }
+        i++;
+    }
+    fclose(f);
+    *n_out = j;
+    if (maxcorr_out && j > capacity) { rr_set_error("rr_maxcorr_read_text: %lld values in the window, room for %lld", (long long)j, (long long)capacity); return RR_E_ARG; }
+    return RR_OK;
+}
+
 /* First-break columns for rows that are single spans.  With contiguous spans the shared
  * coverage |C[ii] & C[jj]| = #{r : start_r <= ii, end_r >= jj} never increases with jj, so
  * the reference's "stop at the first jj with shared coverage < mincov" (807-810) is

@@ -341,6 +341,19 @@ def MaxCorrsEinlesen_bin(inputfile, von, bis, as_text=False):
     return M[:got.value].copy(), A[:got.value].copy()
 
 
+def MaxCorrsEinlesen(inputfile, von, bis):
+    """RepeatResolver.c:609-646: the values of MaxCorrsOf_<MSA> for the columns von..bis (inclusive; five lines per column),
+    None if the file cannot be opened (619).  The reference sizes its array from the MSA window it has read; here the result
+    has as many entries as the window holds lines (rr_maxcorr_read_text)."""
+    n = C.c_int64(0)
+    path = os.fsencode(inputfile)
+    if lib.rr_maxcorr_read_text(path, int(von), int(bis), None, 0, C.byref(n)) != 0:
+        return None
+    out = np.zeros(n.value, dtype=np.float64)
+    _check(lib.rr_maxcorr_read_text(path, int(von), int(bis), out.ctypes.data, len(out), C.byref(n)), "rr_maxcorr_read_text")
+    return out[:n.value]
+
+
 def MaxCorrelation(msa_path, c=30, p=1, variant="auto", flags=FLAG_HOST_FINALIZE, outdir=None):
     """The program: read <msa_path>, scan on p GPUs with coverage floor c, write
     MaxCorrsOf_<msa_path> (MaxCorrelation.c:991-993, 1014).  Returns (path written, stats)."""

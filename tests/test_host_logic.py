@@ -461,3 +461,53 @@ def test_text_writer_is_printf_exact(tmp_path):
     A = np.concatenate([[-1, 0, 9, 10, 2 ** 31 - 1, -2 ** 31], rng.integers(-1, 3_000_000, 70000)]).astype(np.int32)
     assert lib.rr_argmax_write(p.encode(), A.ctypes.data, len(A)) == 0
     assert open(p, "rb").read() == b"".join(b"%d\n" % v for v in A)
+
+
+def _einlesen_file(tmp_path):
+    """a result file with everything MaxCorrsEinlesen's loop can meet: plain "%f" lines, leading blanks, exponents, hex floats,
+    inf / nan, trailing text, a line longer than fgets' 99 characters (counts as several lines) and no newline at the end"""
+    rng = np.random.default_rng(2)
+    lines = [b"%f" % v for v in rng.random(43) * 99] + [b"   7.250000", b"\t1e2", b"0x1.8p3", b"inf", b"-3.5abc", b"98.897959 trailing",
+                                                        b"1" * 120 + b".5", b"0.000001", b"12"]
+    p = tmp_path / "MaxCorrsOf_M"
+    p.write_bytes(b"\n".join(lines))
+    return str(p)
+
+
+def test_maxcorrs_einlesen_window_and_line_rules(tmp_path):
+    """rr_maxcorr_read_text / MaxCorrsEinlesen: fgets(100) lines, sscanf("%lf") values, the window von <= i/5 <= bis"""
+    p = _einlesen_file(tmp_path)
+    all_ = rr.MaxCorrsEinlesen(p, 0, 10 ** 6)
+    # the 122-character line is two fgets lines: 99 ones, then 21 ones and ".5"
+    assert len(all_) == 43 + 6 + 2 + 2
+    assert all_[43] == 7.25 and all_[44] == 100.0 and all_[45] == 12.0 and np.isinf(all_[46]) and all_[47] == -3.5 and all_[48] == 98.897959
+    assert all_[49] == float("1" * 99) and all_[50] == float("1" * 21 + ".5") and all_[51] == 0.000001 and all_[52] == 12.0
+    for von, bis in ((0, 0), (2, 3), (9, 9), (10, 10), (10, 50), (11, 12), (3, 2)):
+        want = all_[[i for i in range(len(all_)) if von <= i // 5 <= bis]]
+        got = rr.MaxCorrsEinlesen(p, von, bis)
+        assert np.array_equal(got, want, equal_nan=True), (von, bis)
+    assert rr.MaxCorrsEinlesen(p + ".missing", 0, 3) is None                  # 619
+    empty = tmp_path / "MaxCorrsOf_E"
+    empty.write_bytes(b"\n\nabc\n")
+    assert list(rr.MaxCorrsEinlesen(str(empty), 0, 0)) == [0.0, 0.0, 0.0]      # no number: 0.0 (the reference: uninitialised)
+    # the text written by the library reads back to the values "%f" carries
+    M = np.random.default_rng(3).random(500) * 99
+    q = str(tmp_path / "MaxCorrsOf_Q")
+    rr.MaxCorrsRausschreiben(M, q)
+    assert np.array_equal(rr.MaxCorrsEinlesen(q, 0, 99), np.array([float("%f" % v) for v in M]))
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_einlesen_driver")),
+                    reason="oracle/_ref is built in the build container only")
+def test_maxcorrs_einlesen_against_the_unmodified_reference(tmp_path):
+    import subprocess
+    p = _einlesen_file(tmp_path)
+    drv = os.path.join(ROOT, "oracle", "_ref", "ref_einlesen_driver")
+    for von, bis in ((0, 10 ** 6), (0, 0), (2, 3), (9, 10), (10, 50)):
+        got = rr.MaxCorrsEinlesen(p, von, bis)
+        out = subprocess.run([drv, p, str(von), str(bis), "40", str(len(got))], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        ref = np.array([float.fromhex(l) if "n" not in l.lower() or "inf" in l.lower() else float(l) for l in out.stdout.split()])
+        assert np.array_equal(got, ref, equal_nan=True), (von, bis)
+    out = subprocess.run([drv, p + ".missing", "0", "3", "40", "1"], capture_output=True, text=True)
+    assert out.stdout.strip() == "NULL"
