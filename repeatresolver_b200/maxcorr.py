@@ -486,6 +486,38 @@ def Kmeans(msa, Unterteilung, u_no, Vars, mingroup, device=0):
     return n.value, u
 
 
+def Unterteilungskomprimierung(Unterteilung):
+    """RepeatResolver.c:1823-1843: the part numbers renamed 0, 1, 2, ... in the order of their first read; negative entries
+    (reads left out) stay.  Returns (number of parts, the renamed partition) - the reference renames in place."""
+    u = np.array(Unterteilung, dtype=np.int32)
+    keep = u > -1
+    vals, first = np.unique(u[keep], return_index=True)
+    order = np.argsort(first, kind="stable")                                 # parts by first appearance
+    rename = np.zeros(int(vals.max()) + 1 if len(vals) else 1, dtype=np.int32)
+    rename[vals[order]] = np.arange(len(vals), dtype=np.int32)
+    u[keep] = rename[u[keep]]
+    return len(vals), u
+
+
+def Kmeans_Subdivision(msa, Unterteilung, MaxCorrs, cutoff, mingroup, device=0, relative_vars=None, kmeans=None):
+    """RepeatResolver.c:3382-3404 (called by main at 4065), the caller of Relative_Vars and Kmeans: the partition is renamed
+    (Unterteilungskomprimierung), every part k that exists at that moment and holds more than 2 * mingroup reads is split by
+    Kmeans on the groups Relative_Vars selects for it - parts are visited in order and the clusters a split creates get
+    numbers above all existing ones, so they are not visited again -, and the result is renamed once more.  Returns (number
+    of parts, the new partition); the reference updates Unterteilung in place.  relative_vars / kmeans default to the
+    device paths (Relative_Vars, Kmeans of this module); the CPU tests pass the oracle's with the same signatures."""
+    relative_vars = relative_vars or (lambda m, u, k, M, c, g: Relative_Vars(m, u, k, M, c, g, device))
+    kmeans = kmeans or (lambda m, u, k, v, g: Kmeans(m, u, k, v, g, device))
+    number, u = Unterteilungskomprimierung(Unterteilung)
+    M = np.ascontiguousarray(MaxCorrs, dtype=np.float64)
+    for k in range(number):
+        if int(np.count_nonzero(u == k)) > mingroup * 2:                     # 3391
+            Vars = relative_vars(msa, u, k, M, cutoff, mingroup)
+            _, u = kmeans(msa, u, k, Vars, mingroup)
+            u = np.asarray(u, dtype=np.int32)
+    return Unterteilungskomprimierung(u)
+
+
 def kmeans_signatures(msa, Unterteilung, u_no, Vars):
     """host piece of rr_kmeans (test hook): (reads of the part, signatures [anzahl][n_vars/64+1] uint64)"""
     u = np.ascontiguousarray(Unterteilung, dtype=np.int32)
