@@ -491,6 +491,12 @@ def bench_rows(args, rr):
     launches = rr.launch_count() - launches0
     clocks = sampler.finish()
     pairs = pairs_rel if args.path == "relvars" else pairs_km
+    if args.path == "relvars":        # per part: the partition up, the selected groups back
+        h2d, d2h = int(4 * R * len(parts)), int(4 * 5 * N * len(parts))
+    else:                             # per part: its rows and group ids up; signatures, centroids, first assignment back (+ the
+        km = [u for u in parts if len(sel[u][0])]                            # dissolution's score table, reads x candidate clusters)
+        h2d = int(sum(sizes[u] * N + 4 * len(sel[u][0]) for u in km))
+        d2h = int(sum(2 * sizes[u] * scv[u] * 8 + 4 * sizes[u] for u in km))
     words = words_rel if args.path == "relvars" else words_km
     peak = 148 * 16 * (clocks["sm_mhz"] or 1965) * 1e6 / 1e12
     achieved = words / (ms * 1e-3) / 1e12
@@ -506,7 +512,7 @@ def bench_rows(args, rr):
                                           "2 x (vars/64+1) per read pair and sweep (kmeans)",
                                    "peak_source": "148 SMs x 16 POPC lanes/clk x median SM clock under load"},
                       "cpu_baseline": cpu, "e2e": {"value": pairs / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
-                                                   "h2d_bytes_per_step": int(4 * R * len(parts)), "d2h_bytes_per_step": int(4 * 5 * N * len(parts))},
+                                                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                       "gpu_launches": launches}))
     return 0
 
