@@ -82,5 +82,47 @@ def main():
         json.dump(cases, f, indent=None, sort_keys=True, separators=(",", ":"))
 
 
+DEEP = dict(gen=dict(type="Tree", copies=80, coverage=40, repeat_len=1500, diff=0.03, seed=5, flank=500, min_overlap=100),
+            frac=(0.3, 0.7), mincov=30, maxclique=30, greedy=3.0, cutoff=7.5, every=50)
+
+
+def deep_inputs():
+    """the deep case: a window of a generated MSA that > 3 000 reads span (several 32-word chunks per bitset on the device),
+    MaxCorrs = 50 for every `every`-th group of a plausible size and for a few others, 0 elsewhere -> (text, von, bis, codes, M)"""
+    import numpy as np
+    import repeatresolver_b200 as rr
+    text = rr.MsaGen(**DEEP["gen"]).text()
+    width = len(text.split(b"\n")[0])
+    von, bis = int(DEEP["frac"][0] * (width - 1)), int(DEEP["frac"][1] * (width - 1))
+    codes = window_codes(text, von, bis)
+    R, N = codes.shape
+    sizes = np.stack([(codes == k).sum(axis=0) for k in range(5)], axis=1).ravel()          # group 5 * site + k
+    M = np.zeros(5 * N)
+    cand = np.flatnonzero((sizes > 30) & (sizes < R // 3))
+    M[cand[::DEEP["every"]]] = 50.0
+    # some groups without partners as well - but not group 0: for a query without partners the reference's trimming loop reads
+    # Clique[-1] (1231), harmless unless the query is 0, which then matches the zero word in front of the array and sends the
+    # loop below the array (a crash in this build)
+    M[[7, 5 * N - 1]] = 50.0
+    M[np.random.default_rng(8).integers(1, 5 * N, 12)] = 50.0
+    return text, von, bis, codes, M
+
+
+def main_deep():
+    import oracle_lib as O
+    text, von, bis, codes, M = deep_inputs()
+    R, N, sc, res, prec = run_driver(text, von, bis, O.fmt_lines(M), DEEP["cutoff"], DEEP["mincov"], DEEP["maxclique"], DEEP["greedy"])
+    assert (R, N) == codes.shape and sc == R // 64 + 1
+    refined = [i for i in sorted(res) if res[i]["size"] > 5]
+    assert len(prec) == 2 * len(refined)
+    for k, i in enumerate(refined):
+        res[i]["precision"] = [list(prec[2 * k]), list(prec[2 * k + 1])]
+    case = {"rows": R, "cols": N, "sc": sc, "von": von, "bis": bis, "groups": {str(i): res[i] for i in sorted(res)}}
+    print("deep", codes.shape, "groups above the cutoff", len(res), "refined", len(refined), "cutoffs", sorted(set(res[i]["cutoff"] for i in refined)))
+    with open(os.path.join(GOLD, "grouprefine_deep.json"), "w") as f:
+        json.dump(case, f, indent=None, sort_keys=True, separators=(",", ":"))
+
+
 if __name__ == "__main__":
     main()
+    main_deep()

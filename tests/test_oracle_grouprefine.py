@@ -74,6 +74,26 @@ def test_group_refinement_matches_the_unmodified_reference(name):
     assert np.array_equal(got_M[untouched], M[untouched])
 
 
+def deep_case():
+    """the deep case of oracle/gen_golden_grouprefine.py (a window > 3 000 generated reads span; MaxCorrs = 50 on chosen groups):
+    (golden record, codes of the window, MaxCorrs, parameters)"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from gen_golden_grouprefine import DEEP, deep_inputs
+    with open(os.path.join(GOLD, "grouprefine_deep.json")) as f:
+        case = json.load(f)
+    text, von, bis, codes, M = deep_inputs()
+    assert (von, bis) == (case["von"], case["bis"]) and codes.shape == (case["rows"], case["cols"])
+    return case, codes, M, DEEP
+
+
+def test_group_refinement_deep_matches_the_unmodified_reference():
+    """51 words of 64 reads per group: the restatement against what the unmodified RepeatResolver.c left for the deep case"""
+    case, codes, M, P = deep_case()
+    o = O.Oracle.from_codes(codes)
+    got_M, got = O.group_refinement(o, codes, M, P["cutoff"], P["mincov"], P["maxclique"], P["greedy"])
+    assert check_against_records(codes, got_M, got, case["groups"], P["maxclique"]) >= 30
+
+
 def test_dropoff_cutoff_rules():
     """the corners of 1488-1509 on hand-made member counts: first minimum wins, zero denominators are skipped, nothing
     admissible leaves cutoff max(1, c) and Drop_Off 1e6"""
