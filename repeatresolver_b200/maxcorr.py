@@ -401,6 +401,19 @@ def Group_Refinement_Cliques(packed, MaxCorrs, cutoff, anfang, ende, mincov, max
     return groups, members, sizes, scores, st
 
 
+def coverage_restriction(MaxCorrs, Coverage):
+    """RepeatResolver.c:4001-4013, the step of its main between reading MaxCorrs and Group_Refinement: the values of every
+    column covered by fewer than 9/10 of the deepest column's reads are set to 0 (Coverage[i/5] * 10 < maxcov * 9, integer
+    arithmetic).  Coverage: reads per column (Packed.sizes()[1]).  Returns a copy."""
+    M = np.array(MaxCorrs, dtype=np.float64)
+    cov = np.asarray(Coverage, dtype=np.int64)
+    if len(M) != 5 * len(cov):
+        raise ValueError("MaxCorrs must hold 5 values per column")
+    maxcov = max(int(cov.max()) if len(cov) else 0, 0)                       # 4002: starts at 0
+    M[np.repeat(cov * 10 < maxcov * 9, 5)] = 0.0
+    return M
+
+
 def Group_Refinement(packed, MaxCorrs, cutoff, anfang, ende, mincov, maxclique, greedy):
     """RepeatResolver.c:1634-1693 with the reference's argument order.  The reference fills its global arrays indexed by
     group; here they come back for the groups above the cutoff only (see Packed.group_refinement), and MaxCorrs - which

@@ -511,3 +511,27 @@ def test_maxcorrs_einlesen_against_the_unmodified_reference(tmp_path):
         assert np.array_equal(got, ref, equal_nan=True), (von, bis)
     out = subprocess.run([drv, p + ".missing", "0", "3", "40", "1"], capture_output=True, text=True)
     assert out.stdout.strip() == "NULL"
+
+
+def test_coverage_restriction():
+    """RepeatResolver.c:4001-4013 restated literally against the vectorised mirror"""
+    rng = np.random.default_rng(9)
+    for trial in range(20):
+        N = int(rng.integers(1, 60))
+        cov = rng.integers(0, 50, N)
+        if trial % 4 == 0:
+            cov[:] = 10 * int(rng.integers(1, 5))                            # exactly at the 9/10 edge for some columns
+            cov[::3] = cov[0] * 9 // 10
+        M = rng.random(5 * N) * 99
+        want = M.copy()
+        maxcov = 0
+        for i in range(N):
+            if cov[i] > maxcov:
+                maxcov = int(cov[i])
+        for i in range(5 * N):
+            if int(cov[i // 5]) * 10 < maxcov * 9:
+                want[i] = 0.0
+        assert np.array_equal(rr.coverage_restriction(M, cov), want)
+    assert len(rr.coverage_restriction([], [])) == 0
+    with pytest.raises(ValueError):
+        rr.coverage_restriction([1.0], [1])
