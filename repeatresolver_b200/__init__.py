@@ -6,7 +6,7 @@ include/rr_maxcorr.h (librr_maxcorr.so: hand-written sm_100a CUDA).  Importing i
 the shared library and fails if it has not been built.
 """
 from .maxcorr import (MSA, Packed, RRError, Einlesen, Parallel_AllMaxCorrsRechner, MaxCorrsRausschreiben, MaxCorrsRausschreiben_bin, MaxCorrsEinlesen_bin, MaxCorrsEinlesen,
-                      MaxCorrelation, Cliquer, CliqueGroup, CliqueCoverage, group_reads, Group_Refinement_Cliques, coverage_restriction, Group_Refinement, Parallel_Group_Refinement, GroupPrecision, dropoff_cutoff_host, Relative_Vars, Kmeans, Kmeans_Subdivision, Unterteilungskomprimierung, kmeans_signatures, kmeans_top5_host, kmeans_majority5_host, kmeans_finish,
+                      MaxCorrelation, Cliquer, CliqueGroup, CliqueCoverage, group_reads, Group_Refinement_Cliques, coverage_restriction, Group_Refinement, Parallel_Group_Refinement, GroupPrecision, dropoff_cutoff_host, Relative_Vars, Kmeans, Kmeans_Subdivision, Unterteilungskomprimierung, UnterteilungsKomplettierung, Unterteilung_Rausschreiben, UnterteilungEinlesen, kmeans_signatures, kmeans_top5_host, kmeans_majority5_host, kmeans_finish,
                       relative_score_host,
                       relative_vars_from_counts, device_count, variant_available, launch_count, lnfact_table, score_host, score_bound_host,
                       below_median_host, breakcols_from_spans, contraction_ranges, length_classes, rank_rows, cliquer_from_counts, cliquer_from_hits, HIT_DTYPE, group_score_host, VARIANTS, VARIANT_NAMES,
@@ -15,7 +15,7 @@ from .msagen import MsaGen
 from . import debug
 
 __all__ = ["MSA", "Packed", "RRError", "Einlesen", "Parallel_AllMaxCorrsRechner", "MaxCorrsRausschreiben", "MaxCorrsRausschreiben_bin", "MaxCorrsEinlesen_bin", "MaxCorrsEinlesen",
-           "MaxCorrelation", "Cliquer", "CliqueGroup", "CliqueCoverage", "group_reads", "Group_Refinement_Cliques", "coverage_restriction", "Group_Refinement", "Parallel_Group_Refinement", "GroupPrecision", "dropoff_cutoff_host", "Relative_Vars", "Kmeans", "Kmeans_Subdivision", "Unterteilungskomprimierung", "kmeans_signatures", "kmeans_top5_host", "kmeans_majority5_host", "kmeans_finish",
+           "MaxCorrelation", "Cliquer", "CliqueGroup", "CliqueCoverage", "group_reads", "Group_Refinement_Cliques", "coverage_restriction", "Group_Refinement", "Parallel_Group_Refinement", "GroupPrecision", "dropoff_cutoff_host", "Relative_Vars", "Kmeans", "Kmeans_Subdivision", "Unterteilungskomprimierung", "UnterteilungsKomplettierung", "Unterteilung_Rausschreiben", "UnterteilungEinlesen", "kmeans_signatures", "kmeans_top5_host", "kmeans_majority5_host", "kmeans_finish",
            "relative_score_host",
            "relative_vars_from_counts", "device_count", "variant_available", "launch_count", "lnfact_table", "score_host", "score_bound_host",
            "below_median_host", "breakcols_from_spans", "contraction_ranges", "length_classes", "rank_rows", "cliquer_from_counts", "cliquer_from_hits", "HIT_DTYPE", "group_score_host", "MsaGen", "debug", "VARIANTS", "VARIANT_NAMES",

@@ -512,6 +512,45 @@ def Unterteilungskomprimierung(Unterteilung):
     return len(vals), u
 
 
+def UnterteilungsKomplettierung(Unterteilung, Ausgelassen):
+    """RepeatResolver.c:1845-1865: the partition of the reads that were read (Ausgelassen[i] == 1) spread back over all reads
+    of the file; the reads left out by the window rule (Ausgelassen[i] == -1) get -1."""
+    a = np.asarray(Ausgelassen)
+    u = np.asarray(Unterteilung, dtype=np.int32)
+    if int(np.count_nonzero(a == 1)) != len(u):
+        raise ValueError("one part number per read with Ausgelassen == 1")
+    out = np.zeros(len(a), dtype=np.int32)                                   # other marks: the reference leaves the slot unset
+    out[a == 1] = u
+    out[a == -1] = -1
+    return out
+
+
+def Unterteilung_Rausschreiben(Unterteilung, outputfile):
+    """RepeatResolver.c:568-585: one part number per line, no newline after the last"""
+    with open(outputfile, "w") as f:
+        f.write("\n".join("%d" % int(x) for x in Unterteilung))
+
+
+def UnterteilungEinlesen(inputfile):
+    """RepeatResolver.c:587-607: one number per line as sscanf("%d") reads it (lines of up to 99 characters; a line without a
+    number keeps 0 here where the reference leaves the slot unset); None if the file cannot be opened"""
+    import re
+    try:
+        with open(inputfile, "rb") as f:
+            data = f.read()
+    except OSError:
+        return None
+    out = []
+    for line in data.split(b"\n") if data else []:
+        pieces = [line[k:k + 99] for k in range(0, len(line), 99)] or [line]  # fgets(buffer, 100, ...)
+        for piece in pieces:
+            m = re.match(rb"\s*([+-]?\d+)", piece)
+            out.append(int(m.group(1)) if m else 0)
+    if data.endswith(b"\n"):
+        out.pop()                                                            # no line after the last newline
+    return np.array(out, dtype=np.int32)
+
+
 def Kmeans_Subdivision(msa, Unterteilung, MaxCorrs, cutoff, mingroup, device=0, relative_vars=None, kmeans=None):
     """RepeatResolver.c:3382-3404 (called by main at 4065), the caller of Relative_Vars and Kmeans: the partition is renamed
     (Unterteilungskomprimierung), every part k that exists at that moment and holds more than 2 * mingroup reads is split by

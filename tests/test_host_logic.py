@@ -535,3 +535,19 @@ def test_coverage_restriction():
     assert len(rr.coverage_restriction([], [])) == 0
     with pytest.raises(ValueError):
         rr.coverage_restriction([1.0], [1])
+
+
+def test_partition_file_and_completion(tmp_path):
+    """Unterteilung_Rausschreiben / UnterteilungEinlesen / UnterteilungsKomplettierung (RepeatResolver.c:568-607, 1845-1865)"""
+    u = np.array([3, 0, -1, 12, 7], dtype=np.int32)
+    p = str(tmp_path / "KmeansSubdivisionOf_x")
+    rr.Unterteilung_Rausschreiben(u, p)
+    assert open(p, "rb").read() == b"3\n0\n-1\n12\n7"                        # no newline after the last (579-582)
+    assert np.array_equal(rr.UnterteilungEinlesen(p), u)
+    open(p, "wb").write(b" 4\n+5 x\n\nabc\n-6\n")
+    assert list(rr.UnterteilungEinlesen(p)) == [4, 5, 0, 0, -6]
+    assert rr.UnterteilungEinlesen(p + ".missing") is None
+    aus = np.array([1, -1, 1, 1, -1, 1, 1])
+    assert list(rr.UnterteilungsKomplettierung(u, aus)) == [3, -1, 0, -1, -1, 12, 7]
+    with pytest.raises(ValueError):
+        rr.UnterteilungsKomplettierung(u[:3], aus)
