@@ -101,6 +101,13 @@ typedef struct rr_scan_stats {
  * rr_msa_free (or the first rr_msa_cells call, which materialises the matrix and drops the mapping).
  * rr_msa_from_text does the same for text in caller-owned memory and copies the kept rows out. */
 int rr_msa_read(const char *path, rr_msa **out);
+/* The reader of RepeatResolver.c (Einlesen 293-429), in front of Group_Refinement, Relative_Vars and Kmeans: the columns
+ * von .. bis of the reads that carry a symbol (anything but ' ') at both ends of the window (330).  bis is lowered to the
+ * last column of any shorter line, from that line on (328), and the lowered value ends the window that is kept (398).
+ * ausgelassen[capacity] (may be NULL with capacity 0) receives 1 per line that was kept and -1 per line left out (332, 367);
+ * *n_lines = lines of the file, also when they exceed the capacity (RR_E_ARG then).  RR_E_IO for a missing file ("MA is
+ * missing.", 318), a last line without newline (326: the reference exits) or a line too short to hold column von. */
+int rr_msa_read_window(const char *path, int von, int bis, rr_msa **out, int8_t *ausgelassen, int64_t capacity, int64_t *n_lines);
 int rr_msa_from_text(const char *text, size_t nbytes, rr_msa **out);
 /* cells[rows][cols]; codes != 0: values 0..5 as in Signatures (304-329); else raw characters */
 int rr_msa_from_cells(const uint8_t *cells, int rows, int cols, int codes, rr_msa **out);

@@ -63,7 +63,7 @@ def _sig(fn, res, args):
 
 # every symbol include/rr_maxcorr.h declares
 ABI_SYMBOLS = [
-    "rr_msa_read", "rr_msa_from_text", "rr_msa_from_cells", "rr_msa_alloc", "rr_msa_rows", "rr_msa_cols",
+    "rr_msa_read", "rr_msa_read_window", "rr_msa_from_text", "rr_msa_from_cells", "rr_msa_alloc", "rr_msa_rows", "rr_msa_cols",
     "rr_msa_cells", "rr_msa_free", "rr_device_count", "rr_variant_available", "rr_pack", "rr_pack_rows", "rr_pack_slice_spans", "rr_pack_set_spans", "rr_pack_bits_device", "rr_pack_finish", "rr_packed_free", "rr_scan", "rr_scan_fetch", "rr_scan_finalize", "rr_scan_set_thresholds", "rr_scan_values_device", "rr_scan_set_thresholds_device",
     "rr_pair_counts", "rr_packed_sizes", "rr_maxcorr_run", "rr_maxcorr_write", "rr_argmax_write", "rr_maxcorr_write_bin", "rr_maxcorr_read_bin", "rr_maxcorr_read_text", "rr_lnfact",
     "rr_lnfact_table", "rr_score_host", "rr_score_bound_host", "rr_below_median_host", "rr_breakcols_from_spans", "rr_contraction_ranges", "rr_length_classes", "rr_cliquer", "rr_cliquer_batch", "rr_clique_groups", "rr_group_refinement", "rr_dropoff_cutoff_host", "rr_cliquer_from_counts", "rr_cliquer_from_hits", "rr_relative_vars", "rr_relative_vars_packed", "rr_relative_vars_from_counts", "rr_relative_score_host", "rr_kmeans", "rr_kmeans_signatures", "rr_kmeans_finish", "rr_kmeans_top5_host", "rr_kmeans_majority5_host", "rr_group_score_host",
@@ -73,6 +73,7 @@ MSAGEN_SYMBOLS = ["rr_msagen_create", "rr_msagen_free", "rr_msagen_rows", "rr_ms
                   "rr_msagen_fill_codes", "rr_msagen_fill_text", "rr_msagen_write"]
 
 _sig(lib.rr_msa_read, _i, [C.c_char_p, _P(_vp)])
+_sig(lib.rr_msa_read_window, _i, [C.c_char_p, _i, _i, _P(_vp), _vp, _i64, _P(_i64)])
 _sig(lib.rr_msa_from_text, _i, [C.c_char_p, C.c_size_t, _P(_vp)])
 _sig(lib.rr_msa_from_cells, _i, [_vp, _i, _i, _i, _P(_vp)])
 _sig(lib.rr_msa_alloc, _i, [_i, _i, _i, _P(_vp)])

@@ -277,6 +277,66 @@ int rr_msa_read(const char *path, rr_msa **out)
     return RR_OK;
 }
 
+/* Einlesen of RepeatResolver.c (293-429), the reader in front of the rows 8f-2 .. 8f-4: the columns von .. bis of the reads
+ * that carry a symbol - anything but ' ' - at BOTH ends of the window (330); bis is lowered to the last column of a shorter
+ * line when one is met and stays lowered for the lines that follow (328), and the window that is finally kept is
+ * von .. the lowered bis (398).  ausgelassen[line] = 1 for a read that was kept, -1 for one left out (332, 367), as
+ * UnterteilungsKomplettierung needs it.  A last line without '\n' is an error (326: the reference exits), and so is a line too
+ * short to hold column von, or von > bis (the reference reads stale buffer contents there).  The cells are kept as raw
+ * characters (classified on the device like every other MSA). */
+int rr_msa_read_window(const char *path, int von, int bis, rr_msa **out, int8_t *ausgelassen, int64_t capacity, int64_t *n_lines)
+{
+    FILE *f;
+    char *text = NULL;
+    size_t len = 0, cap = 0, pos, nl = 0, kept = 0, k;
+    unsigned char *keep = NULL;
+    size_t *lstart = NULL;
+    long fsize;
+    int rc = RR_OK, cols;
+    rr_msa *m = NULL;
+    if (!path || !out || !n_lines || von < 0 || bis < von || capacity < 0 || (capacity && !ausgelassen)) {
+        rr_set_error("rr_msa_read_window: bad arguments");
+        return RR_E_ARG;
+    }
+    *out = NULL; *n_lines = 0;
+    f = fopen(path, "rb");
+    if (!f) { rr_set_error("MA is missing. (%s: %s)", path, strerror(errno)); return RR_E_IO; }
+    if (fseek(f, 0, SEEK_END) != 0 || (fsize = ftell(f)) < 0 || fseek(f, 0, SEEK_SET) != 0) { fclose(f); rr_set_error("cannot size %s", path); return RR_E_IO; }
+    cap = (size_t)fsize;
+    text = (char *)malloc(cap ? cap : 1);
+    if (!text) { fclose(f); rr_set_error("out of host memory (%zu bytes)", cap); return RR_E_NOMEM; }
+    len = fread(text, 1, cap, f);
+    fclose(f);
+    for (pos = 0; pos < len; pos++) nl += text[pos] == '\n';
+    if (len && text[len - 1] != '\n') { free(text); rr_set_error("%s: the last line has no newline", path); return RR_E_IO; }
+    keep = (unsigned char *)calloc(nl ? nl : 1, 1);
+    lstart = (size_t *)malloc(sizeof(size_t) * (nl ? nl : 1));
+    if (!keep || !lstart) { rc = RR_E_NOMEM; rr_set_error("out of host memory"); goto done; }
+    for (pos = 0, k = 0; pos < len; k++) {                               /* one pass in reading order: bis only ever goes down */
+        const char *line = text + pos;
+        const char *e = (const char *)memchr(line, '\n', len - pos);
+        const size_t l = (size_t)(e - line);                             /* without the newline (327) */
+        if ((long)l - 1 < (long)bis) bis = (int)l - 1;                   /* 328 */
+        if (bis < von) { rc = RR_E_IO; rr_set_error("%s: line %zu is too short for column %d", path, k + 1, von); goto done; }
+        lstart[k] = pos;
+        keep[k] = line[von] != ' ' && line[bis] != ' ';                  /* 330 */
+        kept += keep[k];
+        pos += l + 1;
+    }
+    cols = nl ? bis + 1 - von : 0;                                       /* 398 */
+    if (kept > 0x7fffffffu) { rc = RR_E_ARG; rr_set_error("too many reads"); goto done; }
+    if ((rc = rr_msa_alloc((int)kept, cols, 0, &m))) goto done;
+    for (k = 0, pos = 0; k < nl; k++)
+        if (keep[k]) { memcpy(m->cells + pos * (size_t)cols, text + lstart[k] + von, (size_t)cols); pos++; }
+    for (k = 0; k < nl && (int64_t)k < capacity; k++) ausgelassen[k] = keep[k] ? 1 : -1;
+    *n_lines = (int64_t)nl;
+    *out = m;
+    if (ausgelassen && (int64_t)nl > capacity) { rc = RR_E_ARG; rr_set_error("rr_msa_read_window: %zu lines, room for %lld marks", nl, (long long)capacity); rr_msa_free(m); *out = NULL; }
+done:
+    free(text); free(keep); free(lstart);
+    return rc;
+}
+
 /* MaxCorrsRausschreiben (516-532): one "%f\n" per group */
 /* "%f\n" of one double, exactly as printf rounds it (the exact binary value to six decimals, ties to even), without printf:
  * v = m * 2^e with a 53-bit m, so m * 10^6 fits 73 bits and one shift with an exact remainder test gives the digits.

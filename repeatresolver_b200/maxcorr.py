@@ -54,6 +54,21 @@ class MSA:
         return cls(h.value)
 
     @classmethod
+    def read_window(cls, path, von, bis):
+        """RepeatResolver.c's reader (Einlesen 293-429, rr_msa_read_window): (the MSA of the columns von .. bis of the reads with
+        a symbol at both ends of the window, Ausgelassen: int8 per line of the file, 1 = kept, -1 = left out)"""
+        h = C.c_void_p()
+        n = C.c_int64(0)
+        p = os.fsencode(path)
+        rc = lib.rr_msa_read_window(p, int(von), int(bis), C.byref(h), None, 0, C.byref(n))
+        _check(rc, "rr_msa_read_window")
+        lib.rr_msa_free(h)                                                   # the first call counted the lines
+        aus = np.zeros(n.value, dtype=np.int8)
+        h = C.c_void_p()
+        _check(lib.rr_msa_read_window(p, int(von), int(bis), C.byref(h), aus.ctypes.data, len(aus), C.byref(n)), "rr_msa_read_window")
+        return cls(h.value), aus
+
+    @classmethod
     def from_text(cls, text):
         if isinstance(text, str):
             text = text.encode("latin1")
@@ -298,9 +313,12 @@ class Packed:
             pass
 
 
-def Einlesen(path):
-    """MaxCorrelation.c:270-335."""
-    return MSA.read(path)
+def Einlesen(path, von=None, bis=None):
+    """MaxCorrelation.c:270-393 (the whole file) or, with a window, RepeatResolver.c:293-429 (the columns von .. bis of the reads
+    with a symbol at both ends of the window): the MSA, in the second form together with Ausgelassen (1 / -1 per line)"""
+    if von is None and bis is None:
+        return MSA.read(path)
+    return MSA.read_window(path, 0 if von is None else von, 2 ** 31 - 2 if bis is None else bis)
 
 
 def Parallel_AllMaxCorrsRechner(msa, mincov=30, n_gpus=1, variant="auto", flags=FLAG_HOST_FINALIZE):
